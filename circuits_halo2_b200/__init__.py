@@ -1,0 +1,18 @@
+"""circuits_halo2_b200 -- B200-native core of Summa's halo2 (KZG / BN254) prover.
+
+Host-side mirror of the reference's call surface for the hot path, over the C ABI of
+libsumma_b200.so (hand-written sm_100a kernels):
+
+    arithmetic.best_multiexp / best_fft          halo2_proofs::arithmetic
+    domain.EvaluationDomain                      halo2_proofs::poly::EvaluationDomain
+    params.ParamsKZG                             halo2_proofs::poly::kzg::commitment::ParamsKZG
+
+Arrays are numpy views of halo2curves' memory layout (Montgomery, little-endian u64 limbs):
+Fr vectors have shape (n, 4) uint64, G1Affine vectors (n, 8) uint64.
+"""
+from .context import Context, default_context  # noqa: F401
+from .arithmetic import best_fft, best_multiexp  # noqa: F401
+from .domain import EvaluationDomain  # noqa: F401
+from .params import ParamsKZG  # noqa: F401
+
+__all__ = ["Context", "default_context", "best_fft", "best_multiexp", "EvaluationDomain", "ParamsKZG"]

@@ -1,0 +1,105 @@
+// Shared host-side plumbing of libsumma_b200: status codes, the context object, scratch arena.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/summa_b200.h"
+#include "fp.cuh"
+
+namespace sb {
+
+void set_last_error(const char *fmt, ...);
+
+#define SB_CUDA_TRY(expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            ::sb::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return SB_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define SB_TRY(expr)                                                                                 \
+    do {                                                                                             \
+        int32_t s__ = (expr);                                                                        \
+        if (s__ != SB_OK) return s__;                                                                \
+    } while (0)
+
+#define SB_REQUIRE(cond, msg)                                                                        \
+    do {                                                                                             \
+        if (!(cond)) {                                                                               \
+            ::sb::set_last_error("%s:%d: %s", __FILE__, __LINE__, msg);                              \
+            return SB_ERR_ARG;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+// Grow-only device scratch buffers, one per named slot.  cudaMalloc/cudaFree are off the hot path:
+// a slot is re-allocated only when a larger request arrives.
+struct Scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct NttPlan;  // ntt.cu
+
+}  // namespace sb
+
+struct sb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    uint64_t launches = 0;
+    std::map<std::string, sb::Scratch> scratch;
+    std::map<std::string, sb::NttPlan *> ntt_plans;  // key: log_n || omega bytes
+    void *pinned = nullptr;                          // small pinned staging buffer (results)
+    size_t pinned_bytes = 0;
+    // per-phase device times of the last MSM (CUDA events on the launching stream):
+    // [0] recode+sort  [1] reduce level 1 (the dominant kernel)  [2] reduce levels >= 2
+    // [3] bucket reduction  [4] whole device part
+    cudaEvent_t msm_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float msm_phase_ms[5] = {0, 0, 0, 0, 0};
+    uint32_t msm_last_shape[4] = {0, 0, 0, 0};  // c, W, L1, seg_log of the last MSM
+};
+
+namespace sb {
+
+int32_t scratch_get(sb_ctx *ctx, const char *slot, size_t bytes, void **out);
+
+inline cudaStream_t pick_stream(sb_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+// launch accounting (gpu_launches in bench.py)
+#define SB_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                                       \
+    do {                                                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                  \
+        (ctx)->launches++;                                                                           \
+        SB_CUDA_TRY(cudaGetLastError());                                                             \
+    } while (0)
+
+// ---- entry points of the individual translation units (all take device pointers) ----
+int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n, cudaStream_t st);
+void ntt_plans_free(sb_ctx *ctx);
+
+int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st);
+
+int32_t g1_fixed_base_mul(sb_ctx *ctx, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+
+int32_t fr_scale(sb_ctx *ctx, void *d_a, size_t n, const fr_t &s, cudaStream_t st);
+// a[i] *= pat[i % m]  (m <= 8 constants passed by value)
+int32_t fr_scale_pattern(sb_ctx *ctx, void *d_a, size_t n, const fr_t *pat, uint32_t m, cudaStream_t st);
+// dst[i] = i < n_src ? src[i] * pat[i % m] : 0   for i < n_dst
+int32_t fr_scale_pattern_pad(sb_ctx *ctx, const void *d_src, size_t n_src, void *d_dst, size_t n_dst, const fr_t *pat, uint32_t m, cudaStream_t st);
+int32_t fp_vec_op(sb_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n, cudaStream_t st);
+
+// host-side field helpers (exact, slow; plan constants only)
+fr_t fr_pow_host(const fr_t &base, uint64_t e);
+fr_t fr_from_u64_host(uint64_t x);  // to Montgomery
+
+}  // namespace sb

@@ -1,0 +1,311 @@
+// 256-bit Montgomery field arithmetic for BN254 Fr / Fq on 8 x 32-bit limbs (sm_100a).
+//
+// Replaces halo2curves 0.1.0 `bn256::{Fr,Fq}` (reference use: zk_prover/src/circuits/utils.rs:10-13,
+// every `Fr as Fp` import).  Same memory layout: 32 B little-endian, Montgomery form, R = 2^256, so a
+// Rust `&[Fr]` can be handed over untouched.
+//
+// Multiplication is an operand-scanning CIOS whose partial products are kept in two interleaved
+// accumulators ("even"/"odd" limb alignment) so that every 32x32->64 product is one
+// mad.lo.cc/madc.hi.cc pair = one IMAD.WIDE with carry-in/out on the FMA pipe and no carry ripple
+// between products.  The carry primitives below have a bit-exact host emulation so the very same
+// source is unit-tested on the CPU (tests/test_host_field.py) before it ever reaches a GPU.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SB_HD __host__ __device__ __forceinline__
+#else
+#define SB_HD inline
+#endif
+
+namespace sb {
+
+// ------------------------------------------------------------------ carry-chain primitives
+namespace ptx {
+#ifdef __CUDA_ARCH__
+#define SB_ASM2(name, ins)                                                                                  \
+    __device__ __forceinline__ uint32_t name(uint32_t a, uint32_t b) {                                      \
+        uint32_t r;                                                                                         \
+        asm volatile(ins " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                                        \
+        return r;                                                                                           \
+    }
+#define SB_ASM3(name, ins)                                                                                  \
+    __device__ __forceinline__ uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                          \
+        uint32_t r;                                                                                         \
+        asm volatile(ins " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));                            \
+        return r;                                                                                           \
+    }
+SB_ASM2(add_cc, "add.cc.u32")
+SB_ASM2(addc_cc, "addc.cc.u32")
+SB_ASM2(addc, "addc.u32")
+SB_ASM2(sub_cc, "sub.cc.u32")
+SB_ASM2(subc_cc, "subc.cc.u32")
+SB_ASM2(subc, "subc.u32")
+SB_ASM3(mad_lo_cc, "mad.lo.cc.u32")
+SB_ASM3(madc_lo_cc, "madc.lo.cc.u32")
+SB_ASM3(mad_hi_cc, "mad.hi.cc.u32")
+SB_ASM3(madc_hi_cc, "madc.hi.cc.u32")
+SB_ASM3(madc_hi, "madc.hi.u32")
+SB_ASM3(madc_lo, "madc.lo.u32")
+#undef SB_ASM2
+#undef SB_ASM3
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+// Host emulation of the PTX condition-code register (one carry/borrow bit).
+static thread_local uint32_t CF = 0;
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + CF; CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + CF; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b; CF = (uint32_t)(d >> 32) & 1; return (uint32_t)d; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b - CF; CF = (uint32_t)(d >> 32) & 1; return (uint32_t)d; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - CF; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_lo(a, b) + c; CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_lo(a, b) + c + CF; CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_hi(a, b) + c; CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_hi(a, b) + c + CF; CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + CF; }
+inline uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return mul_lo(a, b) + c + CF; }
+#endif
+}  // namespace ptx
+
+// ------------------------------------------------------------------ field parameters
+// Limb tables are constexpr *functions* so that, after unrolling, every modulus limb is an
+// immediate operand of its IMAD (no constant-bank or register traffic).
+struct FrParams {  // scalar field r (InclusionVerifier.sol:210)
+    static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+    SB_HD static constexpr uint32_t mod(int i) {
+        return i == 0 ? 0xf0000001u : i == 1 ? 0x43e1f593u : i == 2 ? 0x79b97091u : i == 3 ? 0x2833e848u
+             : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    SB_HD static constexpr uint32_t one(int i) {  // R mod r
+        return i == 0 ? 0x4ffffffbu : i == 1 ? 0xac96341cu : i == 2 ? 0x9f60cd29u : i == 3 ? 0x36fc7695u
+             : i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    SB_HD static constexpr uint32_t r2(int i) {  // R^2 mod r
+        return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u
+             : i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+    }
+};
+struct FqParams {  // base field q (InclusionVerifier.sol:209)
+    static constexpr uint32_t INV = 0xe4866389u;
+    SB_HD static constexpr uint32_t mod(int i) {
+        return i == 0 ? 0xd87cfd47u : i == 1 ? 0x3c208c16u : i == 2 ? 0x6871ca8du : i == 3 ? 0x97816a91u
+             : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    SB_HD static constexpr uint32_t one(int i) {
+        return i == 0 ? 0xc58f0d9du : i == 1 ? 0xd35d438du : i == 2 ? 0xf5c70b3du : i == 3 ? 0x0a78eb28u
+             : i == 4 ? 0x7879462cu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    SB_HD static constexpr uint32_t r2(int i) {
+        return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u
+             : i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+    }
+};
+
+// ------------------------------------------------------------------ field element
+template <class P>
+struct Fp {
+    uint32_t v[8];
+
+    SB_HD static Fp zero() { Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r; }
+    SB_HD static Fp one() { Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+        return r; }
+    SB_HD static Fp r2() { Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+        return r; }
+    SB_HD bool is_zero() const { return (v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0; }
+    SB_HD bool operator==(const Fp &o) const {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= v[i] ^ o.v[i];
+        return d == 0;
+    }
+    SB_HD bool operator!=(const Fp &o) const { return !(*this == o); }
+};
+
+// r = (t >= p) ? t - p : t      (t < 2p)
+template <class P>
+SB_HD void final_sub(uint32_t r[8], const uint32_t t[8]) {
+    uint32_t s[8];
+    s[0] = ptx::sub_cc(t[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) s[i] = ptx::subc_cc(t[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);  // 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? t[i] : s[i];
+}
+
+template <class P>
+SB_HD Fp<P> add(const Fp<P> &a, const Fp<P> &b) {
+    uint32_t t[8];
+    t[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) t[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    t[7] = ptx::addc(a.v[7], b.v[7]);  // p < 2^254: no carry out of limb 7
+    Fp<P> r;
+    final_sub<P>(r.v, t);
+    return r;
+}
+
+template <class P>
+SB_HD Fp<P> sub(const Fp<P> &a, const Fp<P> &b) {
+    uint32_t t[8];
+    t[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = ptx::subc(0, 0);  // all-ones iff a < b
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(t[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(t[i], P::mod(i) & borrow);
+    r.v[7] = ptx::addc(t[7], P::mod(7) & borrow);
+    return r;
+}
+
+template <class P>
+SB_HD Fp<P> neg(const Fp<P> &a) { return sub(Fp<P>::zero(), a); }
+template <class P>
+SB_HD Fp<P> dbl(const Fp<P> &a) { return add(a, a); }
+
+// One CIOS round on the interleaved accumulators (see header comment).
+//   E: limbs aligned to their index (new "even" accumulator = previous "odd")
+//   O: previous "even" accumulator, E-aligned and with O[0] == 0; it is shifted down two limbs in
+//      place and becomes the new "odd" accumulator (limb j sits at position j + 1).
+template <class P, bool FIRST>
+SB_HD void cios_round(uint32_t E[8], uint32_t O[8], const uint32_t a[8], uint32_t bi) {
+    using namespace ptx;
+    if (FIRST) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            E[j] = mul_lo(a[j], bi);
+            E[j + 1] = mul_hi(a[j], bi);
+            O[j] = mul_lo(a[j + 1], bi);
+            O[j + 1] = mul_hi(a[j + 1], bi);
+        }
+    } else {
+        E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            O[j] = madc_lo_cc(a[j + 1], bi, O[j + 2]);
+            O[j + 1] = madc_hi_cc(a[j + 1], bi, O[j + 3]);
+        }
+        O[6] = madc_lo_cc(a[7], bi, 0);
+        O[7] = madc_hi(a[7], bi, 0);
+        E[0] = mad_lo_cc(a[0], bi, E[0]);
+        E[1] = madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            E[j] = madc_lo_cc(a[j], bi, E[j]);
+            E[j + 1] = madc_hi_cc(a[j], bi, E[j + 1]);
+        }
+        O[7] = addc(O[7], 0);
+    }
+    uint32_t m = mul_lo(E[0], P::INV);
+    O[0] = mad_lo_cc(P::mod(1), m, O[0]);
+    O[1] = madc_hi_cc(P::mod(1), m, O[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        O[j] = madc_lo_cc(P::mod(j + 1), m, O[j]);
+        O[j + 1] = madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
+    }
+    E[0] = mad_lo_cc(P::mod(0), m, E[0]);
+    E[1] = madc_hi_cc(P::mod(0), m, E[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        E[j] = madc_lo_cc(P::mod(j), m, E[j]);
+        E[j + 1] = madc_hi_cc(P::mod(j), m, E[j + 1]);
+    }
+    O[7] = addc(O[7], 0);
+}
+
+// Montgomery product a * b * 2^-256 mod p, fully reduced.
+template <class P>
+SB_HD Fp<P> mul(const Fp<P> &a, const Fp<P> &b) {
+    using namespace ptx;
+    uint32_t X[8], Y[8];
+    cios_round<P, true>(X, Y, a.v, b.v[0]);
+    cios_round<P, false>(Y, X, a.v, b.v[1]);
+    cios_round<P, false>(X, Y, a.v, b.v[2]);
+    cios_round<P, false>(Y, X, a.v, b.v[3]);
+    cios_round<P, false>(X, Y, a.v, b.v[4]);
+    cios_round<P, false>(Y, X, a.v, b.v[5]);
+    cios_round<P, false>(X, Y, a.v, b.v[6]);
+    cios_round<P, false>(Y, X, a.v, b.v[7]);
+    // last round: "even" = Y (Y[0] == 0 after reduction), "odd" = X.  T / 2^32:
+    uint32_t t[8];
+    t[0] = add_cc(Y[1], X[0]);
+#pragma unroll
+    for (int j = 1; j < 7; j++) t[j] = addc_cc(Y[j + 1], X[j]);
+    t[7] = addc(X[7], 0);
+    Fp<P> r;
+    final_sub<P>(r.v, t);
+    return r;
+}
+
+template <class P>
+SB_HD Fp<P> sqr(const Fp<P> &a) { return mul(a, a); }
+
+template <class P>
+SB_HD Fp<P> to_mont(const Fp<P> &a) { return mul(a, Fp<P>::r2()); }
+template <class P>
+SB_HD Fp<P> from_mont(const Fp<P> &a) {
+    Fp<P> o = Fp<P>::zero();
+    o.v[0] = 1;
+    return mul(a, o);
+}
+
+// a^(p-2) (Fermat).  Used only off the hot path (normalisation, constants).
+template <class P>
+SB_HD Fp<P> inv(const Fp<P> &a) {
+    Fp<P> acc = Fp<P>::one();
+    for (int i = 255; i >= 0; i--) {
+        acc = sqr(acc);
+        // exponent p - 2: only limb 0 differs from p (p is odd and p[0] >= 2)
+        uint32_t w = P::mod(i >> 5);
+        if ((i >> 5) == 0) w -= 2;
+        if ((w >> (i & 31)) & 1) acc = mul(acc, a);
+    }
+    return acc;
+}
+
+typedef Fp<FrParams> fr_t;
+typedef Fp<FqParams> fq_t;
+
+// ------------------------------------------------------------------ 128-bit vector global access
+#ifdef __CUDACC__
+template <class P>
+__device__ __forceinline__ Fp<P> load_fp(const void *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    Fp<P> r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+template <class P>
+__device__ __forceinline__ Fp<P> ldg_fp(const void *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    Fp<P> r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+template <class P>
+__device__ __forceinline__ void store_fp(void *p, const Fp<P> &a) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+#endif
+
+}  // namespace sb

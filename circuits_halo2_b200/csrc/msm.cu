@@ -1,0 +1,471 @@
+// Pippenger MSM over BN254 G1 for sm_100a.
+//
+// Replaces halo2_proofs::arithmetic::best_multiexp (reached from
+// zk_prover/src/circuits/utils.rs:75-76 (keygen, 17 calls) and :94-102,171-178 (create_proof,
+// 16 calls) through ParamsKZG::{commit, commit_lagrange}).  The result is a unique group element,
+// so the GPU algorithm is free; it is chosen for B200:
+//
+//   1. recode   every scalar -> W = ceil(255/c) signed c-bit digits; key = window * 2^(c-1) + |d| - 1
+//   2. sort     counting sort of the (key, point index | sign) pairs: histogram with warp-aggregated
+//               atomics, exclusive scan, scatter with warp-aggregated cursor claims (order inside a
+//               bucket is irrelevant, so no stable multi-pass radix sort is needed)
+//   3. reduce-by-key, perfectly load-balanced regardless of the scalar distribution:
+//               every thread owns a fixed-size chunk of the sorted list (not a bucket), walks it with
+//               one XYZZ accumulator (mixed addition, 8M+2S), stores runs that lie strictly inside
+//               its chunk straight into their bucket and hands the first / last run of the chunk to
+//               the next level as a (key, partial sum) pair.  Levels shrink 8x; a last single-CTA
+//               segmented scan finishes.  A bucket holding 90 % of all points (constant columns,
+//               selector columns, Z polynomials) costs exactly the same as a uniform one.
+//   4. bucket reduction  sum_b b * B_b per window, in segments of S buckets (running sums + one small
+//               double-and-add), then a CTA tree per window
+//   5. the <= 64 window sums go to the host, which folds them (254 dependent doublings) and
+//               normalises (host_g1.cpp).
+// Control logic is pinned on the CPU by tests/models/msm_model.py.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace sb {
+
+void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_affine[64]);
+
+static const uint32_t INVALID_KEY = 0xffffffffu;
+static const int LK = 16;          // chunk length of reduce levels >= 2
+static const int FINAL_MAX = 256;  // slots handled by the final single-CTA level
+
+struct MsmShape {
+    uint32_t c, W, B;   // window bits, windows, buckets per window
+    uint32_t L1;        // chunk length of level 1
+    uint32_t seg_log;   // bucket-reduction segment = 2^seg_log buckets
+    uint64_t n, t_max;  // points, sorted-list capacity (W * n rounded up to 4)
+};
+
+// ------------------------------------------------------------------ 1+2: recode, histogram, scatter
+// digit w of canonical scalar s (8 x u32), with the running carry of the signed recoding
+__device__ __forceinline__ uint32_t raw_window(const uint32_t s[8], uint32_t bit, uint32_t c) {
+    const uint32_t limb = bit >> 5, off = bit & 31;
+    uint64_t two = s[limb];
+    if (limb + 1 < 8) two |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(two >> off) & ((1u << c) - 1);
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uint64_t n, MsmShape sh, uint32_t *counts /*histogram or cursor*/,
+                                                       uint32_t *skeys, uint32_t *svals) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count so that every lane reaches the match_any below
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint64_t i = base + lane;
+        const bool live = i < n;
+        uint32_t s[8];
+        if (live) {
+            fr_t x = from_mont(load_fp<FrParams>(scalars + 2 * i));
+#pragma unroll
+            for (int q = 0; q < 8; q++) s[q] = x.v[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) s[q] = 0;
+        }
+        uint32_t carry = 0;
+        const uint32_t half = 1u << (sh.c - 1);
+        for (uint32_t w = 0; w < sh.W; w++) {
+            const uint32_t bit = w * sh.c;
+            uint32_t d = (bit < 256 ? raw_window(s, bit, sh.c) : 0) + carry;
+            uint32_t neg = 0;
+            if (d > half) {
+                d = (1u << sh.c) - d;
+                neg = 1;
+                carry = 1;
+            } else {
+                carry = 0;
+            }
+            const uint32_t key = (live && d) ? w * sh.B + d - 1 : INVALID_KEY;
+            // warp aggregation: one atomic per distinct key per warp (hot buckets stay cheap)
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            const uint32_t leader = __ffs(peers) - 1;
+            uint32_t pos = 0;
+            if (lane == leader && key != INVALID_KEY) pos = atomicAdd(counts + key, __popc(peers));
+            if (SCATTER) {
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (key != INVALID_KEY) {
+                    pos += __popc(peers & ((1u << lane) - 1));
+                    skeys[pos] = key;
+                    svals[pos] = (uint32_t)i | (neg << 31);
+                }
+            }
+        }
+    }
+}
+
+// exclusive scan of m counts (three small kernels; m <= 2^25)
+static const int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+        uint32_t wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += t;
+        }
+        warp_sums[lane] = wi - ws;  // exclusive prefix of warp sums
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    uint32_t r = incl - v + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint32_t *in, uint64_t m, uint32_t *tile_sums) {
+    __shared__ uint32_t total;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++)
+        if (base + q < m) s += in[base + q];
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_of_tile_sums_kernel(uint32_t *tile_sums, uint64_t ntiles, uint32_t *grand_total) {
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (uint64_t base = 0; base < ntiles; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = ex + carry;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *in, uint64_t m, const uint32_t *tile_sums, uint32_t *out_a, uint32_t *out_b) {
+    __shared__ uint32_t total;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) {
+        v[q] = base + q < m ? in[base + q] : 0;
+        s += v[q];
+    }
+    uint32_t ex = block_exclusive_scan(s, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) {
+        if (base + q < m) {
+            out_a[base + q] = ex;
+            out_b[base + q] = ex;
+        }
+        ex += v[q];
+    }
+}
+
+// ------------------------------------------------------------------ 3: chunked reduce-by-key
+__device__ __forceinline__ xyzz_t load_xyzz(const uint4 *p) {
+    xyzz_t r;
+    r.x = load_fp<FqParams>(p);
+    r.y = load_fp<FqParams>(p + 2);
+    r.zz = load_fp<FqParams>(p + 4);
+    r.zzz = load_fp<FqParams>(p + 6);
+    return r;
+}
+__device__ __forceinline__ void store_xyzz(uint4 *p, const xyzz_t &a) {
+    store_fp(p, a.x);
+    store_fp(p + 2, a.y);
+    store_fp(p + 4, a.zz);
+    store_fp(p + 6, a.zzz);
+}
+
+// FIRST: entries are (key, base index | sign) and points are gathered from the affine bases.
+// else : entries are (key, XYZZ partial) produced by the previous level.
+template <bool FIRST>
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t *keys, const uint32_t *vals, const uint4 *bases, const uint4 *pts_in,
+                                                         uint64_t n_in, uint32_t L, uint4 *buckets, uint32_t *keys_out, uint4 *pts_out,
+                                                         uint64_t nchunks) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nchunks) return;
+    const uint64_t start = t * L;
+    uint32_t cur = INVALID_KEY, nruns = 0;
+    uint32_t k0 = INVALID_KEY, k1 = INVALID_KEY;  // partial slots of this chunk
+    xyzz_t acc = xyzz_t::identity();
+    bool done = false;
+    for (uint32_t j = 0; j < L && !done; j += 4) {
+        const uint64_t pos = start + j;
+        if (pos >= n_in) break;
+        const uint4 k4 = *reinterpret_cast<const uint4 *>(keys + pos);
+        uint4 v4 = make_uint4(0, 0, 0, 0);
+        if (FIRST) v4 = *reinterpret_cast<const uint4 *>(vals + pos);
+        const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
+        const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t k = (pos + q < n_in) ? kk[q] : INVALID_KEY;  // n_in need not be a multiple of 4
+            if (k == INVALID_KEY) {
+                if (FIRST) { done = true; break; }  // level 1: valid entries are a prefix of the list
+                continue;
+            }
+            if (k != cur) {
+                if (cur != INVALID_KEY) {
+                    if (nruns == 1) {
+                        k0 = cur;
+                        store_xyzz(pts_out + 8 * (2 * t), acc);
+                    } else {
+                        store_xyzz(buckets + 8 * (uint64_t)cur, acc);  // interior run: sole owner of its bucket
+                    }
+                }
+                cur = k;
+                nruns++;
+                acc = xyzz_t::identity();
+            }
+            if (FIRST) {
+                const uint32_t v = vv[q];
+                const uint4 *bp = bases + 4 * (uint64_t)(v & 0x7fffffffu);
+                affine_t p;
+                p.x = ldg_fp<FqParams>(bp);
+                p.y = ldg_fp<FqParams>(bp + 2);
+                madd(acc, p, (v >> 31) != 0);
+            } else {
+                xyzz_t p = load_xyzz(pts_in + 8 * (pos + q));
+                add(acc, p);
+            }
+        }
+    }
+    if (cur != INVALID_KEY) {
+        if (nruns == 1) {
+            k0 = cur;
+            store_xyzz(pts_out + 8 * (2 * t), acc);
+        } else {
+            k1 = cur;
+            store_xyzz(pts_out + 8 * (2 * t + 1), acc);
+        }
+    }
+    keys_out[2 * t] = k0;
+    keys_out[2 * t + 1] = k1;
+}
+
+// last level: <= FINAL_MAX slots, one CTA.  Compact the valid slots, run a Hillis-Steele segmented
+// inclusive scan over equal keys, and let the tail of every run store its bucket.
+__global__ void __launch_bounds__(FINAL_MAX) msm_reduce_final_kernel(const uint32_t *keys, const uint4 *pts_in, uint32_t n_in, uint4 *buckets) {
+    __shared__ uint32_t s_keys[FINAL_MAX];
+    __shared__ uint4 s_pts[FINAL_MAX * 8];
+    __shared__ uint32_t total;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t k = tid < n_in ? keys[tid] : INVALID_KEY;
+    const uint32_t valid = k != INVALID_KEY;
+    const uint32_t dense = block_exclusive_scan(valid, &total);
+    if (valid) {
+        s_keys[dense] = k;
+        const uint4 *src = pts_in + 8 * (uint64_t)tid;
+#pragma unroll
+        for (int q = 0; q < 8; q++) s_pts[dense * 8 + q] = src[q];
+    }
+    __syncthreads();
+    const uint32_t m = total;
+    xyzz_t mine = xyzz_t::identity();
+    uint32_t my_key = INVALID_KEY;
+    if (tid < m) {
+        my_key = s_keys[tid];
+        mine = load_xyzz(s_pts + tid * 8);
+    }
+    for (uint32_t d = 1; d < m; d <<= 1) {
+        const bool take = tid < m && tid >= d && s_keys[tid - d] == my_key;
+        xyzz_t other = xyzz_t::identity();
+        if (take) other = load_xyzz(s_pts + (tid - d) * 8);
+        __syncthreads();
+        if (take) {
+            add(mine, other);
+            store_xyzz(s_pts + tid * 8, mine);
+        }
+        __syncthreads();
+    }
+    if (tid < m && (tid == m - 1 || s_keys[tid + 1] != my_key)) store_xyzz(buckets + 8 * (uint64_t)my_key, mine);
+}
+
+// ------------------------------------------------------------------ 4: bucket reduction
+// thread = (window, segment of S = 2^seg_log buckets): seg = sum_j (s*S + j + 1) * B[s*S + j]
+__global__ void __launch_bounds__(128) msm_bucket_segment_kernel(const uint4 *buckets, MsmShape sh, uint4 *seg_sums, uint32_t nseg_per_window) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sh.W * nseg_per_window) return;
+    const uint32_t w = t / nseg_per_window, s = t % nseg_per_window;
+    const uint32_t S = 1u << sh.seg_log;
+    const uint4 *bp = buckets + 8 * ((uint64_t)w * sh.B + (uint64_t)s * S);
+    xyzz_t run = xyzz_t::identity(), acc = xyzz_t::identity();
+    for (int j = (int)S - 1; j >= 0; j--) {
+        xyzz_t b = load_xyzz(bp + 8 * j);
+        add(run, b);
+        add(acc, run);
+    }
+    // + (s * S) * run, double-and-add over the bits of s, then seg_log doublings
+    if (s && !run.is_identity()) {
+        xyzz_t extra = xyzz_t::identity();
+        for (int bit = 31 - __clz(s); bit >= 0; bit--) {
+            extra = dbl(extra);
+            if ((s >> bit) & 1) add(extra, run);
+        }
+        for (uint32_t q = 0; q < sh.seg_log; q++) extra = dbl(extra);
+        add(acc, extra);
+    }
+    store_xyzz(seg_sums + 8 * (uint64_t)t, acc);
+}
+
+// one CTA per window: sum its segment sums (strided serial part + shared-memory tree)
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(const uint4 *seg_sums, uint32_t nseg_per_window, uint4 *win_sums) {
+    __shared__ uint4 s_pts[128 * 8];
+    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    xyzz_t acc = xyzz_t::identity();
+    for (uint32_t s = tid; s < nseg_per_window; s += blockDim.x) {
+        xyzz_t p = load_xyzz(seg_sums + 8 * ((uint64_t)w * nseg_per_window + s));
+        add(acc, p);
+    }
+    store_xyzz(s_pts + tid * 8, acc);
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d >= 1; d >>= 1) {
+        if (tid < d) {
+            xyzz_t o = load_xyzz(s_pts + (tid + d) * 8);
+            add(acc, o);
+            store_xyzz(s_pts + tid * 8, acc);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz(win_sums + 8 * (uint64_t)w, acc);
+}
+
+// ------------------------------------------------------------------ host driver
+static uint32_t ilog2_floor(uint64_t x) {
+    uint32_t r = 0;
+    while (x >>= 1) r++;
+    return r;
+}
+
+static MsmShape msm_shape(sb_ctx *ctx, uint64_t n) {
+    MsmShape sh;
+    memset(&sh, 0, sizeof sh);
+    int c = (int)ilog2_floor(n) - 3;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    if (const char *env = getenv("SB_MSM_C")) {
+        int v = atoi(env);
+        if (v >= 2 && v <= 16) c = v;
+    }
+    sh.c = (uint32_t)c;
+    sh.W = (255 + sh.c - 1) / sh.c;
+    sh.B = 1u << (sh.c - 1);
+    sh.n = n;
+    sh.t_max = ((uint64_t)sh.W * n + 3) & ~3ull;
+    const uint64_t want = (uint64_t)ctx->sm_count * 1024;
+    uint32_t L1 = 64;
+    while (L1 > 8 && sh.t_max / L1 < want) L1 >>= 1;
+    if (const char *env = getenv("SB_MSM_L1")) {
+        int v = atoi(env);
+        if (v >= 4 && v <= 1024 && (v % 4) == 0) L1 = (uint32_t)v;
+    }
+    sh.L1 = L1;
+    sh.seg_log = sh.c - 1 >= 4 ? 4 : sh.c - 1;
+    if (const char *env = getenv("SB_MSM_SEG")) {
+        int v = atoi(env);
+        if (v >= 0 && v <= (int)sh.c - 1) sh.seg_log = (uint32_t)v;
+    }
+    return sh;
+}
+
+int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
+    if (n == 0) {
+        memset(out_affine, 0, 64);
+        return SB_OK;
+    }
+    SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
+    const MsmShape sh = msm_shape(ctx, n);
+    SB_REQUIRE(sh.t_max < (1ull << 32), "msm: window count * n must be < 2^32");
+    const uint64_t nb = (uint64_t)sh.W * sh.B;
+
+    // ---- scratch ----
+    uint32_t *d_counts, *d_cursor, *d_tiles, *d_skeys, *d_svals;
+    uint4 *d_buckets, *d_seg, *d_win;
+    const uint64_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+    SB_TRY(scratch_get(ctx, "msm_counts", (nb + 4) * 4, (void **)&d_counts));
+    SB_TRY(scratch_get(ctx, "msm_cursor", (nb + 4) * 4, (void **)&d_cursor));
+    SB_TRY(scratch_get(ctx, "msm_tiles", (ntiles + 4) * 4, (void **)&d_tiles));
+    SB_TRY(scratch_get(ctx, "msm_skeys", sh.t_max * 4, (void **)&d_skeys));
+    SB_TRY(scratch_get(ctx, "msm_svals", sh.t_max * 4, (void **)&d_svals));
+    SB_TRY(scratch_get(ctx, "msm_buckets", nb * 128, (void **)&d_buckets));
+    const uint32_t nseg = sh.B >> sh.seg_log;
+    SB_TRY(scratch_get(ctx, "msm_seg", (uint64_t)sh.W * nseg * 128, (void **)&d_seg));
+    SB_TRY(scratch_get(ctx, "msm_win", (uint64_t)sh.W * 128, (void **)&d_win));
+    const uint64_t nchunks1 = (sh.t_max + sh.L1 - 1) / sh.L1;
+    uint64_t slots_a = 2 * nchunks1;                                   // level-1 output
+    uint64_t slots_b = 2 * ((slots_a + LK - 1) / LK);                  // level-2 output
+    uint32_t *d_keys_a, *d_keys_b;
+    uint4 *d_pts_a, *d_pts_b;
+    SB_TRY(scratch_get(ctx, "msm_keys_a", (slots_a + 4) * 4, (void **)&d_keys_a));
+    SB_TRY(scratch_get(ctx, "msm_pts_a", slots_a * 128, (void **)&d_pts_a));
+    SB_TRY(scratch_get(ctx, "msm_keys_b", (slots_b + 4) * 4, (void **)&d_keys_b));
+    SB_TRY(scratch_get(ctx, "msm_pts_b", slots_b * 128, (void **)&d_pts_b));
+
+    for (int e = 0; e < 5; e++)
+        if (!ctx->msm_ev[e]) SB_CUDA_TRY(cudaEventCreate(&ctx->msm_ev[e]));
+    SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[0], st));
+
+    // ---- 1+2: histogram, scan, scatter ----
+    SB_CUDA_TRY(cudaMemsetAsync(d_counts, 0, (nb + 4) * 4, st));
+    SB_CUDA_TRY(cudaMemsetAsync(d_skeys, 0xff, sh.t_max * 4, st));
+    SB_CUDA_TRY(cudaMemsetAsync(d_buckets, 0, nb * 128, st));
+    unsigned sort_grid = (unsigned)((n + 255) / 256);
+    const unsigned max_grid = (unsigned)ctx->sm_count * 16;
+    if (sort_grid > max_grid) sort_grid = max_grid;
+    SB_LAUNCH(ctx, msm_sort_kernel<false>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_counts, nullptr, nullptr);
+    SB_LAUNCH(ctx, scan_tile_sums_kernel, (unsigned)ntiles, SCAN_THREADS, 0, st, d_counts, nb, d_tiles);
+    SB_LAUNCH(ctx, scan_of_tile_sums_kernel, 1, 1024, 0, st, d_tiles, ntiles, d_counts + nb);
+    SB_LAUNCH(ctx, scan_apply_kernel, (unsigned)ntiles, SCAN_THREADS, 0, st, d_counts, nb, d_tiles, d_counts, d_cursor);
+    SB_LAUNCH(ctx, msm_sort_kernel<true>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_cursor, d_skeys, d_svals);
+
+    // ---- 3: reduce-by-key levels ----
+    SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[1], st));
+    SB_LAUNCH(ctx, msm_reduce_kernel<true>, (unsigned)((nchunks1 + 127) / 128), 128, 0, st, d_skeys, d_svals, (const uint4 *)d_bases,
+              (const uint4 *)nullptr, sh.t_max, sh.L1, d_buckets, d_keys_a, d_pts_a, nchunks1);
+    SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[2], st));
+    uint64_t slots = slots_a;
+    uint32_t *kin = d_keys_a, *kout = d_keys_b;
+    uint4 *pin = d_pts_a, *pout = d_pts_b;
+    while (slots > FINAL_MAX) {
+        const uint64_t nch = (slots + LK - 1) / LK;
+        SB_LAUNCH(ctx, msm_reduce_kernel<false>, (unsigned)((nch + 127) / 128), 128, 0, st, kin, (const uint32_t *)nullptr, (const uint4 *)nullptr,
+                  (const uint4 *)pin, slots, (uint32_t)LK, d_buckets, kout, pout, nch);
+        slots = 2 * nch;
+        uint32_t *tk = kin; kin = kout; kout = tk;
+        uint4 *tp = pin; pin = pout; pout = tp;
+    }
+    SB_LAUNCH(ctx, msm_reduce_final_kernel, 1, FINAL_MAX, 0, st, kin, (const uint4 *)pin, (uint32_t)slots, d_buckets);
+
+    // ---- 4: bucket reduction ----
+    SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[3], st));
+    const uint32_t nthreads_seg = sh.W * nseg;
+    SB_LAUNCH(ctx, msm_bucket_segment_kernel, (nthreads_seg + 127) / 128, 128, 0, st, (const uint4 *)d_buckets, sh, d_seg, nseg);
+    SB_LAUNCH(ctx, msm_window_sum_kernel, sh.W, 128, 0, st, (const uint4 *)d_seg, nseg, d_win);
+
+    // ---- 5: window sums -> host fold ----
+    SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[4], st));
+    SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_win, (size_t)sh.W * 128, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
+    cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
+    ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
+    host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.W, (int)sh.c, out_affine);
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,126 @@
+/* libsumma_b200 -- C ABI of the B200-native halo2 (KZG / BN254) prover core.
+ *
+ * Drop-in boundary for the hot path of summa-dev/circuits-halo2's `zk_prover`.  The reference has
+ * no FFI seam of its own: `zk_prover/src/circuits/utils.rs:14-26` calls generic Rust functions of
+ * the (un-vendored) crate halo2_proofs 0.2.0 @ summa-dev/halo2#8386d6e.  The seam is therefore a
+ * Cargo `[patch]` of halo2_proofs whose function *bodies* call the entry points below
+ * (INTEGRATION.md shows the Rust `extern "C"` block and the patched bodies).  Each entry point
+ * names the Rust item it replaces.
+ *
+ * Conventions
+ *  - Every function returns an int32 status (SB_OK == 0); nothing throws or unwinds across the ABI.
+ *  - Field elements and points use halo2curves' in-memory layout, so Rust passes `slice.as_ptr()`:
+ *      Fr / Fq   : 32 B, 4 x u64 little-endian limbs, Montgomery form (R = 2^256)
+ *      G1Affine  : x || y (64 B), identity = (0, 0)
+ *      G1        : x || y || z Jacobian (96 B), identity z = 0
+ *  - `*_dev` variants take DEVICE pointers (cudaMalloc / torch storage) and a `cudaStream_t` passed
+ *    as `void*` (NULL = the context's own stream).  Host variants copy in/out on the context stream.
+ *  - Caller owns every buffer it passes; the library owns what hides behind its opaque handles.
+ *  - All entry points are re-entrant for distinct contexts; calls on one context are serialised.
+ */
+#ifndef SUMMA_B200_H
+#define SUMMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_CUDA 1       /* a CUDA runtime call failed (sb_last_error() has the text) */
+#define SB_ERR_ARG 2        /* invalid argument (null pointer, size mismatch, k out of range) */
+#define SB_ERR_NO_DEVICE 3  /* no CUDA device visible: there is NO CPU fallback */
+#define SB_ERR_ALLOC 4      /* device or host allocation failed */
+
+#define SB_BASIS_MONOMIAL 0 /* ParamsKZG::g          -> ParamsKZG::commit          */
+#define SB_BASIS_LAGRANGE 1 /* ParamsKZG::g_lagrange -> ParamsKZG::commit_lagrange */
+
+typedef struct sb_ctx sb_ctx;       /* one GPU + its stream, scratch arena and plan cache */
+typedef struct sb_srs sb_srs;       /* device-resident KZG bases (ParamsKZG) */
+typedef struct sb_domain sb_domain; /* device-resident EvaluationDomain constants + NTT plans */
+
+/* ---- library / context ------------------------------------------------------------------ */
+int32_t sb_version(void);
+const char *sb_last_error(void); /* thread-local text of the last non-OK status */
+int32_t sb_device_count(int32_t *out_count);
+int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx);
+int32_t sb_ctx_destroy(sb_ctx *ctx);
+int32_t sb_ctx_synchronize(sb_ctx *ctx);
+/* device memory helpers for callers without a CUDA runtime of their own (Rust FFI crate) */
+int32_t sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **out_dptr);
+int32_t sb_dev_free(sb_ctx *ctx, void *dptr);
+int32_t sb_dev_upload(sb_ctx *ctx, void *dst_dptr, const void *src_host, size_t bytes);
+int32_t sb_dev_download(sb_ctx *ctx, void *dst_host, const void *src_dptr, size_t bytes);
+
+/* ---- field vectors (halo2curves bn256::Fr; used by EvaluationDomain and the parity tests) -- */
+/* op: 0 mul, 1 add, 2 sub (element-wise, n elements, host buffers) */
+int32_t sb_fr_vec_op(sb_ctx *ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+int32_t sb_fq_vec_op(sb_ctx *ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+
+/* ---- MSM: halo2_proofs::arithmetic::best_multiexp ------------------------------------------
+ * Rust: `pub fn best_multiexp<C: CurveAffine>(coeffs: &[C::Scalar], bases: &[C]) -> C::Curve`
+ * (reached from utils.rs:75-76,94-102,171-178 through ParamsKZG::{commit, commit_lagrange}). */
+/* generic form, host buffers; result as Jacobian with z = 1 (or z = 0 for the identity) */
+int32_t sb_best_multiexp(sb_ctx *ctx, const uint8_t *coeffs, const uint8_t *bases, size_t n, uint8_t out_jacobian[96]);
+/* device-resident operands (bases: n x 64 B, scalars: n x 32 B); result affine on the host */
+int32_t sb_msm_g1_dev(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], void *stream);
+
+/* ---- SRS: halo2_proofs::poly::kzg::commitment::ParamsKZG (utils.rs:55,64,70) ---------------- */
+/* g / g_lagrange: 2^k affine points each, exactly the arrays ParamsKZG holds */
+int32_t sb_srs_upload(sb_ctx *ctx, uint32_t k, const uint8_t *g, const uint8_t *g_lagrange, sb_srs **out_srs);
+int32_t sb_srs_destroy(sb_srs *srs);
+/* ParamsKZG::commit (basis 0) / commit_lagrange (basis 1): scalars host, n <= 2^k */
+int32_t sb_msm_g1(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const uint8_t *scalars, size_t n, uint8_t out_affine[64]);
+int32_t sb_msm_g1_srs_dev(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const void *d_scalars, size_t n, uint8_t out_affine[64], void *stream);
+
+/* data-parallel core of ParamsKZG::setup (utils.rs:70: g[i] = [tau^i] G): out[i] = scalars[i] * G,
+ * affine, device pointers (n x 32 B in, n x 64 B out).  Also synthesises bench / test bases. */
+int32_t sb_g1_fixed_base_mul_dev(sb_ctx *ctx, const void *d_scalars, size_t n, void *d_out_affine, void *stream);
+
+/* ---- NTT: halo2_proofs::arithmetic::best_fft ------------------------------------------------
+ * Rust: `pub fn best_fft<Scalar: Field, G: FftGroup<Scalar>>(a: &mut [G], omega: Scalar, log_n: u32)`
+ * natural order in, natural order out, in place: a[k] <- sum_j a[j] omega^(jk). */
+int32_t sb_best_fft(sb_ctx *ctx, uint8_t *a, const uint8_t omega[32], uint32_t log_n);
+int32_t sb_ntt_dev(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n, void *stream);
+
+/* ---- halo2_proofs::poly::EvaluationDomain<Fr> -----------------------------------------------
+ * `EvaluationDomain::new(j, k)`: j = cs.degree(); extended_k = k + ceil(log2(j - 1)). */
+int32_t sb_domain_create(sb_ctx *ctx, uint32_t j, uint32_t k, sb_domain **out_domain);
+int32_t sb_domain_destroy(sb_domain *domain);
+int32_t sb_domain_extended_k(const sb_domain *domain, uint32_t *out);
+/* host-buffer forms (in place unless two pointers are given) */
+int32_t sb_lagrange_to_coeff(sb_ctx *ctx, const sb_domain *d, uint8_t *a /* 2^k */);
+int32_t sb_coeff_to_lagrange(sb_ctx *ctx, const sb_domain *d, uint8_t *a /* 2^k */);
+int32_t sb_coeff_to_extended(sb_ctx *ctx, const sb_domain *d, const uint8_t *coeff /* 2^k */, uint8_t *ext /* 2^ext_k */);
+int32_t sb_extended_to_coeff(sb_ctx *ctx, const sb_domain *d, const uint8_t *ext /* 2^ext_k */, uint8_t *coeff /* (j-1)*2^k */);
+int32_t sb_divide_by_vanishing_poly(sb_ctx *ctx, const sb_domain *d, uint8_t *ext /* 2^ext_k */);
+/* device-pointer forms */
+int32_t sb_lagrange_to_coeff_dev(sb_ctx *ctx, const sb_domain *d, void *d_a, void *stream);
+int32_t sb_coeff_to_lagrange_dev(sb_ctx *ctx, const sb_domain *d, void *d_a, void *stream);
+int32_t sb_coeff_to_extended_dev(sb_ctx *ctx, const sb_domain *d, const void *d_coeff, void *d_ext, void *stream);
+int32_t sb_extended_to_coeff_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext /* clobbered */, void *d_coeff, void *stream);
+int32_t sb_divide_by_vanishing_poly_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *stream);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int32_t sb_launch_count(const sb_ctx *ctx, uint64_t *out);
+/* device time (ms, CUDA events on the launching stream) of the phases of the LAST MSM on this
+ * context: [0] recode + counting sort, [1] reduce level 1 (dominant kernel), [2] reduce levels >= 2,
+ * [3] bucket reduction, [4] whole device part.  out_shape (optional): c, windows, L1, seg_log. */
+int32_t sb_msm_phase_times(const sb_ctx *ctx, float out_ms[5], uint32_t out_shape[4]);
+/* throughput micro-kernel used to MEASURE the integer roof: each of n threads runs `iters`
+ * dependent-free Montgomery products; returns the elapsed milliseconds (CUDA events). */
+int32_t sb_bench_field_mul(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, int32_t field /*0 Fr,1 Fq*/, float *out_ms);
+int32_t sb_bench_imad(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, float *out_ms);      /* 8 IMAD chains / thread */
+int32_t sb_bench_imad_wide(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, float *out_ms); /* 8 IMAD.WIDE chains / thread */
+
+/* ---- host helper: sum of n affine points (folding the per-GPU partial MSM results; the
+ * north_star's "partial G1 sums are reduced on the host") ---------------------------------- */
+int32_t sb_g1_sum_affine(const uint8_t *pts, size_t n, uint8_t out_affine[64]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUMMA_B200_H */

@@ -1,0 +1,174 @@
+"""ctypes front-end of oracle/halo2_cpu.c (CPU ORACLE -- test infrastructure, NOT the product).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+All arrays are numpy uint64 views of halo2curves' memory layout (Montgomery, 4 x u64 LE limbs).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libhalo2_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "halo2_cpu.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.oracle_init()
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _u64(buf) -> np.ndarray:
+    if isinstance(buf, (bytes, bytearray)):
+        return np.frombuffer(bytes(buf), dtype=np.uint64).copy()
+    return np.ascontiguousarray(buf).view(np.uint64).reshape(-1)
+
+
+def _binop(name, a, b):
+    a, b = _u64(a), _u64(b)
+    out = np.empty_like(a)
+    getattr(lib(), name)(_p(out), _p(a), _p(b), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+def fr_mul(a, b): return _binop("oracle_fr_mul", a, b)
+def fr_add(a, b): return _binop("oracle_fr_add", a, b)
+def fr_sub(a, b): return _binop("oracle_fr_sub", a, b)
+def fq_mul(a, b): return _binop("oracle_fq_mul", a, b)
+def fq_add(a, b): return _binop("oracle_fq_add", a, b)
+def fq_sub(a, b): return _binop("oracle_fq_sub", a, b)
+
+
+def _unop(name, a):
+    a = _u64(a)
+    out = np.empty_like(a)
+    getattr(lib(), name)(_p(out), _p(a), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+def fr_inv(a): return _unop("oracle_fr_inv", a)
+def fr_from_canon(a): return _unop("oracle_fr_from_canon", a)
+def fr_to_canon(a): return _unop("oracle_fr_to_canon", a)
+def fq_from_canon(a): return _unop("oracle_fq_from_canon", a)
+def fq_to_canon(a): return _unop("oracle_fq_to_canon", a)
+
+
+def best_multiexp(coeffs, bases, threads: int = 1) -> np.ndarray:
+    """halo2 `best_multiexp`; returns the affine result (8 x u64: x || y, Montgomery)."""
+    c, b = _u64(coeffs), _u64(bases)
+    n = c.size // 4
+    assert b.size // 8 >= n
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_best_multiexp(_p(out), _p(c), _p(b), ctypes.c_size_t(n), ctypes.c_int(threads))
+    return out
+
+
+def best_fft(a, omega, log_n: int, threads: int = 1) -> np.ndarray:
+    """halo2 `best_fft` (natural in / natural out). Returns a new array."""
+    a = _u64(a).copy()
+    w = _u64(omega)
+    assert a.size == 4 << log_n
+    lib().oracle_best_fft(_p(a), _p(w), ctypes.c_uint32(log_n), ctypes.c_int(threads))
+    return a
+
+
+def fr_scale(a, s) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().oracle_fr_scale(_p(a), _p(_u64(s)), ctypes.c_size_t(a.size // 4))
+    return a
+
+
+def fr_scale_pattern(a, pat) -> np.ndarray:
+    a = _u64(a).copy()
+    pat = _u64(pat)
+    lib().oracle_fr_scale_pattern(_p(a), _p(pat), ctypes.c_size_t(pat.size // 4), ctypes.c_size_t(a.size // 4))
+    return a
+
+
+def g1_mul(p, k_mont) -> np.ndarray:
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_g1_mul(_p(out), _p(_u64(p)), _p(_u64(k_mont)))
+    return out
+
+
+def g1_add(a, b) -> np.ndarray:
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_g1_add_affine(_p(out), _p(_u64(a)), _p(_u64(b)))
+    return out
+
+
+class Domain:
+    """EvaluationDomain transforms on Montgomery byte arrays, C speed."""
+
+    def __init__(self, j: int, k: int, threads: int = 1):
+        from . import bn254 as B
+        self.d = B.EvaluationDomain(j, k)
+        self.threads = threads
+        m = lambda x: np.frombuffer(B.fr_to_mont_bytes(x), dtype=np.uint64).copy()
+        self.omega, self.omega_inv = m(self.d.omega), m(self.d.omega_inv)
+        self.ext_omega, self.ext_omega_inv = m(self.d.extended_omega), m(self.d.extended_omega_inv)
+        self.ifft_div, self.ext_ifft_div = m(self.d.ifft_divisor), m(self.d.extended_ifft_divisor)
+        self.coset = np.concatenate([m(1), m(self.d.g_coset), m(self.d.g_coset_inv)])
+        self.coset_inv = np.concatenate([m(1), m(self.d.g_coset_inv), m(self.d.g_coset)])
+        self.t_inv = np.concatenate([m(t) for t in self.d.t_inv])
+
+    def lagrange_to_coeff(self, a):
+        return fr_scale(best_fft(a, self.omega_inv, self.d.k, self.threads), self.ifft_div)
+
+    def coeff_to_lagrange(self, a):
+        return best_fft(a, self.omega, self.d.k, self.threads)
+
+    def coeff_to_extended(self, a):
+        b = fr_scale_pattern(a, self.coset)
+        ext = np.zeros(4 << self.d.extended_k, dtype=np.uint64)
+        ext[: b.size] = b
+        return best_fft(ext, self.ext_omega, self.d.extended_k, self.threads)
+
+    def extended_to_coeff(self, a):
+        b = best_fft(a, self.ext_omega_inv, self.d.extended_k, self.threads)
+        b = fr_scale(b, self.ext_ifft_div)
+        b = fr_scale_pattern(b, self.coset_inv)
+        return b[: 4 * self.d.n * self.d.quotient_poly_degree].copy()
+
+    def divide_by_vanishing_poly(self, a):
+        return fr_scale_pattern(a, self.t_inv)
+
+
+def gen_bases(n: int, seed: int = 1, threads: int = 8) -> np.ndarray:
+    """n distinct valid G1Affine points (s + i t) G, as an (n, 8) uint64 Montgomery array."""
+    from . import bn254 as B
+    rng = np.random.default_rng(seed)
+    s = int.from_bytes(rng.bytes(31), "little") % B.R
+    t = int.from_bytes(rng.bytes(31), "little") % B.R or 1
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().oracle_g1_gen_bases(_p(out), ctypes.c_size_t(n), _p(_u64(B.fr_to_mont_bytes(s))), _p(_u64(B.fr_to_mont_bytes(t))), ctypes.c_int(threads))
+    return out
+
+
+def random_fr(n: int, seed: int = 0) -> np.ndarray:
+    """n field elements < 2^253 (< r), uniform on that range, as an (n, 4) uint64 array.
+    Any value < r is a valid Montgomery residue, so no conversion is needed."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    return a

@@ -1,0 +1,388 @@
+/* CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * Plain-C restatement of the CPU algorithms the reference runs for the hot path.  The code
+ * itself lives in crates that are NOT vendored under /root/reference:
+ *   halo2curves 0.1.0 (crates.io, Cargo.lock:2272-2276)          bn256::{Fr,Fq,G1Affine,G1}
+ *   halo2_proofs 0.2.0 @ summa-dev/halo2#8386d6e (Cargo.lock:2239-2255)
+ *       arithmetic::{best_multiexp, multiexp_serial, best_fft, recursive_butterfly_arithmetic}
+ *       poly::EvaluationDomain::{lagrange_to_coeff, coeff_to_extended, extended_to_coeff,
+ *                                divide_by_vanishing_poly}
+ * Reference call sites: zk_prover/src/circuits/utils.rs:55,64,70,75,76,94-102,171-178.
+ * The published algorithms are restated from SURVEY.md Appendix A.1-A.4.
+ *
+ * Pinning: oracle/bn254.py (python big ints) is checked against the reference's golden vectors
+ * (tests/test_oracle_golden.py: verifier-contract constants, SRS file, fixed_comms[4] MSM KAT);
+ * this C twin is checked against bn254.py on random inputs and on the same KATs.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  Data layout = halo2curves memory layout: 4 x u64 LE limbs, Montgomery form.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+
+typedef struct { u64 m[4]; u64 inv; u64 r[4]; u64 r2[4]; } field_t;
+
+static field_t FR, FQ;
+static int g_init = 0;
+
+/* ------------------------------------------------------------------ field arithmetic */
+static inline int geq(const u64 a[4], const u64 b[4]) {
+    for (int i = 3; i >= 0; i--) { if (a[i] > b[i]) return 1; if (a[i] < b[i]) return 0; }
+    return 1;
+}
+static inline void sub_nc(u64 r[4], const u64 a[4], const u64 b[4]) {
+    u64 br = 0;
+    for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - br; r[i] = (u64)d; br = (u64)(d >> 64) & 1; }
+}
+static inline void f_add(const field_t *F, u64 r[4], const u64 a[4], const u64 b[4]) {
+    u64 c = 0, t[4];
+    for (int i = 0; i < 4; i++) { u128 s = (u128)a[i] + b[i] + c; t[i] = (u64)s; c = (u64)(s >> 64); }
+    if (c || geq(t, F->m)) sub_nc(r, t, F->m); else memcpy(r, t, 32);
+}
+static inline void f_sub(const field_t *F, u64 r[4], const u64 a[4], const u64 b[4]) {
+    u64 br = 0, t[4];
+    for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - br; t[i] = (u64)d; br = (u64)(d >> 64) & 1; }
+    if (br) { u64 c = 0; for (int i = 0; i < 4; i++) { u128 s = (u128)t[i] + F->m[i] + c; t[i] = (u64)s; c = (u64)(s >> 64); } }
+    memcpy(r, t, 32);
+}
+static inline int f_is_zero(const u64 a[4]) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
+static inline int f_eq(const u64 a[4], const u64 b[4]) { return a[0]==b[0] && a[1]==b[1] && a[2]==b[2] && a[3]==b[3]; }
+
+/* Montgomery product a*b*2^-256 mod m (CIOS, 4x64 limbs) */
+static inline void f_mul(const field_t *F, u64 r[4], const u64 a[4], const u64 b[4]) {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u64 carry = 0; u128 acc;
+        for (int j = 0; j < 4; j++) { acc = (u128)a[j] * b[i] + t[j] + carry; t[j] = (u64)acc; carry = (u64)(acc >> 64); }
+        acc = (u128)t[4] + carry; t[4] = (u64)acc; t[5] = (u64)(acc >> 64);
+        u64 mm = t[0] * F->inv;
+        acc = (u128)mm * F->m[0] + t[0]; carry = (u64)(acc >> 64);
+        for (int j = 1; j < 4; j++) { acc = (u128)mm * F->m[j] + t[j] + carry; t[j - 1] = (u64)acc; carry = (u64)(acc >> 64); }
+        acc = (u128)t[4] + carry; t[3] = (u64)acc; t[4] = t[5] + (u64)(acc >> 64);
+    }
+    if (t[4] || geq(t, F->m)) sub_nc(r, t, F->m); else memcpy(r, t, 32);
+}
+static inline void f_sqr(const field_t *F, u64 r[4], const u64 a[4]) { f_mul(F, r, a, a); }
+static inline void f_dbl(const field_t *F, u64 r[4], const u64 a[4]) { f_add(F, r, a, a); }
+static void f_pow(const field_t *F, u64 r[4], const u64 a[4], const u64 e[4]) {
+    u64 acc[4]; memcpy(acc, F->r, 32);
+    for (int i = 255; i >= 0; i--) {
+        f_sqr(F, acc, acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) f_mul(F, acc, acc, a);
+    }
+    memcpy(r, acc, 32);
+}
+static void f_inv(const field_t *F, u64 r[4], const u64 a[4]) {
+    u64 e[4] = {2, 0, 0, 0}, pm2[4];
+    sub_nc(pm2, F->m, e);
+    f_pow(F, r, a, pm2);
+}
+static void f_from_canon(const field_t *F, u64 r[4], const u64 a[4]) { f_mul(F, r, a, F->r2); }
+static void f_to_canon(const field_t *F, u64 r[4], const u64 a[4]) { u64 one[4] = {1, 0, 0, 0}; f_mul(F, r, a, one); }
+
+static void field_setup(field_t *F, const u64 m[4]) {
+    memcpy(F->m, m, 32);
+    u64 x = 1; /* Newton: x = m^-1 mod 2^64 */
+    for (int i = 0; i < 6; i++) x *= 2 - m[0] * x;
+    F->inv = (u64)0 - x;
+    /* R = 2^256 mod m, R2 = 2^512 mod m by repeated doubling */
+    u64 t[4] = {1, 0, 0, 0};
+    for (int i = 0; i < 256; i++) f_add(F, t, t, t);
+    memcpy(F->r, t, 32);
+    for (int i = 0; i < 256; i++) f_add(F, t, t, t);
+    memcpy(F->r2, t, 32);
+}
+
+void oracle_init(void) {
+    if (g_init) return;
+    /* contracts/src/InclusionVerifier.sol:209-210 */
+    static const u64 R_MOD[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+    static const u64 Q_MOD[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+    field_setup(&FR, R_MOD);
+    field_setup(&FQ, Q_MOD);
+    g_init = 1;
+}
+
+/* vector helpers exported for tests (all Montgomery in/out unless stated) */
+void oracle_fr_mul(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_mul(&FR, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_fr_add(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_add(&FR, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_fr_sub(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_sub(&FR, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_fq_mul(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_mul(&FQ, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_fq_add(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_add(&FQ, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_fq_sub(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_sub(&FQ, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_fr_inv(u64 *r, const u64 *a, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_inv(&FR, r + 4 * i, a + 4 * i); }
+void oracle_fr_from_canon(u64 *r, const u64 *a, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_from_canon(&FR, r + 4 * i, a + 4 * i); }
+void oracle_fr_to_canon(u64 *r, const u64 *a, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_to_canon(&FR, r + 4 * i, a + 4 * i); }
+void oracle_fq_from_canon(u64 *r, const u64 *a, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_from_canon(&FQ, r + 4 * i, a + 4 * i); }
+void oracle_fq_to_canon(u64 *r, const u64 *a, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_to_canon(&FQ, r + 4 * i, a + 4 * i); }
+
+/* ------------------------------------------------------------------ G1 (Jacobian, a = 0, b = 3) */
+typedef struct { u64 x[4], y[4], z[4]; } jac_t;   /* identity: z == 0 */
+typedef struct { u64 x[4], y[4]; } aff_t;         /* identity: (0, 0) (halo2curves G1Affine) */
+
+static inline int aff_is_id(const aff_t *p) { return f_is_zero(p->x) && f_is_zero(p->y); }
+static inline void jac_set_id(jac_t *p) { memset(p, 0, sizeof *p); memcpy(p->y, FQ.r, 32); }
+static inline int jac_is_id(const jac_t *p) { return f_is_zero(p->z); }
+
+static void jac_double(jac_t *r, const jac_t *p) {
+    if (jac_is_id(p)) { *r = *p; return; }
+    const field_t *F = &FQ;
+    u64 a[4], b[4], c[4], d[4], e[4], f[4], t[4], x3[4], y3[4], z3[4];
+    f_sqr(F, a, p->x); f_sqr(F, b, p->y); f_sqr(F, c, b);
+    f_add(F, d, p->x, b); f_sqr(F, d, d); f_sub(F, d, d, a); f_sub(F, d, d, c); f_dbl(F, d, d);
+    f_dbl(F, e, a); f_add(F, e, e, a);
+    f_sqr(F, f, e);
+    f_mul(F, z3, p->y, p->z); f_dbl(F, z3, z3);
+    f_dbl(F, t, d); f_sub(F, x3, f, t);
+    f_sub(F, t, d, x3); f_mul(F, y3, e, t);
+    f_dbl(F, c, c); f_dbl(F, c, c); f_dbl(F, c, c); f_sub(F, y3, y3, c);
+    memcpy(r->x, x3, 32); memcpy(r->y, y3, 32); memcpy(r->z, z3, 32);
+}
+static void jac_add(jac_t *r, const jac_t *p, const jac_t *q) {
+    if (jac_is_id(p)) { *r = *q; return; }
+    if (jac_is_id(q)) { *r = *p; return; }
+    const field_t *F = &FQ;
+    u64 z1z1[4], z2z2[4], u1[4], u2[4], s1[4], s2[4], h[4], rr[4], hh[4], hhh[4], v[4], t[4], x3[4], y3[4], z3[4];
+    f_sqr(F, z1z1, p->z); f_sqr(F, z2z2, q->z);
+    f_mul(F, u1, p->x, z2z2); f_mul(F, u2, q->x, z1z1);
+    f_mul(F, s1, p->y, q->z); f_mul(F, s1, s1, z2z2);
+    f_mul(F, s2, q->y, p->z); f_mul(F, s2, s2, z1z1);
+    if (f_eq(u1, u2)) {
+        if (f_eq(s1, s2)) { jac_double(r, p); return; }
+        jac_set_id(r); return;
+    }
+    f_sub(F, h, u2, u1); f_sub(F, rr, s2, s1);
+    f_sqr(F, hh, h); f_mul(F, hhh, h, hh); f_mul(F, v, u1, hh);
+    f_sqr(F, x3, rr); f_sub(F, x3, x3, hhh); f_dbl(F, t, v); f_sub(F, x3, x3, t);
+    f_sub(F, t, v, x3); f_mul(F, y3, rr, t); f_mul(F, t, s1, hhh); f_sub(F, y3, y3, t);
+    f_mul(F, z3, p->z, q->z); f_mul(F, z3, z3, h);
+    memcpy(r->x, x3, 32); memcpy(r->y, y3, 32); memcpy(r->z, z3, 32);
+}
+static void jac_add_affine(jac_t *r, const jac_t *p, const aff_t *q) {
+    if (aff_is_id(q)) { *r = *p; return; }
+    if (jac_is_id(p)) { memcpy(r->x, q->x, 32); memcpy(r->y, q->y, 32); memcpy(r->z, FQ.r, 32); return; }
+    const field_t *F = &FQ;
+    u64 z1z1[4], u2[4], s2[4], h[4], rr[4], hh[4], hhh[4], v[4], t[4], x3[4], y3[4], z3[4];
+    f_sqr(F, z1z1, p->z);
+    f_mul(F, u2, q->x, z1z1);
+    f_mul(F, s2, q->y, p->z); f_mul(F, s2, s2, z1z1);
+    if (f_eq(p->x, u2)) {
+        if (f_eq(p->y, s2)) { jac_double(r, p); return; }
+        jac_set_id(r); return;
+    }
+    f_sub(F, h, u2, p->x); f_sub(F, rr, s2, p->y);
+    f_sqr(F, hh, h); f_mul(F, hhh, h, hh); f_mul(F, v, p->x, hh);
+    f_sqr(F, x3, rr); f_sub(F, x3, x3, hhh); f_dbl(F, t, v); f_sub(F, x3, x3, t);
+    f_sub(F, t, v, x3); f_mul(F, y3, rr, t); f_mul(F, t, p->y, hhh); f_sub(F, y3, y3, t);
+    f_mul(F, z3, p->z, h);
+    memcpy(r->x, x3, 32); memcpy(r->y, y3, 32); memcpy(r->z, z3, 32);
+}
+static void jac_to_affine(aff_t *r, const jac_t *p) {
+    if (jac_is_id(p)) { memset(r, 0, sizeof *r); return; }
+    const field_t *F = &FQ;
+    u64 zi[4], zi2[4], zi3[4];
+    f_inv(F, zi, p->z); f_sqr(F, zi2, zi); f_mul(F, zi3, zi2, zi);
+    f_mul(F, r->x, p->x, zi2); f_mul(F, r->y, p->y, zi3);
+}
+
+/* affine a + b (out affine), for tests */
+void oracle_g1_add_affine(u64 out[8], const u64 a[8], const u64 b[8]) {
+    oracle_init();
+    jac_t acc; jac_set_id(&acc);
+    jac_add_affine(&acc, &acc, (const aff_t *)a);
+    jac_add_affine(&acc, &acc, (const aff_t *)b);
+    jac_to_affine((aff_t *)out, &acc);
+}
+/* affine scalar multiplication k*P, k given as a Montgomery Fr (like Rust `P * k`) */
+void oracle_g1_mul(u64 out[8], const u64 p[8], const u64 k_mont[4]) {
+    oracle_init();
+    u64 k[4]; f_to_canon(&FR, k, k_mont);
+    jac_t acc; jac_set_id(&acc);
+    for (int i = 255; i >= 0; i--) {
+        jac_double(&acc, &acc);
+        if ((k[i >> 6] >> (i & 63)) & 1) jac_add_affine(&acc, &acc, (const aff_t *)p);
+    }
+    jac_to_affine((aff_t *)out, &acc);
+}
+
+/* ------------------------------------------------------------------ best_multiexp */
+/* halo2 `multiexp_serial`: c = 1 (n<4) | 3 (n<32) | ceil(ln n); segments = 256/c + 1, processed
+ * MSB -> LSB with c doublings each; buckets [2^c - 1]; running-sum reduction. */
+static unsigned get_at(unsigned segment, unsigned c, const uint8_t bytes[32]) {
+    unsigned skip_bits = segment * c, skip_bytes = skip_bits / 8;
+    if (skip_bytes >= 32) return 0;
+    uint8_t v[8] = {0};
+    for (unsigned i = 0; i < 8 && skip_bytes + i < 32; i++) v[i] = bytes[skip_bytes + i];
+    u64 tmp; memcpy(&tmp, v, 8);
+    tmp >>= skip_bits - skip_bytes * 8;
+    tmp %= (1ULL << c);
+    return (unsigned)tmp;
+}
+static void multiexp_serial(const u64 *coeffs, const aff_t *bases, size_t n, jac_t *acc) {
+    unsigned c;
+    if (n < 4) c = 1; else if (n < 32) c = 3; else c = (unsigned)ceil(log((double)n));
+    uint8_t *repr = (uint8_t *)malloc(32 * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) { u64 t[4]; f_to_canon(&FR, t, coeffs + 4 * i); memcpy(repr + 32 * i, t, 32); }
+    unsigned segments = 256 / c + 1;
+    size_t nb = ((size_t)1 << c) - 1;
+    jac_t *buckets = (jac_t *)malloc(sizeof(jac_t) * nb);
+    for (int seg = (int)segments - 1; seg >= 0; seg--) {
+        for (unsigned k = 0; k < c; k++) jac_double(acc, acc);
+        for (size_t b = 0; b < nb; b++) jac_set_id(&buckets[b]);
+        for (size_t i = 0; i < n; i++) {
+            unsigned d = get_at((unsigned)seg, c, repr + 32 * i);
+            if (d) jac_add_affine(&buckets[d - 1], &buckets[d - 1], &bases[i]);
+        }
+        jac_t run; jac_set_id(&run);
+        for (size_t b = nb; b-- > 0;) { jac_add(&run, &run, &buckets[b]); jac_add(acc, acc, &run); }
+    }
+    free(buckets); free(repr);
+}
+typedef struct { const u64 *coeffs; const aff_t *bases; size_t n; jac_t acc; } msm_job_t;
+static void *msm_worker(void *p) { msm_job_t *j = (msm_job_t *)p; jac_set_id(&j->acc); multiexp_serial(j->coeffs, j->bases, j->n, &j->acc); return NULL; }
+
+/* `best_multiexp`: n > threads -> contiguous chunks of n/threads, partial sums folded. out = affine. */
+void oracle_best_multiexp(u64 out_affine[8], const u64 *coeffs, const u64 *bases, size_t n, int threads) {
+    oracle_init();
+    jac_t total; jac_set_id(&total);
+    if (threads < 1) threads = 1;
+    if (n > (size_t)threads && threads > 1) {
+        size_t chunk = n / (size_t)threads;
+        size_t njobs = (n + chunk - 1) / chunk;
+        msm_job_t *jobs = (msm_job_t *)calloc(njobs, sizeof(msm_job_t));
+        pthread_t *tids = (pthread_t *)calloc(njobs, sizeof(pthread_t));
+        for (size_t j = 0; j < njobs; j++) {
+            size_t lo = j * chunk, hi = lo + chunk > n ? n : lo + chunk;
+            jobs[j].coeffs = coeffs + 4 * lo; jobs[j].bases = (const aff_t *)bases + lo; jobs[j].n = hi - lo;
+            pthread_create(&tids[j], NULL, msm_worker, &jobs[j]);
+        }
+        for (size_t j = 0; j < njobs; j++) { pthread_join(tids[j], NULL); jac_add(&total, &total, &jobs[j].acc); }
+        free(jobs); free(tids);
+    } else {
+        multiexp_serial(coeffs, (const aff_t *)bases, n, &total);
+    }
+    jac_to_affine((aff_t *)out_affine, &total);
+}
+
+/* ------------------------------------------------------------------ best_fft */
+static inline size_t bitrev(size_t x, unsigned bits) {
+    size_t r = 0; for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r;
+}
+typedef struct { u64 *a; size_t n; size_t chunk; const u64 *tw; int depth; } fft_job_t;
+static void recursive_butterfly(u64 *a, size_t n, size_t twiddle_chunk, const u64 *tw, int spawn_depth);
+static void *fft_worker(void *p) { fft_job_t *j = (fft_job_t *)p; recursive_butterfly(j->a, j->n, j->chunk, j->tw, j->depth); return NULL; }
+/* halo2 `recursive_butterfly_arithmetic`: halves via join, then one combine layer */
+static void recursive_butterfly(u64 *a, size_t n, size_t twiddle_chunk, const u64 *tw, int spawn_depth) {
+    const field_t *F = &FR;
+    if (n == 2) {
+        u64 t[4]; memcpy(t, a + 4, 32);
+        memcpy(a + 4, a, 32);
+        f_add(F, a, a, t); f_sub(F, a + 4, a + 4, t);
+        return;
+    }
+    u64 *left = a, *right = a + 4 * (n / 2);
+    if (spawn_depth > 0) {
+        fft_job_t job = {left, n / 2, twiddle_chunk * 2, tw, spawn_depth - 1};
+        pthread_t tid; pthread_create(&tid, NULL, fft_worker, &job);
+        recursive_butterfly(right, n / 2, twiddle_chunk * 2, tw, spawn_depth - 1);
+        pthread_join(tid, NULL);
+    } else {
+        recursive_butterfly(left, n / 2, twiddle_chunk * 2, tw, 0);
+        recursive_butterfly(right, n / 2, twiddle_chunk * 2, tw, 0);
+    }
+    for (size_t i = 0; i < n / 2; i++) {
+        u64 t[4];
+        if (i == 0) memcpy(t, right, 32); else f_mul(F, t, right + 4 * i, tw + 4 * (i * twiddle_chunk));
+        u64 u[4]; memcpy(u, left + 4 * i, 32);
+        f_add(F, left + 4 * i, u, t); f_sub(F, right + 4 * i, u, t);
+    }
+}
+void oracle_best_fft(u64 *a, const u64 omega[4], uint32_t log_n, int threads) {
+    oracle_init();
+    size_t n = (size_t)1 << log_n;
+    if (n == 1) return;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = bitrev(i, log_n);
+        if (i < j) { u64 t[4]; memcpy(t, a + 4 * i, 32); memcpy(a + 4 * i, a + 4 * j, 32); memcpy(a + 4 * j, t, 32); }
+    }
+    size_t half = n / 2;
+    u64 *tw = (u64 *)malloc(32 * half);
+    memcpy(tw, FR.r, 32);
+    for (size_t i = 1; i < half; i++) f_mul(&FR, tw + 4 * i, tw + 4 * (i - 1), omega);
+    int depth = 0; while ((1 << (depth + 1)) <= threads && (size_t)4 << depth <= n) depth++;
+    if (threads <= 1) depth = 0;
+    recursive_butterfly(a, n, 1, tw, depth);
+    free(tw);
+}
+
+/* ------------------------------------------------------------------ EvaluationDomain pieces */
+/* a[i] *= s  */
+void oracle_fr_scale(u64 *a, const u64 s[4], size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_mul(&FR, a + 4 * i, a + 4 * i, s); }
+/* a[i] *= pat[i % m]   (coset zeta pattern, t_inv pattern) */
+void oracle_fr_scale_pattern(u64 *a, const u64 *pat, size_t m, size_t n) { oracle_init(); for (size_t i = 0; i < n; i++) f_mul(&FR, a + 4 * i, a + 4 * i, pat + 4 * (i % m)); }
+
+/* ------------------------------------------------------------------ synthetic bases (test / bench inputs) */
+/* out[i] = (s + i*t) * G for i < n, affine Montgomery: distinct valid curve points in O(n) field
+ * work (one mixed addition each + batched normalisation).  NOT an SRS: throughput/parity input only. */
+typedef struct { u64 *out; size_t lo, hi; u64 s[4], t[4]; } gen_job_t;
+static void fr_add_small_mul(u64 r[4], const u64 s[4], const u64 t[4], u64 i) {
+    /* r = s + i*t mod r (all Montgomery) */
+    u64 ic[4] = {i, 0, 0, 0}, im[4], it[4];
+    f_from_canon(&FR, im, ic); f_mul(&FR, it, im, t); f_add(&FR, r, s, it);
+}
+static void *gen_worker(void *p) {
+    gen_job_t *j = (gen_job_t *)p;
+    const size_t BATCH = 1024;
+    aff_t g; memset(&g, 0, sizeof g);
+    u64 one_c[4] = {1, 0, 0, 0}, two_c[4] = {2, 0, 0, 0};
+    f_from_canon(&FQ, g.x, one_c); f_from_canon(&FQ, g.y, two_c);
+    aff_t d, start; u64 k0[4];
+    oracle_g1_mul((u64 *)&d, (const u64 *)&g, j->t);
+    fr_add_small_mul(k0, j->s, j->t, (u64)j->lo);
+    oracle_g1_mul((u64 *)&start, (const u64 *)&g, k0);
+    jac_t cur; memcpy(cur.x, start.x, 32); memcpy(cur.y, start.y, 32); memcpy(cur.z, FQ.r, 32);
+    if (aff_is_id(&start)) jac_set_id(&cur);
+    jac_t *buf = (jac_t *)malloc(sizeof(jac_t) * BATCH);
+    u64 *pref = (u64 *)malloc(32 * BATCH);
+    for (size_t base = j->lo; base < j->hi; base += BATCH) {
+        size_t m = j->hi - base < BATCH ? j->hi - base : BATCH;
+        for (size_t i = 0; i < m; i++) { buf[i] = cur; jac_add_affine(&cur, &cur, &d); }
+        /* batch inversion of z (identity cannot occur for the parameters the tests use) */
+        u64 acc[4]; memcpy(acc, FQ.r, 32);
+        for (size_t i = 0; i < m; i++) { memcpy(pref + 4 * i, acc, 32); f_mul(&FQ, acc, acc, buf[i].z); }
+        u64 inv[4]; f_inv(&FQ, inv, acc);
+        for (size_t i = m; i-- > 0;) {
+            u64 zi[4], zi2[4], zi3[4];
+            f_mul(&FQ, zi, inv, pref + 4 * i); f_mul(&FQ, inv, inv, buf[i].z);
+            f_sqr(&FQ, zi2, zi); f_mul(&FQ, zi3, zi2, zi);
+            u64 *o = j->out + 8 * (base + i);
+            f_mul(&FQ, o, buf[i].x, zi2); f_mul(&FQ, o + 4, buf[i].y, zi3);
+        }
+    }
+    free(buf); free(pref);
+    return NULL;
+}
+void oracle_g1_gen_bases(u64 *out, size_t n, const u64 s_mont[4], const u64 t_mont[4], int threads) {
+    oracle_init();
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    gen_job_t *jobs = (gen_job_t *)calloc((size_t)threads, sizeof(gen_job_t));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    size_t per = (n + (size_t)threads - 1) / (size_t)threads;
+    int used = 0;
+    for (int t = 0; t < threads; t++) {
+        size_t lo = (size_t)t * per, hi = lo + per > n ? n : lo + per;
+        if (lo >= hi) break;
+        jobs[t].out = out; jobs[t].lo = lo; jobs[t].hi = hi;
+        memcpy(jobs[t].s, s_mont, 32); memcpy(jobs[t].t, t_mont, 32);
+        pthread_create(&tids[t], NULL, gen_worker, &jobs[t]); used++;
+    }
+    for (int t = 0; t < used; t++) pthread_join(tids[t], NULL);
+    free(jobs); free(tids);
+}

@@ -100,6 +100,7 @@ struct sb_srs {
     uint32_t k = 0;
     void *d_g = nullptr;
     void *d_g_lagrange = nullptr;
+    bool borrowed = false;  // sb_srs_wrap_dev: the caller owns the device arrays
 };
 
 struct sb_domain {
@@ -295,10 +296,23 @@ int32_t sb_srs_upload(sb_ctx *ctx, uint32_t k, const uint8_t *g_pts, const uint8
     *out_srs = s;
     return SB_OK;
 }
+int32_t sb_srs_wrap_dev(sb_ctx *ctx, uint32_t k, const void *d_g, const void *d_g_lagrange, sb_srs **out_srs) {
+    if (!ctx || !d_g || !d_g_lagrange || !out_srs) return SB_ERR_ARG;
+    SB_REQUIRE(k <= 28, "sb_srs_wrap_dev: k > 28");
+    sb_srs *s = new sb_srs();
+    s->k = k;
+    s->d_g = const_cast<void *>(d_g);
+    s->d_g_lagrange = const_cast<void *>(d_g_lagrange);
+    s->borrowed = true;
+    *out_srs = s;
+    return SB_OK;
+}
 int32_t sb_srs_destroy(sb_srs *srs) {
     if (!srs) return SB_OK;
-    cudaFree(srs->d_g);
-    cudaFree(srs->d_g_lagrange);
+    if (!srs->borrowed) {
+        cudaFree(srs->d_g);
+        cudaFree(srs->d_g_lagrange);
+    }
     delete srs;
     return SB_OK;
 }

@@ -31,6 +31,18 @@ class ParamsKZG:
         _lib.check(_lib.lib().sb_srs_upload(self.ctx.handle, ctypes.c_uint32(k), ptr(self.g), ptr(self.g_lagrange), ctypes.byref(self._h)), "sb_srs_upload")
 
     @classmethod
+    def from_device(cls, k: int, d_g: int, d_g_lagrange: int, ctx: Optional[Context] = None) -> "ParamsKZG":
+        """Wrap bases already resident in HBM (device pointers, 2^k x 64 B each; caller keeps ownership)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self._k, self.n = k, 1 << k
+        self.g = self.g_lagrange = None
+        self.tail = b""
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sb_srs_wrap_dev(self.ctx.handle, ctypes.c_uint32(k), ctypes.c_void_p(d_g), ctypes.c_void_p(d_g_lagrange), ctypes.byref(self._h)), "sb_srs_wrap_dev")
+        return self
+
+    @classmethod
     def read(cls, path: str, ctx: Optional[Context] = None) -> "ParamsKZG":
         with open(path, "rb") as f:
             data = f.read()

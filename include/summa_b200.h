@@ -70,6 +70,8 @@ int32_t sb_msm_g1_dev(sb_ctx *ctx, const void *d_bases, const void *d_scalars, s
 /* ---- SRS: halo2_proofs::poly::kzg::commitment::ParamsKZG (utils.rs:55,64,70) ---------------- */
 /* g / g_lagrange: 2^k affine points each, exactly the arrays ParamsKZG holds */
 int32_t sb_srs_upload(sb_ctx *ctx, uint32_t k, const uint8_t *g, const uint8_t *g_lagrange, sb_srs **out_srs);
+/* same handle over bases that already live on the device (borrowed: the caller keeps ownership) */
+int32_t sb_srs_wrap_dev(sb_ctx *ctx, uint32_t k, const void *d_g, const void *d_g_lagrange, sb_srs **out_srs);
 int32_t sb_srs_destroy(sb_srs *srs);
 /* ParamsKZG::commit (basis 0) / commit_lagrange (basis 1): scalars host, n <= 2^k */
 int32_t sb_msm_g1(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const uint8_t *scalars, size_t n, uint8_t out_affine[64]);

@@ -172,3 +172,39 @@ def random_fr(n: int, seed: int = 0) -> np.ndarray:
     a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
     a[:, 3] &= np.uint64((1 << 61) - 1)
     return a
+
+
+def fr_batch_invert(a) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().oracle_fr_batch_invert(_p(a), ctypes.c_size_t(a.size // 4))
+    return a
+
+
+def fr_running_product(a, init, n: int) -> np.ndarray:
+    """z[0] = init, z[i] = z[i-1] * a[i-1] for i < n."""
+    a = _u64(a)
+    out = np.zeros(4 * n, dtype=np.uint64)
+    lib().oracle_fr_running_product(_p(out), _p(a), _p(_u64(init)), ctypes.c_size_t(n))
+    return out
+
+
+def fr_eval_poly(coeffs, x) -> np.ndarray:
+    c = _u64(coeffs)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_fr_eval_poly(_p(out), _p(c), ctypes.c_size_t(c.size // 4), _p(_u64(x)))
+    return out
+
+
+def fr_kate_division(a, b) -> np.ndarray:
+    a = _u64(a)
+    n = a.size // 4
+    q = np.zeros(4 * max(n - 1, 0), dtype=np.uint64)
+    lib().oracle_fr_kate_division(_p(q), _p(a), ctypes.c_size_t(n), _p(_u64(b)))
+    return q
+
+
+def fr_axpby(a, s, b, t) -> np.ndarray:
+    a, b = _u64(a), _u64(b)
+    out = np.empty_like(a)
+    lib().oracle_fr_axpby(_p(out), _p(a), _p(_u64(s)), _p(b), _p(_u64(t)), ctypes.c_size_t(a.size // 4))
+    return out

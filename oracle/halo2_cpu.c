@@ -386,3 +386,49 @@ void oracle_g1_gen_bases(u64 *out, size_t n, const u64 s_mont[4], const u64 t_mo
     for (int t = 0; t < used; t++) pthread_join(tids[t], NULL);
     free(jobs); free(tids);
 }
+
+/* ------------------------------------------------------------------ O(n) prover helpers */
+/* halo2 `batch_invert`: zeros stay zero */
+void oracle_fr_batch_invert(u64 *a, size_t n) {
+    oracle_init();
+    u64 *pref = (u64 *)malloc(32 * (n ? n : 1));
+    u64 acc[4]; memcpy(acc, FR.r, 32);
+    for (size_t i = 0; i < n; i++) { memcpy(pref + 4 * i, acc, 32); if (!f_is_zero(a + 4 * i)) f_mul(&FR, acc, acc, a + 4 * i); }
+    u64 inv[4]; f_inv(&FR, inv, acc);
+    for (size_t i = n; i-- > 0;) {
+        if (f_is_zero(a + 4 * i)) continue;
+        u64 t[4]; f_mul(&FR, t, inv, pref + 4 * i); f_mul(&FR, inv, inv, a + 4 * i); memcpy(a + 4 * i, t, 32);
+    }
+    free(pref);
+}
+/* out[0] = init, out[i] = out[i-1] * a[i-1]  for i < n  (grand-product column Z; a has >= n-1 entries) */
+void oracle_fr_running_product(u64 *out, const u64 *a, const u64 init[4], size_t n) {
+    oracle_init();
+    if (!n) return;
+    memcpy(out, init, 32);
+    for (size_t i = 1; i < n; i++) f_mul(&FR, out + 4 * i, out + 4 * (i - 1), a + 4 * (i - 1));
+}
+/* halo2 `eval_polynomial`: Horner */
+void oracle_fr_eval_poly(u64 out[4], const u64 *coeffs, size_t n, const u64 x[4]) {
+    oracle_init();
+    u64 acc[4] = {0, 0, 0, 0};
+    for (size_t i = n; i-- > 0;) { f_mul(&FR, acc, acc, x); f_add(&FR, acc, acc, coeffs + 4 * i); }
+    memcpy(out, acc, 32);
+}
+/* halo2 `kate_division`: q = (a - a(b)) / (X - b), n-1 coefficients */
+void oracle_fr_kate_division(u64 *q, const u64 *a, size_t n, const u64 b[4]) {
+    oracle_init();
+    if (n < 2) return;
+    u64 tmp[4] = {0, 0, 0, 0};
+    for (size_t i = n - 1; i-- > 0;) {
+        u64 lead[4];
+        f_add(&FR, lead, a + 4 * (i + 1), tmp);      /* r - tmp with b negated == r + b * prev */
+        memcpy(q + 4 * i, lead, 32);
+        f_mul(&FR, tmp, lead, b);
+    }
+}
+/* r[i] = a[i] * s + b[i] * t   (polynomial linear combinations) */
+void oracle_fr_axpby(u64 *r, const u64 *a, const u64 s[4], const u64 *b, const u64 t[4], size_t n) {
+    oracle_init();
+    for (size_t i = 0; i < n; i++) { u64 x[4], y[4]; f_mul(&FR, x, a + 4 * i, s); f_mul(&FR, y, b + 4 * i, t); f_add(&FR, r + 4 * i, x, y); }
+}

@@ -96,33 +96,10 @@ __global__ void bench_imad_wide_kernel(uint64_t *out, uint32_t iters) {
 
 using namespace sb;
 
-struct sb_srs {
-    uint32_t k = 0;
-    void *d_g = nullptr;
-    void *d_g_lagrange = nullptr;
-    bool borrowed = false;  // sb_srs_wrap_dev: the caller owns the device arrays
-};
-
-struct sb_domain {
-    uint32_t j = 0, k = 0, ext_k = 0, quotient_degree = 0;
-    fr_t omega, omega_inv, ext_omega, ext_omega_inv;
-    fr_t ifft_divisor, ext_ifft_divisor;
-    fr_t coset[3], coset_inv[3];  // zeta^(i mod 3), zeta^-(i mod 3)
-    fr_t t_inv[8];
-    uint32_t n_t = 0;
-};
+#include "handles.h"
 
 namespace {
-struct Guard {
-    std::lock_guard<std::mutex> lk;
-    int prev = -1;
-    explicit Guard(sb_ctx *c) : lk(c->mu) {
-        cudaGetDevice(&prev);
-        if (prev != c->device) cudaSetDevice(c->device);
-        else prev = -1;
-    }
-    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
-};
+typedef sb::CtxGuard Guard;
 
 fr_t fr_inv_host(const fr_t &a) { return inv(a); }
 fr_t fr_from_hex_limbs(const uint32_t canon[8]) {
@@ -450,6 +427,14 @@ int32_t sb_divide_by_vanishing_poly_dev(sb_ctx *ctx, const sb_domain *d, void *d
     return fr_scale_pattern(ctx, d_ext, (size_t)1 << d->ext_k, d->t_inv, d->n_t, pick_stream(ctx, stream));
 }
 
+}  // extern "C"
+namespace sb {
+int32_t dom_l2c(sb_ctx *ctx, const sb_domain *d, void *d_a, cudaStream_t st) { return l2c_dev(ctx, d, d_a, st); }
+int32_t dom_c2e(sb_ctx *ctx, const sb_domain *d, const void *d_coeff, void *d_ext, cudaStream_t st) { return c2e_dev(ctx, d, d_coeff, d_ext, st); }
+int32_t dom_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st) { return e2c_dev(ctx, d, d_ext, d_coeff, st); }
+int32_t dom_div_vanishing(sb_ctx *ctx, const sb_domain *d, void *d_ext, cudaStream_t st) { return fr_scale_pattern(ctx, d_ext, (size_t)1 << d->ext_k, d->t_inv, d->n_t, st); }
+}  // namespace sb
+extern "C" {
 // host-buffer forms: stage through scratch on the context stream
 static int32_t host_roundtrip(sb_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t n_out, size_t n_dev, void **d_out) {
     void *dv;

@@ -67,6 +67,9 @@ struct sb_ctx {
     cudaEvent_t msm_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float msm_phase_ms[5] = {0, 0, 0, 0, 0};
     uint32_t msm_last_shape[4] = {0, 0, 0, 0};  // c, W, L1, seg_log of the last MSM
+    // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
+    float last_h_ms = 0;
+    uint32_t last_h_program[4] = {0, 0, 0, 0};
 };
 
 namespace sb {
@@ -89,6 +92,7 @@ void ntt_plans_free(sb_ctx *ctx);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st);
 
+int32_t fr_gen_powers(sb_ctx *ctx, void *d_out, const fr_t &base, size_t count, cudaStream_t st);
 int32_t g1_fixed_base_mul(sb_ctx *ctx, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 
 int32_t fr_scale(sb_ctx *ctx, void *d_a, size_t n, const fr_t &s, cudaStream_t st);

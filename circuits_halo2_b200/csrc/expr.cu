@@ -1,0 +1,269 @@
+// Column-wise evaluation of PLONKish expressions on the GPU: halo2's `GraphEvaluator`
+// re-designed as a compile-then-interpret pipeline.
+//
+// Host: every term (gate polynomial, permutation / lookup identity) is hash-consed into a DAG,
+// linearised, and register-allocated onto a handful of value slots; terms are folded Horner-style
+// with the challenge y (acc = acc * y + term), so the whole quotient numerator h(X) of
+// `Evaluator::evaluate_h` -- 19 gate polynomials + 5 permutation + 5 lookup terms for the Summa
+// circuit -- is ONE program and ONE pass over the extended domain: each of the ~30 extended columns
+// is streamed from HBM once per rotation it is queried at, nothing intermediate is written back.
+// Device: one thread per row; value slots live in shared memory ([slot][thread], 128-bit accesses,
+// conflict-free), instructions and constants are warp-uniform loads, column reads are coalesced
+// 32-byte loads at (row + rotation) mod n.  The only code is one Montgomery product and one add/sub,
+// so the kernel body stays resident in the instruction cache.
+#include <array>
+#include <map>
+#include <tuple>
+
+#include "prover.h"
+
+namespace sb {
+
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_NEG = 3, OP_COPY = 4 };
+enum { K_REG = 0, K_CONST = 1, K_INPUT = 2 };
+static inline uint32_t operand(uint32_t kind, uint32_t idx) { return (kind << 30) | idx; }
+
+ExprP e_const(const fr_t &c) { auto e = std::make_shared<Expr>(); e->kind = Expr::CONST; e->c = c; e->col = e->rot = 0; return e; }
+ExprP e_col(int col, int rot) { auto e = std::make_shared<Expr>(); e->kind = Expr::COL; e->col = col; e->rot = rot; e->c = fr_t::zero(); return e; }
+static ExprP mk(Expr::Kind k, ExprP a, ExprP b) { auto e = std::make_shared<Expr>(); e->kind = k; e->a = a; e->b = b; e->col = e->rot = 0; e->c = fr_t::zero(); return e; }
+ExprP e_neg(ExprP a) { return mk(Expr::NEG, a, nullptr); }
+ExprP e_add(ExprP a, ExprP b) { return mk(Expr::ADD, a, b); }
+ExprP e_sub(ExprP a, ExprP b) { return mk(Expr::SUB, a, b); }
+ExprP e_mul(ExprP a, ExprP b) { return mk(Expr::MUL, a, b); }
+
+namespace {
+
+struct Node {
+    int op;            // OP_* for interior nodes, -1 for leaves
+    uint32_t leaf;     // operand encoding for leaves
+    int a, b;          // children (node ids), -1 if unused
+    int uses = 0;
+    int slot = -1;
+};
+
+struct Builder {
+    Program &p;
+    std::map<std::array<uint32_t, 8>, uint32_t> const_ids;
+    std::map<std::pair<int, int>, uint32_t> input_ids;
+    std::vector<Node> nodes;
+    std::map<std::tuple<int, int, int>, int> interior;  // (op, a, b) -> node id   (per term)
+    std::map<uint32_t, int> leaves;                      // leaf operand -> node id (per term)
+    explicit Builder(Program &prog) : p(prog) {}
+
+    uint32_t const_id(const fr_t &c) {
+        std::array<uint32_t, 8> key;
+        for (int i = 0; i < 8; i++) key[i] = c.v[i];
+        auto it = const_ids.find(key);
+        if (it != const_ids.end()) return it->second;
+        uint32_t id = (uint32_t)p.consts.size();
+        p.consts.push_back(c);
+        const_ids[key] = id;
+        return id;
+    }
+    uint32_t input_id(int col, int rot) {
+        auto key = std::make_pair(col, rot);
+        auto it = input_ids.find(key);
+        if (it != input_ids.end()) return it->second;
+        uint32_t id = (uint32_t)(p.inputs.size() / 2);
+        p.inputs.push_back(col);
+        p.inputs.push_back(rot);
+        input_ids[key] = id;
+        return id;
+    }
+    int leaf_node(uint32_t enc) {
+        auto it = leaves.find(enc);
+        if (it != leaves.end()) return it->second;
+        Node n; n.op = -1; n.leaf = enc; n.a = n.b = -1;
+        nodes.push_back(n);
+        return leaves[enc] = (int)nodes.size() - 1;
+    }
+    int build(const ExprP &e) {
+        switch (e->kind) {
+            case Expr::CONST: return leaf_node(operand(K_CONST, const_id(e->c)));
+            case Expr::COL: return leaf_node(operand(K_INPUT, input_id(e->col, e->rot)));
+            default: break;
+        }
+        int a = build(e->a);
+        int b = e->b ? build(e->b) : -1;
+        int op = e->kind == Expr::ADD ? OP_ADD : e->kind == Expr::SUB ? OP_SUB : e->kind == Expr::MUL ? OP_MUL : OP_NEG;
+        if ((op == OP_ADD || op == OP_MUL) && b < a) std::swap(a, b);  // commutative: canonical order for CSE
+        auto key = std::make_tuple(op, a, b);
+        auto it = interior.find(key);
+        if (it != interior.end()) return it->second;
+        Node n; n.op = op; n.leaf = 0; n.a = a; n.b = b;
+        nodes.push_back(n);
+        return interior[key] = (int)nodes.size() - 1;
+    }
+};
+
+}  // namespace
+
+Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
+    Program p;
+    Builder bld(p);
+    const uint32_t ACC = 0;  // slot 0 holds the running Horner accumulator
+    std::vector<bool> slot_busy(1, true);
+    uint32_t fold_const = fold ? bld.const_id(*fold) : 0;
+    auto emit = [&](int op, uint32_t dst, uint32_t a, uint32_t b) {
+        p.code.push_back(((uint32_t)op << 16) | dst);
+        p.code.push_back(a);
+        p.code.push_back(b);
+        if (op == OP_MUL) p.n_mul++;
+        else if (op != OP_COPY) p.n_addsub++;
+    };
+    for (size_t ti = 0; ti < terms.size(); ti++) {
+        bld.nodes.clear();
+        bld.interior.clear();
+        bld.leaves.clear();
+        const int root = bld.build(terms[ti]);
+        std::vector<Node> &nd = bld.nodes;
+        // nodes are in topological (post-) order by construction; count uses
+        for (auto &n : nd) {
+            if (n.op < 0) continue;
+            nd[n.a].uses++;
+            if (n.b >= 0) nd[n.b].uses++;
+        }
+        auto alloc = [&]() -> uint32_t {
+            for (uint32_t s = 1; s < slot_busy.size(); s++)
+                if (!slot_busy[s]) { slot_busy[s] = true; return s; }
+            slot_busy.push_back(true);
+            return (uint32_t)slot_busy.size() - 1;
+        };
+        auto opnd = [&](int id) -> uint32_t { return nd[id].op < 0 ? nd[id].leaf : operand(K_REG, (uint32_t)nd[id].slot); };
+        auto release = [&](int id) {
+            if (nd[id].op < 0) return;
+            if (--nd[id].uses == 0) slot_busy[nd[id].slot] = false;
+        };
+        for (size_t i = 0; i < nd.size(); i++) {
+            Node &n = nd[i];
+            if (n.op < 0) continue;
+            const uint32_t a = opnd(n.a), b = n.b >= 0 ? opnd(n.b) : 0;
+            // operands may be released before the destination is chosen: dst may alias a dying source
+            release(n.a);
+            if (n.b >= 0) release(n.b);
+            n.slot = (int)alloc();
+            emit(n.op, (uint32_t)n.slot, a, b);
+        }
+        // fold into the accumulator
+        const uint32_t t_op = opnd(root);
+        if (ti == 0) {
+            emit(OP_COPY, ACC, t_op, 0);
+        } else if (fold) {
+            emit(OP_MUL, ACC, operand(K_REG, ACC), operand(K_CONST, fold_const));
+            emit(OP_ADD, ACC, operand(K_REG, ACC), t_op);
+        } else {
+            emit(OP_ADD, ACC, operand(K_REG, ACC), t_op);
+        }
+        if (nd[root].op >= 0) slot_busy[nd[root].slot] = false;
+    }
+    p.n_slots = (uint32_t)slot_busy.size();
+    p.out_slot = ACC;
+    return p;
+}
+
+// ------------------------------------------------------------------ device interpreter
+struct ExprArgs {
+    const uint32_t *code;
+    uint32_t n_instr;
+    const uint4 *consts;
+    const int32_t *inputs;
+    const uint4 *const *cols;
+    uint32_t log_n, rot_scale_log;
+    uint4 *out;
+    uint32_t out_slot;  // (n_slots << 16) | output slot
+};
+
+static const int EXPR_THREADS = 128;
+
+__device__ __forceinline__ fr_t expr_fetch(uint32_t opnd, const ExprArgs &A, const uint4 *s_lo, const uint4 *s_hi, uint32_t tid, uint64_t row) {
+    const uint32_t kind = opnd >> 30, idx = opnd & 0x3fffffffu;
+    fr_t r;
+    if (kind == K_REG) {
+        uint4 a = s_lo[idx * EXPR_THREADS + tid], b = s_hi[idx * EXPR_THREADS + tid];
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    } else if (kind == K_CONST) {
+        r = ldg_fp<FrParams>(A.consts + 2 * idx);
+    } else {
+        const int32_t col = __ldg(A.inputs + 2 * idx), rot = __ldg(A.inputs + 2 * idx + 1);
+        const uint64_t mask = (1ull << A.log_n) - 1;
+        const uint64_t j = (row + (uint64_t)((int64_t)rot * (int64_t)(1ll << A.rot_scale_log))) & mask;
+        const uint4 *base = A.cols[col];
+        r = ldg_fp<FrParams>(base + 2 * j);
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(EXPR_THREADS) expr_eval_kernel(const ExprArgs A) {
+    extern __shared__ uint4 smem[];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t row = blockIdx.x * (uint64_t)EXPR_THREADS + tid;
+    // value slots: [slot][thread]; low 128 bits of every slot first, then the high 128 bits
+    const uint32_t n_slots = A.out_slot >> 16;
+    uint4 *lo = smem, *hi = smem + (size_t)n_slots * EXPR_THREADS;
+    const uint32_t out_slot = A.out_slot & 0xffffu;
+    for (uint32_t pc = 0; pc < A.n_instr; pc++) {
+        const uint32_t w0 = __ldg(A.code + 3 * pc), wa = __ldg(A.code + 3 * pc + 1), wb = __ldg(A.code + 3 * pc + 2);
+        const uint32_t op = w0 >> 16, dst = w0 & 0xffffu;
+        fr_t a = expr_fetch(wa, A, lo, hi, tid, row);
+        fr_t r;
+        if (op == OP_MUL) {
+            r = mul(a, expr_fetch(wb, A, lo, hi, tid, row));
+        } else if (op == OP_ADD) {
+            r = add(a, expr_fetch(wb, A, lo, hi, tid, row));
+        } else if (op == OP_SUB) {
+            r = sub(a, expr_fetch(wb, A, lo, hi, tid, row));
+        } else if (op == OP_NEG) {
+            r = neg(a);
+        } else {
+            r = a;
+        }
+        lo[dst * EXPR_THREADS + tid] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        hi[dst * EXPR_THREADS + tid] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    }
+    A.out[2 * row] = lo[out_slot * EXPR_THREADS + tid];
+    A.out[2 * row + 1] = hi[out_slot * EXPR_THREADS + tid];
+}
+
+int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st) {
+    const uint64_t n = 1ull << log_n;
+    SB_REQUIRE(n >= (uint64_t)EXPR_THREADS, "expr_eval: domain smaller than one CTA");
+    SB_REQUIRE(prog.n_slots >= 1 && prog.n_slots <= 48, "expr_eval: too many live values");
+    const size_t code_b = prog.code.size() * 4, const_b = prog.consts.size() * 32, in_b = prog.inputs.size() * 4, col_b = cols.size() * sizeof(void *);
+    const size_t off_const = (code_b + 31) & ~(size_t)31, off_in = off_const + ((const_b + 31) & ~(size_t)31), off_col = off_in + ((in_b + 31) & ~(size_t)31);
+    const size_t total = off_col + col_b + 32;
+    std::vector<uint8_t> host(total, 0);
+    memcpy(host.data(), prog.code.data(), code_b);
+    if (const_b) memcpy(host.data() + off_const, prog.consts.data(), const_b);
+    if (in_b) memcpy(host.data() + off_in, prog.inputs.data(), in_b);
+    if (col_b) memcpy(host.data() + off_col, cols.data(), col_b);
+    // each launch gets its own staging slice so that programs queued back-to-back on one stream do not clobber each other
+    static thread_local uint32_t ring = 0;
+    const uint32_t slice = ring++ % 8;
+    uint8_t *d_prog;
+    const size_t slice_bytes = 1 << 20;
+    SB_REQUIRE(total <= slice_bytes, "expr_eval: program too large");
+    SB_TRY(scratch_get(ctx, "expr_prog", 8 * slice_bytes, (void **)&d_prog));
+    d_prog += (size_t)slice * slice_bytes;
+    SB_CUDA_TRY(cudaMemcpyAsync(d_prog, host.data(), total, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));  // `host` is pageable and dies at return
+    ExprArgs A;
+    A.code = (const uint32_t *)d_prog;
+    A.n_instr = (uint32_t)(prog.code.size() / 3);
+    A.consts = (const uint4 *)(d_prog + off_const);
+    A.inputs = (const int32_t *)(d_prog + off_in);
+    A.cols = (const uint4 *const *)(d_prog + off_col);
+    A.log_n = log_n;
+    A.rot_scale_log = rot_scale_log;
+    A.out = (uint4 *)d_out;
+    A.out_slot = (prog.n_slots << 16) | prog.out_slot;
+    const size_t smem = (size_t)prog.n_slots * EXPR_THREADS * 32;
+    static bool attr = false;
+    if (!attr) {
+        SB_CUDA_TRY(cudaFuncSetAttribute(expr_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EXPR_THREADS * 32));
+        attr = true;
+    }
+    SB_LAUNCH(ctx, expr_eval_kernel, (unsigned)(n / EXPR_THREADS), EXPR_THREADS, smem, st, A);
+    return SB_OK;
+}
+
+}  // namespace sb

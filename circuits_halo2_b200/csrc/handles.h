@@ -1,0 +1,39 @@
+// Opaque handle layouts shared by api.cu and prover.cu.
+#pragma once
+#include "common.cuh"
+
+struct sb_srs {
+    uint32_t k = 0;
+    void *d_g = nullptr;
+    void *d_g_lagrange = nullptr;
+    bool borrowed = false;  // sb_srs_wrap_dev: the caller owns the device arrays
+};
+
+struct sb_domain {
+    uint32_t j = 0, k = 0, ext_k = 0, quotient_degree = 0;
+    sb::fr_t omega, omega_inv, ext_omega, ext_omega_inv;
+    sb::fr_t ifft_divisor, ext_ifft_divisor;
+    sb::fr_t coset[3], coset_inv[3];  // zeta^(i mod 3), zeta^-(i mod 3)
+    sb::fr_t t_inv[8];
+    uint32_t n_t = 0;
+};
+
+
+namespace sb {
+// EvaluationDomain transforms on device pointers, no locking (callers hold the context)
+int32_t dom_l2c(sb_ctx *ctx, const sb_domain *d, void *d_a, cudaStream_t st);
+int32_t dom_c2e(sb_ctx *ctx, const sb_domain *d, const void *d_coeff, void *d_ext, cudaStream_t st);
+int32_t dom_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st);
+int32_t dom_div_vanishing(sb_ctx *ctx, const sb_domain *d, void *d_ext, cudaStream_t st);
+
+struct CtxGuard {
+    std::lock_guard<std::mutex> lk;
+    int prev = -1;
+    explicit CtxGuard(sb_ctx *c) : lk(c->mu) {
+        cudaGetDevice(&prev);
+        if (prev != c->device) cudaSetDevice(c->device);
+        else prev = -1;
+    }
+    ~CtxGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace sb

@@ -166,6 +166,16 @@ void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_aff
     memcpy(out_affine + 32, y.v, 32);
 }
 
+// Fq Montgomery (32 B) -> canonical little-endian bytes (transcript encodings of commitments)
+void host_fq_to_canonical(const uint8_t mont[32], uint8_t canon_le[32]) {
+    fe a, one_c;
+    memcpy(a.v, mont, 32);
+    memset(&one_c, 0, sizeof one_c);
+    one_c.v[0] = 1;
+    fe c = mul(a, one_c);
+    for (int i = 0; i < 32; i++) canon_le[i] = (uint8_t)(c.v[i >> 3] >> (8 * (i & 7)));
+}
+
 // T[j] = 2^j * G for j < 254, affine halo2curves layout (G = (1, 2))
 void host_pow2_table(uint8_t *out) {
     pt p;

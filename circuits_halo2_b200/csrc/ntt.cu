@@ -187,6 +187,12 @@ __global__ void gen_powers_kernel(uint4 *out, fr_t base, uint64_t count) {
     store_fp(out + 2 * i, acc);
 }
 
+int32_t fr_gen_powers(sb_ctx *ctx, void *d_out, const fr_t &base, size_t count, cudaStream_t st) {
+    if (count == 0) return SB_OK;
+    SB_LAUNCH(ctx, gen_powers_kernel, (unsigned)((count + 127) / 128), 128, 0, st, (uint4 *)d_out, base, (uint64_t)count);
+    return SB_OK;
+}
+
 // ---- host side ------------------------------------------------------------------------------
 fr_t fr_pow_host(const fr_t &base, uint64_t e) {
     fr_t acc = fr_t::one(), b = base;

@@ -1,0 +1,1054 @@
+// halo2 `create_proof` (KZG commitments, SHPLONK multi-open) on one B200.
+//
+// Replaces halo2_proofs::plonk::{keygen_pk (the device-resident part), create_proof}
+// (reference call sites zk_prover/src/circuits/utils.rs:75-76, :94-102 Blake2b transcript,
+// :171-178 Keccak transcript).  The sequence of transcript writes, challenge squeezes and RNG draws is
+// the one SURVEY.md A.5-A.10/A.13 restates; the oracle twin is oracle/halo2_prover.py and the two
+// produce byte-identical proofs for the same seed.
+//
+// Division of labour: everything that touches n or 8n field elements runs on the GPU (MSM, NTT,
+// expression programs over columns, batch inversion, running products, sort, Horner sums, SHPLONK
+// numerators and their exact division by Z_S(X) via a coset NTT); the host keeps the Fiat-Shamir
+// transcript, the ChaCha20 blinding RNG, and O(1) scalar algebra (rotations of x, interpolation of
+// <= 3 points, vanishing products).  All per-circuit constants (fixed / sigma columns in Lagrange,
+// coefficient and extended-coset form, l_0 / l_last / l_active, the coset X column) stay resident in
+// HBM inside the `sb_pk` handle and are reused by every proof.
+#include <algorithm>
+#include <set>
+
+#include "handles.h"
+#include "hostcrypto.h"
+#include "json.h"
+#include "prover.h"
+
+namespace sb {
+void host_fq_to_canonical(const uint8_t mont[32], uint8_t canon_le[32]);
+}
+using namespace sb;
+using hfr::Fr;
+
+namespace {
+
+// ------------------------------------------------------------------ constraint system
+struct JExpr;  // constraint-system expression before column indices are bound
+struct ConstraintSystem {
+    int A = 0, F = 0, I = 0, n_instances = 0;
+    std::vector<std::pair<int, int>> advice_q, fixed_q;
+    std::vector<json::ValueP> gates;
+    struct Lookup { std::vector<json::ValueP> input, table; };
+    std::vector<Lookup> lookups;
+    std::vector<std::pair<std::string, int>> perm_cols;
+    int degree = 0, blinding = 0;
+    json::ValueP root;
+};
+
+Fr fr_from_hex(const std::string &hex) {
+    // canonical value as a hex string ("0x..."), < r
+    uint64_t l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t start = (hex.size() > 2 && hex[1] == 'x') ? 2 : 0;
+    int nib = 0;
+    for (size_t i = hex.size(); i-- > start; nib++) {
+        char c = hex[i];
+        uint64_t v = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : 0;
+        if (nib < 128) l[nib >> 4] |= v << (4 * (nib & 15));
+    }
+    return hfr::from_u512(l);
+}
+
+ConstraintSystem parse_cs(const std::string &text) {
+    ConstraintSystem cs;
+    cs.root = json::parse(text);
+    const json::Value &r = *cs.root;
+    cs.A = (int)r.at("num_advice_columns").as_int();
+    cs.F = (int)r.at("num_fixed_columns").as_int();
+    cs.I = (int)r.at("num_instance_columns").as_int();
+    cs.n_instances = r.has("num_instances") ? (int)r.at("num_instances").as_int() : 0;
+    for (auto &q : r.at("advice_queries").arr) cs.advice_q.push_back({(int)(*q)[0].as_int(), (int)(*q)[1].as_int()});
+    for (auto &q : r.at("fixed_queries").arr) cs.fixed_q.push_back({(int)(*q)[0].as_int(), (int)(*q)[1].as_int()});
+    for (auto &g : r.at("gates").arr) cs.gates.push_back(g);
+    for (auto &l : r.at("lookups").arr) {
+        ConstraintSystem::Lookup lk;
+        for (auto &e : l->at("input").arr) lk.input.push_back(e);
+        for (auto &e : l->at("table").arr) lk.table.push_back(e);
+        if (lk.input.size() != lk.table.size() || lk.input.empty()) throw std::runtime_error("lookup: input/table arity mismatch");
+        cs.lookups.push_back(lk);
+    }
+    for (auto &c : r.at("permutation_columns").arr) cs.perm_cols.push_back({(*c)[0].as_str(), (int)(*c)[1].as_int()});
+    cs.degree = (int)r.at("degree").as_int();
+    cs.blinding = (int)r.at("blinding_factors").as_int();
+    if (cs.I != 1) throw std::runtime_error("exactly one instance column is supported");
+    return cs;
+}
+
+// column-index binding: (kind, column) -> index into a device pointer table
+struct ColMap {
+    int advice0 = 0, fixed0 = 0, instance0 = 0;
+    int col(const std::string &kind, int c) const {
+        if (kind == "advice") return advice0 + c;
+        if (kind == "fixed") return fixed0 + c;
+        if (kind == "instance") return instance0 + c;
+        throw std::runtime_error("unknown column kind " + kind);
+    }
+};
+
+ExprP bind_expr(const json::Value &e, const ColMap &m) {
+    const std::string &k = e[0].as_str();
+    if (k == "const") return e_const(to_dev(fr_from_hex(e[1].as_str())));
+    if (k == "advice" || k == "fixed" || k == "instance") return e_col(m.col(k, (int)e[1].as_int()), (int)e[2].as_int());
+    if (k == "neg") return e_neg(bind_expr(e[1], m));
+    if (k == "add") return e_add(bind_expr(e[1], m), bind_expr(e[2], m));
+    if (k == "sub") return e_sub(bind_expr(e[1], m), bind_expr(e[2], m));
+    if (k == "mul") return e_mul(bind_expr(e[1], m), bind_expr(e[2], m));
+    throw std::runtime_error("unknown expression node " + k);
+}
+
+ExprP ec(const Fr &x) { return e_const(to_dev(x)); }
+
+// ------------------------------------------------------------------ transcripts
+struct Transcript {
+    std::vector<uint8_t> proof;
+    virtual ~Transcript() {}
+    virtual void common_scalar(const Fr &s) = 0;
+    virtual void common_point(const uint8_t aff_mont[64]) = 0;
+    virtual void emit_point(const uint8_t aff_mont[64]) = 0;
+    virtual void emit_scalar(const Fr &s) = 0;
+    virtual Fr squeeze() = 0;
+    bool write_point(const uint8_t aff_mont[64]) {
+        bool id = true;
+        for (int i = 0; i < 64; i++) id = id && aff_mont[i] == 0;
+        if (id) return false;  // both reference transcripts refuse the identity
+        common_point(aff_mont);
+        emit_point(aff_mont);
+        return true;
+    }
+    void write_scalar(const Fr &s) {
+        common_scalar(s);
+        emit_scalar(s);
+    }
+};
+
+struct KeccakTranscript : Transcript {
+    std::vector<uint8_t> buf;
+    static void be32(const uint8_t le[32], uint8_t out[32]) { for (int i = 0; i < 32; i++) out[i] = le[31 - i]; }
+    void common_scalar(const Fr &s) override {
+        uint8_t b[32];
+        hfr::to_bytes_be(s, b);
+        buf.insert(buf.end(), b, b + 32);
+    }
+    void point_bytes(const uint8_t aff[64], uint8_t out[64]) {
+        uint8_t le[32];
+        host_fq_to_canonical(aff, le);
+        be32(le, out);
+        host_fq_to_canonical(aff + 32, le);
+        be32(le, out + 32);
+    }
+    void common_point(const uint8_t aff[64]) override {
+        uint8_t b[64];
+        point_bytes(aff, b);
+        buf.insert(buf.end(), b, b + 64);
+    }
+    void emit_point(const uint8_t aff[64]) override {
+        uint8_t b[64];
+        point_bytes(aff, b);
+        proof.insert(proof.end(), b, b + 64);
+    }
+    void emit_scalar(const Fr &s) override {
+        uint8_t b[32];
+        hfr::to_bytes_be(s, b);
+        proof.insert(proof.end(), b, b + 32);
+    }
+    Fr squeeze() override {
+        std::vector<uint8_t> data(buf);
+        if (buf.size() == 32) data.push_back(1);
+        uint8_t h[32], le[32];
+        keccak256(data.data(), data.size(), h);
+        buf.assign(h, h + 32);
+        for (int i = 0; i < 32; i++) le[i] = h[31 - i];
+        return hfr::from_bytes_le_wide(le, 32);
+    }
+};
+
+struct Blake2bTranscript : Transcript {
+    Blake2b st;
+    Blake2bTranscript() { st.init(64, (const uint8_t *)"Halo2-Transcript"); }
+    void common_scalar(const Fr &s) override {
+        uint8_t b[33];
+        b[0] = 2;
+        hfr::to_bytes_le(s, b + 1);
+        st.update(b, 33);
+    }
+    void common_point(const uint8_t aff[64]) override {
+        uint8_t b[65];
+        b[0] = 1;
+        host_fq_to_canonical(aff, b + 1);
+        host_fq_to_canonical(aff + 32, b + 33);
+        st.update(b, 65);
+    }
+    void emit_point(const uint8_t aff[64]) override {
+        uint8_t x[32], y[32];
+        host_fq_to_canonical(aff, x);
+        host_fq_to_canonical(aff + 32, y);
+        x[31] |= (uint8_t)((y[0] & 1) << 6);
+        proof.insert(proof.end(), x, x + 32);
+    }
+    void emit_scalar(const Fr &s) override {
+        uint8_t b[32];
+        hfr::to_bytes_le(s, b);
+        proof.insert(proof.end(), b, b + 32);
+    }
+    Fr squeeze() override {
+        uint8_t z = 0, h[64];
+        st.update(&z, 1);
+        st.final(h);
+        return hfr::from_bytes_le_wide(h, 64);
+    }
+};
+
+// host scalar helpers
+Fr fpow(const Fr &b, uint64_t e) { return hfr::pow_u64(b, e); }
+Fr rotate(const Fr &x, const Fr &omega, const Fr &omega_inv, int r) { return r >= 0 ? hfr::mul(x, fpow(omega, (uint64_t)r)) : hfr::mul(x, fpow(omega_inv, (uint64_t)(-r))); }
+
+std::vector<Fr> lagrange_interpolate(const std::vector<Fr> &pts, const std::vector<Fr> &evals) {
+    const size_t n = pts.size();
+    std::vector<Fr> out(n, hfr::ZERO);
+    for (size_t j = 0; j < n; j++) {
+        std::vector<Fr> num(1, hfr::ONE);
+        Fr den = hfr::ONE;
+        for (size_t k = 0; k < n; k++) {
+            if (k == j) continue;
+            std::vector<Fr> nxt(num.size() + 1, hfr::ZERO);
+            for (size_t i = 0; i < num.size(); i++) {
+                nxt[i + 1] = hfr::add(nxt[i + 1], num[i]);
+                nxt[i] = hfr::sub(nxt[i], hfr::mul(pts[k], num[i]));
+            }
+            num.swap(nxt);
+            den = hfr::mul(den, hfr::sub(pts[j], pts[k]));
+        }
+        Fr s = hfr::mul(evals[j], hfr::inv(den));
+        for (size_t i = 0; i < num.size(); i++) out[i] = hfr::add(out[i], hfr::mul(num[i], s));
+    }
+    return out;
+}
+Fr eval_small(const std::vector<Fr> &c, const Fr &x) {
+    Fr acc = hfr::ZERO;
+    for (size_t i = c.size(); i-- > 0;) acc = hfr::add(hfr::mul(acc, x), c[i]);
+    return acc;
+}
+
+struct FrLess {
+    bool operator()(const Fr &a, const Fr &b) const { return hfr::cmp(a, b) < 0; }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ proving key handle
+struct sb_pk {
+    ConstraintSystem cs;
+    const sb_srs *srs = nullptr;
+    sb_domain *dom = nullptr;
+    uint32_t k = 0, ext_k = 0;
+    size_t n = 0, ext_n = 0;
+    Fr transcript_repr;
+    int P = 0;
+    // device-resident (all Montgomery Fr arrays)
+    std::vector<void *> fixed_values, fixed_polys, fixed_cosets;
+    std::vector<void *> sigma_values, sigma_polys, sigma_cosets;
+    void *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;  // extended
+    void *x_coset = nullptr;                                     // zeta * ext_omega^i (extended)
+    void *omega_pows = nullptr;                                  // omega^i (n)
+    void *div_g_pows = nullptr, *div_x = nullptr, *div_ginv_scaled = nullptr;  // SHPLONK coset division: g^i, g*omega^i, g^-i / n
+    std::vector<uint8_t> fixed_comms, sigma_comms;               // affine, 64 B each
+    std::vector<void *> owned;
+};
+
+namespace {
+
+int32_t dalloc(sb_pk *pk, size_t bytes, void **out) {
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 32);
+    if (e != cudaSuccess) {
+        set_last_error("pk: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return SB_ERR_ALLOC;
+    }
+    pk->owned.push_back(*out);
+    return SB_OK;
+}
+
+const Fr DIV_G = hfr::from_u64(7);  // multiplicative generator: g * H is disjoint from H
+
+int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint8_t *sigma_values, cudaStream_t st) {
+    const size_t n = pk->n, en = pk->ext_n;
+    const sb_domain *d = pk->dom;
+    auto to_all_forms = [&](const uint8_t *host_vals, int count, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets,
+                            std::vector<uint8_t> &comms) -> int32_t {
+        comms.resize((size_t)count * 64);
+        for (int c = 0; c < count; c++) {
+            void *v, *p, *e;
+            SB_TRY(dalloc(pk, n * 32, &v));
+            SB_TRY(dalloc(pk, n * 32, &p));
+            SB_TRY(dalloc(pk, en * 32, &e));
+            SB_CUDA_TRY(cudaMemcpyAsync(v, host_vals + (size_t)c * n * 32, n * 32, cudaMemcpyHostToDevice, st));
+            SB_CUDA_TRY(cudaMemcpyAsync(p, v, n * 32, cudaMemcpyDeviceToDevice, st));
+            SB_TRY(dom_l2c(ctx, d, p, st));
+            SB_TRY(dom_c2e(ctx, d, p, e, st));
+            SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, v, n, comms.data() + (size_t)c * 64, st));
+            vals.push_back(v); polys.push_back(p); cosets.push_back(e);
+        }
+        return SB_OK;
+    };
+    SB_TRY(to_all_forms(fixed_values, pk->cs.F, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets, pk->fixed_comms));
+    SB_TRY(to_all_forms(sigma_values, pk->P, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets, pk->sigma_comms));
+    // l_0, l_last, l_blind (Lagrange unit vectors) -> extended; l_active = 1 - (l_last + l_blind)
+    const int bf = pk->cs.blinding;
+    std::vector<fr_t> tmp(n, fr_t::zero());
+    void *d_tmp, *d_lblind;
+    SB_TRY(scratch_get(ctx, "pk_tmp", n * 32, &d_tmp));
+    SB_TRY(scratch_get(ctx, "pk_lblind", en * 32, &d_lblind));
+    auto unit_ext = [&](const std::vector<size_t> &rows, void *d_ext) -> int32_t {
+        std::fill(tmp.begin(), tmp.end(), fr_t::zero());
+        for (size_t r : rows) tmp[r] = fr_t::one();
+        SB_CUDA_TRY(cudaMemcpyAsync(d_tmp, tmp.data(), n * 32, cudaMemcpyHostToDevice, st));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        SB_TRY(dom_l2c(ctx, d, d_tmp, st));
+        return dom_c2e(ctx, d, d_tmp, d_ext, st);
+    };
+    SB_TRY(dalloc(pk, en * 32, &pk->l0));
+    SB_TRY(dalloc(pk, en * 32, &pk->l_last));
+    SB_TRY(dalloc(pk, en * 32, &pk->l_active));
+    SB_TRY(unit_ext({0}, pk->l0));
+    SB_TRY(unit_ext({n - (size_t)bf - 1}, pk->l_last));
+    std::vector<size_t> blind_rows;
+    for (size_t r = n - (size_t)bf; r < n; r++) blind_rows.push_back(r);
+    SB_TRY(unit_ext(blind_rows, d_lblind));
+    {
+        std::vector<const void *> cols = {pk->l_last, d_lblind};
+        Program p = compile_terms({e_sub(e_const(fr_t::one()), e_add(e_col(0, 0), e_col(1, 0)))}, nullptr);
+        SB_TRY(expr_eval(ctx, p, cols, pk->ext_k, 0, pk->l_active, st));
+    }
+    // coset X column: zeta * ext_omega^i ; omega^i ; SHPLONK division helpers
+    SB_TRY(dalloc(pk, en * 32, &pk->x_coset));
+    SB_TRY(fr_gen_powers(ctx, pk->x_coset, d->ext_omega, en, st));
+    SB_TRY(fr_scale(ctx, pk->x_coset, en, d->coset[1], st));
+    SB_TRY(dalloc(pk, n * 32, &pk->omega_pows));
+    SB_TRY(fr_gen_powers(ctx, pk->omega_pows, d->omega, n, st));
+    SB_TRY(dalloc(pk, n * 32, &pk->div_g_pows));
+    SB_TRY(dalloc(pk, n * 32, &pk->div_x));
+    SB_TRY(dalloc(pk, n * 32, &pk->div_ginv_scaled));
+    SB_TRY(fr_gen_powers(ctx, pk->div_g_pows, to_dev(DIV_G), n, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(pk->div_x, pk->omega_pows, n * 32, cudaMemcpyDeviceToDevice, st));
+    SB_TRY(fr_scale(ctx, pk->div_x, n, to_dev(DIV_G), st));
+    SB_TRY(fr_gen_powers(ctx, pk->div_ginv_scaled, to_dev(hfr::inv(DIV_G)), n, st));
+    SB_TRY(fr_scale(ctx, pk->div_ginv_scaled, n, d->ifft_divisor, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+// q(X) = p(X) / prod (X - root): exact division through the coset g*H (p is overwritten by q, n coefficients)
+int32_t poly_div_by_roots_k(sb_ctx *ctx, uint32_t k, const fr_t &omega_d, const fr_t &omega_inv_d, const void *g_pows, const void *div_x, const void *ginv_scaled,
+                            void *d_p, const std::vector<Fr> &roots, cudaStream_t st) {
+    const size_t n = (size_t)1 << k;
+    void *d_den;
+    SB_TRY(scratch_get(ctx, "div_den", n * 32, &d_den));
+    SB_TRY(fp_vec_op(ctx, 0, 0, d_p, g_pows, d_p, n, st));
+    SB_TRY(ntt_run(ctx, d_p, (const uint8_t *)omega_d.v, k, st));
+    ExprP den = nullptr;
+    for (const Fr &r : roots) {
+        ExprP f = e_sub(e_col(0, 0), ec(r));
+        den = den ? e_mul(den, f) : f;
+    }
+    Program prog = compile_terms({den}, nullptr);
+    SB_TRY(expr_eval(ctx, prog, {div_x}, k, 0, d_den, st));
+    SB_TRY(fr_batch_invert(ctx, d_den, n, st));
+    SB_TRY(fp_vec_op(ctx, 0, 0, d_p, d_den, d_p, n, st));
+    SB_TRY(ntt_run(ctx, d_p, (const uint8_t *)omega_inv_d.v, k, st));
+    SB_TRY(fp_vec_op(ctx, 0, 0, d_p, ginv_scaled, d_p, n, st));
+    return SB_OK;
+}
+int32_t poly_div_by_roots(sb_ctx *ctx, const sb_pk *pk, void *d_p, const std::vector<Fr> &roots, cudaStream_t st) {
+    return poly_div_by_roots_k(ctx, pk->k, pk->dom->omega, pk->dom->omega_inv, pk->div_g_pows, pk->div_x, pk->div_ginv_scaled, d_p, roots, st);
+}
+
+int32_t upload_frs(void *d_dst, const std::vector<Fr> &v, cudaStream_t st) {
+    if (v.empty()) return SB_OK;
+    SB_CUDA_TRY(cudaMemcpyAsync(d_dst, v.data(), v.size() * 32, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+struct Query {
+    int poly_id;
+    Fr point;
+    const void *d_poly;
+    Fr eval;
+};
+
+int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, Transcript &tr, const std::vector<Query> &queries, cudaStream_t st) {
+    const size_t n = pk->n;
+    const Fr y = tr.squeeze();
+    // construct_intermediate_sets: first-appearance order of polynomials and of rotation sets,
+    // points inside a set in ascending field order
+    std::vector<int> poly_order;
+    std::map<int, std::set<Fr, FrLess>> poly_points;
+    std::map<int, const void *> polys;
+    std::set<Fr, FrLess> super_points;
+    auto find_eval = [&](int pid, const Fr &pt) -> Fr {
+        for (const Query &q : queries)
+            if (q.poly_id == pid && q.point == pt) return q.eval;
+        return hfr::ZERO;
+    };
+    for (const Query &q : queries) {
+        super_points.insert(q.point);
+        if (!poly_points.count(q.poly_id)) {
+            poly_order.push_back(q.poly_id);
+            polys[q.poly_id] = q.d_poly;
+        }
+        poly_points[q.poly_id].insert(q.point);
+    }
+    struct RSet { std::vector<Fr> pts; std::vector<int> members; };
+    std::vector<RSet> sets;
+    for (int pid : poly_order) {
+        std::vector<Fr> key(poly_points[pid].begin(), poly_points[pid].end());
+        bool found = false;
+        for (RSet &s : sets)
+            if (s.pts.size() == key.size() && std::equal(key.begin(), key.end(), s.pts.begin())) { s.members.push_back(pid); found = true; break; }
+        if (!found) sets.push_back({key, {pid}});
+    }
+    const Fr v = tr.squeeze();
+    void *d_hx, *d_nx, *d_lx;
+    SB_TRY(scratch_get(ctx, "sh_hx", n * 32, &d_hx));
+    SB_TRY(scratch_get(ctx, "sh_nx", n * 32, &d_nx));
+    SB_TRY(scratch_get(ctx, "sh_lx", n * 32, &d_lx));
+    std::vector<std::vector<std::vector<Fr>>> low(sets.size());
+    Fr v_pow = hfr::ONE;
+    for (size_t si = 0; si < sets.size(); si++) {
+        RSet &s = sets[si];
+        Fr y_pow = hfr::ONE;
+        std::vector<Fr> head(s.pts.size(), hfr::ZERO);
+        for (size_t mi = 0; mi < s.members.size(); mi++) {
+            const int pid = s.members[mi];
+            std::vector<Fr> evs;
+            for (const Fr &p : s.pts) evs.push_back(find_eval(pid, p));
+            std::vector<Fr> r = lagrange_interpolate(s.pts, evs);
+            low[si].push_back(r);
+            for (size_t i = 0; i < r.size(); i++) head[i] = hfr::add(head[i], hfr::mul(r[i], y_pow));
+            SB_TRY(fr_axpy(ctx, d_nx, polys[pid], to_dev(y_pow), n, mi == 0, st));
+            y_pow = hfr::mul(y_pow, y);
+        }
+        std::vector<fr_t> head_d;
+        for (const Fr &h : head) head_d.push_back(to_dev(h));
+        SB_TRY(fr_sub_head(ctx, d_nx, head_d.data(), (uint32_t)head_d.size(), st));
+        SB_TRY(poly_div_by_roots(ctx, pk, d_nx, s.pts, st));
+        SB_TRY(fr_axpy(ctx, d_hx, d_nx, to_dev(v_pow), n, si == 0, st));
+        v_pow = hfr::mul(v_pow, v);
+    }
+    uint8_t pt[64];
+    SB_TRY(msm_run(ctx, pk->srs->d_g, d_hx, n, pt, st));
+    if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
+    const Fr u = tr.squeeze();
+    std::vector<Fr> super(super_points.begin(), super_points.end());
+    std::vector<Fr> z_diffs;
+    v_pow = hfr::ONE;
+    Fr const_term = hfr::ZERO;
+    bool first = true;
+    for (size_t si = 0; si < sets.size(); si++) {
+        RSet &s = sets[si];
+        Fr z_i = hfr::ONE;
+        for (const Fr &p : super) {
+            bool in = false;
+            for (const Fr &q : s.pts) in = in || (q == p);
+            if (!in) z_i = hfr::mul(z_i, hfr::sub(u, p));
+        }
+        z_diffs.push_back(z_i);
+        Fr y_pow = hfr::ONE;
+        const Fr scale = hfr::mul(z_i, v_pow);
+        for (size_t mi = 0; mi < s.members.size(); mi++) {
+            const Fr coeff = hfr::mul(scale, y_pow);
+            SB_TRY(fr_axpy(ctx, d_lx, polys[s.members[mi]], to_dev(coeff), n, first, st));
+            first = false;
+            const_term = hfr::add(const_term, hfr::mul(coeff, eval_small(low[si][mi], u)));
+            y_pow = hfr::mul(y_pow, y);
+        }
+        v_pow = hfr::mul(v_pow, v);
+    }
+    Fr zt = hfr::ONE;
+    for (const Fr &p : super) zt = hfr::mul(zt, hfr::sub(u, p));
+    SB_TRY(fr_axpy(ctx, d_lx, d_hx, to_dev(hfr::neg(zt)), n, false, st));
+    fr_t ct = to_dev(const_term);
+    SB_TRY(fr_sub_head(ctx, d_lx, &ct, 1, st));
+    SB_TRY(poly_div_by_roots(ctx, pk, d_lx, {u}, st));
+    SB_TRY(fr_scale(ctx, d_lx, n, to_dev(hfr::inv(z_diffs[0])), st));
+    SB_TRY(msm_run(ctx, pk->srs->d_g, d_lx, n, pt, st));
+    if (!tr.write_point(pt)) { set_last_error("shplonk: opening commitment is the identity"); return SB_ERR_ARG; }
+    return SB_OK;
+}
+
+int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_inst, const uint8_t *advice_host, ChaCha20Rng &rng, Transcript &tr,
+                          cudaStream_t st) {
+    const ConstraintSystem &cs = pk->cs;
+    const sb_domain *d = pk->dom;
+    const size_t n = pk->n, en = pk->ext_n;
+    const int A = cs.A, F = cs.F, bf = cs.blinding, P = pk->P;
+    const size_t usable = n - (size_t)(bf + 1);
+    const uint32_t rs_log = pk->ext_k - pk->k;
+    SB_REQUIRE(n_inst <= usable, "create_proof: too many instance values");
+    const Fr omega = to_host(d->omega), omega_inv = to_host(d->omega_inv);
+    uint8_t pt[64];
+
+    // ---- transcript preamble
+    tr.common_scalar(pk->transcript_repr);
+    std::vector<Fr> inst(n_inst);
+    memcpy(inst.data(), instances, n_inst * 32);
+    for (const Fr &v : inst) tr.common_scalar(v);
+
+    // ---- device buffers of this proof
+    void *d_inst, *d_inst_poly, *d_inst_coset;
+    SB_TRY(scratch_get(ctx, "pf_inst", n * 32, &d_inst));
+    SB_TRY(scratch_get(ctx, "pf_inst_poly", n * 32, &d_inst_poly));
+    SB_TRY(scratch_get(ctx, "pf_inst_coset", en * 32, &d_inst_coset));
+    SB_CUDA_TRY(cudaMemsetAsync(d_inst, 0, n * 32, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(d_inst, inst.data(), n_inst * 32, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(d_inst_poly, d_inst, n * 32, cudaMemcpyDeviceToDevice, st));
+    SB_TRY(dom_l2c(ctx, d, d_inst_poly, st));
+    std::vector<void *> adv(A), adv_poly(A), adv_coset(A);
+    {
+        uint8_t *base_v, *base_p, *base_c;
+        SB_TRY(scratch_get(ctx, "pf_adv", (size_t)A * n * 32, (void **)&base_v));
+        SB_TRY(scratch_get(ctx, "pf_adv_poly", (size_t)A * n * 32, (void **)&base_p));
+        SB_TRY(scratch_get(ctx, "pf_adv_coset", (size_t)A * en * 32, (void **)&base_c));
+        for (int c = 0; c < A; c++) {
+            adv[c] = base_v + (size_t)c * n * 32;
+            adv_poly[c] = base_p + (size_t)c * n * 32;
+            adv_coset[c] = base_c + (size_t)c * en * 32;
+        }
+        SB_CUDA_TRY(cudaMemcpyAsync(base_v, advice_host, (size_t)A * n * 32, cudaMemcpyHostToDevice, st));
+    }
+    // blinding rows, blinds (drawn; KZG ignores them), commitments
+    for (int c = 0; c < A; c++) {
+        std::vector<Fr> blind(n - usable);
+        for (Fr &b : blind) b = rng.next_fr();
+        SB_TRY(upload_frs((uint8_t *)adv[c] + usable * 32, blind, st));
+    }
+    for (int c = 0; c < A; c++) (void)rng.next_fr();
+    for (int c = 0; c < A; c++) {
+        SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
+        SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
+    }
+    for (int c = 0; c < A; c++) {
+        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, adv[c], n, pt, st));
+        if (!tr.write_point(pt)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
+    }
+    const Fr theta = tr.squeeze();
+
+    // column tables.  Lagrange: advice | fixed | instance | sigma | omega^i | lookup scratch (4)
+    ColMap lm;
+    lm.advice0 = 0; lm.fixed0 = A; lm.instance0 = A + F;
+    const int L_SIGMA = A + F + 1, L_OMEGA = L_SIGMA + P, L_LK = L_OMEGA + 1;
+    std::vector<const void *> lcols(L_LK + 4, nullptr);
+    for (int c = 0; c < A; c++) lcols[c] = adv[c];
+    for (int c = 0; c < F; c++) lcols[A + c] = pk->fixed_values[c];
+    lcols[A + F] = d_inst;
+    for (int j = 0; j < P; j++) lcols[L_SIGMA + j] = pk->sigma_values[j];
+    lcols[L_OMEGA] = pk->omega_pows;
+
+    // ---- lookups: compress, permute, commit
+    struct LookupState { void *c_in, *c_tab, *p_in, *p_tab, *in_poly, *tab_poly, *z_poly, *z_coset, *in_coset, *tab_coset; };
+    std::vector<LookupState> lks(cs.lookups.size());
+    for (size_t li = 0; li < cs.lookups.size(); li++) {
+        LookupState &L = lks[li];
+        uint8_t *b;
+        SB_TRY(scratch_get(ctx, ("pf_lk" + std::to_string(li)).c_str(), 7 * n * 32 + 3 * en * 32, (void **)&b));
+        L.c_in = b; L.c_tab = b + n * 32; L.p_in = b + 2 * n * 32; L.p_tab = b + 3 * n * 32;
+        L.in_poly = b + 4 * n * 32; L.tab_poly = b + 5 * n * 32; L.z_poly = b + 6 * n * 32;
+        L.z_coset = b + 7 * n * 32; L.in_coset = (uint8_t *)L.z_coset + en * 32; L.tab_coset = (uint8_t *)L.in_coset + en * 32;
+        std::vector<ExprP> in_terms, tab_terms;
+        for (auto &e : cs.lookups[li].input) in_terms.push_back(bind_expr(*e, lm));
+        for (auto &e : cs.lookups[li].table) tab_terms.push_back(bind_expr(*e, lm));
+        fr_t th = to_dev(theta);
+        SB_TRY(expr_eval(ctx, compile_terms(in_terms, &th), lcols, pk->k, 0, L.c_in, st));
+        SB_TRY(expr_eval(ctx, compile_terms(tab_terms, &th), lcols, pk->k, 0, L.c_tab, st));
+        int32_t rc = lookup_permute(ctx, L.c_in, L.c_tab, n, usable, L.p_in, L.p_tab, st);
+        if (rc != SB_OK) return rc;
+        std::vector<Fr> blind(n - usable);
+        for (Fr &x : blind) x = rng.next_fr();
+        SB_TRY(upload_frs((uint8_t *)L.p_in + usable * 32, blind, st));
+        for (Fr &x : blind) x = rng.next_fr();
+        SB_TRY(upload_frs((uint8_t *)L.p_tab + usable * 32, blind, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(L.in_poly, L.p_in, n * 32, cudaMemcpyDeviceToDevice, st));
+        SB_TRY(dom_l2c(ctx, d, L.in_poly, st));
+        (void)rng.next_fr();
+        uint8_t pin[64], ptab[64];
+        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, L.p_in, n, pin, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
+        SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
+        (void)rng.next_fr();
+        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, L.p_tab, n, ptab, st));
+        if (!tr.write_point(pin) || !tr.write_point(ptab)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
+    }
+    const Fr beta = tr.squeeze();
+    const Fr gamma = tr.squeeze();
+
+    // ---- permutation argument
+    const int chunk = cs.degree - 2;
+    const int n_sets = (P + chunk - 1) / chunk;
+    struct PermSet { void *z_poly, *z_coset; int first, count; };
+    std::vector<PermSet> psets(n_sets);
+    {
+        void *d_den, *d_num, *d_z;
+        SB_TRY(scratch_get(ctx, "pf_perm_den", n * 32, &d_den));
+        SB_TRY(scratch_get(ctx, "pf_perm_num", n * 32, &d_num));
+        SB_TRY(scratch_get(ctx, "pf_perm_z", n * 32, &d_z));
+        uint8_t *zb;
+        SB_TRY(scratch_get(ctx, "pf_perm_polys", (size_t)n_sets * (n + en) * 32, (void **)&zb));
+        Fr delta_pow = hfr::ONE;
+        const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+        Fr last_z = hfr::ONE;
+        for (int s = 0; s < n_sets; s++) {
+            PermSet &S = psets[s];
+            S.first = s * chunk;
+            S.count = std::min(chunk, P - S.first);
+            S.z_poly = zb + (size_t)s * (n + en) * 32;
+            S.z_coset = (uint8_t *)S.z_poly + n * 32;
+            ExprP den = nullptr, num = nullptr;
+            for (int j = 0; j < S.count; j++) {
+                const auto &pc = cs.perm_cols[S.first + j];
+                ExprP val = e_col(lm.col(pc.first, pc.second), 0);
+                ExprP dterm = e_add(e_add(e_mul(ec(beta), e_col(L_SIGMA + S.first + j, 0)), ec(gamma)), val);
+                ExprP nterm = e_add(e_add(e_mul(ec(hfr::mul(delta_pow, beta)), e_col(L_OMEGA, 0)), ec(gamma)), val);
+                den = den ? e_mul(den, dterm) : dterm;
+                num = num ? e_mul(num, nterm) : nterm;
+                delta_pow = hfr::mul(delta_pow, DELTA);
+            }
+            SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den, st));
+            SB_TRY(expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num, st));
+            SB_TRY(fr_batch_invert(ctx, d_den, n, st));
+            SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, n, st));
+            SB_TRY(fr_running_product(ctx, d_den, n, to_dev(last_z), d_z, n, st));
+            std::vector<Fr> blind(bf);
+            for (Fr &x : blind) x = rng.next_fr();
+            SB_TRY(upload_frs((uint8_t *)d_z + (n - bf) * 32, blind, st));
+            Fr lz;
+            SB_CUDA_TRY(cudaMemcpyAsync(&lz, (uint8_t *)d_z + (n - (size_t)bf - 1) * 32, 32, cudaMemcpyDeviceToHost, st));
+            SB_CUDA_TRY(cudaStreamSynchronize(st));
+            last_z = lz;
+            (void)rng.next_fr();
+            SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, d_z, n, pt, st));
+            SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
+            SB_TRY(dom_l2c(ctx, d, S.z_poly, st));
+            SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st));
+            if (!tr.write_point(pt)) { set_last_error("permutation product commitment is the identity"); return SB_ERR_ARG; }
+        }
+    }
+
+    // ---- lookup products
+    for (size_t li = 0; li < lks.size(); li++) {
+        LookupState &L = lks[li];
+        void *d_den, *d_num, *d_z;
+        SB_TRY(scratch_get(ctx, "pf_perm_den", n * 32, &d_den));
+        SB_TRY(scratch_get(ctx, "pf_perm_num", n * 32, &d_num));
+        SB_TRY(scratch_get(ctx, "pf_perm_z", n * 32, &d_z));
+        lcols[L_LK + 0] = L.c_in; lcols[L_LK + 1] = L.c_tab; lcols[L_LK + 2] = L.p_in; lcols[L_LK + 3] = L.p_tab;
+        ExprP den = e_mul(e_add(e_col(L_LK + 2, 0), ec(beta)), e_add(e_col(L_LK + 3, 0), ec(gamma)));
+        ExprP num = e_mul(e_add(e_col(L_LK + 0, 0), ec(beta)), e_add(e_col(L_LK + 1, 0), ec(gamma)));
+        SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den, st));
+        SB_TRY(expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num, st));
+        SB_TRY(fr_batch_invert(ctx, d_den, n, st));
+        SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, n, st));
+        SB_TRY(fr_running_product(ctx, d_den, n, fr_t::one(), d_z, n, st));
+        std::vector<Fr> blind(bf);
+        for (Fr &x : blind) x = rng.next_fr();
+        SB_TRY(upload_frs((uint8_t *)d_z + (n - bf) * 32, blind, st));
+        (void)rng.next_fr();
+        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, d_z, n, pt, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
+        SB_TRY(dom_l2c(ctx, d, L.z_poly, st));
+        if (!tr.write_point(pt)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
+    }
+
+    // ---- vanishing argument: random polynomial from a child ChaCha20 stream (1-thread case of the fork)
+    void *d_random;
+    SB_TRY(scratch_get(ctx, "pf_random", n * 32, &d_random));
+    {
+        uint8_t seed[32];
+        rng.fill_bytes(seed, 32);
+        ChaCha20Rng child;
+        child.seed(seed);
+        std::vector<Fr> rp(n);
+        for (Fr &x : rp) x = child.next_fr();
+        SB_TRY(upload_frs(d_random, rp, st));
+        (void)rng.next_fr();
+        SB_TRY(msm_run(ctx, pk->srs->d_g, d_random, n, pt, st));
+        if (!tr.write_point(pt)) { set_last_error("random polynomial commitment is the identity"); return SB_ERR_ARG; }
+    }
+    const Fr yy = tr.squeeze();
+
+    // ---- evaluate_h: one fused program over the extended coset
+    for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st));
+    SB_TRY(dom_c2e(ctx, d, d_inst_poly, d_inst_coset, st));
+    for (LookupState &L : lks) {
+        SB_TRY(dom_c2e(ctx, d, L.z_poly, L.z_coset, st));
+        SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st));
+        SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st));
+    }
+    ColMap em;
+    em.advice0 = 0; em.fixed0 = A; em.instance0 = A + F;
+    const int E_SIGMA = A + F + 1, E_PZ = E_SIGMA + P, E_L0 = E_PZ + n_sets, E_LLAST = E_L0 + 1, E_LACT = E_L0 + 2, E_X = E_L0 + 3, E_LK = E_L0 + 4;
+    std::vector<const void *> ecols(E_LK + 3 * lks.size(), nullptr);
+    for (int c = 0; c < A; c++) ecols[c] = adv_coset[c];
+    for (int c = 0; c < F; c++) ecols[A + c] = pk->fixed_cosets[c];
+    ecols[A + F] = d_inst_coset;
+    for (int j = 0; j < P; j++) ecols[E_SIGMA + j] = pk->sigma_cosets[j];
+    for (int s = 0; s < n_sets; s++) ecols[E_PZ + s] = psets[s].z_coset;
+    ecols[E_L0] = pk->l0; ecols[E_LLAST] = pk->l_last; ecols[E_LACT] = pk->l_active; ecols[E_X] = pk->x_coset;
+    for (size_t li = 0; li < lks.size(); li++) {
+        ecols[E_LK + 3 * li] = lks[li].z_coset;
+        ecols[E_LK + 3 * li + 1] = lks[li].in_coset;
+        ecols[E_LK + 3 * li + 2] = lks[li].tab_coset;
+    }
+    std::vector<ExprP> terms;
+    for (auto &g : cs.gates) terms.push_back(bind_expr(*g, em));
+    const ExprP one = e_const(fr_t::one());
+    const ExprP l0 = e_col(E_L0, 0), llast = e_col(E_LLAST, 0), lact = e_col(E_LACT, 0);
+    if (n_sets > 0) {
+        auto Z = [&](int s, int r) { return e_col(E_PZ + s, r); };
+        terms.push_back(e_mul(e_sub(one, Z(0, 0)), l0));
+        terms.push_back(e_mul(e_sub(e_mul(Z(n_sets - 1, 0), Z(n_sets - 1, 0)), Z(n_sets - 1, 0)), llast));
+        for (int s = 1; s < n_sets; s++) terms.push_back(e_mul(e_sub(Z(s, 0), Z(s - 1, -(bf + 1))), l0));
+        Fr cur_delta = hfr::ONE;
+        const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+        for (int s = 0; s < n_sets; s++) {
+            ExprP left = Z(s, 1), right = Z(s, 0);
+            for (int j = 0; j < psets[s].count; j++) {
+                const auto &pc = cs.perm_cols[psets[s].first + j];
+                ExprP val = e_col(em.col(pc.first, pc.second), 0);
+                left = e_mul(left, e_add(e_add(val, e_mul(ec(beta), e_col(E_SIGMA + psets[s].first + j, 0))), ec(gamma)));
+                right = e_mul(right, e_add(e_add(val, e_mul(ec(hfr::mul(cur_delta, beta)), e_col(E_X, 0))), ec(gamma)));
+                cur_delta = hfr::mul(cur_delta, DELTA);
+            }
+            terms.push_back(e_mul(e_sub(left, right), lact));
+        }
+    }
+    for (size_t li = 0; li < lks.size(); li++) {
+        ExprP z0 = e_col(E_LK + 3 * li, 0), z1 = e_col(E_LK + 3 * li, 1);
+        ExprP a0 = e_col(E_LK + 3 * li + 1, 0), am1 = e_col(E_LK + 3 * li + 1, -1), s0 = e_col(E_LK + 3 * li + 2, 0);
+        auto compress = [&](const std::vector<json::ValueP> &exprs) {
+            ExprP acc = nullptr;
+            for (auto &e : exprs) {
+                ExprP b = bind_expr(*e, em);
+                acc = acc ? e_add(e_mul(acc, ec(theta)), b) : b;
+            }
+            return acc;
+        };
+        ExprP cin = compress(cs.lookups[li].input), ctab = compress(cs.lookups[li].table);
+        ExprP a_minus_s = e_sub(a0, s0);
+        terms.push_back(e_mul(e_sub(one, z0), l0));
+        terms.push_back(e_mul(e_sub(e_mul(z0, z0), z0), llast));
+        terms.push_back(e_mul(e_sub(e_mul(z1, e_mul(e_add(a0, ec(beta)), e_add(s0, ec(gamma)))), e_mul(z0, e_mul(e_add(cin, ec(beta)), e_add(ctab, ec(gamma))))), lact));
+        terms.push_back(e_mul(a_minus_s, l0));
+        terms.push_back(e_mul(e_mul(a_minus_s, e_sub(a0, am1)), lact));
+    }
+    void *d_h;
+    SB_TRY(scratch_get(ctx, "pf_h", en * 32, &d_h));
+    {
+        fr_t yd = to_dev(yy);
+        Program hp = compile_terms(terms, &yd);
+        ctx->last_h_program[0] = (uint32_t)(hp.code.size() / 3);
+        ctx->last_h_program[1] = hp.n_mul;
+        ctx->last_h_program[2] = hp.n_addsub;
+        ctx->last_h_program[3] = hp.n_slots;
+        cudaEvent_t e0, e1;
+        SB_CUDA_TRY(cudaEventCreate(&e0));
+        SB_CUDA_TRY(cudaEventCreate(&e1));
+        SB_CUDA_TRY(cudaEventRecord(e0, st));
+        SB_TRY(expr_eval(ctx, hp, ecols, pk->ext_k, rs_log, d_h, st));
+        SB_CUDA_TRY(cudaEventRecord(e1, st));
+        SB_CUDA_TRY(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&ctx->last_h_ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    // ---- quotient: / t(X), back to coefficients, pieces
+    SB_TRY(dom_div_vanishing(ctx, d, d_h, st));
+    SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
+    const int n_pieces = cs.degree - 1;
+    for (int i = 0; i < n_pieces; i++) (void)rng.next_fr();
+    for (int i = 0; i < n_pieces; i++) {
+        SB_TRY(msm_run(ctx, pk->srs->d_g, (uint8_t *)d_h + (size_t)i * n * 32, n, pt, st));
+        if (!tr.write_point(pt)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
+    }
+    const Fr x = tr.squeeze();
+    const Fr xn = fpow(x, (uint64_t)n);
+    // h(X) folded at x^n
+    void *d_hfold;
+    SB_TRY(scratch_get(ctx, "pf_hfold", n * 32, &d_hfold));
+    {
+        Fr p = hfr::ONE;
+        for (int i = 0; i < n_pieces; i++) {
+            SB_TRY(fr_axpy(ctx, d_hfold, (uint8_t *)d_h + (size_t)i * n * 32, to_dev(p), n, i == 0, st));
+            p = hfr::mul(p, xn);
+        }
+    }
+
+    // ---- evaluations (SURVEY A.5 order), one batched kernel
+    const Fr x_next = rotate(x, omega, omega_inv, 1), x_prev = rotate(x, omega, omega_inv, -1), x_last = rotate(x, omega, omega_inv, -(bf + 1));
+    std::vector<const void *> ev_polys;
+    std::vector<fr_t> ev_pts;
+    auto want = [&](const void *p, const Fr &at) { ev_polys.push_back(p); ev_pts.push_back(to_dev(at)); return (int)ev_polys.size() - 1; };
+    std::vector<int> i_adv, i_fix, i_sig;
+    for (auto &q : cs.advice_q) i_adv.push_back(want(adv_poly[q.first], rotate(x, omega, omega_inv, q.second)));
+    for (auto &q : cs.fixed_q) i_fix.push_back(want(pk->fixed_polys[q.first], rotate(x, omega, omega_inv, q.second)));
+    const int i_rand = want(d_random, x);
+    for (int j = 0; j < P; j++) i_sig.push_back(want(pk->sigma_polys[j], x));
+    std::vector<std::vector<int>> i_perm(n_sets);
+    for (int s = 0; s < n_sets; s++) {
+        i_perm[s].push_back(want(psets[s].z_poly, x));
+        i_perm[s].push_back(want(psets[s].z_poly, x_next));
+        if (s != n_sets - 1) i_perm[s].push_back(want(psets[s].z_poly, x_last));
+    }
+    std::vector<std::vector<int>> i_lk(lks.size());
+    for (size_t li = 0; li < lks.size(); li++) {
+        i_lk[li] = {want(lks[li].z_poly, x), want(lks[li].z_poly, x_next), want(lks[li].in_poly, x), want(lks[li].in_poly, x_prev), want(lks[li].tab_poly, x)};
+    }
+    const int i_h = want(d_hfold, x);
+    std::vector<fr_t> evd;
+    SB_TRY(fr_eval_polys(ctx, ev_polys, ev_pts, n, evd, st));
+    std::vector<Fr> ev(evd.size());
+    for (size_t i = 0; i < evd.size(); i++) ev[i] = to_host(evd[i]);
+    for (int i : i_adv) tr.write_scalar(ev[i]);
+    for (int i : i_fix) tr.write_scalar(ev[i]);
+    tr.write_scalar(ev[i_rand]);
+    for (int i : i_sig) tr.write_scalar(ev[i]);
+    for (int s = 0; s < n_sets; s++)
+        for (int i : i_perm[s]) tr.write_scalar(ev[i]);
+    for (size_t li = 0; li < lks.size(); li++)
+        for (int i : i_lk[li]) tr.write_scalar(ev[i]);
+
+    // ---- multi-open queries in halo2's order
+    std::vector<Query> q;
+    int next_id = 0;
+    std::map<const void *, int> ids;
+    auto pid = [&](const void *p) { auto it = ids.find(p); if (it != ids.end()) return it->second; return ids[p] = next_id++; };
+    for (size_t i = 0; i < cs.advice_q.size(); i++) {
+        const void *p = adv_poly[cs.advice_q[i].first];
+        q.push_back({pid(p), rotate(x, omega, omega_inv, cs.advice_q[i].second), p, ev[i_adv[i]]});
+    }
+    for (int s = 0; s < n_sets; s++) {
+        q.push_back({pid(psets[s].z_poly), x, psets[s].z_poly, ev[i_perm[s][0]]});
+        q.push_back({pid(psets[s].z_poly), x_next, psets[s].z_poly, ev[i_perm[s][1]]});
+    }
+    for (int s = n_sets - 2; s >= 0; s--) q.push_back({pid(psets[s].z_poly), x_last, psets[s].z_poly, ev[i_perm[s][2]]});
+    for (size_t li = 0; li < lks.size(); li++) {
+        const LookupState &L = lks[li];
+        q.push_back({pid(L.z_poly), x, L.z_poly, ev[i_lk[li][0]]});
+        q.push_back({pid(L.in_poly), x, L.in_poly, ev[i_lk[li][2]]});
+        q.push_back({pid(L.tab_poly), x, L.tab_poly, ev[i_lk[li][4]]});
+        q.push_back({pid(L.in_poly), x_prev, L.in_poly, ev[i_lk[li][3]]});
+        q.push_back({pid(L.z_poly), x_next, L.z_poly, ev[i_lk[li][1]]});
+    }
+    for (size_t i = 0; i < cs.fixed_q.size(); i++) {
+        const void *p = pk->fixed_polys[cs.fixed_q[i].first];
+        q.push_back({pid(p), rotate(x, omega, omega_inv, cs.fixed_q[i].second), p, ev[i_fix[i]]});
+    }
+    for (int j = 0; j < P; j++) q.push_back({pid(pk->sigma_polys[j]), x, pk->sigma_polys[j], ev[i_sig[j]]});
+    q.push_back({pid(d_hfold), x, d_hfold, ev[i_h]});
+    q.push_back({pid(d_random), x, d_random, ev[i_rand]});
+    return shplonk(ctx, pk, tr, q, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
+                     const uint8_t transcript_repr[32], sb_pk **out_pk) {
+    if (!ctx || !srs || !cs_json || !fixed_values || !sigma_values || !transcript_repr || !out_pk) return SB_ERR_ARG;
+    SB_REQUIRE(srs->k == k, "sb_pk_create: SRS size does not match k (downsize first)");
+    CtxGuard g(ctx);
+    sb_pk *pk = new sb_pk();
+    try {
+        pk->cs = parse_cs(cs_json);
+    } catch (const std::exception &e) {
+        set_last_error("sb_pk_create: %s", e.what());
+        delete pk;
+        return SB_ERR_ARG;
+    }
+    pk->srs = srs;
+    pk->k = k;
+    pk->n = (size_t)1 << k;
+    pk->P = (int)pk->cs.perm_cols.size();
+    memcpy(pk->transcript_repr.v, transcript_repr, 32);
+    int32_t rc = sb_domain_create(ctx, (uint32_t)pk->cs.degree, k, &pk->dom);
+    if (rc != SB_OK) { delete pk; return rc; }
+    pk->ext_k = pk->dom->ext_k;
+    pk->ext_n = (size_t)1 << pk->ext_k;
+    if (pk->n < 128) { set_last_error("sb_pk_create: k < 7 is not supported"); sb_domain_destroy(pk->dom); delete pk; return SB_ERR_ARG; }
+    try {
+        rc = pk_build(ctx, pk, fixed_values, sigma_values, ctx->stream);
+    } catch (const std::exception &e) {
+        set_last_error("sb_pk_create: %s", e.what());
+        rc = SB_ERR_ARG;
+    }
+    if (rc != SB_OK) {
+        for (void *p : pk->owned) cudaFree(p);
+        sb_domain_destroy(pk->dom);
+        delete pk;
+        return rc;
+    }
+    *out_pk = pk;
+    return SB_OK;
+}
+
+int32_t sb_pk_destroy(sb_pk *pk) {
+    if (!pk) return SB_OK;
+    for (void *p : pk->owned) cudaFree(p);
+    sb_domain_destroy(pk->dom);
+    delete pk;
+    return SB_OK;
+}
+
+int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_comms) {
+    if (!pk || !fixed_comms || !sigma_comms) return SB_ERR_ARG;
+    memcpy(fixed_comms, pk->fixed_comms.data(), pk->fixed_comms.size());
+    memcpy(sigma_comms, pk->sigma_comms.data(), pk->sigma_comms.size());
+    return SB_OK;
+}
+
+int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
+                        int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    if (!ctx || !pk || !advice || !rng_seed || !proof_out || !proof_len || (n_instances && !instances)) return SB_ERR_ARG;
+    SB_REQUIRE(transcript_kind == 0 || transcript_kind == 1, "transcript_kind must be 0 (Blake2b) or 1 (Keccak256/EVM)");
+    CtxGuard g(ctx);
+    ChaCha20Rng rng;
+    rng.seed(rng_seed);
+    KeccakTranscript kt;
+    Blake2bTranscript bt;
+    Transcript &tr = transcript_kind == 1 ? (Transcript &)kt : (Transcript &)bt;
+    int32_t rc;
+    try {
+        rc = create_proof_impl(ctx, pk, instances, n_instances, advice, rng, tr, ctx->stream);
+    } catch (const std::exception &e) {
+        set_last_error("sb_create_proof: %s", e.what());
+        return SB_ERR_ARG;
+    }
+    if (rc != SB_OK) return rc;
+    *proof_len = tr.proof.size();
+    SB_REQUIRE(tr.proof.size() <= proof_cap, "sb_create_proof: output buffer too small");
+    memcpy(proof_out, tr.proof.data(), tr.proof.size());
+    return SB_OK;
+}
+
+// ---- building blocks with host buffers (sb_batch_invert, sb_grand_product, sb_sort_fr, sb_eval_poly, sb_kate_div)
+int32_t sb_fr_batch_invert(sb_ctx *ctx, uint8_t *a, size_t n) {
+    if (!ctx || (n && !a)) return SB_ERR_ARG;
+    CtxGuard g(ctx);
+    void *d;
+    SB_TRY(scratch_get(ctx, "bb_a", n * 32, &d));
+    SB_CUDA_TRY(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(fr_batch_invert(ctx, d, n, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(a, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+int32_t sb_fr_running_product(sb_ctx *ctx, const uint8_t *a, size_t n_a, const uint8_t init[32], uint8_t *z, size_t n_z) {
+    if (!ctx || !init || (n_a && !a) || (n_z && !z)) return SB_ERR_ARG;
+    CtxGuard g(ctx);
+    void *da, *dz;
+    SB_TRY(scratch_get(ctx, "bb_a", (n_a + 1) * 32, &da));
+    SB_TRY(scratch_get(ctx, "bb_b", (n_z + 1) * 32, &dz));
+    SB_CUDA_TRY(cudaMemcpyAsync(da, a, n_a * 32, cudaMemcpyHostToDevice, ctx->stream));
+    fr_t i0;
+    memcpy(i0.v, init, 32);
+    SB_TRY(fr_running_product(ctx, da, n_a, i0, dz, n_z, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(z, dz, n_z * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+int32_t sb_fr_eval_polynomial(sb_ctx *ctx, const uint8_t *coeffs, size_t n, const uint8_t *points, size_t n_points, uint8_t *out) {
+    if (!ctx || !coeffs || !points || !out) return SB_ERR_ARG;
+    CtxGuard g(ctx);
+    void *d;
+    SB_TRY(scratch_get(ctx, "bb_a", n * 32, &d));
+    SB_CUDA_TRY(cudaMemcpyAsync(d, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<const void *> polys(n_points, d);
+    std::vector<fr_t> xs(n_points), res;
+    memcpy(xs.data(), points, n_points * 32);
+    SB_TRY(fr_eval_polys(ctx, polys, xs, n, res, ctx->stream));
+    memcpy(out, res.data(), n_points * 32);
+    return SB_OK;
+}
+int32_t sb_fr_sort(sb_ctx *ctx, uint8_t *a, size_t n) {
+    if (!ctx || (n && !a)) return SB_ERR_ARG;
+    CtxGuard g(ctx);
+    size_t N = 1;
+    while (N < n) N <<= 1;
+    void *d, *d2;
+    SB_TRY(scratch_get(ctx, "bb_a", N * 32, &d));
+    SB_TRY(scratch_get(ctx, "bb_b", N * 32, &d2));
+    SB_CUDA_TRY(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // canonical form for the comparison (halo2curves `Ord`), back to Montgomery afterwards: x * 1 and x * R^2
+    fr_t one_c = fr_t::zero();
+    one_c.v[0] = 1;
+    SB_TRY(fr_scale(ctx, d, n, one_c, ctx->stream));
+    SB_TRY(sort_u256(ctx, d, n, N, ctx->stream));
+    SB_TRY(fr_scale(ctx, d, n, fr_t::r2(), ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(a, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    (void)d2;
+    return SB_OK;
+}
+int32_t sb_lookup_permute(sb_ctx *ctx, const uint8_t *input, const uint8_t *table, size_t n, size_t usable, uint8_t *permuted_input, uint8_t *permuted_table) {
+    if (!ctx || !input || !table || !permuted_input || !permuted_table || usable > n) return SB_ERR_ARG;
+    CtxGuard g(ctx);
+    void *di, *dt, *dpi, *dpt;
+    SB_TRY(scratch_get(ctx, "bb_a", n * 32, &di));
+    SB_TRY(scratch_get(ctx, "bb_b", n * 32, &dt));
+    SB_TRY(scratch_get(ctx, "bb_c", n * 32, &dpi));
+    SB_TRY(scratch_get(ctx, "bb_d", n * 32, &dpt));
+    SB_CUDA_TRY(cudaMemcpyAsync(di, input, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(dt, table, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(lookup_permute(ctx, di, dt, n, usable, dpi, dpt, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(permuted_input, dpi, usable * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(permuted_table, dpt, usable * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+// halo2 `kate_division(a, b)`: q = (a - a(b)) / (X - b); n = 2^log_n coefficients in, n - 1 out (out has n slots, top = 0)
+int32_t sb_kate_division(sb_ctx *ctx, const uint8_t *a, uint32_t log_n, const uint8_t b[32], uint8_t *q) {
+    if (!ctx || !a || !b || !q) return SB_ERR_ARG;
+    SB_REQUIRE(log_n >= 7 && log_n <= 28, "sb_kate_division: log_n must be in [7, 28]");
+    CtxGuard g(ctx);
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)1 << log_n;
+    void *dp, *dg, *dx, *dgi;
+    SB_TRY(scratch_get(ctx, "bb_a", n * 32, &dp));
+    SB_TRY(scratch_get(ctx, "bb_b", n * 32, &dg));
+    SB_TRY(scratch_get(ctx, "bb_c", n * 32, &dx));
+    SB_TRY(scratch_get(ctx, "bb_d", n * 32, &dgi));
+    SB_CUDA_TRY(cudaMemcpyAsync(dp, a, n * 32, cudaMemcpyHostToDevice, st));
+    sb_domain *dom = nullptr;
+    SB_TRY(sb_domain_create(ctx, 2, log_n, &dom));
+    fr_t bd;
+    memcpy(bd.v, b, 32);
+    std::vector<const void *> polys(1, dp);
+    std::vector<fr_t> xs(1, bd), res;
+    SB_TRY(fr_eval_polys(ctx, polys, xs, n, res, st));
+    SB_TRY(fr_sub_head(ctx, dp, res.data(), 1, st));
+    SB_TRY(fr_gen_powers(ctx, dg, to_dev(DIV_G), n, st));
+    SB_TRY(fr_gen_powers(ctx, dx, dom->omega, n, st));
+    SB_TRY(fr_scale(ctx, dx, n, to_dev(DIV_G), st));
+    SB_TRY(fr_gen_powers(ctx, dgi, to_dev(hfr::inv(DIV_G)), n, st));
+    SB_TRY(fr_scale(ctx, dgi, n, dom->ifft_divisor, st));
+    int32_t rc = poly_div_by_roots_k(ctx, log_n, dom->omega, dom->omega_inv, dg, dx, dgi, dp, {to_host(bd)}, st);
+    sb_domain_destroy(dom);
+    if (rc != SB_OK) return rc;
+    SB_CUDA_TRY(cudaMemcpyAsync(q, dp, n * 32, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]) {
+    if (!ctx || !out_ms || !out_program) return SB_ERR_ARG;
+    *out_ms = ctx->last_h_ms;
+    for (int i = 0; i < 4; i++) out_program[i] = ctx->last_h_program[i];
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// Internal interfaces of the create_proof pipeline (prover_kernels.cu, expr.cu, prover.cu).
+#pragma once
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "hostfr.h"
+
+namespace sb {
+
+// ---- prover_kernels.cu ------------------------------------------------------------------
+int32_t fr_batch_invert(sb_ctx *ctx, void *d_a, size_t n, cudaStream_t st);
+int32_t fr_running_product(sb_ctx *ctx, const void *d_a, size_t n_a, const fr_t &init, void *d_z, size_t n_z, cudaStream_t st);
+int32_t fr_eval_polys(sb_ctx *ctx, const std::vector<const void *> &polys, const std::vector<fr_t> &xs, size_t n, std::vector<fr_t> &out, cudaStream_t st);
+int32_t sort_u256(sb_ctx *ctx, void *d_a, size_t count, size_t capacity_pow2, cudaStream_t st);
+int32_t lookup_permute(sb_ctx *ctx, const void *d_in, const void *d_tab, size_t n, size_t u, void *d_a_perm, void *d_s_perm, cudaStream_t st);
+int32_t fr_axpy(sb_ctx *ctx, void *d_acc, const void *d_p, const fr_t &s, size_t n, bool first, cudaStream_t st);
+int32_t fr_sub_head(sb_ctx *ctx, void *d_acc, const fr_t *c, uint32_t k, cudaStream_t st);
+
+// ---- expr.cu: expression DAGs compiled to a register program, evaluated over whole columns ---
+struct Expr;
+typedef std::shared_ptr<Expr> ExprP;
+struct Expr {
+    enum Kind { CONST, COL, NEG, ADD, SUB, MUL } kind;
+    fr_t c;        // CONST
+    int col, rot;  // COL: index into the column-pointer table, row rotation
+    ExprP a, b;
+};
+ExprP e_const(const fr_t &c);
+ExprP e_col(int col, int rot);
+ExprP e_neg(ExprP a);
+ExprP e_add(ExprP a, ExprP b);
+ExprP e_sub(ExprP a, ExprP b);
+ExprP e_mul(ExprP a, ExprP b);
+
+struct Program {
+    std::vector<uint32_t> code;    // 3 words per instruction: (op << 16 | dst), operand a, operand b
+    std::vector<fr_t> consts;
+    std::vector<int32_t> inputs;   // (col, rot) pairs
+    uint32_t n_slots = 0;
+    uint32_t out_slot = 0;
+    uint32_t n_mul = 0, n_addsub = 0;
+};
+// terms folded Horner-style: acc = acc * fold + term (fold == nullptr: a single term, no folding)
+Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold);
+// out[i] = program(columns at row i) for i < 2^log_n; rotations move by rot << rot_scale_log rows (cyclic)
+int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st);
+
+inline fr_t to_dev(const hfr::Fr &x) { fr_t r; memcpy(r.v, x.v, 32); return r; }
+inline hfr::Fr to_host(const fr_t &x) { hfr::Fr r; memcpy(r.v, x.v, 32); return r; }
+
+}  // namespace sb

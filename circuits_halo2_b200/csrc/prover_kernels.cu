@@ -1,0 +1,478 @@
+// O(n) / O(n log n) building blocks of halo2 `create_proof` that sit between the MSMs and NTTs
+// (kernels K6-K8):
+//   fr_batch_invert      halo2 `batch_invert` (zeros stay zero)          -- permutation / lookup denominators
+//   fr_running_product   z[0] = init, z[i] = z[i-1] * a[i-1]             -- grand-product columns Z
+//   fr_eval_polys        halo2 `eval_polynomial` for many (poly, point)   -- the 35 openings + h(x)
+//   fr_sort_canonical    bitonic sort by canonical value (Fr `Ord`)       -- lookup permuted columns
+//   lookup_permute       halo2 `permute_expression_pair`
+//   fr_axpy / fr_sub_head linear combinations of coefficient vectors      -- SHPLONK numerators
+// All operate on device arrays of 32-byte Montgomery elements; grids are sized to the data, one
+// contiguous chunk per thread where a recurrence is involved (HBM-streaming, no atomics).
+#include "common.cuh"
+#include "prover.h"
+
+namespace sb {
+
+// ------------------------------------------------------------------ u32 exclusive scan (flags -> positions)
+static const int PSCAN_ITEMS = 8, PSCAN_THREADS = 256, PSCAN_TILE = PSCAN_ITEMS * PSCAN_THREADS;
+
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+        uint32_t wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += t;
+        }
+        warp_sums[lane] = wi - ws;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    uint32_t r = incl - v + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(PSCAN_THREADS) pscan_tile_sums(const uint32_t *in, uint64_t m, uint32_t *tile_sums) {
+    __shared__ uint32_t total;
+    const uint64_t base = (uint64_t)blockIdx.x * PSCAN_TILE + threadIdx.x * PSCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < PSCAN_ITEMS; q++)
+        if (base + q < m) s += in[base + q];
+    block_excl_scan_u32(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) pscan_of_tiles(uint32_t *tile_sums, uint64_t ntiles, uint32_t *grand_total) {
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (uint64_t base = 0; base < ntiles; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0;
+        uint32_t ex = block_excl_scan_u32(v, &total);
+        if (i < ntiles) tile_sums[i] = ex + carry;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+__global__ void __launch_bounds__(PSCAN_THREADS) pscan_apply(const uint32_t *in, uint64_t m, const uint32_t *tile_sums, uint32_t *out) {
+    __shared__ uint32_t total;
+    const uint64_t base = (uint64_t)blockIdx.x * PSCAN_TILE + threadIdx.x * PSCAN_ITEMS;
+    uint32_t v[PSCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int q = 0; q < PSCAN_ITEMS; q++) {
+        v[q] = base + q < m ? in[base + q] : 0;
+        s += v[q];
+    }
+    uint32_t ex = block_excl_scan_u32(s, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < PSCAN_ITEMS; q++) {
+        if (base + q < m) out[base + q] = ex;
+        ex += v[q];
+    }
+}
+// out[i] = sum_{j<i} in[i]; *d_total = sum of all (d_total: device u32)
+static int32_t scan_u32(sb_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, uint64_t m, uint32_t *d_total, cudaStream_t st) {
+    const uint64_t ntiles = (m + PSCAN_TILE - 1) / PSCAN_TILE;
+    uint32_t *d_tiles;
+    SB_TRY(scratch_get(ctx, "pscan_tiles", (ntiles + 4) * 4, (void **)&d_tiles));
+    SB_LAUNCH(ctx, pscan_tile_sums, (unsigned)ntiles, PSCAN_THREADS, 0, st, d_in, m, d_tiles);
+    SB_LAUNCH(ctx, pscan_of_tiles, 1, 1024, 0, st, d_tiles, ntiles, d_total);
+    SB_LAUNCH(ctx, pscan_apply, (unsigned)ntiles, PSCAN_THREADS, 0, st, d_in, m, d_tiles, d_out);
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------ batch inversion
+static const int BINV_CHUNK = 32;
+__global__ void __launch_bounds__(128) fr_batch_invert_kernel(uint4 *a, uint4 *tmp, uint64_t n) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t lo = t * BINV_CHUNK;
+    if (lo >= n) return;
+    const uint64_t hi = lo + BINV_CHUNK < n ? lo + BINV_CHUNK : n;
+    fr_t acc = fr_t::one();
+    for (uint64_t i = lo; i < hi; i++) {
+        fr_t x = load_fp<FrParams>(a + 2 * i);
+        store_fp(tmp + 2 * i, acc);
+        if (!x.is_zero()) acc = mul(acc, x);
+    }
+    fr_t iv = inv(acc);
+    for (uint64_t i = hi; i-- > lo;) {
+        fr_t x = load_fp<FrParams>(a + 2 * i);
+        if (x.is_zero()) continue;
+        fr_t p = load_fp<FrParams>(tmp + 2 * i);
+        store_fp(a + 2 * i, mul(iv, p));
+        iv = mul(iv, x);
+    }
+}
+int32_t fr_batch_invert(sb_ctx *ctx, void *d_a, size_t n, cudaStream_t st) {
+    if (n == 0) return SB_OK;
+    void *d_tmp;
+    SB_TRY(scratch_get(ctx, "binv_tmp", n * 32, &d_tmp));
+    const uint64_t threads = (n + BINV_CHUNK - 1) / BINV_CHUNK;
+    SB_LAUNCH(ctx, fr_batch_invert_kernel, (unsigned)((threads + 127) / 128), 128, 0, st, (uint4 *)d_a, (uint4 *)d_tmp, (uint64_t)n);
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------ running product
+static const int RP_CHUNK = 64;
+// phase 1: product of a over each chunk of indices [t*C, (t+1)*C) intersected with [0, n_a)
+__global__ void __launch_bounds__(128) rp_chunk_products(const uint4 *a, uint64_t n_a, uint4 *chunk_prod, uint64_t n_chunks) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_chunks) return;
+    const uint64_t lo = t * RP_CHUNK, hi = lo + RP_CHUNK < n_a ? lo + RP_CHUNK : n_a;
+    fr_t acc = fr_t::one();
+    for (uint64_t i = lo; i < hi; i++) acc = mul(acc, load_fp<FrParams>(a + 2 * i));
+    store_fp(chunk_prod + 2 * t, acc);
+}
+// phase 2 (single CTA): exclusive multiplicative scan of the chunk products, in place
+__global__ void __launch_bounds__(1024) rp_scan_chunks(uint4 *chunk_prod, uint64_t n_chunks) {
+    __shared__ uint4 s_lo[1024], s_hi[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
+    const uint64_t lo = tid * per, hi = lo + per < n_chunks ? lo + per : n_chunks;
+    fr_t local = fr_t::one();
+    for (uint64_t i = lo; i < hi; i++) local = mul(local, load_fp<FrParams>(chunk_prod + 2 * i));
+    fr_t incl = local;
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+        s_lo[tid] = make_uint4(incl.v[0], incl.v[1], incl.v[2], incl.v[3]);
+        s_hi[tid] = make_uint4(incl.v[4], incl.v[5], incl.v[6], incl.v[7]);
+        __syncthreads();
+        if (tid >= d) {
+            uint4 a = s_lo[tid - d], b = s_hi[tid - d];
+            fr_t o;
+            o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+            incl = mul(incl, o);
+        }
+        __syncthreads();
+    }
+    // exclusive prefix of this thread's segment = inclusive of previous thread
+    s_lo[tid] = make_uint4(incl.v[0], incl.v[1], incl.v[2], incl.v[3]);
+    s_hi[tid] = make_uint4(incl.v[4], incl.v[5], incl.v[6], incl.v[7]);
+    __syncthreads();
+    fr_t run = fr_t::one();
+    if (tid > 0) {
+        uint4 a = s_lo[tid - 1], b = s_hi[tid - 1];
+        run.v[0] = a.x; run.v[1] = a.y; run.v[2] = a.z; run.v[3] = a.w; run.v[4] = b.x; run.v[5] = b.y; run.v[6] = b.z; run.v[7] = b.w;
+    }
+    for (uint64_t i = lo; i < hi; i++) {
+        fr_t c = load_fp<FrParams>(chunk_prod + 2 * i);
+        store_fp(chunk_prod + 2 * i, run);
+        run = mul(run, c);
+    }
+}
+// phase 3: z[i] = init * prefix[chunk] * prod_{j in chunk, j < i} a[j]   for i < n_z
+__global__ void __launch_bounds__(128) rp_write(const uint4 *a, uint64_t n_a, const uint4 *chunk_prefix, uint64_t n_chunks, fr_t init, uint4 *z, uint64_t n_z) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_chunks) return;
+    const uint64_t lo = t * RP_CHUNK;
+    fr_t cur = mul(init, load_fp<FrParams>(chunk_prefix + 2 * t));
+    for (uint64_t i = lo; i < lo + RP_CHUNK && i < n_z; i++) {
+        store_fp(z + 2 * i, cur);
+        if (i < n_a) cur = mul(cur, load_fp<FrParams>(a + 2 * i));
+    }
+}
+int32_t fr_running_product(sb_ctx *ctx, const void *d_a, size_t n_a, const fr_t &init, void *d_z, size_t n_z, cudaStream_t st) {
+    if (n_z == 0) return SB_OK;
+    const uint64_t n_chunks = (n_z + RP_CHUNK - 1) / RP_CHUNK;
+    void *d_cp;
+    SB_TRY(scratch_get(ctx, "rp_chunks", n_chunks * 32, &d_cp));
+    SB_LAUNCH(ctx, rp_chunk_products, (unsigned)((n_chunks + 127) / 128), 128, 0, st, (const uint4 *)d_a, (uint64_t)n_a, (uint4 *)d_cp, n_chunks);
+    SB_LAUNCH(ctx, rp_scan_chunks, 1, 1024, 0, st, (uint4 *)d_cp, n_chunks);
+    SB_LAUNCH(ctx, rp_write, (unsigned)((n_chunks + 127) / 128), 128, 0, st, (const uint4 *)d_a, (uint64_t)n_a, (const uint4 *)d_cp, n_chunks, init, (uint4 *)d_z, (uint64_t)n_z);
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------ polynomial evaluation (many (poly, point) pairs)
+static const int EV_CHUNK = 256, EV_THREADS = 128;
+struct EvalJob {
+    const uint4 *poly;
+    fr_t x;
+    fr_t x_chunk;  // x^EV_CHUNK
+};
+__global__ void __launch_bounds__(EV_THREADS) eval_poly_partial(const EvalJob *jobs, uint64_t n, uint4 *partials, uint32_t blocks_per_job) {
+    __shared__ uint4 s_lo[EV_THREADS], s_hi[EV_THREADS];
+    const EvalJob job = jobs[blockIdx.y];
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t lo = t * EV_CHUNK;
+    fr_t acc = fr_t::zero();
+    if (lo < n) {
+        const uint64_t hi = lo + EV_CHUNK < n ? lo + EV_CHUNK : n;
+        for (uint64_t i = hi; i-- > lo;) acc = add(mul(acc, job.x), load_fp<FrParams>(job.poly + 2 * i));
+        // times x^(t * EV_CHUNK) = (x^EV_CHUNK)^t
+        fr_t p = fr_t::one(), b = job.x_chunk;
+        uint64_t e = t;
+        while (e) {
+            if (e & 1) p = mul(p, b);
+            b = sqr(b);
+            e >>= 1;
+        }
+        acc = mul(acc, p);
+    }
+    const uint32_t tid = threadIdx.x;
+    s_lo[tid] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+    s_hi[tid] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+    __syncthreads();
+    for (uint32_t d = EV_THREADS / 2; d >= 1; d >>= 1) {
+        if (tid < d) {
+            uint4 a = s_lo[tid + d], b2 = s_hi[tid + d];
+            fr_t o;
+            o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b2.x; o.v[5] = b2.y; o.v[6] = b2.z; o.v[7] = b2.w;
+            acc = add(acc, o);
+            s_lo[tid] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+            s_hi[tid] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_fp(partials + 2 * ((uint64_t)blockIdx.y * blocks_per_job + blockIdx.x), acc);
+}
+__global__ void eval_poly_finish(const uint4 *partials, uint32_t blocks_per_job, uint4 *out) {
+    // one thread per job: blocks_per_job is small (n / 32768)
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= gridDim.x * blockDim.x) return;
+    fr_t acc = fr_t::zero();
+    for (uint32_t b = 0; b < blocks_per_job; b++) acc = add(acc, load_fp<FrParams>(partials + 2 * ((uint64_t)j * blocks_per_job + b)));
+    store_fp(out + 2 * j, acc);
+}
+// host: polys[j] device pointers (n coefficients each), xs[j] points -> out[j] on the host
+int32_t fr_eval_polys(sb_ctx *ctx, const std::vector<const void *> &polys, const std::vector<fr_t> &xs, size_t n, std::vector<fr_t> &out, cudaStream_t st) {
+    const size_t m = polys.size();
+    out.resize(m);
+    if (m == 0) return SB_OK;
+    std::vector<EvalJob> jobs(m);
+    for (size_t j = 0; j < m; j++) {
+        jobs[j].poly = (const uint4 *)polys[j];
+        jobs[j].x = xs[j];
+        jobs[j].x_chunk = fr_pow_host(xs[j], EV_CHUNK);
+    }
+    const uint64_t threads = (n + EV_CHUNK - 1) / EV_CHUNK;
+    const uint32_t bpj = (uint32_t)((threads + EV_THREADS - 1) / EV_THREADS);
+    void *d_jobs, *d_part, *d_out;
+    SB_TRY(scratch_get(ctx, "ev_jobs", m * sizeof(EvalJob), &d_jobs));
+    SB_TRY(scratch_get(ctx, "ev_part", (size_t)m * bpj * 32, &d_part));
+    SB_TRY(scratch_get(ctx, "ev_out", m * 32, &d_out));
+    SB_CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs.data(), m * sizeof(EvalJob), cudaMemcpyHostToDevice, st));
+    SB_LAUNCH(ctx, eval_poly_partial, dim3(bpj, (unsigned)m), EV_THREADS, 0, st, (const EvalJob *)d_jobs, (uint64_t)n, (uint4 *)d_part, bpj);
+    SB_LAUNCH(ctx, eval_poly_finish, (unsigned)m, 1, 0, st, (const uint4 *)d_part, bpj, (uint4 *)d_out);
+    SB_CUDA_TRY(cudaMemcpyAsync(out.data(), d_out, m * 32, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------ canonical <-> Montgomery, sort
+__global__ void fr_convert_kernel(uint4 *a, uint64_t n, int to_mont_flag) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t x = load_fp<FrParams>(a + 2 * i);
+    store_fp(a + 2 * i, to_mont_flag ? to_mont(x) : from_mont(x));
+}
+__global__ void fill_ones_kernel(uint4 *a, uint64_t from, uint64_t to) {
+    uint64_t i = from + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= to) return;
+    a[2 * i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    a[2 * i + 1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+}
+__device__ __forceinline__ bool less256(const uint4 &alo, const uint4 &ahi, const uint4 &blo, const uint4 &bhi) {
+    if (ahi.w != bhi.w) return ahi.w < bhi.w;
+    if (ahi.z != bhi.z) return ahi.z < bhi.z;
+    if (ahi.y != bhi.y) return ahi.y < bhi.y;
+    if (ahi.x != bhi.x) return ahi.x < bhi.x;
+    if (alo.w != blo.w) return alo.w < blo.w;
+    if (alo.z != blo.z) return alo.z < blo.z;
+    if (alo.y != blo.y) return alo.y < blo.y;
+    return alo.x < blo.x;
+}
+__device__ __forceinline__ bool eq256(const uint4 &alo, const uint4 &ahi, const uint4 &blo, const uint4 &bhi) {
+    return alo.x == blo.x && alo.y == blo.y && alo.z == blo.z && alo.w == blo.w && ahi.x == bhi.x && ahi.y == bhi.y && ahi.z == bhi.z && ahi.w == bhi.w;
+}
+// one compare-exchange step of the bitonic network on raw 256-bit little-endian integers
+__global__ void bitonic_step_kernel(uint4 *a, uint64_t n, uint64_t j, uint64_t k) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n / 2) return;
+    // t enumerates the pairs: insert a zero bit at position log2(j)
+    const uint64_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const uint64_t l = i | j;
+    uint4 ilo = a[2 * i], ihi = a[2 * i + 1], llo = a[2 * l], lhi = a[2 * l + 1];
+    const bool asc = (i & k) == 0;
+    const bool swap = asc ? less256(llo, lhi, ilo, ihi) : less256(ilo, ihi, llo, lhi);
+    if (swap) {
+        a[2 * i] = llo; a[2 * i + 1] = lhi;
+        a[2 * l] = ilo; a[2 * l + 1] = ihi;
+    }
+}
+// in-shared-memory phase: all steps with j < 2 * TILE handled by one CTA on a tile of 2*blockDim elements
+static const int BITONIC_SMEM_THREADS = 512;  // tile = 1024 elements = 32 KB
+__global__ void __launch_bounds__(BITONIC_SMEM_THREADS) bitonic_smem_kernel(uint4 *a, uint64_t n, uint64_t k, uint64_t j_start) {
+    __shared__ uint4 s_lo[2 * BITONIC_SMEM_THREADS], s_hi[2 * BITONIC_SMEM_THREADS];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t base = (uint64_t)blockIdx.x * (2 * BITONIC_SMEM_THREADS);
+    for (uint32_t q = tid; q < 2 * BITONIC_SMEM_THREADS; q += BITONIC_SMEM_THREADS) {
+        s_lo[q] = a[2 * (base + q)];
+        s_hi[q] = a[2 * (base + q) + 1];
+    }
+    __syncthreads();
+    for (uint64_t j = j_start; j > 0; j >>= 1) {
+        const uint32_t i = (uint32_t)(((tid & ~(j - 1)) << 1) | (tid & (j - 1)));
+        const uint32_t l = i | (uint32_t)j;
+        const bool asc = ((base + i) & k) == 0;
+        uint4 ilo = s_lo[i], ihi = s_hi[i], llo = s_lo[l], lhi = s_hi[l];
+        const bool swap = asc ? less256(llo, lhi, ilo, ihi) : less256(ilo, ihi, llo, lhi);
+        if (swap) {
+            s_lo[i] = llo; s_hi[i] = lhi;
+            s_lo[l] = ilo; s_hi[l] = ihi;
+        }
+        __syncthreads();
+    }
+    for (uint32_t q = tid; q < 2 * BITONIC_SMEM_THREADS; q += BITONIC_SMEM_THREADS) {
+        a[2 * (base + q)] = s_lo[q];
+        a[2 * (base + q) + 1] = s_hi[q];
+    }
+}
+// sorts d_a[0 .. count) ascending as raw 256-bit integers; d_a must have room for the next power of two
+int32_t sort_u256(sb_ctx *ctx, void *d_a, size_t count, size_t capacity_pow2, cudaStream_t st) {
+    const uint64_t N = capacity_pow2;
+    if (N > count) SB_LAUNCH(ctx, fill_ones_kernel, (unsigned)((N - count + 255) / 256), 256, 0, st, (uint4 *)d_a, (uint64_t)count, N);
+    if (N < 2) return SB_OK;
+    const uint64_t tile = 2 * BITONIC_SMEM_THREADS;
+    for (uint64_t k = 2; k <= N; k <<= 1) {
+        uint64_t j = k >> 1;
+        if (N >= tile) {
+            for (; j >= tile; j >>= 1) SB_LAUNCH(ctx, bitonic_step_kernel, (unsigned)((N / 2 + 255) / 256), 256, 0, st, (uint4 *)d_a, N, j, k);
+            SB_LAUNCH(ctx, bitonic_smem_kernel, (unsigned)(N / tile), BITONIC_SMEM_THREADS, 0, st, (uint4 *)d_a, N, k, j);
+        } else {
+            for (; j > 0; j >>= 1) SB_LAUNCH(ctx, bitonic_step_kernel, (unsigned)((N / 2 + 255) / 256), 256, 0, st, (uint4 *)d_a, N, j, k);
+        }
+    }
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------ lookup: permute_expression_pair
+// a_sorted / t_sorted: canonical, ascending, u entries each.
+// rep[r]  = 1 iff row r of the sorted input repeats the previous value (r > 0)
+// left[p] = 1 iff sorted table entry p is NOT consumed by a first occurrence of an input value
+__global__ void lookup_flags_kernel(const uint4 *a_sorted, const uint4 *t_sorted, uint64_t u, uint32_t *rep, uint32_t *left) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    uint4 alo = a_sorted[2 * i], ahi = a_sorted[2 * i + 1];
+    rep[i] = (i > 0 && eq256(alo, ahi, a_sorted[2 * (i - 1)], a_sorted[2 * (i - 1) + 1])) ? 1u : 0u;
+    uint4 tlo = t_sorted[2 * i], thi = t_sorted[2 * i + 1];
+    bool consumed = false;
+    if (i == 0 || !eq256(tlo, thi, t_sorted[2 * (i - 1)], t_sorted[2 * (i - 1) + 1])) {
+        // first occurrence of this table value: consumed iff the value occurs among the inputs
+        uint64_t lo = 0, hi = u;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (less256(a_sorted[2 * mid], a_sorted[2 * mid + 1], tlo, thi)) lo = mid + 1;
+            else hi = mid;
+        }
+        consumed = lo < u && eq256(a_sorted[2 * lo], a_sorted[2 * lo + 1], tlo, thi);
+    }
+    left[i] = consumed ? 0u : 1u;
+}
+__global__ void lookup_compact_kernel(const uint4 *t_sorted, uint64_t u, const uint32_t *rep, const uint32_t *rep_pos, const uint32_t *left, const uint32_t *left_pos,
+                                      uint32_t *rep_rows, uint4 *left_vals) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    if (rep[i]) rep_rows[rep_pos[i]] = (uint32_t)i;
+    if (left[i]) {
+        left_vals[2 * left_pos[i]] = t_sorted[2 * i];
+        left_vals[2 * left_pos[i] + 1] = t_sorted[2 * i + 1];
+    }
+}
+// permuted table: first occurrences take the input value; repeated rows, from the LAST one backwards, take the
+// leftover table values in ascending order
+__global__ void lookup_fill_kernel(const uint4 *a_sorted, uint64_t u, const uint32_t *rep, const uint32_t *rep_rows, const uint4 *left_vals, uint32_t m, uint4 *s_perm) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < u && !rep[i]) {
+        s_perm[2 * i] = a_sorted[2 * i];
+        s_perm[2 * i + 1] = a_sorted[2 * i + 1];
+    }
+    if (i < m) {
+        const uint32_t row = rep_rows[m - 1 - i];
+        s_perm[2 * row] = left_vals[2 * i];
+        s_perm[2 * row + 1] = left_vals[2 * i + 1];
+    }
+}
+// d_in / d_tab: compressed input / table columns (Montgomery, n rows).  Outputs (Montgomery, first u rows
+// written): d_a_perm, d_s_perm.  Returns SB_ERR_ARG if an input value is missing from the table.
+int32_t lookup_permute(sb_ctx *ctx, const void *d_in, const void *d_tab, size_t n, size_t u, void *d_a_perm, void *d_s_perm, cudaStream_t st) {
+    size_t N = 1;
+    while (N < u) N <<= 1;
+    void *d_as, *d_ts, *d_leftv;
+    uint32_t *d_flags;
+    SB_TRY(scratch_get(ctx, "lk_as", N * 32, &d_as));
+    SB_TRY(scratch_get(ctx, "lk_ts", N * 32, &d_ts));
+    SB_TRY(scratch_get(ctx, "lk_leftv", (u + 1) * 32, &d_leftv));
+    SB_TRY(scratch_get(ctx, "lk_flags", (5 * (u + 4) + 8) * 4, (void **)&d_flags));
+    uint32_t *rep = d_flags, *rep_pos = rep + (u + 4), *left = rep_pos + (u + 4), *left_pos = left + (u + 4), *rep_rows = left_pos + (u + 4), *totals = rep_rows + (u + 4);
+    SB_CUDA_TRY(cudaMemcpyAsync(d_as, d_in, u * 32, cudaMemcpyDeviceToDevice, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(d_ts, d_tab, u * 32, cudaMemcpyDeviceToDevice, st));
+    const unsigned gu = (unsigned)((u + 255) / 256);
+    SB_LAUNCH(ctx, fr_convert_kernel, gu, 256, 0, st, (uint4 *)d_as, (uint64_t)u, 0);
+    SB_LAUNCH(ctx, fr_convert_kernel, gu, 256, 0, st, (uint4 *)d_ts, (uint64_t)u, 0);
+    SB_TRY(sort_u256(ctx, d_as, u, N, st));
+    SB_TRY(sort_u256(ctx, d_ts, u, N, st));
+    SB_LAUNCH(ctx, lookup_flags_kernel, gu, 256, 0, st, (const uint4 *)d_as, (const uint4 *)d_ts, (uint64_t)u, rep, left);
+    SB_TRY(scan_u32(ctx, rep, rep_pos, u, totals, st));
+    SB_TRY(scan_u32(ctx, left, left_pos, u, totals + 1, st));
+    uint32_t h_tot[2];
+    SB_CUDA_TRY(cudaMemcpyAsync(h_tot, totals, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_tot[0] != h_tot[1]) {
+        set_last_error("lookup: an input value is not contained in the table (repeated rows %u, leftover table values %u)", h_tot[0], h_tot[1]);
+        return SB_ERR_ARG;
+    }
+    SB_LAUNCH(ctx, lookup_compact_kernel, gu, 256, 0, st, (const uint4 *)d_ts, (uint64_t)u, rep, rep_pos, left, left_pos, rep_rows, (uint4 *)d_leftv);
+    SB_LAUNCH(ctx, lookup_fill_kernel, gu, 256, 0, st, (const uint4 *)d_as, (uint64_t)u, rep, rep_rows, (const uint4 *)d_leftv, h_tot[0], (uint4 *)d_s_perm);
+    SB_CUDA_TRY(cudaMemcpyAsync(d_a_perm, d_as, u * 32, cudaMemcpyDeviceToDevice, st));
+    SB_LAUNCH(ctx, fr_convert_kernel, gu, 256, 0, st, (uint4 *)d_a_perm, (uint64_t)u, 1);
+    SB_LAUNCH(ctx, fr_convert_kernel, gu, 256, 0, st, (uint4 *)d_s_perm, (uint64_t)u, 1);
+    (void)n;
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------ linear combinations
+__global__ void fr_axpy_kernel(uint4 *acc, const uint4 *p, fr_t s, uint64_t n, int first) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v = mul(load_fp<FrParams>(p + 2 * i), s);
+    if (!first) v = add(v, load_fp<FrParams>(acc + 2 * i));
+    store_fp(acc + 2 * i, v);
+}
+// acc = (first ? 0 : acc) + s * p
+int32_t fr_axpy(sb_ctx *ctx, void *d_acc, const void *d_p, const fr_t &s, size_t n, bool first, cudaStream_t st) {
+    if (n == 0) return SB_OK;
+    SB_LAUNCH(ctx, fr_axpy_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_acc, (const uint4 *)d_p, s, (uint64_t)n, first ? 1 : 0);
+    return SB_OK;
+}
+struct HeadArgs {
+    fr_t c[4];
+    uint32_t k;
+};
+__global__ void fr_sub_head_kernel(uint4 *acc, HeadArgs h) {
+    uint32_t i = threadIdx.x;
+    if (i >= h.k) return;
+    store_fp(acc + 2 * i, sub(load_fp<FrParams>(acc + 2 * i), h.c[i]));
+}
+// acc[i] -= c[i] for i < k <= 4
+int32_t fr_sub_head(sb_ctx *ctx, void *d_acc, const fr_t *c, uint32_t k, cudaStream_t st) {
+    if (k == 0) return SB_OK;
+    SB_REQUIRE(k <= 4, "fr_sub_head: k > 4");
+    HeadArgs h;
+    for (uint32_t i = 0; i < 4; i++) h.c[i] = i < k ? c[i] : fr_t::zero();
+    h.k = k;
+    SB_LAUNCH(ctx, fr_sub_head_kernel, 1, 4, 0, st, (uint4 *)d_acc, h);
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -43,6 +43,49 @@ class ParamsKZG:
         return self
 
     @classmethod
+    def setup(cls, k: int, tau: int, ctx: Optional[Context] = None) -> "ParamsKZG":
+        """`ParamsKZG::setup(k, rng)` with an explicit (UNSAFE, test-only) secret tau: g[i] = [tau^i] G and
+        g_lagrange[i] = [L_i(tau)] G.  The 2 x 2^k fixed-base products run on the GPU; the scalars are host
+        integers (setup is not on the proving path)."""
+        from . import fields
+        ctx = ctx or default_context()
+        r, n = fields.FR_MODULUS, 1 << k
+        w = fields.omega(k)
+        mono, t = [], 1
+        for _ in range(n):
+            mono.append(t)
+            t = t * tau % r
+        tn = (pow(tau, n, r) - 1) % r
+        ninv = pow(n, -1, r)
+        # L_i(tau) = omega^i (tau^n - 1) / (n (tau - omega^i)), denominators inverted in one batch
+        wi, dens, ws = 1, [], []
+        for _ in range(n):
+            ws.append(wi)
+            dens.append((tau - wi) % r)
+            wi = wi * w % r
+        pref, acc = [], 1
+        for dd in dens:
+            pref.append(acc)
+            acc = acc * dd % r
+        inv = pow(acc, -1, r)
+        lag = [0] * n
+        for i in range(n - 1, -1, -1):
+            lag[i] = ws[i] * tn % r * ninv % r * (inv * pref[i] % r) % r
+            inv = inv * dens[i] % r
+        scal = np.concatenate([fields.fr_to_mont(x) for x in mono + lag]).reshape(2 * n, 4)
+        d_s = ctx.alloc(scal.nbytes)
+        d_p = ctx.alloc(2 * n * 64)
+        try:
+            ctx.upload(d_s, scal)
+            _lib.check(_lib.lib().sb_g1_fixed_base_mul_dev(ctx.handle, ctypes.c_void_p(d_s), ctypes.c_size_t(2 * n), ctypes.c_void_p(d_p), None), "sb_g1_fixed_base_mul_dev")
+            ctx.synchronize()
+            pts = ctx.download(d_p, 2 * n * 64).reshape(2 * n, 8)
+        finally:
+            ctx.free(d_s)
+            ctx.free(d_p)
+        return cls(k, pts[:n].copy(), pts[n:].copy(), b"", ctx)
+
+    @classmethod
     def read(cls, path: str, ctx: Optional[Context] = None) -> "ParamsKZG":
         with open(path, "rb") as f:
             data = f.read()

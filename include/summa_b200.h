@@ -105,6 +105,41 @@ int32_t sb_coeff_to_extended_dev(sb_ctx *ctx, const sb_domain *d, const void *d_
 int32_t sb_extended_to_coeff_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext /* clobbered */, void *d_coeff, void *stream);
 int32_t sb_divide_by_vanishing_poly_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *stream);
 
+/* ---- halo2_proofs::plonk::{keygen_pk, create_proof} --------------------------------------------
+ * Rust: `create_proof<KZGCommitmentScheme<Bn256>, ProverSHPLONK<'_, Bn256>, _, R: RngCore, T, C>(params, &pk,
+ *        &[circuit], &[&[&[F]]], rng, &mut transcript)`  (utils.rs:94-102 Blake2bWrite, :171-178 Keccak256Transcript).
+ * The constraint system travels as JSON (schema: tests/golden/mst_inclusion_cs.json -- gates / lookups as
+ * expression trees over (advice|fixed|instance, column, rotation), permutation columns, query lists, degree,
+ * blinding_factors); fixed_values / sigma_values are `pk.fixed_values` and `pk.permutation.permutations`
+ * (Lagrange form, n x 32 B per column, column-major).  The handle keeps every per-circuit polynomial in HBM. */
+typedef struct sb_pk sb_pk;
+int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
+                     const uint8_t transcript_repr[32] /* vk.transcript_repr, Montgomery */, sb_pk **out_pk);
+int32_t sb_pk_destroy(sb_pk *pk);
+/* keygen_vk's commitments of the fixed and permutation columns (affine, 64 B each) */
+int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_comms);
+/* instances: n_instances x 32 B (Montgomery); advice: num_advice x n x 32 B assigned cells (rows >= n - blinding - 1
+ * are overwritten by blinding); rng_seed: ChaCha20Rng::from_seed; transcript_kind 0 = Blake2b (full_prover),
+ * 1 = Keccak256 / EVM (gen_proof_solidity_calldata).  Writes the proof bytes and their length. */
+int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
+                        int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+/* device time (ms) of the fused evaluate_h kernel of the last create_proof on this context and its program shape:
+ * instructions, field products, additions/subtractions, live value slots */
+int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);
+/* building blocks of create_proof with host buffers (halo2 arithmetic::{eval_polynomial, kate_division},
+ * poly::batch_invert, the grand-product scan of permutation / lookup Z, lookup `permute_expression_pair`) */
+int32_t sb_fr_batch_invert(sb_ctx *ctx, uint8_t *a, size_t n);                                   /* zeros stay zero */
+int32_t sb_fr_running_product(sb_ctx *ctx, const uint8_t *a, size_t n_a, const uint8_t init[32], uint8_t *z, size_t n_z); /* z[0]=init, z[i]=z[i-1]*a[i-1] */
+int32_t sb_fr_eval_polynomial(sb_ctx *ctx, const uint8_t *coeffs, size_t n, const uint8_t *points, size_t n_points, uint8_t *out);
+int32_t sb_fr_sort(sb_ctx *ctx, uint8_t *a, size_t n);                                            /* ascending canonical value (Fr `Ord`) */
+int32_t sb_lookup_permute(sb_ctx *ctx, const uint8_t *input, const uint8_t *table, size_t n, size_t usable, uint8_t *permuted_input, uint8_t *permuted_table);
+int32_t sb_kate_division(sb_ctx *ctx, const uint8_t *a, uint32_t log_n, const uint8_t b[32], uint8_t *q /* 2^log_n slots, top one zero */);
+/* host-side primitives of the transcript / RNG, exported for the CPU test-suite */
+int32_t sb_test_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
+int32_t sb_test_blake2b512(const uint8_t *data, size_t len, const uint8_t personal[16], uint8_t out[64]);
+int32_t sb_test_chacha_fr(uint64_t seed_u64, uint32_t skip_bytes, uint32_t count, uint8_t *out);
+int32_t sb_test_host_fr(int32_t op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int32_t sb_launch_count(const sb_ctx *ctx, uint64_t *out);

@@ -1,0 +1,201 @@
+"""GPU parity tests of the create_proof pipeline (python -m pytest tests -m gpu).
+
+Rows a6-a9 of SURVEY 8(a): batch inversion, grand-product scan, lookup permutation (sort), polynomial
+evaluation, kate division, then the whole `create_proof`: the GPU prover's proof must be BYTE-IDENTICAL to
+the oracle prover's (oracle/halo2_prover.py, itself accepted by the reference's verifier contract) for the
+same circuit, SRS and ChaCha20 seed, under both transcripts.  Bit-exact; no tolerance."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as B
+from oracle import cpu
+from oracle import halo2_prover as HP
+from oracle import mst as M
+from oracle import mst_circuit as C
+from oracle.chacha import ChaCha20Rng
+from oracle.transcript import Blake2bTranscript, KeccakTranscript
+
+pytestmark = pytest.mark.gpu
+
+
+def fr(x):
+    return np.frombuffer(B.fr_to_mont_bytes(x), dtype=np.uint64).copy()
+
+
+def L():
+    from circuits_halo2_b200 import _lib
+    return _lib
+
+
+def P(a):
+    from circuits_halo2_b200.context import ptr
+    return ptr(a)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 1 << 16])
+def test_batch_invert(ctx, n):
+    a = cpu.random_fr(n, 11 + n)
+    a[::7] = 0  # zeros stay zero (halo2 batch_invert)
+    got = a.copy()
+    L().check(L().lib().sb_fr_batch_invert(ctx.handle, P(got), ctypes.c_size_t(n)), "batch_invert")
+    assert (got.reshape(-1) == cpu.fr_batch_invert(a)).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 5000, (1 << 17) + 3])
+def test_running_product(ctx, n):
+    a = cpu.random_fr(n, 21 + n)
+    init = fr(12345)
+    z = np.zeros((n, 4), dtype=np.uint64)
+    L().check(L().lib().sb_fr_running_product(ctx.handle, P(a), ctypes.c_size_t(n), P(init), P(z), ctypes.c_size_t(n)), "running_product")
+    assert (z.reshape(-1) == cpu.fr_running_product(a, init, n)).all()
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 1 << 12, (1 << 16) + 17])
+def test_eval_polynomial(ctx, n):
+    coeffs = cpu.random_fr(n, 31 + n)
+    xs = [0, 1, 7, B.R - 1, B.omega_for(10), 0x1234567890ABCDEF1234567890ABCDEF]
+    pts = np.concatenate([fr(x) for x in xs]).reshape(-1, 4)
+    out = np.zeros((len(xs), 4), dtype=np.uint64)
+    L().check(L().lib().sb_fr_eval_polynomial(ctx.handle, P(coeffs), ctypes.c_size_t(n), P(pts), ctypes.c_size_t(len(xs)), P(out)), "eval")
+    for i in range(len(xs)):
+        assert (out[i] == cpu.fr_eval_poly(coeffs, pts[i])).all(), (n, i)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 100, 1024, 1025, 5000, 1 << 15])
+def test_sort_matches_fr_ord(ctx, n):
+    a = cpu.random_fr(n, 41 + n)
+    a[: n // 3] = a[0]                      # duplicates
+    if n > 10:
+        a[5] = fr(0); a[6] = fr(B.R - 1); a[7] = fr(1)
+    got = a.copy()
+    L().check(L().lib().sb_fr_sort(ctx.handle, P(got), ctypes.c_size_t(n)), "sort")
+    ref = sorted(HP.to_ints(a))
+    assert HP.to_ints(got) == ref
+
+
+@pytest.mark.parametrize("n,kind", [(256, "bytes"), (2048, "bytes"), (2048, "random"), (1 << 14, "bytes")])
+def test_lookup_permute(ctx, n, kind):
+    rng = np.random.default_rng(n)
+    usable = n - 6
+    table_vals = list(range(256)) + [0] * (n - 256) if kind == "bytes" else [int(x) for x in rng.integers(1, 1 << 62, size=n)]
+    if kind == "bytes":
+        inp_vals = [int(x) for x in rng.integers(0, min(256, usable), size=n)]  # only values present in the usable table rows
+        inp_vals[: n // 2] = [0] * (n // 2)
+    else:
+        inp_vals = [table_vals[int(i)] for i in rng.integers(0, usable, size=n)]
+    inp, tab = HP.from_ints(inp_vals), HP.from_ints(table_vals)
+    a_ref, s_ref = HP.permute_expression_pair(inp_vals, table_vals, usable)
+    a_out = np.zeros((usable, 4), dtype=np.uint64)
+    s_out = np.zeros((usable, 4), dtype=np.uint64)
+    L().check(L().lib().sb_lookup_permute(ctx.handle, P(inp), P(tab), ctypes.c_size_t(n), ctypes.c_size_t(usable), P(a_out), P(s_out)), "lookup_permute")
+    assert HP.to_ints(a_out) == a_ref
+    assert HP.to_ints(s_out) == s_ref
+
+
+def test_lookup_permute_rejects_value_outside_table(ctx):
+    from circuits_halo2_b200._lib import SummaB200Error
+    n, usable = 256, 250
+    inp = HP.from_ints([999] + [1] * (n - 1))
+    tab = HP.from_ints(list(range(n)))
+    out = np.zeros((usable, 4), dtype=np.uint64)
+    with pytest.raises(SummaB200Error):
+        L().check(L().lib().sb_lookup_permute(ctx.handle, P(inp), P(tab), ctypes.c_size_t(n), ctypes.c_size_t(usable), P(out), P(out.copy())), "lookup_permute")
+
+
+@pytest.mark.parametrize("log_n", [7, 11, 16])
+def test_kate_division(ctx, log_n):
+    n = 1 << log_n
+    a = cpu.random_fr(n, 51 + log_n)
+    b = fr(0xDEADBEEF1234567)
+    q = np.zeros((n, 4), dtype=np.uint64)
+    L().check(L().lib().sb_kate_division(ctx.handle, P(a), ctypes.c_uint32(log_n), P(b), P(q)), "kate")
+    ref = cpu.fr_kate_division(a, b).reshape(-1, 4)
+    assert (q[: n - 1] == ref).all() and not q[n - 1].any()
+
+
+# ------------------------------------------------------------------ the real circuit, real SRS (k = 11)
+@pytest.fixture(scope="module")
+def real(golden_dir, ctx):
+    import circuits_halo2_b200 as sb
+    tree = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"))
+    lay = C.synthesize(11, tree.generate_proof(0), 4, 2, 8)
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    oparams = HP.Params.read(os.path.join(golden_dir, "hermez-raw-11"))
+    fixed = np.stack([HP.from_ints(c) for c in C.fixed_columns(lay)])
+    opk = HP.ProvingKey(oparams, cs, fixed, C.permutation_mapping(lay))
+    advice = np.stack([HP.from_ints(c) for c in C.advice_columns(lay)])
+    instances = [tree.nodes[0][0][0], tree.root[0]] + tree.root[1]
+    params = sb.ParamsKZG.read(os.path.join(golden_dir, "hermez-raw-11"), ctx)
+    pk = sb.ProvingKey(params, cs, fixed, opk.sigma_values, opk.transcript_repr, ctx)
+    return dict(cs=cs, oparams=oparams, opk=opk, advice=advice, instances=instances, params=params, pk=pk)
+
+
+def test_pk_commitments_equal_reference_vk(real, golden_dir):
+    """keygen commitments computed on the GPU == the constants of the reference's verifier contract (.sol:238-271)."""
+    vk = json.load(open(os.path.join(golden_dir, "verifier_constants.json")))
+    f, s = real["pk"].commitments()
+    for i in range(11):
+        assert B.g1_from_mont_bytes(f[i].tobytes()) == (int(vk[f"fixed_comms[{i}].x"], 16), int(vk[f"fixed_comms[{i}].y"], 16))
+    for j in range(6):
+        assert B.g1_from_mont_bytes(s[j].tobytes()) == (int(vk[f"permutation_comms[{j}].x"], 16), int(vk[f"permutation_comms[{j}].y"], 16))
+
+
+@pytest.mark.parametrize("seed", [42, 7])
+def test_create_proof_keccak_is_byte_identical_to_oracle(real, seed):
+    import circuits_halo2_b200 as sb
+    tr = KeccakTranscript()
+    HP.create_proof(real["oparams"], real["opk"], real["instances"], real["advice"], ChaCha20Rng.seed_from_u64(seed), tr)
+    ref = tr.finalize()
+    got = sb.create_proof(real["pk"], real["instances"], real["advice"], sb.seed_from_u64(seed), sb.TRANSCRIPT_KECCAK)
+    assert len(got) == 2144
+    if got != ref:
+        first = next(i for i in range(min(len(got), len(ref))) if got[i] != ref[i])
+        pytest.fail(f"proof differs from the oracle's at byte {first:#x} (section boundaries: advice 0x0, lookup 0xc0, perm 0x140, lookupZ 0x1c0, "
+                    f"random 0x200, h 0x240, evals 0x380, W 0x7e0, W' 0x820)")
+
+
+def test_create_proof_blake2b_is_byte_identical_to_oracle(real):
+    import circuits_halo2_b200 as sb
+    tr = Blake2bTranscript()
+    HP.create_proof(real["oparams"], real["opk"], real["instances"], real["advice"], ChaCha20Rng.seed_from_u64(3), tr)
+    got = sb.create_proof(real["pk"], real["instances"], real["advice"], sb.seed_from_u64(3), sb.TRANSCRIPT_BLAKE2B)
+    assert got == tr.finalize() and len(got) == 51 * 32
+
+
+def test_create_proof_rejects_unsatisfiable_lookup(real):
+    """a balance that does not fit N_BYTES makes a range-check input fall outside the table: the prover errors like halo2 does."""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200._lib import SummaB200Error
+    bad = real["advice"].copy()
+    lay_row = 246  # first range-check region: z_0 at advice column 0 (circuits/tests.rs:287)
+    bad[0, lay_row] = fr(B.R - 5)
+    with pytest.raises(SummaB200Error):
+        sb.create_proof(real["pk"], real["instances"], bad, sb.seed_from_u64(1), sb.TRANSCRIPT_KECCAK)
+
+
+@pytest.mark.parametrize("k", [12, 13])
+def test_create_proof_larger_k_synthetic_srs(ctx, golden_dir, k):
+    """Same circuit in a larger domain, unsafe synthetic SRS generated on the GPU: byte-identical to the oracle."""
+    import circuits_halo2_b200 as sb
+    tree = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"))
+    lay = C.synthesize(k, tree.generate_proof(3), 4, 2, 8)
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    params = sb.ParamsKZG.setup(k, 0x5A110000 + k, ctx)
+    oparams = HP.Params(k, params.g, params.g_lagrange, threads=8)
+    # the synthetic SRS must be a KZG SRS: commit(lagrange_to_coeff(v)) == commit_lagrange(v)
+    v = cpu.random_fr(1 << k, 5)
+    dom = sb.EvaluationDomain(6, k, ctx)
+    assert (params.commit(dom.lagrange_to_coeff(v)) == params.commit_lagrange(v)).all()
+    fixed = np.stack([HP.from_ints(c) for c in C.fixed_columns(lay)])
+    opk = HP.ProvingKey(oparams, cs, fixed, C.permutation_mapping(lay), transcript_repr=0x1234)
+    advice = np.stack([HP.from_ints(c) for c in C.advice_columns(lay)])
+    instances = [tree.nodes[0][3][0], tree.root[0]] + tree.root[1]
+    pk = sb.ProvingKey(params, cs, fixed, opk.sigma_values, 0x1234, ctx)
+    tr = KeccakTranscript()
+    HP.create_proof(oparams, opk, instances, advice, ChaCha20Rng.seed_from_u64(k), tr)
+    got = sb.create_proof(pk, instances, advice, sb.seed_from_u64(k), sb.TRANSCRIPT_KECCAK)
+    assert got == tr.finalize()

@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--ntt-log-n", type=int, default=22, help="size of the NTT side measurement (0 = skip)")
     ap.add_argument("--cpu-sample-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--proof-k", type=str, default="17", help="comma-separated k values for the create_proof side measurement ('' = skip)")
+    ap.add_argument("--dump-proof", type=str, default="", help="directory to write the last proof / vk commitments / instances to")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -150,6 +152,7 @@ def main():
 
     import circuits_halo2_b200 as sb
     from circuits_halo2_b200 import _lib
+    from circuits_halo2_b200 import fields as fields_mod
     from circuits_halo2_b200.context import ptr
 
     if not torch.cuda.is_available():
@@ -331,6 +334,59 @@ def main():
                "imad_frac": 68 * nn * ln / (t_ntt * 1e-3) / 1e12 / imadw_peak}
         del a
 
+    # ---- create_proof side measurement: the reference circuit MstInclusionCircuit<4,2,8> (entry_16.csv, user 0) at k = proof_k ----
+    proofs = []
+    if rank == 0 and args.proof_k:
+        import json as _json
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "mst_inclusion_assignment.npz"))
+        cs_text = open(os.path.join(ROOT, "tests", "golden", "mst_inclusion_cs.json")).read()
+        for pk_k in [int(x) for x in args.proof_k.split(",") if x]:
+            nrow = 1 << pk_k
+            t0 = time.perf_counter()
+            kzg = sb.ParamsKZG.setup(pk_k, 0x5A110000 + pk_k, ctx, download=False)
+            t_srs = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            pkey = sb.ProvingKey.from_sparse(kzg, cs_text, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234, ctx)
+            t_pk = time.perf_counter() - t0
+            adv_host = torch.zeros((3, nrow, 4), dtype=torch.int64).pin_memory()
+            adv_np = adv_host.numpy().view(np.uint64)
+            cells = fx["advice_cells"]
+            adv_np[cells[:, 0], cells[:, 1]] = fx["advice_values"]
+            insts = [fields_mod.fr_from_mont(v) for v in fx["instances"]]
+            seed = sb.seed_from_u64(42)
+            proof = b""
+            for _ in range(2):
+                proof = sb.create_proof(pkey, insts, adv_np, seed, sb.TRANSCRIPT_KECCAK)
+            torch.cuda.synchronize()
+            l0p = ctx.launch_count()
+            reps = max(2, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                proof2 = sb.create_proof(pkey, insts, adv_np, seed, sb.TRANSCRIPT_KECCAK)
+            torch.cuda.synchronize()
+            ms_proof = (time.perf_counter() - t0) / reps * 1e3
+            assert proof2 == proof, "create_proof is not deterministic in the seed"
+            hms = ctypes.c_float()
+            hprog = (ctypes.c_uint32 * 4)()
+            L.sb_last_h_profile(ctx.handle, ctypes.byref(hms), hprog)
+            stg = (ctypes.c_float * 12)()
+            L.sb_last_proof_stages(ctx.handle, stg)
+            stage_names = ["advice_commit", "lookup_permute_commit", "permutation_product", "lookup_product", "random_poly", "coset_ntt", "evaluate_h",
+                           "quotient_commit", "evaluations", "shplonk"]
+            ext_pts = nrow * 8
+            proofs.append({"k": pk_k, "ms_per_proof": ms_proof, "transcript": "keccak256/evm", "proof_bytes": len(proof),
+                           "launches_per_proof": (ctx.launch_count() - l0p) // reps, "h2d_bytes_per_proof": 3 * nrow * 32,
+                           "setup_srs_s": t_srs, "keygen_pk_s": t_pk, "stages_ms": {nm: round(float(stg[i]), 3) for i, nm in enumerate(stage_names)},
+                           "evaluate_h": {"ms": hms.value, "instructions": int(hprog[0]), "field_mul": int(hprog[1]), "field_addsub": int(hprog[2]), "live_slots": int(hprog[3]),
+                                          "G_field_mul_per_s": ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9 if hms.value else None,
+                                          "field_mul_frac_of_peak": (ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9) / fmul_peak if hms.value else None}})
+            if args.dump_proof:
+                os.makedirs(args.dump_proof, exist_ok=True)
+                fcom, scom = pkey.commitments()
+                np.savez(os.path.join(args.dump_proof, f"proof_k{pk_k}.npz"), proof=np.frombuffer(proof, dtype=np.uint8), fixed_comms=fcom, sigma_comms=scom,
+                         instances=fx["instances"], k=np.array([pk_k]), transcript_repr=np.array([0x1234]))
+            del pkey, kzg, adv_host
+
     # ---- CPU baseline (rank 0, bounded sample of the same workload) ----
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -366,7 +422,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "extra": {"ntt": ntt},
+            "extra": {"ntt": ntt, "create_proof": proofs},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -70,6 +70,7 @@ struct sb_ctx {
     // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
     float last_h_ms = 0;
     uint32_t last_h_program[4] = {0, 0, 0, 0};
+    float last_proof_stage_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // prover.cu `mark()` stages
 };
 
 namespace sb {

@@ -14,6 +14,7 @@
 // coefficient and extended-coset form, l_0 / l_last / l_active, the coset X column) stay resident in
 // HBM inside the `sb_pk` handle and are reused by every proof.
 #include <algorithm>
+#include <chrono>
 #include <set>
 
 #include "handles.h"
@@ -275,10 +276,20 @@ int32_t dalloc(sb_pk *pk, size_t bytes, void **out) {
 
 const Fr DIV_G = hfr::from_u64(7);  // multiplicative generator: g * H is disjoint from H
 
-int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint8_t *sigma_values, cudaStream_t st) {
+struct SparseAssignment {  // keygen output in sparse form (cells that differ from the default column)
+    const uint32_t *fixed_cells = nullptr;  // (col, row) pairs
+    const uint8_t *fixed_values = nullptr;  // 32 B each
+    size_t n_fixed = 0;
+    const uint32_t *perm_cells = nullptr;   // (col, row, to_col, to_row): sigma_col(omega^row) = delta^to_col * omega^to_row
+    size_t n_perm = 0;
+};
+
+int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint8_t *sigma_values, const SparseAssignment *sparse, cudaStream_t st) {
     const size_t n = pk->n, en = pk->ext_n;
     const sb_domain *d = pk->dom;
-    auto to_all_forms = [&](const uint8_t *host_vals, int count, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets,
+    const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+    const Fr omega = to_host(d->omega);
+    auto to_all_forms = [&](int count, bool is_sigma, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets,
                             std::vector<uint8_t> &comms) -> int32_t {
         comms.resize((size_t)count * 64);
         for (int c = 0; c < count; c++) {
@@ -286,7 +297,34 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
             SB_TRY(dalloc(pk, n * 32, &v));
             SB_TRY(dalloc(pk, n * 32, &p));
             SB_TRY(dalloc(pk, en * 32, &e));
-            SB_CUDA_TRY(cudaMemcpyAsync(v, host_vals + (size_t)c * n * 32, n * 32, cudaMemcpyHostToDevice, st));
+            if (!sparse) {
+                const uint8_t *src = (is_sigma ? sigma_values : fixed_values) + (size_t)c * n * 32;
+                SB_CUDA_TRY(cudaMemcpyAsync(v, src, n * 32, cudaMemcpyHostToDevice, st));
+            } else if (!is_sigma) {
+                SB_CUDA_TRY(cudaMemsetAsync(v, 0, n * 32, st));
+                for (size_t i = 0; i < sparse->n_fixed; i++) {
+                    if ((int)sparse->fixed_cells[2 * i] != c) continue;
+                    const size_t row = sparse->fixed_cells[2 * i + 1];
+                    SB_REQUIRE(row < n, "sparse fixed cell row out of range");
+                    SB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)v + row * 32, sparse->fixed_values + i * 32, 32, cudaMemcpyHostToDevice, st));
+                }
+            } else {
+                // identity permutation delta^c * omega^row, then the cells moved by copy constraints
+                SB_TRY(fr_gen_powers(ctx, v, d->omega, n, st));
+                SB_TRY(fr_scale(ctx, v, n, to_dev(hfr::pow_u64(DELTA, (uint64_t)c)), st));
+                std::vector<Fr> patch;
+                std::vector<size_t> rows;
+                for (size_t i = 0; i < sparse->n_perm; i++) {
+                    if ((int)sparse->perm_cells[4 * i] != c) continue;
+                    const size_t row = sparse->perm_cells[4 * i + 1], tc = sparse->perm_cells[4 * i + 2], trow = sparse->perm_cells[4 * i + 3];
+                    SB_REQUIRE(row < n && trow < n && (int)tc < count, "sparse permutation cell out of range");
+                    rows.push_back(row);
+                    patch.push_back(hfr::mul(hfr::pow_u64(DELTA, tc), hfr::pow_u64(omega, trow)));
+                }
+                for (size_t i = 0; i < rows.size(); i++)
+                    SB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)v + rows[i] * 32, &patch[i], 32, cudaMemcpyHostToDevice, st));
+                SB_CUDA_TRY(cudaStreamSynchronize(st));  // `patch` is about to go out of scope
+            }
             SB_CUDA_TRY(cudaMemcpyAsync(p, v, n * 32, cudaMemcpyDeviceToDevice, st));
             SB_TRY(dom_l2c(ctx, d, p, st));
             SB_TRY(dom_c2e(ctx, d, p, e, st));
@@ -295,8 +333,8 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
         }
         return SB_OK;
     };
-    SB_TRY(to_all_forms(fixed_values, pk->cs.F, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets, pk->fixed_comms));
-    SB_TRY(to_all_forms(sigma_values, pk->P, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets, pk->sigma_comms));
+    SB_TRY(to_all_forms(pk->cs.F, false, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets, pk->fixed_comms));
+    SB_TRY(to_all_forms(pk->P, true, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets, pk->sigma_comms));
     // l_0, l_last, l_blind (Lagrange unit vectors) -> extended; l_active = 1 - (l_last + l_blind)
     const int bf = pk->cs.blinding;
     std::vector<fr_t> tmp(n, fr_t::zero());
@@ -492,6 +530,16 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
     SB_REQUIRE(n_inst <= usable, "create_proof: too many instance values");
     const Fr omega = to_host(d->omega), omega_inv = to_host(d->omega_inv);
     uint8_t pt[64];
+    // wall-clock per stage (every stage ends on a stream synchronisation: MSM results and challenges come back to the host)
+    int stage = 0;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&]() {
+        cudaStreamSynchronize(st);
+        auto now = std::chrono::steady_clock::now();
+        if (stage < 12) ctx->last_proof_stage_ms[stage++] = std::chrono::duration<float, std::milli>(now - t_prev).count();
+        t_prev = now;
+    };
+    for (int i = 0; i < 12; i++) ctx->last_proof_stage_ms[i] = 0;
 
     // ---- transcript preamble
     tr.common_scalar(pk->transcript_repr);
@@ -537,6 +585,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         if (!tr.write_point(pt)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr theta = tr.squeeze();
+    mark();  // [0] instance / advice upload, blinding, lagrange_to_coeff, 3 advice commitments
 
     // column tables.  Lagrange: advice | fixed | instance | sigma | omega^i | lookup scratch (4)
     ColMap lm;
@@ -585,6 +634,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
     }
     const Fr beta = tr.squeeze();
     const Fr gamma = tr.squeeze();
+    mark();  // [1] lookup: compress, sort / permute, 2 iNTT, 2 commitments
 
     // ---- permutation argument
     const int chunk = cs.degree - 2;
@@ -638,6 +688,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         }
     }
 
+    mark();  // [2] permutation products: denominators, batch inversion, scan, commitments, iNTT + coset NTT
     // ---- lookup products
     for (size_t li = 0; li < lks.size(); li++) {
         LookupState &L = lks[li];
@@ -663,6 +714,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         if (!tr.write_point(pt)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
     }
 
+    mark();  // [3] lookup product
     // ---- vanishing argument: random polynomial from a child ChaCha20 stream (1-thread case of the fork)
     void *d_random;
     SB_TRY(scratch_get(ctx, "pf_random", n * 32, &d_random));
@@ -671,14 +723,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         rng.fill_bytes(seed, 32);
         ChaCha20Rng child;
         child.seed(seed);
-        std::vector<Fr> rp(n);
-        for (Fr &x : rp) x = child.next_fr();
-        SB_TRY(upload_frs(d_random, rp, st));
+        SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random, n, st));  // coefficient i = keystream block i
         (void)rng.next_fr();
         SB_TRY(msm_run(ctx, pk->srs->d_g, d_random, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("random polynomial commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr yy = tr.squeeze();
+    mark();  // [4] random polynomial (ChaCha20 on the device) + commitment
 
     // ---- evaluate_h: one fused program over the extended coset
     for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st));
@@ -688,6 +739,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st));
         SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st));
     }
+    mark();  // [5] coeff_to_extended of advice / instance / lookup polynomials
     ColMap em;
     em.advice0 = 0; em.fixed0 = A; em.instance0 = A + F;
     const int E_SIGMA = A + F + 1, E_PZ = E_SIGMA + P, E_L0 = E_PZ + n_sets, E_LLAST = E_L0 + 1, E_LACT = E_L0 + 2, E_X = E_L0 + 3, E_LK = E_L0 + 4;
@@ -765,6 +817,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
+    mark();  // [6] evaluate_h (fused program)
     // ---- quotient: / t(X), back to coefficients, pieces
     SB_TRY(dom_div_vanishing(ctx, d, d_h, st));
     SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
@@ -775,6 +828,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         if (!tr.write_point(pt)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr x = tr.squeeze();
+    mark();  // [7] divide by t(X), extended iNTT, quotient piece commitments
     const Fr xn = fpow(x, (uint64_t)n);
     // h(X) folded at x^n
     void *d_hfold;
@@ -821,6 +875,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
     for (size_t li = 0; li < lks.size(); li++)
         for (int i : i_lk[li]) tr.write_scalar(ev[i]);
 
+    mark();  // [8] h fold + the batched evaluations
     // ---- multi-open queries in halo2's order
     std::vector<Query> q;
     int next_id = 0;
@@ -850,16 +905,17 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
     for (int j = 0; j < P; j++) q.push_back({pid(pk->sigma_polys[j]), x, pk->sigma_polys[j], ev[i_sig[j]]});
     q.push_back({pid(d_hfold), x, d_hfold, ev[i_h]});
     q.push_back({pid(d_random), x, d_random, ev[i_rand]});
-    return shplonk(ctx, pk, tr, q, st);
+    int32_t rc_sh = shplonk(ctx, pk, tr, q, st);
+    mark();  // [9] SHPLONK
+    return rc_sh;
 }
 
 }  // namespace
 
 extern "C" {
 
-int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
-                     const uint8_t transcript_repr[32], sb_pk **out_pk) {
-    if (!ctx || !srs || !cs_json || !fixed_values || !sigma_values || !transcript_repr || !out_pk) return SB_ERR_ARG;
+static int32_t pk_create_common(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
+                                const SparseAssignment *sparse, const uint8_t transcript_repr[32], sb_pk **out_pk) {
     SB_REQUIRE(srs->k == k, "sb_pk_create: SRS size does not match k (downsize first)");
     CtxGuard g(ctx);
     sb_pk *pk = new sb_pk();
@@ -881,7 +937,7 @@ int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32
     pk->ext_n = (size_t)1 << pk->ext_k;
     if (pk->n < 128) { set_last_error("sb_pk_create: k < 7 is not supported"); sb_domain_destroy(pk->dom); delete pk; return SB_ERR_ARG; }
     try {
-        rc = pk_build(ctx, pk, fixed_values, sigma_values, ctx->stream);
+        rc = pk_build(ctx, pk, fixed_values, sigma_values, sparse, ctx->stream);
     } catch (const std::exception &e) {
         set_last_error("sb_pk_create: %s", e.what());
         rc = SB_ERR_ARG;
@@ -894,6 +950,21 @@ int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32
     }
     *out_pk = pk;
     return SB_OK;
+}
+
+int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
+                     const uint8_t transcript_repr[32], sb_pk **out_pk) {
+    if (!ctx || !srs || !cs_json || !fixed_values || !sigma_values || !transcript_repr || !out_pk) return SB_ERR_ARG;
+    return pk_create_common(ctx, srs, cs_json, k, fixed_values, sigma_values, nullptr, transcript_repr, out_pk);
+}
+
+int32_t sb_pk_create_sparse(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint32_t *fixed_cells, const uint8_t *fixed_cell_values,
+                            size_t n_fixed, const uint32_t *perm_cells, size_t n_perm, const uint8_t transcript_repr[32], sb_pk **out_pk) {
+    if (!ctx || !srs || !cs_json || !transcript_repr || !out_pk || (n_fixed && (!fixed_cells || !fixed_cell_values)) || (n_perm && !perm_cells)) return SB_ERR_ARG;
+    SparseAssignment sp;
+    sp.fixed_cells = fixed_cells; sp.fixed_values = fixed_cell_values; sp.n_fixed = n_fixed;
+    sp.perm_cells = perm_cells; sp.n_perm = n_perm;
+    return pk_create_common(ctx, srs, cs_json, k, nullptr, nullptr, &sp, transcript_repr, out_pk);
 }
 
 int32_t sb_pk_destroy(sb_pk *pk) {
@@ -1044,6 +1115,67 @@ int32_t sb_kate_division(sb_ctx *ctx, const uint8_t *a, uint32_t log_n, const ui
     return SB_OK;
 }
 
+// `ParamsKZG::setup(k, rng)` (utils.rs:70) with an explicit secret: g[i] = [tau^i] G, g_lagrange[i] = [L_i(tau)] G, all on the device.
+// UNSAFE by construction (the caller knows tau): test / benchmark SRS only.
+int32_t sb_srs_setup_unsafe(sb_ctx *ctx, uint32_t k, const uint8_t tau_mont[32], sb_srs **out_srs) {
+    if (!ctx || !tau_mont || !out_srs) return SB_ERR_ARG;
+    SB_REQUIRE(k >= 7 && k <= 26, "sb_srs_setup_unsafe: k must be in [7, 26]");
+    CtxGuard g(ctx);
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)1 << k;
+    Fr tau;
+    memcpy(tau.v, tau_mont, 32);
+    sb_domain *dom = nullptr;
+    SB_TRY(sb_domain_create(ctx, 2, k, &dom));
+    sb_srs *srs = new sb_srs();
+    srs->k = k;
+    if (cudaMalloc(&srs->d_g, n * 64) != cudaSuccess || cudaMalloc(&srs->d_g_lagrange, n * 64) != cudaSuccess) {
+        set_last_error("sb_srs_setup_unsafe: cudaMalloc(2 x %zu) failed", n * 64);
+        if (srs->d_g) cudaFree(srs->d_g);
+        delete srs;
+        sb_domain_destroy(dom);
+        return SB_ERR_ALLOC;
+    }
+    void *d_s, *d_w;
+    int32_t rc = scratch_get(ctx, "setup_s", n * 32, &d_s);
+    if (rc == SB_OK) rc = scratch_get(ctx, "setup_w", n * 32, &d_w);
+    if (rc == SB_OK) rc = fr_gen_powers(ctx, d_s, to_dev(tau), n, st);
+    if (rc == SB_OK) rc = g1_fixed_base_mul(ctx, d_s, n, srs->d_g, st);
+    // L_i(tau) = omega^i * (tau^n - 1) / (n * (tau - omega^i))
+    if (rc == SB_OK) rc = fr_gen_powers(ctx, d_w, dom->omega, n, st);
+    if (rc == SB_OK) rc = expr_eval(ctx, compile_terms({e_sub(ec(tau), e_col(0, 0))}, nullptr), {d_w}, k, 0, d_s, st);
+    if (rc == SB_OK) rc = fr_batch_invert(ctx, d_s, n, st);
+    if (rc == SB_OK) {
+        const Fr c = hfr::mul(hfr::sub(hfr::pow_u64(tau, (uint64_t)n), hfr::ONE), to_host(dom->ifft_divisor));
+        rc = expr_eval(ctx, compile_terms({e_mul(e_mul(ec(c), e_col(0, 0)), e_col(1, 0))}, nullptr), {d_w, d_s}, k, 0, d_s, st);
+    }
+    if (rc == SB_OK) rc = g1_fixed_base_mul(ctx, d_s, n, srs->d_g_lagrange, st);
+    if (rc == SB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = SB_ERR_CUDA;
+    sb_domain_destroy(dom);
+    if (rc != SB_OK) {
+        cudaFree(srs->d_g);
+        cudaFree(srs->d_g_lagrange);
+        delete srs;
+        return rc;
+    }
+    *out_srs = srs;
+    return SB_OK;
+}
+int32_t sb_srs_download(sb_ctx *ctx, const sb_srs *srs, uint8_t *g_out, uint8_t *g_lagrange_out) {
+    if (!ctx || !srs || !g_out || !g_lagrange_out) return SB_ERR_ARG;
+    CtxGuard g(ctx);
+    const size_t bytes = (size_t)64 << srs->k;
+    SB_CUDA_TRY(cudaMemcpyAsync(g_out, srs->d_g, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(g_lagrange_out, srs->d_g_lagrange, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]) {
+    if (!ctx || !out_ms) return SB_ERR_ARG;
+    for (int i = 0; i < 12; i++) out_ms[i] = ctx->last_proof_stage_ms[i];
+    return SB_OK;
+}
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]) {
     if (!ctx || !out_ms || !out_program) return SB_ERR_ARG;
     *out_ms = ctx->last_h_ms;

@@ -16,6 +16,7 @@ int32_t fr_running_product(sb_ctx *ctx, const void *d_a, size_t n_a, const fr_t 
 int32_t fr_eval_polys(sb_ctx *ctx, const std::vector<const void *> &polys, const std::vector<fr_t> &xs, size_t n, std::vector<fr_t> &out, cudaStream_t st);
 int32_t sort_u256(sb_ctx *ctx, void *d_a, size_t count, size_t capacity_pow2, cudaStream_t st);
 int32_t lookup_permute(sb_ctx *ctx, const void *d_in, const void *d_tab, size_t n, size_t u, void *d_a_perm, void *d_s_perm, cudaStream_t st);
+int32_t chacha_fr_fill(sb_ctx *ctx, const uint32_t key[8], uint64_t counter0, void *d_out, size_t n, cudaStream_t st);
 int32_t fr_axpy(sb_ctx *ctx, void *d_acc, const void *d_p, const fr_t &s, size_t n, bool first, cudaStream_t st);
 int32_t fr_sub_head(sb_ctx *ctx, void *d_acc, const fr_t *c, uint32_t k, cudaStream_t st);
 

@@ -441,6 +441,45 @@ int32_t lookup_permute(sb_ctx *ctx, const void *d_in, const void *d_tab, size_t 
     return SB_OK;
 }
 
+// ------------------------------------------------------------------ ChaCha20 -> Fr (vanishing argument's random polynomial)
+// halo2curves `Fr::random` consumes 8 x next_u64 = 16 keystream words = exactly ONE ChaCha20 block, so coefficient i of the
+// random polynomial is block (counter0 + i) of the child stream: counter-mode makes the whole column one parallel kernel.
+struct ChaChaKey { uint32_t k[8]; };
+__device__ __forceinline__ uint32_t rotl32d(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+#define SB_CQR(a, b, c, d) a += b; d = rotl32d(d ^ a, 16); c += d; b = rotl32d(b ^ c, 12); a += b; d = rotl32d(d ^ a, 8); c += d; b = rotl32d(b ^ c, 7);
+__global__ void chacha_fr_kernel(ChaChaKey key, uint64_t counter0, uint4 *out, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t ctr = counter0 + i;
+    uint32_t init[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6], key.k[7],
+                         (uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t s[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) s[q] = init[q];
+    for (int r = 0; r < 10; r++) {
+        SB_CQR(s[0], s[4], s[8], s[12]) SB_CQR(s[1], s[5], s[9], s[13]) SB_CQR(s[2], s[6], s[10], s[14]) SB_CQR(s[3], s[7], s[11], s[15])
+        SB_CQR(s[0], s[5], s[10], s[15]) SB_CQR(s[1], s[6], s[11], s[12]) SB_CQR(s[2], s[7], s[8], s[13]) SB_CQR(s[3], s[4], s[9], s[14])
+    }
+    fr_t lo, hi;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        lo.v[q] = s[q] + init[q];
+        hi.v[q] = s[8 + q] + init[8 + q];
+    }
+    // from_u512: (lo + hi * 2^256) mod r in Montgomery form = lo * R^2 * R^-1 + hi * R^3 * R^-1
+    const fr_t r2 = fr_t::r2();
+    const fr_t r3 = mul(r2, r2);
+    store_fp(out + 2 * i, add(mul(lo, r2), mul(hi, r3)));
+}
+#undef SB_CQR
+int32_t chacha_fr_fill(sb_ctx *ctx, const uint32_t key[8], uint64_t counter0, void *d_out, size_t n, cudaStream_t st) {
+    if (n == 0) return SB_OK;
+    ChaChaKey k;
+    for (int i = 0; i < 8; i++) k.k[i] = key[i];
+    SB_LAUNCH(ctx, chacha_fr_kernel, (unsigned)((n + 255) / 256), 256, 0, st, k, counter0, (uint4 *)d_out, (uint64_t)n);
+    return SB_OK;
+}
+
 // ------------------------------------------------------------------ linear combinations
 __global__ void fr_axpy_kernel(uint4 *acc, const uint4 *p, fr_t s, uint64_t n, int first) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;

@@ -43,47 +43,22 @@ class ParamsKZG:
         return self
 
     @classmethod
-    def setup(cls, k: int, tau: int, ctx: Optional[Context] = None) -> "ParamsKZG":
+    def setup(cls, k: int, tau: int, ctx: Optional[Context] = None, download: bool = True) -> "ParamsKZG":
         """`ParamsKZG::setup(k, rng)` with an explicit (UNSAFE, test-only) secret tau: g[i] = [tau^i] G and
-        g_lagrange[i] = [L_i(tau)] G.  The 2 x 2^k fixed-base products run on the GPU; the scalars are host
-        integers (setup is not on the proving path)."""
+        g_lagrange[i] = [L_i(tau)] G, computed entirely on the GPU.  `download=False` skips the host copies."""
         from . import fields
-        ctx = ctx or default_context()
-        r, n = fields.FR_MODULUS, 1 << k
-        w = fields.omega(k)
-        mono, t = [], 1
-        for _ in range(n):
-            mono.append(t)
-            t = t * tau % r
-        tn = (pow(tau, n, r) - 1) % r
-        ninv = pow(n, -1, r)
-        # L_i(tau) = omega^i (tau^n - 1) / (n (tau - omega^i)), denominators inverted in one batch
-        wi, dens, ws = 1, [], []
-        for _ in range(n):
-            ws.append(wi)
-            dens.append((tau - wi) % r)
-            wi = wi * w % r
-        pref, acc = [], 1
-        for dd in dens:
-            pref.append(acc)
-            acc = acc * dd % r
-        inv = pow(acc, -1, r)
-        lag = [0] * n
-        for i in range(n - 1, -1, -1):
-            lag[i] = ws[i] * tn % r * ninv % r * (inv * pref[i] % r) % r
-            inv = inv * dens[i] % r
-        scal = np.concatenate([fields.fr_to_mont(x) for x in mono + lag]).reshape(2 * n, 4)
-        d_s = ctx.alloc(scal.nbytes)
-        d_p = ctx.alloc(2 * n * 64)
-        try:
-            ctx.upload(d_s, scal)
-            _lib.check(_lib.lib().sb_g1_fixed_base_mul_dev(ctx.handle, ctypes.c_void_p(d_s), ctypes.c_size_t(2 * n), ctypes.c_void_p(d_p), None), "sb_g1_fixed_base_mul_dev")
-            ctx.synchronize()
-            pts = ctx.download(d_p, 2 * n * 64).reshape(2 * n, 8)
-        finally:
-            ctx.free(d_s)
-            ctx.free(d_p)
-        return cls(k, pts[:n].copy(), pts[n:].copy(), b"", ctx)
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self._k, self.n = k, 1 << k
+        self.tail = b""
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sb_srs_setup_unsafe(self.ctx.handle, ctypes.c_uint32(k), ptr(fields.fr_to_mont(tau)), ctypes.byref(self._h)), "sb_srs_setup_unsafe")
+        self.g = self.g_lagrange = None
+        if download:
+            self.g = np.zeros((self.n, 8), dtype=np.uint64)
+            self.g_lagrange = np.zeros((self.n, 8), dtype=np.uint64)
+            _lib.check(_lib.lib().sb_srs_download(self.ctx.handle, self._h, ptr(self.g), ptr(self.g_lagrange)), "sb_srs_download")
+        return self
 
     @classmethod
     def read(cls, path: str, ctx: Optional[Context] = None) -> "ParamsKZG":

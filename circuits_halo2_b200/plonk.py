@@ -50,6 +50,27 @@ class ProvingKey:
         _lib.check(_lib.lib().sb_pk_create(self.ctx.handle, params.handle, ctypes.c_char_p(text), ctypes.c_uint32(params.k()), ptr(fv), ptr(sv),
                                            ptr(fields.fr_to_mont(transcript_repr)), ctypes.byref(self._h)), "sb_pk_create")
 
+    @classmethod
+    def from_sparse(cls, params: ParamsKZG, cs, fixed_cells, fixed_cell_values, perm_cells, transcript_repr: int, ctx: Optional[Context] = None) -> "ProvingKey":
+        """Build the key from keygen's sparse output: fixed_cells (m, 2) uint32 (col, row) with fixed_cell_values (m, 4) uint64,
+        perm_cells (p, 4) uint32 (col, row, to_col, to_row).  Everything dense is materialised on the GPU."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or params.ctx
+        self.params = params
+        self.cs = json.loads(cs) if isinstance(cs, str) else cs
+        text = json.dumps(self.cs).encode()
+        self.num_fixed, self.num_sigma = self.cs["num_fixed_columns"], len(self.cs["permutation_columns"])
+        fc = np.ascontiguousarray(fixed_cells, dtype=np.uint32).reshape(-1, 2)
+        fvv = np.ascontiguousarray(as_u64(fixed_cell_values, 4)).reshape(-1, 4)
+        pc = np.ascontiguousarray(perm_cells, dtype=np.uint32).reshape(-1, 4)
+        if fc.shape[0] != fvv.shape[0]:
+            raise AssertionError("ProvingKey.from_sparse: one value per fixed cell")
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sb_pk_create_sparse(self.ctx.handle, params.handle, ctypes.c_char_p(text), ctypes.c_uint32(params.k()), ptr(fc), ptr(fvv),
+                                                  ctypes.c_size_t(fc.shape[0]), ptr(pc), ctypes.c_size_t(pc.shape[0]), ptr(fields.fr_to_mont(transcript_repr)),
+                                                  ctypes.byref(self._h)), "sb_pk_create_sparse")
+        return self
+
     @property
     def handle(self):
         return self._h

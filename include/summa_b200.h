@@ -70,6 +70,10 @@ int32_t sb_msm_g1_dev(sb_ctx *ctx, const void *d_bases, const void *d_scalars, s
 /* ---- SRS: halo2_proofs::poly::kzg::commitment::ParamsKZG (utils.rs:55,64,70) ---------------- */
 /* g / g_lagrange: 2^k affine points each, exactly the arrays ParamsKZG holds */
 int32_t sb_srs_upload(sb_ctx *ctx, uint32_t k, const uint8_t *g, const uint8_t *g_lagrange, sb_srs **out_srs);
+/* `ParamsKZG::setup(k, rng)` (utils.rs:70) with an explicit secret tau (Montgomery Fr): UNSAFE test / benchmark SRS,
+ * generated entirely on the device (powers of tau, Lagrange weights, 2 x 2^k fixed-base products) */
+int32_t sb_srs_setup_unsafe(sb_ctx *ctx, uint32_t k, const uint8_t tau[32], sb_srs **out_srs);
+int32_t sb_srs_download(sb_ctx *ctx, const sb_srs *srs, uint8_t *g_out, uint8_t *g_lagrange_out);
 /* same handle over bases that already live on the device (borrowed: the caller keeps ownership) */
 int32_t sb_srs_wrap_dev(sb_ctx *ctx, uint32_t k, const void *d_g, const void *d_g_lagrange, sb_srs **out_srs);
 int32_t sb_srs_destroy(sb_srs *srs);
@@ -115,6 +119,11 @@ int32_t sb_divide_by_vanishing_poly_dev(sb_ctx *ctx, const sb_domain *d, void *d
 typedef struct sb_pk sb_pk;
 int32_t sb_pk_create(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
                      const uint8_t transcript_repr[32] /* vk.transcript_repr, Montgomery */, sb_pk **out_pk);
+/* same, from keygen's sparse output: the assigned fixed cells (col,row pairs + 32 B values; all other cells 0) and the
+ * cells (col,row,to_col,to_row) that copy constraints moved away from the identity permutation.  Dense columns are built
+ * on the device, so a k = 20..23 key costs no host memory. */
+int32_t sb_pk_create_sparse(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint32_t *fixed_cells, const uint8_t *fixed_cell_values,
+                            size_t n_fixed, const uint32_t *perm_cells, size_t n_perm, const uint8_t transcript_repr[32], sb_pk **out_pk);
 int32_t sb_pk_destroy(sb_pk *pk);
 /* keygen_vk's commitments of the fixed and permutation columns (affine, 64 B each) */
 int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_comms);
@@ -126,6 +135,10 @@ int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, 
 /* device time (ms) of the fused evaluate_h kernel of the last create_proof on this context and its program shape:
  * instructions, field products, additions/subtractions, live value slots */
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);
+/* host wall-clock (ms) of the stages of the last create_proof: [0] advice upload + commitments, [1] lookup permute + commitments,
+ * [2] permutation products, [3] lookup product, [4] random polynomial, [5] coset NTTs, [6] evaluate_h, [7] quotient + commitments,
+ * [8] evaluations, [9] SHPLONK */
+int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]);
 /* building blocks of create_proof with host buffers (halo2 arithmetic::{eval_polynomial, kate_division},
  * poly::batch_invert, the grand-product scan of permutation / lookup Z, lookup `permute_expression_pair`) */
 int32_t sb_fr_batch_invert(sb_ctx *ctx, uint8_t *a, size_t n);                                   /* zeros stay zero */

@@ -199,3 +199,32 @@ def test_create_proof_larger_k_synthetic_srs(ctx, golden_dir, k):
     HP.create_proof(oparams, opk, instances, advice, ChaCha20Rng.seed_from_u64(k), tr)
     got = sb.create_proof(pk, instances, advice, sb.seed_from_u64(k), sb.TRANSCRIPT_KECCAK)
     assert got == tr.finalize()
+
+
+def test_sparse_key_and_device_srs_match_dense_path(ctx, golden_dir):
+    """ProvingKey.from_sparse (fixture of tests/golden/make_assignment.py) + ParamsKZG.setup on the device give the same
+    proof as the dense path, and that proof equals the oracle's at k = 14."""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import fields
+    k = 14
+    n = 1 << k
+    fx = np.load(os.path.join(golden_dir, "mst_inclusion_assignment.npz"))
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    params = sb.ParamsKZG.setup(k, 0xABCDEF, ctx)
+    pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x77, ctx)
+    advice = np.zeros((3, n, 4), dtype=np.uint64)
+    advice[fx["advice_cells"][:, 0], fx["advice_cells"][:, 1]] = fx["advice_values"]
+    instances = [fields.fr_from_mont(v) for v in fx["instances"]]
+    got = sb.create_proof(pk, instances, advice, sb.seed_from_u64(5), sb.TRANSCRIPT_KECCAK)
+    # oracle over the same SRS bytes, circuit re-synthesised by the oracle at this k
+    tree = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"))
+    lay = C.synthesize(k, tree.generate_proof(0), 4, 2, 8)
+    oparams = HP.Params(k, params.g, params.g_lagrange, threads=8)
+    fixed = np.stack([HP.from_ints(c) for c in C.fixed_columns(lay)])
+    opk = HP.ProvingKey(oparams, cs, fixed, C.permutation_mapping(lay), transcript_repr=0x77)
+    f, s = pk.commitments()
+    assert [B.g1_from_mont_bytes(x.tobytes()) for x in f] == opk.fixed_commitments
+    assert [B.g1_from_mont_bytes(x.tobytes()) for x in s] == opk.sigma_commitments
+    tr = KeccakTranscript()
+    HP.create_proof(oparams, opk, instances, np.stack([HP.from_ints(c) for c in C.advice_columns(lay)]), ChaCha20Rng.seed_from_u64(5), tr)
+    assert got == tr.finalize()

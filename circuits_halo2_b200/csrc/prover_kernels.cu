@@ -466,6 +466,14 @@ __global__ void chacha_fr_kernel(ChaChaKey key, uint64_t counter0, uint4 *out, u
         lo.v[q] = s[q] + init[q];
         hi.v[q] = s[8 + q] + init[8 + q];
     }
+    // lo, hi are arbitrary 256-bit integers (< 6 r): bring them below r first, the Montgomery product needs operands < 2^254
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        fr_t t = lo;
+        final_sub<FrParams>(lo.v, t.v);
+        t = hi;
+        final_sub<FrParams>(hi.v, t.v);
+    }
     // from_u512: (lo + hi * 2^256) mod r in Montgomery form = lo * R^2 * R^-1 + hi * R^3 * R^-1
     const fr_t r2 = fr_t::r2();
     const fr_t r3 = mul(r2, r2);

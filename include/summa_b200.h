@@ -153,6 +153,28 @@ int32_t sb_test_blake2b512(const uint8_t *data, size_t len, const uint8_t person
 int32_t sb_test_chacha_fr(uint64_t seed_u64, uint32_t skip_bytes, uint32_t count, uint8_t *out);
 int32_t sb_test_host_fr(int32_t op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 
+/* ---- zk_prover::merkle_sum_tree: MerkleSumTree::from_entries / Tree::generate_proof ------------------
+ * The tree is built and kept in HBM: Keccak-256 of the usernames (entry.rs:15-27), Poseidon leaf hashes
+ * H(username, balances...) (node.rs:16-27,57-69), middle nodes H(sum balances..., hash_l, hash_r) (node.rs:32-45,73-84),
+ * one launch per level (utils/build_tree.rs:5-78).  Entries are padded with zero entries to 2^depth, depth = ceil(log2 n)
+ * (mst.rs:106-114).  All field elements cross the ABI as 32 B Montgomery Fr. */
+typedef struct sb_mst sb_mst;
+/* usernames: concatenated UTF-8 bytes, entry i = usernames[offsets[i] .. offsets[i+1]); balances: n_entries x n_currencies u64 (N_BYTES <= 8) */
+int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint64_t *balances, size_t n_entries, uint32_t n_currencies,
+                     sb_mst **out_mst);
+/* build_merkle_tree_from_leaves over Node::leaf_node_from_preimage: n_leaves (a power of two) x (n_currencies + 1) x 32 B: [username, balances...] */
+int32_t sb_mst_build_from_preimages(sb_ctx *ctx, const uint8_t *leaf_preimages, size_t n_leaves, uint32_t n_currencies, sb_mst **out_mst);
+int32_t sb_mst_destroy(sb_mst *mst);
+/* depth, N_CURRENCIES and the device time (ms) the build took (H2D of the entries + all kernels) */
+int32_t sb_mst_shape(const sb_mst *mst, uint32_t *out_depth, uint32_t *out_n_currencies, float *out_build_ms);
+int32_t sb_mst_root(const sb_mst *mst, uint8_t out_hash[32], uint8_t *out_balances /* n_currencies x 32 B */);
+int32_t sb_mst_node(const sb_mst *mst, uint32_t level, size_t index, uint8_t out_hash[32], uint8_t *out_balances); /* Tree::nodes()[level][index] */
+int32_t sb_mst_level_hashes(const sb_mst *mst, uint32_t level, uint8_t *out_hashes /* 2^(depth-level) x 32 B */);
+/* Tree::generate_proof (tree.rs:85-137) for n_proofs user indices at once.  Per proof, out_preimages holds
+ * entry preimage (n_cur+1) | sibling leaf preimage (n_cur+1) | (depth-1) x sibling middle-node preimage (n_cur+2)  field elements,
+ * out_path_indices holds depth bytes (0 = the node is a left child). */
+int32_t sb_mst_proofs(const sb_mst *mst, const uint64_t *indices, size_t n_proofs, uint8_t *out_preimages, uint8_t *out_path_indices);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int32_t sb_launch_count(const sb_ctx *ctx, uint64_t *out);

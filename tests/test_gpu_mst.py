@@ -1,0 +1,114 @@
+"""GPU parity tests of the Merkle-sum-tree build (python -m pytest tests -m gpu).
+
+The CUDA tree (Keccak-256 usernames, Poseidon leaves / middle nodes, Merkle proofs) must equal the CPU oracle
+(oracle/mst.py, pinned on the Rust tests' known answers) bit for bit; at 2^20 users the size-independent properties
+are root balances = column sums and oracle-side verification of GPU Merkle proofs (tree.rs:139-186)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as B
+from oracle import mst as M
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_verify(proof, n_cur):
+    """Tree::verify_proof (tree.rs:139-186) with the oracle's Poseidon."""
+    node_hash = M.poseidon_hash(proof.entry_preimage)
+    bal = list(proof.entry_preimage[1:])
+    sib_hash, sib_bal = M.poseidon_hash(proof.sibling_leaf_node_hash_preimage), proof.sibling_leaf_node_hash_preimage[1:]
+    for lvl, pos in enumerate(proof.path_indices):
+        if lvl > 0:
+            pre = proof.sibling_middle_node_hash_preimages[lvl - 1]
+            sib_hash, sib_bal = M.poseidon_hash(pre), pre[:n_cur]
+        bal = [(a + b) % B.R for a, b in zip(bal, sib_bal)]
+        hs = [node_hash, sib_hash] if pos == 0 else [sib_hash, node_hash]
+        node_hash = M.poseidon_hash(bal + hs)
+    return node_hash == proof.root.hash and bal == proof.root.balances
+
+
+def test_entry_16_csv_known_answers(ctx, golden_dir):
+    import circuits_halo2_b200 as sb
+    gold = json.load(open(os.path.join(golden_dir, "mst_hashes.json")))
+    t = sb.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"), ctx)
+    assert t.depth() == 4 and t.n_currencies == 2
+    assert hex(t.node(0, 0).hash) in gold["circuit_tests_hex"]      # circuits/tests.rs:341
+    assert hex(t.node(0, 1).hash) in gold["circuit_tests_hex"]      # circuits/tests.rs:346
+    root = t.root()
+    assert hex(root.hash) in gold["backend_tests_hex"]              # backend/src/tests.rs:265
+    assert root.balances == [556862, 556862]                        # merkle_sum_tree/tests.rs:24
+    o = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"))
+    for level in range(5):
+        for i in range(1 << (4 - level)):
+            n = t.node(level, i)
+            assert (n.hash, n.balances) == (o.nodes[level][i][0], o.nodes[level][i][1]), (level, i)
+    for idx in (0, 1, 7, 15):
+        p, q = t.generate_proof(idx), o.generate_proof(idx)
+        assert p.entry_preimage == q["entry"].preimage()
+        assert p.sibling_leaf_node_hash_preimage == q["sibling_leaf_node_hash_preimage"]
+        assert p.sibling_middle_node_hash_preimages == q["sibling_middle_node_hash_preimages"]
+        assert p.path_indices == q["path_indices"]
+        assert oracle_verify(p, 2)
+    with pytest.raises(IndexError):
+        t.generate_proof(16)
+
+
+@pytest.mark.parametrize("n_entries,n_cur", [(1, 1), (2, 2), (3, 2), (5, 3), (16, 1), (100, 2), (513, 4), (1000, 8)])
+def test_ragged_sizes_match_oracle(ctx, n_entries, n_cur):
+    """non-power-of-two entry counts are padded with zero entries (mst.rs:106-114); long and empty usernames exercise the Keccak padding"""
+    import circuits_halo2_b200 as sb
+    rng = np.random.default_rng(n_entries * 10 + n_cur)
+    names = []
+    for i in range(n_entries):
+        ln = [0, 1, 8, 135, 136, 137, 271, 272, 300][i % 9] if i % 5 == 0 else int(rng.integers(1, 24))
+        names.append(bytes(rng.integers(33, 127, size=ln, dtype=np.uint8)).decode())
+    bal = rng.integers(0, 1 << 63, size=(n_entries, n_cur), dtype=np.uint64)
+    bal[0, :] = np.uint64((1 << 64) - 1)
+    ents = [sb.Entry(nm, [int(x) for x in bal[i]]) for i, nm in enumerate(names)]
+    t = sb.MerkleSumTree.from_entries(ents, ctx=ctx)
+    o = M.MerkleSumTree([M.Entry(nm, [int(x) for x in bal[i]]) for i, nm in enumerate(names)])
+    assert t.depth() == o.depth
+    for level in range(o.depth + 1):
+        got = t.level_hashes(level)
+        ref = np.stack([np.frombuffer(B.fr_to_mont_bytes(h), dtype=np.uint64) for h, _ in o.nodes[level]])
+        assert (got == ref).all(), level
+    r = t.root()
+    assert (r.hash, r.balances) == (o.root[0], o.root[1])
+    if o.depth > 0:
+        idx = [0, n_entries - 1, (1 << o.depth) - 1]
+        for p, i in zip(t.generate_proofs(idx), idx):
+            q = o.generate_proof(i)
+            assert p.sibling_middle_node_hash_preimages == q["sibling_middle_node_hash_preimages"] and p.path_indices == q["path_indices"]
+            assert p.sibling_leaf_node_hash_preimage == q["sibling_leaf_node_hash_preimage"]
+
+
+def test_from_leaf_preimages_equals_from_entries(ctx):
+    import circuits_halo2_b200 as sb
+    ents = [sb.Entry(f"user_{i}", [i * 7 + 1, i * 11 + 2]) for i in range(64)]
+    t = sb.MerkleSumTree.from_entries(ents, ctx=ctx)
+    pre = np.stack([np.stack([np.frombuffer(B.fr_to_mont_bytes(v), dtype=np.uint64) for v in M.Entry(e.username, e.balances).preimage()]) for e in ents])
+    u = sb.MerkleSumTree.from_leaf_preimages(pre, 2, ctx)
+    assert (t.level_hashes(0) == u.level_hashes(0)).all() and t.root() == u.root()
+    with pytest.raises(Exception):
+        sb.MerkleSumTree.from_leaf_preimages(pre[:48], 2, ctx)   # build_tree.rs:17: the leaf layer must be a power of two
+
+
+def test_two_to_the_twenty_users(ctx):
+    """config 3's snapshot: 2^20 users, 2 currencies.  Properties: root balances are the column sums; GPU Merkle proofs verify with the oracle's Poseidon."""
+    import circuits_halo2_b200 as sb
+    n = 1 << 20
+    rng = np.random.default_rng(20)
+    bal = rng.integers(0, 1 << 40, size=(n, 2), dtype=np.uint64)
+    names = [b"user_%d" % i for i in range(n)]
+    t = sb.MerkleSumTree.from_arrays(names, bal, ctx=ctx)
+    assert t.depth() == 20
+    root = t.root()
+    assert root.balances == [int(bal[:, 0].astype(object).sum()), int(bal[:, 1].astype(object).sum())]
+    idx = [0, 1, 123456, n - 1]
+    for p, i in zip(t.generate_proofs(idx), idx):
+        assert p.entry_preimage == M.Entry(names[i].decode(), [int(x) for x in bal[i]]).preimage()
+        assert oracle_verify(p, 2)
+    print(f"\n[mst] 2^20 users x 2 currencies built in {t.build_ms:.1f} ms on the device")

@@ -101,6 +101,8 @@ int32_t fr_scale(sb_ctx *ctx, void *d_a, size_t n, const fr_t &s, cudaStream_t s
 int32_t fr_scale_pattern(sb_ctx *ctx, void *d_a, size_t n, const fr_t *pat, uint32_t m, cudaStream_t st);
 // dst[i] = i < n_src ? src[i] * pat[i % m] : 0   for i < n_dst
 int32_t fr_scale_pattern_pad(sb_ctx *ctx, const void *d_src, size_t n_src, void *d_dst, size_t n_dst, const fr_t *pat, uint32_t m, cudaStream_t st);
+// d_out[(r << shift) + j] = d_in[j * 2^log_n + r] * pat[j]
+int32_t fr_coset_interleave_scale(sb_ctx *ctx, const void *d_in, void *d_out, uint32_t log_n, uint32_t shift, const fr_t *pat, cudaStream_t st);
 int32_t fp_vec_op(sb_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n, cudaStream_t st);
 
 // host-side field helpers (exact, slow; plan constants only)

@@ -168,6 +168,7 @@ struct ExprArgs {
     const uint4 *consts;
     const int32_t *inputs;
     const uint4 *const *cols;
+    const uint8_t *col_shift;  // per column: log2 of the element stride (0 = compact column, 3 = one coset of an extended column)
     uint32_t log_n, rot_scale_log;
     uint4 *out;
     uint32_t out_slot;  // (n_slots << 16) | output slot
@@ -188,7 +189,7 @@ __device__ __forceinline__ fr_t expr_fetch(uint32_t opnd, const ExprArgs &A, con
         const uint64_t mask = (1ull << A.log_n) - 1;
         const uint64_t j = (row + (uint64_t)((int64_t)rot * (int64_t)(1ll << A.rot_scale_log))) & mask;
         const uint4 *base = A.cols[col];
-        r = ldg_fp<FrParams>(base + 2 * j);
+        r = ldg_fp<FrParams>(base + 2 * (j << __ldg(A.col_shift + col)));
     }
     return r;
 }
@@ -224,18 +225,22 @@ __global__ void __launch_bounds__(EXPR_THREADS) expr_eval_kernel(const ExprArgs 
     A.out[2 * row + 1] = hi[out_slot * EXPR_THREADS + tid];
 }
 
-int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st) {
+int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st,
+                  const std::vector<uint8_t> *col_shift) {
     const uint64_t n = 1ull << log_n;
     SB_REQUIRE(n >= (uint64_t)EXPR_THREADS, "expr_eval: domain smaller than one CTA");
     SB_REQUIRE(prog.n_slots >= 1 && prog.n_slots <= 48, "expr_eval: too many live values");
     const size_t code_b = prog.code.size() * 4, const_b = prog.consts.size() * 32, in_b = prog.inputs.size() * 4, col_b = cols.size() * sizeof(void *);
     const size_t off_const = (code_b + 31) & ~(size_t)31, off_in = off_const + ((const_b + 31) & ~(size_t)31), off_col = off_in + ((in_b + 31) & ~(size_t)31);
-    const size_t total = off_col + col_b + 32;
+    const size_t off_shift = off_col + ((col_b + 31) & ~(size_t)31);
+    const size_t total = off_shift + cols.size() + 32;
+    SB_REQUIRE(!col_shift || col_shift->size() == cols.size(), "expr_eval: one stride per column");
     std::vector<uint8_t> host(total, 0);
     memcpy(host.data(), prog.code.data(), code_b);
     if (const_b) memcpy(host.data() + off_const, prog.consts.data(), const_b);
     if (in_b) memcpy(host.data() + off_in, prog.inputs.data(), in_b);
     if (col_b) memcpy(host.data() + off_col, cols.data(), col_b);
+    if (col_shift && !cols.empty()) memcpy(host.data() + off_shift, col_shift->data(), cols.size());
     // each launch gets its own staging slice so that programs queued back-to-back on one stream do not clobber each other
     static thread_local uint32_t ring = 0;
     const uint32_t slice = ring++ % 8;
@@ -252,6 +257,7 @@ int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void
     A.consts = (const uint4 *)(d_prog + off_const);
     A.inputs = (const int32_t *)(d_prog + off_in);
     A.cols = (const uint4 *const *)(d_prog + off_col);
+    A.col_shift = (const uint8_t *)(d_prog + off_shift);
     A.log_n = log_n;
     A.rot_scale_log = rot_scale_log;
     A.out = (uint4 *)d_out;

@@ -72,6 +72,28 @@ int32_t fr_scale_pattern_pad(sb_ctx *ctx, const void *d_src, size_t n_src, void 
     return SB_OK;
 }
 
+// out[(r << shift) + j] = in[j * n + r] * pat[j]   (coset-major -> extended order; pat = t_inv of divide_by_vanishing_poly)
+__global__ void fr_coset_interleave_scale_kernel(const uint4 *in, uint4 *out, uint32_t log_n, uint32_t shift, const PatArgs pa) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;  // output index
+    if (i >= (1ull << (log_n + shift))) return;
+    const uint32_t j = (uint32_t)(i & ((1u << shift) - 1));
+    const uint64_t r = i >> shift;
+    fr_t s = pa.pat[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++)
+        if (j == (uint32_t)q) s = pa.pat[q];
+    store_fp(out + 2 * i, mul(load_fp<FrParams>(in + 2 * (((uint64_t)j << log_n) + r)), s));
+}
+int32_t fr_coset_interleave_scale(sb_ctx *ctx, const void *d_in, void *d_out, uint32_t log_n, uint32_t shift, const fr_t *pat, cudaStream_t st) {
+    SB_REQUIRE(shift <= 3, "coset interleave: at most 8 cosets");
+    PatArgs pa;
+    for (uint32_t i = 0; i < 8; i++) pa.pat[i] = pat[i < (1u << shift) ? i : 0];
+    pa.m = 1u << shift;
+    const uint64_t total = 1ull << (log_n + shift);
+    SB_LAUNCH(ctx, fr_coset_interleave_scale_kernel, (unsigned)((total + 255) / 256), 256, 0, st, (const uint4 *)d_in, (uint4 *)d_out, log_n, shift, pa);
+    return SB_OK;
+}
+
 int32_t fp_vec_op(sb_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n, cudaStream_t st) {
     SB_REQUIRE(op >= 0 && op <= 2, "vec op must be 0 (mul), 1 (add) or 2 (sub)");
     if (n == 0) return SB_OK;

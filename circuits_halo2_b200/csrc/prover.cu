@@ -259,12 +259,14 @@ struct sb_pk {
     void *omega_pows = nullptr;                                  // omega^i (n)
     void *div_g_pows = nullptr, *div_x = nullptr, *div_ginv_scaled = nullptr;  // SHPLONK coset division: g^i, g*omega^i, g^-i / n
     std::vector<uint8_t> fixed_comms, sigma_comms;               // affine, 64 B each
-    std::vector<void *> owned;
+    // sharded proving: zeta^(m mod 3) * ext_omega^(j m), m < n, for coset j of the extended domain (built on first use)
+    mutable std::vector<void *> coset_pows;
+    mutable std::vector<void *> owned;
 };
 
 namespace {
 
-int32_t dalloc(sb_pk *pk, size_t bytes, void **out) {
+int32_t dalloc(const sb_pk *pk, size_t bytes, void **out) {
     cudaError_t e = cudaMalloc(out, bytes ? bytes : 32);
     if (e != cudaSuccess) {
         set_last_error("pk: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -412,6 +414,8 @@ int32_t upload_frs(void *d_dst, const std::vector<Fr> &v, cudaStream_t st) {
     return SB_OK;
 }
 
+int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const void *d_bases, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st);
+
 struct Query {
     int poly_id;
     Fr point;
@@ -419,7 +423,7 @@ struct Query {
     Fr eval;
 };
 
-int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, Transcript &tr, const std::vector<Query> &queries, cudaStream_t st) {
+int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &tr, const std::vector<Query> &queries, cudaStream_t st) {
     const size_t n = pk->n;
     const Fr y = tr.squeeze();
     // construct_intermediate_sets: first-appearance order of polynomials and of rotation sets,
@@ -479,7 +483,7 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, Transcript &tr, const std::vector<
         v_pow = hfr::mul(v_pow, v);
     }
     uint8_t pt[64];
-    SB_TRY(msm_run(ctx, pk->srs->d_g, d_hx, n, pt, st));
+    SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, d_hx, n, pt, st));
     if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
     const Fr u = tr.squeeze();
     std::vector<Fr> super(super_points.begin(), super_points.end());
@@ -514,13 +518,53 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, Transcript &tr, const std::vector<
     SB_TRY(fr_sub_head(ctx, d_lx, &ct, 1, st));
     SB_TRY(poly_div_by_roots(ctx, pk, d_lx, {u}, st));
     SB_TRY(fr_scale(ctx, d_lx, n, to_dev(hfr::inv(z_diffs[0])), st));
-    SB_TRY(msm_run(ctx, pk->srs->d_g, d_lx, n, pt, st));
+    SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, d_lx, n, pt, st));
     if (!tr.write_point(pt)) { set_last_error("shplonk: opening commitment is the identity"); return SB_ERR_ARG; }
     return SB_OK;
 }
 
-int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_inst, const uint8_t *advice_host, ChaCha20Rng &rng, Transcript &tr,
-                          cudaStream_t st) {
+
+// ------------------------------------------------------------------ sharded proving
+// One process per GPU; every rank runs the whole transcript in lock step on replicated inputs and owns
+//   * a contiguous base range of every MSM (partial commitments are all-gathered as 64-byte points and added on the host),
+//   * 2^(ext_k-k) / world cosets of the extended domain: extended index i = (i >> rs_log) * 2^rs_log + j lies on the coset
+//     zeta * ext_omega^j * H, rotations move inside a coset, so coset NTTs, evaluate_h and the division by t(X) need no exchange;
+//     the quotient's coset-major values are all-gathered once (device buffer) before the extended inverse NTT.
+int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const void *d_bases, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st) {
+    if (!comm || comm->world <= 1) return msm_run(ctx, d_bases, d_scalars, n, out, st);
+    const size_t W = (size_t)comm->world, r = (size_t)comm->rank;
+    const size_t per = n / W, lo = r * per, hi = (r + 1 == W) ? n : lo + per;
+    uint8_t part[64];
+    SB_TRY(msm_run(ctx, (const uint8_t *)d_bases + lo * 64, (const uint8_t *)d_scalars + lo * 32, hi - lo, part, st));
+    std::vector<uint8_t> all(W * 64);
+    if (comm->allgather_host(comm->user, part, all.data(), 64) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+    return sb_g1_sum_affine(all.data(), W, out);
+}
+
+int32_t pk_coset_pows(sb_ctx *ctx, const sb_pk *pk, uint32_t j, void **out, cudaStream_t st) {
+    const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
+    if (pk->coset_pows.size() != n_cosets) pk->coset_pows.assign(n_cosets, nullptr);
+    if (!pk->coset_pows[j]) {
+        void *p;
+        SB_TRY(dalloc(pk, pk->n * 32, &p));
+        SB_TRY(fr_gen_powers(ctx, p, to_dev(hfr::pow_u64(to_host(pk->dom->ext_omega), j)), pk->n, st));
+        SB_TRY(fr_scale_pattern(ctx, p, pk->n, pk->dom->coset, 3, st));
+        pk->coset_pows[j] = p;
+    }
+    *out = pk->coset_pows[j];
+    return SB_OK;
+}
+
+// values of the polynomial `d_coeff` (n coefficients) on coset j: NTT_n(coeff[m] * zeta^(m mod 3) * ext_omega^(j m))
+int32_t coset_values(sb_ctx *ctx, const sb_pk *pk, const void *d_coeff, uint32_t j, void *d_out, cudaStream_t st) {
+    void *pw;
+    SB_TRY(pk_coset_pows(ctx, pk, j, &pw, st));
+    SB_TRY(fp_vec_op(ctx, 0, 0, d_coeff, pw, d_out, pk->n, st));
+    return ntt_run(ctx, d_out, (const uint8_t *)pk->dom->omega.v, pk->k, st);
+}
+
+int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_inst, const uint8_t *advice_host, ChaCha20Rng &rng,
+                          Transcript &tr, cudaStream_t st) {
     const ConstraintSystem &cs = pk->cs;
     const sb_domain *d = pk->dom;
     const size_t n = pk->n, en = pk->ext_n;
@@ -581,7 +625,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
     }
     for (int c = 0; c < A; c++) {
-        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, adv[c], n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, adv[c], n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr theta = tr.squeeze();
@@ -625,11 +669,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         SB_TRY(dom_l2c(ctx, d, L.in_poly, st));
         (void)rng.next_fr();
         uint8_t pin[64], ptab[64];
-        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, L.p_in, n, pin, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, L.p_in, n, pin, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
         (void)rng.next_fr();
-        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, L.p_tab, n, ptab, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, L.p_tab, n, ptab, st));
         if (!tr.write_point(pin) || !tr.write_point(ptab)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr beta = tr.squeeze();
@@ -680,10 +724,10 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
             SB_CUDA_TRY(cudaStreamSynchronize(st));
             last_z = lz;
             (void)rng.next_fr();
-            SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, d_z, n, pt, st));
+            SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, d_z, n, pt, st));
             SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
             SB_TRY(dom_l2c(ctx, d, S.z_poly, st));
-            SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st));
+            if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st));
             if (!tr.write_point(pt)) { set_last_error("permutation product commitment is the identity"); return SB_ERR_ARG; }
         }
     }
@@ -708,7 +752,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         for (Fr &x : blind) x = rng.next_fr();
         SB_TRY(upload_frs((uint8_t *)d_z + (n - bf) * 32, blind, st));
         (void)rng.next_fr();
-        SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, d_z, n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, d_z, n, pt, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.z_poly, st));
         if (!tr.write_point(pt)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
@@ -725,13 +769,14 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         child.seed(seed);
         SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random, n, st));  // coefficient i = keystream block i
         (void)rng.next_fr();
-        SB_TRY(msm_run(ctx, pk->srs->d_g, d_random, n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, d_random, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("random polynomial commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr yy = tr.squeeze();
     mark();  // [4] random polynomial (ChaCha20 on the device) + commitment
 
     // ---- evaluate_h: one fused program over the extended coset
+    if (!comm) {
     for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st));
     SB_TRY(dom_c2e(ctx, d, d_inst_poly, d_inst_coset, st));
     for (LookupState &L : lks) {
@@ -739,7 +784,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st));
         SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st));
     }
-    mark();  // [5] coeff_to_extended of advice / instance / lookup polynomials
+    }
+    mark();  // [5] coeff_to_extended of advice / instance / lookup polynomials (sharded: done per owned coset in stage 6)
     ColMap em;
     em.advice0 = 0; em.fixed0 = A; em.instance0 = A + F;
     const int E_SIGMA = A + F + 1, E_PZ = E_SIGMA + P, E_L0 = E_PZ + n_sets, E_LLAST = E_L0 + 1, E_LACT = E_L0 + 2, E_X = E_L0 + 3, E_LK = E_L0 + 4;
@@ -810,7 +856,43 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
         SB_CUDA_TRY(cudaEventCreate(&e0));
         SB_CUDA_TRY(cudaEventCreate(&e1));
         SB_CUDA_TRY(cudaEventRecord(e0, st));
-        SB_TRY(expr_eval(ctx, hp, ecols, pk->ext_k, rs_log, d_h, st));
+        if (!comm) {
+            SB_TRY(expr_eval(ctx, hp, ecols, pk->ext_k, rs_log, d_h, st));
+        } else {
+            // coset-sharded: this rank owns cosets [rank * per, (rank + 1) * per) of the 2^rs_log cosets
+            const uint32_t n_cosets = 1u << rs_log, W = (uint32_t)comm->world, per = n_cosets / W;
+            // per-proof polynomials whose coset values are computed here: advice, instance, permutation Z, lookup (Z, A', S')
+            std::vector<std::pair<int, const void *>> dyn;  // (ecols index, coefficient form)
+            for (int c = 0; c < A; c++) dyn.push_back({c, adv_poly[c]});
+            dyn.push_back({A + F, d_inst_poly});
+            for (int s2 = 0; s2 < n_sets; s2++) dyn.push_back({E_PZ + s2, psets[s2].z_poly});
+            for (size_t li = 0; li < lks.size(); li++) {
+                dyn.push_back({E_LK + 3 * (int)li, lks[li].z_poly});
+                dyn.push_back({E_LK + 3 * (int)li + 1, lks[li].in_poly});
+                dyn.push_back({E_LK + 3 * (int)li + 2, lks[li].tab_poly});
+            }
+            uint8_t *d_dyn, *d_hcm;
+            SB_TRY(scratch_get(ctx, "pf_coset_dyn", dyn.size() * n * 32, (void **)&d_dyn));
+            SB_TRY(scratch_get(ctx, "pf_h_cm", en * 32, (void **)&d_hcm));
+            std::vector<const void *> ccols(ecols.size(), nullptr);
+            std::vector<uint8_t> shifts(ecols.size(), (uint8_t)rs_log);
+            for (uint32_t j = comm->rank * per; j < (comm->rank + 1) * per; j++) {
+                for (size_t c = 0; c < ecols.size(); c++) ccols[c] = ecols[c] ? (const uint8_t *)ecols[c] + (size_t)j * 32 : nullptr;
+                for (size_t q = 0; q < dyn.size(); q++) {
+                    void *dst = d_dyn + q * n * 32;
+                    SB_TRY(coset_values(ctx, pk, dyn[q].second, j, dst, st));
+                    ccols[dyn[q].first] = dst;
+                    shifts[dyn[q].first] = 0;
+                }
+                SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, d_hcm + (size_t)j * n * 32, st, &shifts));
+            }
+            if (W > 1) {
+                SB_CUDA_TRY(cudaStreamSynchronize(st));
+                if (comm->allgather_dev(comm->user, d_hcm, (size_t)per * n * 32, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
+            }
+            // coset-major -> extended order, fused with the division by t(X) (constant t_inv[j] on coset j)
+            SB_TRY(fr_coset_interleave_scale(ctx, d_hcm, d_h, pk->k, rs_log, d->t_inv, st));
+        }
         SB_CUDA_TRY(cudaEventRecord(e1, st));
         SB_CUDA_TRY(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ctx->last_h_ms, e0, e1);
@@ -819,12 +901,12 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
     }
     mark();  // [6] evaluate_h (fused program)
     // ---- quotient: / t(X), back to coefficients, pieces
-    SB_TRY(dom_div_vanishing(ctx, d, d_h, st));
+    if (!comm) SB_TRY(dom_div_vanishing(ctx, d, d_h, st));
     SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
     const int n_pieces = cs.degree - 1;
     for (int i = 0; i < n_pieces; i++) (void)rng.next_fr();
     for (int i = 0; i < n_pieces; i++) {
-        SB_TRY(msm_run(ctx, pk->srs->d_g, (uint8_t *)d_h + (size_t)i * n * 32, n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, (uint8_t *)d_h + (size_t)i * n * 32, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr x = tr.squeeze();
@@ -905,7 +987,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances
     for (int j = 0; j < P; j++) q.push_back({pid(pk->sigma_polys[j]), x, pk->sigma_polys[j], ev[i_sig[j]]});
     q.push_back({pid(d_hfold), x, d_hfold, ev[i_h]});
     q.push_back({pid(d_random), x, d_random, ev[i_rand]});
-    int32_t rc_sh = shplonk(ctx, pk, tr, q, st);
+    int32_t rc_sh = shplonk(ctx, pk, comm, tr, q, st);
     mark();  // [9] SHPLONK
     return rc_sh;
 }
@@ -982,10 +1064,16 @@ int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_
     return SB_OK;
 }
 
-int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
-                        int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+static int32_t create_proof_entry(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
+                                  const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
     if (!ctx || !pk || !advice || !rng_seed || !proof_out || !proof_len || (n_instances && !instances)) return SB_ERR_ARG;
     SB_REQUIRE(transcript_kind == 0 || transcript_kind == 1, "transcript_kind must be 0 (Blake2b) or 1 (Keccak256/EVM)");
+    if (comm) {
+        const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
+        SB_REQUIRE(comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world, "sb_comm: rank / world out of range");
+        SB_REQUIRE((uint32_t)comm->world <= n_cosets && n_cosets % (uint32_t)comm->world == 0, "sb_comm: world must divide the 2^(extended_k - k) cosets of the extended domain");
+        SB_REQUIRE(comm->world == 1 || (comm->allgather_host && comm->allgather_dev), "sb_comm: callbacks missing");
+    }
     CtxGuard g(ctx);
     ChaCha20Rng rng;
     rng.seed(rng_seed);
@@ -994,7 +1082,7 @@ int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, 
     Transcript &tr = transcript_kind == 1 ? (Transcript &)kt : (Transcript &)bt;
     int32_t rc;
     try {
-        rc = create_proof_impl(ctx, pk, instances, n_instances, advice, rng, tr, ctx->stream);
+        rc = create_proof_impl(ctx, pk, comm, instances, n_instances, advice, rng, tr, ctx->stream);
     } catch (const std::exception &e) {
         set_last_error("sb_create_proof: %s", e.what());
         return SB_ERR_ARG;
@@ -1004,6 +1092,15 @@ int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, 
     SB_REQUIRE(tr.proof.size() <= proof_cap, "sb_create_proof: output buffer too small");
     memcpy(proof_out, tr.proof.data(), tr.proof.size());
     return SB_OK;
+}
+int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
+                        int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    return create_proof_entry(ctx, pk, nullptr, instances, n_instances, advice, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+}
+int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
+                                const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    if (!comm) return SB_ERR_ARG;
+    return create_proof_entry(ctx, pk, comm, instances, n_instances, advice, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
 }
 
 // ---- building blocks with host buffers (sb_batch_invert, sb_grand_product, sb_sort_fr, sb_eval_poly, sb_kate_div)

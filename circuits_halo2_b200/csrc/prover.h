@@ -46,8 +46,11 @@ struct Program {
 };
 // terms folded Horner-style: acc = acc * fold + term (fold == nullptr: a single term, no folding)
 Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold);
-// out[i] = program(columns at row i) for i < 2^log_n; rotations move by rot << rot_scale_log rows (cyclic)
-int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st);
+// out[i] = program(columns at row i) for i < 2^log_n; rotations move by rot << rot_scale_log rows (cyclic).
+// col_shift (optional): column c is read at element ((row + rot) mod 2^log_n) << col_shift[c], i.e. with a power-of-two stride
+// (one coset of an extended-domain column, the pointer already offset to the coset's first element).
+int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st,
+                  const std::vector<uint8_t> *col_shift = nullptr);
 
 inline fr_t to_dev(const hfr::Fr &x) { fr_t r; memcpy(r.v, x.v, 32); return r; }
 inline hfr::Fr to_host(const fr_t &x) { hfr::Fr r; memcpy(r.v, x.v, 32); return r; }

@@ -91,9 +91,92 @@ class ProvingKey:
             pass
 
 
-def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK) -> bytes:
+class _SbComm(ctypes.Structure):
+    _AG_HOST = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+    _AG_DEV = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("user", ctypes.c_void_p), ("allgather_host", _AG_HOST), ("allgather_dev", _AG_DEV)]
+
+
+class _DevMem:
+    """zero-copy view of library-owned device memory for torch (`__cuda_array_interface__`)"""
+
+    def __init__(self, dptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (dptr, False), "version": 2}
+
+
+def shard_range(n: int, rank: int, world: int):
+    """base range of rank `rank` in an MSM of n points split over `world` GPUs (the last rank takes the remainder)"""
+    per = n // world
+    return rank * per, n if rank + 1 == world else (rank + 1) * per
+
+
+class ShardComm:
+    """`sb_comm` over a torch.distributed process group: one process per GPU, NCCL (device all-gather of the quotient's coset
+    values over NVLink) and NCCL or gloo for the 64-byte partial commitments.  `world` must divide 2^(extended_k - k) = 8."""
+
+    def __init__(self, group=None, device: Optional[int] = None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        backend = str(dist.get_backend(group))
+        self.host_on_cpu = "gloo" in backend
+        self.device = device if device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else None)
+        self.error = None
+        self._c = _SbComm(self.rank, self.world, None, _SbComm._AG_HOST(self._allgather_host), _SbComm._AG_DEV(self._allgather_dev))
+
+    def _allgather_host(self, _user, send, recv, nbytes):
+        try:
+            torch, dist = self.torch, self.dist
+            mine = torch.frombuffer(ctypes.string_at(send, nbytes), dtype=torch.uint8).clone()
+            if self.host_on_cpu:
+                out = torch.empty(self.world * nbytes, dtype=torch.uint8)
+                dist.all_gather_into_tensor(out, mine, group=self.group)
+            else:
+                dev = torch.device("cuda", self.device)
+                out_d = torch.empty(self.world * nbytes, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(out_d, mine.to(dev), group=self.group)
+                out = out_d.cpu()
+            ctypes.memmove(recv, out.numpy().ctypes.data, self.world * nbytes)
+            return 0
+        except Exception as e:  # never unwind into C
+            self.error = e
+            return 1
+
+    def _allgather_dev(self, _user, d_buf, bytes_per_rank, stream):
+        try:
+            torch, dist = self.torch, self.dist
+            full = torch.as_tensor(_DevMem(d_buf, bytes_per_rank * self.world), device=torch.device("cuda", self.device))
+            ext = torch.cuda.ExternalStream(stream, device=torch.device("cuda", self.device)) if stream else torch.cuda.current_stream()
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(full, full[self.rank * bytes_per_rank:(self.rank + 1) * bytes_per_rank], group=self.group)
+            ext.synchronize()
+            return 0
+        except Exception as e:
+            self.error = e
+            return 1
+
+    @property
+    def struct(self):
+        return self._c
+
+
+class LocalComm:
+    """world = 1: the coset-sharded code path on a single GPU (all cosets owned, no exchange)"""
+
+    def __init__(self):
+        self.rank, self.world, self.error = 0, 1, None
+        self._c = _SbComm(0, 1, None, _SbComm._AG_HOST(0), _SbComm._AG_DEV(0))
+
+    @property
+    def struct(self):
+        return self._c
+
+
+def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, comm=None) -> bytes:
     """One circuit instance.  instances: public inputs (python ints); advice: (A, n, 4) uint64 assigned advice columns;
-    rng_seed: 32 bytes for ChaCha20Rng::from_seed.  Returns the proof bytes (transcript.finalize())."""
+    rng_seed: 32 bytes for ChaCha20Rng::from_seed.  Returns the proof bytes (transcript.finalize()).
+    comm (ShardComm): shard this proof over the ranks of a process group; every rank must call with the same arguments."""
     if len(rng_seed) != 32:
         raise AssertionError("rng_seed must be 32 bytes")
     inst = np.concatenate([fields.fr_to_mont(int(v)) for v in instances]) if len(instances) else np.zeros(0, dtype=np.uint64)
@@ -105,6 +188,13 @@ def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: byt
     out = np.zeros(cap, dtype=np.uint8)
     plen = ctypes.c_size_t()
     seed = np.frombuffer(rng_seed, dtype=np.uint8).copy()
-    _lib.check(_lib.lib().sb_create_proof(pk.ctx.handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed), ctypes.c_int32(transcript),
-                                          ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen)), "sb_create_proof")
+    if comm is None:
+        _lib.check(_lib.lib().sb_create_proof(pk.ctx.handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed), ctypes.c_int32(transcript),
+                                              ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen)), "sb_create_proof")
+    else:
+        st = _lib.lib().sb_create_proof_sharded(pk.ctx.handle, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed),
+                                                ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+        if st != 0 and comm.error is not None:
+            raise comm.error
+        _lib.check(st, "sb_create_proof_sharded")
     return out[: plen.value].tobytes()

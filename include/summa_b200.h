@@ -132,6 +132,23 @@ int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_
  * 1 = Keccak256 / EVM (gen_proof_solidity_calldata).  Writes the proof bytes and their length. */
 int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
                         int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+/* ---- one proof sharded over the GPUs of a box (BASELINE configs[3]) --------------------------------
+ * One process (or thread) per GPU, each with its own sb_ctx / sb_srs / sb_pk built from the same inputs.  Every rank calls
+ * sb_create_proof_sharded with identical arguments; the ranks run the transcript in lock step and return the same proof bytes.
+ * Sharded work: every commitment MSM by base range (64-byte partial points meet in allgather_host and are added on the host),
+ * the coset NTTs, evaluate_h and the division by t(X) by cosets of the extended domain (the quotient's values meet in
+ * allgather_dev).  `world` must divide 2^(extended_k - k).  The callbacks are the host's collective library (NCCL, MPI, gloo):
+ * both gather `bytes_per_rank` bytes from every rank in rank order and return 0 on success.  allgather_dev works in place on
+ * device memory: rank r's part already sits at d_buf + r * bytes_per_rank; it must be complete (or stream-ordered on `stream`)
+ * when it returns. */
+typedef struct sb_comm {
+    int32_t rank, world;
+    void *user;
+    int32_t (*allgather_host)(void *user, const void *send, void *recv, size_t bytes_per_rank);
+    int32_t (*allgather_dev)(void *user, void *d_buf, size_t bytes_per_rank, void *stream);
+} sb_comm;
+int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
+                                const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
 /* device time (ms) of the fused evaluate_h kernel of the last create_proof on this context and its program shape:
  * instructions, field products, additions/subtractions, live value slots */
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);

@@ -1,0 +1,78 @@
+"""GPU tests of the sharded create_proof: coset-sharded evaluate_h + base-range-sharded MSMs.
+
+world = 1 exercises the coset path on one GPU against the oracle prover; world = 2 (when the box has two GPUs) runs one
+process per GPU under torchrun and requires byte equality with the single-GPU proof."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import halo2_prover as HP
+from oracle import mst as M
+from oracle import mst_circuit as C
+from oracle.chacha import ChaCha20Rng
+from oracle.transcript import KeccakTranscript
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_coset_path_world1_is_byte_identical_to_oracle(ctx, golden_dir):
+    import circuits_halo2_b200 as sb
+    tree = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"))
+    lay = C.synthesize(11, tree.generate_proof(5), 4, 2, 8)
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    oparams = HP.Params.read(os.path.join(golden_dir, "hermez-raw-11"))
+    fixed = np.stack([HP.from_ints(c) for c in C.fixed_columns(lay)])
+    opk = HP.ProvingKey(oparams, cs, fixed, C.permutation_mapping(lay))
+    advice = np.stack([HP.from_ints(c) for c in C.advice_columns(lay)])
+    instances = [tree.nodes[0][5][0], tree.root[0]] + tree.root[1]
+    params = sb.ParamsKZG.read(os.path.join(golden_dir, "hermez-raw-11"), ctx)
+    pk = sb.ProvingKey(params, cs, fixed, opk.sigma_values, opk.transcript_repr, ctx)
+    tr = KeccakTranscript()
+    HP.create_proof(oparams, opk, instances, advice, ChaCha20Rng.seed_from_u64(11), tr)
+    got = sb.create_proof(pk, instances, advice, sb.seed_from_u64(11), sb.TRANSCRIPT_KECCAK, comm=sb.LocalComm())
+    assert got == tr.finalize()
+
+
+@pytest.mark.parametrize("k", [13, 16])
+def test_coset_path_world1_equals_plain_path(ctx, golden_dir, k):
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import fields
+    fx = np.load(os.path.join(golden_dir, "mst_inclusion_assignment.npz"))
+    cs = open(os.path.join(golden_dir, "mst_inclusion_cs.json")).read()
+    params = sb.ParamsKZG.setup(k, 0x5A110000 + k, ctx, download=False)
+    pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234, ctx)
+    advice = np.zeros((3, 1 << k, 4), dtype=np.uint64)
+    advice[fx["advice_cells"][:, 0], fx["advice_cells"][:, 1]] = fx["advice_values"]
+    instances = [fields.fr_from_mont(v) for v in fx["instances"]]
+    for tk in (sb.TRANSCRIPT_KECCAK, sb.TRANSCRIPT_BLAKE2B):
+        assert sb.create_proof(pk, instances, advice, sb.seed_from_u64(k), tk, comm=sb.LocalComm()) == sb.create_proof(pk, instances, advice, sb.seed_from_u64(k), tk)
+
+
+def test_sharded_rejects_world_that_does_not_divide_the_cosets(ctx, golden_dir):
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import fields
+    from circuits_halo2_b200._lib import SummaB200Error
+    fx = np.load(os.path.join(golden_dir, "mst_inclusion_assignment.npz"))
+    cs = open(os.path.join(golden_dir, "mst_inclusion_cs.json")).read()
+    params = sb.ParamsKZG.setup(12, 1, ctx, download=False)
+    pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 1, ctx)
+    advice = np.zeros((3, 1 << 12, 4), dtype=np.uint64)
+    bad = sb.LocalComm()
+    bad.struct.world, bad.struct.rank = 3, 0
+    with pytest.raises(SummaB200Error):
+        sb.create_proof(pk, [fields.fr_from_mont(v) for v in fx["instances"]], advice, sb.seed_from_u64(1), sb.TRANSCRIPT_KECCAK, comm=bad)
+
+
+def test_two_gpu_sharded_proof_equals_single_gpu_proof():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(ROOT, "tests", "multi", "sharded_proof_worker.py"), "14"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -134,9 +134,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=22, help="MSM size per GPU (2^log_n points)")
     ap.add_argument("--ntt-log-n", type=int, default=22, help="size of the NTT side measurement (0 = skip)")
+    ap.add_argument("--batch-k", type=int, default=13, help="k of the batched inclusion-proof side measurement (0 = skip)")
+    ap.add_argument("--batch-proofs", type=int, default=64, help="proofs per GPU in the batch")
+    ap.add_argument("--batch-workers", type=str, default="1,4,8", help="worker threads (contexts) per GPU to sweep")
+    ap.add_argument("--mst-log-n", type=int, default=20, help="users (2^x) of the Merkle-sum-tree build side measurement (0 = skip)")
     ap.add_argument("--cpu-sample-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--proof-k", type=str, default="17", help="comma-separated k values for the create_proof side measurement ('' = skip)")
+    ap.add_argument("--proof-k", type=str, default="17,20", help="comma-separated k values for the create_proof side measurement ('' = skip)")
     ap.add_argument("--dump-proof", type=str, default="", help="directory to write the last proof / vk commitments / instances to")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -334,12 +338,42 @@ def main():
                "imad_frac": 68 * nn * ln / (t_ntt * 1e-3) / 1e12 / imadw_peak}
         del a
 
+    # ---- Merkle-sum-tree build (BASELINE configs[2]'s 2^20-user snapshot): Keccak usernames + Poseidon tree on the device ----
+    mst = None
+    if rank == 0 and args.mst_log_n:
+        nm = 1 << args.mst_log_n
+        rng_m = np.random.default_rng(20)
+        bal = rng_m.integers(0, 1 << 40, size=(nm, 2), dtype=np.uint64)
+        names = [b"user_%d" % i for i in range(nm)]
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            tree = sb.MerkleSumTree.from_arrays(names, bal, ctx=ctx)
+            wall = time.perf_counter() - t0
+            best = tree.build_ms if best is None else min(best, tree.build_ms)
+            root = tree.root()
+            tree.close()
+        assert root.balances == [int(bal[:, 0].astype(object).sum()), int(bal[:, 1].astype(object).sum())], "MST root balances != column sums"
+        perms = nm * 3 + (nm - 1) * 4  # Poseidon permutations: leaf = N_CURRENCIES + 1, middle = N_CURRENCIES + 2 (N_CURRENCIES = 2)
+        mst = {"users": nm, "currencies": 2, "device_ms": best, "wall_ms_incl_host_packing": wall * 1e3, "musers_per_s": nm / (best * 1e-3) / 1e6,
+               "poseidon_permutations": perms, "G_field_mul_per_s": perms * 472 / (best * 1e-3) / 1e9, "field_mul_frac_of_peak": perms * 472 / (best * 1e-3) / 1e9 / fmul_peak}
+
     # ---- create_proof side measurement: the reference circuit MstInclusionCircuit<4,2,8> (entry_16.csv, user 0) at k = proof_k ----
+    # N = 1: one GPU.  N > 1: the SAME proof sharded over the N ranks (sb_create_proof_sharded: MSMs by base range, evaluate_h / coset
+    # NTTs by cosets of the extended domain); every rank builds the same key, the proof bytes must equal the single-GPU proof.
     proofs = []
-    if rank == 0 and args.proof_k:
-        import json as _json
+    if args.proof_k:
         fx = np.load(os.path.join(ROOT, "tests", "golden", "mst_inclusion_assignment.npz"))
         cs_text = open(os.path.join(ROOT, "tests", "golden", "mst_inclusion_cs.json")).read()
+        stage_names = ["advice_commit", "lookup_permute_commit", "permutation_product", "lookup_product", "random_poly", "coset_ntt", "evaluate_h",
+                       "quotient_commit", "evaluations", "shplonk"]
+        comm = sb.ShardComm(device=local) if world > 1 else None
+
+        def stages():
+            stg = (ctypes.c_float * 12)()
+            L.sb_last_proof_stages(ctx.handle, stg)
+            return {nm: round(float(stg[i]), 3) for i, nm in enumerate(stage_names)}
+
         for pk_k in [int(x) for x in args.proof_k.split(",") if x]:
             nrow = 1 << pk_k
             t0 = time.perf_counter()
@@ -354,38 +388,84 @@ def main():
             adv_np[cells[:, 0], cells[:, 1]] = fx["advice_values"]
             insts = [fields_mod.fr_from_mont(v) for v in fx["instances"]]
             seed = sb.seed_from_u64(42)
-            proof = b""
-            for _ in range(2):
-                proof = sb.create_proof(pkey, insts, adv_np, seed, sb.TRANSCRIPT_KECCAK)
-            torch.cuda.synchronize()
-            l0p = ctx.launch_count()
             reps = max(2, min(args.steps, 5))
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                proof2 = sb.create_proof(pkey, insts, adv_np, seed, sb.TRANSCRIPT_KECCAK)
-            torch.cuda.synchronize()
-            ms_proof = (time.perf_counter() - t0) / reps * 1e3
-            assert proof2 == proof, "create_proof is not deterministic in the seed"
+
+            def run(c):
+                for _ in range(2):
+                    pr = sb.create_proof(pkey, insts, adv_np, seed, sb.TRANSCRIPT_KECCAK, comm=c)
+                barrier()
+                l0p = ctx.launch_count()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    pr2 = sb.create_proof(pkey, insts, adv_np, seed, sb.TRANSCRIPT_KECCAK, comm=c)
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) / reps * 1e3
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                assert pr2 == pr, "create_proof is not deterministic in the seed"
+                return pr, ms, (ctx.launch_count() - l0p) // reps, stages()
+
+            proof, ms_proof, launches_p, stg_plain = run(None)
             hms = ctypes.c_float()
             hprog = (ctypes.c_uint32 * 4)()
             L.sb_last_h_profile(ctx.handle, ctypes.byref(hms), hprog)
-            stg = (ctypes.c_float * 12)()
-            L.sb_last_proof_stages(ctx.handle, stg)
-            stage_names = ["advice_commit", "lookup_permute_commit", "permutation_product", "lookup_product", "random_poly", "coset_ntt", "evaluate_h",
-                           "quotient_commit", "evaluations", "shplonk"]
             ext_pts = nrow * 8
-            proofs.append({"k": pk_k, "ms_per_proof": ms_proof, "transcript": "keccak256/evm", "proof_bytes": len(proof),
-                           "launches_per_proof": (ctx.launch_count() - l0p) // reps, "h2d_bytes_per_proof": 3 * nrow * 32,
-                           "setup_srs_s": t_srs, "keygen_pk_s": t_pk, "stages_ms": {nm: round(float(stg[i]), 3) for i, nm in enumerate(stage_names)},
-                           "evaluate_h": {"ms": hms.value, "instructions": int(hprog[0]), "field_mul": int(hprog[1]), "field_addsub": int(hprog[2]), "live_slots": int(hprog[3]),
-                                          "G_field_mul_per_s": ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9 if hms.value else None,
-                                          "field_mul_frac_of_peak": (ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9) / fmul_peak if hms.value else None}})
-            if args.dump_proof:
+            rec = {"k": pk_k, "ms_per_proof": ms_proof, "transcript": "keccak256/evm", "proof_bytes": len(proof),
+                   "launches_per_proof": launches_p, "h2d_bytes_per_proof": 3 * nrow * 32,
+                   "setup_srs_s": t_srs, "keygen_pk_s": t_pk, "stages_ms": stg_plain,
+                   "evaluate_h": {"ms": hms.value, "instructions": int(hprog[0]), "field_mul": int(hprog[1]), "field_addsub": int(hprog[2]), "live_slots": int(hprog[3]),
+                                  "G_field_mul_per_s": ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9 if hms.value else None,
+                                  "field_mul_frac_of_peak": (ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9) / fmul_peak if hms.value else None}}
+            if world > 1:
+                sproof, ms_sh, launches_s, stg_sh = run(comm)
+                assert sproof == proof, "sharded proof differs from the single-GPU proof"
+                rec["sharded"] = {"n_gpus": world, "ms_per_proof": ms_sh, "speedup_vs_1gpu": ms_proof / ms_sh, "launches_per_proof_per_rank": launches_s,
+                                  "stages_ms_rank0": stg_sh, "proof_equals_single_gpu": True,
+                                  "timing": "wall clock around the lock-step call, barrier + synchronize on both sides, max over ranks"}
+            proofs.append(rec)
+            if args.dump_proof and rank == 0:
                 os.makedirs(args.dump_proof, exist_ok=True)
                 fcom, scom = pkey.commitments()
                 np.savez(os.path.join(args.dump_proof, f"proof_k{pk_k}.npz"), proof=np.frombuffer(proof, dtype=np.uint8), fixed_comms=fcom, sigma_comms=scom,
                          instances=fx["instances"], k=np.array([pk_k]), transcript_repr=np.array([0x1234]))
             del pkey, kzg, adv_host
+
+    # ---- batched inclusion proofs (BASELINE configs[4]): many independent create_proof calls against one resident key; every rank
+    #      is a replica proving its own share ("replicas only": no collective), proofs/s is the sum over ranks ----
+    batched = None
+    if args.batch_k:
+        bk, nb_proofs = args.batch_k, args.batch_proofs
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "mst_inclusion_assignment.npz"))
+        cs_text = open(os.path.join(ROOT, "tests", "golden", "mst_inclusion_cs.json")).read()
+        kzg = sb.ParamsKZG.setup(bk, 0x5A110000 + bk, ctx, download=False)
+        pkey = sb.ProvingKey.from_sparse(kzg, cs_text, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234, ctx)
+        adv_np = torch.zeros((3, 1 << bk, 4), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+        adv_np[fx["advice_cells"][:, 0], fx["advice_cells"][:, 1]] = fx["advice_values"]
+        insts = [fields_mod.fr_from_mont(v) for v in fx["instances"]]
+        jobs = [(insts, adv_np, sb.seed_from_u64(1000 * rank + j), sb.TRANSCRIPT_KECCAK) for j in range(nb_proofs)]
+        first = sb.create_proof(pkey, *jobs[0])
+        sweep = {}
+        for workers in [int(x) for x in args.batch_workers.split(",") if x]:
+            bp = sb.BatchProver(pkey, workers)
+            bp.prove_many(jobs[: 2 * workers])  # warm-up: scratch arenas and NTT plans of every context
+            barrier()
+            t0 = time.perf_counter()
+            out = bp.prove_many(jobs)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            assert out[0] == first and len(set(out)) == len(out), "batched proofs must equal the sequential ones and differ per seed"
+            sweep[str(workers)] = world * nb_proofs / dt
+            bp.close()
+        batched = {"k": bk, "proofs_per_rank": nb_proofs, "n_gpus": world, "proofs_per_s_by_workers_per_gpu": sweep, "best_proofs_per_s": max(sweep.values()),
+                   "host_cores": os.cpu_count(), "circuit": "MstInclusionCircuit<4,2,8> witness of entry_16.csv user 0, one ChaCha20 seed per proof",
+                   "timing": "wall clock over the whole batch, barrier + synchronize on both sides, max over ranks"}
+        del pkey, kzg
 
     # ---- CPU baseline (rank 0, bounded sample of the same workload) ----
     cpu_baseline = None
@@ -422,7 +502,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "extra": {"ntt": ntt, "create_proof": proofs},
+            "extra": {"ntt": ntt, "merkle_sum_tree": mst, "create_proof": proofs, "batched_inclusion_proofs": batched},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -93,6 +93,11 @@ void ntt_plans_free(sb_ctx *ctx);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st);
 
+// window-sharded MSM (multi-GPU): window bits / count for n points, the XYZZ sums of windows [w_lo, w_hi), and the host Horner fold
+void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W);
+int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint32_t w_lo, uint32_t w_hi, uint8_t *win_out, cudaStream_t st);
+void msm_fold_windows(const uint8_t *win, uint32_t W, uint32_t c, uint8_t out_affine[64]);
+
 int32_t fr_gen_powers(sb_ctx *ctx, void *d_out, const fr_t &base, size_t count, cudaStream_t st);
 int32_t g1_fixed_base_mul(sb_ctx *ctx, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 

@@ -39,6 +39,7 @@ struct MsmShape {
     uint32_t L1;        // chunk length of level 1
     uint32_t seg_log;   // bucket-reduction segment = 2^seg_log buckets
     uint64_t n, t_max;  // points, sorted-list capacity (W * n rounded up to 4)
+    uint32_t w_lo, W_all;  // this launch set covers windows [w_lo, w_lo + W) of the W_all windows of the scalar (window-sharded MSM)
 };
 
 // ------------------------------------------------------------------ 1+2: recode, histogram, scatter
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
         }
         uint32_t carry = 0;
         const uint32_t half = 1u << (sh.c - 1);
-        for (uint32_t w = 0; w < sh.W; w++) {
+        for (uint32_t w = 0; w < sh.w_lo + sh.W; w++) {
             const uint32_t bit = w * sh.c;
             uint32_t d = (bit < 256 ? raw_window(s, bit, sh.c) : 0) + carry;
             uint32_t neg = 0;
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
             } else {
                 carry = 0;
             }
-            const uint32_t key = (live && d) ? w * sh.B + d - 1 : INVALID_KEY;
+            if (w < sh.w_lo) continue;  // warp-uniform: earlier windows only feed the carry
+            const uint32_t key = (live && d) ? (w - sh.w_lo) * sh.B + d - 1 : INVALID_KEY;
             // warp aggregation: one atomic per distinct key per warp (hot buckets stay cheap)
             const uint32_t peers = __match_any_sync(0xffffffffu, key);
             const uint32_t leader = __ffs(peers) - 1;
@@ -352,7 +354,7 @@ static uint32_t ilog2_floor(uint64_t x) {
     return r;
 }
 
-static MsmShape msm_shape(sb_ctx *ctx, uint64_t n) {
+static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1) {
     MsmShape sh;
     memset(&sh, 0, sizeof sh);
     int c = (int)ilog2_floor(n) - 3;
@@ -363,7 +365,9 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n) {
         if (v >= 2 && v <= 16) c = v;
     }
     sh.c = (uint32_t)c;
-    sh.W = (255 + sh.c - 1) / sh.c;
+    sh.W_all = (255 + sh.c - 1) / sh.c;
+    sh.w_lo = (uint32_t)w_lo;
+    sh.W = (w_hi < 0 ? sh.W_all : (uint32_t)w_hi) - sh.w_lo;
     sh.B = 1u << (sh.c - 1);
     sh.n = n;
     sh.t_max = ((uint64_t)sh.W * n + 3) & ~3ull;
@@ -383,13 +387,32 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n) {
     return sh;
 }
 
+void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W) {
+    const MsmShape sh = msm_shape(ctx, n);
+    *c = sh.c;
+    *W = sh.W_all;
+}
+
+static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out, cudaStream_t st);
+
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
+    return msm_run_impl(ctx, d_bases, d_scalars, n, 0, -1, out_affine, st);
+}
+// windows [w_lo, w_hi) only: writes (w_hi - w_lo) XYZZ window sums (128 B each) instead of the folded point
+int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint32_t w_lo, uint32_t w_hi, uint8_t *win_out, cudaStream_t st) {
+    SB_REQUIRE(w_lo < w_hi, "msm_run_windows: empty window range");
+    return msm_run_impl(ctx, d_bases, d_scalars, n, (int32_t)w_lo, (int32_t)w_hi, win_out, st);
+}
+void msm_fold_windows(const uint8_t *win, uint32_t W, uint32_t c, uint8_t out_affine[64]) { host_fold_windows(win, (int)W, (int)c, out_affine); }
+
+static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out_affine, cudaStream_t st) {
     if (n == 0) {
-        memset(out_affine, 0, 64);
+        memset(out_affine, 0, w_hi < 0 ? 64 : (size_t)(w_hi - w_lo) * 128);
         return SB_OK;
     }
     SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
-    const MsmShape sh = msm_shape(ctx, n);
+    const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi);
+    SB_REQUIRE(w_hi < 0 || (uint32_t)w_hi <= sh.W_all, "msm: window range exceeds the scalar");
     SB_REQUIRE(sh.t_max < (1ull << 32), "msm: window count * n must be < 2^32");
     const uint64_t nb = (uint64_t)sh.W * sh.B;
 
@@ -464,7 +487,8 @@ int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t 
     for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
     cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
-    host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.W, (int)sh.c, out_affine);
+    if (w_hi < 0) host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.W, (int)sh.c, out_affine);
+    else memcpy(out_affine, ctx->pinned, (size_t)sh.W * 128);
     return SB_OK;
 }
 

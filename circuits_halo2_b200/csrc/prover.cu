@@ -532,13 +532,31 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
 //     the quotient's coset-major values are all-gathered once (device buffer) before the extended inverse NTT.
 int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const void *d_bases, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st) {
     if (!comm || comm->world <= 1) return msm_run(ctx, d_bases, d_scalars, n, out, st);
-    const size_t W = (size_t)comm->world, r = (size_t)comm->rank;
-    const size_t per = n / W, lo = r * per, hi = (r + 1 == W) ? n : lo + per;
+    const uint32_t Wd = (uint32_t)comm->world, r = (uint32_t)comm->rank;
+    uint32_t c, W;
+    msm_window_shape(ctx, n, &c, &W);
+    if (W >= Wd && getenv("SB_SHARD_MSM_BY_RANGE") == nullptr) {
+        // by signed-digit window: rank r accumulates windows [r W / world, (r + 1) W / world) over ALL bases (level-1 additions, sort and bucket
+        // reduction all divide by world); the W window sums (128 B XYZZ each) meet on the host and are folded by Horner there
+        const uint32_t per = (W + Wd - 1) / Wd;  // slots per rank in the gathered buffer (ragged tails stay zero = identity)
+        const uint32_t lo = r * W / Wd, hi = (r + 1) * W / Wd;
+        std::vector<uint8_t> mine((size_t)per * 128, 0), all((size_t)Wd * per * 128), win((size_t)W * 128);
+        SB_TRY(msm_run_windows(ctx, d_bases, d_scalars, n, lo, hi, mine.data(), st));
+        if (comm->allgather_host(comm->user, mine.data(), all.data(), (size_t)per * 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+        for (uint32_t q = 0; q < Wd; q++) {
+            const uint32_t qlo = q * W / Wd, qhi = (q + 1) * W / Wd;
+            memcpy(win.data() + (size_t)qlo * 128, all.data() + (size_t)q * per * 128, (size_t)(qhi - qlo) * 128);
+        }
+        msm_fold_windows(win.data(), W, c, out);
+        return SB_OK;
+    }
+    // by base range (north_star): 64-byte partial commitments added on the host
+    const size_t per = n / Wd, lo = r * per, hi = (r + 1 == Wd) ? n : lo + per;
     uint8_t part[64];
     SB_TRY(msm_run(ctx, (const uint8_t *)d_bases + lo * 64, (const uint8_t *)d_scalars + lo * 32, hi - lo, part, st));
-    std::vector<uint8_t> all(W * 64);
+    std::vector<uint8_t> all((size_t)Wd * 64);
     if (comm->allgather_host(comm->user, part, all.data(), 64) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
-    return sb_g1_sum_affine(all.data(), W, out);
+    return sb_g1_sum_affine(all.data(), Wd, out);
 }
 
 int32_t pk_coset_pows(sb_ctx *ctx, const sb_pk *pk, uint32_t j, void **out, cudaStream_t st) {

@@ -173,10 +173,11 @@ class LocalComm:
         return self._c
 
 
-def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, comm=None) -> bytes:
+def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, comm=None, ctx: Optional[Context] = None) -> bytes:
     """One circuit instance.  instances: public inputs (python ints); advice: (A, n, 4) uint64 assigned advice columns;
     rng_seed: 32 bytes for ChaCha20Rng::from_seed.  Returns the proof bytes (transcript.finalize()).
-    comm (ShardComm): shard this proof over the ranks of a process group; every rank must call with the same arguments."""
+    comm (ShardComm): shard this proof over the ranks of a process group; every rank must call with the same arguments.
+    ctx: run on another context of the key's device (its own stream and scratch; the key is read-only) -- see BatchProver."""
     if len(rng_seed) != 32:
         raise AssertionError("rng_seed must be 32 bytes")
     inst = np.concatenate([fields.fr_to_mont(int(v)) for v in instances]) if len(instances) else np.zeros(0, dtype=np.uint64)
@@ -189,12 +190,47 @@ def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: byt
     plen = ctypes.c_size_t()
     seed = np.frombuffer(rng_seed, dtype=np.uint8).copy()
     if comm is None:
-        _lib.check(_lib.lib().sb_create_proof(pk.ctx.handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed), ctypes.c_int32(transcript),
+        _lib.check(_lib.lib().sb_create_proof((ctx or pk.ctx).handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed), ctypes.c_int32(transcript),
                                               ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen)), "sb_create_proof")
     else:
-        st = _lib.lib().sb_create_proof_sharded(pk.ctx.handle, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed),
+        st = _lib.lib().sb_create_proof_sharded((ctx or pk.ctx).handle, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed),
                                                 ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
         if st != 0 and comm.error is not None:
             raise comm.error
         _lib.check(st, "sb_create_proof_sharded")
     return out[: plen.value].tobytes()
+
+
+class BatchProver:
+    """Many independent proofs against ONE proving key (BASELINE configs[4]; the reference proves one user per
+    `create_proof` call, backend/src/apis/round.rs:153-174, so a batch is many calls with a shared key).  Each worker thread
+    owns a context (stream + scratch) on the key's GPU; the key and the SRS stay resident and are shared read-only, so the
+    small kernels of different proofs overlap on the device and the host-side transcript work runs on several cores."""
+
+    def __init__(self, pk: ProvingKey, workers: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        import queue
+        self.pk = pk
+        self.contexts = [Context(pk.ctx.device) for _ in range(workers)]
+        self._free = queue.SimpleQueue()
+        for c in self.contexts:
+            self._free.put(c)
+        self._pool = ThreadPoolExecutor(max_workers=workers)
+
+    def _one(self, job):
+        instances, advice, seed, transcript = job
+        c = self._free.get()
+        try:
+            return create_proof(self.pk, instances, advice, seed, transcript, ctx=c)
+        finally:
+            self._free.put(c)
+
+    def prove_many(self, jobs):
+        """jobs: iterable of (instances, advice, rng_seed, transcript); returns the proofs in job order."""
+        return list(self._pool.map(self._one, jobs))
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for c in self.contexts:
+            c.close()
+        self.contexts = []

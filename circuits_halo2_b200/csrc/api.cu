@@ -290,6 +290,8 @@ int32_t sb_srs_destroy(sb_srs *srs) {
         cudaFree(srs->d_g);
         cudaFree(srs->d_g_lagrange);
     }
+    for (int b = 0; b < 2; b++)
+        if (srs->tab[b].d_tables && (b == 0 || srs->tab[1].d_tables != srs->tab[0].d_tables)) cudaFree(srs->tab[b].d_tables);
     delete srs;
     return SB_OK;
 }
@@ -298,8 +300,32 @@ int32_t sb_msm_g1_srs_dev(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const v
     SB_REQUIRE(basis == SB_BASIS_MONOMIAL || basis == SB_BASIS_LAGRANGE, "basis must be 0 or 1");
     SB_REQUIRE(n <= ((size_t)1 << srs->k), "msm: more scalars than SRS bases");
     Guard g(ctx);
-    return msm_run(ctx, basis == SB_BASIS_MONOMIAL ? srs->d_g : srs->d_g_lagrange, d_scalars, n, out_affine, pick_stream(ctx, stream));
+    return srs_msm(ctx, srs, basis, d_scalars, n, out_affine, pick_stream(ctx, stream));
 }
+int32_t sb_srs_precompute(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32_t window_bits) {
+    if (!ctx || !srs) return SB_ERR_ARG;
+    Guard g(ctx);
+    return srs_precompute_impl(ctx, srs, basis_mask, window_bits);
+}
+}  // extern "C"
+namespace sb {
+int32_t srs_precompute_impl(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32_t window_bits) {
+    SB_REQUIRE(basis_mask >= 1 && basis_mask <= 3, "sb_srs_precompute: basis_mask is a bit set of (1 << SB_BASIS_*)");
+    if (srs->k < 11) return SB_OK;  // tiny SRS: plain Pippenger is launch-bound either way
+    uint32_t c = window_bits;
+    if (c == 0) {
+        c = srs->k <= 20 ? srs->k : (srs->k >= 23 ? 22 : 20);
+        if (const char *env = getenv("SB_TAB_C")) c = (uint32_t)atoi(env);
+    }
+    for (int b = 0; b < 2; b++) {
+        if (!((basis_mask >> b) & 1) || srs->tab[b].d_tables) continue;
+        if (b == 1 && srs->d_g_lagrange == srs->d_g && srs->tab[0].d_tables) { srs->tab[1] = srs->tab[0]; continue; }
+        SB_TRY(msm_tables_build(ctx, b == 0 ? srs->d_g : srs->d_g_lagrange, (size_t)1 << srs->k, c, &srs->tab[b], ctx->stream));
+    }
+    return SB_OK;
+}
+}  // namespace sb
+extern "C" {
 int32_t sb_msm_g1(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const uint8_t *scalars, size_t n, uint8_t out_affine[64]) {
     if (!ctx || !srs || !out_affine || (n && !scalars)) return SB_ERR_ARG;
     SB_REQUIRE(basis == SB_BASIS_MONOMIAL || basis == SB_BASIS_LAGRANGE, "basis must be 0 or 1");
@@ -308,7 +334,7 @@ int32_t sb_msm_g1(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const uint8_t *
     void *ds;
     SB_TRY(scratch_get(ctx, "mx_scalars", n * 32, &ds));
     SB_CUDA_TRY(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    return msm_run(ctx, basis == SB_BASIS_MONOMIAL ? srs->d_g : srs->d_g_lagrange, ds, n, out_affine, ctx->stream);
+    return srs_msm(ctx, srs, basis, ds, n, out_affine, ctx->stream);
 }
 
 // ---- NTT ------------------------------------------------------------------------------------

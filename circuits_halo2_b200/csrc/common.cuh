@@ -93,6 +93,14 @@ void ntt_plans_free(sb_ctx *ctx);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st);
 
+// fixed-base window tables of an SRS basis (msm.cu): tables[w * stride + i] = 2^(c w) * base_i, affine
+struct MsmTables {
+    void *d_tables = nullptr;
+    uint32_t c = 0, W = 0;
+    uint64_t stride = 0;
+};
+int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st);
+int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out, cudaStream_t st);
 // window-sharded MSM (multi-GPU): window bits / count for n points, the XYZZ sums of windows [w_lo, w_hi), and the host Horner fold
 void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W);
 int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint32_t w_lo, uint32_t w_hi, uint8_t *win_out, cudaStream_t st);

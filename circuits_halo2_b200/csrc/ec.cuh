@@ -11,6 +11,16 @@
 
 namespace sb {
 
+// Field products of the group law.  With SB_EC_NOINLINE_MUL the Montgomery product is ONE shared subroutine (operands and result
+// by value, i.e. in registers under the device ABI) instead of ten inlined copies per addition: the fully inlined madd body is
+// ~40 KB of SASS and ncu shows `no_instruction` (instruction-cache miss) as the top stall of the MSM accumulation kernel.
+#if defined(SB_EC_NOINLINE_MUL) && defined(__CUDA_ARCH__)
+static __device__ __noinline__ fq_t ec_mul(fq_t a, fq_t b) { return mul(a, b); }
+#else
+SB_HD fq_t ec_mul(const fq_t &a, const fq_t &b) { return mul(a, b); }
+#endif
+SB_HD fq_t ec_sqr(const fq_t &a) { return ec_mul(a, a); }
+
 struct affine_t {  // halo2curves G1Affine: 64 B, identity = (0, 0)
     fq_t x, y;
     SB_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
@@ -36,13 +46,13 @@ struct xyzz_t {  // identity: zz == 0
 SB_HD xyzz_t dbl_affine(const affine_t &p) {
     xyzz_t r;
     fq_t u = dbl(p.y);
-    fq_t v = sqr(u);
-    fq_t w = mul(u, v);
-    fq_t s = mul(p.x, v);
-    fq_t xx = sqr(p.x);
+    fq_t v = ec_sqr(u);
+    fq_t w = ec_mul(u, v);
+    fq_t s = ec_mul(p.x, v);
+    fq_t xx = ec_sqr(p.x);
     fq_t m = add(dbl(xx), xx);
-    r.x = sub(sqr(m), dbl(s));
-    r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+    r.x = sub(ec_sqr(m), dbl(s));
+    r.y = sub(ec_mul(m, sub(s, r.x)), ec_mul(w, p.y));
     r.zz = v;
     r.zzz = w;
     return r;
@@ -53,15 +63,15 @@ SB_HD xyzz_t dbl(const xyzz_t &p) {
     if (p.is_identity()) return p;
     xyzz_t r;
     fq_t u = dbl(p.y);
-    fq_t v = sqr(u);
-    fq_t w = mul(u, v);
-    fq_t s = mul(p.x, v);
-    fq_t xx = sqr(p.x);
+    fq_t v = ec_sqr(u);
+    fq_t w = ec_mul(u, v);
+    fq_t s = ec_mul(p.x, v);
+    fq_t xx = ec_sqr(p.x);
     fq_t m = add(dbl(xx), xx);
-    r.x = sub(sqr(m), dbl(s));
-    r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
-    r.zz = mul(v, p.zz);
-    r.zzz = mul(w, p.zzz);
+    r.x = sub(ec_sqr(m), dbl(s));
+    r.y = sub(ec_mul(m, sub(s, r.x)), ec_mul(w, p.y));
+    r.zz = ec_mul(v, p.zz);
+    r.zzz = ec_mul(w, p.zzz);
     return r;
 }
 
@@ -73,8 +83,8 @@ SB_HD void madd(xyzz_t &acc, const affine_t &q, bool negate) {
         acc.x = q.x; acc.y = qy; acc.zz = fq_t::one(); acc.zzz = fq_t::one();
         return;
     }
-    fq_t u2 = mul(q.x, acc.zz);
-    fq_t s2 = mul(qy, acc.zzz);
+    fq_t u2 = ec_mul(q.x, acc.zz);
+    fq_t s2 = ec_mul(qy, acc.zzz);
     fq_t p = sub(u2, acc.x);
     fq_t r = sub(s2, acc.y);
     if (p.is_zero()) {
@@ -86,25 +96,25 @@ SB_HD void madd(xyzz_t &acc, const affine_t &q, bool negate) {
         }
         return;
     }
-    fq_t pp = sqr(p);
-    fq_t ppp = mul(p, pp);
-    fq_t qq = mul(acc.x, pp);
-    fq_t x3 = sub(sub(sqr(r), ppp), dbl(qq));
-    fq_t y3 = sub(mul(r, sub(qq, x3)), mul(acc.y, ppp));
+    fq_t pp = ec_sqr(p);
+    fq_t ppp = ec_mul(p, pp);
+    fq_t qq = ec_mul(acc.x, pp);
+    fq_t x3 = sub(sub(ec_sqr(r), ppp), dbl(qq));
+    fq_t y3 = sub(ec_mul(r, sub(qq, x3)), ec_mul(acc.y, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = mul(acc.zz, pp);
-    acc.zzz = mul(acc.zzz, ppp);
+    acc.zz = ec_mul(acc.zz, pp);
+    acc.zzz = ec_mul(acc.zzz, ppp);
 }
 
 // acc += q   (add-2008-s: 12M + 2S)
 SB_HD void add(xyzz_t &acc, const xyzz_t &q) {
     if (q.is_identity()) return;
     if (acc.is_identity()) { acc = q; return; }
-    fq_t u1 = mul(acc.x, q.zz);
-    fq_t u2 = mul(q.x, acc.zz);
-    fq_t s1 = mul(acc.y, q.zzz);
-    fq_t s2 = mul(q.y, acc.zzz);
+    fq_t u1 = ec_mul(acc.x, q.zz);
+    fq_t u2 = ec_mul(q.x, acc.zz);
+    fq_t s1 = ec_mul(acc.y, q.zzz);
+    fq_t s2 = ec_mul(q.y, acc.zzz);
     fq_t p = sub(u2, u1);
     fq_t r = sub(s2, s1);
     if (p.is_zero()) {
@@ -112,15 +122,15 @@ SB_HD void add(xyzz_t &acc, const xyzz_t &q) {
         else acc = xyzz_t::identity();
         return;
     }
-    fq_t pp = sqr(p);
-    fq_t ppp = mul(p, pp);
-    fq_t qq = mul(u1, pp);
-    fq_t x3 = sub(sub(sqr(r), ppp), dbl(qq));
-    fq_t y3 = sub(mul(r, sub(qq, x3)), mul(s1, ppp));
+    fq_t pp = ec_sqr(p);
+    fq_t ppp = ec_mul(p, pp);
+    fq_t qq = ec_mul(u1, pp);
+    fq_t x3 = sub(sub(ec_sqr(r), ppp), dbl(qq));
+    fq_t y3 = sub(ec_mul(r, sub(qq, x3)), ec_mul(s1, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = mul(mul(acc.zz, q.zz), pp);
-    acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);
+    acc.zz = ec_mul(ec_mul(acc.zz, q.zz), pp);
+    acc.zzz = ec_mul(ec_mul(acc.zzz, q.zzz), ppp);
 }
 
 SB_HD xyzz_t neg(const xyzz_t &p) {
@@ -134,11 +144,11 @@ SB_HD affine_t to_affine(const xyzz_t &p) {
     affine_t r;
     if (p.is_identity()) { r.x = fq_t::zero(); r.y = fq_t::zero(); return r; }
     // 1/ZZZ; x = X * ZZZ^-2 * ZZ^2 ... use: 1/ZZ = ZZ^2 / ZZZ^2 * ... simpler: invert both via one inversion
-    fq_t zi = inv(mul(p.zz, p.zzz));      // 1 / (ZZ * ZZZ)
-    fq_t zz_inv = mul(zi, p.zzz);         // 1 / ZZ
-    fq_t zzz_inv = mul(zi, p.zz);         // 1 / ZZZ
-    r.x = mul(p.x, zz_inv);
-    r.y = mul(p.y, zzz_inv);
+    fq_t zi = inv(ec_mul(p.zz, p.zzz));      // 1 / (ZZ * ZZZ)
+    fq_t zz_inv = ec_mul(zi, p.zzz);         // 1 / ZZ
+    fq_t zzz_inv = ec_mul(zi, p.zz);         // 1 / ZZZ
+    r.x = ec_mul(p.x, zz_inv);
+    r.y = ec_mul(p.y, zzz_inv);
     return r;
 }
 

@@ -7,7 +7,18 @@ struct sb_srs {
     void *d_g = nullptr;
     void *d_g_lagrange = nullptr;
     bool borrowed = false;  // sb_srs_wrap_dev: the caller owns the device arrays
+    // fixed-base window tables per basis (sb_srs_precompute): [0] monomial, [1] Lagrange; d_tables == nullptr -> plain Pippenger
+    sb::MsmTables tab[2];
 };
+
+namespace sb {
+int32_t srs_precompute_impl(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32_t window_bits);  // no locking
+// commit through the SRS handle: the table path when the basis has been precomputed, plain Pippenger otherwise
+inline int32_t srs_msm(sb_ctx *ctx, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
+    if (srs->tab[basis].d_tables) return msm_run_tables(ctx, &srs->tab[basis], d_scalars, n, 0, -1, out_affine, st);
+    return msm_run(ctx, basis == 0 ? srs->d_g : srs->d_g_lagrange, d_scalars, n, out_affine, st);
+}
+}
 
 struct sb_domain {
     uint32_t j = 0, k = 0, ext_k = 0, quotient_degree = 0;

@@ -23,6 +23,9 @@
 // Control logic is pinned on the CPU by tests/models/msm_model.py.
 #include <stdlib.h>
 
+#ifndef SB_EC_INLINE_MUL
+#define SB_EC_NOINLINE_MUL 1
+#endif
 #include "common.cuh"
 #include "ec.cuh"
 
@@ -40,6 +43,8 @@ struct MsmShape {
     uint32_t seg_log;   // bucket-reduction segment = 2^seg_log buckets
     uint64_t n, t_max;  // points, sorted-list capacity (W * n rounded up to 4)
     uint32_t w_lo, W_all;  // this launch set covers windows [w_lo, w_lo + W) of the W_all windows of the scalar (window-sharded MSM)
+    uint32_t Wb;           // bucket sets: W, or 1 when the bases come from fixed-base window tables (all windows share one set)
+    uint32_t tab_stride;   // 0, or the table stride: the point for (window w, base i) is tables[w * tab_stride + i] = 2^(c w) * P_i
 };
 
 // ------------------------------------------------------------------ 1+2: recode, histogram, scatter
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                 carry = 0;
             }
             if (w < sh.w_lo) continue;  // warp-uniform: earlier windows only feed the carry
-            const uint32_t key = (live && d) ? (w - sh.w_lo) * sh.B + d - 1 : INVALID_KEY;
+            const uint32_t key = (live && d) ? (sh.tab_stride ? 0u : (w - sh.w_lo) * sh.B) + d - 1 : INVALID_KEY;
             // warp aggregation: one atomic per distinct key per warp (hot buckets stay cheap)
             const uint32_t peers = __match_any_sync(0xffffffffu, key);
             const uint32_t leader = __ffs(peers) - 1;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                 if (key != INVALID_KEY) {
                     pos += __popc(peers & ((1u << lane) - 1));
                     skeys[pos] = key;
-                    svals[pos] = (uint32_t)i | (neg << 31);
+                    svals[pos] = (uint32_t)(sh.tab_stride ? w * sh.tab_stride + i : i) | (neg << 31);
                 }
             }
         }
@@ -299,33 +304,83 @@ __global__ void __launch_bounds__(FINAL_MAX) msm_reduce_final_kernel(const uint3
 }
 
 // ------------------------------------------------------------------ 4: bucket reduction
-// thread = (window, segment of S = 2^seg_log buckets): seg = sum_j (s*S + j + 1) * B[s*S + j]
-__global__ void __launch_bounds__(128) msm_bucket_segment_kernel(const uint4 *buckets, MsmShape sh, uint4 *seg_sums, uint32_t nseg_per_window) {
+// Window sum R = sum_i (i + 1) * B_i over the m = 2^(c-1) buckets of a window, as a hierarchy of running sums with no scalar
+// multiplication: write R = sum_i [Q_i + lambda * i * P_i] (level 0: P = Q = B, lambda = 1).  A segment of S consecutive
+// elements, i = s S + j, contributes  sum_j Q_j + lambda * sum_j j P_j  +  (lambda S) * s * T_s  with T_s = sum_j P_j, so the
+// next level is the same problem on P'_s = T_s, Q'_s = sum_j Q_j + lambda * sum_j j P_j, lambda' = lambda S (a power of two:
+// log2(lambda) doublings).  sum_j j P_j is the classic running sum (2 additions per element).  The recursion ends at m = 1,
+// where R = Q_0.  Thread = (window, segment); level 0 does 2 general additions per bucket, every later level is 2^seg_log
+// times smaller.
+template <bool HAS_Q>
+__global__ void __launch_bounds__(128) msm_bucket_level_kernel(const uint4 *P, const uint4 *Q /* !HAS_Q: Q aliases P (level 0) */, uint32_t n_windows, uint32_t m,
+                                                               uint32_t seg_log, uint32_t lambda_log, uint4 *P_out, uint4 *Q_out) {
+    const uint32_t nseg = m >> seg_log;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= sh.W * nseg_per_window) return;
-    const uint32_t w = t / nseg_per_window, s = t % nseg_per_window;
-    const uint32_t S = 1u << sh.seg_log;
-    const uint4 *bp = buckets + 8 * ((uint64_t)w * sh.B + (uint64_t)s * S);
+    if (t >= n_windows * nseg) return;
+    const uint32_t w = t / nseg, sg = t % nseg;
+    const uint32_t S = 1u << seg_log;
+    const uint64_t base = (uint64_t)w * m + (uint64_t)sg * S;
     xyzz_t run = xyzz_t::identity(), acc = xyzz_t::identity();
-    for (int j = (int)S - 1; j >= 0; j--) {
-        xyzz_t b = load_xyzz(bp + 8 * j);
+    for (uint32_t j = S - 1; j >= 1; j--) {
+        xyzz_t b = load_xyzz(P + 8 * (base + j));
         add(run, b);
         add(acc, run);
     }
-    // + (s * S) * run, double-and-add over the bits of s, then seg_log doublings
-    if (s && !run.is_identity()) {
-        xyzz_t extra = xyzz_t::identity();
-        for (int bit = 31 - __clz(s); bit >= 0; bit--) {
-            extra = dbl(extra);
-            if ((s >> bit) & 1) add(extra, run);
-        }
-        for (uint32_t q = 0; q < sh.seg_log; q++) extra = dbl(extra);
-        add(acc, extra);
+    {
+        xyzz_t b = load_xyzz(P + 8 * base);
+        add(run, b);  // run = T_s
     }
-    store_xyzz(seg_sums + 8 * (uint64_t)t, acc);
+    store_xyzz(P_out + 8 * (uint64_t)t, run);
+    for (uint32_t q = 0; q < lambda_log; q++) acc = dbl(acc);
+    if (HAS_Q) {
+        for (uint32_t j = 0; j < S; j++) {
+            xyzz_t q = load_xyzz(Q + 8 * (base + j));
+            add(acc, q);
+        }
+    } else {
+        add(acc, run);
+    }
+    store_xyzz(Q_out + 8 * (uint64_t)t, acc);
 }
 
-// one CTA per window: sum its segment sums (strided serial part + shared-memory tree)
+// The remaining m elements of every window: V_s = Q_s + lambda * s * P_s by double-and-add over the bits of s (few elements, so the
+// scalar multiplication is cheap here), then a CTA tree; one partial per CTA.  Q == nullptr: V_s = (s + 1) * P_s.
+__global__ void __launch_bounds__(128) msm_bucket_finish_kernel(const uint4 *P, const uint4 *Q, uint32_t m, uint32_t lambda_log, uint32_t ctas_per_window, uint4 *partials) {
+    __shared__ uint4 s_pts[128 * 8];
+    const uint32_t w = blockIdx.x / ctas_per_window, cb = blockIdx.x % ctas_per_window, tid = threadIdx.x;
+    const uint32_t sidx = cb * 128 + tid;
+    xyzz_t v = xyzz_t::identity();
+    if (sidx < m) {
+        const uint64_t pos = (uint64_t)w * m + sidx;
+        xyzz_t p = load_xyzz(P + 8 * pos);
+        if (sidx && !p.is_identity()) {
+            for (int bit = 31 - __clz(sidx); bit >= 0; bit--) {
+                v = dbl(v);
+                if ((sidx >> bit) & 1) add(v, p);
+            }
+            for (uint32_t q = 0; q < lambda_log; q++) v = dbl(v);
+        }
+        if (Q) {
+            xyzz_t qv = load_xyzz(Q + 8 * pos);
+            add(v, qv);
+        } else {
+            add(v, p);
+        }
+    }
+    store_xyzz(s_pts + tid * 8, v);
+    __syncthreads();
+    for (uint32_t d = 64; d >= 1; d >>= 1) {
+        if (tid < d) {
+            xyzz_t o = load_xyzz(s_pts + (tid + d) * 8);
+            add(v, o);
+            store_xyzz(s_pts + tid * 8, v);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz(partials + 8 * (uint64_t)blockIdx.x, v);
+}
+
+// one CTA per window: sum its partials (strided serial part + shared-memory tree)
 __global__ void __launch_bounds__(128) msm_window_sum_kernel(const uint4 *seg_sums, uint32_t nseg_per_window, uint4 *win_sums) {
     __shared__ uint4 s_pts[128 * 8];
     const uint32_t w = blockIdx.x, tid = threadIdx.x;
@@ -347,6 +402,49 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const uint4 *seg_su
     if (tid == 0) store_xyzz(win_sums + 8 * (uint64_t)w, acc);
 }
 
+// ------------------------------------------------------------------ fixed-base window tables
+// tables[w * stride + i] = 2^(c w) * P_i (affine) for w < W: with them every window of the scalar addresses the SAME bucket
+// set, so the window size can grow (c = 20: 13 windows instead of 16) at no bucket-reduction cost.  One thread per base: the
+// chain of c doublings per window in XYZZ, then ONE inversion per base (Montgomery trick over its W - 1 table entries).
+static const int TAB_MAX_W = 24;
+__global__ void __launch_bounds__(128) msm_table_build_kernel(const uint4 *bases, uint64_t n, uint64_t stride, uint32_t c, uint32_t W, uint4 *tables) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= stride) return;
+    affine_t p;
+    p.x = fq_t::zero();
+    p.y = fq_t::zero();
+    if (i < n) {
+        p.x = load_fp<FqParams>(bases + 4 * i);
+        p.y = load_fp<FqParams>(bases + 4 * i + 2);
+    }
+    store_fp(tables + 4 * i, p.x);
+    store_fp(tables + 4 * i + 2, p.y);
+    xyzz_t pts[TAB_MAX_W];
+    fq_t pref[TAB_MAX_W];
+    xyzz_t cur = xyzz_t::from_affine(p);
+    fq_t prod = fq_t::one();
+    for (uint32_t w = 1; w < W; w++) {
+        for (uint32_t q = 0; q < c; q++) cur = dbl(cur);
+        pts[w] = cur;
+        pref[w] = prod;
+        if (!cur.is_identity()) prod = mul(prod, mul(cur.zz, cur.zzz));
+    }
+    fq_t inv_all = inv(prod);
+    for (uint32_t w = W - 1; w >= 1; w--) {
+        affine_t r;
+        r.x = fq_t::zero();
+        r.y = fq_t::zero();
+        if (!pts[w].is_identity()) {
+            fq_t zi = mul(inv_all, pref[w]);                    // 1 / (zz * zzz) of entry w
+            inv_all = mul(inv_all, mul(pts[w].zz, pts[w].zzz));
+            r.x = mul(pts[w].x, mul(zi, pts[w].zzz));
+            r.y = mul(pts[w].y, mul(zi, pts[w].zz));
+        }
+        store_fp(tables + 4 * ((uint64_t)w * stride + i), r.x);
+        store_fp(tables + 4 * ((uint64_t)w * stride + i) + 2, r.y);
+    }
+}
+
 // ------------------------------------------------------------------ host driver
 static uint32_t ilog2_floor(uint64_t x) {
     uint32_t r = 0;
@@ -354,7 +452,7 @@ static uint32_t ilog2_floor(uint64_t x) {
     return r;
 }
 
-static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1) {
+static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1, const MsmTables *tabs = nullptr) {
     MsmShape sh;
     memset(&sh, 0, sizeof sh);
     int c = (int)ilog2_floor(n) - 3;
@@ -364,11 +462,14 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_h
         int v = atoi(env);
         if (v >= 2 && v <= 16) c = v;
     }
+    if (tabs) c = (int)tabs->c;
     sh.c = (uint32_t)c;
     sh.W_all = (255 + sh.c - 1) / sh.c;
+    sh.tab_stride = tabs ? (uint32_t)tabs->stride : 0;
     sh.w_lo = (uint32_t)w_lo;
     sh.W = (w_hi < 0 ? sh.W_all : (uint32_t)w_hi) - sh.w_lo;
     sh.B = 1u << (sh.c - 1);
+    sh.Wb = tabs ? 1 : sh.W;
     sh.n = n;
     sh.t_max = ((uint64_t)sh.W * n + 3) & ~3ull;
     const uint64_t want = (uint64_t)ctx->sm_count * 1024;
@@ -379,7 +480,7 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_h
         if (v >= 4 && v <= 1024 && (v % 4) == 0) L1 = (uint32_t)v;
     }
     sh.L1 = L1;
-    sh.seg_log = sh.c - 1 >= 4 ? 4 : sh.c - 1;
+    sh.seg_log = sh.c - 1 >= 3 ? 3 : sh.c - 1;
     if (const char *env = getenv("SB_MSM_SEG")) {
         int v = atoi(env);
         if (v >= 0 && v <= (int)sh.c - 1) sh.seg_log = (uint32_t)v;
@@ -393,28 +494,51 @@ void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W) {
     *W = sh.W_all;
 }
 
-static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out, cudaStream_t st);
+static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out, cudaStream_t st);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
-    return msm_run_impl(ctx, d_bases, d_scalars, n, 0, -1, out_affine, st);
+    return msm_run_impl(ctx, d_bases, d_scalars, n, 0, -1, nullptr, out_affine, st);
 }
 // windows [w_lo, w_hi) only: writes (w_hi - w_lo) XYZZ window sums (128 B each) instead of the folded point
 int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint32_t w_lo, uint32_t w_hi, uint8_t *win_out, cudaStream_t st) {
     SB_REQUIRE(w_lo < w_hi, "msm_run_windows: empty window range");
-    return msm_run_impl(ctx, d_bases, d_scalars, n, (int32_t)w_lo, (int32_t)w_hi, win_out, st);
+    return msm_run_impl(ctx, d_bases, d_scalars, n, (int32_t)w_lo, (int32_t)w_hi, nullptr, win_out, st);
 }
 void msm_fold_windows(const uint8_t *win, uint32_t W, uint32_t c, uint8_t out_affine[64]) { host_fold_windows(win, (int)W, (int)c, out_affine); }
 
-static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out_affine, cudaStream_t st) {
+// fixed-base tables: the whole MSM (out: 64 B affine) or windows [w_lo, w_hi) of it (out: ONE 128 B XYZZ partial that already carries its 2^(c w) factors)
+int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out, cudaStream_t st) {
+    SB_REQUIRE(tabs && tabs->d_tables && n <= tabs->stride, "msm_run_tables: more scalars than table columns");
+    return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st);
+}
+
+int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st) {
+    SB_REQUIRE(c >= 11 && c <= 24, "msm tables: window bits must be 11..24");
+    const uint32_t W = (255 + c - 1) / c;
+    SB_REQUIRE(W <= (uint32_t)TAB_MAX_W && (uint64_t)W * n < (1ull << 31), "msm tables: too many windows / points");
+    void *d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&d_tab, (size_t)W * n * 64);
+    if (e != cudaSuccess) { set_last_error("msm tables: cudaMalloc(%zu): %s", (size_t)W * n * 64, cudaGetErrorString(e)); return SB_ERR_ALLOC; }
+    SB_LAUNCH(ctx, msm_table_build_kernel, (unsigned)((n + 127) / 128), 128, 0, st, (const uint4 *)d_bases, (uint64_t)n, (uint64_t)n, c, W, (uint4 *)d_tab);
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    out->d_tables = d_tab;
+    out->c = c;
+    out->W = W;
+    out->stride = n;
+    return SB_OK;
+}
+
+static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out_affine,
+                            cudaStream_t st) {
     if (n == 0) {
-        memset(out_affine, 0, w_hi < 0 ? 64 : (size_t)(w_hi - w_lo) * 128);
+        memset(out_affine, 0, w_hi < 0 ? 64 : (size_t)(tabs ? 1 : (w_hi - w_lo)) * 128);
         return SB_OK;
     }
     SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
-    const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi);
+    const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs);
     SB_REQUIRE(w_hi < 0 || (uint32_t)w_hi <= sh.W_all, "msm: window range exceeds the scalar");
     SB_REQUIRE(sh.t_max < (1ull << 32), "msm: window count * n must be < 2^32");
-    const uint64_t nb = (uint64_t)sh.W * sh.B;
+    const uint64_t nb = (uint64_t)sh.Wb * sh.B;
 
     // ---- scratch ----
     uint32_t *d_counts, *d_cursor, *d_tiles, *d_skeys, *d_svals;
@@ -427,8 +551,11 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     SB_TRY(scratch_get(ctx, "msm_svals", sh.t_max * 4, (void **)&d_svals));
     SB_TRY(scratch_get(ctx, "msm_buckets", nb * 128, (void **)&d_buckets));
     const uint32_t nseg = sh.B >> sh.seg_log;
-    SB_TRY(scratch_get(ctx, "msm_seg", (uint64_t)sh.W * nseg * 128, (void **)&d_seg));
-    SB_TRY(scratch_get(ctx, "msm_win", (uint64_t)sh.W * 128, (void **)&d_win));
+    {
+        const uint64_t cap = (uint64_t)sh.Wb * (sh.B >> 1) + 128;
+        SB_TRY(scratch_get(ctx, "msm_seg", (4 * cap + (uint64_t)sh.Wb * ((sh.B + 127) / 128) + 8 + sh.Wb + 8) * 128, (void **)&d_seg));  // bucket hierarchy scratch
+    }
+    (void)nseg;
     const uint64_t nchunks1 = (sh.t_max + sh.L1 - 1) / sh.L1;
     uint64_t slots_a = 2 * nchunks1;                                   // level-1 output
     uint64_t slots_b = 2 * ((slots_a + LK - 1) / LK);                  // level-2 output
@@ -476,19 +603,40 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
 
     // ---- 4: bucket reduction ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[3], st));
-    const uint32_t nthreads_seg = sh.W * nseg;
-    SB_LAUNCH(ctx, msm_bucket_segment_kernel, (nthreads_seg + 127) / 128, 128, 0, st, (const uint4 *)d_buckets, sh, d_seg, nseg);
-    SB_LAUNCH(ctx, msm_window_sum_kernel, sh.W, 128, 0, st, (const uint4 *)d_seg, nseg, d_win);
+    {
+        // scratch layout (XYZZ slots): P/Q ping-pong of the level kernels, CTA partials, window sums
+        const uint64_t cap = (uint64_t)sh.Wb * (sh.B >> 1) + 128;
+        uint4 *bufP[2] = {d_seg, d_seg + 8 * cap}, *bufQ[2] = {d_seg + 16 * cap, d_seg + 24 * cap};
+        uint4 *d_part = d_seg + 32 * cap;
+        d_win = d_part + 8 * ((uint64_t)sh.Wb * ((sh.B + 127) / 128) + 8);
+        const uint4 *bP = d_buckets, *bQ = nullptr;
+        uint32_t m = sh.B, lambda_log = 0;
+        int pp = 0;
+        for (int level = 0; level < 2 && m > 1024; level++) {
+            const uint32_t sl = level == 0 ? (sh.seg_log ? sh.seg_log : 1) : 3;
+            const uint32_t threads = sh.Wb * (m >> sl);
+            if (bQ) SB_LAUNCH(ctx, msm_bucket_level_kernel<true>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);
+            else SB_LAUNCH(ctx, msm_bucket_level_kernel<false>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);
+            bP = bufP[pp];
+            bQ = bufQ[pp];
+            pp ^= 1;
+            lambda_log += sl;
+            m >>= sl;
+        }
+        const uint32_t ctas = (m + 127) / 128;
+        SB_LAUNCH(ctx, msm_bucket_finish_kernel, sh.Wb * ctas, 128, 0, st, bP, bQ, m, lambda_log, ctas, d_part);
+        SB_LAUNCH(ctx, msm_window_sum_kernel, sh.Wb, 128, 0, st, (const uint4 *)d_part, ctas, d_win);
+    }
 
     // ---- 5: window sums -> host fold ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[4], st));
-    SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_win, (size_t)sh.W * 128, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_win, (size_t)sh.Wb * 128, cudaMemcpyDeviceToHost, st));
     SB_CUDA_TRY(cudaStreamSynchronize(st));
     for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
     cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
-    if (w_hi < 0) host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.W, (int)sh.c, out_affine);
-    else memcpy(out_affine, ctx->pinned, (size_t)sh.W * 128);
+    if (w_hi < 0) host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.Wb, (int)sh.c, out_affine);
+    else memcpy(out_affine, ctx->pinned, (size_t)sh.Wb * 128);
     return SB_OK;
 }
 

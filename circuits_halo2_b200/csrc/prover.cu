@@ -330,7 +330,7 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
             SB_CUDA_TRY(cudaMemcpyAsync(p, v, n * 32, cudaMemcpyDeviceToDevice, st));
             SB_TRY(dom_l2c(ctx, d, p, st));
             SB_TRY(dom_c2e(ctx, d, p, e, st));
-            SB_TRY(msm_run(ctx, pk->srs->d_g_lagrange, v, n, comms.data() + (size_t)c * 64, st));
+            SB_TRY(srs_msm(ctx, pk->srs, 1, v, n, comms.data() + (size_t)c * 64, st));
             vals.push_back(v); polys.push_back(p); cosets.push_back(e);
         }
         return SB_OK;
@@ -414,7 +414,7 @@ int32_t upload_frs(void *d_dst, const std::vector<Fr> &v, cudaStream_t st) {
     return SB_OK;
 }
 
-int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const void *d_bases, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st);
+int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st);
 
 struct Query {
     int poly_id;
@@ -483,7 +483,7 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         v_pow = hfr::mul(v_pow, v);
     }
     uint8_t pt[64];
-    SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, d_hx, n, pt, st));
+    SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_hx, n, pt, st));
     if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
     const Fr u = tr.squeeze();
     std::vector<Fr> super(super_points.begin(), super_points.end());
@@ -518,7 +518,7 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
     SB_TRY(fr_sub_head(ctx, d_lx, &ct, 1, st));
     SB_TRY(poly_div_by_roots(ctx, pk, d_lx, {u}, st));
     SB_TRY(fr_scale(ctx, d_lx, n, to_dev(hfr::inv(z_diffs[0])), st));
-    SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, d_lx, n, pt, st));
+    SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_lx, n, pt, st));
     if (!tr.write_point(pt)) { set_last_error("shplonk: opening commitment is the identity"); return SB_ERR_ARG; }
     return SB_OK;
 }
@@ -530,16 +530,28 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
 //   * 2^(ext_k-k) / world cosets of the extended domain: extended index i = (i >> rs_log) * 2^rs_log + j lies on the coset
 //     zeta * ext_omega^j * H, rotations move inside a coset, so coset NTTs, evaluate_h and the division by t(X) need no exchange;
 //     the quotient's coset-major values are all-gathered once (device buffer) before the extended inverse NTT.
-int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const void *d_bases, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st) {
-    if (!comm || comm->world <= 1) return msm_run(ctx, d_bases, d_scalars, n, out, st);
+int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st) {
+    if (!comm || comm->world <= 1) return srs_msm(ctx, srs, basis, d_scalars, n, out, st);
+    const void *d_bases = basis == 0 ? srs->d_g : srs->d_g_lagrange;
+    const MsmTables *tabs = srs->tab[basis].d_tables ? &srs->tab[basis] : nullptr;
     const uint32_t Wd = (uint32_t)comm->world, r = (uint32_t)comm->rank;
     uint32_t c, W;
     msm_window_shape(ctx, n, &c, &W);
+    if (tabs) { c = tabs->c; W = tabs->W; }
     if (W >= Wd && getenv("SB_SHARD_MSM_BY_RANGE") == nullptr) {
         // by signed-digit window: rank r accumulates windows [r W / world, (r + 1) W / world) over ALL bases (level-1 additions, sort and bucket
-        // reduction all divide by world); the W window sums (128 B XYZZ each) meet on the host and are folded by Horner there
-        const uint32_t per = (W + Wd - 1) / Wd;  // slots per rank in the gathered buffer (ragged tails stay zero = identity)
+        // reduction all divide by world).  Plain bases: the W window sums (128 B XYZZ each) meet on the host and are folded by Horner there.
+        // Table bases: every rank's partial already carries its 2^(c w) factors, so the host adds world points.
         const uint32_t lo = r * W / Wd, hi = (r + 1) * W / Wd;
+        if (tabs) {
+            uint8_t mine[128];
+            std::vector<uint8_t> all((size_t)Wd * 128);
+            SB_TRY(msm_run_tables(ctx, tabs, d_scalars, n, (int32_t)lo, (int32_t)hi, mine, st));
+            if (comm->allgather_host(comm->user, mine, all.data(), 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+            msm_fold_windows(all.data(), Wd, 0, out);
+            return SB_OK;
+        }
+        const uint32_t per = (W + Wd - 1) / Wd;  // slots per rank in the gathered buffer (ragged tails stay zero = identity)
         std::vector<uint8_t> mine((size_t)per * 128, 0), all((size_t)Wd * per * 128), win((size_t)W * 128);
         SB_TRY(msm_run_windows(ctx, d_bases, d_scalars, n, lo, hi, mine.data(), st));
         if (comm->allgather_host(comm->user, mine.data(), all.data(), (size_t)per * 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
@@ -643,7 +655,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
     }
     for (int c = 0; c < A; c++) {
-        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, adv[c], n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, adv[c], n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr theta = tr.squeeze();
@@ -687,11 +699,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(dom_l2c(ctx, d, L.in_poly, st));
         (void)rng.next_fr();
         uint8_t pin[64], ptab[64];
-        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, L.p_in, n, pin, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, L.p_in, n, pin, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
         (void)rng.next_fr();
-        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, L.p_tab, n, ptab, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, L.p_tab, n, ptab, st));
         if (!tr.write_point(pin) || !tr.write_point(ptab)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr beta = tr.squeeze();
@@ -742,7 +754,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             SB_CUDA_TRY(cudaStreamSynchronize(st));
             last_z = lz;
             (void)rng.next_fr();
-            SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, d_z, n, pt, st));
+            SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_z, n, pt, st));
             SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
             SB_TRY(dom_l2c(ctx, d, S.z_poly, st));
             if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st));
@@ -770,7 +782,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         for (Fr &x : blind) x = rng.next_fr();
         SB_TRY(upload_frs((uint8_t *)d_z + (n - bf) * 32, blind, st));
         (void)rng.next_fr();
-        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g_lagrange, d_z, n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_z, n, pt, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.z_poly, st));
         if (!tr.write_point(pt)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
@@ -787,7 +799,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         child.seed(seed);
         SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random, n, st));  // coefficient i = keystream block i
         (void)rng.next_fr();
-        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, d_random, n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_random, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("random polynomial commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr yy = tr.squeeze();
@@ -924,7 +936,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     const int n_pieces = cs.degree - 1;
     for (int i = 0; i < n_pieces; i++) (void)rng.next_fr();
     for (int i = 0; i < n_pieces; i++) {
-        SB_TRY(msm_commit(ctx, comm, pk->srs->d_g, (uint8_t *)d_h + (size_t)i * n * 32, n, pt, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 0, (uint8_t *)d_h + (size_t)i * n * 32, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr x = tr.squeeze();
@@ -1036,6 +1048,11 @@ static int32_t pk_create_common(sb_ctx *ctx, const sb_srs *srs, const char *cs_j
     pk->ext_k = pk->dom->ext_k;
     pk->ext_n = (size_t)1 << pk->ext_k;
     if (pk->n < 128) { set_last_error("sb_pk_create: k < 7 is not supported"); sb_domain_destroy(pk->dom); delete pk; return SB_ERR_ARG; }
+    // fixed-base window tables for both bases of this key's SRS (the handle is shared and logically const: tables change speed, not results)
+    if (!getenv("SB_NO_TABLES")) {
+        rc = srs_precompute_impl(ctx, const_cast<sb_srs *>(srs), 3, 0);
+        if (rc != SB_OK) { sb_domain_destroy(pk->dom); delete pk; return rc; }
+    }
     try {
         rc = pk_build(ctx, pk, fixed_values, sigma_values, sparse, ctx->stream);
     } catch (const std::exception &e) {

@@ -228,3 +228,48 @@ def test_best_multiexp_large_split_property(ctx, log_n, kind):
     lhs = sb.best_multiexp(ssum, bases, ctx)[:8]
     rhs = cpu.g1_add(full, sb.best_multiexp(sc2, bases, ctx)[:8])
     assert (lhs == rhs).all()
+
+
+@pytest.mark.parametrize("k,window_bits", [(11, 0), (12, 13), (14, 0), (14, 16), (16, 20)])
+def test_fixed_base_tables_give_identical_commitments(ctx, k, window_bits):
+    """sb_srs_precompute (2^(c w) * P_i tables, one shared bucket set) must not change a single bit of commit / commit_lagrange:
+    every scalar distribution, prefixes n < 2^k, identity and repeated bases in the SRS, all checked against the table-free path
+    and (k <= 14) against the oracle."""
+    import circuits_halo2_b200 as sb
+    n = 1 << k
+    g = cpu.gen_bases(n, seed=40 + k, threads=8)
+    gl = cpu.gen_bases(n, seed=90 + k, threads=8)
+    g[3] = 0
+    g[7] = g[8]
+    gl[0] = 0
+    plain = sb.ParamsKZG(k, g, gl, ctx=ctx)
+    tabbed = sb.ParamsKZG(k, g, gl, ctx=ctx).precompute(3, window_bits)
+    for kind in ["U", "Z", "C", "S", "E"]:
+        sc = scalar_distribution(kind, n, 7000 + k)
+        sc[7] = sc[8]
+        a, b = tabbed.commit(sc), plain.commit(sc)
+        assert (a == b).all(), (kind, "commit")
+        assert (tabbed.commit_lagrange(sc) == plain.commit_lagrange(sc)).all(), (kind, "commit_lagrange")
+        if k <= 14 and kind in ("U", "E"):
+            assert (a == cpu.best_multiexp(sc, g, threads=8)).all()
+    for m in (1, 5, n // 2 + 3, n - 1):
+        sc = cpu.random_fr(m, 7100 + m)
+        assert (tabbed.commit(sc) == plain.commit(sc)).all(), m
+    assert not tabbed.commit(np.zeros((n, 4), dtype=np.uint64)).any()
+
+
+def test_fixed_base_tables_large(ctx):
+    """2^20 bases, c = 20 (13 windows, 2^19 shared buckets): equal to the table-free MSM on uniform and constant-heavy scalars."""
+    import ctypes
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import _lib
+    k = 20
+    params = sb.ParamsKZG.setup(k, 0x5A110000 + k, ctx, download=False)
+    res = {}
+    for kind in ["U", "C", "Z"]:
+        sc = scalar_distribution(kind, 1 << k, 7200)
+        res[kind] = (params.commit(sc), params.commit_lagrange(sc))
+    params.precompute()
+    for kind in ["U", "C", "Z"]:
+        sc = scalar_distribution(kind, 1 << k, 7200)
+        assert (params.commit(sc) == res[kind][0]).all() and (params.commit_lagrange(sc) == res[kind][1]).all(), kind

@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--batch-proofs", type=int, default=64, help="proofs per GPU in the batch")
     ap.add_argument("--batch-workers", type=str, default="1,4,8", help="worker threads (contexts) per GPU to sweep")
     ap.add_argument("--mst-log-n", type=int, default=20, help="users (2^x) of the Merkle-sum-tree build side measurement (0 = skip)")
-    ap.add_argument("--cpu-sample-log-n", type=int, default=18, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=22, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--proof-k", type=str, default="17,20", help="comma-separated k values for the create_proof side measurement ('' = skip)")
     ap.add_argument("--dump-proof", type=str, default="", help="directory to write the last proof / vk commitments / instances to")

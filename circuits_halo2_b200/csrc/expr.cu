@@ -11,6 +11,7 @@
 // conflict-free), instructions and constants are warp-uniform loads, column reads are coalesced
 // 32-byte loads at (row + rotation) mod n.  The only code is one Montgomery product and one add/sub,
 // so the kernel body stays resident in the instruction cache.
+#include <algorithm>
 #include <array>
 #include <map>
 #include <tuple>
@@ -39,6 +40,7 @@ struct Node {
     int a, b;          // children (node ids), -1 if unused
     int uses = 0;
     int slot = -1;
+    int nmul = 0;      // products in the subtree (0: an addition chain over leaves, cheap to recompute)
 };
 
 struct Builder {
@@ -46,8 +48,9 @@ struct Builder {
     std::map<std::array<uint32_t, 8>, uint32_t> const_ids;
     std::map<std::pair<int, int>, uint32_t> input_ids;
     std::vector<Node> nodes;
-    std::map<std::tuple<int, int, int>, int> interior;  // (op, a, b) -> node id   (per term)
-    std::map<uint32_t, int> leaves;                      // leaf operand -> node id (per term)
+    std::map<std::tuple<int, int, int, int>, int> interior;  // (op, a, b, scope) -> node id; scope = -1 shared by all terms, else the term
+    std::map<uint32_t, int> leaves;                           // leaf operand -> node id
+    int cur_term = 0;
     explicit Builder(Program &prog) : p(prog) {}
 
     uint32_t const_id(const fr_t &c) {
@@ -87,10 +90,11 @@ struct Builder {
         int b = e->b ? build(e->b) : -1;
         int op = e->kind == Expr::ADD ? OP_ADD : e->kind == Expr::SUB ? OP_SUB : e->kind == Expr::MUL ? OP_MUL : OP_NEG;
         if ((op == OP_ADD || op == OP_MUL) && b < a) std::swap(a, b);  // commutative: canonical order for CSE
-        auto key = std::make_tuple(op, a, b);
+        const int nmul = (op == OP_MUL ? 1 : 0) + nodes[a].nmul + (b >= 0 ? nodes[b].nmul : 0);
+        auto key = std::make_tuple(op, a, b, -1);
         auto it = interior.find(key);
         if (it != interior.end()) return it->second;
-        Node n; n.op = op; n.leaf = 0; n.a = a; n.b = b;
+        Node n; n.op = op; n.leaf = 0; n.a = a; n.b = b; n.nmul = nmul > 1000000 ? 1000000 : nmul;
         nodes.push_back(n);
         return interior[key] = (int)nodes.size() - 1;
     }
@@ -111,54 +115,205 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
         if (op == OP_MUL) p.n_mul++;
         else if (op != OP_COPY) p.n_addsub++;
     };
-    for (size_t ti = 0; ti < terms.size(); ti++) {
-        bld.nodes.clear();
-        bld.interior.clear();
-        bld.leaves.clear();
-        const int root = bld.build(terms[ti]);
-        std::vector<Node> &nd = bld.nodes;
-        // nodes are in topological (post-) order by construction; count uses
-        for (auto &n : nd) {
-            if (n.op < 0) continue;
-            nd[n.a].uses++;
-            if (n.b >= 0) nd[n.b].uses++;
+    // ONE hash-consed DAG for all terms: a sub-expression shared by several gates (an S-box output feeding both MDS rows, the
+    // round polynomial that the two Poseidon configurations gate with different selectors) is computed once.  The fold
+    // sum_i y^(T-1-i) term_i is linear, so the terms may be ACCUMULATED IN ANY ORDER with explicit powers of y as constants
+    // (one product + one addition per term, like Horner): terms that share the most work are scheduled next to each other so
+    // shared values die quickly and the program needs few value slots (slots are shared memory: they bound occupancy).
+    const size_t T = terms.size();
+    std::vector<int> roots(T);
+    for (size_t ti = 0; ti < T; ti++) {
+        bld.cur_term = (int)ti;
+        roots[ti] = bld.build(terms[ti]);
+    }
+    std::vector<Node> &nd = bld.nodes;
+    for (auto &n : nd) {
+        if (n.op < 0) continue;
+        nd[n.a].uses++;
+        if (n.b >= 0) nd[n.b].uses++;
+    }
+    for (int r : roots) nd[r].uses++;
+    // interior nodes reachable from every root (sorted id lists) and their cost (a product ~ 8 additions)
+    std::vector<std::vector<int>> reach(T);
+    for (size_t ti = 0; ti < T; ti++) {
+        std::vector<char> seen(nd.size(), 0);
+        std::vector<int> stack{roots[ti]};
+        while (!stack.empty()) {
+            int id = stack.back();
+            stack.pop_back();
+            if (seen[id] || nd[id].op < 0) continue;
+            seen[id] = 1;
+            reach[ti].push_back(id);
+            stack.push_back(nd[id].a);
+            if (nd[id].b >= 0) stack.push_back(nd[id].b);
         }
-        auto alloc = [&]() -> uint32_t {
-            for (uint32_t s = 1; s < slot_busy.size(); s++)
-                if (!slot_busy[s]) { slot_busy[s] = true; return s; }
-            slot_busy.push_back(true);
-            return (uint32_t)slot_busy.size() - 1;
-        };
-        auto opnd = [&](int id) -> uint32_t { return nd[id].op < 0 ? nd[id].leaf : operand(K_REG, (uint32_t)nd[id].slot); };
-        auto release = [&](int id) {
+        std::sort(reach[ti].begin(), reach[ti].end());
+    }
+    std::vector<char> emitted(nd.size(), 0), used(T, 0);
+    // next term: the one that consumes the most value already sitting in slots (a product ~ 8 additions), i.e. lets shared values
+    // die soonest; nothing live to consume -> the first unscheduled term in source order.  Plain sums keep source order.
+    auto pick_next = [&]() -> size_t {
+        size_t best = T;
+        int best_w = 0;
+        for (size_t c = 0; c < T; c++) {
+            if (used[c]) continue;
+            if (!fold) return c;
+            int w = 0;
+            for (int id : reach[c])
+                if (emitted[id] && nd[id].uses > 0) w += nd[id].op == OP_MUL ? 8 : 1;
+            if (w > best_w) { best_w = w; best = c; }
+        }
+        if (best == T)
+            for (size_t c = 0; c < T && best == T; c++)
+                if (!used[c]) best = c;
+        return best;
+    };
+    auto alloc = [&]() -> uint32_t {
+        for (uint32_t s = 1; s < slot_busy.size(); s++)
+            if (!slot_busy[s]) { slot_busy[s] = true; return s; }
+        slot_busy.push_back(true);
+        return (uint32_t)slot_busy.size() - 1;
+    };
+    auto opnd = [&](int id) -> uint32_t { return nd[id].op < 0 ? nd[id].leaf : operand(K_REG, (uint32_t)nd[id].slot); };
+    auto release = [&](int id) {
+        if (nd[id].op < 0) return;
+        if (--nd[id].uses == 0) slot_busy[nd[id].slot] = false;
+    };
+    // powers of the fold challenge: term i carries y^(T-1-i)
+    std::vector<uint32_t> pow_const(T, 0);
+    if (fold) {
+        hfr::Fr yp = hfr::ONE;
+        const hfr::Fr y = to_host(*fold);
+        for (size_t k = 0; k < T; k++) {
+            pow_const[T - 1 - k] = bld.const_id(to_dev(yp));
+            yp = hfr::mul(yp, y);
+        }
+    }
+    (void)fold_const;
+    // Product-free sub-expressions (negated cells, selector complements, sums of cells) are identified globally like everything
+    // else, but their VALUES are not kept across terms: a term that needs one recomputes it (one addition is cheaper than a value
+    // slot held for a long time; slots are shared memory and bound occupancy).  term_uses counts, per term, the edges from the
+    // nodes emitted in that term into each cheap node.
+    std::vector<int> cheap_stamp(nd.size(), -1), touch_stamp(nd.size(), -1), term_uses(nd.size(), 0);
+    bool acc_live = false;
+    for (size_t oi = 0; oi < T; oi++) {
+        const size_t ti = pick_next();
+        used[ti] = 1;
+        const int stamp = (int)oi;
+        auto is_cheap = [&](int id) { return nd[id].op >= 0 && nd[id].nmul == 0; };
+        {   // dry walk: uses of cheap nodes inside this term
+            std::vector<int> stack{roots[ti]};
+            std::vector<char> seen_exp;
+            auto touch = [&](int id) {
+                if (touch_stamp[id] != stamp) { touch_stamp[id] = stamp; term_uses[id] = 0; }
+                term_uses[id]++;
+            };
+            if (is_cheap(roots[ti])) touch(roots[ti]);  // the fold
+            std::vector<int> visited_exp;
+            while (!stack.empty()) {
+                const int id = stack.back();
+                stack.pop_back();
+                Node &n = nd[id];
+                if (n.op < 0) continue;
+                if (is_cheap(id)) {
+                    if (cheap_stamp[id] == stamp) continue;  // already expanded in this term
+                    cheap_stamp[id] = stamp;
+                } else {
+                    if (emitted[id]) continue;
+                    if (n.slot == -2) continue;  // already expanded in this dry walk
+                    n.slot = -2;
+                    visited_exp.push_back(id);
+                }
+                for (int ch : {n.a, n.b}) {
+                    if (ch < 0) continue;
+                    if (is_cheap(ch)) touch(ch);
+                    stack.push_back(ch);
+                }
+            }
+            for (int id : visited_exp) nd[id].slot = -1;
+            for (size_t q = 0; q < nd.size(); q++)
+                if (cheap_stamp[q] == stamp) cheap_stamp[q] = -1 - stamp;  // mark "to be emitted in this term", not yet emitted
+        }
+        auto cheap_ready = [&](int id) { return cheap_stamp[id] == stamp; };
+        auto release2 = [&](int id) {
             if (nd[id].op < 0) return;
-            if (--nd[id].uses == 0) slot_busy[nd[id].slot] = false;
+            if (is_cheap(id)) {
+                if (--term_uses[id] == 0) slot_busy[nd[id].slot] = false;
+            } else {
+                release(id);
+            }
         };
-        for (size_t i = 0; i < nd.size(); i++) {
-            Node &n = nd[i];
-            if (n.op < 0) continue;
+        // post-order walk from the root, skipping what is already available
+        std::vector<std::pair<int, int>> stack{{roots[ti], 0}};
+        while (!stack.empty()) {
+            auto &top = stack.back();
+            const int id = top.first;
+            Node &n = nd[id];
+            if (n.op < 0 || (is_cheap(id) ? cheap_ready(id) : (bool)emitted[id])) { stack.pop_back(); continue; }
+            if (top.second == 0) { top.second = 1; stack.push_back({n.a, 0}); continue; }
+            if (top.second == 1) { top.second = 2; if (n.b >= 0) { stack.push_back({n.b, 0}); continue; } }
             const uint32_t a = opnd(n.a), b = n.b >= 0 ? opnd(n.b) : 0;
             // operands may be released before the destination is chosen: dst may alias a dying source
-            release(n.a);
-            if (n.b >= 0) release(n.b);
+            release2(n.a);
+            if (n.b >= 0) release2(n.b);
             n.slot = (int)alloc();
             emit(n.op, (uint32_t)n.slot, a, b);
+            if (is_cheap(id)) cheap_stamp[id] = stamp;
+            else emitted[id] = 1;
+            stack.pop_back();
         }
-        // fold into the accumulator
+        const int root = roots[ti];
         const uint32_t t_op = opnd(root);
-        if (ti == 0) {
-            emit(OP_COPY, ACC, t_op, 0);
-        } else if (fold) {
-            emit(OP_MUL, ACC, operand(K_REG, ACC), operand(K_CONST, fold_const));
-            emit(OP_ADD, ACC, operand(K_REG, ACC), t_op);
+        if (getenv("SB_EXPR_DEBUG")) {
+            int busy = 0;
+            for (bool bsy : slot_busy) busy += bsy;
+            fprintf(stderr, "[expr] term %zu scheduled at %zu: %zu instr so far, %d busy slots, %zu slots allocated\n", ti, oi, p.code.size() / 3, busy, slot_busy.size());
+        }
+        const bool scaled = fold && ti != T - 1;  // the last term carries y^0
+        if (!acc_live) {
+            if (scaled) emit(OP_MUL, ACC, t_op, operand(K_CONST, pow_const[ti]));
+            else emit(OP_COPY, ACC, t_op, 0);
+            release2(root);
+            acc_live = true;
+        } else if (scaled) {
+            release2(root);
+            const uint32_t tmp = alloc();
+            emit(OP_MUL, tmp, t_op, operand(K_CONST, pow_const[ti]));
+            emit(OP_ADD, ACC, operand(K_REG, ACC), operand(K_REG, tmp));
+            slot_busy[tmp] = false;
         } else {
             emit(OP_ADD, ACC, operand(K_REG, ACC), t_op);
+            release2(root);
         }
-        if (nd[root].op >= 0) slot_busy[nd[root].slot] = false;
     }
     p.n_slots = (uint32_t)slot_busy.size();
     p.out_slot = ACC;
     return p;
+}
+
+// Host interpreter of a compiled program for ONE row (CPU tests of the compiler; the device kernel below runs the same code).
+// inputs[i] is the value of p.inputs pair i (column, rotation) at that row.
+fr_t program_eval_host(const Program &p, const std::vector<fr_t> &inputs) {
+    std::vector<hfr::Fr> slot(p.n_slots, hfr::ZERO);
+    auto fetch = [&](uint32_t o) -> hfr::Fr {
+        const uint32_t kind = o >> 30, idx = o & 0x3fffffffu;
+        if (kind == K_REG) return slot[idx];
+        if (kind == K_CONST) return to_host(p.consts[idx]);
+        return to_host(inputs[idx]);
+    };
+    for (size_t pc = 0; pc < p.code.size() / 3; pc++) {
+        const uint32_t w0 = p.code[3 * pc], wa = p.code[3 * pc + 1], wb = p.code[3 * pc + 2];
+        const uint32_t op = w0 >> 16, dst = w0 & 0xffffu;
+        const hfr::Fr a = fetch(wa);
+        hfr::Fr r;
+        if (op == OP_MUL) r = hfr::mul(a, fetch(wb));
+        else if (op == OP_ADD) r = hfr::add(a, fetch(wb));
+        else if (op == OP_SUB) r = hfr::sub(a, fetch(wb));
+        else if (op == OP_NEG) r = hfr::neg(a);
+        else r = a;
+        slot[dst] = r;
+    }
+    return to_dev(slot[p.out_slot]);
 }
 
 // ------------------------------------------------------------------ device interpreter

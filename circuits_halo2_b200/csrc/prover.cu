@@ -524,6 +524,75 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
 }
 
 
+// ------------------------------------------------------------------ quotient numerator terms
+// Column-table layout of evaluate_h (both the full extended domain and one coset of it):
+//   advice | fixed | instance | sigma (P) | permutation Z (n_sets) | l_0, l_last, l_active, X | per lookup: Z, A', S'
+struct HLayout {
+    int A, F, E_SIGMA, E_PZ, E_L0, E_LLAST, E_LACT, E_X, E_LK, n_cols;
+    HLayout(const ConstraintSystem &cs, int P, int n_sets, size_t n_lookups) {
+        A = cs.A; F = cs.F;
+        E_SIGMA = A + F + 1; E_PZ = E_SIGMA + P; E_L0 = E_PZ + n_sets; E_LLAST = E_L0 + 1; E_LACT = E_L0 + 2; E_X = E_L0 + 3; E_LK = E_L0 + 4;
+        n_cols = E_LK + 3 * (int)n_lookups;
+    }
+};
+
+// gate polynomials, then the permutation argument's terms, then every lookup's terms, in halo2's fold order
+std::vector<ExprP> h_terms(const ConstraintSystem &cs, int P, const std::vector<std::pair<int, int>> &sets /* (first column, count) */, size_t n_lookups,
+                           const Fr &theta, const Fr &beta, const Fr &gamma) {
+    const int n_sets = (int)sets.size(), bf = cs.blinding;
+    const HLayout lay(cs, P, n_sets, n_lookups);
+    const int E_SIGMA = lay.E_SIGMA, E_PZ = lay.E_PZ, E_L0 = lay.E_L0, E_LLAST = lay.E_LLAST, E_LACT = lay.E_LACT, E_X = lay.E_X, E_LK = lay.E_LK;
+    ColMap em;
+    em.advice0 = 0; em.fixed0 = cs.A; em.instance0 = cs.A + cs.F;
+    struct { int first, count; } psets_[64];
+    for (int i = 0; i < n_sets && i < 64; i++) { psets_[i].first = sets[i].first; psets_[i].count = sets[i].second; }
+    auto &psets = psets_;
+    struct { size_t n; size_t size() const { return n; } } lks{n_lookups};
+    std::vector<ExprP> terms;
+    for (auto &g : cs.gates) terms.push_back(bind_expr(*g, em));
+    const ExprP one = e_const(fr_t::one());
+    const ExprP l0 = e_col(E_L0, 0), llast = e_col(E_LLAST, 0), lact = e_col(E_LACT, 0);
+    if (n_sets > 0) {
+        auto Z = [&](int s, int r) { return e_col(E_PZ + s, r); };
+        terms.push_back(e_mul(e_sub(one, Z(0, 0)), l0));
+        terms.push_back(e_mul(e_sub(e_mul(Z(n_sets - 1, 0), Z(n_sets - 1, 0)), Z(n_sets - 1, 0)), llast));
+        for (int s = 1; s < n_sets; s++) terms.push_back(e_mul(e_sub(Z(s, 0), Z(s - 1, -(bf + 1))), l0));
+        Fr cur_delta = hfr::ONE;
+        const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+        for (int s = 0; s < n_sets; s++) {
+            ExprP left = Z(s, 1), right = Z(s, 0);
+            for (int j = 0; j < psets[s].count; j++) {
+                const auto &pc = cs.perm_cols[psets[s].first + j];
+                ExprP val = e_col(em.col(pc.first, pc.second), 0);
+                left = e_mul(left, e_add(e_add(val, e_mul(ec(beta), e_col(E_SIGMA + psets[s].first + j, 0))), ec(gamma)));
+                right = e_mul(right, e_add(e_add(val, e_mul(ec(hfr::mul(cur_delta, beta)), e_col(E_X, 0))), ec(gamma)));
+                cur_delta = hfr::mul(cur_delta, DELTA);
+            }
+            terms.push_back(e_mul(e_sub(left, right), lact));
+        }
+    }
+    for (size_t li = 0; li < lks.size(); li++) {
+        ExprP z0 = e_col(E_LK + 3 * li, 0), z1 = e_col(E_LK + 3 * li, 1);
+        ExprP a0 = e_col(E_LK + 3 * li + 1, 0), am1 = e_col(E_LK + 3 * li + 1, -1), s0 = e_col(E_LK + 3 * li + 2, 0);
+        auto compress = [&](const std::vector<json::ValueP> &exprs) {
+            ExprP acc = nullptr;
+            for (auto &e : exprs) {
+                ExprP b = bind_expr(*e, em);
+                acc = acc ? e_add(e_mul(acc, ec(theta)), b) : b;
+            }
+            return acc;
+        };
+        ExprP cin = compress(cs.lookups[li].input), ctab = compress(cs.lookups[li].table);
+        ExprP a_minus_s = e_sub(a0, s0);
+        terms.push_back(e_mul(e_sub(one, z0), l0));
+        terms.push_back(e_mul(e_sub(e_mul(z0, z0), z0), llast));
+        terms.push_back(e_mul(e_sub(e_mul(z1, e_mul(e_add(a0, ec(beta)), e_add(s0, ec(gamma)))), e_mul(z0, e_mul(e_add(cin, ec(beta)), e_add(ctab, ec(gamma))))), lact));
+        terms.push_back(e_mul(a_minus_s, l0));
+        terms.push_back(e_mul(e_mul(a_minus_s, e_sub(a0, am1)), lact));
+    }
+    return terms;
+}
+
 // ------------------------------------------------------------------ sharded proving
 // One process per GPU; every rank runs the whole transcript in lock step on replicated inputs and owns
 //   * a contiguous base range of every MSM (partial commitments are all-gathered as 64-byte points and added on the host),
@@ -831,48 +900,9 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         ecols[E_LK + 3 * li + 1] = lks[li].in_coset;
         ecols[E_LK + 3 * li + 2] = lks[li].tab_coset;
     }
-    std::vector<ExprP> terms;
-    for (auto &g : cs.gates) terms.push_back(bind_expr(*g, em));
-    const ExprP one = e_const(fr_t::one());
-    const ExprP l0 = e_col(E_L0, 0), llast = e_col(E_LLAST, 0), lact = e_col(E_LACT, 0);
-    if (n_sets > 0) {
-        auto Z = [&](int s, int r) { return e_col(E_PZ + s, r); };
-        terms.push_back(e_mul(e_sub(one, Z(0, 0)), l0));
-        terms.push_back(e_mul(e_sub(e_mul(Z(n_sets - 1, 0), Z(n_sets - 1, 0)), Z(n_sets - 1, 0)), llast));
-        for (int s = 1; s < n_sets; s++) terms.push_back(e_mul(e_sub(Z(s, 0), Z(s - 1, -(bf + 1))), l0));
-        Fr cur_delta = hfr::ONE;
-        const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
-        for (int s = 0; s < n_sets; s++) {
-            ExprP left = Z(s, 1), right = Z(s, 0);
-            for (int j = 0; j < psets[s].count; j++) {
-                const auto &pc = cs.perm_cols[psets[s].first + j];
-                ExprP val = e_col(em.col(pc.first, pc.second), 0);
-                left = e_mul(left, e_add(e_add(val, e_mul(ec(beta), e_col(E_SIGMA + psets[s].first + j, 0))), ec(gamma)));
-                right = e_mul(right, e_add(e_add(val, e_mul(ec(hfr::mul(cur_delta, beta)), e_col(E_X, 0))), ec(gamma)));
-                cur_delta = hfr::mul(cur_delta, DELTA);
-            }
-            terms.push_back(e_mul(e_sub(left, right), lact));
-        }
-    }
-    for (size_t li = 0; li < lks.size(); li++) {
-        ExprP z0 = e_col(E_LK + 3 * li, 0), z1 = e_col(E_LK + 3 * li, 1);
-        ExprP a0 = e_col(E_LK + 3 * li + 1, 0), am1 = e_col(E_LK + 3 * li + 1, -1), s0 = e_col(E_LK + 3 * li + 2, 0);
-        auto compress = [&](const std::vector<json::ValueP> &exprs) {
-            ExprP acc = nullptr;
-            for (auto &e : exprs) {
-                ExprP b = bind_expr(*e, em);
-                acc = acc ? e_add(e_mul(acc, ec(theta)), b) : b;
-            }
-            return acc;
-        };
-        ExprP cin = compress(cs.lookups[li].input), ctab = compress(cs.lookups[li].table);
-        ExprP a_minus_s = e_sub(a0, s0);
-        terms.push_back(e_mul(e_sub(one, z0), l0));
-        terms.push_back(e_mul(e_sub(e_mul(z0, z0), z0), llast));
-        terms.push_back(e_mul(e_sub(e_mul(z1, e_mul(e_add(a0, ec(beta)), e_add(s0, ec(gamma)))), e_mul(z0, e_mul(e_add(cin, ec(beta)), e_add(ctab, ec(gamma))))), lact));
-        terms.push_back(e_mul(a_minus_s, l0));
-        terms.push_back(e_mul(e_mul(a_minus_s, e_sub(a0, am1)), lact));
-    }
+    std::vector<std::pair<int, int>> set_ranges;
+    for (int s2 = 0; s2 < n_sets; s2++) set_ranges.push_back({psets[s2].first, psets[s2].count});
+    const std::vector<ExprP> terms = h_terms(cs, P, set_ranges, lks.size(), theta, beta, gamma);
     void *d_h;
     SB_TRY(scratch_get(ctx, "pf_h", en * 32, &d_h));
     {
@@ -1300,6 +1330,61 @@ int32_t sb_srs_download(sb_ctx *ctx, const sb_srs *srs, uint8_t *g_out, uint8_t 
     SB_CUDA_TRY(cudaMemcpyAsync(g_out, srs->d_g, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA_TRY(cudaMemcpyAsync(g_lagrange_out, srs->d_g_lagrange, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// CPU-only check of the evaluate_h compiler: builds the quotient-numerator program of a constraint system (challenges theta, beta,
+// gamma, y derived from `seed`), evaluates it for one row of pseudo-random column values with the host interpreter AND by walking
+// the expression trees directly (no CSE, no slots), and returns both values plus the program shape.
+static hfr::Fr direct_eval(const ExprP &e, const std::map<std::pair<int, int>, hfr::Fr> &vals) {
+    switch (e->kind) {
+        case Expr::CONST: return to_host(e->c);
+        case Expr::COL: return vals.at({e->col, e->rot});
+        case Expr::NEG: return hfr::neg(direct_eval(e->a, vals));
+        case Expr::ADD: return hfr::add(direct_eval(e->a, vals), direct_eval(e->b, vals));
+        case Expr::SUB: return hfr::sub(direct_eval(e->a, vals), direct_eval(e->b, vals));
+        default: return hfr::mul(direct_eval(e->a, vals), direct_eval(e->b, vals));
+    }
+}
+static void collect_inputs(const ExprP &e, std::map<std::pair<int, int>, hfr::Fr> &vals, ChaCha20Rng &rng) {
+    if (!e) return;
+    if (e->kind == Expr::COL) {
+        if (!vals.count({e->col, e->rot})) vals[{e->col, e->rot}] = rng.next_fr();
+        return;
+    }
+    collect_inputs(e->a, vals, rng);
+    collect_inputs(e->b, vals, rng);
+}
+int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_program_value[32], uint8_t out_direct_value[32], uint32_t out_shape[4]) {
+    if (!cs_json || !out_program_value || !out_direct_value || !out_shape) return SB_ERR_ARG;
+    try {
+        ConstraintSystem cs = parse_cs(cs_json);
+        ChaCha20Rng rng;
+        rng.seed_from_u64(seed);
+        const Fr theta = rng.next_fr(), beta = rng.next_fr(), gamma = rng.next_fr(), y = rng.next_fr();
+        const int P = (int)cs.perm_cols.size(), chunk = cs.degree - 2;
+        std::vector<std::pair<int, int>> sets;
+        for (int f = 0; f < P; f += chunk) sets.push_back({f, std::min(chunk, P - f)});
+        const std::vector<ExprP> terms = h_terms(cs, P, sets, cs.lookups.size(), theta, beta, gamma);
+        fr_t yd = to_dev(y);
+        Program prog = compile_terms(terms, &yd);
+        std::map<std::pair<int, int>, hfr::Fr> vals;
+        for (auto &t : terms) collect_inputs(t, vals, rng);
+        std::vector<fr_t> inputs(prog.inputs.size() / 2);
+        for (size_t i = 0; i < inputs.size(); i++) inputs[i] = to_dev(vals.at({prog.inputs[2 * i], prog.inputs[2 * i + 1]}));
+        fr_t got = program_eval_host(prog, inputs);
+        hfr::Fr acc = hfr::ZERO;
+        for (size_t i = 0; i < terms.size(); i++) acc = hfr::add(hfr::mul(acc, y), direct_eval(terms[i], vals));
+        memcpy(out_program_value, got.v, 32);
+        memcpy(out_direct_value, acc.v, 32);
+        out_shape[0] = (uint32_t)(prog.code.size() / 3);
+        out_shape[1] = prog.n_mul;
+        out_shape[2] = prog.n_addsub;
+        out_shape[3] = prog.n_slots;
+    } catch (const std::exception &e) {
+        set_last_error("sb_test_h_program: %s", e.what());
+        return SB_ERR_ARG;
+    }
     return SB_OK;
 }
 

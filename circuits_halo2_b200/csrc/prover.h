@@ -46,6 +46,8 @@ struct Program {
 };
 // terms folded Horner-style: acc = acc * fold + term (fold == nullptr: a single term, no folding)
 Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold);
+// the same program on the host for one row: inputs[i] = value of the (column, rotation) pair i of prog.inputs
+fr_t program_eval_host(const Program &prog, const std::vector<fr_t> &inputs);
 // out[i] = program(columns at row i) for i < 2^log_n; rotations move by rot << rot_scale_log rows (cyclic).
 // col_shift (optional): column c is read at element ((row + rot) mod 2^log_n) << col_shift[c], i.e. with a power-of-two stride
 // (one coset of an extended-domain column, the pointer already offset to the coset's first element).

@@ -174,6 +174,9 @@ int32_t sb_kate_division(sb_ctx *ctx, const uint8_t *a, uint32_t log_n, const ui
 int32_t sb_test_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
 int32_t sb_test_blake2b512(const uint8_t *data, size_t len, const uint8_t personal[16], uint8_t out[64]);
 int32_t sb_test_chacha_fr(uint64_t seed_u64, uint32_t skip_bytes, uint32_t count, uint8_t *out);
+/* evaluate_h compiler on the CPU: quotient-numerator program of `cs_json` (challenges from `seed`) run by the host interpreter on one
+ * pseudo-random row vs a direct walk of the expression trees; out_shape = instructions, field products, add/sub, live value slots */
+int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_program_value[32], uint8_t out_direct_value[32], uint32_t out_shape[4]);
 int32_t sb_test_host_fr(int32_t op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 
 /* ---- zk_prover::merkle_sum_tree: MerkleSumTree::from_entries / Tree::generate_proof ------------------

@@ -18,6 +18,15 @@ inline int32_t srs_msm(sb_ctx *ctx, const sb_srs *srs, int basis, const void *d_
     if (srs->tab[basis].d_tables) return msm_run_tables(ctx, &srs->tab[basis], d_scalars, n, 0, -1, out_affine, st);
     return msm_run(ctx, basis == 0 ? srs->d_g : srs->d_g_lagrange, d_scalars, n, out_affine, st);
 }
+// m scalar vectors (contiguous, n each) against one basis: one launch set with tables, a loop otherwise; out = m x 64 B
+inline int32_t srs_msm_batch(sb_ctx *ctx, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint32_t m, uint8_t *out_affine, cudaStream_t st) {
+    if (srs->tab[basis].d_tables) return msm_run_tables_batch(ctx, &srs->tab[basis], d_scalars, n, m, out_affine, st);
+    for (uint32_t j = 0; j < m; j++) {
+        int32_t rc = msm_run(ctx, basis == 0 ? srs->d_g : srs->d_g_lagrange, (const uint8_t *)d_scalars + (size_t)j * n * 32, n, out_affine + (size_t)j * 64, st);
+        if (rc != SB_OK) return rc;
+    }
+    return SB_OK;
+}
 }
 
 struct sb_domain {

@@ -44,6 +44,7 @@ struct MsmShape {
     uint64_t n, t_max;  // points, sorted-list capacity (W * n rounded up to 4)
     uint32_t w_lo, W_all;  // this launch set covers windows [w_lo, w_lo + W) of the W_all windows of the scalar (window-sharded MSM)
     uint32_t Wb;           // bucket sets: W, or 1 when the bases come from fixed-base window tables (all windows share one set)
+    uint32_t batch;        // scalar vectors sharing the bases (tables only): vector j = scalars[j n .. (j+1) n), bucket set j
     uint32_t tab_stride;   // 0, or the table stride: the point for (window w, base i) is tables[w * tab_stride + i] = 2^(c w) * P_i
 };
 
@@ -62,12 +63,15 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     // warp-uniform trip count so that every lane reaches the match_any below
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint64_t i = base + lane;
-        const bool live = i < n;
+    const uint64_t n_all = n * sh.batch;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_all; base += stride) {
+        const uint64_t gi = base + lane;
+        const bool live = gi < n_all;
+        const uint32_t piece = (uint32_t)(gi / n);
+        const uint64_t i = gi - (uint64_t)piece * n;
         uint32_t s[8];
         if (live) {
-            fr_t x = from_mont(load_fp<FrParams>(scalars + 2 * i));
+            fr_t x = from_mont(load_fp<FrParams>(scalars + 2 * gi));
 #pragma unroll
             for (int q = 0; q < 8; q++) s[q] = x.v[q];
         } else {
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                 carry = 0;
             }
             if (w < sh.w_lo) continue;  // warp-uniform: earlier windows only feed the carry
-            const uint32_t key = (live && d) ? (sh.tab_stride ? 0u : (w - sh.w_lo) * sh.B) + d - 1 : INVALID_KEY;
+            const uint32_t key = (live && d) ? (sh.tab_stride ? piece * sh.B : (w - sh.w_lo) * sh.B) + d - 1 : INVALID_KEY;
             // warp aggregation: one atomic per distinct key per warp (hot buckets stay cheap)
             const uint32_t peers = __match_any_sync(0xffffffffu, key);
             const uint32_t leader = __ffs(peers) - 1;
@@ -452,7 +456,7 @@ static uint32_t ilog2_floor(uint64_t x) {
     return r;
 }
 
-static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1, const MsmTables *tabs = nullptr) {
+static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1, const MsmTables *tabs = nullptr, uint32_t batch = 1) {
     MsmShape sh;
     memset(&sh, 0, sizeof sh);
     int c = (int)ilog2_floor(n) - 3;
@@ -469,9 +473,10 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_h
     sh.w_lo = (uint32_t)w_lo;
     sh.W = (w_hi < 0 ? sh.W_all : (uint32_t)w_hi) - sh.w_lo;
     sh.B = 1u << (sh.c - 1);
-    sh.Wb = tabs ? 1 : sh.W;
+    sh.batch = batch;
+    sh.Wb = tabs ? batch : sh.W;
     sh.n = n;
-    sh.t_max = ((uint64_t)sh.W * n + 3) & ~3ull;
+    sh.t_max = ((uint64_t)sh.W * n * batch + 3) & ~3ull;
     const uint64_t want = (uint64_t)ctx->sm_count * 1024;
     uint32_t L1 = 64;
     while (L1 > 8 && sh.t_max / L1 < want) L1 >>= 1;
@@ -494,7 +499,8 @@ void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W) {
     *W = sh.W_all;
 }
 
-static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out, cudaStream_t st);
+static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out, cudaStream_t st,
+                            uint32_t batch = 1);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
     return msm_run_impl(ctx, d_bases, d_scalars, n, 0, -1, nullptr, out_affine, st);
@@ -528,14 +534,31 @@ int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c,
     return SB_OK;
 }
 
+// `batch` scalar vectors (contiguous, n each) against the same table bases in ONE launch set: out = batch x 64 B affine commitments.
+// The vectors only differ in which bucket set their digits land in, so sort, accumulation and bucket reduction run once over
+// batch * W * n digits and the latency-bound tails (upper reduce levels, bucket hierarchy, host round trip) are paid once.
+int32_t msm_run_tables_batch(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, uint8_t *out_affine, cudaStream_t st) {
+    SB_REQUIRE(tabs && tabs->d_tables && n <= tabs->stride && batch >= 1, "msm_run_tables_batch: bad arguments");
+    // one launch set as long as the sorted list fits 32-bit positions
+    uint32_t done = 0;
+    while (done < batch) {
+        uint32_t take = batch - done;
+        while (take > 1 && (uint64_t)tabs->W * n * take >= (1ull << 32) - 8) take--;
+        SB_TRY(msm_run_impl(ctx, tabs->d_tables, (const uint8_t *)d_scalars + (size_t)done * n * 32, n, 0, -1, tabs, out_affine + (size_t)done * 64, st, take));
+        done += take;
+    }
+    return SB_OK;
+}
+
 static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out_affine,
-                            cudaStream_t st) {
+                            cudaStream_t st, uint32_t batch) {
     if (n == 0) {
-        memset(out_affine, 0, w_hi < 0 ? 64 : (size_t)(tabs ? 1 : (w_hi - w_lo)) * 128);
+        memset(out_affine, 0, w_hi < 0 ? (size_t)64 * batch : (size_t)(tabs ? 1 : (w_hi - w_lo)) * 128);
         return SB_OK;
     }
     SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
-    const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs);
+    SB_REQUIRE(batch == 1 || (tabs && w_hi < 0), "msm: batches need table bases and the full window range");
+    const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs, batch);
     SB_REQUIRE(w_hi < 0 || (uint32_t)w_hi <= sh.W_all, "msm: window range exceeds the scalar");
     SB_REQUIRE(sh.t_max < (1ull << 32), "msm: window count * n must be < 2^32");
     const uint64_t nb = (uint64_t)sh.Wb * sh.B;
@@ -574,7 +597,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     SB_CUDA_TRY(cudaMemsetAsync(d_counts, 0, (nb + 4) * 4, st));
     SB_CUDA_TRY(cudaMemsetAsync(d_skeys, 0xff, sh.t_max * 4, st));
     SB_CUDA_TRY(cudaMemsetAsync(d_buckets, 0, nb * 128, st));
-    unsigned sort_grid = (unsigned)((n + 255) / 256);
+    unsigned sort_grid = (unsigned)((n * batch + 255) / 256);
     const unsigned max_grid = (unsigned)ctx->sm_count * 16;
     if (sort_grid > max_grid) sort_grid = max_grid;
     SB_LAUNCH(ctx, msm_sort_kernel<false>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_counts, nullptr, nullptr);
@@ -635,8 +658,10 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
     cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
-    if (w_hi < 0) host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.Wb, (int)sh.c, out_affine);
-    else memcpy(out_affine, ctx->pinned, (size_t)sh.Wb * 128);
+    if (w_hi >= 0) memcpy(out_affine, ctx->pinned, (size_t)sh.Wb * 128);
+    else if (tabs)
+        for (uint32_t j = 0; j < batch; j++) host_fold_windows((const uint8_t *)ctx->pinned + (size_t)j * 128, 1, (int)sh.c, out_affine + (size_t)j * 64);
+    else host_fold_windows((const uint8_t *)ctx->pinned, (int)sh.Wb, (int)sh.c, out_affine);
     return SB_OK;
 }
 

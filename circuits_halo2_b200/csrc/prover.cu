@@ -640,6 +640,13 @@ int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basi
     return sb_g1_sum_affine(all.data(), Wd, out);
 }
 
+// m commitments over contiguous scalar vectors: one batched launch set on a single GPU, the sharded path one by one
+int32_t msm_commit_batch(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint32_t m, uint8_t *out, cudaStream_t st) {
+    if (!comm || comm->world <= 1) return srs_msm_batch(ctx, srs, basis, d_scalars, n, m, out, st);
+    for (uint32_t j = 0; j < m; j++) SB_TRY(msm_commit(ctx, comm, srs, basis, (const uint8_t *)d_scalars + (size_t)j * n * 32, n, out + (size_t)j * 64, st));
+    return SB_OK;
+}
+
 int32_t pk_coset_pows(sb_ctx *ctx, const sb_pk *pk, uint32_t j, void **out, cudaStream_t st) {
     const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
     if (pk->coset_pows.size() != n_cosets) pk->coset_pows.assign(n_cosets, nullptr);
@@ -723,9 +730,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
     }
-    for (int c = 0; c < A; c++) {
-        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, adv[c], n, pt, st));
-        if (!tr.write_point(pt)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
+    {
+        std::vector<uint8_t> pts((size_t)A * 64);
+        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, adv[0], n, (uint32_t)A, pts.data(), st));  // the A columns are contiguous
+        for (int c = 0; c < A; c++)
+            if (!tr.write_point(pts.data() + (size_t)c * 64)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr theta = tr.squeeze();
     mark();  // [0] instance / advice upload, blinding, lagrange_to_coeff, 3 advice commitments
@@ -767,13 +776,12 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_CUDA_TRY(cudaMemcpyAsync(L.in_poly, L.p_in, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.in_poly, st));
         (void)rng.next_fr();
-        uint8_t pin[64], ptab[64];
-        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, L.p_in, n, pin, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
         (void)rng.next_fr();
-        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, L.p_tab, n, ptab, st));
-        if (!tr.write_point(pin) || !tr.write_point(ptab)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
+        uint8_t pin_tab[128];
+        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, L.p_in, n, 2, pin_tab, st));  // p_in and p_tab are adjacent in the lookup scratch block
+        if (!tr.write_point(pin_tab) || !tr.write_point(pin_tab + 64)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr beta = tr.squeeze();
     const Fr gamma = tr.squeeze();
@@ -965,9 +973,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
     const int n_pieces = cs.degree - 1;
     for (int i = 0; i < n_pieces; i++) (void)rng.next_fr();
-    for (int i = 0; i < n_pieces; i++) {
-        SB_TRY(msm_commit(ctx, comm, pk->srs, 0, (uint8_t *)d_h + (size_t)i * n * 32, n, pt, st));
-        if (!tr.write_point(pt)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
+    {
+        std::vector<uint8_t> pts((size_t)n_pieces * 64);
+        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 0, d_h, n, (uint32_t)n_pieces, pts.data(), st));
+        for (int i = 0; i < n_pieces; i++)
+            if (!tr.write_point(pts.data() + (size_t)i * 64)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr x = tr.squeeze();
     mark();  // [7] divide by t(X), extended iNTT, quotient piece commitments

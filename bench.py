@@ -321,6 +321,14 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = n * W * (64 + 8) + n * 32  # gathered base + sorted (key,val) per digit, + scalar
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture of this same workload, committed under profiles/
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("log_n") == args.log_n and tj.get("fixed_base_tables") == (not args.no_tables):
+            traffic, traffic_src = tj["msm_reduce_level1_dram_bytes_per_launch"], tj.get("source")
+    except Exception:
+        pass
     roofline = {
         "kernel": "msm_reduce_kernel<true> (level-1 bucket accumulation)",
         "bound": "imad", "achieved": achieved, "peak": imadw_peak, "unit": "T wide-IMAD/s", "frac": achieved / imadw_peak,
@@ -330,7 +338,7 @@ def main():
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
         "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "phases_ms": {"recode_sort": mean_phase[0], "reduce_level1": mean_phase[1], "reduce_levels_ge2": mean_phase[2],
                       "bucket_reduce": mean_phase[3], "device_total": mean_phase[4]},
     }

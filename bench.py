@@ -297,7 +297,7 @@ def main():
     ms_e2e /= args.steps
     e2e_val = world * n / (ms_e2e * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (msm_reduce_kernel<true>: level-1 bucket accumulation) ----
+    # ---- roofline of the dominant kernel (msm_reduce_first_kernel: level-1 bucket accumulation) ----
     c, W, L1, seg = [int(x) for x in shape]
     k_ms = statistics.mean(p[1] for p in phases)
     mean_phase = [statistics.mean(p[i] for p in phases) for i in range(5)]
@@ -330,7 +330,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "msm_reduce_kernel<true> (level-1 bucket accumulation)",
+        "kernel": "msm_reduce_first_kernel (level-1 bucket accumulation)",
         "bound": "imad", "achieved": achieved, "peak": imadw_peak, "unit": "T wide-IMAD/s", "frac": achieved / imadw_peak,
         "peak_source": "measured live: sb_bench_imad_wide (8 independent IMAD.WIDE chains/thread)",
         "imad32_peak": imad_peak, "field_mul_peak_G_per_s": fmul_peak,

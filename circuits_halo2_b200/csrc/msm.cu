@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t raw_window(const uint32_t s[8], uint32_t bit
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uint64_t n, MsmShape sh, uint32_t *counts /*histogram or cursor*/,
-                                                       uint32_t *skeys, uint32_t *svals) {
+                                                       uint32_t *svals) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     // warp-uniform trip count so that every lane reaches the match_any below
@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                 pos = __shfl_sync(0xffffffffu, pos, leader);
                 if (key != INVALID_KEY) {
                     pos += __popc(peers & ((1u << lane) - 1));
-                    skeys[pos] = key;
                     svals[pos] = (uint32_t)(sh.tab_stride ? w * sh.tab_stride + i : i) | (neg << 31);
                 }
             }
@@ -202,34 +201,94 @@ __device__ __forceinline__ void store_xyzz(uint4 *p, const xyzz_t &a) {
     store_fp(p + 6, a.zzz);
 }
 
-// FIRST: entries are (key, base index | sign) and points are gathered from the affine bases.
-// else : entries are (key, XYZZ partial) produced by the previous level.
-template <bool FIRST>
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t *keys, const uint32_t *vals, const uint4 *bases, const uint4 *pts_in,
-                                                         uint64_t n_in, uint32_t L, uint4 *buckets, uint32_t *keys_out, uint4 *pts_out,
-                                                         uint64_t nchunks) {
+// Level 1: the sorted list holds only (base index | sign); the bucket of position `pos` follows from the exclusive offsets of the
+// counting sort (offsets[b] <= pos < offsets[b + 1]), so the scatter writes 4 bytes per digit instead of 8 and nothing reads keys
+// back.  A thread finds the bucket of its first entry by binary search and re-searches whenever it walks off the current bucket
+// (a linear walk could cross arbitrarily many empty buckets).  offsets[nb] is the number of valid digits.
+__device__ __forceinline__ uint32_t bucket_of(const uint32_t *offsets, uint32_t nb, uint32_t pos) {
+    uint32_t lo = 0, hi = nb;  // largest b in [0, nb) with offsets[b] <= pos
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= pos) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(128) msm_reduce_first_kernel(const uint32_t *offsets, uint32_t nb, const uint32_t *vals, const uint4 *bases, uint32_t L, uint4 *buckets,
+                                                               uint32_t *keys_out, uint4 *pts_out, uint64_t nchunks) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nchunks) return;
+    const uint32_t n_valid = __ldg(offsets + nb);
+    const uint64_t start64 = t * L;
+    uint32_t k0 = INVALID_KEY, k1 = INVALID_KEY;  // partial slots of this chunk
+    if (start64 < n_valid) {
+        const uint32_t start = (uint32_t)start64;
+        const uint32_t end = min(n_valid, start + L);
+        uint32_t cur = bucket_of(offsets, nb, start);
+        uint32_t next_off = __ldg(offsets + cur + 1);
+        uint32_t nruns = 1;
+        xyzz_t acc = xyzz_t::identity();
+        for (uint32_t pos = start; pos < end; pos += 4) {
+            const uint4 v4 = *reinterpret_cast<const uint4 *>(vals + pos);  // start and L are multiples of 4; the list is padded
+            const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (pos + q >= end) break;
+                if (pos + q >= next_off) {
+                    if (nruns == 1) {
+                        k0 = cur;
+                        store_xyzz(pts_out + 8 * (2 * t), acc);
+                    } else {
+                        store_xyzz(buckets + 8 * (uint64_t)cur, acc);  // interior run: sole owner of its bucket
+                    }
+                    // the next bucket is almost always the neighbour: one load; otherwise (runs of empty buckets) search
+                    cur++;
+                    next_off = __ldg(offsets + cur + 1);
+                    if (pos + q >= next_off) {
+                        cur = bucket_of(offsets, nb, pos + q);
+                        next_off = __ldg(offsets + cur + 1);
+                    }
+                    nruns++;
+                    acc = xyzz_t::identity();
+                }
+                const uint32_t v = vv[q];
+                const uint4 *bp = bases + 4 * (uint64_t)(v & 0x7fffffffu);
+                affine_t p;
+                p.x = ldg_fp<FqParams>(bp);
+                p.y = ldg_fp<FqParams>(bp + 2);
+                madd(acc, p, (v >> 31) != 0);
+            }
+        }
+        if (nruns == 1) {
+            k0 = cur;
+            store_xyzz(pts_out + 8 * (2 * t), acc);
+        } else {
+            k1 = cur;
+            store_xyzz(pts_out + 8 * (2 * t + 1), acc);
+        }
+    }
+    keys_out[2 * t] = k0;
+    keys_out[2 * t + 1] = k1;
+}
+
+// Levels >= 2: entries are (key, XYZZ partial) produced by the previous level; INVALID slots are skipped.
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t *keys, const uint4 *pts_in, uint64_t n_in, uint32_t L, uint4 *buckets, uint32_t *keys_out,
+                                                         uint4 *pts_out, uint64_t nchunks) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nchunks) return;
     const uint64_t start = t * L;
     uint32_t cur = INVALID_KEY, nruns = 0;
     uint32_t k0 = INVALID_KEY, k1 = INVALID_KEY;  // partial slots of this chunk
     xyzz_t acc = xyzz_t::identity();
-    bool done = false;
-    for (uint32_t j = 0; j < L && !done; j += 4) {
+    for (uint32_t j = 0; j < L; j += 4) {
         const uint64_t pos = start + j;
         if (pos >= n_in) break;
         const uint4 k4 = *reinterpret_cast<const uint4 *>(keys + pos);
-        uint4 v4 = make_uint4(0, 0, 0, 0);
-        if (FIRST) v4 = *reinterpret_cast<const uint4 *>(vals + pos);
         const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
-        const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t k = (pos + q < n_in) ? kk[q] : INVALID_KEY;  // n_in need not be a multiple of 4
-            if (k == INVALID_KEY) {
-                if (FIRST) { done = true; break; }  // level 1: valid entries are a prefix of the list
-                continue;
-            }
+            if (k == INVALID_KEY) continue;
             if (k != cur) {
                 if (cur != INVALID_KEY) {
                     if (nruns == 1) {
@@ -243,17 +302,8 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t *keys, c
                 nruns++;
                 acc = xyzz_t::identity();
             }
-            if (FIRST) {
-                const uint32_t v = vv[q];
-                const uint4 *bp = bases + 4 * (uint64_t)(v & 0x7fffffffu);
-                affine_t p;
-                p.x = ldg_fp<FqParams>(bp);
-                p.y = ldg_fp<FqParams>(bp + 2);
-                madd(acc, p, (v >> 31) != 0);
-            } else {
-                xyzz_t p = load_xyzz(pts_in + 8 * (pos + q));
-                add(acc, p);
-            }
+            xyzz_t p = load_xyzz(pts_in + 8 * (pos + q));
+            add(acc, p);
         }
     }
     if (cur != INVALID_KEY) {
@@ -564,14 +614,13 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     const uint64_t nb = (uint64_t)sh.Wb * sh.B;
 
     // ---- scratch ----
-    uint32_t *d_counts, *d_cursor, *d_tiles, *d_skeys, *d_svals;
+    uint32_t *d_counts, *d_cursor, *d_tiles, *d_svals;
     uint4 *d_buckets, *d_seg, *d_win;
     const uint64_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
     SB_TRY(scratch_get(ctx, "msm_counts", (nb + 4) * 4, (void **)&d_counts));
     SB_TRY(scratch_get(ctx, "msm_cursor", (nb + 4) * 4, (void **)&d_cursor));
     SB_TRY(scratch_get(ctx, "msm_tiles", (ntiles + 4) * 4, (void **)&d_tiles));
-    SB_TRY(scratch_get(ctx, "msm_skeys", sh.t_max * 4, (void **)&d_skeys));
-    SB_TRY(scratch_get(ctx, "msm_svals", sh.t_max * 4, (void **)&d_svals));
+    SB_TRY(scratch_get(ctx, "msm_svals", (sh.t_max + 64) * 4, (void **)&d_svals));
     SB_TRY(scratch_get(ctx, "msm_buckets", nb * 128, (void **)&d_buckets));
     const uint32_t nseg = sh.B >> sh.seg_log;
     {
@@ -595,29 +644,27 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
 
     // ---- 1+2: histogram, scan, scatter ----
     SB_CUDA_TRY(cudaMemsetAsync(d_counts, 0, (nb + 4) * 4, st));
-    SB_CUDA_TRY(cudaMemsetAsync(d_skeys, 0xff, sh.t_max * 4, st));
     SB_CUDA_TRY(cudaMemsetAsync(d_buckets, 0, nb * 128, st));
     unsigned sort_grid = (unsigned)((n * batch + 255) / 256);
     const unsigned max_grid = (unsigned)ctx->sm_count * 16;
     if (sort_grid > max_grid) sort_grid = max_grid;
-    SB_LAUNCH(ctx, msm_sort_kernel<false>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_counts, nullptr, nullptr);
+    SB_LAUNCH(ctx, msm_sort_kernel<false>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_counts, nullptr);
     SB_LAUNCH(ctx, scan_tile_sums_kernel, (unsigned)ntiles, SCAN_THREADS, 0, st, d_counts, nb, d_tiles);
     SB_LAUNCH(ctx, scan_of_tile_sums_kernel, 1, 1024, 0, st, d_tiles, ntiles, d_counts + nb);
     SB_LAUNCH(ctx, scan_apply_kernel, (unsigned)ntiles, SCAN_THREADS, 0, st, d_counts, nb, d_tiles, d_counts, d_cursor);
-    SB_LAUNCH(ctx, msm_sort_kernel<true>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_cursor, d_skeys, d_svals);
+    SB_LAUNCH(ctx, msm_sort_kernel<true>, sort_grid, 256, 0, st, (const uint4 *)d_scalars, (uint64_t)n, sh, d_cursor, d_svals);
 
     // ---- 3: reduce-by-key levels ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[1], st));
-    SB_LAUNCH(ctx, msm_reduce_kernel<true>, (unsigned)((nchunks1 + 127) / 128), 128, 0, st, d_skeys, d_svals, (const uint4 *)d_bases,
-              (const uint4 *)nullptr, sh.t_max, sh.L1, d_buckets, d_keys_a, d_pts_a, nchunks1);
+    SB_LAUNCH(ctx, msm_reduce_first_kernel, (unsigned)((nchunks1 + 127) / 128), 128, 0, st, (const uint32_t *)d_counts, (uint32_t)nb, d_svals, (const uint4 *)d_bases,
+              sh.L1, d_buckets, d_keys_a, d_pts_a, nchunks1);
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[2], st));
     uint64_t slots = slots_a;
     uint32_t *kin = d_keys_a, *kout = d_keys_b;
     uint4 *pin = d_pts_a, *pout = d_pts_b;
     while (slots > FINAL_MAX) {
         const uint64_t nch = (slots + LK - 1) / LK;
-        SB_LAUNCH(ctx, msm_reduce_kernel<false>, (unsigned)((nch + 127) / 128), 128, 0, st, kin, (const uint32_t *)nullptr, (const uint4 *)nullptr,
-                  (const uint4 *)pin, slots, (uint32_t)LK, d_buckets, kout, pout, nch);
+        SB_LAUNCH(ctx, msm_reduce_kernel, (unsigned)((nch + 127) / 128), 128, 0, st, kin, (const uint4 *)pin, slots, (uint32_t)LK, d_buckets, kout, pout, nch);
         slots = 2 * nch;
         uint32_t *tk = kin; kin = kout; kout = tk;
         uint4 *tp = pin; pin = pout; pout = tp;

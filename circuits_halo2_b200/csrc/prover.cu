@@ -390,13 +390,9 @@ int32_t poly_div_by_roots_k(sb_ctx *ctx, uint32_t k, const fr_t &omega_d, const 
     SB_TRY(scratch_get(ctx, "div_den", n * 32, &d_den));
     SB_TRY(fp_vec_op(ctx, 0, 0, d_p, g_pows, d_p, n, st));
     SB_TRY(ntt_run(ctx, d_p, (const uint8_t *)omega_d.v, k, st));
-    ExprP den = nullptr;
-    for (const Fr &r : roots) {
-        ExprP f = e_sub(e_col(0, 0), ec(r));
-        den = den ? e_mul(den, f) : f;
-    }
-    Program prog = compile_terms({den}, nullptr);
-    SB_TRY(expr_eval(ctx, prog, {div_x}, k, 0, d_den, st));
+    std::vector<fr_t> rd;
+    for (const Fr &r : roots) rd.push_back(to_dev(r));
+    SB_TRY(fr_vanish(ctx, div_x, rd, d_den, n, st));
     SB_TRY(fr_batch_invert(ctx, d_den, n, st));
     SB_TRY(fp_vec_op(ctx, 0, 0, d_p, d_den, d_p, n, st));
     SB_TRY(ntt_run(ctx, d_p, (const uint8_t *)omega_inv_d.v, k, st));
@@ -455,16 +451,29 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         if (!found) sets.push_back({key, {pid}});
     }
     const Fr v = tr.squeeze();
-    void *d_hx, *d_nx, *d_lx;
+    void *d_hx, *d_nx, *d_lx, *d_invd;
     SB_TRY(scratch_get(ctx, "sh_hx", n * 32, &d_hx));
     SB_TRY(scratch_get(ctx, "sh_nx", n * 32, &d_nx));
     SB_TRY(scratch_get(ctx, "sh_lx", n * 32, &d_lx));
+    SB_TRY(scratch_get(ctx, "sh_invd", n * 32, &d_invd));
+    // h(X) = sum_i v^i N_i(X) / Z_{S_i}(X), all divisions exact.  Work on the coset g*H: E = sum_i v^i NTT(g^j N_i) * (1 / Z_{S_i}) is
+    // accumulated in the evaluation domain, so the whole sum needs ONE inverse NTT, and 1 / Z_{S_i} = (1 / Z_T) * prod_{p in T \ S_i}(x - p)
+    // with T the super set of opening points, so ONE batch inversion serves every rotation set.
+    const std::vector<Fr> super(super_points.begin(), super_points.end());
+    {
+        std::vector<fr_t> sd;
+        for (const Fr &p : super) sd.push_back(to_dev(p));
+        SB_TRY(fr_vanish(ctx, pk->div_x, sd, d_invd, n, st));
+        SB_TRY(fr_batch_invert(ctx, d_invd, n, st));
+    }
     std::vector<std::vector<std::vector<Fr>>> low(sets.size());
     Fr v_pow = hfr::ONE;
     for (size_t si = 0; si < sets.size(); si++) {
         RSet &s = sets[si];
         Fr y_pow = hfr::ONE;
         std::vector<Fr> head(s.pts.size(), hfr::ZERO);
+        std::vector<const void *> lc_polys;
+        std::vector<fr_t> lc_coeffs;
         for (size_t mi = 0; mi < s.members.size(); mi++) {
             const int pid = s.members[mi];
             std::vector<Fr> evs;
@@ -472,25 +481,37 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
             std::vector<Fr> r = lagrange_interpolate(s.pts, evs);
             low[si].push_back(r);
             for (size_t i = 0; i < r.size(); i++) head[i] = hfr::add(head[i], hfr::mul(r[i], y_pow));
-            SB_TRY(fr_axpy(ctx, d_nx, polys[pid], to_dev(y_pow), n, mi == 0, st));
+            lc_polys.push_back(polys[pid]);
+            lc_coeffs.push_back(to_dev(y_pow));
             y_pow = hfr::mul(y_pow, y);
         }
         std::vector<fr_t> head_d;
         for (const Fr &h : head) head_d.push_back(to_dev(h));
-        SB_TRY(fr_sub_head(ctx, d_nx, head_d.data(), (uint32_t)head_d.size(), st));
-        SB_TRY(poly_div_by_roots(ctx, pk, d_nx, s.pts, st));
-        SB_TRY(fr_axpy(ctx, d_hx, d_nx, to_dev(v_pow), n, si == 0, st));
+        SB_REQUIRE(head_d.size() <= 4, "shplonk: rotation sets of more than 4 points are not supported");
+        SB_TRY(fr_lincomb(ctx, d_nx, lc_polys, lc_coeffs, head_d, n, false, st));
+        // N_i on the coset
+        SB_TRY(fp_vec_op(ctx, 0, 0, d_nx, pk->div_g_pows, d_nx, n, st));
+        SB_TRY(ntt_run(ctx, d_nx, (const uint8_t *)pk->dom->omega.v, pk->k, st));
+        std::vector<fr_t> comp;
+        for (const Fr &p : super) {
+            bool in = false;
+            for (const Fr &q : s.pts) in = in || (q == p);
+            if (!in) comp.push_back(to_dev(p));
+        }
+        SB_TRY(fr_div_combine(ctx, d_hx, d_nx, d_invd, pk->div_x, comp, to_dev(v_pow), n, si == 0, st));
         v_pow = hfr::mul(v_pow, v);
     }
+    SB_TRY(ntt_run(ctx, d_hx, (const uint8_t *)pk->dom->omega_inv.v, pk->k, st));
+    SB_TRY(fp_vec_op(ctx, 0, 0, d_hx, pk->div_ginv_scaled, d_hx, n, st));
     uint8_t pt[64];
     SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_hx, n, pt, st));
     if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
     const Fr u = tr.squeeze();
-    std::vector<Fr> super(super_points.begin(), super_points.end());
     std::vector<Fr> z_diffs;
     v_pow = hfr::ONE;
     Fr const_term = hfr::ZERO;
-    bool first = true;
+    std::vector<const void *> lc_polys;
+    std::vector<fr_t> lc_coeffs;
     for (size_t si = 0; si < sets.size(); si++) {
         RSet &s = sets[si];
         Fr z_i = hfr::ONE;
@@ -504,8 +525,8 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         const Fr scale = hfr::mul(z_i, v_pow);
         for (size_t mi = 0; mi < s.members.size(); mi++) {
             const Fr coeff = hfr::mul(scale, y_pow);
-            SB_TRY(fr_axpy(ctx, d_lx, polys[s.members[mi]], to_dev(coeff), n, first, st));
-            first = false;
+            lc_polys.push_back(polys[s.members[mi]]);
+            lc_coeffs.push_back(to_dev(coeff));
             const_term = hfr::add(const_term, hfr::mul(coeff, eval_small(low[si][mi], u)));
             y_pow = hfr::mul(y_pow, y);
         }
@@ -513,9 +534,9 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
     }
     Fr zt = hfr::ONE;
     for (const Fr &p : super) zt = hfr::mul(zt, hfr::sub(u, p));
-    SB_TRY(fr_axpy(ctx, d_lx, d_hx, to_dev(hfr::neg(zt)), n, false, st));
-    fr_t ct = to_dev(const_term);
-    SB_TRY(fr_sub_head(ctx, d_lx, &ct, 1, st));
+    lc_polys.push_back(d_hx);
+    lc_coeffs.push_back(to_dev(hfr::neg(zt)));
+    SB_TRY(fr_lincomb(ctx, d_lx, lc_polys, lc_coeffs, {to_dev(const_term)}, n, false, st));
     SB_TRY(poly_div_by_roots(ctx, pk, d_lx, {u}, st));
     SB_TRY(fr_scale(ctx, d_lx, n, to_dev(hfr::inv(z_diffs[0])), st));
     SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_lx, n, pt, st));

@@ -19,6 +19,14 @@ int32_t lookup_permute(sb_ctx *ctx, const void *d_in, const void *d_tab, size_t 
 int32_t chacha_fr_fill(sb_ctx *ctx, const uint32_t key[8], uint64_t counter0, void *d_out, size_t n, cudaStream_t st);
 int32_t fr_axpy(sb_ctx *ctx, void *d_acc, const void *d_p, const fr_t &s, size_t n, bool first, cudaStream_t st);
 int32_t fr_sub_head(sb_ctx *ctx, void *d_acc, const fr_t *c, uint32_t k, cudaStream_t st);
+// out (+)= sum_m coeffs[m] * polys[m], then out[i] -= head[i] for i < head.size() (<= 4); one pass per 24 polynomials
+int32_t fr_lincomb(sb_ctx *ctx, void *d_out, const std::vector<const void *> &polys, const std::vector<fr_t> &coeffs, const std::vector<fr_t> &head, size_t n, bool accumulate,
+                   cudaStream_t st);
+// out[j] = prod_r (x[j] - roots[r])
+int32_t fr_vanish(sb_ctx *ctx, const void *d_x, const std::vector<fr_t> &roots, void *d_out, size_t n, cudaStream_t st);
+// acc[j] (+)= scale * f[j] * inv_d[j] * prod_{r in comp} (x[j] - r)
+int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_inv_d, const void *d_x, const std::vector<fr_t> &comp, const fr_t &scale, size_t n, bool first,
+                       cudaStream_t st);
 
 // ---- expr.cu: expression DAGs compiled to a register program, evaluated over whole columns ---
 struct Expr;

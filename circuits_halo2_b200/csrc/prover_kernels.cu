@@ -522,4 +522,91 @@ int32_t fr_sub_head(sb_ctx *ctx, void *d_acc, const fr_t *c, uint32_t k, cudaStr
     return SB_OK;
 }
 
+
+// ------------------------------------------------------------------ SHPLONK helpers
+// out = sum_m coeff[m] * poly[m] over up to LINCOMB_MAX coefficient vectors in ONE pass (each input read once, one write),
+// minus up to 4 leading coefficients (the low-degree interpolant r(X) of the rotation set).
+static const int LINCOMB_MAX = 24;
+struct LinCombArgs {
+    const uint4 *poly[LINCOMB_MAX];
+    fr_t coeff[LINCOMB_MAX];
+    fr_t head[4];
+    uint32_t m, n_head, accumulate;
+};
+__global__ void fr_lincomb_kernel(uint4 *out, const LinCombArgs a, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t acc = a.accumulate ? load_fp<FrParams>(out + 2 * i) : fr_t::zero();
+    for (uint32_t m = 0; m < a.m; m++) acc = add(acc, mul(load_fp<FrParams>(a.poly[m] + 2 * i), a.coeff[m]));
+    if (i < a.n_head) acc = sub(acc, a.head[i]);
+    store_fp(out + 2 * i, acc);
+}
+int32_t fr_lincomb(sb_ctx *ctx, void *d_out, const std::vector<const void *> &polys, const std::vector<fr_t> &coeffs, const std::vector<fr_t> &head, size_t n, bool accumulate,
+                   cudaStream_t st) {
+    SB_REQUIRE(polys.size() == coeffs.size() && head.size() <= 4, "fr_lincomb: bad arguments");
+    size_t done = 0;
+    bool acc = accumulate;
+    do {
+        LinCombArgs a;
+        const size_t take = std::min((size_t)LINCOMB_MAX, polys.size() - done);
+        for (size_t m = 0; m < take; m++) { a.poly[m] = (const uint4 *)polys[done + m]; a.coeff[m] = coeffs[done + m]; }
+        for (size_t m = take; m < (size_t)LINCOMB_MAX; m++) { a.poly[m] = nullptr; a.coeff[m] = fr_t::zero(); }
+        a.m = (uint32_t)take;
+        const bool last = done + take == polys.size();
+        a.n_head = last ? (uint32_t)head.size() : 0;
+        for (size_t h = 0; h < 4; h++) a.head[h] = h < head.size() ? head[h] : fr_t::zero();
+        a.accumulate = acc ? 1 : 0;
+        SB_LAUNCH(ctx, fr_lincomb_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_out, a, (uint64_t)n);
+        done += take;
+        acc = true;
+    } while (done < polys.size());
+    return SB_OK;
+}
+
+// out[j] = prod_r (x[j] - root[r])   (vanishing polynomial of a rotation set on the division coset)
+struct RootArgs {
+    fr_t r[8];
+    uint32_t k;
+};
+__global__ void fr_vanish_kernel(const uint4 *x, RootArgs ra, uint4 *out, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr_t xv = load_fp<FrParams>(x + 2 * i);
+    fr_t p = sub(xv, ra.r[0]);
+    for (uint32_t q = 1; q < ra.k; q++) p = mul(p, sub(xv, ra.r[q]));
+    store_fp(out + 2 * i, p);
+}
+int32_t fr_vanish(sb_ctx *ctx, const void *d_x, const std::vector<fr_t> &roots, void *d_out, size_t n, cudaStream_t st) {
+    SB_REQUIRE(!roots.empty() && roots.size() <= 8, "fr_vanish: 1..8 roots");
+    RootArgs ra;
+    for (size_t q = 0; q < 8; q++) ra.r[q] = q < roots.size() ? roots[q] : fr_t::zero();
+    ra.k = (uint32_t)roots.size();
+    SB_LAUNCH(ctx, fr_vanish_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const uint4 *)d_x, ra, (uint4 *)d_out, (uint64_t)n);
+    return SB_OK;
+}
+
+// acc[j] (+)= scale * f[j] * inv_d[j] * prod_{r in comp} (x[j] - r):  f / Z_S on the coset, with 1 / Z_S = (1 / Z_T) * prod over the
+// points of the super set T that are NOT in S (one batch inversion of Z_T serves every rotation set)
+__global__ void fr_div_combine_kernel(uint4 *acc, const uint4 *f, const uint4 *inv_d, const uint4 *x, RootArgs comp, fr_t scale, uint64_t n, int first) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v = mul(mul(load_fp<FrParams>(f + 2 * i), load_fp<FrParams>(inv_d + 2 * i)), scale);
+    if (comp.k) {
+        const fr_t xv = load_fp<FrParams>(x + 2 * i);
+        for (uint32_t q = 0; q < comp.k; q++) v = mul(v, sub(xv, comp.r[q]));
+    }
+    if (!first) v = add(v, load_fp<FrParams>(acc + 2 * i));
+    store_fp(acc + 2 * i, v);
+}
+int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_inv_d, const void *d_x, const std::vector<fr_t> &comp, const fr_t &scale, size_t n, bool first,
+                       cudaStream_t st) {
+    SB_REQUIRE(comp.size() <= 8, "fr_div_combine: at most 8 complement roots");
+    RootArgs ra;
+    for (size_t q = 0; q < 8; q++) ra.r[q] = q < comp.size() ? comp[q] : fr_t::zero();
+    ra.k = (uint32_t)comp.size();
+    SB_LAUNCH(ctx, fr_div_combine_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_acc, (const uint4 *)d_f, (const uint4 *)d_inv_d, (const uint4 *)d_x, ra, scale,
+              (uint64_t)n, first ? 1 : 0);
+    return SB_OK;
+}
+
 }  // namespace sb

@@ -808,21 +808,31 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     const Fr gamma = tr.squeeze();
     mark();  // [1] lookup: compress, sort / permute, 2 iNTT, 2 commitments
 
-    // ---- permutation argument
+    // ---- permutation argument and lookup products: all grand-product columns Z are built side by side in one
+    //      buffer and committed by ONE batched MSM.  A permutation set's product starts from the previous set's last value; each set is
+    //      scanned from 1 and scaled afterwards by the running boundary value (read back once), which is the same field element.
     const int chunk = cs.degree - 2;
     const int n_sets = (P + chunk - 1) / chunk;
     struct PermSet { void *z_poly, *z_coset; int first, count; };
     std::vector<PermSet> psets(n_sets);
     {
-        void *d_den, *d_num, *d_z;
+        const int n_z = n_sets + (int)lks.size();
+        void *d_den, *d_num;
+        uint8_t *d_zall;
         SB_TRY(scratch_get(ctx, "pf_perm_den", n * 32, &d_den));
         SB_TRY(scratch_get(ctx, "pf_perm_num", n * 32, &d_num));
-        SB_TRY(scratch_get(ctx, "pf_perm_z", n * 32, &d_z));
+        SB_TRY(scratch_get(ctx, "pf_z_all", (size_t)n_z * n * 32, (void **)&d_zall));
         uint8_t *zb;
         SB_TRY(scratch_get(ctx, "pf_perm_polys", (size_t)n_sets * (n + en) * 32, (void **)&zb));
         Fr delta_pow = hfr::ONE;
         const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
-        Fr last_z = hfr::ONE;
+        auto ratio_scan = [&](ExprP den, ExprP num, void *d_z) -> int32_t {
+            SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den, st));
+            SB_TRY(expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num, st));
+            SB_TRY(fr_batch_invert(ctx, d_den, n, st));
+            SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, n, st));
+            return fr_running_product(ctx, d_den, n, fr_t::one(), d_z, n, st);
+        };
         for (int s = 0; s < n_sets; s++) {
             PermSet &S = psets[s];
             S.first = s * chunk;
@@ -839,51 +849,48 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
                 num = num ? e_mul(num, nterm) : nterm;
                 delta_pow = hfr::mul(delta_pow, DELTA);
             }
-            SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den, st));
-            SB_TRY(expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num, st));
-            SB_TRY(fr_batch_invert(ctx, d_den, n, st));
-            SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, n, st));
-            SB_TRY(fr_running_product(ctx, d_den, n, to_dev(last_z), d_z, n, st));
+            SB_TRY(ratio_scan(den, num, d_zall + (size_t)s * n * 32));
+        }
+        for (size_t li = 0; li < lks.size(); li++) {
+            LookupState &L = lks[li];
+            lcols[L_LK + 0] = L.c_in; lcols[L_LK + 1] = L.c_tab; lcols[L_LK + 2] = L.p_in; lcols[L_LK + 3] = L.p_tab;
+            ExprP den = e_mul(e_add(e_col(L_LK + 2, 0), ec(beta)), e_add(e_col(L_LK + 3, 0), ec(gamma)));
+            ExprP num = e_mul(e_add(e_col(L_LK + 0, 0), ec(beta)), e_add(e_col(L_LK + 1, 0), ec(gamma)));
+            SB_TRY(ratio_scan(den, num, d_zall + (size_t)(n_sets + (int)li) * n * 32));
+        }
+        // boundary values of the un-chained permutation products, one read-back
+        std::vector<Fr> local_last(n_sets);
+        for (int s = 0; s + 1 < n_sets; s++)
+            SB_CUDA_TRY(cudaMemcpyAsync(&local_last[s], d_zall + ((size_t)s * n + (n - (size_t)bf - 1)) * 32, 32, cudaMemcpyDeviceToHost, st));
+        if (n_sets > 1) SB_CUDA_TRY(cudaStreamSynchronize(st));
+        Fr carry = hfr::ONE;
+        for (int s = 1; s < n_sets; s++) {
+            carry = hfr::mul(carry, local_last[s - 1]);
+            SB_TRY(fr_scale(ctx, d_zall + (size_t)s * n * 32, n, to_dev(carry), st));
+        }
+        // blinding rows and blinds in halo2's draw order: every permutation set, then every lookup product
+        for (int z = 0; z < n_z; z++) {
             std::vector<Fr> blind(bf);
             for (Fr &x : blind) x = rng.next_fr();
-            SB_TRY(upload_frs((uint8_t *)d_z + (n - bf) * 32, blind, st));
-            Fr lz;
-            SB_CUDA_TRY(cudaMemcpyAsync(&lz, (uint8_t *)d_z + (n - (size_t)bf - 1) * 32, 32, cudaMemcpyDeviceToHost, st));
-            SB_CUDA_TRY(cudaStreamSynchronize(st));
-            last_z = lz;
+            SB_TRY(upload_frs(d_zall + ((size_t)z * n + (n - bf)) * 32, blind, st));
             (void)rng.next_fr();
-            SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_z, n, pt, st));
-            SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
+        }
+        std::vector<uint8_t> pts((size_t)n_z * 64);
+        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, d_zall, n, (uint32_t)n_z, pts.data(), st));
+        for (int s = 0; s < n_sets; s++) {
+            PermSet &S = psets[s];
+            SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st));
             SB_TRY(dom_l2c(ctx, d, S.z_poly, st));
             if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st));
-            if (!tr.write_point(pt)) { set_last_error("permutation product commitment is the identity"); return SB_ERR_ARG; }
+            if (!tr.write_point(pts.data() + (size_t)s * 64)) { set_last_error("permutation product commitment is the identity"); return SB_ERR_ARG; }
         }
-    }
-
-    mark();  // [2] permutation products: denominators, batch inversion, scan, commitments, iNTT + coset NTT
-    // ---- lookup products
-    for (size_t li = 0; li < lks.size(); li++) {
-        LookupState &L = lks[li];
-        void *d_den, *d_num, *d_z;
-        SB_TRY(scratch_get(ctx, "pf_perm_den", n * 32, &d_den));
-        SB_TRY(scratch_get(ctx, "pf_perm_num", n * 32, &d_num));
-        SB_TRY(scratch_get(ctx, "pf_perm_z", n * 32, &d_z));
-        lcols[L_LK + 0] = L.c_in; lcols[L_LK + 1] = L.c_tab; lcols[L_LK + 2] = L.p_in; lcols[L_LK + 3] = L.p_tab;
-        ExprP den = e_mul(e_add(e_col(L_LK + 2, 0), ec(beta)), e_add(e_col(L_LK + 3, 0), ec(gamma)));
-        ExprP num = e_mul(e_add(e_col(L_LK + 0, 0), ec(beta)), e_add(e_col(L_LK + 1, 0), ec(gamma)));
-        SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den, st));
-        SB_TRY(expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num, st));
-        SB_TRY(fr_batch_invert(ctx, d_den, n, st));
-        SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, n, st));
-        SB_TRY(fr_running_product(ctx, d_den, n, fr_t::one(), d_z, n, st));
-        std::vector<Fr> blind(bf);
-        for (Fr &x : blind) x = rng.next_fr();
-        SB_TRY(upload_frs((uint8_t *)d_z + (n - bf) * 32, blind, st));
-        (void)rng.next_fr();
-        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_z, n, pt, st));
-        SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_z, n * 32, cudaMemcpyDeviceToDevice, st));
-        SB_TRY(dom_l2c(ctx, d, L.z_poly, st));
-        if (!tr.write_point(pt)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
+        mark();  // [2] permutation + lookup products: ratios, batch inversion, scans, ONE batched commitment, permutation iNTT + coset NTT
+        for (size_t li = 0; li < lks.size(); li++) {
+            LookupState &L = lks[li];
+            SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st));
+            SB_TRY(dom_l2c(ctx, d, L.z_poly, st));
+            if (!tr.write_point(pts.data() + (size_t)(n_sets + (int)li) * 64)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
+        }
     }
 
     mark();  // [3] lookup product

@@ -16,6 +16,22 @@ void set_last_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int32_t h2d_staged(sb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return SB_OK;
+    if (bytes > sb_ctx::STAGE_SLOT_BYTES || !ctx->stage) {
+        SB_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        return SB_OK;
+    }
+    const uint32_t slot = ctx->stage_next++ % sb_ctx::STAGE_SLOTS;
+    SB_CUDA_TRY(cudaEventSynchronize(ctx->stage_ev[slot]));  // the copy that last used this slot (a never-recorded event is complete)
+    uint8_t *h = ctx->stage + (size_t)slot * sb_ctx::STAGE_SLOT_BYTES;
+    memcpy(h, h_src, bytes);
+    SB_CUDA_TRY(cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[slot], st));
+    return SB_OK;
+}
+
 int32_t scratch_get(sb_ctx *ctx, const char *slot, size_t bytes, void **out) {
     Scratch &s = ctx->scratch[slot];
     if (s.bytes < bytes) {
@@ -142,6 +158,8 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx) {
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->pinned_bytes = 1 << 16;
     SB_CUDA_TRY(cudaHostAlloc(&c->pinned, c->pinned_bytes, cudaHostAllocDefault));
+    SB_CUDA_TRY(cudaHostAlloc((void **)&c->stage, sb_ctx::STAGE_SLOTS * sb_ctx::STAGE_SLOT_BYTES, cudaHostAllocDefault));
+    for (int i = 0; i < sb_ctx::STAGE_SLOTS; i++) SB_CUDA_TRY(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
     *out_ctx = c;
     return SB_OK;
 }
@@ -155,6 +173,9 @@ int32_t sb_ctx_destroy(sb_ctx *ctx) {
         for (auto &kv : ctx->scratch)
             if (kv.second.ptr) cudaFree(kv.second.ptr);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        for (int i = 0; i < sb_ctx::STAGE_SLOTS; i++)
+            if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
         for (int e = 0; e < 5; e++)
             if (ctx->msm_ev[e]) cudaEventDestroy(ctx->msm_ev[e]);
         cudaStreamDestroy(ctx->stream);

@@ -61,6 +61,13 @@ struct sb_ctx {
     std::map<std::string, sb::NttPlan *> ntt_plans;  // key: log_n || omega bytes
     void *pinned = nullptr;                          // small pinned staging buffer (results)
     size_t pinned_bytes = 0;
+    // pinned upload ring: small host -> device copies (blinding rows, compiled programs) go through it so the caller's pageable
+    // buffer may die at once and no stream synchronisation is needed; a slot is reused only after its copy's event has fired
+    static const int STAGE_SLOTS = 16;
+    static const size_t STAGE_SLOT_BYTES = 64 << 10;
+    uint8_t *stage = nullptr;
+    cudaEvent_t stage_ev[STAGE_SLOTS] = {};
+    uint32_t stage_next = 0;
     // per-phase device times of the last MSM (CUDA events on the launching stream):
     // [0] recode+sort  [1] reduce level 1 (the dominant kernel)  [2] reduce levels >= 2
     // [3] bucket reduction  [4] whole device part
@@ -76,6 +83,9 @@ struct sb_ctx {
 namespace sb {
 
 int32_t scratch_get(sb_ctx *ctx, const char *slot, size_t bytes, void **out);
+
+// asynchronous upload of a small host buffer through the context's pinned ring (falls back to a synchronous copy when it does not fit)
+int32_t h2d_staged(sb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);
 
 inline cudaStream_t pick_stream(sb_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 

@@ -404,8 +404,7 @@ int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void
     SB_REQUIRE(total <= slice_bytes, "expr_eval: program too large");
     SB_TRY(scratch_get(ctx, "expr_prog", 8 * slice_bytes, (void **)&d_prog));
     d_prog += (size_t)slice * slice_bytes;
-    SB_CUDA_TRY(cudaMemcpyAsync(d_prog, host.data(), total, cudaMemcpyHostToDevice, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));  // `host` is pageable and dies at return
+    SB_TRY(h2d_staged(ctx, d_prog, host.data(), total, st));  // pinned ring: no stream synchronisation, `host` may die at return
     ExprArgs A;
     A.code = (const uint32_t *)d_prog;
     A.n_instr = (uint32_t)(prog.code.size() / 3);

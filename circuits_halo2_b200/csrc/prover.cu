@@ -403,11 +403,9 @@ int32_t poly_div_by_roots(sb_ctx *ctx, const sb_pk *pk, void *d_p, const std::ve
     return poly_div_by_roots_k(ctx, pk->k, pk->dom->omega, pk->dom->omega_inv, pk->div_g_pows, pk->div_x, pk->div_ginv_scaled, d_p, roots, st);
 }
 
-int32_t upload_frs(void *d_dst, const std::vector<Fr> &v, cudaStream_t st) {
+int32_t upload_frs(sb_ctx *ctx, void *d_dst, const std::vector<Fr> &v, cudaStream_t st) {
     if (v.empty()) return SB_OK;
-    SB_CUDA_TRY(cudaMemcpyAsync(d_dst, v.data(), v.size() * 32, cudaMemcpyHostToDevice, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
-    return SB_OK;
+    return h2d_staged(ctx, d_dst, v.data(), v.size() * 32, st);
 }
 
 int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st);
@@ -744,7 +742,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     for (int c = 0; c < A; c++) {
         std::vector<Fr> blind(n - usable);
         for (Fr &b : blind) b = rng.next_fr();
-        SB_TRY(upload_frs((uint8_t *)adv[c] + usable * 32, blind, st));
+        SB_TRY(upload_frs(ctx, (uint8_t *)adv[c] + usable * 32, blind, st));
     }
     for (int c = 0; c < A; c++) (void)rng.next_fr();
     for (int c = 0; c < A; c++) {
@@ -791,9 +789,9 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         if (rc != SB_OK) return rc;
         std::vector<Fr> blind(n - usable);
         for (Fr &x : blind) x = rng.next_fr();
-        SB_TRY(upload_frs((uint8_t *)L.p_in + usable * 32, blind, st));
+        SB_TRY(upload_frs(ctx, (uint8_t *)L.p_in + usable * 32, blind, st));
         for (Fr &x : blind) x = rng.next_fr();
-        SB_TRY(upload_frs((uint8_t *)L.p_tab + usable * 32, blind, st));
+        SB_TRY(upload_frs(ctx, (uint8_t *)L.p_tab + usable * 32, blind, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.in_poly, L.p_in, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.in_poly, st));
         (void)rng.next_fr();
@@ -872,7 +870,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         for (int z = 0; z < n_z; z++) {
             std::vector<Fr> blind(bf);
             for (Fr &x : blind) x = rng.next_fr();
-            SB_TRY(upload_frs(d_zall + ((size_t)z * n + (n - bf)) * 32, blind, st));
+            SB_TRY(upload_frs(ctx, d_zall + ((size_t)z * n + (n - bf)) * 32, blind, st));
             (void)rng.next_fr();
         }
         std::vector<uint8_t> pts((size_t)n_z * 64);

@@ -567,6 +567,13 @@ int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars
     SB_REQUIRE(tabs && tabs->d_tables && n <= tabs->stride, "msm_run_tables: more scalars than table columns");
     return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st);
 }
+// windows [w_lo, w_hi) of `batch` scalar vectors in one launch set: out = batch XYZZ partials (128 B each) that carry their 2^(c w) factors
+int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, int32_t w_lo, int32_t w_hi, uint8_t *out,
+                                     cudaStream_t st) {
+    SB_REQUIRE(tabs && tabs->d_tables && n <= tabs->stride && batch >= 1 && w_lo < w_hi, "msm_run_tables_batch_windows: bad arguments");
+    SB_REQUIRE((uint64_t)(w_hi - w_lo) * n * batch < (1ull << 32) - 8, "msm_run_tables_batch_windows: batch too large");
+    return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st, batch);
+}
 
 int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st) {
     SB_REQUIRE(c >= 11 && c <= 24, "msm tables: window bits must be 11..24");
@@ -603,11 +610,11 @@ int32_t msm_run_tables_batch(sb_ctx *ctx, const MsmTables *tabs, const void *d_s
 static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out_affine,
                             cudaStream_t st, uint32_t batch) {
     if (n == 0) {
-        memset(out_affine, 0, w_hi < 0 ? (size_t)64 * batch : (size_t)(tabs ? 1 : (w_hi - w_lo)) * 128);
+        memset(out_affine, 0, w_hi < 0 ? (size_t)64 * batch : (size_t)(tabs ? batch : (uint32_t)(w_hi - w_lo)) * 128);
         return SB_OK;
     }
     SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
-    SB_REQUIRE(batch == 1 || (tabs && w_hi < 0), "msm: batches need table bases and the full window range");
+    SB_REQUIRE(batch == 1 || tabs, "msm: batches need table bases");
     const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs, batch);
     SB_REQUIRE(w_hi < 0 || (uint32_t)w_hi <= sh.W_all, "msm: window range exceeds the scalar");
     SB_REQUIRE(sh.t_max < (1ull << 32), "msm: window count * n must be < 2^32");

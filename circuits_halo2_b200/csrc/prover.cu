@@ -662,6 +662,20 @@ int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basi
 // m commitments over contiguous scalar vectors: one batched launch set on a single GPU, the sharded path one by one
 int32_t msm_commit_batch(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint32_t m, uint8_t *out, cudaStream_t st) {
     if (!comm || comm->world <= 1) return srs_msm_batch(ctx, srs, basis, d_scalars, n, m, out, st);
+    const MsmTables *tabs = srs->tab[basis].d_tables ? &srs->tab[basis] : nullptr;
+    const uint32_t Wd = (uint32_t)comm->world, r = (uint32_t)comm->rank;
+    if (tabs && tabs->W >= Wd && (uint64_t)tabs->W * n * m < (1ull << 32) - 8 && getenv("SB_SHARD_MSM_BY_RANGE") == nullptr) {
+        // all m commitments, this rank's windows, ONE launch set and ONE exchange of m XYZZ partials per rank
+        const uint32_t lo = r * tabs->W / Wd, hi = (r + 1) * tabs->W / Wd;
+        std::vector<uint8_t> mine((size_t)m * 128), all((size_t)Wd * m * 128), col((size_t)Wd * 128);
+        SB_TRY(msm_run_tables_batch_windows(ctx, tabs, d_scalars, n, m, (int32_t)lo, (int32_t)hi, mine.data(), st));
+        if (comm->allgather_host(comm->user, mine.data(), all.data(), (size_t)m * 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+        for (uint32_t j = 0; j < m; j++) {
+            for (uint32_t q = 0; q < Wd; q++) memcpy(col.data() + (size_t)q * 128, all.data() + ((size_t)q * m + j) * 128, 128);
+            msm_fold_windows(col.data(), Wd, 0, out + (size_t)j * 64);
+        }
+        return SB_OK;
+    }
     for (uint32_t j = 0; j < m; j++) SB_TRY(msm_commit(ctx, comm, srs, basis, (const uint8_t *)d_scalars + (size_t)j * n * 32, n, out + (size_t)j * 64, st));
     return SB_OK;
 }
@@ -736,7 +750,16 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             adv_poly[c] = base_p + (size_t)c * n * 32;
             adv_coset[c] = base_c + (size_t)c * en * 32;
         }
-        SB_CUDA_TRY(cudaMemcpyAsync(base_v, advice_host, (size_t)A * n * 32, cudaMemcpyHostToDevice, st));
+        const size_t adv_bytes = (size_t)A * n * 32;
+        if (comm && comm->world > 1 && adv_bytes % ((size_t)comm->world * 256) == 0) {
+            // every rank holds the same host witness: upload 1 / world of it over PCIe and gather the rest over NVLink
+            const size_t per = adv_bytes / (size_t)comm->world, off = per * (size_t)comm->rank;
+            SB_CUDA_TRY(cudaMemcpyAsync(base_v + off, advice_host + off, per, cudaMemcpyHostToDevice, st));
+            SB_CUDA_TRY(cudaStreamSynchronize(st));
+            if (comm->allgather_dev(comm->user, base_v, per, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
+        } else {
+            SB_CUDA_TRY(cudaMemcpyAsync(base_v, advice_host, adv_bytes, cudaMemcpyHostToDevice, st));
+        }
     }
     // blinding rows, blinds (drawn; KZG ignores them), commitments
     for (int c = 0; c < A; c++) {

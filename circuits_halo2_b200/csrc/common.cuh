@@ -120,6 +120,8 @@ int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars,
 void msm_fold_windows(const uint8_t *win, uint32_t W, uint32_t c, uint8_t out_affine[64]);
 
 int32_t fr_gen_powers(sb_ctx *ctx, void *d_out, const fr_t &base, size_t count, cudaStream_t st);
+// group-element inverse FFT (ParamsKZG::downsize / g_to_lagrange)
+int32_t g1_to_lagrange(sb_ctx *ctx, const void *d_g, uint32_t log_n, const fr_t &omega_inv, const fr_t &n_inv, void *d_lagrange_out, cudaStream_t st);
 int32_t g1_fixed_base_mul(sb_ctx *ctx, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 
 int32_t fr_scale(sb_ctx *ctx, void *d_a, size_t n, const fr_t &s, cudaStream_t st);

@@ -1382,6 +1382,43 @@ int32_t sb_srs_setup_unsafe(sb_ctx *ctx, uint32_t k, const uint8_t tau_mont[32],
     *out_srs = srs;
     return SB_OK;
 }
+int32_t sb_srs_downsize(sb_ctx *ctx, const sb_srs *srs, uint32_t new_k, sb_srs **out_srs) {
+    if (!ctx || !srs || !out_srs) return SB_ERR_ARG;
+    SB_REQUIRE(new_k <= srs->k, "sb_srs_downsize: the new k must not exceed the SRS's k (halo2 asserts k <= self.k)");
+    CtxGuard g(ctx);
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)1 << new_k;
+    sb_domain *dom = nullptr;
+    SB_TRY(sb_domain_create(ctx, 2, new_k, &dom));
+    sb_srs *out = new sb_srs();
+    out->k = new_k;
+    if (cudaMalloc(&out->d_g, n * 64) != cudaSuccess || cudaMalloc(&out->d_g_lagrange, n * 64) != cudaSuccess) {
+        set_last_error("sb_srs_downsize: cudaMalloc(2 x %zu) failed", n * 64);
+        if (out->d_g) cudaFree(out->d_g);
+        delete out;
+        sb_domain_destroy(dom);
+        return SB_ERR_ALLOC;
+    }
+    int32_t rc = SB_OK;
+    if (cudaMemcpyAsync(out->d_g, srs->d_g, n * 64, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = SB_ERR_CUDA;
+    if (rc == SB_OK) {
+        if (new_k == srs->k) {
+            if (cudaMemcpyAsync(out->d_g_lagrange, srs->d_g_lagrange, n * 64, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = SB_ERR_CUDA;
+        } else {
+            rc = g1_to_lagrange(ctx, out->d_g, new_k, dom->omega_inv, dom->ifft_divisor, out->d_g_lagrange, st);
+        }
+    }
+    if (rc == SB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = SB_ERR_CUDA;
+    sb_domain_destroy(dom);
+    if (rc != SB_OK) {
+        cudaFree(out->d_g);
+        cudaFree(out->d_g_lagrange);
+        delete out;
+        return rc;
+    }
+    *out_srs = out;
+    return SB_OK;
+}
 int32_t sb_srs_download(sb_ctx *ctx, const sb_srs *srs, uint8_t *g_out, uint8_t *g_lagrange_out) {
     if (!ctx || !srs || !g_out || !g_lagrange_out) return SB_ERR_ARG;
     CtxGuard g(ctx);

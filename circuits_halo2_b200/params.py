@@ -73,6 +73,21 @@ class ParamsKZG:
     def k(self) -> int:
         return self._k
 
+    def downsize(self, new_k: int, download: bool = True) -> "ParamsKZG":
+        """`ParamsKZG::downsize` (utils.rs:62-66); returns the smaller params (halo2 mutates in place), Lagrange bases by a group-element iFFT on the GPU."""
+        if new_k > self._k:
+            raise AssertionError("downsize: k must not exceed the current k")
+        out = ParamsKZG.__new__(ParamsKZG)
+        out.ctx, out._k, out.n, out.tail = self.ctx, new_k, 1 << new_k, self.tail
+        out._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sb_srs_downsize(self.ctx.handle, self._h, ctypes.c_uint32(new_k), ctypes.byref(out._h)), "sb_srs_downsize")
+        out.g = out.g_lagrange = None
+        if download:
+            out.g = np.zeros((out.n, 8), dtype=np.uint64)
+            out.g_lagrange = np.zeros((out.n, 8), dtype=np.uint64)
+            _lib.check(_lib.lib().sb_srs_download(self.ctx.handle, out._h, ptr(out.g), ptr(out.g_lagrange)), "sb_srs_download")
+        return out
+
     def precompute(self, bases: int = 3, window_bits: int = 0) -> "ParamsKZG":
         """Fixed-base window tables for `commit` (bit 0) / `commit_lagrange` (bit 1): 2^(c w) * P_i for every window w, so all
         windows share one bucket set and c can be 20-22 bits.  Same results, ceil(255 / c) x the base memory.  `ProvingKey`

@@ -74,6 +74,9 @@ int32_t sb_srs_upload(sb_ctx *ctx, uint32_t k, const uint8_t *g, const uint8_t *
  * generated entirely on the device (powers of tau, Lagrange weights, 2 x 2^k fixed-base products) */
 int32_t sb_srs_setup_unsafe(sb_ctx *ctx, uint32_t k, const uint8_t tau[32], sb_srs **out_srs);
 int32_t sb_srs_download(sb_ctx *ctx, const sb_srs *srs, uint8_t *g_out, uint8_t *g_lagrange_out);
+/* `ParamsKZG::downsize(new_k)` (utils.rs:62-66): the first 2^new_k monomial bases and their Lagrange bases, recomputed on the device by an
+ * inverse FFT over group elements (halo2 `g_to_lagrange`).  Returns a new handle; new_k <= k. */
+int32_t sb_srs_downsize(sb_ctx *ctx, const sb_srs *srs, uint32_t new_k, sb_srs **out_srs);
 /* same handle over bases that already live on the device (borrowed: the caller keeps ownership) */
 int32_t sb_srs_wrap_dev(sb_ctx *ctx, uint32_t k, const void *d_g, const void *d_g_lagrange, sb_srs **out_srs);
 int32_t sb_srs_destroy(sb_srs *srs);

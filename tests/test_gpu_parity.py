@@ -273,3 +273,28 @@ def test_fixed_base_tables_large(ctx):
     for kind in ["U", "C", "Z"]:
         sc = scalar_distribution(kind, 1 << k, 7200)
         assert (params.commit(sc) == res[kind][0]).all() and (params.commit_lagrange(sc) == res[kind][1]).all(), kind
+
+
+def test_params_downsize_matches_g_to_lagrange(ctx, golden_dir):
+    """ParamsKZG::downsize on the reference's own SRS (hermez-raw-11): the first 2^k monomial bases are kept and the Lagrange bases
+    equal the definition g_lagrange[i] = MSM(coefficients of L_i, g) computed by the oracle (k = 4), and commit_lagrange(v) ==
+    commit(lagrange_to_coeff(v)) for the downsized params (k = 4, 7, 10); downsize(11) is the identity."""
+    import circuits_halo2_b200 as sb
+    params = sb.ParamsKZG.read(os.path.join(golden_dir, "hermez-raw-11"), ctx)
+    same = params.downsize(11)
+    assert (same.g == params.g).all() and (same.g_lagrange == params.g_lagrange).all()
+    for k in (4, 7, 10):
+        small = params.downsize(k)
+        n = 1 << k
+        assert (small.g == params.g[:n]).all()
+        dom = sb.EvaluationDomain(6, k, ctx)
+        v = cpu.random_fr(n, 600 + k)
+        assert (small.commit_lagrange(v) == small.commit(dom.lagrange_to_coeff(v))).all(), k
+        if k == 4:
+            for i in (0, 1, 5, 15):
+                e = np.zeros((n, 4), dtype=np.uint64)
+                e[i] = fr_bytes(1)
+                li = dom.lagrange_to_coeff(e)  # coefficients of the i-th Lagrange polynomial
+                assert (small.g_lagrange[i] == cpu.best_multiexp(np.ascontiguousarray(li.reshape(n, 4)), np.ascontiguousarray(params.g[:n]), threads=2)).all(), i
+    with pytest.raises(AssertionError):
+        params.downsize(12)

@@ -149,25 +149,7 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
         }
         std::sort(reach[ti].begin(), reach[ti].end());
     }
-    std::vector<char> emitted(nd.size(), 0), used(T, 0);
-    // next term: the one that consumes the most value already sitting in slots (a product ~ 8 additions), i.e. lets shared values
-    // die soonest; nothing live to consume -> the first unscheduled term in source order.  Plain sums keep source order.
-    auto pick_next = [&]() -> size_t {
-        size_t best = T;
-        int best_w = 0;
-        for (size_t c = 0; c < T; c++) {
-            if (used[c]) continue;
-            if (!fold) return c;
-            int w = 0;
-            for (int id : reach[c])
-                if (emitted[id] && nd[id].uses > 0) w += nd[id].op == OP_MUL ? 8 : 1;
-            if (w > best_w) { best_w = w; best = c; }
-        }
-        if (best == T)
-            for (size_t c = 0; c < T && best == T; c++)
-                if (!used[c]) best = c;
-        return best;
-    };
+    std::vector<char> emitted(nd.size(), 0);
     auto alloc = [&]() -> uint32_t {
         for (uint32_t s = 1; s < slot_busy.size(); s++)
             if (!slot_busy[s]) { slot_busy[s] = true; return s; }
@@ -190,25 +172,84 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
         }
     }
     (void)fold_const;
+
+    // ---- scheduling units.  Terms of the shape f * body_i that share the factor f (the gates behind one selector, or behind one
+    //      selector polynomial q(1-q)(2-q)...) are accumulated as f * sum_i y^(e_i) body_i: |G| + 1 products instead of 2 |G|.
+    struct Unit { int factor; std::vector<size_t> terms; };
+    std::vector<Unit> units;
+    {
+        std::map<int, int> root_count, child_freq;
+        for (size_t ti = 0; ti < T; ti++) root_count[roots[ti]]++;
+        auto groupable = [&](size_t ti) {
+            const Node &r = nd[roots[ti]];
+            return fold && r.op == OP_MUL && r.uses == 1 && root_count[roots[ti]] == 1 && r.a != r.b;
+        };
+        for (size_t ti = 0; ti < T; ti++)
+            if (groupable(ti)) { child_freq[nd[roots[ti]].a]++; child_freq[nd[roots[ti]].b]++; }
+        std::map<int, size_t> unit_of_factor;
+        for (size_t ti = 0; ti < T; ti++) {
+            int f = -1;
+            if (groupable(ti)) {
+                const int a2 = nd[roots[ti]].a, b2 = nd[roots[ti]].b;
+                const int fa = child_freq[a2], fb = child_freq[b2];
+                if (std::max(fa, fb) >= 2) f = fa >= fb ? a2 : b2;
+            }
+            if (f < 0) { units.push_back({-1, {ti}}); continue; }
+            auto it = unit_of_factor.find(f);
+            if (it == unit_of_factor.end()) { unit_of_factor[f] = units.size(); units.push_back({f, {ti}}); }
+            else units[it->second].terms.push_back(ti);
+        }
+        for (Unit &u : units) {
+            if (u.factor >= 0 && u.terms.size() == 1) u.factor = -1;  // the other sharers chose a different factor
+            if (u.factor >= 0 && nd[u.factor].op >= 0) nd[u.factor].uses -= (int)u.terms.size() - 1;  // one use by the grouped product
+        }
+    }
+    std::vector<char> unit_used(units.size(), 0);
+    // next unit: the one that consumes the most value already sitting in slots (a product ~ 8 additions), i.e. lets shared values
+    // die soonest; nothing live to consume -> the first unscheduled unit in source order.  Plain sums keep source order.
+    auto pick_next = [&]() -> size_t {
+        size_t best = units.size();
+        int best_w = 0;
+        for (size_t c = 0; c < units.size(); c++) {
+            if (unit_used[c]) continue;
+            if (!fold) return c;
+            int w = 0;
+            for (size_t ti : units[c].terms)
+                for (int id : reach[ti])
+                    if (emitted[id] && nd[id].uses > 0) w += nd[id].op == OP_MUL ? 8 : 1;
+            if (w > best_w) { best_w = w; best = c; }
+        }
+        if (best == units.size())
+            for (size_t c = 0; c < units.size() && best == units.size(); c++)
+                if (!unit_used[c]) best = c;
+        return best;
+    };
+
     // Product-free sub-expressions (negated cells, selector complements, sums of cells) are identified globally like everything
-    // else, but their VALUES are not kept across terms: a term that needs one recomputes it (one addition is cheaper than a value
-    // slot held for a long time; slots are shared memory and bound occupancy).  term_uses counts, per term, the edges from the
-    // nodes emitted in that term into each cheap node.
+    // else, but their VALUES are not kept across evaluations: an evaluation that needs one recomputes it (one addition is cheaper than
+    // a value slot held for a long time; slots are shared memory and bound occupancy).  term_uses counts, per evaluation, the edges
+    // from the nodes emitted in it into each cheap node (+ 1 for the caller's use of a cheap root).
     std::vector<int> cheap_stamp(nd.size(), -1), touch_stamp(nd.size(), -1), term_uses(nd.size(), 0);
-    bool acc_live = false;
-    for (size_t oi = 0; oi < T; oi++) {
-        const size_t ti = pick_next();
-        used[ti] = 1;
-        const int stamp = (int)oi;
-        auto is_cheap = [&](int id) { return nd[id].op >= 0 && nd[id].nmul == 0; };
-        {   // dry walk: uses of cheap nodes inside this term
-            std::vector<int> stack{roots[ti]};
-            std::vector<char> seen_exp;
+    int stamp = 0;
+    auto is_cheap = [&](int id) { return nd[id].op >= 0 && nd[id].nmul == 0; };
+    auto release2 = [&](int id) {
+        if (nd[id].op < 0) return;
+        if (is_cheap(id)) {
+            if (--term_uses[id] == 0) slot_busy[nd[id].slot] = false;
+        } else {
+            release(id);
+        }
+    };
+    // make opnd(root) valid; the caller owes exactly one release2(root)
+    auto eval = [&](int root) {
+        stamp++;
+        {   // dry walk: uses of cheap nodes inside this evaluation
+            std::vector<int> stack{root};
             auto touch = [&](int id) {
                 if (touch_stamp[id] != stamp) { touch_stamp[id] = stamp; term_uses[id] = 0; }
                 term_uses[id]++;
             };
-            if (is_cheap(roots[ti])) touch(roots[ti]);  // the fold
+            if (is_cheap(root)) touch(root);  // the caller's use
             std::vector<int> visited_exp;
             while (!stack.empty()) {
                 const int id = stack.back();
@@ -216,7 +257,7 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
                 Node &n = nd[id];
                 if (n.op < 0) continue;
                 if (is_cheap(id)) {
-                    if (cheap_stamp[id] == stamp) continue;  // already expanded in this term
+                    if (cheap_stamp[id] == stamp) continue;  // already expanded in this evaluation
                     cheap_stamp[id] = stamp;
                 } else {
                     if (emitted[id]) continue;
@@ -232,24 +273,15 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
             }
             for (int id : visited_exp) nd[id].slot = -1;
             for (size_t q = 0; q < nd.size(); q++)
-                if (cheap_stamp[q] == stamp) cheap_stamp[q] = -1 - stamp;  // mark "to be emitted in this term", not yet emitted
+                if (cheap_stamp[q] == stamp) cheap_stamp[q] = -1 - stamp;  // "to be emitted in this evaluation", not yet emitted
         }
-        auto cheap_ready = [&](int id) { return cheap_stamp[id] == stamp; };
-        auto release2 = [&](int id) {
-            if (nd[id].op < 0) return;
-            if (is_cheap(id)) {
-                if (--term_uses[id] == 0) slot_busy[nd[id].slot] = false;
-            } else {
-                release(id);
-            }
-        };
         // post-order walk from the root, skipping what is already available
-        std::vector<std::pair<int, int>> stack{{roots[ti], 0}};
+        std::vector<std::pair<int, int>> stack{{root, 0}};
         while (!stack.empty()) {
             auto &top = stack.back();
             const int id = top.first;
             Node &n = nd[id];
-            if (n.op < 0 || (is_cheap(id) ? cheap_ready(id) : (bool)emitted[id])) { stack.pop_back(); continue; }
+            if (n.op < 0 || (is_cheap(id) ? cheap_stamp[id] == stamp : (bool)emitted[id])) { stack.pop_back(); continue; }
             if (top.second == 0) { top.second = 1; stack.push_back({n.a, 0}); continue; }
             if (top.second == 1) { top.second = 2; if (n.b >= 0) { stack.push_back({n.b, 0}); continue; } }
             const uint32_t a = opnd(n.a), b = n.b >= 0 ? opnd(n.b) : 0;
@@ -262,28 +294,71 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
             else emitted[id] = 1;
             stack.pop_back();
         }
-        const int root = roots[ti];
-        const uint32_t t_op = opnd(root);
-        if (getenv("SB_EXPR_DEBUG")) {
-            int busy = 0;
-            for (bool bsy : slot_busy) busy += bsy;
-            fprintf(stderr, "[expr] term %zu scheduled at %zu: %zu instr so far, %d busy slots, %zu slots allocated\n", ti, oi, p.code.size() / 3, busy, slot_busy.size());
-        }
-        const bool scaled = fold && ti != T - 1;  // the last term carries y^0
+    };
+    bool acc_live = false;
+    // acc (+)= value * y^(T-1-ti); value is an operand the caller has already released (it may die into the destination)
+    auto accumulate = [&](uint32_t v_op, bool scaled, uint32_t pconst) {
         if (!acc_live) {
-            if (scaled) emit(OP_MUL, ACC, t_op, operand(K_CONST, pow_const[ti]));
-            else emit(OP_COPY, ACC, t_op, 0);
-            release2(root);
+            if (scaled) emit(OP_MUL, ACC, v_op, operand(K_CONST, pconst));
+            else emit(OP_COPY, ACC, v_op, 0);
             acc_live = true;
         } else if (scaled) {
-            release2(root);
             const uint32_t tmp = alloc();
-            emit(OP_MUL, tmp, t_op, operand(K_CONST, pow_const[ti]));
+            emit(OP_MUL, tmp, v_op, operand(K_CONST, pconst));
             emit(OP_ADD, ACC, operand(K_REG, ACC), operand(K_REG, tmp));
             slot_busy[tmp] = false;
         } else {
-            emit(OP_ADD, ACC, operand(K_REG, ACC), t_op);
+            emit(OP_ADD, ACC, operand(K_REG, ACC), v_op);
+        }
+    };
+    for (size_t oi = 0; oi < units.size(); oi++) {
+        const size_t ui = pick_next();
+        unit_used[ui] = 1;
+        const Unit &u = units[ui];
+        if (u.factor < 0) {
+            const size_t ti = u.terms[0];
+            const int root = roots[ti];
+            eval(root);
+            const uint32_t t_op = opnd(root);
             release2(root);
+            accumulate(t_op, fold && ti != T - 1, pow_const[ti]);  // the last term carries y^0
+        } else {
+            // gacc = sum_i y^(e_i) body_i, then acc += factor * gacc.  The roots factor * body_i themselves are never emitted.
+            uint32_t gacc = 0;
+            bool g_live = false;
+            for (size_t ti : u.terms) {
+                const Node &r = nd[roots[ti]];
+                const int body = r.a == u.factor ? r.b : r.a;
+                eval(body);
+                const uint32_t b_op = opnd(body);
+                release2(body);
+                const bool scaled = ti != T - 1;
+                if (!g_live) {
+                    gacc = alloc();
+                    if (scaled) emit(OP_MUL, gacc, b_op, operand(K_CONST, pow_const[ti]));
+                    else emit(OP_COPY, gacc, b_op, 0);
+                    g_live = true;
+                } else if (scaled) {
+                    const uint32_t tmp = alloc();
+                    emit(OP_MUL, tmp, b_op, operand(K_CONST, pow_const[ti]));
+                    emit(OP_ADD, gacc, operand(K_REG, gacc), operand(K_REG, tmp));
+                    slot_busy[tmp] = false;
+                } else {
+                    emit(OP_ADD, gacc, operand(K_REG, gacc), b_op);
+                }
+            }
+            eval(u.factor);
+            const uint32_t f_op = opnd(u.factor);
+            release2(u.factor);
+            emit(OP_MUL, gacc, operand(K_REG, gacc), f_op);
+            slot_busy[gacc] = false;
+            accumulate(operand(K_REG, gacc), false, 0);
+        }
+        if (getenv("SB_EXPR_DEBUG")) {
+            int busy = 0;
+            for (bool bsy : slot_busy) busy += bsy;
+            fprintf(stderr, "[expr] unit %zu (factor %d, %zu terms) scheduled at %zu: %zu instr so far, %d busy slots, %zu slots allocated\n", ui, u.factor, u.terms.size(), oi,
+                    p.code.size() / 3, busy, slot_busy.size());
         }
     }
     p.n_slots = (uint32_t)slot_busy.size();
@@ -417,11 +492,8 @@ int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void
     A.out = (uint4 *)d_out;
     A.out_slot = (prog.n_slots << 16) | prog.out_slot;
     const size_t smem = (size_t)prog.n_slots * EXPR_THREADS * 32;
-    static bool attr = false;
-    if (!attr) {
-        SB_CUDA_TRY(cudaFuncSetAttribute(expr_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EXPR_THREADS * 32));
-        attr = true;
-    }
+    // per device and idempotent: safe to repeat from concurrent contexts
+    SB_CUDA_TRY(cudaFuncSetAttribute(expr_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EXPR_THREADS * 32));
     SB_LAUNCH(ctx, expr_eval_kernel, (unsigned)(n / EXPR_THREADS), EXPR_THREADS, smem, st, A);
     return SB_OK;
 }

@@ -563,10 +563,6 @@ std::vector<ExprP> h_terms(const ConstraintSystem &cs, int P, const std::vector<
     const int E_SIGMA = lay.E_SIGMA, E_PZ = lay.E_PZ, E_L0 = lay.E_L0, E_LLAST = lay.E_LLAST, E_LACT = lay.E_LACT, E_X = lay.E_X, E_LK = lay.E_LK;
     ColMap em;
     em.advice0 = 0; em.fixed0 = cs.A; em.instance0 = cs.A + cs.F;
-    struct { int first, count; } psets_[64];
-    for (int i = 0; i < n_sets && i < 64; i++) { psets_[i].first = sets[i].first; psets_[i].count = sets[i].second; }
-    auto &psets = psets_;
-    struct { size_t n; size_t size() const { return n; } } lks{n_lookups};
     std::vector<ExprP> terms;
     for (auto &g : cs.gates) terms.push_back(bind_expr(*g, em));
     const ExprP one = e_const(fr_t::one());
@@ -580,17 +576,17 @@ std::vector<ExprP> h_terms(const ConstraintSystem &cs, int P, const std::vector<
         const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
         for (int s = 0; s < n_sets; s++) {
             ExprP left = Z(s, 1), right = Z(s, 0);
-            for (int j = 0; j < psets[s].count; j++) {
-                const auto &pc = cs.perm_cols[psets[s].first + j];
+            for (int j = 0; j < sets[s].second; j++) {
+                const auto &pc = cs.perm_cols[sets[s].first + j];
                 ExprP val = e_col(em.col(pc.first, pc.second), 0);
-                left = e_mul(left, e_add(e_add(val, e_mul(ec(beta), e_col(E_SIGMA + psets[s].first + j, 0))), ec(gamma)));
+                left = e_mul(left, e_add(e_add(val, e_mul(ec(beta), e_col(E_SIGMA + sets[s].first + j, 0))), ec(gamma)));
                 right = e_mul(right, e_add(e_add(val, e_mul(ec(hfr::mul(cur_delta, beta)), e_col(E_X, 0))), ec(gamma)));
                 cur_delta = hfr::mul(cur_delta, DELTA);
             }
             terms.push_back(e_mul(e_sub(left, right), lact));
         }
     }
-    for (size_t li = 0; li < lks.size(); li++) {
+    for (size_t li = 0; li < n_lookups; li++) {
         ExprP z0 = e_col(E_LK + 3 * li, 0), z1 = e_col(E_LK + 3 * li, 1);
         ExprP a0 = e_col(E_LK + 3 * li + 1, 0), am1 = e_col(E_LK + 3 * li + 1, -1), s0 = e_col(E_LK + 3 * li + 2, 0);
         auto compress = [&](const std::vector<json::ValueP> &exprs) {
@@ -942,8 +938,6 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     }
     }
     mark();  // [5] coeff_to_extended of advice / instance / lookup polynomials (sharded: done per owned coset in stage 6)
-    ColMap em;
-    em.advice0 = 0; em.fixed0 = A; em.instance0 = A + F;
     const int E_SIGMA = A + F + 1, E_PZ = E_SIGMA + P, E_L0 = E_PZ + n_sets, E_LLAST = E_L0 + 1, E_LACT = E_L0 + 2, E_X = E_L0 + 3, E_LK = E_L0 + 4;
     std::vector<const void *> ecols(E_LK + 3 * lks.size(), nullptr);
     for (int c = 0; c < A; c++) ecols[c] = adv_coset[c];

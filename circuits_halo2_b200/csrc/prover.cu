@@ -259,6 +259,15 @@ struct sb_pk {
     void *omega_pows = nullptr;                                  // omega^i (n)
     void *div_g_pows = nullptr, *div_x = nullptr, *div_ginv_scaled = nullptr;  // SHPLONK coset division: g^i, g*omega^i, g^-i / n
     std::vector<uint8_t> fixed_comms, sigma_comms;               // affine, 64 B each
+    // evaluate_h program compiled once per key with placeholder challenges; per proof only the challenge-derived constants are patched
+    struct HProgramCache {
+        std::mutex mu;
+        bool valid = false;
+        Program prog;
+        std::vector<uint32_t> theta, beta, gamma;               // constant slots holding theta / beta / gamma
+        std::vector<std::pair<uint32_t, int>> delta_beta, ypow;  // (slot, j): delta^j * beta ; (slot, e): y^e
+    };
+    mutable HProgramCache hcache;
     // sharded proving: zeta^(m mod 3) * ext_omega^(j m), m < n, for coset j of the extended domain (built on first use)
     mutable std::vector<void *> coset_pows;
     mutable std::vector<void *> owned;
@@ -608,6 +617,61 @@ std::vector<ExprP> h_terms(const ConstraintSystem &cs, int P, const std::vector<
     return terms;
 }
 
+// The quotient-numerator program of this key for the given challenges.  Structure (DAG, schedule, slots) depends only on the
+// constraint system, so it is compiled once with placeholder challenges; afterwards the constant table is patched.
+Program h_program_for(const sb_pk *pk, const std::vector<std::pair<int, int>> &sets, size_t n_lookups, const Fr &theta, const Fr &beta, const Fr &gamma, const Fr &y) {
+    const ConstraintSystem &cs = pk->cs;
+    const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+    sb_pk::HProgramCache &hc = pk->hcache;
+    std::lock_guard<std::mutex> lk(hc.mu);
+    if (!hc.valid) {
+        // placeholders: fixed, pairwise distinct, astronomically unlikely to collide with a constant of the circuit
+        const Fr t0 = fr_from_hex("0x1b3c5d7e9fa1c3e5071929bb4d6f8192a3b5c7d9ebfd0f21334557697b8d9fb1");
+        const Fr b0 = fr_from_hex("0x0a1c2e40526476889aacbed0e2f40618293b4d5f718395a7b9cbddef01132537");
+        const Fr g0 = fr_from_hex("0x2f1d0bf9e7d5c3b1a08f7e6d5c4b3a291807f6e5d4c3b2a1908f7e6d5c4b3a29");
+        const Fr y0 = fr_from_hex("0x13579bdf02468ace13579bdf02468ace13579bdf02468ace13579bdf02468acf");
+        const std::vector<ExprP> terms = h_terms(cs, pk->P, sets, n_lookups, t0, b0, g0);
+        fr_t yd = to_dev(y0);
+        hc.prog = compile_terms(terms, &yd);
+        std::vector<Fr> db(pk->P), yp(terms.size() + 1);
+        Fr d = hfr::ONE;
+        for (int j = 0; j < pk->P; j++) { db[j] = hfr::mul(d, b0); d = hfr::mul(d, DELTA); }
+        yp[0] = hfr::ONE;
+        for (size_t e = 1; e < yp.size(); e++) yp[e] = hfr::mul(yp[e - 1], y0);
+        for (uint32_t ci = 0; ci < hc.prog.consts.size(); ci++) {
+            const Fr c = to_host(hc.prog.consts[ci]);
+            if (c == t0) { hc.theta.push_back(ci); continue; }
+            if (c == b0) { hc.beta.push_back(ci); continue; }
+            if (c == g0) { hc.gamma.push_back(ci); continue; }
+            bool hit = false;
+            for (int j = 1; j < pk->P && !hit; j++)
+                if (c == db[j]) { hc.delta_beta.push_back({ci, j}); hit = true; }
+            for (size_t e = 1; e < yp.size() && !hit; e++)
+                if (c == yp[e]) { hc.ypow.push_back({ci, (int)e}); hit = true; }
+        }
+        hc.valid = true;
+    }
+    Program p = hc.prog;
+    for (uint32_t ci : hc.theta) p.consts[ci] = to_dev(theta);
+    for (uint32_t ci : hc.beta) p.consts[ci] = to_dev(beta);
+    for (uint32_t ci : hc.gamma) p.consts[ci] = to_dev(gamma);
+    if (!hc.delta_beta.empty()) {
+        std::vector<Fr> db(pk->P);
+        Fr d = hfr::ONE;
+        for (int j = 0; j < pk->P; j++) { db[j] = hfr::mul(d, beta); d = hfr::mul(d, DELTA); }
+        for (auto &e : hc.delta_beta) p.consts[e.first] = to_dev(db[e.second]);
+    }
+    if (!hc.ypow.empty()) {
+        int emax = 0;
+        for (auto &e : hc.ypow) emax = std::max(emax, e.second);
+        std::vector<Fr> yp(emax + 1);
+        yp[0] = hfr::ONE;
+        for (int e = 1; e <= emax; e++) yp[e] = hfr::mul(yp[e - 1], y);
+        for (auto &e : hc.ypow) p.consts[e.first] = to_dev(yp[e.second]);
+    }
+    return p;
+}
+
 // ------------------------------------------------------------------ sharded proving
 // One process per GPU; every rank runs the whole transcript in lock step on replicated inputs and owns
 //   * a contiguous base range of every MSM (partial commitments are all-gathered as 64-byte points and added on the host),
@@ -953,12 +1017,16 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     }
     std::vector<std::pair<int, int>> set_ranges;
     for (int s2 = 0; s2 < n_sets; s2++) set_ranges.push_back({psets[s2].first, psets[s2].count});
-    const std::vector<ExprP> terms = h_terms(cs, P, set_ranges, lks.size(), theta, beta, gamma);
     void *d_h;
     SB_TRY(scratch_get(ctx, "pf_h", en * 32, &d_h));
     {
-        fr_t yd = to_dev(yy);
-        Program hp = compile_terms(terms, &yd);
+        Program hp;
+        if (getenv("SB_NO_HPROG_CACHE")) {
+            fr_t yd = to_dev(yy);
+            hp = compile_terms(h_terms(cs, P, set_ranges, lks.size(), theta, beta, gamma), &yd);
+        } else {
+            hp = h_program_for(pk, set_ranges, lks.size(), theta, beta, gamma, yy);
+        }
         ctx->last_h_program[0] = (uint32_t)(hp.code.size() / 3);
         ctx->last_h_program[1] = hp.n_mul;
         ctx->last_h_program[2] = hp.n_addsub;
@@ -1465,6 +1533,21 @@ int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_progra
         fr_t got = program_eval_host(prog, inputs);
         hfr::Fr acc = hfr::ZERO;
         for (size_t i = 0; i < terms.size(); i++) acc = hfr::add(hfr::mul(acc, y), direct_eval(terms[i], vals));
+        // the per-key cached program (compiled with placeholder challenges, constants patched) must give the same value, twice
+        {
+            sb_pk fake;
+            fake.cs = cs;
+            fake.P = P;
+            for (int rep = 0; rep < 2; rep++) {
+                Program cached = h_program_for(&fake, sets, cs.lookups.size(), theta, beta, gamma, y);
+                std::vector<fr_t> in2(cached.inputs.size() / 2);
+                for (size_t i = 0; i < in2.size(); i++) in2[i] = to_dev(vals.at({cached.inputs[2 * i], cached.inputs[2 * i + 1]}));
+                if (!(to_host(program_eval_host(cached, in2)) == acc)) {
+                    set_last_error("sb_test_h_program: cached program (constants patched) disagrees with the direct evaluation");
+                    return SB_ERR_ARG;
+                }
+            }
+        }
         memcpy(out_program_value, got.v, 32);
         memcpy(out_direct_value, acc.v, 32);
         out_shape[0] = (uint32_t)(prog.code.size() / 3);

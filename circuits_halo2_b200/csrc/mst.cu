@@ -274,6 +274,64 @@ __global__ void mst_proof_kernel(TreeView t, const uint64_t *idx, uint4 *out, ui
     store_fp(q + 2 * (t.n_cur + 1), load_fp<FrParams>(t.hash + 2 * (ch + 1)));
 }
 
+
+// MerkleSumTree::update_leaf (mst.rs:158-197): new balances for one entry, then the path to the root; one thread (depth + 1 dependent hashes)
+__global__ void mst_update_kernel(TreeView t, uint64_t index, const uint64_t *bal64) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fr_t bals[SB_MAX_CUR];
+    for (uint32_t c = 0; c < t.n_cur; c++) {
+        fr_t x = fr_t::zero();
+        x.v[0] = (uint32_t)bal64[c];
+        x.v[1] = (uint32_t)(bal64[c] >> 32);
+        bals[c] = to_mont(x);
+    }
+    leaf_from_preimage(t, index, load_fp<FrParams>(t.uname + 2 * index), bals);
+    for (uint32_t level = 1; level <= t.depth; level++) {
+        __threadfence();
+        middle_node(t, level, index >> level);
+    }
+}
+
+// Tree::verify_proof (tree.rs:139-186), one thread per proof.  pre: the layout sb_mst_proofs writes.
+__global__ void mst_verify_kernel(const uint4 *pre, const uint8_t *path, uint32_t depth, uint32_t n_cur, const uint4 *root /* hash | balances */, uint64_t n_proofs, uint8_t *ok) {
+    const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n_proofs) return;
+    const uint64_t per = 2ull * (n_cur + 1) + (uint64_t)(depth > 0 ? depth - 1 : 0) * (n_cur + 2);
+    const uint4 *p = pre + 2 * j * per;
+    auto hash_n = [&](const uint4 *q, uint32_t len) {
+        fr_t s0 = fr_t::zero(), s1 = sponge_init_capacity(len);
+        for (uint32_t i = 0; i < len; i++) {
+            s0 = add(s0, load_fp<FrParams>(q + 2 * i));
+            poseidon_permute(s0, s1);
+        }
+        return s0;
+    };
+    fr_t bal[SB_MAX_CUR];
+    fr_t node = hash_n(p, n_cur + 1);
+    for (uint32_t c = 0; c < n_cur; c++) bal[c] = load_fp<FrParams>(p + 2 * (c + 1));
+    for (uint32_t level = 0; level < depth; level++) {
+        const uint4 *sp = level == 0 ? p + 2 * (n_cur + 1) : p + 2 * (2ull * (n_cur + 1) + (uint64_t)(level - 1) * (n_cur + 2));
+        const uint32_t slen = level == 0 ? n_cur + 1 : n_cur + 2;
+        const fr_t sib = hash_n(sp, slen);
+        const uint4 *sbal = level == 0 ? sp + 2 : sp;  // leaf preimage: [username, balances...]; middle preimage: [balances..., hash_l, hash_r]
+        fr_t s0 = fr_t::zero(), s1 = sponge_init_capacity(n_cur + 2);
+        for (uint32_t c = 0; c < n_cur; c++) {
+            bal[c] = add(bal[c], load_fp<FrParams>(sbal + 2 * c));
+            s0 = add(s0, bal[c]);
+            poseidon_permute(s0, s1);
+        }
+        const bool right = path[j * depth + level] != 0;
+        s0 = add(s0, right ? sib : node);
+        poseidon_permute(s0, s1);
+        s0 = add(s0, right ? node : sib);
+        poseidon_permute(s0, s1);
+        node = s0;
+    }
+    bool good = node == load_fp<FrParams>(root);
+    for (uint32_t c = 0; c < n_cur; c++) good = good && (bal[c] == load_fp<FrParams>(root + 2 * (c + 1)));
+    ok[j] = good ? 1 : 0;
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -485,6 +543,47 @@ int32_t sb_mst_proofs(const sb_mst *mst, const uint64_t *indices, size_t n_proof
     }
     SB_CUDA_TRY(cudaMemcpyAsync(out_preimages, d_out, n_proofs * per * 32, cudaMemcpyDeviceToHost, st));
     if (d) SB_CUDA_TRY(cudaMemcpyAsync(out_path_indices, d_path, n_proofs * d, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+int32_t sb_mst_update_leaf(sb_mst *mst, size_t index, const uint64_t *new_balances, uint8_t out_root_hash[32], uint8_t *out_root_balances) {
+    if (!mst || !new_balances) return SB_ERR_ARG;
+    SB_REQUIRE(index < (1ull << mst->depth), "sb_mst_update_leaf: index out of bounds");
+    sb_ctx *ctx = mst->ctx;
+    {
+        CtxGuard g(ctx);
+        void *d_b;
+        SB_TRY(scratch_get(ctx, "mst_upd", mst->n_cur * 8, &d_b));
+        SB_TRY(h2d_staged(ctx, d_b, new_balances, mst->n_cur * 8, ctx->stream));
+        SB_LAUNCH(ctx, mst_update_kernel, 1, 32, 0, ctx->stream, mst->view(), (uint64_t)index, (const uint64_t *)d_b);
+        SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (out_root_hash && out_root_balances) return sb_mst_root(mst, out_root_hash, out_root_balances);
+    return SB_OK;
+}
+
+int32_t sb_mst_verify_proofs(sb_ctx *ctx, uint32_t n_currencies, uint32_t depth, const uint8_t *preimages, const uint8_t *path_indices, const uint8_t root_hash[32],
+                             const uint8_t *root_balances, size_t n_proofs, uint8_t *out_ok) {
+    if (!ctx || !preimages || !path_indices || !root_hash || !root_balances || !out_ok) return SB_ERR_ARG;
+    SB_REQUIRE(n_currencies >= 1 && n_currencies <= SB_MAX_CUR && depth <= 30, "sb_mst_verify_proofs: bad shape");
+    if (n_proofs == 0) return SB_OK;
+    CtxGuard g(ctx);
+    SB_TRY(poseidon_consts_load(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t per = 2ull * (n_currencies + 1) + (size_t)(depth > 0 ? depth - 1 : 0) * (n_currencies + 2);
+    void *d_pre, *d_path, *d_root, *d_ok;
+    SB_TRY(scratch_get(ctx, "mst_vpre", n_proofs * per * 32, &d_pre));
+    SB_TRY(scratch_get(ctx, "mst_vpath", n_proofs * (depth ? depth : 1), &d_path));
+    SB_TRY(scratch_get(ctx, "mst_vroot", (n_currencies + 1) * 32, &d_root));
+    SB_TRY(scratch_get(ctx, "mst_vok", n_proofs, &d_ok));
+    SB_CUDA_TRY(cudaMemcpyAsync(d_pre, preimages, n_proofs * per * 32, cudaMemcpyHostToDevice, st));
+    if (depth) SB_CUDA_TRY(cudaMemcpyAsync(d_path, path_indices, n_proofs * depth, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(d_root, root_hash, 32, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_root + 32, root_balances, n_currencies * 32, cudaMemcpyHostToDevice, st));
+    SB_LAUNCH(ctx, mst_verify_kernel, (unsigned)((n_proofs + 63) / 64), 64, 0, st, (const uint4 *)d_pre, (const uint8_t *)d_path, depth, n_currencies, (const uint4 *)d_root,
+              (uint64_t)n_proofs, (uint8_t *)d_ok);
+    SB_CUDA_TRY(cudaMemcpyAsync(out_ok, d_ok, n_proofs, cudaMemcpyDeviceToHost, st));
     SB_CUDA_TRY(cudaStreamSynchronize(st));
     return SB_OK;
 }

@@ -150,6 +150,60 @@ class MerkleSumTree:
             out.append(MerkleProof(vals[: c + 1], root, vals[c + 1: 2 * (c + 1)], mids, [int(x) for x in path[j, :d]]))
         return out
 
+    def index_of_username(self, username: str) -> int:
+        """mst.rs:200-216: linear search, or binary search when the tree was built sorted"""
+        if self._entries is None:
+            raise AssertionError("tree built from preimages keeps no entries")
+        if self.is_sorted:
+            import bisect
+            names = [e.username for e in self._entries]
+            i = bisect.bisect_left(names, username)
+            if i < len(names) and names[i] == username:
+                return i
+        else:
+            for i, e in enumerate(self._entries):
+                if e.username == username:
+                    return i
+        raise KeyError("Username not found")
+
+    def update_leaf(self, username: str, new_balances: Sequence[int]) -> Node:
+        """mst.rs:158-197: store the new balances, rehash the leaf and its path on the GPU, return the new root"""
+        index = self.index_of_username(username)
+        if len(new_balances) != self.n_currencies:
+            raise AssertionError("update_leaf: N_CURRENCIES balances expected")
+        bal = np.ascontiguousarray(new_balances, dtype=np.uint64)
+        hs = np.zeros(4, dtype=np.uint64)
+        bl = np.zeros((self.n_currencies, 4), dtype=np.uint64)
+        _lib.check(_lib.lib().sb_mst_update_leaf(self._h, ctypes.c_size_t(index), ptr(bal), ptr(hs), ptr(bl)), "sb_mst_update_leaf")
+        self._entries[index] = Entry(username, [int(x) for x in new_balances])
+        return Node(fields.fr_from_mont(hs), _fr_list(bl))
+
+    def verify_proofs(self, proofs: Sequence[MerkleProof]) -> List[bool]:
+        """tree.rs:139-186 on the GPU, one thread per proof"""
+        if not proofs:
+            return []
+        c, d = self.n_currencies, len(proofs[0].path_indices)
+        per = 2 * (c + 1) + max(d - 1, 0) * (c + 2)
+        pre = np.zeros((len(proofs), per, 4), dtype=np.uint64)
+        path = np.zeros((len(proofs), max(d, 1)), dtype=np.uint8)
+        for j, p in enumerate(proofs):
+            vals = list(p.entry_preimage) + list(p.sibling_leaf_node_hash_preimage) + [x for m in p.sibling_middle_node_hash_preimages for x in m]
+            if len(vals) != per or len(p.path_indices) != d:
+                raise AssertionError("verify_proofs: proofs of different shapes")
+            for i, v in enumerate(vals):
+                pre[j, i] = fields.fr_to_mont(v)
+            path[j, :d] = p.path_indices
+        root = proofs[0].root
+        rh = fields.fr_to_mont(root.hash)
+        rb = np.stack([fields.fr_to_mont(b) for b in root.balances])
+        ok = np.zeros(len(proofs), dtype=np.uint8)
+        _lib.check(_lib.lib().sb_mst_verify_proofs(self.ctx.handle, ctypes.c_uint32(c), ctypes.c_uint32(d), ptr(pre), ptr(path), ptr(rh), ptr(rb), ctypes.c_size_t(len(proofs)), ptr(ok)),
+                   "sb_mst_verify_proofs")
+        return [bool(x) for x in ok]
+
+    def verify_proof(self, proof: MerkleProof) -> bool:
+        return self.verify_proofs([proof])[0]
+
     def generate_proof(self, index: int) -> MerkleProof:
         if not 0 <= index < (1 << self._depth):
             raise IndexError("Index out of bounds")

@@ -203,6 +203,13 @@ int32_t sb_mst_level_hashes(const sb_mst *mst, uint32_t level, uint8_t *out_hash
  * entry preimage (n_cur+1) | sibling leaf preimage (n_cur+1) | (depth-1) x sibling middle-node preimage (n_cur+2)  field elements,
  * out_path_indices holds depth bytes (0 = the node is a left child). */
 int32_t sb_mst_proofs(const sb_mst *mst, const uint64_t *indices, size_t n_proofs, uint8_t *out_preimages, uint8_t *out_path_indices);
+/* MerkleSumTree::update_leaf (mst.rs:158-197): new balances (n_currencies u64) for the entry at `index`, the path to the root is rehashed;
+ * optionally returns the new root */
+int32_t sb_mst_update_leaf(sb_mst *mst, size_t index, const uint64_t *new_balances, uint8_t out_root_hash[32], uint8_t *out_root_balances);
+/* Tree::verify_proof (tree.rs:139-186) for n_proofs proofs in the layout sb_mst_proofs writes, against one root; out_ok[j] = 1 iff proof j
+ * hashes up to root_hash with balances equal to root_balances */
+int32_t sb_mst_verify_proofs(sb_ctx *ctx, uint32_t n_currencies, uint32_t depth, const uint8_t *preimages, const uint8_t *path_indices, const uint8_t root_hash[32],
+                             const uint8_t *root_balances, size_t n_proofs, uint8_t *out_ok);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */

@@ -112,3 +112,48 @@ def test_two_to_the_twenty_users(ctx):
         assert p.entry_preimage == M.Entry(names[i].decode(), [int(x) for x in bal[i]]).preimage()
         assert oracle_verify(p, 2)
     print(f"\n[mst] 2^20 users x 2 currencies built in {t.build_ms:.1f} ms on the device")
+
+
+def test_verify_update_and_sorted_like_the_reference_tests(ctx, golden_dir):
+    """merkle_sum_tree/tests.rs: test_mst (verify, tampered proofs rejected), test_update_mst_leaf, test_update_invalid_mst_leaf, test_sorted_mst."""
+    import copy
+    import circuits_halo2_b200 as sb
+    path = os.path.join(golden_dir, "entry_16.csv")
+    t = sb.MerkleSumTree.from_csv(path, ctx)
+    proofs = t.generate_proofs(list(range(16)))
+    assert all(t.verify_proofs(proofs)) and all(oracle_verify(p, 2) for p in proofs)
+    bad1 = copy.deepcopy(proofs[0])
+    bad1.sibling_leaf_node_hash_preimage[1] += 1            # tests.rs:52-60: a wrong sibling balance
+    bad2 = copy.deepcopy(proofs[0])
+    bad2.path_indices[0] ^= 1                               # tests.rs:62-65: a wrong path index
+    bad3 = copy.deepcopy(proofs[3])
+    bad3.entry_preimage[0] = (bad3.entry_preimage[0] + 1) % B.R
+    assert t.verify_proofs([bad1, bad2, bad3, proofs[5]]) == [False, False, False, True]
+    # update_leaf: change, compare with the oracle tree of the changed csv, change back (tests.rs:69-92)
+    root0 = t.root()
+    name = t.get_entry(7).username
+    old = list(t.get_entry(7).balances)
+    r1 = t.update_leaf(name, [11, 22])
+    o = M.MerkleSumTree.from_csv(path)
+    ents = [M.Entry(e.username, list(e.balances)) for e in o.entries]
+    ents[7] = M.Entry(name, [11, 22])
+    o2 = M.MerkleSumTree(ents)
+    assert (r1.hash, r1.balances) == (o2.root[0], o2.root[1]) and r1.hash != root0.hash
+    for level in range(5):
+        got = t.level_hashes(level)
+        assert [fr_int(x) for x in got] == [h for h, _ in o2.nodes[level]], level
+    assert t.verify_proof(t.generate_proof(7))
+    r2 = t.update_leaf(name, old)
+    assert (r2.hash, r2.balances) == (root0.hash, root0.balances)
+    with pytest.raises(KeyError):
+        t.update_leaf("non_existing_user", [1, 2])           # tests.rs:95-106
+    # sorted tree (tests.rs:110-127): same balances, different root hash, entries ordered by username
+    ts = sb.MerkleSumTree.from_csv(path, ctx, sort=True)
+    assert ts.root().balances == root0.balances and ts.root().hash != root0.hash
+    names = [ts.get_entry(i).username for i in range(16)]
+    assert names == sorted(names) and ts.index_of_username(names[5]) == 5
+
+
+def fr_int(limbs):
+    from circuits_halo2_b200 import fields
+    return fields.fr_from_mont(limbs)

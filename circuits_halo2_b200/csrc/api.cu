@@ -338,6 +338,7 @@ int32_t srs_precompute_impl(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32
         c = srs->k <= 20 ? srs->k : (srs->k >= 23 ? 22 : 20);
         if (const char *env = getenv("SB_TAB_C")) c = (uint32_t)atoi(env);
     }
+    std::lock_guard<std::mutex> tab_lock(srs->tab_mu);
     for (int b = 0; b < 2; b++) {
         if (!((basis_mask >> b) & 1) || srs->tab[b].d_tables) continue;
         if (b == 1 && srs->d_g_lagrange == srs->d_g && srs->tab[0].d_tables) { srs->tab[1] = srs->tab[0]; continue; }

@@ -338,8 +338,71 @@ __global__ void __launch_bounds__(BITONIC_SMEM_THREADS) bitonic_smem_kernel(uint
         a[2 * (base + q) + 1] = s_hi[q];
     }
 }
+// ---- small-key fast path: when every key is below 2^16 (range-check inputs, byte tables, selector-gated zeros) the sorted array is
+//      fully described by a 65 536-bin histogram: count, scan, and let every output position look its value up in the offsets.
+static const uint32_t SMALLKEY_BINS = 1u << 16;
+__global__ void smallkey_hist_kernel(const uint4 *a, uint64_t n, uint32_t *hist, uint32_t *too_big) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 lo = a[2 * i], hi = a[2 * i + 1];
+    if ((lo.x >> 16) | lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) {
+        *too_big = 1;
+        return;
+    }
+    // warp-aggregated: constant columns put a whole warp into one bin
+    const uint32_t peers = __match_any_sync(__activemask(), lo.x);
+    if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(hist + lo.x, __popc(peers));
+}
+__global__ void smallkey_scan_kernel(uint32_t *hist /* in: counts, out: exclusive offsets; [BINS] = total */) {
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x, per = SMALLKEY_BINS / 1024;
+    uint32_t s = 0;
+    for (uint32_t q = 0; q < per; q++) s += hist[t * per + q];
+    part[t] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - s;
+    for (uint32_t q = 0; q < per; q++) {
+        const uint32_t c = hist[t * per + q];
+        hist[t * per + q] = run;
+        run += c;
+    }
+    if (t == 1023) hist[SMALLKEY_BINS] = run;
+}
+__global__ void smallkey_expand_kernel(const uint32_t *offsets, uint4 *out, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t lo = 0, hi = SMALLKEY_BINS;  // largest v with offsets[v] <= i
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= (uint32_t)i) lo = mid;
+        else hi = mid;
+    }
+    out[2 * i] = make_uint4(lo, 0, 0, 0);
+    out[2 * i + 1] = make_uint4(0, 0, 0, 0);
+}
+
 // sorts d_a[0 .. count) ascending as raw 256-bit integers; d_a must have room for the next power of two
 int32_t sort_u256(sb_ctx *ctx, void *d_a, size_t count, size_t capacity_pow2, cudaStream_t st) {
+    if (count >= 4096 && count < (1ull << 32) && !getenv("SB_NO_SMALLKEY_SORT")) {
+        uint32_t *d_hist;
+        SB_TRY(scratch_get(ctx, "sort_hist", (SMALLKEY_BINS + 2) * 4, (void **)&d_hist));
+        SB_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (SMALLKEY_BINS + 2) * 4, st));
+        SB_LAUNCH(ctx, smallkey_hist_kernel, (unsigned)((count + 255) / 256), 256, 0, st, (const uint4 *)d_a, (uint64_t)count, d_hist, d_hist + SMALLKEY_BINS + 1);
+        uint32_t too_big = 1;
+        SB_CUDA_TRY(cudaMemcpyAsync(&too_big, d_hist + SMALLKEY_BINS + 1, 4, cudaMemcpyDeviceToHost, st));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!too_big) {
+            SB_LAUNCH(ctx, smallkey_scan_kernel, 1, 1024, 0, st, d_hist);
+            SB_LAUNCH(ctx, smallkey_expand_kernel, (unsigned)((count + 255) / 256), 256, 0, st, (const uint32_t *)d_hist, (uint4 *)d_a, (uint64_t)count);
+            return SB_OK;
+        }
+    }
     const uint64_t N = capacity_pow2;
     if (N > count) SB_LAUNCH(ctx, fill_ones_kernel, (unsigned)((N - count + 255) / 256), 256, 0, st, (uint4 *)d_a, (uint64_t)count, N);
     if (N < 2) return SB_OK;

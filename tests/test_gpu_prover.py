@@ -77,6 +77,19 @@ def test_sort_matches_fr_ord(ctx, n):
     assert HP.to_ints(got) == ref
 
 
+@pytest.mark.parametrize("n,top", [(4096, 255), (5000, 65535), (1 << 16, 65535), (5000, 65536), ((1 << 15) + 7, 1 << 200)])
+def test_sort_small_keys_counting_path_and_fallback(ctx, n, top):
+    """keys below 2^16 take the histogram path (byte tables, range-check inputs); a single larger key falls back to the bitonic network"""
+    rng = np.random.default_rng(n + top % 1000)
+    vals = [int(x) for x in rng.integers(0, 256, size=n)]
+    vals[0], vals[1], vals[n // 2] = 0, top, top
+    vals[n // 3: n // 3 + 700] = [7] * 700      # a hot bin
+    a = np.stack([fr(v) for v in vals])
+    got = a.copy()
+    L().check(L().lib().sb_fr_sort(ctx.handle, P(got), ctypes.c_size_t(n)), "sort")
+    assert HP.to_ints(got) == sorted(vals)
+
+
 @pytest.mark.parametrize("n,kind", [(256, "bytes"), (2048, "bytes"), (2048, "random"), (1 << 14, "bytes")])
 def test_lookup_permute(ctx, n, kind):
     rng = np.random.default_rng(n)

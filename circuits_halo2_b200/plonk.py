@@ -128,7 +128,7 @@ class ShardComm:
     def _allgather_host(self, _user, send, recv, nbytes):
         try:
             torch, dist = self.torch, self.dist
-            mine = torch.frombuffer(ctypes.string_at(send, nbytes), dtype=torch.uint8).clone()
+            mine = torch.frombuffer(bytearray(ctypes.string_at(send, nbytes)), dtype=torch.uint8)
             if self.host_on_cpu:
                 out = torch.empty(self.world * nbytes, dtype=torch.uint8)
                 dist.all_gather_into_tensor(out, mine, group=self.group)

@@ -241,3 +241,35 @@ def test_sparse_key_and_device_srs_match_dense_path(ctx, golden_dir):
     tr = KeccakTranscript()
     HP.create_proof(oparams, opk, instances, np.stack([HP.from_ints(c) for c in C.advice_columns(lay)]), ChaCha20Rng.seed_from_u64(5), tr)
     assert got == tr.finalize()
+
+
+@pytest.mark.parametrize("user", [1, 9])
+def test_end_to_end_gpu_tree_to_gpu_proof_for_other_users(real, golden_dir, ctx, user):
+    """The whole product flow for users other than the fixture's: Merkle sum tree on the GPU -> its Merkle proof for `user` -> the circuit's
+    witness (the Rust front-end's job; restated by oracle/mst_circuit.py) -> create_proof on the GPU with the key built for user 0.
+    The proof must equal the oracle prover's byte for byte (that prover's proofs are accepted by the reference's verifier contract,
+    tests/test_oracle_circuit.py) and carry the user's leaf hash and the tree's root as public inputs."""
+    import circuits_halo2_b200 as sb
+
+    class _E:  # what oracle/mst_circuit.py reads from the entry: its hash preimage
+        def __init__(self, pre):
+            self._pre = pre
+
+        def preimage(self):
+            return self._pre
+
+    tree = sb.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv"), ctx)
+    mp = tree.generate_proof(user)
+    assert tree.verify_proof(mp)
+    proof_dict = {"entry": _E(mp.entry_preimage), "root": (mp.root.hash, mp.root.balances),
+                  "sibling_leaf_node_hash_preimage": mp.sibling_leaf_node_hash_preimage,
+                  "sibling_middle_node_hash_preimages": mp.sibling_middle_node_hash_preimages, "path_indices": mp.path_indices}
+    lay = C.synthesize(11, proof_dict, 4, 2, 8)
+    # the key does not depend on the user: fixed columns and permutation are those of the fixture's key
+    assert (np.stack([HP.from_ints(c) for c in C.fixed_columns(lay)]) == np.stack([HP.from_ints(c) for c in C.fixed_columns(C.synthesize(11, M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16.csv")).generate_proof(0), 4, 2, 8))])).all()
+    advice = np.stack([HP.from_ints(c) for c in C.advice_columns(lay)])
+    instances = [tree.node(0, user).hash, mp.root.hash] + list(mp.root.balances)
+    tr = KeccakTranscript()
+    HP.create_proof(real["oparams"], real["opk"], instances, advice, ChaCha20Rng.seed_from_u64(100 + user), tr)
+    got = sb.create_proof(real["pk"], instances, advice, sb.seed_from_u64(100 + user), sb.TRANSCRIPT_KECCAK)
+    assert got == tr.finalize()

@@ -1,9 +1,10 @@
 """Executable model of the MSM pipeline in csrc/msm.cu, over an abstract additive group.
 
 Pins, on the CPU, the control logic that is hard to eyeball in CUDA: signed-digit recoding,
-counting sort by (window, bucket), the chunked reduce-by-key levels (first/last runs of a chunk
-become partials for the next level, interior runs go straight to their bucket), the final
-single-CTA segmented scan, the segmented bucket reduction and the host window fold.
+counting sort by (window, bucket), the key-less level 1 (bucket of a position from the sort's offsets), the chunked reduce-by-key levels
+(first/last runs of a chunk become partials for the next level, interior runs go straight to their bucket),
+the final single-CTA segmented scan, the hierarchical bucket reduction, fixed-base window tables with batches of
+scalar vectors, window ranges (multi-GPU sharding) and the host window fold.
 The "group" is pluggable: integers mod a prime (fast, exact multiset check) or real G1 points.
 """
 INVALID = 0xFFFFFFFF
@@ -82,65 +83,163 @@ def final_level(grp, keys, pts, buckets):
             buckets[ks[i]] = grp.add(buckets[ks[i]], ps[i])
 
 
-def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2):
-    n = len(scalars)
-    W = window_count(c)
+def bucket_of(offsets, nb, pos):
+    """largest b in [0, nb) with offsets[b] <= pos (msm.cu::bucket_of)"""
+    lo, hi = 0, nb
+    while hi - lo > 1:
+        mid = (lo + hi) >> 1
+        if offsets[mid] <= pos:
+            lo = mid
+        else:
+            hi = mid
+    return lo
+
+
+def reduce_first(grp, offsets, nb, vals, points, L, buckets):
+    """level 1 without a key array (msm_reduce_first_kernel): the bucket of a sorted position follows from the exclusive offsets of
+    the counting sort; neighbour check first, binary search when the walk crosses empty buckets."""
+    n_valid = offsets[nb]
+    nchunks = (max(n_valid, 1) + L - 1) // L
+    okeys, opts = [INVALID] * (2 * nchunks), [grp.zero()] * (2 * nchunks)
+    for t in range(nchunks):
+        start = t * L
+        if start >= n_valid:
+            continue
+        end = min(n_valid, start + L)
+        cur = bucket_of(offsets, nb, start)
+        next_off = offsets[cur + 1]
+        nruns, acc = 1, grp.zero()
+        for pos in range(start, end):
+            if pos >= next_off:
+                if nruns == 1:
+                    okeys[2 * t], opts[2 * t] = cur, acc
+                else:
+                    buckets[cur] = grp.add(buckets[cur], acc)
+                cur += 1
+                next_off = offsets[cur + 1]
+                if pos >= next_off:
+                    cur = bucket_of(offsets, nb, pos)
+                    next_off = offsets[cur + 1]
+                nruns += 1
+                acc = grp.zero()
+            v = vals[pos]
+            p = points[v & 0x7FFFFFFF]
+            acc = grp.add(acc, grp.neg(p) if v >> 31 else p)
+        slot = 2 * t if nruns == 1 else 2 * t + 1
+        okeys[slot], opts[slot] = cur, acc
+    return okeys, opts
+
+
+def bucket_hierarchy(grp, buckets, n_sets, B, seg_log0, finish_at=8):
+    """sum_i (i + 1) * B_i per bucket set without scalar multiplication until few elements are left
+    (msm_bucket_level_kernel<0/1>, msm_bucket_finish_kernel): R = sum_i [Q_i + lambda * i * P_i]."""
+    out = []
+    for w in range(n_sets):
+        P = list(buckets[w * B:(w + 1) * B])
+        Q = None
+        m, lam_log, level = B, 0, 0
+        while level < 2 and m > finish_at:
+            sl = (seg_log0 if seg_log0 else 1) if level == 0 else 3
+            while (1 << sl) > m:
+                sl -= 1
+            S = 1 << sl
+            nP, nQ = [], []
+            for sg in range(m >> sl):
+                run, acc = grp.zero(), grp.zero()
+                for j in range(S - 1, 0, -1):
+                    run = grp.add(run, P[sg * S + j])
+                    acc = grp.add(acc, run)
+                run = grp.add(run, P[sg * S])
+                for _ in range(lam_log):
+                    acc = grp.dbl(acc)
+                if Q is None:
+                    acc = grp.add(acc, run)
+                else:
+                    for j in range(S):
+                        acc = grp.add(acc, Q[sg * S + j])
+                nP.append(run)
+                nQ.append(acc)
+            P, Q = nP, nQ
+            lam_log += sl
+            m >>= sl
+            level += 1
+        total = grp.zero()
+        for sidx in range(m):   # finish: V_s = Q_s + lambda * s * P_s by double-and-add, then a tree (order-free in an abelian group)
+            v = grp.zero()
+            if sidx:
+                for bit in reversed(range(sidx.bit_length())):
+                    v = grp.dbl(v)
+                    if (sidx >> bit) & 1:
+                        v = grp.add(v, P[sidx])
+                for _ in range(lam_log):
+                    v = grp.dbl(v)
+            v = grp.add(v, Q[sidx] if Q is not None else P[sidx])
+            total = grp.add(total, v)
+        out.append(total)
+    return out
+
+
+def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None):
+    """scalars: batch * n values (vector j = scalars[j n:(j+1) n], tables only).  Returns the list of `batch` results (tables), or the
+    single result; with a window range [w_lo, w_hi) the partial sum over those windows (tables: already carrying 2^(c w))."""
+    n = len(bases)
+    assert len(scalars) == n * batch and (batch == 1 or tables)
+    W_all = window_count(c)
+    w_hi = W_all if w_hi is None else w_hi
     B = 1 << (c - 1)
-    # counting sort by key = w * B + |d| - 1
-    counts = [0] * (W * B)
-    digs = [recode(s, c, W) for s in scalars]
-    for i in range(n):
-        for w, d in enumerate(digs[i]):
+    n_sets = batch if tables else (w_hi - w_lo)
+    nb = n_sets * B
+    if tables:   # tables[w * n + i] = 2^(c w) * P_i
+        points = []
+        for w in range(W_all):
+            for i in range(n):
+                t = bases[i]
+                for _ in range(c * w):
+                    t = grp.dbl(t)
+                points.append(t)
+    else:
+        points = bases
+    digs = [recode(s, c, W_all) for s in scalars]
+
+    def key_val(gi, w, d):
+        piece, i = divmod(gi, n)
+        key = (piece * B if tables else (w - w_lo) * B) + abs(d) - 1
+        val = (w * n + i if tables else i) | ((1 << 31) if d < 0 else 0)
+        return key, val
+
+    counts = [0] * nb
+    for gi in range(n * batch):
+        for w in range(w_lo, w_hi):
+            d = digs[gi][w]
             if d:
-                counts[w * B + abs(d) - 1] += 1
-    offs, run = [], 0
+                counts[key_val(gi, w, d)[0]] += 1
+    offsets, run = [], 0
     for x in counts:
-        offs.append(run)
+        offsets.append(run)
         run += x
-    T = run
-    cursor = list(offs)
-    skeys, svals = [INVALID] * (W * n), [0] * (W * n)
-    for i in range(n):
-        for w, d in enumerate(digs[i]):
+    offsets.append(run)                       # offsets[nb] = number of valid digits
+    offsets += [0, 0, 0]
+    cursor = list(offsets[:nb])
+    svals = [0] * (run + 4)
+    for gi in range(n * batch):
+        for w in range(w_lo, w_hi):
+            d = digs[gi][w]
             if d:
-                k = w * B + abs(d) - 1
-                pos = cursor[k]
+                k, v = key_val(gi, w, d)
+                svals[cursor[k]] = v
                 cursor[k] += 1
-                skeys[pos] = k
-                svals[pos] = i | ((1 << 31) if d < 0 else 0)
-    assert all(k == INVALID for k in skeys[T:])
-    buckets = [grp.zero()] * (W * B)
-    # level 1: gather (signed) bases
-    pts = [grp.zero() if k == INVALID else (grp.neg(bases[v & 0x7FFFFFFF]) if v >> 31 else bases[v & 0x7FFFFFFF])
-           for k, v in zip(skeys, svals)]
-    keys, pts = reduce_level(grp, skeys, pts, L1, buckets)
+    buckets = [grp.zero()] * nb
+    keys, pts = reduce_first(grp, offsets, nb, svals, points, L1, buckets)
     while len(keys) > final_max:
         keys, pts = reduce_level(grp, keys, pts, LK, buckets)
     final_level(grp, keys, pts, buckets)
-    # segmented bucket reduction: per window, segments of S buckets
-    S = 1 << seg_log
-    if S > B:
-        S = B
-    wins = []
-    for w in range(W):
-        total_w = grp.zero()
-        for s in range(B // S):
-            runs, acc = grp.zero(), grp.zero()
-            for j in reversed(range(S)):
-                runs = grp.add(runs, buckets[w * B + s * S + j])
-                acc = grp.add(acc, runs)
-            # + (s*S) * runs  via double-and-add
-            m, t, add = s * S, runs, grp.zero()
-            while m:
-                if m & 1:
-                    add = grp.add(add, t)
-                t = grp.dbl(t)
-                m >>= 1
-            total_w = grp.add(total_w, grp.add(acc, add))
-        wins.append(total_w)
-    # host fold (Horner over windows)
+    wins = bucket_hierarchy(grp, buckets, n_sets, B, seg_log)
+    if tables:
+        return wins                           # one (partial) commitment per scalar vector
+    if w_hi - w_lo != W_all:
+        return wins                           # window sums of the range, folded by the caller
     acc = grp.zero()
-    for w in reversed(range(W)):
+    for w in reversed(range(W_all)):
         for _ in range(c):
             acc = grp.dbl(acc)
         acc = grp.add(acc, wins[w])

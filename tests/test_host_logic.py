@@ -99,6 +99,18 @@ def test_ntt_plan_model_matches_best_fft(tile_log, rmax_log, ks):
         ntt_model.TILE_LOG, ntt_model.RMAX_LOG = old
 
 
+def _scalars(rnd, n, mode):
+    sc = [rnd.randrange(B.R) for _ in range(n)]
+    if mode == "Z":
+        sc = [s if rnd.random() < 0.1 else 0 for s in sc]
+    if mode == "C":
+        v = rnd.randrange(B.R)
+        sc = [v if rnd.random() < 0.9 else s for s in sc]
+    if mode == "S":
+        sc = [rnd.randrange(256) for _ in sc]
+    return sc
+
+
 def test_msm_pipeline_model():
     rnd = random.Random(5)
     g = msm_model.IntGroup(B.R)
@@ -106,20 +118,43 @@ def test_msm_pipeline_model():
         n = rnd.choice([1, 2, 3, 7, 16, 33, 100, 257])
         c = rnd.choice([2, 3, 4, 5, 8])
         mode = rnd.choice("UZCS")
-        sc = [rnd.randrange(B.R) for _ in range(n)]
-        if mode == "Z":
-            sc = [s if rnd.random() < 0.1 else 0 for s in sc]
-        if mode == "C":
-            v = rnd.randrange(B.R)
-            sc = [v if rnd.random() < 0.9 else s for s in sc]
-        if mode == "S":
-            sc = [rnd.randrange(256) for _ in sc]
+        sc = _scalars(rnd, n, mode)
         if trial % 17 == 0:
             sc[0] = B.R - 1
         bs = [rnd.randrange(B.R) for _ in range(n)]
         exp = sum(s * b for s, b in zip(sc, bs)) % B.R
         got = msm_model.msm(g, sc, bs, c, L1=rnd.choice([4, 8]), LK=rnd.choice([3, 4]), final_max=rnd.choice([4, 16]), seg_log=rnd.choice([0, 1, 2, 3]))
         assert got == exp, (trial, n, c, mode)
+
+
+def test_msm_model_tables_batches_and_window_shards():
+    """fixed-base window tables (one shared bucket set), batches of scalar vectors in one launch set, and the window-range shards of
+    the multi-GPU proof: partial sums over disjoint window ranges add up to the commitment (with tables) or fold by Horner (without)."""
+    rnd = random.Random(11)
+    g = msm_model.IntGroup(B.R)
+    for trial in range(40):
+        n = rnd.choice([1, 5, 16, 40, 129])
+        c = rnd.choice([3, 4, 6, 9])
+        batch = rnd.choice([1, 2, 3, 5])
+        bs = [rnd.randrange(B.R) for _ in range(n)]
+        sc = []
+        for _ in range(batch):
+            sc += _scalars(rnd, n, rnd.choice("UZCS"))
+        exp = [sum(s * b for s, b in zip(sc[j * n:(j + 1) * n], bs)) % B.R for j in range(batch)]
+        kw = dict(L1=rnd.choice([4, 8]), LK=4, final_max=rnd.choice([4, 16]), seg_log=rnd.choice([1, 2, 3]))
+        assert msm_model.msm(g, sc, bs, c, tables=True, batch=batch, **kw) == exp, (trial, "batch")
+        W = msm_model.window_count(c)
+        world = rnd.choice([2, 4, 8])
+        if W >= world:
+            parts = [msm_model.msm(g, sc, bs, c, tables=True, batch=batch, w_lo=r * W // world, w_hi=(r + 1) * W // world, **kw) for r in range(world)]
+            assert [sum(p[j] for p in parts) % B.R for j in range(batch)] == exp, (trial, "window shards, tables")
+            wins = []
+            for r in range(world):
+                wins += msm_model.msm(g, sc[:n], bs, c, w_lo=r * W // world, w_hi=(r + 1) * W // world, **kw)
+            acc = 0
+            for w in reversed(range(W)):
+                acc = (acc * (1 << c) + wins[w]) % B.R
+            assert acc == exp[0], (trial, "window shards, plain bases")
 
 
 def test_abi_library_loads_and_exports_every_declared_symbol():

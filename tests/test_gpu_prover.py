@@ -273,3 +273,43 @@ def test_end_to_end_gpu_tree_to_gpu_proof_for_other_users(real, golden_dir, ctx,
     HP.create_proof(real["oparams"], real["opk"], instances, advice, ChaCha20Rng.seed_from_u64(100 + user), tr)
     got = sb.create_proof(real["pk"], instances, advice, sb.seed_from_u64(100 + user), sb.TRANSCRIPT_KECCAK)
     assert got == tr.finalize()
+
+
+def test_batch_prover_equals_sequential_proofs(real):
+    """BatchProver (one context per worker thread, one shared key): every proof equals the one the key's own context makes for the same
+    seed, under both transcripts, and distinct seeds give distinct proofs."""
+    import circuits_halo2_b200 as sb
+    jobs = [(real["instances"], real["advice"], sb.seed_from_u64(500 + j), sb.TRANSCRIPT_KECCAK if j % 2 == 0 else sb.TRANSCRIPT_BLAKE2B) for j in range(12)]
+    bp = sb.BatchProver(real["pk"], workers=4)
+    try:
+        got = bp.prove_many(jobs)
+    finally:
+        bp.close()
+    ref = [sb.create_proof(real["pk"], *job) for job in jobs]
+    assert got == ref and len(set(got)) == len(got)
+
+
+def test_new_entry_points_reject_bad_arguments(ctx, golden_dir):
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import _lib
+    from circuits_halo2_b200._lib import SummaB200Error
+    params = sb.ParamsKZG.read(os.path.join(golden_dir, "hermez-raw-11"), ctx)
+    with pytest.raises(SummaB200Error):
+        params.precompute(bases=0)                      # empty basis mask
+    with pytest.raises(SummaB200Error):
+        params.precompute(bases=1, window_bits=30)      # window wider than the tables support
+    small = params.downsize(8)
+    small.precompute()                                  # k < 11: a no-op, commits keep working
+    v = cpu.random_fr(256, 3)
+    assert (small.commit(v) == params.commit(v)).all()  # the first 2^8 monomial bases are shared
+    assert not params.commit(np.zeros((0, 4), dtype=np.uint64)).any()   # empty polynomial -> identity, with or without tables
+    params.precompute()
+    assert not params.commit(np.zeros((0, 4), dtype=np.uint64)).any()
+    with pytest.raises(AssertionError):
+        sb.MerkleSumTree.from_entries([], ctx=ctx)
+    with pytest.raises(SummaB200Error):
+        sb.MerkleSumTree.from_arrays([b"a"], np.zeros((1, 33), dtype=np.uint64), ctx=ctx)   # more than 32 currencies
+    t = sb.MerkleSumTree.from_entries([sb.Entry("solo", [5])], ctx=ctx)                    # a single entry: depth 0, the leaf is the root
+    assert t.depth() == 0 and t.root().balances == [5] and t.root().hash == M.poseidon_hash(M.Entry("solo", [5]).preimage())
+    p = t.generate_proof(0)
+    assert p.path_indices == [] and p.sibling_middle_node_hash_preimages == []

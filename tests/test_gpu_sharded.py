@@ -76,3 +76,8 @@ def test_two_gpu_sharded_proof_equals_single_gpu_proof():
            os.path.join(ROOT, "tests", "multi", "sharded_proof_worker.py"), "14"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    # the north_star's other split of a commitment: by base range, 64-byte partial points added on the host
+    env = dict(os.environ, SB_SHARD_MSM_BY_RANGE="1")
+    cmd[cmd.index("29533")] = "29534"
+    out = subprocess.run(cmd[:-1] + ["13"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

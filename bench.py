@@ -392,7 +392,7 @@ def main():
         assert root.balances == [int(bal[:, 0].astype(object).sum()), int(bal[:, 1].astype(object).sum())], "MST root balances != column sums"
         perms = nm * 3 + (nm - 1) * 4  # Poseidon permutations: leaf = N_CURRENCIES + 1, middle = N_CURRENCIES + 2 (N_CURRENCIES = 2)
         mst = {"users": nm, "currencies": 2, "device_ms": best, "wall_ms_incl_host_packing": wall * 1e3, "musers_per_s": nm / (best * 1e-3) / 1e6,
-               "poseidon_permutations": perms, "G_field_mul_per_s": perms * 472 / (best * 1e-3) / 1e9, "field_mul_frac_of_peak": perms * 472 / (best * 1e-3) / 1e9 / fmul_peak}
+               "poseidon_permutations": perms, "G_field_mul_per_s": perms * 417 / (best * 1e-3) / 1e9, "field_mul_frac_of_peak": perms * 417 / (best * 1e-3) / 1e9 / fmul_peak}
 
     # ---- create_proof side measurement: the reference circuit MstInclusionCircuit<4,2,8> (entry_16.csv, user 0) at k = proof_k ----
     # N = 1: one GPU.  N > 1: the SAME proof sharded over the N ranks (sb_create_proof_sharded: MSMs by base range, evaluate_h / coset

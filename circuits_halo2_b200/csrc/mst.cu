@@ -5,7 +5,7 @@
 // utils/build_tree.rs:5-78}: the reference walks `Vec<Vec<Node>>` with rayon, one level at a time.  Here the whole tree
 // lives in two flat HBM arrays (hashes, balances as one plane per currency) indexed by a closed-form level offset, every
 // level is one launch of one-thread-per-node Poseidon sponges, and the levels with <= 256 nodes are folded into a single
-// one-CTA kernel.  Bound: fmaheavy (a leaf costs 3 permutations = 1416 field products, a middle node 4 + ... = 472 * (N_CURRENCIES + 2)).
+// one-CTA kernel.  Bound: fmaheavy (a leaf costs N_CURRENCIES + 1 permutations of 417 field products, a middle node N_CURRENCIES + 2).
 #include "common.cuh"
 #include "handles.h"
 #include "poseidon_constants.inc"
@@ -15,6 +15,8 @@ namespace sb {
 struct PoseidonConsts {
     fr_t rc[64][2];
     fr_t mds[2][2];
+    fr_t partial[56][4];  // rounds 4..59 in scaled-lane form: rc0, rc1 / d, w = m01 d, v = m10 / (m11 d)
+    fr_t partial_scale;   // d after the last partial round
 };
 __constant__ PoseidonConsts c_pos;
 static std::mutex g_pos_mu;
@@ -26,6 +28,8 @@ static int32_t poseidon_consts_load(int device) {
     PoseidonConsts h;
     memcpy(h.rc, POSEIDON_RC_HOST, sizeof(h.rc));
     memcpy(h.mds, POSEIDON_MDS_HOST, sizeof(h.mds));
+    memcpy(h.partial, POSEIDON_PARTIAL_HOST, sizeof(h.partial));
+    memcpy(&h.partial_scale, POSEIDON_PARTIAL_SCALE_HOST, sizeof(h.partial_scale));
     SB_CUDA_TRY(cudaMemcpyToSymbol(c_pos, &h, sizeof(h)));
     if (device < 64) g_pos_loaded[device] = true;
     return SB_OK;
@@ -38,17 +42,28 @@ __device__ __forceinline__ fr_t pow5(const fr_t &x) {
 }
 
 // halo2_gadgets poseidon::primitives::permute for T = 2: add round constants, S-box on both lanes in the
-// 4 + 4 full rounds and on lane 0 only in the 56 partial rounds, then the MDS product.
+// 4 + 4 full rounds and on lane 0 only in the 56 partial rounds, then the MDS product.  The partial rounds run in an exactly
+// equivalent "scaled lane" form (lane 1 = d * s1_hat, d updated analytically; constants precomputed by
+// tools/gen_poseidon_header.py): 6 instead of 7 products per round, 417 instead of 472 per permutation, same field elements out.
+__device__ __forceinline__ void poseidon_full_round(fr_t &s0, fr_t &s1, int r) {
+    fr_t a = pow5(add(s0, c_pos.rc[r][0]));
+    fr_t b = pow5(add(s1, c_pos.rc[r][1]));
+    s0 = add(mul(c_pos.mds[0][0], a), mul(c_pos.mds[0][1], b));
+    s1 = add(mul(c_pos.mds[1][0], a), mul(c_pos.mds[1][1], b));
+}
 __device__ __noinline__ void poseidon_permute(fr_t &s0, fr_t &s1) {
 #pragma unroll 1
-    for (int r = 0; r < 64; r++) {
-        fr_t a = add(s0, c_pos.rc[r][0]);
-        fr_t b = add(s1, c_pos.rc[r][1]);
-        a = pow5(a);
-        if (r < 4 || r >= 60) b = pow5(b);
-        s0 = add(mul(c_pos.mds[0][0], a), mul(c_pos.mds[0][1], b));
-        s1 = add(mul(c_pos.mds[1][0], a), mul(c_pos.mds[1][1], b));
+    for (int r = 0; r < 4; r++) poseidon_full_round(s0, s1, r);
+#pragma unroll 1
+    for (int r = 0; r < 56; r++) {
+        fr_t a = pow5(add(s0, c_pos.partial[r][0]));
+        fr_t b = add(s1, c_pos.partial[r][1]);
+        s0 = add(mul(c_pos.mds[0][0], a), mul(c_pos.partial[r][2], b));
+        s1 = add(mul(c_pos.partial[r][3], a), b);
     }
+    s1 = mul(s1, c_pos.partial_scale);
+#pragma unroll 1
+    for (int r = 60; r < 64; r++) poseidon_full_round(s0, s1, r);
 }
 
 // ConstantLength<L> sponge, RATE 1: capacity lane starts at L * 2^64

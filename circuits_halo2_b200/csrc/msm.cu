@@ -34,7 +34,10 @@ namespace sb {
 void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_affine[64]);
 
 static const uint32_t INVALID_KEY = 0xffffffffu;
-static const int LK = 16;          // chunk length of reduce levels >= 2
+// chunk length of reduce levels >= 2: these levels are chains of dependent EC additions on few threads, so short chunks (more, smaller
+// levels) finish sooner than long ones; 8 measured best from 2^13 to 2^22 points (SB_MSM_LK overrides)
+static int LK_env() { const char *e = getenv("SB_MSM_LK"); int v = e ? atoi(e) : 8; return (v >= 4 && v <= 64 && v % 4 == 0) ? v : 8; }
+#define LK (LK_env())
 static const int FINAL_MAX = 256;  // slots handled by the final single-CTA level
 
 struct MsmShape {
@@ -690,7 +693,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
         uint32_t m = sh.B, lambda_log = 0;
         int pp = 0;
         for (int level = 0; level < 2 && m > 1024; level++) {
-            const uint32_t sl = level == 0 ? (sh.seg_log ? sh.seg_log : 1) : 3;
+            const uint32_t sl = level == 0 ? (sh.seg_log ? sh.seg_log : 1) : (getenv("SB_MSM_SEG1") ? (uint32_t)atoi(getenv("SB_MSM_SEG1")) : 2u);  // level 1 is latency-bound: segments of 4
             const uint32_t threads = sh.Wb * (m >> sl);
             if (bQ) SB_LAUNCH(ctx, msm_bucket_level_kernel<true>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);
             else SB_LAUNCH(ctx, msm_bucket_level_kernel<false>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);

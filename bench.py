@@ -473,7 +473,10 @@ def main():
     batched = None
     if args.batch_k:
         bk, nb_proofs = args.batch_k, args.batch_proofs
-        fx = np.load(os.path.join(ROOT, "tests", "golden", "mst_inclusion_assignment.npz"))
+        # the circuit of configs[4]: MstInclusionCircuit<20, 2, 8> (a tree of 2^20 users), minimum k = 13; tests/golden/make_assignment_l20.py
+        l20 = os.path.join(ROOT, "tests", "golden", "mst_inclusion_assignment_l20.npz")
+        use_l20 = bk >= 13 and os.path.exists(l20)
+        fx = np.load(l20 if use_l20 else os.path.join(ROOT, "tests", "golden", "mst_inclusion_assignment.npz"))
         cs_text = open(os.path.join(ROOT, "tests", "golden", "mst_inclusion_cs.json")).read()
         kzg = sb.ParamsKZG.setup(bk, 0x5A110000 + bk, ctx, download=False)
         pkey = sb.ProvingKey.from_sparse(kzg, cs_text, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234, ctx)
@@ -482,6 +485,11 @@ def main():
         insts = [fields_mod.fr_from_mont(v) for v in fx["instances"]]
         jobs = [(insts, adv_np, sb.seed_from_u64(1000 * rank + j), sb.TRANSCRIPT_KECCAK) for j in range(nb_proofs)]
         first = sb.create_proof(pkey, *jobs[0])
+        if args.dump_proof and rank == 0:
+            os.makedirs(args.dump_proof, exist_ok=True)
+            fcom, scom = pkey.commitments()
+            np.savez(os.path.join(args.dump_proof, f"proof_batch_k{bk}.npz"), proof=np.frombuffer(first, dtype=np.uint8), fixed_comms=fcom, sigma_comms=scom,
+                     instances=fx["instances"], k=np.array([bk]), transcript_repr=np.array([0x1234]))
         sweep = {}
         for workers in [int(x) for x in args.batch_workers.split(",") if x]:
             bp = sb.BatchProver(pkey, workers)
@@ -499,7 +507,8 @@ def main():
             sweep[str(workers)] = world * nb_proofs / dt
             bp.close()
         batched = {"k": bk, "proofs_per_rank": nb_proofs, "n_gpus": world, "proofs_per_s_by_workers_per_gpu": sweep, "best_proofs_per_s": max(sweep.values()),
-                   "host_cores": os.cpu_count(), "circuit": "MstInclusionCircuit<4,2,8> witness of entry_16.csv user 0, one ChaCha20 seed per proof",
+                   "host_cores": os.cpu_count(), "circuit": ("MstInclusionCircuit<20,2,8> (LEVELS = 20: a 2^20-user tree), one witness, one ChaCha20 seed per proof" if use_l20
+                               else "MstInclusionCircuit<4,2,8> witness of entry_16.csv user 0, one ChaCha20 seed per proof"),
                    "timing": "wall clock over the whole batch, barrier + synchronize on both sides, max over ranks"}
         del pkey, kzg
 

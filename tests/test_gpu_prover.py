@@ -313,3 +313,32 @@ def test_new_entry_points_reject_bad_arguments(ctx, golden_dir):
     assert t.depth() == 0 and t.root().balances == [5] and t.root().hash == M.poseidon_hash(M.Entry("solo", [5]).preimage())
     p = t.generate_proof(0)
     assert p.path_indices == [] and p.sibling_middle_node_hash_preimages == []
+
+
+def test_levels_20_circuit_fixture_proof_equals_oracle(ctx, golden_dir):
+    """BASELINE configs[4]'s circuit, MstInclusionCircuit<20, 2, 8> at its minimum k = 13 (fixture of tests/golden/make_assignment_l20.py: one
+    fabricated Merkle path of a 2^20-leaf tree): key from the sparse fixture, proof byte-identical to the oracle prover's over the same SRS."""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import fields
+    k, n = 13, 1 << 13
+    fx = np.load(os.path.join(golden_dir, "mst_inclusion_assignment_l20.npz"))
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    assert int(fx["rows_used"][0]) <= n - 6
+    params = sb.ParamsKZG.setup(k, 0x5A110000 + k, ctx)
+    pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234, ctx)
+    advice = np.zeros((3, n, 4), dtype=np.uint64)
+    advice[fx["advice_cells"][:, 0], fx["advice_cells"][:, 1]] = fx["advice_values"]
+    instances = [fields.fr_from_mont(v) for v in fx["instances"]]
+    got = sb.create_proof(pk, instances, advice, sb.seed_from_u64(20), sb.TRANSCRIPT_KECCAK)
+    # the oracle's key from the same sparse data (dense columns rebuilt on the host)
+    fixed = np.zeros((cs["num_fixed_columns"], n, 4), dtype=np.uint64)
+    fixed[fx["fixed_cells"][:, 0], fx["fixed_cells"][:, 1]] = fx["fixed_values"]
+    ncols = len(cs["permutation_columns"])
+    mapping = [[(c, r) for r in range(n)] for c in range(ncols)]
+    for c, r, tc, tr in fx["perm_cells"]:
+        mapping[int(c)][int(r)] = (int(tc), int(tr))
+    oparams = HP.Params(k, params.g, params.g_lagrange, threads=8)
+    opk = HP.ProvingKey(oparams, cs, fixed, mapping, transcript_repr=0x1234)
+    tr = KeccakTranscript()
+    HP.create_proof(oparams, opk, instances, advice, ChaCha20Rng.seed_from_u64(20), tr)
+    assert got == tr.finalize()

@@ -73,14 +73,20 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
         const uint32_t piece = (uint32_t)(gi / n);
         const uint64_t i = gi - (uint64_t)piece * n;
         uint32_t s[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) s[q] = 0;
+        bool nonzero = false;
         if (live) {
-            fr_t x = from_mont(load_fp<FrParams>(scalars + 2 * gi));
+            const fr_t raw = load_fp<FrParams>(scalars + 2 * gi);
+            nonzero = !raw.is_zero();  // Montgomery form of zero is zero
+            if (nonzero) {
+                const fr_t x = from_mont(raw);
 #pragma unroll
-            for (int q = 0; q < 8; q++) s[q] = x.v[q];
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) s[q] = 0;
+                for (int q = 0; q < 8; q++) s[q] = x.v[q];
+            }
         }
+        // witness and lookup columns are almost entirely zero: a warp of zero scalars has no digits to count or scatter
+        if (!__any_sync(0xffffffffu, nonzero)) continue;
         uint32_t carry = 0;
         const uint32_t half = 1u << (sh.c - 1);
         for (uint32_t w = 0; w < sh.w_lo + sh.W; w++) {

@@ -156,6 +156,8 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx) {
     SB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SB_CUDA_TRY(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) SB_CUDA_TRY(cudaEventCreateWithFlags(&c->side_ev[i], cudaEventDisableTiming));
     c->pinned_bytes = 1 << 16;
     SB_CUDA_TRY(cudaHostAlloc(&c->pinned, c->pinned_bytes, cudaHostAllocDefault));
     SB_CUDA_TRY(cudaHostAlloc((void **)&c->stage, sb_ctx::STAGE_SLOTS * sb_ctx::STAGE_SLOT_BYTES, cudaHostAllocDefault));
@@ -178,6 +180,9 @@ int32_t sb_ctx_destroy(sb_ctx *ctx) {
             if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
         for (int e = 0; e < 5; e++)
             if (ctx->msm_ev[e]) cudaEventDestroy(ctx->msm_ev[e]);
+        if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+        for (int i = 0; i < 2; i++)
+            if (ctx->side_ev[i]) cudaEventDestroy(ctx->side_ev[i]);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;

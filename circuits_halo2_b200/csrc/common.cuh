@@ -55,6 +55,8 @@ struct sb_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // create_proof: coset NTTs that no challenge is waiting for run here, under the MSM tails
+    cudaEvent_t side_ev[2] = {nullptr, nullptr};
     std::mutex mu;
     uint64_t launches = 0;
     std::map<std::string, sb::Scratch> scratch;

@@ -267,6 +267,9 @@ static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, cu
         // omega_R = omega^(N / R)
         SB_TRY(gen(pl->w_block[t], fr_pow_host(w, 1ull << (log_n - pl->radix[t])), cnt));
     }
+    // the tables are generated on `st` but a plan is used from any stream of the context afterwards (create_proof runs its coset NTTs
+    // on a side stream): make them visible once, here
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
     ctx->ntt_plans[key] = pl;
     *out = pl;
     return SB_OK;
@@ -292,10 +295,10 @@ int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n,
     if (log_n == 0) return SB_OK;
     NttPlan *pl = nullptr;
     SB_TRY(plan_get(ctx, omega, log_n, st, &pl));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // per device
+    if (ctx->device >= 64 || !attr_set[ctx->device]) {
         SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(TILE_LOG, 0)));
-        attr_set = true;
+        if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     const size_t bytes = (size_t)32 << log_n;
     void *d_tmp = nullptr;

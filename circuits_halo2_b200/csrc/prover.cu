@@ -783,6 +783,26 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         t_prev = now;
     };
     for (int i = 0; i < 12; i++) ctx->last_proof_stage_ms[i] = 0;
+    // Side stream: coeff_to_extended of the per-proof polynomials depends on no later challenge, so it is enqueued as soon as a
+    // polynomial exists and runs under the latency-bound tails of the commitments on the main stream; joined before evaluate_h.
+    const bool use_side = !comm && ctx->side_stream && st == ctx->stream && !getenv("SB_NO_SIDE_STREAM");
+    cudaStream_t st2 = use_side ? ctx->side_stream : st;
+    auto side_after_main = [&]() -> int32_t {  // everything enqueued on st so far happens before later work on st2
+        if (!use_side) return SB_OK;
+        SB_CUDA_TRY(cudaEventRecord(ctx->side_ev[0], st));
+        SB_CUDA_TRY(cudaStreamWaitEvent(st2, ctx->side_ev[0], 0));
+        return SB_OK;
+    };
+    auto main_after_side = [&]() -> int32_t {
+        if (!use_side) return SB_OK;
+        SB_CUDA_TRY(cudaEventRecord(ctx->side_ev[1], st2));
+        SB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->side_ev[1], 0));
+        return SB_OK;
+    };
+    struct SideJoin {  // an early return must not leave side work in flight on buffers the next call reuses
+        cudaStream_t s; bool on;
+        ~SideJoin() { if (on) cudaStreamSynchronize(s); }
+    } side_join{st2, use_side};
 
     // ---- transcript preamble
     tr.common_scalar(pk->transcript_repr);
@@ -831,6 +851,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     for (int c = 0; c < A; c++) {
         SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
+    }
+    if (!comm) {  // advice / instance cosets on the side stream, under the commitment below
+        SB_TRY(side_after_main());
+        for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st2));
+        SB_TRY(dom_c2e(ctx, d, d_inst_poly, d_inst_coset, st2));
     }
     {
         std::vector<uint8_t> pts((size_t)A * 64);
@@ -881,6 +906,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
         (void)rng.next_fr();
+        if (!comm) {
+            SB_TRY(side_after_main());
+            SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st2));
+            SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st2));
+        }
         uint8_t pin_tab[128];
         SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, L.p_in, n, 2, pin_tab, st));  // p_in and p_tab are adjacent in the lookup scratch block
         if (!tr.write_point(pin_tab) || !tr.write_point(pin_tab + 64)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
@@ -956,22 +986,27 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             SB_TRY(upload_frs(ctx, d_zall + ((size_t)z * n + (n - bf)) * 32, blind, st));
             (void)rng.next_fr();
         }
-        std::vector<uint8_t> pts((size_t)n_z * 64);
-        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, d_zall, n, (uint32_t)n_z, pts.data(), st));
+        // coefficient and coset forms of every Z on the side stream (sharded proving: coefficient form only), under the batched commitment
+        SB_TRY(side_after_main());
         for (int s = 0; s < n_sets; s++) {
             PermSet &S = psets[s];
-            SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st));
-            SB_TRY(dom_l2c(ctx, d, S.z_poly, st));
-            if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st));
-            if (!tr.write_point(pts.data() + (size_t)s * 64)) { set_last_error("permutation product commitment is the identity"); return SB_ERR_ARG; }
+            SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
+            SB_TRY(dom_l2c(ctx, d, S.z_poly, st2));
+            if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st2));
         }
-        mark();  // [2] permutation + lookup products: ratios, batch inversion, scans, ONE batched commitment, permutation iNTT + coset NTT
         for (size_t li = 0; li < lks.size(); li++) {
             LookupState &L = lks[li];
-            SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st));
-            SB_TRY(dom_l2c(ctx, d, L.z_poly, st));
-            if (!tr.write_point(pts.data() + (size_t)(n_sets + (int)li) * 64)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
+            SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
+            SB_TRY(dom_l2c(ctx, d, L.z_poly, st2));
+            if (!comm) SB_TRY(dom_c2e(ctx, d, L.z_poly, L.z_coset, st2));
         }
+        std::vector<uint8_t> pts((size_t)n_z * 64);
+        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, d_zall, n, (uint32_t)n_z, pts.data(), st));
+        for (int s = 0; s < n_sets; s++)
+            if (!tr.write_point(pts.data() + (size_t)s * 64)) { set_last_error("permutation product commitment is the identity"); return SB_ERR_ARG; }
+        mark();  // [2] permutation + lookup products: ratios, batch inversion, scans, ONE batched commitment (iNTTs / coset NTTs on the side stream)
+        for (size_t li = 0; li < lks.size(); li++)
+            if (!tr.write_point(pts.data() + (size_t)(n_sets + (int)li) * 64)) { set_last_error("lookup product commitment is the identity"); return SB_ERR_ARG; }
     }
 
     mark();  // [3] lookup product
@@ -991,16 +1026,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     const Fr yy = tr.squeeze();
     mark();  // [4] random polynomial (ChaCha20 on the device) + commitment
 
-    // ---- evaluate_h: one fused program over the extended coset
-    if (!comm) {
-    for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st));
-    SB_TRY(dom_c2e(ctx, d, d_inst_poly, d_inst_coset, st));
-    for (LookupState &L : lks) {
-        SB_TRY(dom_c2e(ctx, d, L.z_poly, L.z_coset, st));
-        SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st));
-        SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st));
-    }
-    }
+    // ---- evaluate_h: one fused program over the extended coset; first join the side stream (all coset forms)
+    SB_TRY(main_after_side());
     mark();  // [5] coeff_to_extended of advice / instance / lookup polynomials (sharded: done per owned coset in stage 6)
     const int E_SIGMA = A + F + 1, E_PZ = E_SIGMA + P, E_L0 = E_PZ + n_sets, E_LLAST = E_L0 + 1, E_LACT = E_L0 + 2, E_X = E_L0 + 3, E_LK = E_L0 + 4;
     std::vector<const void *> ecols(E_LK + 3 * lks.size(), nullptr);

@@ -302,7 +302,8 @@ int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n,
     }
     const size_t bytes = (size_t)32 << log_n;
     void *d_tmp = nullptr;
-    if (pl->npass > 1) SB_TRY(scratch_get(ctx, "ntt_tmp", bytes, &d_tmp));
+    // the ping-pong buffer is per stream: create_proof runs coset NTTs on the side stream while the main stream transforms other columns
+    if (pl->npass > 1) SB_TRY(scratch_get(ctx, st == ctx->side_stream ? "ntt_tmp_side" : "ntt_tmp", bytes, &d_tmp));
 
     uint32_t log_a = 0;
     for (int t = 0; t < pl->npass; t++) {

@@ -785,7 +785,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     for (int i = 0; i < 12; i++) ctx->last_proof_stage_ms[i] = 0;
     // Side stream: coeff_to_extended of the per-proof polynomials depends on no later challenge, so it is enqueued as soon as a
     // polynomial exists and runs under the latency-bound tails of the commitments on the main stream; joined before evaluate_h.
-    const bool use_side = !comm && ctx->side_stream && st == ctx->stream && !getenv("SB_NO_SIDE_STREAM");
+    const bool use_side = ctx->side_stream && st == ctx->stream && !getenv("SB_NO_SIDE_STREAM");
     cudaStream_t st2 = use_side ? ctx->side_stream : st;
     auto side_after_main = [&]() -> int32_t {  // everything enqueued on st so far happens before later work on st2
         if (!use_side) return SB_OK;
@@ -803,6 +803,19 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         cudaStream_t s; bool on;
         ~SideJoin() { if (on) cudaStreamSynchronize(s); }
     } side_join{st2, use_side};
+    // Sharded proving: this rank's cosets of the extended domain and the slab that receives the per-proof polynomials' values on them
+    // (index [local coset][polynomial][row]); polynomial order: advice | instance | permutation Z | per lookup (Z, A', S')
+    const int n_sets_all = (P + (cs.degree - 2) - 1) / (cs.degree - 2);
+    const uint32_t n_cosets = 1u << rs_log;
+    const uint32_t co_per = comm ? n_cosets / (uint32_t)comm->world : 0, co_lo = comm ? (uint32_t)comm->rank * co_per : 0;
+    const size_t n_dyn = (size_t)A + 1 + (size_t)n_sets_all + 3 * cs.lookups.size();
+    uint8_t *d_dyn = nullptr;
+    if (comm) SB_TRY(scratch_get(ctx, "pf_coset_dyn", (size_t)co_per * n_dyn * n * 32, (void **)&d_dyn));
+    auto dyn_slot = [&](uint32_t jl, size_t q) -> void * { return d_dyn + ((size_t)jl * n_dyn + q) * n * 32; };
+    auto side_cosets = [&](size_t q, const void *d_coeff) -> int32_t {  // values of one polynomial on every owned coset, on the side stream
+        for (uint32_t jl = 0; jl < co_per; jl++) SB_TRY(coset_values(ctx, pk, d_coeff, co_lo + jl, dyn_slot(jl, q), st2));
+        return SB_OK;
+    };
 
     // ---- transcript preamble
     tr.common_scalar(pk->transcript_repr);
@@ -852,10 +865,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
     }
-    if (!comm) {  // advice / instance cosets on the side stream, under the commitment below
-        SB_TRY(side_after_main());
+    SB_TRY(side_after_main());  // advice / instance cosets on the side stream, under the commitment below
+    if (!comm) {
         for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st2));
         SB_TRY(dom_c2e(ctx, d, d_inst_poly, d_inst_coset, st2));
+    } else {
+        for (int c = 0; c < A; c++) SB_TRY(side_cosets((size_t)c, adv_poly[c]));
+        SB_TRY(side_cosets((size_t)A, d_inst_poly));
     }
     {
         std::vector<uint8_t> pts((size_t)A * 64);
@@ -906,10 +922,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
         SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
         (void)rng.next_fr();
+        SB_TRY(side_after_main());
         if (!comm) {
-            SB_TRY(side_after_main());
             SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st2));
             SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st2));
+        } else {
+            SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 1, L.in_poly));
+            SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 2, L.tab_poly));
         }
         uint8_t pin_tab[128];
         SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, L.p_in, n, 2, pin_tab, st));  // p_in and p_tab are adjacent in the lookup scratch block
@@ -993,12 +1012,14 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
             SB_TRY(dom_l2c(ctx, d, S.z_poly, st2));
             if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st2));
+            else SB_TRY(side_cosets((size_t)A + 1 + s, S.z_poly));
         }
         for (size_t li = 0; li < lks.size(); li++) {
             LookupState &L = lks[li];
             SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
             SB_TRY(dom_l2c(ctx, d, L.z_poly, st2));
             if (!comm) SB_TRY(dom_c2e(ctx, d, L.z_poly, L.z_coset, st2));
+            else SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li, L.z_poly));
         }
         std::vector<uint8_t> pts((size_t)n_z * 64);
         SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, d_zall, n, (uint32_t)n_z, pts.data(), st));
@@ -1065,30 +1086,28 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         if (!comm) {
             SB_TRY(expr_eval(ctx, hp, ecols, pk->ext_k, rs_log, d_h, st));
         } else {
-            // coset-sharded: this rank owns cosets [rank * per, (rank + 1) * per) of the 2^rs_log cosets
-            const uint32_t n_cosets = 1u << rs_log, W = (uint32_t)comm->world, per = n_cosets / W;
-            // per-proof polynomials whose coset values are computed here: advice, instance, permutation Z, lookup (Z, A', S')
-            std::vector<std::pair<int, const void *>> dyn;  // (ecols index, coefficient form)
-            for (int c = 0; c < A; c++) dyn.push_back({c, adv_poly[c]});
-            dyn.push_back({A + F, d_inst_poly});
-            for (int s2 = 0; s2 < n_sets; s2++) dyn.push_back({E_PZ + s2, psets[s2].z_poly});
+            // coset-sharded: this rank owns cosets [rank * per, (rank + 1) * per) of the 2^rs_log cosets; the per-proof polynomials' values on
+            // them were computed on the side stream as the polynomials appeared (slab d_dyn), the key's columns are read in place at stride 8
+            const uint32_t W = (uint32_t)comm->world, per = co_per;
+            std::vector<int> dyn_col;  // ecols index of polynomial q
+            for (int c = 0; c < A; c++) dyn_col.push_back(c);
+            dyn_col.push_back(A + F);
+            for (int s2 = 0; s2 < n_sets; s2++) dyn_col.push_back(E_PZ + s2);
             for (size_t li = 0; li < lks.size(); li++) {
-                dyn.push_back({E_LK + 3 * (int)li, lks[li].z_poly});
-                dyn.push_back({E_LK + 3 * (int)li + 1, lks[li].in_poly});
-                dyn.push_back({E_LK + 3 * (int)li + 2, lks[li].tab_poly});
+                dyn_col.push_back(E_LK + 3 * (int)li);
+                dyn_col.push_back(E_LK + 3 * (int)li + 1);
+                dyn_col.push_back(E_LK + 3 * (int)li + 2);
             }
-            uint8_t *d_dyn, *d_hcm;
-            SB_TRY(scratch_get(ctx, "pf_coset_dyn", dyn.size() * n * 32, (void **)&d_dyn));
+            uint8_t *d_hcm;
             SB_TRY(scratch_get(ctx, "pf_h_cm", en * 32, (void **)&d_hcm));
             std::vector<const void *> ccols(ecols.size(), nullptr);
             std::vector<uint8_t> shifts(ecols.size(), (uint8_t)rs_log);
-            for (uint32_t j = comm->rank * per; j < (comm->rank + 1) * per; j++) {
+            for (uint32_t jl = 0; jl < per; jl++) {
+                const uint32_t j = co_lo + jl;
                 for (size_t c = 0; c < ecols.size(); c++) ccols[c] = ecols[c] ? (const uint8_t *)ecols[c] + (size_t)j * 32 : nullptr;
-                for (size_t q = 0; q < dyn.size(); q++) {
-                    void *dst = d_dyn + q * n * 32;
-                    SB_TRY(coset_values(ctx, pk, dyn[q].second, j, dst, st));
-                    ccols[dyn[q].first] = dst;
-                    shifts[dyn[q].first] = 0;
+                for (size_t q = 0; q < dyn_col.size(); q++) {
+                    ccols[dyn_col[q]] = dyn_slot(jl, q);
+                    shifts[dyn_col[q]] = 0;
                 }
                 SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, d_hcm + (size_t)j * n * 32, st, &shifts));
             }

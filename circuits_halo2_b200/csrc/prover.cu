@@ -947,21 +947,18 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     std::vector<PermSet> psets(n_sets);
     {
         const int n_z = n_sets + (int)lks.size();
-        void *d_den, *d_num;
-        uint8_t *d_zall;
-        SB_TRY(scratch_get(ctx, "pf_perm_den", n * 32, &d_den));
-        SB_TRY(scratch_get(ctx, "pf_perm_num", n * 32, &d_num));
+        uint8_t *d_den, *d_num, *d_zall;
+        SB_TRY(scratch_get(ctx, "pf_perm_den", (size_t)n_z * n * 32, (void **)&d_den));
+        SB_TRY(scratch_get(ctx, "pf_perm_num", (size_t)n_z * n * 32, (void **)&d_num));
         SB_TRY(scratch_get(ctx, "pf_z_all", (size_t)n_z * n * 32, (void **)&d_zall));
         uint8_t *zb;
         SB_TRY(scratch_get(ctx, "pf_perm_polys", (size_t)n_sets * (n + en) * 32, (void **)&zb));
         Fr delta_pow = hfr::ONE;
         const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
-        auto ratio_scan = [&](ExprP den, ExprP num, void *d_z) -> int32_t {
-            SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den, st));
-            SB_TRY(expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num, st));
-            SB_TRY(fr_batch_invert(ctx, d_den, n, st));
-            SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, n, st));
-            return fr_running_product(ctx, d_den, n, fr_t::one(), d_z, n, st);
+        // numerators and denominators of every grand product side by side, then ONE batch inversion and ONE product pass for all of them
+        auto ratio_terms = [&](ExprP den, ExprP num, int z) -> int32_t {
+            SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den + (size_t)z * n * 32, st));
+            return expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num + (size_t)z * n * 32, st);
         };
         for (int s = 0; s < n_sets; s++) {
             PermSet &S = psets[s];
@@ -979,15 +976,18 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
                 num = num ? e_mul(num, nterm) : nterm;
                 delta_pow = hfr::mul(delta_pow, DELTA);
             }
-            SB_TRY(ratio_scan(den, num, d_zall + (size_t)s * n * 32));
+            SB_TRY(ratio_terms(den, num, s));
         }
         for (size_t li = 0; li < lks.size(); li++) {
             LookupState &L = lks[li];
             lcols[L_LK + 0] = L.c_in; lcols[L_LK + 1] = L.c_tab; lcols[L_LK + 2] = L.p_in; lcols[L_LK + 3] = L.p_tab;
             ExprP den = e_mul(e_add(e_col(L_LK + 2, 0), ec(beta)), e_add(e_col(L_LK + 3, 0), ec(gamma)));
             ExprP num = e_mul(e_add(e_col(L_LK + 0, 0), ec(beta)), e_add(e_col(L_LK + 1, 0), ec(gamma)));
-            SB_TRY(ratio_scan(den, num, d_zall + (size_t)(n_sets + (int)li) * n * 32));
+            SB_TRY(ratio_terms(den, num, n_sets + (int)li));
         }
+        SB_TRY(fr_batch_invert(ctx, d_den, (size_t)n_z * n, st));
+        SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, (size_t)n_z * n, st));
+        for (int z = 0; z < n_z; z++) SB_TRY(fr_running_product(ctx, d_den + (size_t)z * n * 32, n, fr_t::one(), d_zall + (size_t)z * n * 32, n, st));
         // boundary values of the un-chained permutation products, one read-back
         std::vector<Fr> local_last(n_sets);
         for (int s = 0; s + 1 < n_sets; s++)

@@ -209,9 +209,11 @@ struct Blake2bTranscript : Transcript {
 Fr fpow(const Fr &b, uint64_t e) { return hfr::pow_u64(b, e); }
 Fr rotate(const Fr &x, const Fr &omega, const Fr &omega_inv, int r) { return r >= 0 ? hfr::mul(x, fpow(omega, (uint64_t)r)) : hfr::mul(x, fpow(omega_inv, (uint64_t)(-r))); }
 
-std::vector<Fr> lagrange_interpolate(const std::vector<Fr> &pts, const std::vector<Fr> &evals) {
+// Lagrange basis of a point set as coefficient vectors: basis[j](pts[k]) = [j == k].  One field inversion per point (host inversions are
+// Fermat powers, ~15 us each), shared by every polynomial opened at this set.
+std::vector<std::vector<Fr>> lagrange_basis(const std::vector<Fr> &pts) {
     const size_t n = pts.size();
-    std::vector<Fr> out(n, hfr::ZERO);
+    std::vector<std::vector<Fr>> basis(n);
     for (size_t j = 0; j < n; j++) {
         std::vector<Fr> num(1, hfr::ONE);
         Fr den = hfr::ONE;
@@ -225,9 +227,19 @@ std::vector<Fr> lagrange_interpolate(const std::vector<Fr> &pts, const std::vect
             num.swap(nxt);
             den = hfr::mul(den, hfr::sub(pts[j], pts[k]));
         }
-        Fr s = hfr::mul(evals[j], hfr::inv(den));
-        for (size_t i = 0; i < num.size(); i++) out[i] = hfr::add(out[i], hfr::mul(num[i], s));
+        if (n > 1) {
+            const Fr dinv = hfr::inv(den);
+            for (Fr &c : num) c = hfr::mul(c, dinv);
+        }
+        basis[j] = num;
     }
+    return basis;
+}
+std::vector<Fr> lagrange_interpolate(const std::vector<std::vector<Fr>> &basis, const std::vector<Fr> &evals) {
+    const size_t n = basis.size();
+    std::vector<Fr> out(n, hfr::ZERO);
+    for (size_t j = 0; j < n; j++)
+        for (size_t i = 0; i < basis[j].size(); i++) out[i] = hfr::add(out[i], hfr::mul(basis[j][i], evals[j]));
     return out;
 }
 Fr eval_small(const std::vector<Fr> &c, const Fr &x) {
@@ -481,11 +493,12 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         std::vector<Fr> head(s.pts.size(), hfr::ZERO);
         std::vector<const void *> lc_polys;
         std::vector<fr_t> lc_coeffs;
+        const std::vector<std::vector<Fr>> basis = lagrange_basis(s.pts);
         for (size_t mi = 0; mi < s.members.size(); mi++) {
             const int pid = s.members[mi];
             std::vector<Fr> evs;
             for (const Fr &p : s.pts) evs.push_back(find_eval(pid, p));
-            std::vector<Fr> r = lagrange_interpolate(s.pts, evs);
+            std::vector<Fr> r = lagrange_interpolate(basis, evs);
             low[si].push_back(r);
             for (size_t i = 0; i < r.size(); i++) head[i] = hfr::add(head[i], hfr::mul(r[i], y_pow));
             lc_polys.push_back(polys[pid]);

@@ -366,6 +366,61 @@ __global__ void __launch_bounds__(FINAL_MAX) msm_reduce_final_kernel(const uint3
     if (tid < m && (tid == m - 1 || s_keys[tid + 1] != my_key)) store_xyzz(buckets + 8 * (uint64_t)my_key, mine);
 }
 
+// Middle levels with few slots (latency-bound): the same compaction + segmented scan, one CTA per FINAL_MAX slots.  A run that lies strictly
+// inside the CTA's slots is complete (sorted keys: nobody else holds that key) and goes to its bucket; the runs touching the first / last
+// valid slot may continue in the neighbouring CTAs and become this CTA's two partial slots.  8 dependent additions shrink the list 128 x,
+// where the chunked kernel needs 8 dependent additions to shrink it 4 x.
+__global__ void __launch_bounds__(FINAL_MAX) msm_reduce_cta_kernel(const uint32_t *keys, const uint4 *pts_in, uint64_t n_in, uint4 *buckets, uint32_t *keys_out,
+                                                                   uint4 *pts_out) {
+    __shared__ uint32_t s_keys[FINAL_MAX];
+    __shared__ uint4 s_pts[FINAL_MAX * 8];
+    __shared__ uint32_t total;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t g = (uint64_t)blockIdx.x * FINAL_MAX + tid;
+    const uint32_t k = g < n_in ? keys[g] : INVALID_KEY;
+    const uint32_t valid = k != INVALID_KEY;
+    const uint32_t dense = block_exclusive_scan(valid, &total);
+    if (valid) {
+        s_keys[dense] = k;
+        const uint4 *src = pts_in + 8 * g;
+#pragma unroll
+        for (int q = 0; q < 8; q++) s_pts[dense * 8 + q] = src[q];
+    }
+    __syncthreads();
+    const uint32_t m = total;
+    xyzz_t mine = xyzz_t::identity();
+    uint32_t my_key = INVALID_KEY;
+    if (tid < m) {
+        my_key = s_keys[tid];
+        mine = load_xyzz(s_pts + tid * 8);
+    }
+    for (uint32_t d = 1; d < m; d <<= 1) {
+        const bool take = tid < m && tid >= d && s_keys[tid - d] == my_key;
+        xyzz_t other = xyzz_t::identity();
+        if (take) other = load_xyzz(s_pts + (tid - d) * 8);
+        __syncthreads();
+        if (take) {
+            add(mine, other);
+            store_xyzz(s_pts + tid * 8, mine);
+        }
+        __syncthreads();
+    }
+    if (tid < 2) keys_out[2 * (uint64_t)blockIdx.x + tid] = INVALID_KEY;
+    __syncthreads();
+    if (tid < m && (tid == m - 1 || s_keys[tid + 1] != my_key)) {  // tail of a run: it holds the run's sum
+        const bool first_run = my_key == s_keys[0], last_run = tid == m - 1;
+        if (first_run) {
+            keys_out[2 * (uint64_t)blockIdx.x] = my_key;
+            store_xyzz(pts_out + 8 * (2 * (uint64_t)blockIdx.x), mine);
+        } else if (last_run) {
+            keys_out[2 * (uint64_t)blockIdx.x + 1] = my_key;
+            store_xyzz(pts_out + 8 * (2 * (uint64_t)blockIdx.x + 1), mine);
+        } else {
+            store_xyzz(buckets + 8 * (uint64_t)my_key, mine);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ 4: bucket reduction
 // Window sum R = sum_i (i + 1) * B_i over the m = 2^(c-1) buckets of a window, as a hierarchy of running sums with no scalar
 // multiplication: write R = sum_i [Q_i + lambda * i * P_i] (level 0: P = Q = B, lambda = 1).  A segment of S consecutive
@@ -678,9 +733,16 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     uint64_t slots = slots_a;
     uint32_t *kin = d_keys_a, *kout = d_keys_b;
     uint4 *pin = d_pts_a, *pout = d_pts_b;
+    static const uint64_t CTA_SCAN_MAX = 16384;  // below this many slots the levels are latency-bound: one CTA-wide scan per 256 slots
     while (slots > FINAL_MAX) {
-        const uint64_t nch = (slots + LK - 1) / LK;
-        SB_LAUNCH(ctx, msm_reduce_kernel, (unsigned)((nch + 127) / 128), 128, 0, st, kin, (const uint4 *)pin, slots, (uint32_t)LK, d_buckets, kout, pout, nch);
+        uint64_t nch;
+        if (slots <= CTA_SCAN_MAX && !getenv("SB_MSM_NO_CTA_SCAN")) {
+            nch = (slots + FINAL_MAX - 1) / FINAL_MAX;
+            SB_LAUNCH(ctx, msm_reduce_cta_kernel, (unsigned)nch, FINAL_MAX, 0, st, kin, (const uint4 *)pin, slots, d_buckets, kout, pout);
+        } else {
+            nch = (slots + LK - 1) / LK;
+            SB_LAUNCH(ctx, msm_reduce_kernel, (unsigned)((nch + 127) / 128), 128, 0, st, kin, (const uint4 *)pin, slots, (uint32_t)LK, d_buckets, kout, pout, nch);
+        }
         slots = 2 * nch;
         uint32_t *tk = kin; kin = kout; kout = tk;
         uint4 *tp = pin; pin = pout; pout = tp;

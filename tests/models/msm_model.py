@@ -83,6 +83,32 @@ def final_level(grp, keys, pts, buckets):
             buckets[ks[i]] = grp.add(buckets[ks[i]], ps[i])
 
 
+def cta_level(grp, keys, pts, width, buckets):
+    """msm_reduce_cta_kernel: one CTA per `width` slots; compaction + segmented scan; runs strictly inside the CTA's valid slots are complete
+    and go to their bucket, the runs touching its first / last valid slot become its two partial slots."""
+    n = len(keys)
+    nct = (n + width - 1) // width
+    okeys, opts = [INVALID] * (2 * nct), [grp.zero()] * (2 * nct)
+    for b in range(nct):
+        dense = [(k, p) for k, p in zip(keys[b * width:(b + 1) * width], pts[b * width:(b + 1) * width]) if k != INVALID]
+        m = len(dense)
+        i = 0
+        while i < m:
+            j, acc = i, grp.zero()
+            while j < m and dense[j][0] == dense[i][0]:
+                acc = grp.add(acc, dense[j][1])
+                j += 1
+            key = dense[i][0]
+            if key == dense[0][0]:
+                okeys[2 * b], opts[2 * b] = key, acc
+            elif j == m:
+                okeys[2 * b + 1], opts[2 * b + 1] = key, acc
+            else:
+                buckets[key] = grp.add(buckets[key], acc)
+            i = j
+    return okeys, opts
+
+
 def bucket_of(offsets, nb, pos):
     """largest b in [0, nb) with offsets[b] <= pos (msm.cu::bucket_of)"""
     lo, hi = 0, nb
@@ -179,7 +205,7 @@ def bucket_hierarchy(grp, buckets, n_sets, B, seg_log0, finish_at=8):
     return out
 
 
-def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None):
+def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None, cta_scan_max=0):
     """scalars: batch * n values (vector j = scalars[j n:(j+1) n], tables only).  Returns the list of `batch` results (tables), or the
     single result; with a window range [w_lo, w_hi) the partial sum over those windows (tables: already carrying 2^(c w))."""
     n = len(bases)
@@ -231,7 +257,10 @@ def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=Fals
     buckets = [grp.zero()] * nb
     keys, pts = reduce_first(grp, offsets, nb, svals, points, L1, buckets)
     while len(keys) > final_max:
-        keys, pts = reduce_level(grp, keys, pts, LK, buckets)
+        if len(keys) <= cta_scan_max:
+            keys, pts = cta_level(grp, keys, pts, final_max, buckets)
+        else:
+            keys, pts = reduce_level(grp, keys, pts, LK, buckets)
     final_level(grp, keys, pts, buckets)
     wins = bucket_hierarchy(grp, buckets, n_sets, B, seg_log)
     if tables:

@@ -141,7 +141,7 @@ def test_msm_model_tables_batches_and_window_shards():
         for _ in range(batch):
             sc += _scalars(rnd, n, rnd.choice("UZCS"))
         exp = [sum(s * b for s, b in zip(sc[j * n:(j + 1) * n], bs)) % B.R for j in range(batch)]
-        kw = dict(L1=rnd.choice([4, 8]), LK=4, final_max=rnd.choice([4, 16]), seg_log=rnd.choice([1, 2, 3]))
+        kw = dict(L1=rnd.choice([4, 8]), LK=4, final_max=rnd.choice([4, 16]), seg_log=rnd.choice([1, 2, 3]), cta_scan_max=rnd.choice([0, 64, 1 << 20]))
         assert msm_model.msm(g, sc, bs, c, tables=True, batch=batch, **kw) == exp, (trial, "batch")
         W = msm_model.window_count(c)
         world = rnd.choice([2, 4, 8])

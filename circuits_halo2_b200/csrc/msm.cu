@@ -760,7 +760,8 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
         const uint4 *bP = d_buckets, *bQ = nullptr;
         uint32_t m = sh.B, lambda_log = 0;
         int pp = 0;
-        for (int level = 0; level < 2 && m > 1024; level++) {
+        const uint32_t finish_at = getenv("SB_MSM_FINISH_AT") ? (uint32_t)atoi(getenv("SB_MSM_FINISH_AT")) : 16384u;  // below this the level kernels are latency-bound and the finish (double-and-add + CTA tree) is shorter
+        for (int level = 0; level < 2 && m > finish_at; level++) {
             const uint32_t sl = level == 0 ? (sh.seg_log ? sh.seg_log : 1) : (getenv("SB_MSM_SEG1") ? (uint32_t)atoi(getenv("SB_MSM_SEG1")) : 2u);  // level 1 is latency-bound: segments of 4
             const uint32_t threads = sh.Wb * (m >> sl);
             if (bQ) SB_LAUNCH(ctx, msm_bucket_level_kernel<true>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);

@@ -316,8 +316,12 @@ int32_t sb_srs_destroy(sb_srs *srs) {
         cudaFree(srs->d_g);
         cudaFree(srs->d_g_lagrange);
     }
-    for (int b = 0; b < 2; b++)
-        if (srs->tab[b].d_tables && (b == 0 || srs->tab[1].d_tables != srs->tab[0].d_tables)) cudaFree(srs->tab[b].d_tables);
+    if (srs->tab_slab) {
+        cudaFree(srs->tab_slab);
+    } else {
+        for (int b = 0; b < 2; b++)
+            if (srs->tab[b].d_tables && (b == 0 || srs->tab[1].d_tables != srs->tab[0].d_tables)) cudaFree(srs->tab[b].d_tables);
+    }
     delete srs;
     return SB_OK;
 }
@@ -344,6 +348,25 @@ int32_t srs_precompute_impl(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32
         if (const char *env = getenv("SB_TAB_C")) c = (uint32_t)atoi(env);
     }
     std::lock_guard<std::mutex> tab_lock(srs->tab_mu);
+    if (basis_mask == 3 && !srs->tab[0].d_tables && !srs->tab[1].d_tables && srs->d_g_lagrange != srs->d_g) {
+        // both bases at once: one slab, monomial tables first
+        const uint32_t W = (255 + c - 1) / c;
+        const size_t one = ((size_t)W << srs->k) * 64;
+        void *slab = nullptr;
+        if (c >= 11 && c <= 24 && cudaMalloc(&slab, 2 * one) == cudaSuccess) {
+            int32_t rc = msm_tables_build(ctx, srs->d_g, (size_t)1 << srs->k, c, &srs->tab[0], ctx->stream, slab);
+            if (rc == SB_OK) rc = msm_tables_build(ctx, srs->d_g_lagrange, (size_t)1 << srs->k, c, &srs->tab[1], ctx->stream, (uint8_t *)slab + one);
+            if (rc != SB_OK) {
+                cudaFree(slab);
+                srs->tab[0] = MsmTables();
+                srs->tab[1] = MsmTables();
+                return rc;
+            }
+            srs->tab_slab = slab;
+            return SB_OK;
+        }
+        cudaGetLastError();  // fall through to separate allocations (or to the argument check inside the builder)
+    }
     for (int b = 0; b < 2; b++) {
         if (!((basis_mask >> b) & 1) || srs->tab[b].d_tables) continue;
         if (b == 1 && srs->d_g_lagrange == srs->d_g && srs->tab[0].d_tables) { srs->tab[1] = srs->tab[0]; continue; }

@@ -111,7 +111,9 @@ struct MsmTables {
     uint32_t c = 0, W = 0;
     uint64_t stride = 0;
 };
-int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st);
+int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st, void *d_dst = nullptr);
+int32_t msm_run_tables_batch_mixed(sb_ctx *ctx, const MsmTables *t0, const MsmTables *t1, const void *d_scalars, size_t n, uint32_t batch, const uint8_t *basis_of,
+                                   uint8_t *out_affine, cudaStream_t st);
 int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out, cudaStream_t st);
 int32_t msm_run_tables_batch(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, uint8_t *out_affine, cudaStream_t st);
 int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, int32_t w_lo, int32_t w_hi, uint8_t *out,

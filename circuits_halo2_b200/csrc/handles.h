@@ -9,6 +9,7 @@ struct sb_srs {
     bool borrowed = false;  // sb_srs_wrap_dev: the caller owns the device arrays
     // fixed-base window tables per basis (sb_srs_precompute): [0] monomial, [1] Lagrange; d_tables == nullptr -> plain Pippenger
     sb::MsmTables tab[2];
+    void *tab_slab = nullptr;  // both tables in one allocation (monomial first): lets one launch set commit over both bases
     std::mutex tab_mu;  // two keys created concurrently over one SRS build its tables once
 };
 

@@ -48,6 +48,7 @@ struct MsmShape {
     uint32_t w_lo, W_all;  // this launch set covers windows [w_lo, w_lo + W) of the W_all windows of the scalar (window-sharded MSM)
     uint32_t Wb;           // bucket sets: W, or 1 when the bases come from fixed-base window tables (all windows share one set)
     uint32_t batch;        // scalar vectors sharing the bases (tables only): vector j = scalars[j n .. (j+1) n), bucket set j
+    uint32_t piece_off[8]; // table-entry offset of vector j (0, or the distance to the other basis' tables inside one slab)
     uint32_t tab_stride;   // 0, or the table stride: the point for (window w, base i) is tables[w * tab_stride + i] = 2^(c w) * P_i
 };
 
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                 pos = __shfl_sync(0xffffffffu, pos, leader);
                 if (key != INVALID_KEY) {
                     pos += __popc(peers & ((1u << lane) - 1));
-                    svals[pos] = (uint32_t)(sh.tab_stride ? w * sh.tab_stride + i : i) | (neg << 31);
+                    svals[pos] = (uint32_t)(sh.tab_stride ? sh.piece_off[piece & 7] + w * sh.tab_stride + i : i) | (neg << 31);
                 }
             }
         }
@@ -614,7 +615,7 @@ void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W) {
 }
 
 static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out, cudaStream_t st,
-                            uint32_t batch = 1);
+                            uint32_t batch = 1, const uint32_t *piece_off = nullptr);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
     return msm_run_impl(ctx, d_bases, d_scalars, n, 0, -1, nullptr, out_affine, st);
@@ -639,13 +640,15 @@ int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const v
     return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st, batch);
 }
 
-int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st) {
+int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st, void *d_dst) {
     SB_REQUIRE(c >= 11 && c <= 24, "msm tables: window bits must be 11..24");
     const uint32_t W = (255 + c - 1) / c;
     SB_REQUIRE(W <= (uint32_t)TAB_MAX_W && (uint64_t)W * n < (1ull << 31), "msm tables: too many windows / points");
-    void *d_tab = nullptr;
-    cudaError_t e = cudaMalloc(&d_tab, (size_t)W * n * 64);
-    if (e != cudaSuccess) { set_last_error("msm tables: cudaMalloc(%zu): %s", (size_t)W * n * 64, cudaGetErrorString(e)); return SB_ERR_ALLOC; }
+    void *d_tab = d_dst;
+    if (!d_tab) {
+        cudaError_t e = cudaMalloc(&d_tab, (size_t)W * n * 64);
+        if (e != cudaSuccess) { set_last_error("msm tables: cudaMalloc(%zu): %s", (size_t)W * n * 64, cudaGetErrorString(e)); return SB_ERR_ALLOC; }
+    }
     SB_LAUNCH(ctx, msm_table_build_kernel, (unsigned)((n + 127) / 128), 128, 0, st, (const uint4 *)d_bases, (uint64_t)n, (uint64_t)n, c, W, (uint4 *)d_tab);
     SB_CUDA_TRY(cudaStreamSynchronize(st));
     out->d_tables = d_tab;
@@ -671,15 +674,30 @@ int32_t msm_run_tables_batch(sb_ctx *ctx, const MsmTables *tabs, const void *d_s
     return SB_OK;
 }
 
+// a batch whose vectors commit to DIFFERENT bases of one SRS (advice columns over the Lagrange basis + the random polynomial over the monomial
+// basis): both tables live in one slab, a vector's table is selected by an entry offset.  basis_of[j] in {0, 1}; at most 8 vectors.
+int32_t msm_run_tables_batch_mixed(sb_ctx *ctx, const MsmTables *t0, const MsmTables *t1, const void *d_scalars, size_t n, uint32_t batch, const uint8_t *basis_of,
+                                   uint8_t *out_affine, cudaStream_t st) {
+    SB_REQUIRE(t0 && t1 && t0->d_tables && t1->d_tables && t0->c == t1->c && t0->W == t1->W && t0->stride == t1->stride, "mixed batch: the two tables must have one shape");
+    SB_REQUIRE((const uint8_t *)t1->d_tables == (const uint8_t *)t0->d_tables + (size_t)t0->W * t0->stride * 64, "mixed batch: the tables must be adjacent in one slab");
+    SB_REQUIRE(batch >= 1 && batch <= 8 && n <= t0->stride && (uint64_t)t0->W * n * batch < (1ull << 32) - 8 && 2ull * t0->W * t0->stride < (1ull << 31),
+               "mixed batch: too large");
+    uint32_t off[8];
+    for (uint32_t j = 0; j < batch; j++) off[j] = basis_of[j] ? (uint32_t)((uint64_t)t0->W * t0->stride) : 0u;
+    return msm_run_impl(ctx, t0->d_tables, d_scalars, n, 0, -1, t0, out_affine, st, batch, off);
+}
+
 static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out_affine,
-                            cudaStream_t st, uint32_t batch) {
+                            cudaStream_t st, uint32_t batch, const uint32_t *piece_off) {
     if (n == 0) {
         memset(out_affine, 0, w_hi < 0 ? (size_t)64 * batch : (size_t)(tabs ? batch : (uint32_t)(w_hi - w_lo)) * 128);
         return SB_OK;
     }
     SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
     SB_REQUIRE(batch == 1 || tabs, "msm: batches need table bases");
-    const MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs, batch);
+    MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs, batch);
+    SB_REQUIRE(!piece_off || batch <= 8, "msm: at most 8 vectors in a mixed-basis batch");
+    for (uint32_t j = 0; j < 8; j++) sh.piece_off[j] = (piece_off && j < batch) ? piece_off[j] : 0;
     SB_REQUIRE(w_hi < 0 || (uint32_t)w_hi <= sh.W_all, "msm: window range exceeds the scalar");
     SB_REQUIRE(sh.t_max < (1ull << 32), "msm: window count * n must be < 2^32");
     const uint64_t nb = (uint64_t)sh.Wb * sh.B;

@@ -846,9 +846,10 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     SB_CUDA_TRY(cudaMemcpyAsync(d_inst_poly, d_inst, n * 32, cudaMemcpyDeviceToDevice, st));
     SB_TRY(dom_l2c(ctx, d, d_inst_poly, st));
     std::vector<void *> adv(A), adv_poly(A), adv_coset(A);
+    void *d_random_early = nullptr;
     {
         uint8_t *base_v, *base_p, *base_c;
-        SB_TRY(scratch_get(ctx, "pf_adv", (size_t)A * n * 32, (void **)&base_v));
+        SB_TRY(scratch_get(ctx, "pf_adv", (size_t)(A + 1) * n * 32, (void **)&base_v));  // + 1: the vanishing argument's random polynomial (early commitment)
         SB_TRY(scratch_get(ctx, "pf_adv_poly", (size_t)A * n * 32, (void **)&base_p));
         SB_TRY(scratch_get(ctx, "pf_adv_coset", (size_t)A * en * 32, (void **)&base_c));
         for (int c = 0; c < A; c++) {
@@ -856,6 +857,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             adv_poly[c] = base_p + (size_t)c * n * 32;
             adv_coset[c] = base_c + (size_t)c * en * 32;
         }
+        d_random_early = base_v + (size_t)A * n * 32;
         const size_t adv_bytes = (size_t)A * n * 32;
         if (comm && comm->world > 1 && adv_bytes % ((size_t)comm->world * 256) == 0) {
             // every rank holds the same host witness: upload 1 / world of it over PCIe and gather the rest over NVLink
@@ -886,9 +888,34 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         for (int c = 0; c < A; c++) SB_TRY(side_cosets((size_t)c, adv_poly[c]));
         SB_TRY(side_cosets((size_t)A, d_inst_poly));
     }
+    // The vanishing argument's random polynomial depends on no challenge, only on the RNG stream: a CLONE of the RNG is advanced past every
+    // draw that precedes its seed (all data-independent counts), so the polynomial can be generated now and committed in the SAME launch set
+    // as the advice columns (mixed-basis batch: advice over the Lagrange tables, the random polynomial over the monomial tables).  The main
+    // RNG still makes its draws at the usual place, so the proof bytes do not change.
+    uint8_t random_commitment[64];
+    bool random_early = false;
     {
-        std::vector<uint8_t> pts((size_t)A * 64);
-        SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, adv[0], n, (uint32_t)A, pts.data(), st));  // the A columns are contiguous
+        const sb_srs *srs = pk->srs;
+        const bool mixed_ok = !comm && A + 1 <= 8 && srs->tab_slab && srs->tab[0].d_tables && srs->tab[1].d_tables && !getenv("SB_NO_EARLY_RANDOM");
+        std::vector<uint8_t> pts((size_t)(A + 1) * 64);
+        if (mixed_ok) {
+            ChaCha20Rng ahead = rng;
+            const size_t n_z_cols = (size_t)((P + (cs.degree - 2) - 1) / (cs.degree - 2)) + cs.lookups.size();
+            const size_t draws = cs.lookups.size() * (2 * (n - usable) + 2) + n_z_cols * ((size_t)bf + 1);
+            for (size_t q = 0; q < draws; q++) (void)ahead.next_fr();
+            uint8_t seed[32];
+            ahead.fill_bytes(seed, 32);
+            ChaCha20Rng child;
+            child.seed(seed);
+            SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random_early, n, st));
+            std::vector<uint8_t> basis_of((size_t)A + 1, 1);
+            basis_of[A] = 0;
+            SB_TRY(msm_run_tables_batch_mixed(ctx, &srs->tab[0], &srs->tab[1], adv[0], n, (uint32_t)A + 1, basis_of.data(), pts.data(), st));
+            memcpy(random_commitment, pts.data() + (size_t)A * 64, 64);
+            random_early = true;
+        } else {
+            SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, adv[0], n, (uint32_t)A, pts.data(), st));  // the A columns are contiguous
+        }
         for (int c = 0; c < A; c++)
             if (!tr.write_point(pts.data() + (size_t)c * 64)) { set_last_error("advice commitment is the identity"); return SB_ERR_ARG; }
     }
@@ -1050,11 +1077,16 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     {
         uint8_t seed[32];
         rng.fill_bytes(seed, 32);
-        ChaCha20Rng child;
-        child.seed(seed);
-        SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random, n, st));  // coefficient i = keystream block i
         (void)rng.next_fr();
-        SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_random, n, pt, st));
+        if (random_early) {
+            d_random = d_random_early;  // generated and committed with the advice columns (same seed: the clone made the same draws)
+            memcpy(pt, random_commitment, 64);
+        } else {
+            ChaCha20Rng child;
+            child.seed(seed);
+            SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random, n, st));  // coefficient i = keystream block i
+            SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_random, n, pt, st));
+        }
         if (!tr.write_point(pt)) { set_last_error("random polynomial commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr yy = tr.squeeze();

@@ -116,8 +116,9 @@ int32_t msm_run_tables_batch_mixed(sb_ctx *ctx, const MsmTables *t0, const MsmTa
                                    uint8_t *out_affine, cudaStream_t st);
 int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, uint8_t *out, cudaStream_t st);
 int32_t msm_run_tables_batch(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, uint8_t *out_affine, cudaStream_t st);
+// piece_off (optional, <= 8 vectors): table-entry offset per vector inside one slab (mixed-basis batch)
 int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, int32_t w_lo, int32_t w_hi, uint8_t *out,
-                                     cudaStream_t st);
+                                     cudaStream_t st, const uint32_t *piece_off = nullptr);
 // window-sharded MSM (multi-GPU): window bits / count for n points, the XYZZ sums of windows [w_lo, w_hi), and the host Horner fold
 void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W);
 int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint32_t w_lo, uint32_t w_hi, uint8_t *win_out, cudaStream_t st);

@@ -634,10 +634,10 @@ int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars
 }
 // windows [w_lo, w_hi) of `batch` scalar vectors in one launch set: out = batch XYZZ partials (128 B each) that carry their 2^(c w) factors
 int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, int32_t w_lo, int32_t w_hi, uint8_t *out,
-                                     cudaStream_t st) {
+                                     cudaStream_t st, const uint32_t *piece_off) {
     SB_REQUIRE(tabs && tabs->d_tables && n <= tabs->stride && batch >= 1 && w_lo < w_hi, "msm_run_tables_batch_windows: bad arguments");
     SB_REQUIRE((uint64_t)(w_hi - w_lo) * n * batch < (1ull << 32) - 8, "msm_run_tables_batch_windows: batch too large");
-    return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st, batch);
+    return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st, batch, piece_off);
 }
 
 int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st, void *d_dst) {

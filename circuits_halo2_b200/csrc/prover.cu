@@ -753,6 +753,26 @@ int32_t msm_commit_batch(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, in
     return SB_OK;
 }
 
+// mixed-basis batch (vector j over basis basis_of[j] of one table slab): one launch set on a single GPU, window-sharded with one exchange otherwise
+int32_t msm_commit_batch_mixed(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, const void *d_scalars, size_t n, uint32_t m, const uint8_t *basis_of, uint8_t *out,
+                               cudaStream_t st) {
+    const MsmTables *t0 = &srs->tab[0], *t1 = &srs->tab[1];
+    if (!comm || comm->world <= 1) return msm_run_tables_batch_mixed(ctx, t0, t1, d_scalars, n, m, basis_of, out, st);
+    const uint32_t Wd = (uint32_t)comm->world, r = (uint32_t)comm->rank;
+    SB_REQUIRE(m <= 8 && t0->W >= Wd && (uint64_t)t0->W * n * m < (1ull << 32) - 8, "msm_commit_batch_mixed: shape");
+    uint32_t off[8];
+    for (uint32_t j = 0; j < m; j++) off[j] = basis_of[j] ? (uint32_t)((uint64_t)t0->W * t0->stride) : 0u;
+    const uint32_t lo = r * t0->W / Wd, hi = (r + 1) * t0->W / Wd;
+    std::vector<uint8_t> mine((size_t)m * 128), all((size_t)Wd * m * 128), col((size_t)Wd * 128);
+    SB_TRY(msm_run_tables_batch_windows(ctx, t0, d_scalars, n, m, (int32_t)lo, (int32_t)hi, mine.data(), st, off));
+    if (comm->allgather_host(comm->user, mine.data(), all.data(), (size_t)m * 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+    for (uint32_t j = 0; j < m; j++) {
+        for (uint32_t q = 0; q < Wd; q++) memcpy(col.data() + (size_t)q * 128, all.data() + ((size_t)q * m + j) * 128, 128);
+        msm_fold_windows(col.data(), Wd, 0, out + (size_t)j * 64);
+    }
+    return SB_OK;
+}
+
 int32_t pk_coset_pows(sb_ctx *ctx, const sb_pk *pk, uint32_t j, void **out, cudaStream_t st) {
     const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
     if (pk->coset_pows.size() != n_cosets) pk->coset_pows.assign(n_cosets, nullptr);
@@ -896,7 +916,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     bool random_early = false;
     {
         const sb_srs *srs = pk->srs;
-        const bool mixed_ok = !comm && A + 1 <= 8 && srs->tab_slab && srs->tab[0].d_tables && srs->tab[1].d_tables && !getenv("SB_NO_EARLY_RANDOM");
+        const bool shard_ok = !comm || comm->world <= 1 || (srs->tab[0].W >= (uint32_t)comm->world && !getenv("SB_SHARD_MSM_BY_RANGE"));
+        const bool mixed_ok = shard_ok && A + 1 <= 8 && srs->tab_slab && srs->tab[0].d_tables && srs->tab[1].d_tables && !getenv("SB_NO_EARLY_RANDOM");
         std::vector<uint8_t> pts((size_t)(A + 1) * 64);
         if (mixed_ok) {
             ChaCha20Rng ahead = rng;
@@ -910,7 +931,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             SB_TRY(chacha_fr_fill(ctx, child.key, 0, d_random_early, n, st));
             std::vector<uint8_t> basis_of((size_t)A + 1, 1);
             basis_of[A] = 0;
-            SB_TRY(msm_run_tables_batch_mixed(ctx, &srs->tab[0], &srs->tab[1], adv[0], n, (uint32_t)A + 1, basis_of.data(), pts.data(), st));
+            SB_TRY(msm_commit_batch_mixed(ctx, comm, srs, adv[0], n, (uint32_t)A + 1, basis_of.data(), pts.data(), st));
             memcpy(random_commitment, pts.data() + (size_t)A * 64, 64);
             random_early = true;
         } else {

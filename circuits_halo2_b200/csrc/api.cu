@@ -57,6 +57,53 @@ int32_t scratch_get(sb_ctx *ctx, const char *slot, size_t bytes, void **out) {
     return SB_OK;
 }
 
+void ctx_read_env(sb_ctx *ctx) {
+    Tuning &t = ctx->tune;
+    auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    auto getb = [](const char *name) { return getenv(name) != nullptr; };
+    t.tab_c = geti("SB_TAB_C", 0);
+    int lk = geti("SB_MSM_LK", 8);
+    t.msm_lk = (lk >= 4 && lk <= 64 && lk % 4 == 0) ? lk : 8;
+    t.msm_c = geti("SB_MSM_C", 0);
+    t.msm_l1 = geti("SB_MSM_L1", 0);
+    t.msm_seg = geti("SB_MSM_SEG", -1);
+    t.msm_seg1 = geti("SB_MSM_SEG1", 2);
+    t.msm_finish_at = geti("SB_MSM_FINISH_AT", 16384);
+    t.msm_no_cta_scan = getb("SB_MSM_NO_CTA_SCAN");
+    t.shard_msm_by_range = getb("SB_SHARD_MSM_BY_RANGE");
+    t.no_side_stream = getb("SB_NO_SIDE_STREAM");
+    t.no_early_random = getb("SB_NO_EARLY_RANDOM");
+    t.no_hprog_cache = getb("SB_NO_HPROG_CACHE");
+    t.no_tables = getb("SB_NO_TABLES");
+    t.no_smallkey_sort = getb("SB_NO_SMALLKEY_SORT");
+}
+void ctx_retain(sb_ctx *ctx) { ctx->refs.fetch_add(1, std::memory_order_relaxed); }
+void ctx_release(sb_ctx *ctx) {
+    if (ctx->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+    ntt_plans_free(ctx);
+    for (auto &kv : ctx->scratch)
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (int i = 0; i < sb_ctx::STAGE_SLOTS; i++)
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    for (int e = 0; e < 5; e++)
+        if (ctx->msm_ev[e]) cudaEventDestroy(ctx->msm_ev[e]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->side_ev[i]) cudaEventDestroy(ctx->side_ev[i]);
+        if (ctx->h_ev[i]) cudaEventDestroy(ctx->h_ev[i]);
+    }
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    delete ctx;
+}
+
 // ---- integer-roof probes --------------------------------------------------------------------
 template <class P>
 __global__ void bench_field_mul_kernel(uint4 *out, uint32_t iters) {
@@ -143,14 +190,7 @@ int32_t sb_device_count(int32_t *out_count) {
     return SB_OK;
 }
 
-int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx) {
-    if (!out_ctx) return SB_ERR_ARG;
-    *out_ctx = nullptr;
-    int32_t n = 0;
-    SB_TRY(sb_device_count(&n));
-    SB_REQUIRE(device >= 0 && device < n, "sb_ctx_create: device index out of range");
-    SB_CUDA_TRY(cudaSetDevice(device));
-    sb_ctx *c = new sb_ctx();
+static int32_t ctx_init(sb_ctx *c, int32_t device) {
     c->device = device;
     cudaDeviceProp prop;
     SB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -162,30 +202,34 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx) {
     SB_CUDA_TRY(cudaHostAlloc(&c->pinned, c->pinned_bytes, cudaHostAllocDefault));
     SB_CUDA_TRY(cudaHostAlloc((void **)&c->stage, sb_ctx::STAGE_SLOTS * sb_ctx::STAGE_SLOT_BYTES, cudaHostAllocDefault));
     for (int i = 0; i < sb_ctx::STAGE_SLOTS; i++) SB_CUDA_TRY(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    return SB_OK;
+}
+
+int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx) {
+    if (!out_ctx) return SB_ERR_ARG;
+    *out_ctx = nullptr;
+    int32_t n = 0;
+    SB_TRY(sb_device_count(&n));
+    SB_REQUIRE(device >= 0 && device < n, "sb_ctx_create: device index out of range");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    SB_CUDA_TRY(cudaSetDevice(device));
+    sb_ctx *c = new sb_ctx();
+    sb::ctx_read_env(c);
+    const int32_t rc = ctx_init(c, device);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);  // the caller's current device is not ours to change
+    if (rc != SB_OK) {
+        c->device = device;
+        sb::ctx_release(c);  // frees whatever was created before the failing call
+        return rc;
+    }
     *out_ctx = c;
     return SB_OK;
 }
 
 int32_t sb_ctx_destroy(sb_ctx *ctx) {
     if (!ctx) return SB_OK;
-    {
-        Guard g(ctx);
-        cudaStreamSynchronize(ctx->stream);
-        ntt_plans_free(ctx);
-        for (auto &kv : ctx->scratch)
-            if (kv.second.ptr) cudaFree(kv.second.ptr);
-        if (ctx->pinned) cudaFreeHost(ctx->pinned);
-        if (ctx->stage) cudaFreeHost(ctx->stage);
-        for (int i = 0; i < sb_ctx::STAGE_SLOTS; i++)
-            if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
-        for (int e = 0; e < 5; e++)
-            if (ctx->msm_ev[e]) cudaEventDestroy(ctx->msm_ev[e]);
-        if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
-        for (int i = 0; i < 2; i++)
-            if (ctx->side_ev[i]) cudaEventDestroy(ctx->side_ev[i]);
-        cudaStreamDestroy(ctx->stream);
-    }
-    delete ctx;
+    sb::ctx_release(ctx);  // the caller's reference; children created on this context (sb_mst, sb_pk) may still hold theirs
     return SB_OK;
 }
 
@@ -312,6 +356,7 @@ int32_t sb_srs_wrap_dev(sb_ctx *ctx, uint32_t k, const void *d_g, const void *d_
 }
 int32_t sb_srs_destroy(sb_srs *srs) {
     if (!srs) return SB_OK;
+    if (srs->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return SB_OK;
     if (!srs->borrowed) {
         cudaFree(srs->d_g);
         cudaFree(srs->d_g_lagrange);
@@ -345,7 +390,7 @@ int32_t srs_precompute_impl(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32
     uint32_t c = window_bits;
     if (c == 0) {
         c = srs->k <= 20 ? srs->k : (srs->k >= 23 ? 22 : 20);
-        if (const char *env = getenv("SB_TAB_C")) c = (uint32_t)atoi(env);
+        if (ctx->tune.tab_c > 0) c = (uint32_t)ctx->tune.tab_c;
     }
     std::lock_guard<std::mutex> tab_lock(srs->tab_mu);
     if (basis_mask == 3 && !srs->tab[0].d_tables && !srs->tab[1].d_tables && srs->d_g_lagrange != srs->d_g) {
@@ -441,7 +486,11 @@ int32_t sb_domain_create(sb_ctx *ctx, uint32_t j, uint32_t k, sb_domain **out_do
     d->coset_inv[0] = fr_t::one(); d->coset_inv[1] = zeta2; d->coset_inv[2] = zeta;
     // t(X) = X^n - 1 on the extended coset: 2^(ext-k) distinct values, inverted
     d->n_t = 1u << (ext - k);
-    SB_REQUIRE(d->n_t <= 8, "EvaluationDomain: extended_k - k > 3 is not supported");
+    if (d->n_t > 8) {
+        delete d;
+        set_last_error("EvaluationDomain: extended_k - k > 3 is not supported");
+        return SB_ERR_ARG;
+    }
     fr_t cur = fr_pow_host(zeta, 1ull << k);
     fr_t step = fr_pow_host(d->ext_omega, 1ull << k);
     for (uint32_t i = 0; i < d->n_t; i++) {

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -49,9 +50,32 @@ struct Scratch {
 
 struct NttPlan;  // ntt.cu
 
+// Developer knobs (SB_* environment variables), read ONCE by sb_ctx_create: nothing on a per-call path touches the environment.
+struct Tuning {
+    int tab_c = 0;            // SB_TAB_C: window bits of the fixed-base tables (0 = choose from k)
+    int msm_lk = 8;           // SB_MSM_LK: chunk length of MSM reduce levels >= 2
+    int msm_c = 0;            // SB_MSM_C: window bits of the table-free MSM (0 = choose from n)
+    int msm_l1 = 0;           // SB_MSM_L1: chunk length of reduce level 1 (0 = choose)
+    int msm_seg = -1;         // SB_MSM_SEG: log2 segment of the first bucket level (-1 = choose)
+    int msm_seg1 = 2;         // SB_MSM_SEG1: log2 segment of later bucket levels
+    int msm_finish_at = 16384;  // SB_MSM_FINISH_AT: bucket count below which the hierarchy finishes in one step
+    bool msm_no_cta_scan = false;    // SB_MSM_NO_CTA_SCAN
+    bool shard_msm_by_range = false; // SB_SHARD_MSM_BY_RANGE
+    bool no_side_stream = false;     // SB_NO_SIDE_STREAM
+    bool no_early_random = false;    // SB_NO_EARLY_RANDOM
+    bool no_hprog_cache = false;     // SB_NO_HPROG_CACHE
+    bool no_tables = false;          // SB_NO_TABLES
+    bool no_smallkey_sort = false;   // SB_NO_SMALLKEY_SORT
+};
+
 }  // namespace sb
 
 struct sb_ctx {
+    // Lifetime: handles that keep a pointer to their context (sb_mst, sb_pk) hold a reference; sb_ctx_destroy drops the caller's
+    // reference and the context (stream, scratch arena, pinned buffers) is torn down when the LAST holder lets go, so the
+    // destruction order of a context and its children is free (a Rust `Drop` order, Python GC order).
+    std::atomic<int> refs{1};
+    sb::Tuning tune;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -77,6 +101,7 @@ struct sb_ctx {
     float msm_phase_ms[5] = {0, 0, 0, 0, 0};
     uint32_t msm_last_shape[4] = {0, 0, 0, 0};  // c, W, L1, seg_log of the last MSM
     // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
+    cudaEvent_t h_ev[2] = {nullptr, nullptr};
     float last_h_ms = 0;
     uint32_t last_h_program[4] = {0, 0, 0, 0};
     float last_proof_stage_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // prover.cu `mark()` stages
@@ -85,6 +110,9 @@ struct sb_ctx {
 namespace sb {
 
 int32_t scratch_get(sb_ctx *ctx, const char *slot, size_t bytes, void **out);
+void ctx_read_env(sb_ctx *ctx);
+void ctx_retain(sb_ctx *ctx);
+void ctx_release(sb_ctx *ctx);  // frees the context when the last reference goes
 
 // asynchronous upload of a small host buffer through the context's pinned ring (falls back to a synchronous copy when it does not fit)
 int32_t h2d_staged(sb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);

@@ -354,12 +354,6 @@ Program compile_terms(const std::vector<ExprP> &terms, const fr_t *fold) {
             slot_busy[gacc] = false;
             accumulate(operand(K_REG, gacc), false, 0);
         }
-        if (getenv("SB_EXPR_DEBUG")) {
-            int busy = 0;
-            for (bool bsy : slot_busy) busy += bsy;
-            fprintf(stderr, "[expr] unit %zu (factor %d, %zu terms) scheduled at %zu: %zu instr so far, %d busy slots, %zu slots allocated\n", ui, u.factor, u.terms.size(), oi,
-                    p.code.size() / 3, busy, slot_busy.size());
-        }
     }
     p.n_slots = (uint32_t)slot_busy.size();
     p.out_slot = ACC;

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 struct sb_srs {
+    std::atomic<int> refs{1};  // a proving key holds a reference to its SRS: sb_srs_destroy before sb_pk_destroy is legal
     uint32_t k = 0;
     void *d_g = nullptr;
     void *d_g_lagrange = nullptr;

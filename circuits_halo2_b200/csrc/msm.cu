@@ -36,8 +36,7 @@ void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_aff
 static const uint32_t INVALID_KEY = 0xffffffffu;
 // chunk length of reduce levels >= 2: these levels are chains of dependent EC additions on few threads, so short chunks (more, smaller
 // levels) finish sooner than long ones; 8 measured best from 2^13 to 2^22 points (SB_MSM_LK overrides)
-static int LK_env() { const char *e = getenv("SB_MSM_LK"); int v = e ? atoi(e) : 8; return (v >= 4 && v <= 64 && v % 4 == 0) ? v : 8; }
-#define LK (LK_env())
+#define LK (ctx->tune.msm_lk)
 static const int FINAL_MAX = 256;  // slots handled by the final single-CTA level
 
 struct MsmShape {
@@ -577,10 +576,7 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_h
     int c = (int)ilog2_floor(n) - 3;
     if (c < 4) c = 4;
     if (c > 16) c = 16;
-    if (const char *env = getenv("SB_MSM_C")) {
-        int v = atoi(env);
-        if (v >= 2 && v <= 16) c = v;
-    }
+    if (ctx->tune.msm_c >= 2 && ctx->tune.msm_c <= 16) c = ctx->tune.msm_c;
     if (tabs) c = (int)tabs->c;
     sh.c = (uint32_t)c;
     sh.W_all = (255 + sh.c - 1) / sh.c;
@@ -595,16 +591,10 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_h
     const uint64_t want = (uint64_t)ctx->sm_count * 1024;
     uint32_t L1 = 64;
     while (L1 > 8 && sh.t_max / L1 < want) L1 >>= 1;
-    if (const char *env = getenv("SB_MSM_L1")) {
-        int v = atoi(env);
-        if (v >= 4 && v <= 1024 && (v % 4) == 0) L1 = (uint32_t)v;
-    }
+    if (ctx->tune.msm_l1 >= 4 && ctx->tune.msm_l1 <= 1024 && (ctx->tune.msm_l1 % 4) == 0) L1 = (uint32_t)ctx->tune.msm_l1;
     sh.L1 = L1;
     sh.seg_log = sh.c - 1 >= 3 ? 3 : sh.c - 1;
-    if (const char *env = getenv("SB_MSM_SEG")) {
-        int v = atoi(env);
-        if (v >= 0 && v <= (int)sh.c - 1) sh.seg_log = (uint32_t)v;
-    }
+    if (ctx->tune.msm_seg >= 0 && ctx->tune.msm_seg <= (int)sh.c - 1) sh.seg_log = (uint32_t)ctx->tune.msm_seg;
     return sh;
 }
 
@@ -754,7 +744,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     static const uint64_t CTA_SCAN_MAX = 16384;  // below this many slots the levels are latency-bound: one CTA-wide scan per 256 slots
     while (slots > FINAL_MAX) {
         uint64_t nch;
-        if (slots <= CTA_SCAN_MAX && !getenv("SB_MSM_NO_CTA_SCAN")) {
+        if (slots <= CTA_SCAN_MAX && !ctx->tune.msm_no_cta_scan) {
             nch = (slots + FINAL_MAX - 1) / FINAL_MAX;
             SB_LAUNCH(ctx, msm_reduce_cta_kernel, (unsigned)nch, FINAL_MAX, 0, st, kin, (const uint4 *)pin, slots, d_buckets, kout, pout);
         } else {
@@ -778,9 +768,9 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
         const uint4 *bP = d_buckets, *bQ = nullptr;
         uint32_t m = sh.B, lambda_log = 0;
         int pp = 0;
-        const uint32_t finish_at = getenv("SB_MSM_FINISH_AT") ? (uint32_t)atoi(getenv("SB_MSM_FINISH_AT")) : 16384u;  // below this the level kernels are latency-bound and the finish (double-and-add + CTA tree) is shorter
+        const uint32_t finish_at = (uint32_t)ctx->tune.msm_finish_at;  // below this the level kernels are latency-bound and the finish (double-and-add + CTA tree) is shorter
         for (int level = 0; level < 2 && m > finish_at; level++) {
-            const uint32_t sl = level == 0 ? (sh.seg_log ? sh.seg_log : 1) : (getenv("SB_MSM_SEG1") ? (uint32_t)atoi(getenv("SB_MSM_SEG1")) : 2u);  // level 1 is latency-bound: segments of 4
+            const uint32_t sl = level == 0 ? (sh.seg_log ? sh.seg_log : 1) : (uint32_t)ctx->tune.msm_seg1;  // level 1 is latency-bound: segments of 4
             const uint32_t threads = sh.Wb * (m >> sl);
             if (bQ) SB_LAUNCH(ctx, msm_bucket_level_kernel<true>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);
             else SB_LAUNCH(ctx, msm_bucket_level_kernel<false>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, sl, lambda_log, bufP[pp], bufQ[pp]);

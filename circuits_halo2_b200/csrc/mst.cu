@@ -370,6 +370,7 @@ struct sb_mst {
 static int32_t mst_alloc(sb_ctx *ctx, uint32_t depth, uint32_t n_cur, sb_mst **out) {
     sb_mst *m = new sb_mst();
     m->ctx = ctx;
+    ctx_retain(ctx);  // the tree keeps its context alive: sb_ctx_destroy before sb_mst_destroy is legal
     m->depth = depth;
     m->n_cur = n_cur;
     const size_t slots = 2ull << depth;
@@ -382,6 +383,7 @@ static int32_t mst_alloc(sb_ctx *ctx, uint32_t depth, uint32_t n_cur, sb_mst **o
         cudaFree(m->d_bal);
         cudaFree(m->d_uname);
         delete m;
+        ctx_release(ctx);
         return SB_ERR_ALLOC;
     }
     *out = m;
@@ -413,6 +415,9 @@ int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offs
     SB_REQUIRE(n_entries >= 1 && usernames && offsets && balances, "sb_mst_build: empty input");
     SB_REQUIRE(n_currencies >= 1 && n_currencies <= SB_MAX_CUR, "sb_mst_build: n_currencies must be 1..32");
     SB_REQUIRE(n_entries <= (1ull << 30), "sb_mst_build: more than 2^30 entries");
+    // the leaf kernel reads names[offs[i] .. offs[i+1]): a non-monotone array would make that length wrap and fault the device
+    SB_REQUIRE(offsets[0] == 0, "sb_mst_build: offsets[0] must be 0");
+    for (size_t i = 0; i < n_entries; i++) SB_REQUIRE(offsets[i] <= offsets[i + 1], "sb_mst_build: offsets must be non-decreasing");
     CtxGuard g(ctx);
     SB_TRY(poseidon_consts_load(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -495,6 +500,7 @@ int32_t sb_mst_destroy(sb_mst *mst) {
         cudaFree(mst->d_bal);
         cudaFree(mst->d_uname);
     }
+    ctx_release(mst->ctx);
     delete mst;
     return SB_OK;
 }

@@ -311,53 +311,68 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
     const size_t n = pk->n, en = pk->ext_n;
     const sb_domain *d = pk->dom;
     const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
-    const Fr omega = to_host(d->omega);
-    auto to_all_forms = [&](int count, bool is_sigma, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets,
-                            std::vector<uint8_t> &comms) -> int32_t {
-        comms.resize((size_t)count * 64);
+    // omega^i first: the sparse permutation columns are built from it
+    SB_TRY(dalloc(pk, n * 32, &pk->omega_pows));
+    SB_TRY(fr_gen_powers(ctx, pk->omega_pows, d->omega, n, st));
+    auto alloc_forms = [&](int count, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets) -> int32_t {
         for (int c = 0; c < count; c++) {
             void *v, *p, *e;
             SB_TRY(dalloc(pk, n * 32, &v));
             SB_TRY(dalloc(pk, n * 32, &p));
             SB_TRY(dalloc(pk, en * 32, &e));
-            if (!sparse) {
-                const uint8_t *src = (is_sigma ? sigma_values : fixed_values) + (size_t)c * n * 32;
-                SB_CUDA_TRY(cudaMemcpyAsync(v, src, n * 32, cudaMemcpyHostToDevice, st));
-            } else if (!is_sigma) {
-                SB_CUDA_TRY(cudaMemsetAsync(v, 0, n * 32, st));
-                for (size_t i = 0; i < sparse->n_fixed; i++) {
-                    if ((int)sparse->fixed_cells[2 * i] != c) continue;
-                    const size_t row = sparse->fixed_cells[2 * i + 1];
-                    SB_REQUIRE(row < n, "sparse fixed cell row out of range");
-                    SB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)v + row * 32, sparse->fixed_values + i * 32, 32, cudaMemcpyHostToDevice, st));
-                }
-            } else {
-                // identity permutation delta^c * omega^row, then the cells moved by copy constraints
-                SB_TRY(fr_gen_powers(ctx, v, d->omega, n, st));
-                SB_TRY(fr_scale(ctx, v, n, to_dev(hfr::pow_u64(DELTA, (uint64_t)c)), st));
-                std::vector<Fr> patch;
-                std::vector<size_t> rows;
-                for (size_t i = 0; i < sparse->n_perm; i++) {
-                    if ((int)sparse->perm_cells[4 * i] != c) continue;
-                    const size_t row = sparse->perm_cells[4 * i + 1], tc = sparse->perm_cells[4 * i + 2], trow = sparse->perm_cells[4 * i + 3];
-                    SB_REQUIRE(row < n && trow < n && (int)tc < count, "sparse permutation cell out of range");
-                    rows.push_back(row);
-                    patch.push_back(hfr::mul(hfr::pow_u64(DELTA, tc), hfr::pow_u64(omega, trow)));
-                }
-                for (size_t i = 0; i < rows.size(); i++)
-                    SB_CUDA_TRY(cudaMemcpyAsync((uint8_t *)v + rows[i] * 32, &patch[i], 32, cudaMemcpyHostToDevice, st));
-                SB_CUDA_TRY(cudaStreamSynchronize(st));  // `patch` is about to go out of scope
-            }
-            SB_CUDA_TRY(cudaMemcpyAsync(p, v, n * 32, cudaMemcpyDeviceToDevice, st));
-            SB_TRY(dom_l2c(ctx, d, p, st));
-            SB_TRY(dom_c2e(ctx, d, p, e, st));
-            SB_TRY(srs_msm(ctx, pk->srs, 1, v, n, comms.data() + (size_t)c * 64, st));
             vals.push_back(v); polys.push_back(p); cosets.push_back(e);
         }
         return SB_OK;
     };
-    SB_TRY(to_all_forms(pk->cs.F, false, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets, pk->fixed_comms));
-    SB_TRY(to_all_forms(pk->P, true, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets, pk->sigma_comms));
+    SB_TRY(alloc_forms(pk->cs.F, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets));
+    SB_TRY(alloc_forms(pk->P, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets));
+    if (!sparse) {
+        for (int c = 0; c < pk->cs.F; c++) SB_CUDA_TRY(cudaMemcpyAsync(pk->fixed_values[c], fixed_values + (size_t)c * n * 32, n * 32, cudaMemcpyHostToDevice, st));
+        for (int c = 0; c < pk->P; c++) SB_CUDA_TRY(cudaMemcpyAsync(pk->sigma_values[c], sigma_values + (size_t)c * n * 32, n * 32, cudaMemcpyHostToDevice, st));
+    } else {
+        // keygen's sparse output: ONE upload of the cell list and ONE scatter kernel per kind (the k = 20..23 keys have 10^5..10^6 assigned cells)
+        SB_REQUIRE(pk->cs.F <= 32 && pk->P <= 16, "sparse key: at most 32 fixed and 16 permutation columns");
+        for (size_t i = 0; i < sparse->n_fixed; i++)
+            SB_REQUIRE((int)sparse->fixed_cells[2 * i] < pk->cs.F && sparse->fixed_cells[2 * i + 1] < n, "sparse fixed cell out of range");
+        for (size_t i = 0; i < sparse->n_perm; i++)
+            SB_REQUIRE((int)sparse->perm_cells[4 * i] < pk->P && sparse->perm_cells[4 * i + 1] < n && (int)sparse->perm_cells[4 * i + 2] < pk->P && sparse->perm_cells[4 * i + 3] < n,
+                       "sparse permutation cell out of range");
+        void *d_cells, *d_vals;
+        SB_TRY(scratch_get(ctx, "pk_cells", std::max(sparse->n_fixed * 8, sparse->n_perm * 16) + 16, &d_cells));
+        SB_TRY(scratch_get(ctx, "pk_cell_vals", sparse->n_fixed * 32 + 32, &d_vals));
+        for (int c = 0; c < pk->cs.F; c++) SB_CUDA_TRY(cudaMemsetAsync(pk->fixed_values[c], 0, n * 32, st));
+        if (sparse->n_fixed) {
+            SB_CUDA_TRY(cudaMemcpyAsync(d_cells, sparse->fixed_cells, sparse->n_fixed * 8, cudaMemcpyHostToDevice, st));
+            SB_CUDA_TRY(cudaMemcpyAsync(d_vals, sparse->fixed_values, sparse->n_fixed * 32, cudaMemcpyHostToDevice, st));
+            SB_TRY(scatter_cells(ctx, pk->fixed_values.data(), (uint32_t)pk->cs.F, d_cells, d_vals, sparse->n_fixed, st));
+        }
+        // identity permutation delta^c * omega^row, then the cells moved by copy constraints: delta^to_col * omega^to_row
+        std::vector<fr_t> delta_pows(pk->P);
+        Fr dpow = hfr::ONE;
+        for (int c = 0; c < pk->P; c++) {
+            delta_pows[c] = to_dev(dpow);
+            SB_CUDA_TRY(cudaMemcpyAsync(pk->sigma_values[c], pk->omega_pows, n * 32, cudaMemcpyDeviceToDevice, st));
+            if (c) SB_TRY(fr_scale(ctx, pk->sigma_values[c], n, delta_pows[c], st));
+            dpow = hfr::mul(dpow, DELTA);
+        }
+        if (sparse->n_perm) {
+            SB_CUDA_TRY(cudaMemcpyAsync(d_cells, sparse->perm_cells, sparse->n_perm * 16, cudaMemcpyHostToDevice, st));
+            SB_TRY(sigma_patch(ctx, pk->sigma_values.data(), (uint32_t)pk->P, d_cells, sparse->n_perm, pk->omega_pows, delta_pows.data(), st));
+        }
+        SB_CUDA_TRY(cudaStreamSynchronize(st));  // the caller's (pageable) cell arrays are free again
+    }
+    auto derive_forms = [&](int count, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets, std::vector<uint8_t> &comms) -> int32_t {
+        comms.resize((size_t)count * 64);
+        for (int c = 0; c < count; c++) {
+            SB_CUDA_TRY(cudaMemcpyAsync(polys[c], vals[c], n * 32, cudaMemcpyDeviceToDevice, st));
+            SB_TRY(dom_l2c(ctx, d, polys[c], st));
+            SB_TRY(dom_c2e(ctx, d, polys[c], cosets[c], st));
+            SB_TRY(srs_msm(ctx, pk->srs, 1, vals[c], n, comms.data() + (size_t)c * 64, st));
+        }
+        return SB_OK;
+    };
+    SB_TRY(derive_forms(pk->cs.F, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets, pk->fixed_comms));
+    SB_TRY(derive_forms(pk->P, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets, pk->sigma_comms));
     // l_0, l_last, l_blind (Lagrange unit vectors) -> extended; l_active = 1 - (l_last + l_blind)
     const int bf = pk->cs.blinding;
     std::vector<fr_t> tmp(n, fr_t::zero());
@@ -389,8 +404,6 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
     SB_TRY(dalloc(pk, en * 32, &pk->x_coset));
     SB_TRY(fr_gen_powers(ctx, pk->x_coset, d->ext_omega, en, st));
     SB_TRY(fr_scale(ctx, pk->x_coset, en, d->coset[1], st));
-    SB_TRY(dalloc(pk, n * 32, &pk->omega_pows));
-    SB_TRY(fr_gen_powers(ctx, pk->omega_pows, d->omega, n, st));
     SB_TRY(dalloc(pk, n * 32, &pk->div_g_pows));
     SB_TRY(dalloc(pk, n * 32, &pk->div_x));
     SB_TRY(dalloc(pk, n * 32, &pk->div_ginv_scaled));
@@ -699,7 +712,7 @@ int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basi
     uint32_t c, W;
     msm_window_shape(ctx, n, &c, &W);
     if (tabs) { c = tabs->c; W = tabs->W; }
-    if (W >= Wd && getenv("SB_SHARD_MSM_BY_RANGE") == nullptr) {
+    if (W >= Wd && !ctx->tune.shard_msm_by_range) {
         // by signed-digit window: rank r accumulates windows [r W / world, (r + 1) W / world) over ALL bases (level-1 additions, sort and bucket
         // reduction all divide by world).  Plain bases: the W window sums (128 B XYZZ each) meet on the host and are folded by Horner there.
         // Table bases: every rank's partial already carries its 2^(c w) factors, so the host adds world points.
@@ -737,7 +750,7 @@ int32_t msm_commit_batch(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, in
     if (!comm || comm->world <= 1) return srs_msm_batch(ctx, srs, basis, d_scalars, n, m, out, st);
     const MsmTables *tabs = srs->tab[basis].d_tables ? &srs->tab[basis] : nullptr;
     const uint32_t Wd = (uint32_t)comm->world, r = (uint32_t)comm->rank;
-    if (tabs && tabs->W >= Wd && (uint64_t)tabs->W * n * m < (1ull << 32) - 8 && getenv("SB_SHARD_MSM_BY_RANGE") == nullptr) {
+    if (tabs && tabs->W >= Wd && (uint64_t)tabs->W * n * m < (1ull << 32) - 8 && !ctx->tune.shard_msm_by_range) {
         // all m commitments, this rank's windows, ONE launch set and ONE exchange of m XYZZ partials per rank
         const uint32_t lo = r * tabs->W / Wd, hi = (r + 1) * tabs->W / Wd;
         std::vector<uint8_t> mine((size_t)m * 128), all((size_t)Wd * m * 128), col((size_t)Wd * 128);
@@ -795,7 +808,17 @@ int32_t coset_values(sb_ctx *ctx, const sb_pk *pk, const void *d_coeff, uint32_t
     return ntt_run(ctx, d_out, (const uint8_t *)pk->dom->omega.v, pk->k, st);
 }
 
-int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_inst, const uint8_t *advice_host, ChaCha20Rng &rng,
+// where the assigned advice cells come from: dense host columns (A x n x 32 B), dense device columns (left untouched), or the non-zero cells only
+struct Witness {
+    const uint8_t *host = nullptr;
+    const void *dev = nullptr;
+    const uint32_t *cells = nullptr;   // (col, row) pairs
+    const uint8_t *values = nullptr;   // 32 B each
+    size_t n_cells = 0;
+    bool sparse = false;
+};
+
+int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_inst, const Witness &wit, ChaCha20Rng &rng,
                           Transcript &tr, cudaStream_t st) {
     const ConstraintSystem &cs = pk->cs;
     const sb_domain *d = pk->dom;
@@ -818,7 +841,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     for (int i = 0; i < 12; i++) ctx->last_proof_stage_ms[i] = 0;
     // Side stream: coeff_to_extended of the per-proof polynomials depends on no later challenge, so it is enqueued as soon as a
     // polynomial exists and runs under the latency-bound tails of the commitments on the main stream; joined before evaluate_h.
-    const bool use_side = ctx->side_stream && st == ctx->stream && !getenv("SB_NO_SIDE_STREAM");
+    const bool use_side = ctx->side_stream && st == ctx->stream && !ctx->tune.no_side_stream;
     cudaStream_t st2 = use_side ? ctx->side_stream : st;
     auto side_after_main = [&]() -> int32_t {  // everything enqueued on st so far happens before later work on st2
         if (!use_side) return SB_OK;
@@ -879,14 +902,30 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         }
         d_random_early = base_v + (size_t)A * n * 32;
         const size_t adv_bytes = (size_t)A * n * 32;
-        if (comm && comm->world > 1 && adv_bytes % ((size_t)comm->world * 256) == 0) {
+        if (wit.sparse) {
+            // only the assigned cells cross PCIe (a few thousand for MstInclusionCircuit, whatever k is): zero the columns, upload, scatter
+            SB_REQUIRE(A <= 32, "sparse witness: at most 32 advice columns");
+            for (size_t i = 0; i < wit.n_cells; i++)
+                SB_REQUIRE((int)wit.cells[2 * i] < A && wit.cells[2 * i + 1] < n, "sparse witness: cell out of range");
+            void *d_cells, *d_vals;
+            SB_TRY(scratch_get(ctx, "pf_wit_cells", wit.n_cells * 8 + 16, &d_cells));
+            SB_TRY(scratch_get(ctx, "pf_wit_vals", wit.n_cells * 32 + 32, &d_vals));
+            SB_CUDA_TRY(cudaMemsetAsync(base_v, 0, adv_bytes, st));
+            if (wit.n_cells) {
+                SB_CUDA_TRY(cudaMemcpyAsync(d_cells, wit.cells, wit.n_cells * 8, cudaMemcpyHostToDevice, st));
+                SB_CUDA_TRY(cudaMemcpyAsync(d_vals, wit.values, wit.n_cells * 32, cudaMemcpyHostToDevice, st));
+                SB_TRY(scatter_cells(ctx, adv.data(), (uint32_t)A, d_cells, d_vals, wit.n_cells, st));
+            }
+        } else if (wit.dev) {
+            SB_CUDA_TRY(cudaMemcpyAsync(base_v, wit.dev, adv_bytes, cudaMemcpyDeviceToDevice, st));  // the blinding rows are written into the copy
+        } else if (comm && comm->world > 1 && adv_bytes % ((size_t)comm->world * 256) == 0) {
             // every rank holds the same host witness: upload 1 / world of it over PCIe and gather the rest over NVLink
             const size_t per = adv_bytes / (size_t)comm->world, off = per * (size_t)comm->rank;
-            SB_CUDA_TRY(cudaMemcpyAsync(base_v + off, advice_host + off, per, cudaMemcpyHostToDevice, st));
+            SB_CUDA_TRY(cudaMemcpyAsync(base_v + off, wit.host + off, per, cudaMemcpyHostToDevice, st));
             SB_CUDA_TRY(cudaStreamSynchronize(st));
             if (comm->allgather_dev(comm->user, base_v, per, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
         } else {
-            SB_CUDA_TRY(cudaMemcpyAsync(base_v, advice_host, adv_bytes, cudaMemcpyHostToDevice, st));
+            SB_CUDA_TRY(cudaMemcpyAsync(base_v, wit.host, adv_bytes, cudaMemcpyHostToDevice, st));
         }
     }
     // blinding rows, blinds (drawn; KZG ignores them), commitments
@@ -916,8 +955,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     bool random_early = false;
     {
         const sb_srs *srs = pk->srs;
-        const bool shard_ok = !comm || comm->world <= 1 || (srs->tab[0].W >= (uint32_t)comm->world && !getenv("SB_SHARD_MSM_BY_RANGE"));
-        const bool mixed_ok = shard_ok && A + 1 <= 8 && srs->tab_slab && srs->tab[0].d_tables && srs->tab[1].d_tables && !getenv("SB_NO_EARLY_RANDOM");
+        const bool shard_ok = !comm || comm->world <= 1 || (srs->tab[0].W >= (uint32_t)comm->world && !ctx->tune.shard_msm_by_range);
+        const bool mixed_ok = shard_ok && A + 1 <= 8 && srs->tab_slab && srs->tab[0].d_tables && srs->tab[1].d_tables && !ctx->tune.no_early_random;
         std::vector<uint8_t> pts((size_t)(A + 1) * 64);
         if (mixed_ok) {
             ChaCha20Rng ahead = rng;
@@ -1006,7 +1045,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     const int n_sets = (P + chunk - 1) / chunk;
     struct PermSet { void *z_poly, *z_coset; int first, count; };
     std::vector<PermSet> psets(n_sets);
-    {
+    if (n_sets + (int)lks.size() > 0) {  // a circuit with neither copy constraints nor lookups has no grand product to commit
         const int n_z = n_sets + (int)lks.size();
         uint8_t *d_den, *d_num, *d_zall;
         SB_TRY(scratch_get(ctx, "pf_perm_den", (size_t)n_z * n * 32, (void **)&d_den));
@@ -1135,7 +1174,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     SB_TRY(scratch_get(ctx, "pf_h", en * 32, &d_h));
     {
         Program hp;
-        if (getenv("SB_NO_HPROG_CACHE")) {
+        if (ctx->tune.no_hprog_cache) {
             fr_t yd = to_dev(yy);
             hp = compile_terms(h_terms(cs, P, set_ranges, lks.size(), theta, beta, gamma), &yd);
         } else {
@@ -1145,9 +1184,11 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         ctx->last_h_program[1] = hp.n_mul;
         ctx->last_h_program[2] = hp.n_addsub;
         ctx->last_h_program[3] = hp.n_slots;
-        cudaEvent_t e0, e1;
-        SB_CUDA_TRY(cudaEventCreate(&e0));
-        SB_CUDA_TRY(cudaEventCreate(&e1));
+        if (!ctx->h_ev[0]) {  // created once per context: an early SB_TRY return below leaks nothing
+            SB_CUDA_TRY(cudaEventCreate(&ctx->h_ev[0]));
+            SB_CUDA_TRY(cudaEventCreate(&ctx->h_ev[1]));
+        }
+        cudaEvent_t e0 = ctx->h_ev[0], e1 = ctx->h_ev[1];
         SB_CUDA_TRY(cudaEventRecord(e0, st));
         if (!comm) {
             SB_TRY(expr_eval(ctx, hp, ecols, pk->ext_k, rs_log, d_h, st));
@@ -1187,8 +1228,6 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_CUDA_TRY(cudaEventRecord(e1, st));
         SB_CUDA_TRY(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ctx->last_h_ms, e0, e1);
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     }
     mark();  // [6] evaluate_h (fused program)
     // ---- quotient: / t(X), back to coefficients, pieces
@@ -1289,32 +1328,76 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
 
 extern "C" {
 
+static void pk_free(sb_pk *pk) {
+    for (void *p : pk->owned) cudaFree(p);
+    if (pk->dom) sb_domain_destroy(pk->dom);
+    if (pk->srs) sb_srs_destroy(const_cast<sb_srs *>(pk->srs));  // drops the key's reference
+    delete pk;
+}
+
+// every column / rotation an expression tree touches must exist (a bad index would be an out-of-bounds host read later)
+static void validate_expr(const json::Value &e, const ConstraintSystem &cs) {
+    const std::string &k = e[0].as_str();
+    if (k == "const") return;
+    if (k == "advice" || k == "fixed" || k == "instance") {
+        const int c = (int)e[1].as_int(), r = (int)e[2].as_int();
+        const int lim = k == "advice" ? cs.A : k == "fixed" ? cs.F : cs.I;
+        if (c < 0 || c >= lim) throw std::runtime_error("expression: " + k + " column index out of range");
+        if (r < -64 || r > 64) throw std::runtime_error("expression: rotation out of range");
+        return;
+    }
+    if (k == "neg") { validate_expr(e[1], cs); return; }
+    if (k == "add" || k == "sub" || k == "mul") { validate_expr(e[1], cs); validate_expr(e[2], cs); return; }
+    throw std::runtime_error("unknown expression node " + k);
+}
+static void validate_cs(const ConstraintSystem &cs, size_t n) {
+    if (cs.degree < 3) throw std::runtime_error("constraint system: degree must be >= 3 (halo2 clamps cs.degree() to the permutation argument's 3)");
+    if (cs.A < 1 || cs.A > 64 || cs.F < 0 || cs.F > 256) throw std::runtime_error("constraint system: column counts out of range");
+    if (cs.blinding < 0 || (size_t)cs.blinding + 1 >= n) throw std::runtime_error("constraint system: blinding_factors + 1 must be < 2^k");
+    if (cs.n_instances < 0 || (size_t)cs.n_instances > n - (size_t)cs.blinding - 1) throw std::runtime_error("constraint system: num_instances exceeds the usable rows");
+    for (auto &q : cs.advice_q)
+        if (q.first < 0 || q.first >= cs.A || q.second < -64 || q.second > 64) throw std::runtime_error("advice query out of range");
+    for (auto &q : cs.fixed_q)
+        if (q.first < 0 || q.first >= cs.F || q.second < -64 || q.second > 64) throw std::runtime_error("fixed query out of range");
+    for (auto &pc : cs.perm_cols) {
+        const int lim = pc.first == "advice" ? cs.A : pc.first == "fixed" ? cs.F : pc.first == "instance" ? cs.I : -1;
+        if (lim < 0 || pc.second < 0 || pc.second >= lim) throw std::runtime_error("permutation column out of range");
+    }
+    for (auto &g : cs.gates) validate_expr(*g, cs);
+    for (auto &l : cs.lookups) {
+        for (auto &e : l.input) validate_expr(*e, cs);
+        for (auto &e : l.table) validate_expr(*e, cs);
+    }
+}
+
 static int32_t pk_create_common(sb_ctx *ctx, const sb_srs *srs, const char *cs_json, uint32_t k, const uint8_t *fixed_values, const uint8_t *sigma_values,
                                 const SparseAssignment *sparse, const uint8_t transcript_repr[32], sb_pk **out_pk) {
     SB_REQUIRE(srs->k == k, "sb_pk_create: SRS size does not match k (downsize first)");
+    SB_REQUIRE(k >= 7 && k <= 25, "sb_pk_create: k must be in [7, 25]");
     CtxGuard g(ctx);
     sb_pk *pk = new sb_pk();
     try {
         pk->cs = parse_cs(cs_json);
+        validate_cs(pk->cs, (size_t)1 << k);
     } catch (const std::exception &e) {
         set_last_error("sb_pk_create: %s", e.what());
-        delete pk;
+        pk_free(pk);
         return SB_ERR_ARG;
     }
     pk->srs = srs;
+    const_cast<sb_srs *>(srs)->refs.fetch_add(1, std::memory_order_relaxed);
     pk->k = k;
     pk->n = (size_t)1 << k;
     pk->P = (int)pk->cs.perm_cols.size();
     memcpy(pk->transcript_repr.v, transcript_repr, 32);
     int32_t rc = sb_domain_create(ctx, (uint32_t)pk->cs.degree, k, &pk->dom);
-    if (rc != SB_OK) { delete pk; return rc; }
+    if (rc != SB_OK) { pk_free(pk); return rc; }
     pk->ext_k = pk->dom->ext_k;
     pk->ext_n = (size_t)1 << pk->ext_k;
-    if (pk->n < 128) { set_last_error("sb_pk_create: k < 7 is not supported"); sb_domain_destroy(pk->dom); delete pk; return SB_ERR_ARG; }
     // fixed-base window tables for both bases of this key's SRS (the handle is shared and logically const: tables change speed, not results)
-    if (!getenv("SB_NO_TABLES")) {
+    if (!ctx->tune.no_tables) {
         rc = srs_precompute_impl(ctx, const_cast<sb_srs *>(srs), 3, 0);
-        if (rc != SB_OK) { sb_domain_destroy(pk->dom); delete pk; return rc; }
+        if (rc != SB_OK) { pk_free(pk); return rc; }
     }
     try {
         rc = pk_build(ctx, pk, fixed_values, sigma_values, sparse, ctx->stream);
@@ -1323,9 +1406,8 @@ static int32_t pk_create_common(sb_ctx *ctx, const sb_srs *srs, const char *cs_j
         rc = SB_ERR_ARG;
     }
     if (rc != SB_OK) {
-        for (void *p : pk->owned) cudaFree(p);
-        sb_domain_destroy(pk->dom);
-        delete pk;
+        cudaStreamSynchronize(ctx->stream);
+        pk_free(pk);
         return rc;
     }
     *out_pk = pk;
@@ -1349,9 +1431,7 @@ int32_t sb_pk_create_sparse(sb_ctx *ctx, const sb_srs *srs, const char *cs_json,
 
 int32_t sb_pk_destroy(sb_pk *pk) {
     if (!pk) return SB_OK;
-    for (void *p : pk->owned) cudaFree(p);
-    sb_domain_destroy(pk->dom);
-    delete pk;
+    pk_free(pk);
     return SB_OK;
 }
 
@@ -1362,9 +1442,10 @@ int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_
     return SB_OK;
 }
 
-static int32_t create_proof_entry(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
+static int32_t create_proof_entry(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const Witness &wit,
                                   const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
-    if (!ctx || !pk || !advice || !rng_seed || !proof_out || !proof_len || (n_instances && !instances)) return SB_ERR_ARG;
+    if (!ctx || !pk || !rng_seed || !proof_out || !proof_len || (n_instances && !instances)) return SB_ERR_ARG;
+    if (wit.sparse ? (wit.n_cells && (!wit.cells || !wit.values)) : (!wit.host && !wit.dev)) return SB_ERR_ARG;
     SB_REQUIRE(transcript_kind == 0 || transcript_kind == 1, "transcript_kind must be 0 (Blake2b) or 1 (Keccak256/EVM)");
     if (comm) {
         const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
@@ -1380,7 +1461,7 @@ static int32_t create_proof_entry(sb_ctx *ctx, const sb_pk *pk, const sb_comm *c
     Transcript &tr = transcript_kind == 1 ? (Transcript &)kt : (Transcript &)bt;
     int32_t rc;
     try {
-        rc = create_proof_impl(ctx, pk, comm, instances, n_instances, advice, rng, tr, ctx->stream);
+        rc = create_proof_impl(ctx, pk, comm, instances, n_instances, wit, rng, tr, ctx->stream);
     } catch (const std::exception &e) {
         set_last_error("sb_create_proof: %s", e.what());
         return SB_ERR_ARG;
@@ -1393,12 +1474,40 @@ static int32_t create_proof_entry(sb_ctx *ctx, const sb_pk *pk, const sb_comm *c
 }
 int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
                         int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
-    return create_proof_entry(ctx, pk, nullptr, instances, n_instances, advice, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+    if (!advice) return SB_ERR_ARG;
+    Witness w;
+    w.host = advice;
+    return create_proof_entry(ctx, pk, nullptr, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+}
+int32_t sb_create_proof_dev(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const void *d_advice, const uint8_t rng_seed[32],
+                            int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    if (!d_advice) return SB_ERR_ARG;
+    Witness w;
+    w.dev = d_advice;
+    return create_proof_entry(ctx, pk, nullptr, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+}
+int32_t sb_create_proof_sparse(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells, const uint8_t *advice_cell_values,
+                               size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    Witness w;
+    w.sparse = true;
+    w.cells = advice_cells; w.values = advice_cell_values; w.n_cells = n_cells;
+    return create_proof_entry(ctx, pk, nullptr, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
 }
 int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
                                 const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    if (!comm || !advice) return SB_ERR_ARG;
+    Witness w;
+    w.host = advice;
+    return create_proof_entry(ctx, pk, comm, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+}
+int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells,
+                                       const uint8_t *advice_cell_values, size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out,
+                                       size_t proof_cap, size_t *proof_len) {
     if (!comm) return SB_ERR_ARG;
-    return create_proof_entry(ctx, pk, comm, instances, n_instances, advice, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+    Witness w;
+    w.sparse = true;
+    w.cells = advice_cells; w.values = advice_cell_values; w.n_cells = n_cells;
+    return create_proof_entry(ctx, pk, comm, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
 }
 
 // ---- building blocks with host buffers (sb_batch_invert, sb_grand_product, sb_sort_fr, sb_eval_poly, sb_kate_div)

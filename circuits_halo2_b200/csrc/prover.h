@@ -28,6 +28,10 @@ int32_t fr_vanish(sb_ctx *ctx, const void *d_x, const std::vector<fr_t> &roots, 
 int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_inv_d, const void *d_x, const std::vector<fr_t> &comp, const fr_t &scale, size_t n, bool first,
                        cudaStream_t st);
 
+// sparse cells -> dense columns (device copies of the cell / value arrays; indices validated by the caller)
+int32_t scatter_cells(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, const void *d_values, size_t n_cells, cudaStream_t st);
+int32_t sigma_patch(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, size_t n_cells, const void *d_omega_pows, const fr_t *delta_pows, cudaStream_t st);
+
 // ---- expr.cu: expression DAGs compiled to a register program, evaluated over whole columns ---
 struct Expr;
 typedef std::shared_ptr<Expr> ExprP;

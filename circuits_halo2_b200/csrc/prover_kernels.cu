@@ -389,7 +389,7 @@ __global__ void smallkey_expand_kernel(const uint32_t *offsets, uint4 *out, uint
 
 // sorts d_a[0 .. count) ascending as raw 256-bit integers; d_a must have room for the next power of two
 int32_t sort_u256(sb_ctx *ctx, void *d_a, size_t count, size_t capacity_pow2, cudaStream_t st) {
-    if (count >= 4096 && count < (1ull << 32) && !getenv("SB_NO_SMALLKEY_SORT")) {
+    if (count >= 4096 && count < (1ull << 32) && !ctx->tune.no_smallkey_sort) {
         uint32_t *d_hist;
         SB_TRY(scratch_get(ctx, "sort_hist", (SMALLKEY_BINS + 2) * 4, (void **)&d_hist));
         SB_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (SMALLKEY_BINS + 2) * 4, st));
@@ -669,6 +669,44 @@ int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_
     ra.k = (uint32_t)comp.size();
     SB_LAUNCH(ctx, fr_div_combine_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_acc, (const uint4 *)d_f, (const uint4 *)d_inv_d, (const uint4 *)d_x, ra, scale,
               (uint64_t)n, first ? 1 : 0);
+    return SB_OK;
+}
+
+// ---- sparse cells -> dense columns (keygen's fixed cells, the witness' advice cells, the permutation's moved cells) ----
+// cells: (col, row) pairs; column c of the output starts at cols.p[c]; one 32-byte value per cell
+struct ColPtrs { uint4 *p[32]; };
+__global__ void scatter_cells_kernel(ColPtrs cols, const uint32_t *cells, const uint4 *values, uint64_t n_cells) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    uint4 *dst = cols.p[cells[2 * i]] + 2 * (uint64_t)cells[2 * i + 1];
+    dst[0] = values[2 * i];
+    dst[1] = values[2 * i + 1];
+}
+// sigma_col(omega^row) = delta^to_col * omega^to_row for the cells copy constraints moved: (col, row, to_col, to_row) quadruples
+struct DeltaPows { fr_t d[16]; };
+__global__ void sigma_patch_kernel(ColPtrs cols, const uint32_t *cells, uint64_t n_cells, const uint4 *omega_pows, DeltaPows dp) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const uint32_t c = cells[4 * i], row = cells[4 * i + 1], tc = cells[4 * i + 2], trow = cells[4 * i + 3];
+    store_fp(cols.p[c] + 2 * (uint64_t)row, mul(dp.d[tc], load_fp<FrParams>(omega_pows + 2 * (uint64_t)trow)));
+}
+// host validates the indices (column < n_cols <= 32, row < n) before the launch; d_cells / d_values are device copies
+int32_t scatter_cells(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, const void *d_values, size_t n_cells, cudaStream_t st) {
+    if (n_cells == 0) return SB_OK;
+    SB_REQUIRE(n_cols <= 32, "scatter_cells: more than 32 columns");
+    ColPtrs cp;
+    for (uint32_t c = 0; c < 32; c++) cp.p[c] = c < n_cols ? (uint4 *)col_ptrs[c] : nullptr;
+    SB_LAUNCH(ctx, scatter_cells_kernel, (unsigned)((n_cells + 255) / 256), 256, 0, st, cp, (const uint32_t *)d_cells, (const uint4 *)d_values, (uint64_t)n_cells);
+    return SB_OK;
+}
+int32_t sigma_patch(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, size_t n_cells, const void *d_omega_pows, const fr_t *delta_pows, cudaStream_t st) {
+    if (n_cells == 0) return SB_OK;
+    SB_REQUIRE(n_cols <= 16, "sigma_patch: more than 16 permutation columns");
+    ColPtrs cp;
+    DeltaPows dp;
+    for (uint32_t c = 0; c < 32; c++) cp.p[c] = c < n_cols ? (uint4 *)col_ptrs[c] : nullptr;
+    for (uint32_t c = 0; c < 16; c++) dp.d[c] = c < n_cols ? delta_pows[c] : fr_t::zero();
+    SB_LAUNCH(ctx, sigma_patch_kernel, (unsigned)((n_cells + 255) / 256), 256, 0, st, cp, (const uint32_t *)d_cells, (uint64_t)n_cells, (const uint4 *)d_omega_pows, dp);
     return SB_OK;
 }
 

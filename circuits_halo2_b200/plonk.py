@@ -173,6 +173,17 @@ class LocalComm:
         return self._c
 
 
+def _instances_mont(instances) -> np.ndarray:
+    return np.concatenate([fields.fr_to_mont(int(v)) for v in instances]) if len(instances) else np.zeros(0, dtype=np.uint64)
+
+
+def _finish(status: int, what: str, comm, out: np.ndarray, plen) -> bytes:
+    if status != 0 and comm is not None and comm.error is not None:
+        raise comm.error
+    _lib.check(status, what)
+    return out[: plen.value].tobytes()
+
+
 def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, comm=None, ctx: Optional[Context] = None) -> bytes:
     """One circuit instance.  instances: public inputs (python ints); advice: (A, n, 4) uint64 assigned advice columns;
     rng_seed: 32 bytes for ChaCha20Rng::from_seed.  Returns the proof bytes (transcript.finalize()).
@@ -180,7 +191,7 @@ def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: byt
     ctx: run on another context of the key's device (its own stream and scratch; the key is read-only) -- see BatchProver."""
     if len(rng_seed) != 32:
         raise AssertionError("rng_seed must be 32 bytes")
-    inst = np.concatenate([fields.fr_to_mont(int(v)) for v in instances]) if len(instances) else np.zeros(0, dtype=np.uint64)
+    inst = _instances_mont(instances)
     adv = np.ascontiguousarray(as_u64(advice, 4))
     n = 1 << pk.params.k()
     if adv.shape[0] != pk.cs["num_advice_columns"] * n:
@@ -189,16 +200,53 @@ def create_proof(pk: ProvingKey, instances: Sequence[int], advice, rng_seed: byt
     out = np.zeros(cap, dtype=np.uint8)
     plen = ctypes.c_size_t()
     seed = np.frombuffer(rng_seed, dtype=np.uint8).copy()
+    h = (ctx or pk.ctx).handle
     if comm is None:
-        _lib.check(_lib.lib().sb_create_proof((ctx or pk.ctx).handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed), ctypes.c_int32(transcript),
-                                              ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen)), "sb_create_proof")
-    else:
-        st = _lib.lib().sb_create_proof_sharded((ctx or pk.ctx).handle, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed),
-                                                ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
-        if st != 0 and comm.error is not None:
-            raise comm.error
-        _lib.check(st, "sb_create_proof_sharded")
-    return out[: plen.value].tobytes()
+        st = _lib.lib().sb_create_proof(h, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed), ctypes.c_int32(transcript),
+                                        ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+        return _finish(st, "sb_create_proof", None, out, plen)
+    st = _lib.lib().sb_create_proof_sharded(h, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)), ptr(adv), ptr(seed),
+                                            ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+    return _finish(st, "sb_create_proof_sharded", comm, out, plen)
+
+
+def create_proof_sparse(pk: ProvingKey, instances: Sequence[int], advice_cells, advice_values, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, comm=None,
+                        ctx: Optional[Context] = None) -> bytes:
+    """Same proof from the ASSIGNED advice cells only: advice_cells (m, 2) uint32 (column, row), advice_values (m, 4) uint64; every other
+    cell is zero.  The bytes equal `create_proof` on the dense columns."""
+    if len(rng_seed) != 32:
+        raise AssertionError("rng_seed must be 32 bytes")
+    inst = _instances_mont(instances)
+    cells = np.ascontiguousarray(advice_cells, dtype=np.uint32).reshape(-1, 2)
+    vals = np.ascontiguousarray(as_u64(advice_values, 4)).reshape(-1, 4)
+    if cells.shape[0] != vals.shape[0]:
+        raise AssertionError("create_proof_sparse: one value per advice cell")
+    cap = 1 << 16
+    out = np.zeros(cap, dtype=np.uint8)
+    plen = ctypes.c_size_t()
+    seed = np.frombuffer(rng_seed, dtype=np.uint8).copy()
+    h = (ctx or pk.ctx).handle
+    if comm is None:
+        st = _lib.lib().sb_create_proof_sparse(h, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ptr(cells), ptr(vals), ctypes.c_size_t(cells.shape[0]), ptr(seed),
+                                               ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+        return _finish(st, "sb_create_proof_sparse", None, out, plen)
+    st = _lib.lib().sb_create_proof_sharded_sparse(h, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)), ptr(cells), ptr(vals),
+                                                   ctypes.c_size_t(cells.shape[0]), ptr(seed), ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+    return _finish(st, "sb_create_proof_sharded_sparse", comm, out, plen)
+
+
+def create_proof_dev(pk: ProvingKey, instances: Sequence[int], d_advice: int, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, ctx: Optional[Context] = None) -> bytes:
+    """Same proof with the advice columns already in device memory (`d_advice`: device pointer to A x n x 32 B; left untouched)."""
+    if len(rng_seed) != 32:
+        raise AssertionError("rng_seed must be 32 bytes")
+    inst = _instances_mont(instances)
+    cap = 1 << 16
+    out = np.zeros(cap, dtype=np.uint8)
+    plen = ctypes.c_size_t()
+    seed = np.frombuffer(rng_seed, dtype=np.uint8).copy()
+    st = _lib.lib().sb_create_proof_dev((ctx or pk.ctx).handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ctypes.c_void_p(d_advice), ptr(seed),
+                                        ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+    return _finish(st, "sb_create_proof_dev", None, out, plen)
 
 
 class BatchProver:

@@ -141,10 +141,20 @@ int32_t sb_pk_commitments(const sb_pk *pk, uint8_t *fixed_comms, uint8_t *sigma_
  * 1 = Keccak256 / EVM (gen_proof_solidity_calldata).  Writes the proof bytes and their length. */
 int32_t sb_create_proof(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint8_t *advice, const uint8_t rng_seed[32],
                         int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+/* The same proof from other forms of the witness (identical bytes for identical cells, seed and key):
+ *  _dev:    advice already in device memory (A x n x 32 B, column-major; left untouched) -- a device witness generator, or bench.py's
+ *           HBM-resident measurement;
+ *  _sparse: only the ASSIGNED advice cells, n_cells x (col, row) u32 pairs + n_cells x 32 B values, all other cells zero.
+ *           `MstInclusionCircuit` assigns a few thousand cells whatever k is, so a k = 23 proof uploads ~1 MB instead of 768 MiB. */
+int32_t sb_create_proof_dev(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const void *d_advice, const uint8_t rng_seed[32],
+                            int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+int32_t sb_create_proof_sparse(sb_ctx *ctx, const sb_pk *pk, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells, const uint8_t *advice_cell_values,
+                               size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
 /* ---- one proof sharded over the GPUs of a box (BASELINE configs[3]) --------------------------------
  * One process (or thread) per GPU, each with its own sb_ctx / sb_srs / sb_pk built from the same inputs.  Every rank calls
  * sb_create_proof_sharded with identical arguments; the ranks run the transcript in lock step and return the same proof bytes.
- * Sharded work: every commitment MSM by base range (64-byte partial points meet in allgather_host and are added on the host),
+ * Sharded work: every commitment MSM by signed-digit WINDOW (rank r accumulates windows [r W / world, (r + 1) W / world) over all bases; the 128-byte
+ * XYZZ partials meet in allgather_host and are added on the host -- a base-range split remains selectable with SB_SHARD_MSM_BY_RANGE),
  * the coset NTTs, evaluate_h and the division by t(X) by cosets of the extended domain (the quotient's values meet in
  * allgather_dev).  `world` must divide 2^(extended_k - k).  The callbacks are the host's collective library (NCCL, MPI, gloo):
  * both gather `bytes_per_rank` bytes from every rank in rank order and return 0 on success.  allgather_dev works in place on
@@ -158,6 +168,9 @@ typedef struct sb_comm {
 } sb_comm;
 int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
                                 const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells,
+                                       const uint8_t *advice_cell_values, size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out,
+                                       size_t proof_cap, size_t *proof_len);
 /* device time (ms) of the fused evaluate_h kernel of the last create_proof on this context and its program shape:
  * instructions, field products, additions/subtractions, live value slots */
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);

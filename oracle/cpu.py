@@ -133,25 +133,25 @@ class Domain:
         self.t_inv = np.concatenate([m(t) for t in self.d.t_inv])
 
     def lagrange_to_coeff(self, a):
-        return fr_scale(best_fft(a, self.omega_inv, self.d.k, self.threads), self.ifft_div)
+        return par_fr_scale(best_fft(a, self.omega_inv, self.d.k, self.threads), self.ifft_div)
 
     def coeff_to_lagrange(self, a):
         return best_fft(a, self.omega, self.d.k, self.threads)
 
     def coeff_to_extended(self, a):
-        b = fr_scale_pattern(a, self.coset)
+        b = par_fr_scale_pattern(a, self.coset)
         ext = np.zeros(4 << self.d.extended_k, dtype=np.uint64)
         ext[: b.size] = b
         return best_fft(ext, self.ext_omega, self.d.extended_k, self.threads)
 
     def extended_to_coeff(self, a):
         b = best_fft(a, self.ext_omega_inv, self.d.extended_k, self.threads)
-        b = fr_scale(b, self.ext_ifft_div)
-        b = fr_scale_pattern(b, self.coset_inv)
+        b = par_fr_scale(b, self.ext_ifft_div)
+        b = par_fr_scale_pattern(b, self.coset_inv)
         return b[: 4 * self.d.n * self.d.quotient_poly_degree].copy()
 
     def divide_by_vanishing_poly(self, a):
-        return fr_scale_pattern(a, self.t_inv)
+        return par_fr_scale_pattern(a, self.t_inv)
 
 
 def gen_bases(n: int, seed: int = 1, threads: int = 8) -> np.ndarray:
@@ -207,4 +207,180 @@ def fr_axpby(a, s, b, t) -> np.ndarray:
     a, b = _u64(a), _u64(b)
     out = np.empty_like(a)
     lib().oracle_fr_axpby(_p(out), _p(a), _p(_u64(s)), _p(b), _p(_u64(t)), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# threaded forms (OpenMP inside halo2_cpu.c): what halo2 does with rayon's `parallelize`
+def set_threads(t: int) -> None:
+    lib().oracle_set_threads(ctypes.c_int(int(t)))
+
+
+def get_threads() -> int:
+    return int(lib().oracle_get_threads())
+
+
+def _par_binop(name, a, b):
+    a, b = _u64(a), _u64(b)
+    out = np.empty_like(a)
+    getattr(lib(), name)(_p(out), _p(a), _p(b), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+def par_fr_mul(a, b): return _par_binop("oracle_par_fr_mul", a, b)
+def par_fr_add(a, b): return _par_binop("oracle_par_fr_add", a, b)
+def par_fr_sub(a, b): return _par_binop("oracle_par_fr_sub", a, b)
+
+
+def par_fr_scale(a, s) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().oracle_par_fr_scale(_p(a), _p(_u64(s)), ctypes.c_size_t(a.size // 4))
+    return a
+
+
+def par_fr_scale_pattern(a, pat) -> np.ndarray:
+    a = _u64(a).copy()
+    pat = _u64(pat)
+    lib().oracle_par_fr_scale_pattern(_p(a), _p(pat), ctypes.c_size_t(pat.size // 4), ctypes.c_size_t(a.size // 4))
+    return a
+
+
+def par_fr_add_const(a, c) -> np.ndarray:
+    a = _u64(a)
+    out = np.empty_like(a)
+    lib().oracle_par_fr_add_const(_p(out), _p(a), _p(_u64(c)), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+def par_fr_axpby(a, s, b, t) -> np.ndarray:
+    a, b = _u64(a), _u64(b)
+    out = np.empty_like(a)
+    lib().oracle_par_fr_axpby(_p(out), _p(a), _p(_u64(s)), _p(b), _p(_u64(t)), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+def fr_powers(base, n: int) -> np.ndarray:
+    """(n, 4): base^i in Montgomery form."""
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().oracle_fr_powers(_p(out), _p(_u64(base)), ctypes.c_size_t(n))
+    return out
+
+
+def par_fr_batch_invert(a) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().oracle_par_fr_batch_invert(_p(a), ctypes.c_size_t(a.size // 4))
+    return a
+
+
+def par_fr_eval_poly(coeffs, x) -> np.ndarray:
+    c = _u64(coeffs)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_par_fr_eval_poly(_p(out), _p(c), ctypes.c_size_t(c.size // 4), _p(_u64(x)))
+    return out
+
+
+def expr_eval(cols, code: np.ndarray, consts: np.ndarray, n_regs: int, out_reg: int, n_rows: int, rot_scale: int) -> np.ndarray:
+    """Row-parallel register program over whole columns (halo2 `GraphEvaluator`): cols = list of (n_rows, 4) uint64 arrays,
+    code = (n_ins, 4) int32 rows (op, dst, a, b), consts (m, 4) uint64.  Returns (n_rows, 4)."""
+    keep = [np.ascontiguousarray(c).reshape(-1) for c in cols]
+    for c in keep:
+        assert c.size == 4 * n_rows
+    ptrs = (ctypes.c_void_p * max(len(keep), 1))(*[c.ctypes.data for c in keep])
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    consts = np.ascontiguousarray(consts, dtype=np.uint64).reshape(-1)
+    out = np.empty((n_rows, 4), dtype=np.uint64)
+    lib().oracle_expr_eval(_p(out), ctypes.c_size_t(n_rows), ptrs, _p(code), ctypes.c_size_t(code.shape[0]), _p(consts) if consts.size else None,
+                           ctypes.c_int32(n_regs), ctypes.c_int32(out_reg), ctypes.c_int64(rot_scale))
+    return out
+
+
+def permute_expression_pair(inp, tab, usable: int):
+    """halo2 lookup `permute_expression_pair` on Montgomery arrays; raises ValueError when an input is not in the table."""
+    a, t = _u64(inp), _u64(tab)
+    p_in = np.zeros((usable, 4), dtype=np.uint64)
+    p_tab = np.zeros((usable, 4), dtype=np.uint64)
+    rc = lib().oracle_permute_expression_pair(_p(p_in), _p(p_tab), _p(a), _p(t), ctypes.c_size_t(usable))
+    if rc != 0:
+        raise ValueError("lookup input value not in table (ConstraintSystemFailure)")
+    return p_in, p_tab
+
+
+def chacha_fr_fill(key_words, block0: int, n: int) -> np.ndarray:
+    """n consecutive `Fr::random` draws of a ChaCha20Rng with this key, starting at keystream block `block0` (one draw = one block)."""
+    key = np.array(list(key_words), dtype=np.uint32)
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().oracle_chacha_fr_fill(_p(out), _p(key), ctypes.c_uint64(block0), ctypes.c_size_t(n))
+    return out
+
+
+def keccak256(data: bytes) -> bytes:
+    out = np.zeros(32, dtype=np.uint8)
+    buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+    lib().oracle_keccak256(_p(out), _p(np.ascontiguousarray(buf)), ctypes.c_size_t(len(data)))
+    return out.tobytes()
+
+
+_poseidon_ready = False
+
+
+def _poseidon_init():
+    global _poseidon_ready
+    if _poseidon_ready:
+        return
+    import json
+    from . import bn254 as B
+    golden = os.path.join(os.path.dirname(_HERE), "tests", "golden", "poseidon_params.json")
+    P = json.load(open(golden))
+    m = lambda x: np.frombuffer(B.fr_to_mont_bytes(int(x, 16)), dtype=np.uint64)
+    rc = np.concatenate([m(x) for row in P["round_constants"] for x in row])
+    mds = np.concatenate([m(x) for row in P["mds"] for x in row])
+    lib().oracle_poseidon_set_params(_p(np.ascontiguousarray(rc)), _p(np.ascontiguousarray(mds)))
+    _poseidon_ready = True
+
+
+def poseidon_hash(inputs_mont) -> np.ndarray:
+    _poseidon_init()
+    a = _u64(inputs_mont)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_poseidon_hash(_p(out), _p(a), ctypes.c_size_t(a.size // 4))
+    return out
+
+
+class MstC:
+    """Merkle sum tree built by the C oracle (threaded): the whole tree as flat level-major arrays."""
+
+    def __init__(self, names, balances: np.ndarray):
+        """names: list of bytes; balances (n, n_cur) uint64."""
+        _poseidon_init()
+        n = len(names)
+        bal = np.ascontiguousarray(balances, dtype=np.uint64)
+        self.n_cur = bal.shape[1]
+        self.depth = max(0, (n - 1).bit_length())
+        offs = np.zeros(n + 1, dtype=np.uint32)
+        offs[1:] = np.cumsum([len(x) for x in names])
+        blob = np.frombuffer(b"".join(names), dtype=np.uint8) if offs[-1] else np.zeros(1, dtype=np.uint8)
+        slots = 2 << self.depth
+        self.hashes = np.zeros((slots, 4), dtype=np.uint64)
+        self.balances = np.zeros((slots, self.n_cur, 4), dtype=np.uint64)
+        self.unames = np.zeros((1 << self.depth, 4), dtype=np.uint64)
+        lib().oracle_mst_build(_p(self.hashes), _p(self.balances), _p(self.unames), _p(np.ascontiguousarray(blob)), _p(offs), _p(bal), ctypes.c_size_t(n),
+                               ctypes.c_uint32(self.n_cur), ctypes.c_uint32(self.depth))
+
+    def level_offset(self, level: int) -> int:
+        return sum(1 << (self.depth - l) for l in range(level))
+
+    def node(self, level: int, index: int):
+        o = self.level_offset(level) + index
+        return self.hashes[o], self.balances[o]
+
+    def root(self):
+        return self.node(self.depth, 0)
+
+
+def g1_fixed_base_mul(scalars) -> np.ndarray:
+    """out[i] = scalars[i] * G (affine Montgomery, (n, 8) uint64): the data-parallel core of `ParamsKZG::setup`."""
+    s = _u64(scalars)
+    n = s.size // 4
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().oracle_g1_fixed_base_mul(_p(out), _p(s), ctypes.c_size_t(n))
     return out

@@ -432,3 +432,332 @@ void oracle_fr_axpby(u64 *r, const u64 *a, const u64 s[4], const u64 *b, const u
     oracle_init();
     for (size_t i = 0; i < n; i++) { u64 x[4], y[4]; f_mul(&FR, x, a + 4 * i, s); f_mul(&FR, y, b + 4 * i, t); f_add(&FR, r + 4 * i, x, y); }
 }
+
+/* ====================================================================================================
+ * Second half: what the restated `create_proof` (oracle/halo2_prover.py) needs to run at k = 17 .. 20 in
+ * seconds on all host cores, the way halo2 runs it with rayon: element-wise passes split over threads
+ * (`parallelize`), `Evaluator::evaluate_h` as a row-parallel interpreter of a flattened calculation list
+ * (halo2 `GraphEvaluator`), chunk-parallel `eval_polynomial` / `batch_invert`, the lookup
+ * argument's `permute_expression_pair`, ChaCha20 `Fr::random` streams, and the Merkle sum tree's
+ * Keccak-256 + Poseidon hashing (zk_prover/src/merkle_sum_tree/{entry.rs:15-27,node.rs:16-85},
+ * utils/build_tree.rs:5-78).  Threads: OpenMP, `oracle_set_threads`.
+ * ==================================================================================================== */
+#include <omp.h>
+
+static int g_threads = 1;
+void oracle_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
+int oracle_get_threads(void) { return g_threads; }
+
+#define PAR_FOR _Pragma("omp parallel for schedule(static) num_threads(g_threads)")
+
+void oracle_par_fr_mul(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); PAR_FOR for (size_t i = 0; i < n; i++) f_mul(&FR, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_par_fr_add(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); PAR_FOR for (size_t i = 0; i < n; i++) f_add(&FR, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_par_fr_sub(u64 *r, const u64 *a, const u64 *b, size_t n) { oracle_init(); PAR_FOR for (size_t i = 0; i < n; i++) f_sub(&FR, r + 4 * i, a + 4 * i, b + 4 * i); }
+void oracle_par_fr_scale(u64 *a, const u64 s[4], size_t n) { oracle_init(); PAR_FOR for (size_t i = 0; i < n; i++) f_mul(&FR, a + 4 * i, a + 4 * i, s); }
+void oracle_par_fr_scale_pattern(u64 *a, const u64 *pat, size_t m, size_t n) { oracle_init(); PAR_FOR for (size_t i = 0; i < n; i++) f_mul(&FR, a + 4 * i, a + 4 * i, pat + 4 * (i % m)); }
+void oracle_par_fr_add_const(u64 *r, const u64 *a, const u64 c[4], size_t n) { oracle_init(); PAR_FOR for (size_t i = 0; i < n; i++) f_add(&FR, r + 4 * i, a + 4 * i, c); }
+void oracle_par_fr_axpby(u64 *r, const u64 *a, const u64 s[4], const u64 *b, const u64 t[4], size_t n) {
+    oracle_init();
+    PAR_FOR for (size_t i = 0; i < n; i++) { u64 x[4], y[4]; f_mul(&FR, x, a + 4 * i, s); f_mul(&FR, y, b + 4 * i, t); f_add(&FR, r + 4 * i, x, y); }
+}
+/* out[i] = base^i (Montgomery), i < n: each thread starts its chunk with one exponentiation */
+void oracle_fr_powers(u64 *out, const u64 base[4], size_t n) {
+    oracle_init();
+    const size_t CH = 4096;
+    const size_t nch = (n + CH - 1) / CH;
+    PAR_FOR for (size_t c = 0; c < nch; c++) {
+        size_t lo = c * CH, hi = lo + CH > n ? n : lo + CH;
+        u64 e[4] = {lo, 0, 0, 0}, cur[4];
+        f_pow(&FR, cur, base, e);
+        for (size_t i = lo; i < hi; i++) { memcpy(out + 4 * i, cur, 32); f_mul(&FR, cur, cur, base); }
+    }
+}
+/* halo2 `batch_invert` under `parallelize`: one Montgomery-trick chain per chunk (zeros stay zero) */
+void oracle_par_fr_batch_invert(u64 *a, size_t n) {
+    oracle_init();
+    const size_t CH = 1 << 14;
+    const size_t nch = (n + CH - 1) / CH;
+    PAR_FOR for (size_t c = 0; c < nch; c++) {
+        size_t lo = c * CH, hi = lo + CH > n ? n : lo + CH;
+        oracle_fr_batch_invert(a + 4 * lo, hi - lo);
+    }
+}
+/* halo2 `eval_polynomial`: chunks evaluated by Horner and recombined with x^offset */
+void oracle_par_fr_eval_poly(u64 out[4], const u64 *coeffs, size_t n, const u64 x[4]) {
+    oracle_init();
+    const size_t CH = 1 << 14;
+    const size_t nch = (n + CH - 1) / CH;
+    if (nch <= 1) { oracle_fr_eval_poly(out, coeffs, n, x); return; }
+    u64 *part = (u64 *)malloc(32 * nch);
+    PAR_FOR for (size_t c = 0; c < nch; c++) {
+        size_t lo = c * CH, hi = lo + CH > n ? n : lo + CH;
+        u64 v[4], e[4] = {lo, 0, 0, 0}, xp[4];
+        oracle_fr_eval_poly(v, coeffs + 4 * lo, hi - lo, x);
+        f_pow(&FR, xp, x, e);
+        f_mul(&FR, part + 4 * c, v, xp);
+    }
+    u64 acc[4] = {0, 0, 0, 0};
+    for (size_t c = 0; c < nch; c++) f_add(&FR, acc, acc, part + 4 * c);
+    memcpy(out, acc, 32);
+    free(part);
+}
+
+/* ---- Evaluator::evaluate_h as a row-parallel register program (halo2 GraphEvaluator) ----
+ * code: n_ins x 4 int32 (op, dst, a, b).  ops: 0 CONST dst <- consts[a]; 1 COL dst <- cols[a][(row + b * rot_scale) mod n];
+ * 2 ADD; 3 SUB; 4 MUL; 5 NEG.  Registers are per-thread (halo2's `intermediates`).  out[row] = reg[out_reg]. */
+void oracle_expr_eval(u64 *out, size_t n_rows, const u64 *const *cols, const int32_t *code, size_t n_ins, const u64 *consts, int32_t n_regs, int32_t out_reg,
+                      int64_t rot_scale) {
+    oracle_init();
+#pragma omp parallel num_threads(g_threads)
+    {
+        u64 *reg = (u64 *)calloc((size_t)(n_regs > 0 ? n_regs : 1), 32);
+#pragma omp for schedule(static)
+        for (size_t row = 0; row < n_rows; row++) {
+            for (size_t i = 0; i < n_ins; i++) {
+                const int32_t *ins = code + 4 * i;
+                u64 *d = reg + 4 * (size_t)ins[1];
+                switch (ins[0]) {
+                    case 0: memcpy(d, consts + 4 * (size_t)ins[2], 32); break;
+                    case 1: {
+                        int64_t r = ((int64_t)row + (int64_t)ins[3] * rot_scale) % (int64_t)n_rows;
+                        if (r < 0) r += (int64_t)n_rows;
+                        memcpy(d, cols[ins[2]] + 4 * (size_t)r, 32);
+                        break;
+                    }
+                    case 2: f_add(&FR, d, reg + 4 * (size_t)ins[2], reg + 4 * (size_t)ins[3]); break;
+                    case 3: f_sub(&FR, d, reg + 4 * (size_t)ins[2], reg + 4 * (size_t)ins[3]); break;
+                    case 4: f_mul(&FR, d, reg + 4 * (size_t)ins[2], reg + 4 * (size_t)ins[3]); break;
+                    default: { u64 z[4] = {0, 0, 0, 0}; f_sub(&FR, d, z, reg + 4 * (size_t)ins[2]); break; }
+                }
+            }
+            memcpy(out + 4 * row, reg + 4 * (size_t)out_reg, 32);
+        }
+        free(reg);
+    }
+}
+
+/* ---- lookup argument: halo2 `permute_expression_pair`.  Inputs Montgomery; returns 0, or 1 when an input value is not in the table. */
+static int cmp256(const void *pa, const void *pb) {
+    const u64 *a = (const u64 *)pa, *b = (const u64 *)pb;
+    for (int i = 3; i >= 0; i--) { if (a[i] < b[i]) return -1; if (a[i] > b[i]) return 1; }
+    return 0;
+}
+int oracle_permute_expression_pair(u64 *p_in, u64 *p_tab, const u64 *in, const u64 *tab, size_t usable) {
+    oracle_init();
+    u64 *a = (u64 *)malloc(32 * (usable ? usable : 1)), *t = (u64 *)malloc(32 * (usable ? usable : 1));
+    PAR_FOR for (size_t i = 0; i < usable; i++) { f_to_canon(&FR, a + 4 * i, in + 4 * i); f_to_canon(&FR, t + 4 * i, tab + 4 * i); }
+    qsort(a, usable, 32, cmp256);   /* permuted input = sorted input (Fr `Ord` = canonical value) */
+    qsort(t, usable, 32, cmp256);   /* the BTreeMap of leftover table values, iterated in ascending order */
+    /* first occurrence of each input value takes that value from the table multiset; repeated rows are filled afterwards from the
+     * leftover table values in ascending order, popping rows from the END of the repeated-row list */
+    size_t *repeated = (size_t *)malloc(sizeof(size_t) * (usable ? usable : 1));
+    uint8_t *taken = (uint8_t *)calloc(usable ? usable : 1, 1);
+    size_t n_rep = 0, tp = 0;
+    int bad = 0;
+    for (size_t row = 0; row < usable && !bad; row++) {
+        if (row == 0 || cmp256(a + 4 * row, a + 4 * (row - 1)) != 0) {
+            while (tp < usable && cmp256(t + 4 * tp, a + 4 * row) < 0) tp++;
+            if (tp >= usable || cmp256(t + 4 * tp, a + 4 * row) != 0) { bad = 1; break; }
+            taken[tp] = 1;
+            memcpy(p_tab + 4 * row, a + 4 * row, 32);
+            tp++;
+        } else {
+            repeated[n_rep++] = row;
+        }
+    }
+    if (!bad) {
+        for (size_t i = 0; i < usable; i++) {
+            if (taken[i]) continue;
+            if (!n_rep) { bad = 2; break; }
+            memcpy(p_tab + 4 * repeated[--n_rep], t + 4 * i, 32);
+        }
+        if (n_rep) bad = 2;
+    }
+    if (!bad) {
+        memcpy(p_in, a, 32 * usable);
+        PAR_FOR for (size_t i = 0; i < usable; i++) { f_from_canon(&FR, p_in + 4 * i, p_in + 4 * i); f_from_canon(&FR, p_tab + 4 * i, p_tab + 4 * i); }
+    }
+    free(a); free(t); free(repeated); free(taken);
+    return bad;
+}
+
+/* ---- rand_chacha 0.3.1 ChaCha20Rng + halo2curves `Fr::random` (oracle/chacha.py is the readable twin) ---- */
+#define ROTL32(x, n) (((x) << (n)) | ((x) >> (32 - (n))))
+#define CQR(a, b, c, d) a += b; d ^= a; d = ROTL32(d, 16); c += d; b ^= c; b = ROTL32(b, 12); a += b; d ^= a; d = ROTL32(d, 8); c += d; b ^= c; b = ROTL32(b, 7);
+static void chacha20_block(const uint32_t key[8], u64 counter, uint32_t out[16]) {
+    uint32_t in[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                       (uint32_t)counter, (uint32_t)(counter >> 32), 0, 0};
+    uint32_t s[16];
+    memcpy(s, in, 64);
+    for (int i = 0; i < 10; i++) {
+        CQR(s[0], s[4], s[8], s[12]) CQR(s[1], s[5], s[9], s[13]) CQR(s[2], s[6], s[10], s[14]) CQR(s[3], s[7], s[11], s[15])
+        CQR(s[0], s[5], s[10], s[15]) CQR(s[1], s[6], s[11], s[12]) CQR(s[2], s[7], s[8], s[13]) CQR(s[3], s[4], s[9], s[14])
+    }
+    for (int i = 0; i < 16; i++) out[i] = s[i] + in[i];
+}
+/* 512-bit little-endian integer (8 x u64) mod r, to Montgomery: lo * R^2 * R^-1 + hi * R^3 * R^-1 ... = lo*R + hi*2^256*R */
+static void fr_from_u512(u64 r[4], const u64 w[8]) {
+    u64 lo[4], hi[4], r3[4];
+    /* w_lo, w_hi may exceed the modulus: f_mul tolerates any 256-bit inputs whose product / R stays < 2^256 * something; reduce first by
+     * conditional subtraction (values < 2^256 < 6r) */
+    memcpy(lo, w, 32); memcpy(hi, w + 4, 32);
+    while (geq(lo, FR.m)) sub_nc(lo, lo, FR.m);
+    while (geq(hi, FR.m)) sub_nc(hi, hi, FR.m);
+    f_mul(&FR, r3, FR.r2, FR.r2);          /* R^3 */
+    f_mul(&FR, lo, lo, FR.r2);             /* lo * R */
+    f_mul(&FR, hi, hi, r3);                /* hi * R^2 = (hi * 2^256) * R */
+    f_add(&FR, r, lo, hi);
+}
+/* out[i] = Fr::random drawn from keystream blocks starting at `block0` (one Fr = 8 x next_u64 = exactly one 64-byte block) */
+void oracle_chacha_fr_fill(u64 *out, const uint32_t key[8], u64 block0, size_t n) {
+    oracle_init();
+    PAR_FOR for (size_t i = 0; i < n; i++) {
+        uint32_t b[16]; u64 w[8];
+        chacha20_block(key, block0 + i, b);
+        for (int j = 0; j < 8; j++) w[j] = (u64)b[2 * j] | ((u64)b[2 * j + 1] << 32);
+        fr_from_u512(out + 4 * i, w);
+    }
+}
+
+/* ---- Keccak-256 (Ethereum padding), for Entry::new's hashed username (entry.rs:21) ---- */
+static const u64 KRC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+    0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+    0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+static void keccak_f(u64 st[25]) {
+    static const int rotc[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const int piln[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    for (int round = 0; round < 24; round++) {
+        u64 bc[5], t;
+        for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+        for (int i = 0; i < 5; i++) { t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63)); for (int j = 0; j < 25; j += 5) st[j + i] ^= t; }
+        t = st[1];
+        for (int i = 0; i < 24; i++) { int j = piln[i]; u64 b = st[j]; st[j] = (t << rotc[i]) | (t >> (64 - rotc[i])); t = b; }
+        for (int j = 0; j < 25; j += 5) { for (int i = 0; i < 5; i++) bc[i] = st[j + i]; for (int i = 0; i < 5; i++) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5]; }
+        st[0] ^= KRC[round];
+    }
+}
+void oracle_keccak256(uint8_t out[32], const uint8_t *data, size_t len) {
+    u64 st[25]; memset(st, 0, sizeof st);
+    const size_t rate = 136;
+    while (len >= rate) { for (size_t i = 0; i < rate / 8; i++) { u64 w; memcpy(&w, data + 8 * i, 8); st[i] ^= w; } keccak_f(st); data += rate; len -= rate; }
+    uint8_t blk[136]; memset(blk, 0, sizeof blk); memcpy(blk, data, len);
+    blk[len] ^= 0x01; blk[rate - 1] ^= 0x80;
+    for (size_t i = 0; i < rate / 8; i++) { u64 w; memcpy(&w, blk + 8 * i, 8); st[i] ^= w; }
+    keccak_f(st);
+    memcpy(out, st, 32);
+}
+
+/* ---- Poseidon (WIDTH 2, RATE 1, R_F 8, R_P 56, x^5) and the Merkle sum tree ---- */
+static u64 P_RC[64][2][4], P_MDS[2][2][4];
+static int g_poseidon = 0;
+/* rc: 64 x 2 field elements, mds: 2 x 2, all Montgomery (tests/golden/poseidon_params.json, i.e. chips/poseidon/poseidon_params.rs) */
+void oracle_poseidon_set_params(const u64 *rc, const u64 *mds) { oracle_init(); memcpy(P_RC, rc, sizeof P_RC); memcpy(P_MDS, mds, sizeof P_MDS); g_poseidon = 1; }
+static inline void pow5(u64 r[4], const u64 a[4]) { u64 a2[4], a4[4]; f_sqr(&FR, a2, a); f_sqr(&FR, a4, a2); f_mul(&FR, r, a4, a); }
+static void poseidon_permute(u64 s[2][4]) {
+    for (int r = 0; r < 64; r++) {
+        u64 t0[4], t1[4], a[4], b[4];
+        f_add(&FR, t0, s[0], P_RC[r][0]); f_add(&FR, t1, s[1], P_RC[r][1]);
+        pow5(t0, t0);
+        if (r < 4 || r >= 60) pow5(t1, t1);
+        f_mul(&FR, a, P_MDS[0][0], t0); f_mul(&FR, b, P_MDS[0][1], t1); f_add(&FR, s[0], a, b);
+        f_mul(&FR, a, P_MDS[1][0], t0); f_mul(&FR, b, P_MDS[1][1], t1); f_add(&FR, s[1], a, b);
+    }
+}
+/* ConstantLength<L>: state [0, L * 2^64], absorb one element per permutation, output state[0] */
+static void poseidon_hash(u64 out[4], const u64 *inputs, size_t L) {
+    u64 s[2][4], c[4] = {0, (u64)L, 0, 0};
+    memset(s[0], 0, 32);
+    f_from_canon(&FR, s[1], c);
+    for (size_t i = 0; i < L; i++) { f_add(&FR, s[0], s[0], inputs + 4 * i); poseidon_permute(s); }
+    memcpy(out, s[0], 32);
+}
+void oracle_poseidon_hash(u64 out[4], const u64 *inputs, size_t L) { oracle_init(); poseidon_hash(out, inputs, L); }
+
+/* Entry::new + compute_leaf for every entry (usernames concatenated, offsets[n + 1]; balances n x n_cur u64), zero entries pad to 2^depth
+ * (mst.rs:106-120); then build_merkle_tree_from_leaves (build_tree.rs:5-78).  Layout of the result: hashes[level][index] flat with level
+ * offsets 0, 2^depth, 2^depth + 2^(depth-1), ...; balances likewise x n_cur; unames: 2^depth hashed usernames (mod r). */
+void oracle_mst_build(u64 *hashes, u64 *balances, u64 *unames, const uint8_t *names, const uint32_t *offsets, const u64 *bal64, size_t n_entries, uint32_t n_cur, uint32_t depth) {
+    oracle_init();
+    const size_t leaves = (size_t)1 << depth;
+    PAR_FOR for (size_t i = 0; i < leaves; i++) {
+        u64 pre[4 * 34];
+        memset(pre, 0, 32 * (size_t)(n_cur + 1));
+        if (i < n_entries) {
+            uint8_t h[32], le[32];
+            oracle_keccak256(h, names + offsets[i], offsets[i + 1] - offsets[i]);
+            for (int b = 0; b < 32; b++) le[b] = h[31 - b];   /* BigUint::from_bytes_be */
+            u64 w[4]; memcpy(w, le, 32);
+            while (geq(w, FR.m)) sub_nc(w, w, FR.m);
+            f_from_canon(&FR, pre, w);
+            for (uint32_t c = 0; c < n_cur; c++) { u64 v[4] = {bal64[i * n_cur + c], 0, 0, 0}; f_from_canon(&FR, pre + 4 * (c + 1), v); }
+        }
+        memcpy(unames + 4 * i, pre, 32);
+        for (uint32_t c = 0; c < n_cur; c++) memcpy(balances + 4 * (i * n_cur + c), pre + 4 * (c + 1), 32);
+        poseidon_hash(hashes + 4 * i, pre, n_cur + 1);
+    }
+    size_t off = 0;
+    for (uint32_t level = 1; level <= depth; level++) {
+        const size_t cnt = (size_t)1 << (depth - level), prev = off;
+        off += (size_t)1 << (depth - level + 1);
+        PAR_FOR for (size_t i = 0; i < cnt; i++) {
+            u64 pre[4 * 35];
+            for (uint32_t c = 0; c < n_cur; c++) {
+                f_add(&FR, pre + 4 * c, balances + 4 * ((prev + 2 * i) * n_cur + c), balances + 4 * ((prev + 2 * i + 1) * n_cur + c));
+                memcpy(balances + 4 * ((off + i) * n_cur + c), pre + 4 * c, 32);
+            }
+            memcpy(pre + 4 * n_cur, hashes + 4 * (prev + 2 * i), 32);
+            memcpy(pre + 4 * (n_cur + 1), hashes + 4 * (prev + 2 * i + 1), 32);
+            poseidon_hash(hashes + 4 * (off + i), pre, n_cur + 2);
+        }
+    }
+}
+
+/* ---- `ParamsKZG::setup(k, rng)` core (utils.rs:70): out[i] = scalars[i] * G, affine.  8-bit fixed windows over a table of
+ * j * 2^(8w) * G (32 x 255 affine points), one mixed addition per non-zero byte, batched normalisation. ---- */
+void oracle_g1_fixed_base_mul(u64 *out, const u64 *scalars_mont, size_t n) {
+    oracle_init();
+    aff_t *table = (aff_t *)malloc(sizeof(aff_t) * 32 * 255);
+    {
+        aff_t g; memset(&g, 0, sizeof g);
+        u64 one_c[4] = {1, 0, 0, 0}, two_c[4] = {2, 0, 0, 0};
+        f_from_canon(&FQ, g.x, one_c); f_from_canon(&FQ, g.y, two_c);
+        jac_t base; memcpy(base.x, g.x, 32); memcpy(base.y, g.y, 32); memcpy(base.z, FQ.r, 32);
+        for (int w = 0; w < 32; w++) {
+            jac_t acc = base;
+            aff_t base_aff; jac_to_affine(&base_aff, &base);
+            for (int j = 1; j <= 255; j++) {
+                jac_to_affine(&table[w * 255 + j - 1], &acc);
+                jac_add_affine(&acc, &acc, &base_aff);
+            }
+            base = acc;  /* 256 * previous base */
+        }
+    }
+    const size_t BATCH = 1024;
+    const size_t nb = (n + BATCH - 1) / BATCH;
+    PAR_FOR for (size_t bi = 0; bi < nb; bi++) {
+        size_t lo = bi * BATCH, m = lo + BATCH > n ? n - lo : BATCH;
+        jac_t *buf = (jac_t *)malloc(sizeof(jac_t) * BATCH);
+        u64 *pref = (u64 *)malloc(32 * BATCH);
+        for (size_t i = 0; i < m; i++) {
+            u64 c[4]; f_to_canon(&FR, c, scalars_mont + 4 * (lo + i));
+            const uint8_t *bytes = (const uint8_t *)c;
+            jac_t acc; jac_set_id(&acc);
+            for (int w = 0; w < 32; w++) if (bytes[w]) jac_add_affine(&acc, &acc, &table[w * 255 + bytes[w] - 1]);
+            buf[i] = acc;
+        }
+        u64 acc[4]; memcpy(acc, FQ.r, 32);
+        for (size_t i = 0; i < m; i++) { memcpy(pref + 4 * i, acc, 32); if (!jac_is_id(&buf[i])) f_mul(&FQ, acc, acc, buf[i].z); }
+        u64 inv[4]; f_inv(&FQ, inv, acc);
+        for (size_t i = m; i-- > 0;) {
+            u64 *o = out + 8 * (lo + i);
+            if (jac_is_id(&buf[i])) { memset(o, 0, 64); continue; }
+            u64 zi[4], zi2[4], zi3[4];
+            f_mul(&FQ, zi, inv, pref + 4 * i); f_mul(&FQ, inv, inv, buf[i].z);
+            f_sqr(&FQ, zi2, zi); f_mul(&FQ, zi3, zi2, zi);
+            f_mul(&FQ, o, buf[i].x, zi2); f_mul(&FQ, o + 4, buf[i].y, zi3);
+        }
+        free(buf); free(pref);
+    }
+    free(table);
+}

@@ -47,27 +47,27 @@ def to_ints(a: np.ndarray) -> List[int]:
 
 
 def vmul(a, b):
-    return cpu.fr_mul(a.reshape(-1), b.reshape(-1)).reshape(-1, 4)
+    return cpu.par_fr_mul(a.reshape(-1), b.reshape(-1)).reshape(-1, 4)
 
 
 def vadd(a, b):
-    return cpu.fr_add(a.reshape(-1), b.reshape(-1)).reshape(-1, 4)
+    return cpu.par_fr_add(a.reshape(-1), b.reshape(-1)).reshape(-1, 4)
 
 
 def vsub(a, b):
-    return cpu.fr_sub(a.reshape(-1), b.reshape(-1)).reshape(-1, 4)
+    return cpu.par_fr_sub(a.reshape(-1), b.reshape(-1)).reshape(-1, 4)
 
 
 def vscale(a, s: int):
-    return cpu.fr_scale(a.reshape(-1), m(s)).reshape(-1, 4)
+    return cpu.par_fr_scale(a.reshape(-1), m(s)).reshape(-1, 4)
 
 
 def vadd_const(a, s: int):
-    return vadd(a, const_vec(s, a.shape[0]))
+    return cpu.par_fr_add_const(a.reshape(-1), m(s)).reshape(-1, 4)
 
 
 def eval_poly(coeffs: np.ndarray, x: int) -> int:
-    return um(cpu.fr_eval_poly(coeffs.reshape(-1), m(x)))
+    return um(cpu.par_fr_eval_poly(coeffs.reshape(-1), m(x)))
 
 
 def rot(a: np.ndarray, r: int, scale: int = 1) -> np.ndarray:
@@ -85,7 +85,61 @@ def eval_expr(e, col, n: int) -> np.ndarray:
     if k == "neg":
         return vsub(np.zeros((n, 4), dtype=np.uint64), eval_expr(e[1], col, n))
     a, b = eval_expr(e[1], col, n), eval_expr(e[2], col, n)
-    return vadd(a, b) if k == "add" else vmul(a, b)
+    return vadd(a, b) if k == "add" else vsub(a, b) if k == "sub" else vmul(a, b)
+
+
+class ProgramBuilder:
+    """Flattens expression trees into the register program `oracle_expr_eval` runs row by row -- halo2's `GraphEvaluator`
+    (SURVEY A.12): identical sub-expressions are computed once (`add_calculation` de-duplicates), every value lives in a
+    per-thread `intermediates` slot.  Nodes: ("const", int) | ("col", index, rot) | ("neg", a) | ("add"|"sub"|"mul", a, b),
+    where a / b are node ids returned by earlier calls."""
+    OPS = {"const": 0, "col": 1, "add": 2, "sub": 3, "mul": 4, "neg": 5}
+
+    def __init__(self):
+        self.memo: Dict[tuple, int] = {}
+        self.code: List[Tuple[int, int, int, int]] = []
+        self.consts: List[int] = []
+        self.const_ix: Dict[int, int] = {}
+
+    def _emit(self, key, op, a, b):
+        if key in self.memo:
+            return self.memo[key]
+        dst = len(self.code)
+        self.code.append((op, dst, a, b))
+        self.memo[key] = dst
+        return dst
+
+    def const(self, v: int) -> int:
+        v %= R
+        if v not in self.const_ix:
+            self.const_ix[v] = len(self.consts)
+            self.consts.append(v)
+        return self._emit(("const", v), 0, self.const_ix[v], 0)
+
+    def col(self, index: int, rot_: int = 0) -> int:
+        return self._emit(("col", index, rot_), 1, index, rot_)
+
+    def add(self, a, b): return self._emit(("add", min(a, b), max(a, b)), 2, a, b)
+    def sub(self, a, b): return self._emit(("sub", a, b), 3, a, b)
+    def mul(self, a, b): return self._emit(("mul", min(a, b), max(a, b)), 4, a, b)
+    def neg(self, a): return self._emit(("neg", a), 5, a, 0)
+
+    def tree(self, e, colmap) -> int:
+        """expression tree of the constraint-system JSON; colmap(kind, column) -> column-table index"""
+        k = e[0]
+        if k == "const":
+            return self.const(int(e[1], 16))
+        if k in ("advice", "fixed", "instance"):
+            return self.col(colmap(k, e[1]), e[2])
+        if k == "neg":
+            return self.neg(self.tree(e[1], colmap))
+        a, b = self.tree(e[1], colmap), self.tree(e[2], colmap)
+        return self.add(a, b) if k == "add" else self.sub(a, b) if k == "sub" else self.mul(a, b)
+
+    def run(self, cols, out: int, n_rows: int, rot_scale: int) -> np.ndarray:
+        code = np.array(self.code, dtype=np.int32).reshape(-1, 4)
+        consts = from_ints(self.consts) if self.consts else np.zeros((0, 4), dtype=np.uint64)
+        return cpu.expr_eval(cols, code, consts, len(self.code), out, n_rows, rot_scale)
 
 
 class Params:
@@ -98,6 +152,20 @@ class Params:
     def read(cls, path: str, threads: int = 8) -> "Params":
         p = B.ParamsKZG.read(path)
         return cls(p.k, np.frombuffer(p.g_bytes, dtype=np.uint64).reshape(-1, 8), np.frombuffer(p.g_lagrange_bytes, dtype=np.uint64).reshape(-1, 8), threads)
+
+    @classmethod
+    def setup(cls, k: int, tau: int, threads: int = 8) -> "Params":
+        """`ParamsKZG::setup(k, rng)` (utils.rs:70) with an explicit secret (UNSAFE test SRS): g[i] = [tau^i] G,
+        g_lagrange[i] = [L_i(tau)] G with L_i(tau) = omega^i (tau^n - 1) / (n (tau - omega^i))."""
+        n = 1 << k
+        cpu.set_threads(threads)
+        d = B.EvaluationDomain(3, k)
+        g = cpu.g1_fixed_base_mul(cpu.fr_powers(m(tau), n).reshape(-1))
+        w = cpu.fr_powers(m(d.omega), n)
+        den = cpu.par_fr_batch_invert(vsub(const_vec(tau, n), w).reshape(-1)).reshape(n, 4)
+        c = (pow(tau, n, R) - 1) * d.ifft_divisor % R
+        lag = vscale(vmul(w, den), c)
+        return cls(k, g, cpu.g1_fixed_base_mul(lag.reshape(-1)), threads)
 
     def _commit(self, bases, scalars) -> B.Point:
         out = cpu.best_multiexp(np.ascontiguousarray(scalars).reshape(-1), bases[: scalars.shape[0]].reshape(-1), self.threads)
@@ -115,10 +183,11 @@ class ProvingKey:
     """What halo2's `ProvingKey` + `VerifyingKey` hold for `create_proof` (keygen_vk / keygen_pk)."""
 
     def __init__(self, params: Params, cs: dict, fixed: np.ndarray, sigma_mapping: Optional[List[List[Tuple[int, int]]]] = None,
-                 transcript_repr: int = 0x10F28BC710A8BDD00DD701DF2F5FC4F5CCDB260238EBA6F819DB692F79DC3DC9):
+                 transcript_repr: int = 0x10F28BC710A8BDD00DD701DF2F5FC4F5CCDB260238EBA6F819DB692F79DC3DC9, perm_cells=None):
         """fixed: (F, n, 4) Lagrange values of the fixed columns (after selector compression).
         sigma_mapping[j][i] = (column index in cs['permutation_columns'], row) that cell (j, i) is
-        mapped to by the copy-constraint permutation (identity if None)."""
+        mapped to by the copy-constraint permutation (identity if None); perm_cells: the same in sparse form, rows
+        (col, row, to_col, to_row) for the cells that moved (the format of tests/golden/mst_inclusion_assignment*.npz)."""
         self.cs = cs
         self.k, self.n = params.k, params.n
         n = self.n
@@ -133,17 +202,21 @@ class ProvingKey:
         self.fixed_commitments = [params.commit_lagrange(f) for f in fixed]
         # permutation argument: sigma_j(omega^i) = delta^(col') * omega^(row')
         ncols = len(cs["permutation_columns"])
-        omega_pows = [1] * n
-        for i in range(1, n):
-            omega_pows[i] = omega_pows[i - 1] * d.omega % R
+        self.omega_pows = cpu.fr_powers(m(d.omega), n)
         delta_pows = [pow(B.DELTA, j, R) for j in range(ncols)]
         sig = []
         for j in range(ncols):
-            if sigma_mapping is None:
-                vals = [delta_pows[j] * omega_pows[i] % R for i in range(n)]
-            else:
-                vals = [delta_pows[sigma_mapping[j][i][0]] * omega_pows[sigma_mapping[j][i][1]] % R for i in range(n)]
-            sig.append(from_ints(vals))
+            # identity permutation delta^j * omega^i, then the cells moved by copy constraints
+            v = vscale(self.omega_pows, delta_pows[j])
+            if perm_cells is not None:
+                for (c, row, tc, trow) in perm_cells:
+                    if c == j:
+                        v[row] = m(delta_pows[tc] * pow(d.omega, int(trow), R) % R)
+            elif sigma_mapping is not None:
+                for i in range(n):
+                    if sigma_mapping[j][i] != (j, i):
+                        v[i] = m(delta_pows[sigma_mapping[j][i][0]] * pow(d.omega, sigma_mapping[j][i][1], R) % R)
+            sig.append(v)
         self.sigma_values = np.stack(sig)
         self.sigma_polys = np.stack([self.dom.lagrange_to_coeff(s.reshape(-1)).reshape(n, 4) for s in sig])
         self.sigma_cosets = np.stack([self.dom.coeff_to_extended(p.reshape(-1)).reshape(-1, 4) for p in self.sigma_polys])
@@ -157,6 +230,16 @@ class ProvingKey:
         self.l0, self.l_last = ext(l0), ext(l_last)
         l_blind_ext = ext(l_blind)
         self.l_active_row = vsub(const_vec(1, self.ext_n), vadd(self.l_last, l_blind_ext))
+        # X on the extended coset: zeta * ext_omega^i
+        self.x_coset = vscale(cpu.fr_powers(m(d.extended_omega), self.ext_n), d.g_coset)
+
+    @classmethod
+    def from_sparse(cls, params: Params, cs: dict, fixed_cells, fixed_cell_values, perm_cells, transcript_repr: int) -> "ProvingKey":
+        """keygen output in the sparse form of tests/golden/mst_inclusion_assignment*.npz, expanded to k = params.k"""
+        fixed = np.zeros((cs["num_fixed_columns"], params.n, 4), dtype=np.uint64)
+        fc = np.asarray(fixed_cells)
+        fixed[fc[:, 0], fc[:, 1]] = np.asarray(fixed_cell_values, dtype=np.uint64)
+        return cls(params, cs, fixed, None, transcript_repr, perm_cells=[tuple(int(x) for x in r) for r in np.asarray(perm_cells)])
 
 
 # ------------------------------------------------------------------ lookup: permute_expression_pair (SURVEY A.7)
@@ -295,6 +378,107 @@ def shplonk_create_proof(params: Params, transcript, queries: List[Tuple[int, in
     transcript.write_point(params.commit(hq))
 
 
+# ------------------------------------------------------------------ evaluate_h
+def _h_numerator_columnwise(cs, pk, ext_col, perm_sets, lk_cosets, theta, beta, gamma, y, ext_n, rs, bf):
+    """The quotient numerator term by term over whole columns: the readable form (one pass over the extended domain per operator)."""
+    h = np.zeros((ext_n, 4), dtype=np.uint64)
+    fold = lambda acc, term: vadd(vscale(acc, y), term)
+    for g in cs["gates"]:
+        h = fold(h, eval_expr(g, ext_col, ext_n))
+    one = const_vec(1, ext_n)
+    if perm_sets:
+        first, last = perm_sets[0], perm_sets[-1]
+        h = fold(h, vmul(vsub(one, first["coset"]), pk.l0))
+        h = fold(h, vmul(vsub(vmul(last["coset"], last["coset"]), last["coset"]), pk.l_last))
+        for i in range(1, len(perm_sets)):
+            h = fold(h, vmul(vsub(perm_sets[i]["coset"], rot(perm_sets[i - 1]["coset"], -(bf + 1), rs)), pk.l0))
+        beta_x = vscale(pk.x_coset, beta)   # beta * X on the extended coset: X = zeta * ext_omega^idx
+        cur_delta = 1
+        for s in perm_sets:
+            left = rot(s["coset"], 1, rs)
+            right = s["coset"]
+            for j, kc in enumerate(s["cols"]):
+                vals = ext_col(kc[0], kc[1], 0)
+                left = vmul(left, vadd_const(vadd(vals, vscale(pk.sigma_cosets[s["first"] + j], beta)), gamma))
+                right = vmul(right, vadd_const(vadd(vals, vscale(beta_x, cur_delta)), gamma))
+                cur_delta = cur_delta * B.DELTA % R
+            h = fold(h, vmul(vsub(left, right), pk.l_active_row))
+    for (zc, ic, tc), lkdef in zip(lk_cosets, cs["lookups"]):
+
+        def compress_ext(exprs):
+            acc = np.zeros((ext_n, 4), dtype=np.uint64)
+            for e in exprs:
+                acc = vadd(vscale(acc, theta), eval_expr(e, ext_col, ext_n))
+            return acc
+        tvi = vmul(vadd_const(compress_ext(lkdef["input"]), beta), vadd_const(compress_ext(lkdef["table"]), gamma))
+        a_minus_s = vsub(ic, tc)
+        h = fold(h, vmul(vsub(one, zc), pk.l0))
+        h = fold(h, vmul(vsub(vmul(zc, zc), zc), pk.l_last))
+        h = fold(h, vmul(vsub(vmul(rot(zc, 1, rs), vmul(vadd_const(ic, beta), vadd_const(tc, gamma))), vmul(zc, tvi)), pk.l_active_row))
+        h = fold(h, vmul(a_minus_s, pk.l0))
+        h = fold(h, vmul(vmul(a_minus_s, vsub(ic, rot(ic, -1, rs))), pk.l_active_row))
+    return h
+
+
+def _h_numerator_program(cs, pk, advice_cosets, inst_coset, perm_sets, lk_cosets, theta, beta, gamma, y, ext_n, rs, bf):
+    """The same numerator the way halo2's `Evaluator::evaluate_h` computes it: ONE pass over the extended domain, rows split across
+    threads, every row running the flattened calculation list (`GraphEvaluator`); terms folded by Horner in y in the same order."""
+    A, F, P = cs["num_advice_columns"], cs["num_fixed_columns"], len(cs["permutation_columns"])
+    n_sets = len(perm_sets)
+    cols = list(advice_cosets) + [pk.fixed_cosets[c] for c in range(F)] + [inst_coset] + [pk.sigma_cosets[j] for j in range(P)]
+    E_SIGMA = A + F + 1
+    E_PZ = len(cols); cols += [s_["coset"] for s_ in perm_sets]
+    E_L0 = len(cols); cols += [pk.l0, pk.l_last, pk.l_active_row, pk.x_coset]
+    E_LLAST, E_LACT, E_X = E_L0 + 1, E_L0 + 2, E_L0 + 3
+    E_LK = len(cols)
+    for trio in lk_cosets:
+        cols += list(trio)
+    colmap = lambda kind, c: c if kind == "advice" else A + c if kind == "fixed" else A + F
+    pb = ProgramBuilder()
+    terms = [pb.tree(g, colmap) for g in cs["gates"]]
+    one, l0, llast, lact = pb.const(1), pb.col(E_L0), pb.col(E_LLAST), pb.col(E_LACT)
+    cb, cg = pb.const(beta), pb.const(gamma)
+    if n_sets:
+        Z = lambda s_, r: pb.col(E_PZ + s_, r)
+        terms.append(pb.mul(pb.sub(one, Z(0, 0)), l0))
+        zl = Z(n_sets - 1, 0)
+        terms.append(pb.mul(pb.sub(pb.mul(zl, zl), zl), llast))
+        for i in range(1, n_sets):
+            terms.append(pb.mul(pb.sub(Z(i, 0), Z(i - 1, -(bf + 1))), l0))
+        cur_delta = 1
+        for si, s_ in enumerate(perm_sets):
+            left, right = Z(si, 1), Z(si, 0)
+            for j, kc in enumerate(s_["cols"]):
+                val = pb.col(colmap(kc[0], kc[1]))
+                left = pb.mul(left, pb.add(pb.add(val, pb.mul(cb, pb.col(E_SIGMA + s_["first"] + j))), cg))
+                right = pb.mul(right, pb.add(pb.add(val, pb.mul(pb.const(cur_delta * beta % R), pb.col(E_X))), cg))
+                cur_delta = cur_delta * B.DELTA % R
+            terms.append(pb.mul(pb.sub(left, right), lact))
+    cth = pb.const(theta)
+    for li, lkdef in enumerate(cs["lookups"]):
+        z0, z1 = pb.col(E_LK + 3 * li), pb.col(E_LK + 3 * li, 1)
+        a0, am1, s0 = pb.col(E_LK + 3 * li + 1), pb.col(E_LK + 3 * li + 1, -1), pb.col(E_LK + 3 * li + 2)
+
+        def compress(exprs):
+            acc = None
+            for e in exprs:
+                t = pb.tree(e, colmap)
+                acc = t if acc is None else pb.add(pb.mul(acc, cth), t)
+            return acc
+        cin, ctab = compress(lkdef["input"]), compress(lkdef["table"])
+        a_minus_s = pb.sub(a0, s0)
+        terms.append(pb.mul(pb.sub(one, z0), l0))
+        terms.append(pb.mul(pb.sub(pb.mul(z0, z0), z0), llast))
+        terms.append(pb.mul(pb.sub(pb.mul(z1, pb.mul(pb.add(a0, cb), pb.add(s0, cg))), pb.mul(z0, pb.mul(pb.add(cin, cb), pb.add(ctab, cg)))), lact))
+        terms.append(pb.mul(a_minus_s, l0))
+        terms.append(pb.mul(pb.mul(a_minus_s, pb.sub(a0, am1)), lact))
+    cy = pb.const(y)
+    acc = None
+    for t in terms:
+        acc = t if acc is None else pb.add(pb.mul(acc, cy), t)
+    return pb.run(cols, acc, ext_n, rs)
+
+
 # ------------------------------------------------------------------ create_proof (SURVEY A.5)
 def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: np.ndarray, rng, transcript, trace: Optional[dict] = None):
     """advice: (A, n, 4) assigned advice columns (rows >= n - 6 are overwritten with blinding).
@@ -341,10 +525,13 @@ def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: n
                 acc = vadd(vscale(acc, theta), eval_expr(e, lagrange_col, n))
             return acc
         c_in, c_tab = compress(lk["input"]), compress(lk["table"])
-        p_in, p_tab = permute_expression_pair(to_ints(c_in), to_ints(c_tab), usable)
-        p_in += [rng.next_fr() for _ in range(bf + 1)]
-        p_tab += [rng.next_fr() for _ in range(bf + 1)]
-        p_in_v, p_tab_v = from_ints(p_in), from_ints(p_tab)
+        if n <= 4096:   # the readable python twin (the C form is checked against it in tests/test_oracle_circuit.py)
+            p_in, p_tab = permute_expression_pair(to_ints(c_in), to_ints(c_tab), usable)
+            p_in_u, p_tab_u = from_ints(p_in), from_ints(p_tab)
+        else:
+            p_in_u, p_tab_u = cpu.permute_expression_pair(c_in, c_tab, usable)
+        p_in_v = np.concatenate([p_in_u, from_ints([rng.next_fr() for _ in range(bf + 1)])])
+        p_tab_v = np.concatenate([p_tab_u, from_ints([rng.next_fr() for _ in range(bf + 1)])])
         in_poly = dom.lagrange_to_coeff(p_in_v.reshape(-1)).reshape(n, 4)
         _b = rng.next_fr()
         in_comm = params.commit_lagrange(p_in_v)
@@ -361,12 +548,7 @@ def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: n
     chunk = cs["degree"] - 2
     pcols = cs["permutation_columns"]
     col_values = lambda kc: advice[kc[1]] if kc[0] == "advice" else pk.fixed_values[kc[1]] if kc[0] == "fixed" else inst_vals
-    omega_vec = from_ints([pow(d.omega, i, R) for i in range(n)]) if n <= 4096 else None
-    if omega_vec is None:
-        pw = [1] * n
-        for i in range(1, n):
-            pw[i] = pw[i - 1] * d.omega % R
-        omega_vec = from_ints(pw)
+    omega_vec = pk.omega_pows
     deltaomega = 1  # delta^col
     last_z = 1
     perm_sets = []
@@ -375,7 +557,7 @@ def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: n
         mod = const_vec(1, n)
         for j, kc in enumerate(cols):
             mod = vmul(mod, vadd_const(vadd(vscale(pk.sigma_values[s0 + j], beta), col_values(kc)), gamma))
-        mod = cpu.fr_batch_invert(mod.reshape(-1)).reshape(n, 4)
+        mod = cpu.par_fr_batch_invert(mod.reshape(-1)).reshape(n, 4)
         for kc in cols:
             mod = vmul(mod, vadd_const(vadd(vscale(omega_vec, deltaomega * beta % R), col_values(kc)), gamma))
             deltaomega = deltaomega * B.DELTA % R
@@ -393,7 +575,7 @@ def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: n
     # lookup products
     for lk in lookups:
         den = vmul(vadd_const(lk["p_in"], beta), vadd_const(lk["p_tab"], gamma))
-        den = cpu.fr_batch_invert(den.reshape(-1)).reshape(n, 4)
+        den = cpu.par_fr_batch_invert(den.reshape(-1)).reshape(n, 4)
         prod = vmul(den, vmul(vadd_const(lk["c_in"], beta), vadd_const(lk["c_tab"], gamma)))
         z = cpu.fr_running_product(prod.reshape(-1), m(1), n).reshape(n, 4)
         z[n - bf:] = from_ints([rng.next_fr() for _ in range(bf)])
@@ -405,7 +587,7 @@ def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: n
     # vanishing argument: random polynomial (one ChaCha20 child stream seeded from rng = the 1-thread case of the fork)
     from .chacha import ChaCha20Rng
     child = ChaCha20Rng(rng.fill_bytes(32))
-    random_poly = from_ints([child.next_fr() for _ in range(n)])
+    random_poly = cpu.chacha_fr_fill(child.key, 0, n)   # coefficient i = `Fr::random` draw i = keystream block i
     _b = rng.next_fr()
     transcript.write_point(params.commit(random_poly))
     y = transcript.squeeze_challenge()
@@ -418,49 +600,11 @@ def create_proof(params: Params, pk: ProvingKey, instances: List[int], advice: n
         src = advice_cosets[c] if kind == "advice" else pk.fixed_cosets[c] if kind == "fixed" else inst_coset
         return rot(src, r, rs)
 
-    h = np.zeros((ext_n, 4), dtype=np.uint64)
-    fold = lambda acc, term: vadd(vscale(acc, y), term)
-    for g in cs["gates"]:
-        h = fold(h, eval_expr(g, ext_col, ext_n))
-    one = const_vec(1, ext_n)
-    if perm_sets:
-        first, last = perm_sets[0], perm_sets[-1]
-        h = fold(h, vmul(vsub(one, first["coset"]), pk.l0))
-        h = fold(h, vmul(vsub(vmul(last["coset"], last["coset"]), last["coset"]), pk.l_last))
-        for i in range(1, len(perm_sets)):
-            h = fold(h, vmul(vsub(perm_sets[i]["coset"], rot(perm_sets[i - 1]["coset"], -(bf + 1), rs)), pk.l0))
-        # beta * X on the extended coset: X = zeta * ext_omega^idx
-        xs = [1] * ext_n
-        for i in range(1, ext_n):
-            xs[i] = xs[i - 1] * d.extended_omega % R
-        beta_x = vscale(from_ints(xs), beta * d.g_coset % R)
-        cur_delta = 1
-        for s in perm_sets:
-            left = rot(s["coset"], 1, rs)
-            right = s["coset"]
-            for j, kc in enumerate(s["cols"]):
-                vals = ext_col(kc[0], kc[1], 0)
-                left = vmul(left, vadd_const(vadd(vals, vscale(pk.sigma_cosets[s["first"] + j], beta)), gamma))
-                right = vmul(right, vadd_const(vadd(vals, vscale(beta_x, cur_delta)), gamma))
-                cur_delta = cur_delta * B.DELTA % R
-            h = fold(h, vmul(vsub(left, right), pk.l_active_row))
-    for lk, lkdef in zip(lookups, cs["lookups"]):
-        zc = dom.coeff_to_extended(lk["z_poly"].reshape(-1)).reshape(-1, 4)
-        ic = dom.coeff_to_extended(lk["in_poly"].reshape(-1)).reshape(-1, 4)
-        tc = dom.coeff_to_extended(lk["tab_poly"].reshape(-1)).reshape(-1, 4)
-
-        def compress_ext(exprs):
-            acc = np.zeros((ext_n, 4), dtype=np.uint64)
-            for e in exprs:
-                acc = vadd(vscale(acc, theta), eval_expr(e, ext_col, ext_n))
-            return acc
-        tvi = vmul(vadd_const(compress_ext(lkdef["input"]), beta), vadd_const(compress_ext(lkdef["table"]), gamma))
-        a_minus_s = vsub(ic, tc)
-        h = fold(h, vmul(vsub(one, zc), pk.l0))
-        h = fold(h, vmul(vsub(vmul(zc, zc), zc), pk.l_last))
-        h = fold(h, vmul(vsub(vmul(rot(zc, 1, rs), vmul(vadd_const(ic, beta), vadd_const(tc, gamma))), vmul(zc, tvi)), pk.l_active_row))
-        h = fold(h, vmul(a_minus_s, pk.l0))
-        h = fold(h, vmul(vmul(a_minus_s, vsub(ic, rot(ic, -1, rs))), pk.l_active_row))
+    lk_cosets = [[dom.coeff_to_extended(lk[nm].reshape(-1)).reshape(-1, 4) for nm in ("z_poly", "in_poly", "tab_poly")] for lk in lookups]
+    if tr.get("columnwise_h"):
+        h = _h_numerator_columnwise(cs, pk, ext_col, perm_sets, lk_cosets, theta, beta, gamma, y, ext_n, rs, bf)
+    else:
+        h = _h_numerator_program(cs, pk, advice_cosets, inst_coset, perm_sets, lk_cosets, theta, beta, gamma, y, ext_n, rs, bf)
     tr["h_numerator_ext"] = h
 
     # ---- quotient: divide by t(X), back to coefficients, 5 pieces ----

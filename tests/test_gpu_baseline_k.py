@@ -1,0 +1,119 @@
+"""Driver-run parity at BASELINE's K values (python -m pytest tests -m gpu).
+
+k = 17: `MstInclusionCircuit<4,2,8>` (csv/entry_16.csv, user 0) in the 2^17 domain; k = 20: `MstInclusionCircuit<20,2,8>` for one user of a
+2^20-user Merkle sum tree built on the GPU (BASELINE configs[2] as written).  For each k the GPU proof must
+  (1) equal, byte for byte, the proof the CPU oracle made for the same circuit, unsafe SRS (same tau) and ChaCha20 seed
+      (tests/golden/golden_proof_k{17,20}.npz, written by tests/golden/make_golden_proofs.py),
+  (2) be ACCEPTED by the reference's own verifier contract (tests/golden/InclusionVerifier.sol run by oracle/yul.py with the key's
+      constants), and a tampered proof / instance must be rejected,
+and the key's 11 fixed + 6 permutation commitments computed on the GPU must equal the oracle's (`best_multiexp` on the CPU), which pins
+the k = 17 / 20 keys independently of the proof.  Bit-exact; no tolerance."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_verifier as RV
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(ctx, golden_dir, k, witness_file):
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import fields
+    gold = np.load(os.path.join(golden_dir, f"golden_proof_k{k}.npz"))
+    fx = np.load(os.path.join(golden_dir, witness_file))
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    tau, repr_ = int(gold["tau"][0]), int(gold["transcript_repr"][0])
+    params = sb.ParamsKZG.setup(k, tau, ctx, download=False)
+    pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], repr_, ctx)
+    n = 1 << k
+    advice = np.zeros((3, n, 4), dtype=np.uint64)
+    advice[fx["advice_cells"][:, 0], fx["advice_cells"][:, 1]] = fx["advice_values"]
+    instances = [fields.fr_from_mont(v) for v in fx["instances"]]
+    return sb, gold, fx, params, pk, advice, instances, tau, repr_
+
+
+def _check(sb, gold, pk, advice, instances, k, tau, repr_, fx):
+    f, s = pk.commitments()
+    assert (f == gold["fixed_comms"]).all(), "fixed-column commitments differ from the CPU oracle's keygen"
+    assert (s == gold["sigma_comms"]).all(), "permutation commitments differ from the CPU oracle's keygen"
+    seed = sb.seed_from_u64(int(gold["seed_u64"][0]))
+    got = sb.create_proof(pk, instances, advice, seed, sb.TRANSCRIPT_KECCAK)
+    ref = gold["proof"].tobytes()
+    if got != ref:
+        first = next(i for i in range(min(len(got), len(ref))) if got[i] != ref[i])
+        pytest.fail(f"k = {k}: GPU proof differs from the CPU oracle's golden proof at byte {first:#x}")
+    # the sparse-witness entry gives the same bytes (cells + values instead of A x n dense columns)
+    got_sparse = sb.create_proof_sparse(pk, instances, fx["advice_cells"], fx["advice_values"], seed, sb.TRANSCRIPT_KECCAK)
+    assert got_sparse == ref
+    v = RV.verifier_for_key(k, tau, [RV.B.g1_from_mont_bytes(c.tobytes()) for c in f], [RV.B.g1_from_mont_bytes(c.tobytes()) for c in s], repr_)
+    assert v.verify(got, instances), f"k = {k}: the reference verifier contract rejects the GPU proof"
+    bad = bytearray(got)
+    bad[0x400] ^= 1
+    assert not v.verify(bytes(bad), instances), "tampered evaluation accepted"
+    bad = bytearray(got)
+    bad[0x10] ^= 1   # inside the first advice commitment: either not on the curve or a different point
+    assert not v.verify(bytes(bad), instances), "tampered commitment accepted"
+    assert not v.verify(got, [instances[0] ^ 1] + instances[1:]), "tampered instance accepted"
+    # a fresh seed gives a different proof that verifies too (the golden equality is not a replay)
+    other = sb.create_proof(pk, instances, advice, sb.seed_from_u64(12345), sb.TRANSCRIPT_KECCAK)
+    assert other != got and v.verify(other, instances)
+
+
+def test_k17_proof_equals_cpu_oracle_golden_and_reference_verifier_accepts(ctx, golden_dir):
+    sb, gold, fx, params, pk, advice, instances, tau, repr_ = _setup(ctx, golden_dir, 17, "mst_inclusion_assignment.npz")
+    _check(sb, gold, pk, advice, instances, 17, tau, repr_, fx)
+
+
+def test_k20_levels20_tree_on_gpu_proof_equals_golden_and_reference_verifier_accepts(ctx, golden_dir):
+    """configs[2]: 2^20 users -> Merkle sum tree on the GPU -> Merkle path of user 123456 -> MstInclusionCircuit<20,2,8> at k = 20."""
+    sb, gold, fx, params, pk, advice, instances, tau, repr_ = _setup(ctx, golden_dir, 20, "mst_inclusion_assignment_l20_tree.npz")
+    from circuits_halo2_b200 import fields
+    n_users, index = int(fx["n_users"][0]), int(fx["user_index"][0])
+    bal = np.random.default_rng(int(fx["balance_seed"][0])).integers(0, 1 << 40, size=(n_users, 2), dtype=np.uint64)
+    tree = sb.MerkleSumTree.from_arrays([b"user_%d" % i for i in range(n_users)], bal, ctx=ctx)
+    root = tree.root()
+    # the GPU tree equals the CPU oracle's (C restatement of merkle_sum_tree/): root, and the whole Merkle path of the user
+    assert root.hash == fields.fr_from_mont(fx["root_hash"]) and root.balances == [fields.fr_from_mont(b) for b in fx["root_balances"]]
+    mp = tree.generate_proof(index)
+    assert tree.verify_proof(mp)
+    assert mp.path_indices == [int(b) for b in fx["path_indices"]]
+    assert mp.sibling_leaf_node_hash_preimage == [fields.fr_from_mont(v) for v in fx["sibling_leaf_preimage"]]
+    assert mp.sibling_middle_node_hash_preimages == [[fields.fr_from_mont(v) for v in pre] for pre in fx["sibling_middle_preimages"]]
+    # the circuit's public inputs are the user's leaf hash, the root hash and the root balances of THIS tree
+    assert instances == [tree.node(0, index).hash, root.hash] + list(root.balances)
+    tree.close()
+    _check(sb, gold, pk, advice, instances, 20, tau, repr_, fx)
+
+
+def test_handles_may_outlive_their_context(golden_dir):
+    """Destruction order is free (the context is reference counted by its children; a proving key keeps its SRS alive): destroy the
+    context FIRST, then every child handle type -- the round-1 use-after-free (sb_mst_destroy locking a freed context)."""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import _lib
+    c = sb.Context(0)
+    tree = sb.MerkleSumTree.from_entries([sb.Entry(f"u{i}", [i, 2 * i]) for i in range(5)], ctx=c)
+    params = sb.ParamsKZG.read(os.path.join(golden_dir, "hermez-raw-11"), c)
+    dom = sb.EvaluationDomain(6, 10, c)
+    fx = np.load(os.path.join(golden_dir, "mst_inclusion_assignment.npz"))
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234, c)
+    want_root = tree.root().hash
+    L = _lib.lib()
+    L.sb_ctx_destroy(c._h)          # the caller lets go of the context while four children are alive
+    c._h = ctypes.c_void_p()
+    assert tree.root().hash == want_root      # the tree still works: it holds a reference to the context
+    L.sb_srs_destroy(params._h)     # the SRS before the key that uses it
+    params._h = ctypes.c_void_p()
+    tree.close()
+    del dom
+    del pk
+    # and a fresh context afterwards is healthy
+    c2 = sb.Context(0)
+    t2 = sb.MerkleSumTree.from_entries([sb.Entry("solo", [5])], ctx=c2)
+    assert t2.root().balances == [5]
+    c2.close()
+    t2.close()

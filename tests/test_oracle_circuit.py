@@ -6,8 +6,8 @@
    the floor planner, the Pow5 / range / MST chip layouts, selector compression and Assembly::copy;
  * create_proof: a fresh oracle proof is ACCEPTED by the reference's own verifier
    (contracts/src/InclusionVerifier.sol run by oracle/yul.py), the checked-in golden proof
-   is accepted, tampered proofs / instances are rejected.  The contract text is read from
-   /root/reference (build container only); those tests skip where the tree is absent."""
+   is accepted, tampered proofs / instances are rejected.  The contract text is the committed fixture
+   tests/golden/InclusionVerifier.sol (byte-identical to the reference's file: test_oracle_golden.py)."""
 import json
 import os
 
@@ -21,8 +21,9 @@ from oracle import mst_circuit as C
 from oracle.chacha import ChaCha20Rng
 from oracle.transcript import Blake2bTranscript, KeccakTranscript
 
-SOL = "/root/reference/contracts/src/InclusionVerifier.sol"
-needs_reference = pytest.mark.skipif(not os.path.exists(SOL), reason="reference tree not mounted")
+from oracle.reference_verifier import SOL  # the reference contract, committed unchanged as a fixture
+
+needs_reference = pytest.mark.skipif(not os.path.exists(SOL), reason="verifier fixture missing")
 
 
 @pytest.fixture(scope="module")

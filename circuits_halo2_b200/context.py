@@ -41,6 +41,12 @@ class Context:
     def synchronize(self) -> None:
         _lib.check(_lib.lib().sb_ctx_synchronize(self.handle), "sb_ctx_synchronize")
 
+    def stream(self) -> int:
+        """the context's cudaStream_t (for CUDA-event timing by the caller)"""
+        out = ctypes.c_void_p()
+        _lib.check(_lib.lib().sb_ctx_stream(self.handle, ctypes.byref(out)), "sb_ctx_stream")
+        return out.value or 0
+
     def launch_count(self) -> int:
         out = ctypes.c_uint64()
         _lib.check(_lib.lib().sb_launch_count(self.handle, ctypes.byref(out)), "sb_launch_count")

@@ -240,6 +240,12 @@ int32_t sb_ctx_synchronize(sb_ctx *ctx) {
     return SB_OK;
 }
 
+int32_t sb_ctx_stream(const sb_ctx *ctx, void **out_stream) {
+    if (!ctx || !out_stream) return SB_ERR_ARG;
+    *out_stream = (void *)ctx->stream;
+    return SB_OK;
+}
+
 int32_t sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **out_dptr) {
     if (!ctx || !out_dptr) return SB_ERR_ARG;
     Guard g(ctx);

@@ -100,6 +100,12 @@ struct sb_ctx {
     cudaEvent_t msm_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float msm_phase_ms[5] = {0, 0, 0, 0, 0};
     uint32_t msm_last_shape[4] = {0, 0, 0, 0};  // c, W, L1, seg_log of the last MSM
+    // running totals over MSM launch sets since the last sb_perf_reset (create_proof resets them at entry): the phase times above, the
+    // signed digits (= level-1 mixed additions) sorted and accumulated, and the number of launch sets
+    float acc_msm_ms[5] = {0, 0, 0, 0, 0};
+    uint64_t acc_msm_digits = 0;
+    uint32_t acc_msm_sets = 0;
+    // device time of every NTT pass kernel since the last reset is NOT kept (it would need an event pair per pass); bench.py's ncu launch list has it
     // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
     cudaEvent_t h_ev[2] = {nullptr, nullptr};
     float last_h_ms = 0;

@@ -791,6 +791,9 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     SB_CUDA_TRY(cudaStreamSynchronize(st));
     for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
     cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
+    for (int e = 0; e < 5; e++) ctx->acc_msm_ms[e] += ctx->msm_phase_ms[e];   // running totals since sb_perf_reset (one proof = several launch sets)
+    ctx->acc_msm_digits += (uint64_t)sh.W * n * batch;
+    ctx->acc_msm_sets++;
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
     if (w_hi >= 0) memcpy(out_affine, ctx->pinned, (size_t)sh.Wb * 128);
     else if (tabs)

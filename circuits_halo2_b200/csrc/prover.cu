@@ -839,6 +839,9 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         t_prev = now;
     };
     for (int i = 0; i < 12; i++) ctx->last_proof_stage_ms[i] = 0;
+    for (int i = 0; i < 5; i++) ctx->acc_msm_ms[i] = 0;
+    ctx->acc_msm_digits = 0;
+    ctx->acc_msm_sets = 0;
     // Side stream: coeff_to_extended of the per-proof polynomials depends on no later challenge, so it is enqueued as soon as a
     // polynomial exists and runs under the latency-bound tails of the commitments on the main stream; joined before evaluate_h.
     const bool use_side = ctx->side_stream && st == ctx->stream && !ctx->tune.no_side_stream;
@@ -1500,6 +1503,13 @@ int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *com
     w.host = advice;
     return create_proof_entry(ctx, pk, comm, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
 }
+int32_t sb_create_proof_sharded_dev(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const void *d_advice,
+                                    const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
+    if (!comm || !d_advice) return SB_ERR_ARG;
+    Witness w;
+    w.dev = d_advice;
+    return create_proof_entry(ctx, pk, comm, instances, n_instances, w, rng_seed, transcript_kind, proof_out, proof_cap, proof_len);
+}
 int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells,
                                        const uint8_t *advice_cell_values, size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out,
                                        size_t proof_cap, size_t *proof_len) {
@@ -1782,6 +1792,13 @@ int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_progra
     return SB_OK;
 }
 
+int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digits, uint32_t *out_launch_sets) {
+    if (!ctx || !out_ms) return SB_ERR_ARG;
+    for (int i = 0; i < 5; i++) out_ms[i] = ctx->acc_msm_ms[i];
+    if (out_digits) *out_digits = ctx->acc_msm_digits;
+    if (out_launch_sets) *out_launch_sets = ctx->acc_msm_sets;
+    return SB_OK;
+}
 int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]) {
     if (!ctx || !out_ms) return SB_ERR_ARG;
     for (int i = 0; i < 12; i++) out_ms[i] = ctx->last_proof_stage_ms[i];

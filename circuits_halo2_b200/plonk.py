@@ -235,7 +235,8 @@ def create_proof_sparse(pk: ProvingKey, instances: Sequence[int], advice_cells, 
     return _finish(st, "sb_create_proof_sharded_sparse", comm, out, plen)
 
 
-def create_proof_dev(pk: ProvingKey, instances: Sequence[int], d_advice: int, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, ctx: Optional[Context] = None) -> bytes:
+def create_proof_dev(pk: ProvingKey, instances: Sequence[int], d_advice: int, rng_seed: bytes, transcript: int = TRANSCRIPT_KECCAK, comm=None,
+                     ctx: Optional[Context] = None) -> bytes:
     """Same proof with the advice columns already in device memory (`d_advice`: device pointer to A x n x 32 B; left untouched)."""
     if len(rng_seed) != 32:
         raise AssertionError("rng_seed must be 32 bytes")
@@ -244,6 +245,10 @@ def create_proof_dev(pk: ProvingKey, instances: Sequence[int], d_advice: int, rn
     out = np.zeros(cap, dtype=np.uint8)
     plen = ctypes.c_size_t()
     seed = np.frombuffer(rng_seed, dtype=np.uint8).copy()
+    if comm is not None:
+        st = _lib.lib().sb_create_proof_sharded_dev((ctx or pk.ctx).handle, pk.handle, ctypes.byref(comm.struct), ptr(inst), ctypes.c_size_t(len(instances)),
+                                                    ctypes.c_void_p(d_advice), ptr(seed), ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
+        return _finish(st, "sb_create_proof_sharded_dev", comm, out, plen)
     st = _lib.lib().sb_create_proof_dev((ctx or pk.ctx).handle, pk.handle, ptr(inst), ctypes.c_size_t(len(instances)), ctypes.c_void_p(d_advice), ptr(seed),
                                         ctypes.c_int32(transcript), ptr(out), ctypes.c_size_t(cap), ctypes.byref(plen))
     return _finish(st, "sb_create_proof_dev", None, out, plen)
@@ -276,6 +281,18 @@ class BatchProver:
     def prove_many(self, jobs):
         """jobs: iterable of (instances, advice, rng_seed, transcript); returns the proofs in job order."""
         return list(self._pool.map(self._one, jobs))
+
+    def _one_sparse(self, job):
+        instances, cells, values, seed, transcript = job
+        c = self._free.get()
+        try:
+            return create_proof_sparse(self.pk, instances, cells, values, seed, transcript, ctx=c)
+        finally:
+            self._free.put(c)
+
+    def prove_many_sparse(self, jobs):
+        """jobs: iterable of (instances, advice_cells, advice_values, rng_seed, transcript): the sparse-witness entry, one user per job."""
+        return list(self._pool.map(self._one_sparse, jobs))
 
     def close(self):
         self._pool.shutdown(wait=True)

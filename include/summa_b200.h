@@ -48,6 +48,8 @@ int32_t sb_device_count(int32_t *out_count);
 int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx);
 int32_t sb_ctx_destroy(sb_ctx *ctx);
 int32_t sb_ctx_synchronize(sb_ctx *ctx);
+/* the context's own CUDA stream (a cudaStream_t): callers that time with CUDA events record them here */
+int32_t sb_ctx_stream(const sb_ctx *ctx, void **out_stream);
 /* device memory helpers for callers without a CUDA runtime of their own (Rust FFI crate) */
 int32_t sb_dev_alloc(sb_ctx *ctx, size_t bytes, void **out_dptr);
 int32_t sb_dev_free(sb_ctx *ctx, void *dptr);
@@ -168,6 +170,8 @@ typedef struct sb_comm {
 } sb_comm;
 int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
                                 const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+int32_t sb_create_proof_sharded_dev(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const void *d_advice,
+                                    const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
 int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells,
                                        const uint8_t *advice_cell_values, size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out,
                                        size_t proof_cap, size_t *proof_len);
@@ -178,6 +182,9 @@ int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program
  * [2] permutation products, [3] lookup product, [4] random polynomial, [5] coset NTTs, [6] evaluate_h, [7] quotient + commitments,
  * [8] evaluations, [9] SHPLONK */
 int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]);
+/* the commitments (MSM launch sets) of the last create_proof on this context: summed device times of the phases listed at sb_msm_phase_times,
+ * the number of signed digits accumulated (= level-1 mixed additions: sum over launch sets of windows x points x vectors) and of launch sets */
+int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digits, uint32_t *out_launch_sets);
 /* building blocks of create_proof with host buffers (halo2 arithmetic::{eval_polynomial, kate_division},
  * poly::batch_invert, the grand-product scan of permutation / lookup Z, lookup `permute_expression_pair`) */
 int32_t sb_fr_batch_invert(sb_ctx *ctx, uint8_t *a, size_t n);                                   /* zeros stay zero */

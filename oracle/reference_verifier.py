@@ -78,3 +78,37 @@ def verify_mont(k: int, tau: int, fixed_comms_mont, sigma_comms_mont, transcript
     pts = lambda a: [B.g1_from_mont_bytes(np.ascontiguousarray(c).tobytes()) for c in a]
     v = verifier_for_key(k, tau, pts(fixed_comms_mont), pts(sigma_comms_mont), transcript_repr)
     return v.verify(bytes(proof), [B.fr_from_mont_bytes(np.ascontiguousarray(x).tobytes()) for x in instances_mont])
+
+
+def expected_key_commitments(k: int, tau: int, n_fixed: int, n_perm: int, fixed_cells, fixed_values_mont, perm_cells):
+    """keygen_vk's commitments in CLOSED FORM for an SRS whose secret is known (the unsafe test SRS): commit_lagrange(v) = [sum_i v_i L_i(tau)] G
+    with L_i(tau) = omega^i (tau^n - 1) / (n (tau - omega^i)).  A fixed column is the sum over its assigned cells; a permutation column is the
+    identity column delta^c omega^i -- whose commitment is [delta^c tau] G because sum_i omega^i L_i(X) = X -- plus the cells copy constraints
+    moved.  Independent of every MSM / NTT / SRS array, at any k, in milliseconds: pins the k = 17 / 20 / 23 keys.
+    Returns (fixed, sigma) lists of affine points (x, y)."""
+    import numpy as np
+    from . import cpu
+    R = B.R
+    n = 1 << k
+    dom = B.EvaluationDomain(6, k)
+    c0 = (pow(tau, n, R) - 1) * dom.ifft_divisor % R
+    lag = {}
+
+    def L(i):
+        if i not in lag:
+            w = pow(dom.omega, i, R)
+            lag[i] = w * c0 % R * pow((tau - w) % R, -1, R) % R
+        return lag[i]
+    g = np.frombuffer(B.g1_to_mont_bytes((1, 2)), dtype=np.uint64)
+    mont = lambda x: np.frombuffer(B.fr_to_mont_bytes(x % R), dtype=np.uint64)
+    point = lambda s: B.g1_from_mont_bytes(cpu.g1_mul(g, mont(s)).tobytes())
+    fsum = [0] * n_fixed
+    for (c, row), v in zip(np.asarray(fixed_cells), np.asarray(fixed_values_mont)):
+        fsum[int(c)] = (fsum[int(c)] + B.fr_from_mont_bytes(np.ascontiguousarray(v).tobytes()) * L(int(row))) % R
+    ssum = [pow(B.DELTA, c, R) * tau % R for c in range(n_perm)]
+    for c, row, tc, trow in np.asarray(perm_cells):
+        c, row, tc, trow = int(c), int(row), int(tc), int(trow)
+        new = pow(B.DELTA, tc, R) * pow(dom.omega, trow, R) % R
+        old = pow(B.DELTA, c, R) * pow(dom.omega, row, R) % R
+        ssum[c] = (ssum[c] + (new - old) * L(row)) % R
+    return [point(s) for s in fsum], [point(s) for s in ssum]

@@ -69,6 +69,9 @@ void ctx_read_env(sb_ctx *ctx) {
     t.msm_seg = geti("SB_MSM_SEG", -1);
     t.msm_seg1 = geti("SB_MSM_SEG1", 2);
     t.msm_finish_at = geti("SB_MSM_FINISH_AT", 16384);
+    t.ntt_tile = geti("SB_NTT_TILE", 0);
+    t.ntt_passes = geti("SB_NTT_PASSES", 0);
+    t.ntt_tw_mb = geti("SB_NTT_TW_MB", 1024);
     t.msm_no_cta_scan = getb("SB_MSM_NO_CTA_SCAN");
     t.shard_msm_by_range = getb("SB_SHARD_MSM_BY_RANGE");
     t.no_side_stream = getb("SB_NO_SIDE_STREAM");
@@ -513,23 +516,35 @@ int32_t sb_domain_extended_k(const sb_domain *domain, uint32_t *out) {
     return SB_OK;
 }
 
+// EvaluationDomain's scalings ride inside the transform (ntt.cu NttFuse): no separate pass over the data for n^-1, the zeta-coset pattern,
+// the zero padding to the extended size, t(X)^-1 or the truncation to (j - 1) n coefficients
 static int32_t l2c_dev(sb_ctx *ctx, const sb_domain *d, void *d_a, cudaStream_t st) {
-    SB_TRY(ntt_run(ctx, d_a, (const uint8_t *)d->omega_inv.v, d->k, st));
-    return fr_scale(ctx, d_a, (size_t)1 << d->k, d->ifft_divisor, st);
+    NttFuse f;
+    f.has_scale = true;
+    f.scale = d->ifft_divisor;
+    return ntt_run_fused(ctx, d_a, d_a, (const uint8_t *)d->omega_inv.v, d->k, &f, st);
 }
 static int32_t c2e_dev(sb_ctx *ctx, const sb_domain *d, const void *d_coeff, void *d_ext, cudaStream_t st) {
-    SB_TRY(fr_scale_pattern_pad(ctx, d_coeff, (size_t)1 << d->k, d_ext, (size_t)1 << d->ext_k, d->coset, 3, st));
-    return ntt_run(ctx, d_ext, (const uint8_t *)d->ext_omega.v, d->ext_k, st);
+    // coefficient i is scaled by zeta^(i mod 3) as it is loaded; coefficients n .. 2^ext_k are zeros that are never read
+    NttFuse f;
+    f.pre_m = 3;
+    for (int i = 0; i < 3; i++) f.pre_pat[i] = d->coset[i];
+    f.n_in = (uint64_t)1 << d->k;
+    return ntt_run_fused(ctx, d_coeff, d_ext, (const uint8_t *)d->ext_omega.v, d->ext_k, &f, st);
 }
-static int32_t e2c_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st) {
-    SB_TRY(ntt_run(ctx, d_ext, (const uint8_t *)d->ext_omega_inv.v, d->ext_k, st));
-    // x * ext_ifft_divisor * zeta^-(i mod 3), truncated to (j-1) * n coefficients
-    fr_t pat[3];
-    for (int i = 0; i < 3; i++) pat[i] = mul(d->coset_inv[i], d->ext_ifft_divisor);
-    const size_t n_out = (size_t)d->quotient_degree << d->k;
-    SB_TRY(fr_scale_pattern(ctx, d_ext, n_out, pat, 3, st));
-    if (d_coeff != d_ext) SB_CUDA_TRY(cudaMemcpyAsync(d_coeff, d_ext, n_out * 32, cudaMemcpyDeviceToDevice, st));
-    return SB_OK;
+// divide != 0: the division by t(X) = X^n - 1 (a pattern of 2^(ext_k - k) constants) is applied to the values as they are loaded
+static int32_t e2c_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, int divide, cudaStream_t st) {
+    NttFuse f;
+    f.has_scale = true;
+    f.scale = d->ext_ifft_divisor;
+    f.post_m = 3;
+    for (int i = 0; i < 3; i++) f.post_pat[i] = d->coset_inv[i];  // zeta^-(i mod 3)
+    f.n_out = (uint64_t)d->quotient_degree << d->k;                // truncated to (j - 1) n coefficients
+    if (divide) {
+        f.pre_m = d->n_t;
+        for (uint32_t i = 0; i < d->n_t; i++) f.pre_pat[i] = d->t_inv[i];
+    }
+    return ntt_run_fused(ctx, d_ext, d_coeff, (const uint8_t *)d->ext_omega_inv.v, d->ext_k, &f, st);
 }
 
 int32_t sb_lagrange_to_coeff_dev(sb_ctx *ctx, const sb_domain *d, void *d_a, void *stream) {
@@ -550,7 +565,7 @@ int32_t sb_coeff_to_extended_dev(sb_ctx *ctx, const sb_domain *d, const void *d_
 int32_t sb_extended_to_coeff_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, void *stream) {
     if (!ctx || !d || !d_coeff || !d_ext) return SB_ERR_ARG;
     Guard g(ctx);
-    return e2c_dev(ctx, d, d_ext, d_coeff, pick_stream(ctx, stream));
+    return e2c_dev(ctx, d, d_ext, d_coeff, 0, pick_stream(ctx, stream));
 }
 int32_t sb_divide_by_vanishing_poly_dev(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *stream) {
     if (!ctx || !d || !d_ext) return SB_ERR_ARG;
@@ -562,7 +577,8 @@ int32_t sb_divide_by_vanishing_poly_dev(sb_ctx *ctx, const sb_domain *d, void *d
 namespace sb {
 int32_t dom_l2c(sb_ctx *ctx, const sb_domain *d, void *d_a, cudaStream_t st) { return l2c_dev(ctx, d, d_a, st); }
 int32_t dom_c2e(sb_ctx *ctx, const sb_domain *d, const void *d_coeff, void *d_ext, cudaStream_t st) { return c2e_dev(ctx, d, d_coeff, d_ext, st); }
-int32_t dom_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st) { return e2c_dev(ctx, d, d_ext, d_coeff, st); }
+int32_t dom_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st) { return e2c_dev(ctx, d, d_ext, d_coeff, 0, st); }
+int32_t dom_div_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st) { return e2c_dev(ctx, d, d_ext, d_coeff, 1, st); }
 int32_t dom_div_vanishing(sb_ctx *ctx, const sb_domain *d, void *d_ext, cudaStream_t st) { return fr_scale_pattern(ctx, d_ext, (size_t)1 << d->ext_k, d->t_inv, d->n_t, st); }
 }  // namespace sb
 extern "C" {
@@ -616,7 +632,7 @@ int32_t sb_extended_to_coeff(sb_ctx *ctx, const sb_domain *d, const uint8_t *ext
     const size_t ne = (size_t)1 << d->ext_k, n_out = (size_t)d->quotient_degree << d->k;
     void *de;
     SB_TRY(host_roundtrip(ctx, ext, ne, nullptr, 0, ne, &de));
-    SB_TRY(e2c_dev(ctx, d, de, de, ctx->stream));
+    SB_TRY(e2c_dev(ctx, d, de, de, 0, ctx->stream));
     SB_CUDA_TRY(cudaMemcpyAsync(coeff, de, n_out * 32, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SB_OK;

@@ -59,6 +59,9 @@ struct Tuning {
     int msm_seg = -1;         // SB_MSM_SEG: log2 segment of the first bucket level (-1 = choose)
     int msm_seg1 = 2;         // SB_MSM_SEG1: log2 segment of later bucket levels
     int msm_finish_at = 16384;  // SB_MSM_FINISH_AT: bucket count below which the hierarchy finishes in one step
+    int ntt_tile = 0;         // SB_NTT_TILE: 11 | 12 = log2 elements per NTT tile (0 = choose from the size)
+    int ntt_passes = 0;       // SB_NTT_PASSES: minimum number of NTT passes (0 = as few as the tile allows)
+    int ntt_tw_mb = 1024;     // SB_NTT_TW_MB: budget (MiB) of a plan's full inter-pass twiddle tables; above it the two-level tables are used
     bool msm_no_cta_scan = false;    // SB_MSM_NO_CTA_SCAN
     bool shard_msm_by_range = false; // SB_SHARD_MSM_BY_RANGE
     bool no_side_stream = false;     // SB_NO_SIDE_STREAM
@@ -135,6 +138,19 @@ inline cudaStream_t pick_stream(sb_ctx *ctx, void *stream) { return stream ? (cu
 
 // ---- entry points of the individual translation units (all take device pointers) ----
 int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n, cudaStream_t st);
+// The same transform with the scalings EvaluationDomain wraps around best_fft folded in (no extra pass over the data), out of place if wanted:
+//   in[i] is read as zero for i >= n_in, multiplied by pre_vec[i] (device vector) and by pre_pat[i % pre_m];
+//   out[i] is multiplied by `scale`, by post_pat[i % post_m] and by post_vec[i] (device vector), and only i < n_out is stored.
+struct NttFuse {
+    const void *pre_vec = nullptr, *post_vec = nullptr;
+    uint32_t pre_m = 0, post_m = 0;
+    fr_t pre_pat[8], post_pat[8];
+    bool has_scale = false;
+    fr_t scale;
+    uint64_t n_in = 0, n_out = 0;  // 0 = the full size
+};
+int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t omega[32], uint32_t log_n, const NttFuse *fuse, cudaStream_t st);
+void ntt_make_plan(uint32_t log_n, uint32_t tile_log, uint32_t max_passes_hint, int *npass, uint32_t *radix);
 void ntt_plans_free(sb_ctx *ctx);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st);

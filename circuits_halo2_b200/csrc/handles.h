@@ -48,6 +48,7 @@ int32_t dom_l2c(sb_ctx *ctx, const sb_domain *d, void *d_a, cudaStream_t st);
 int32_t dom_c2e(sb_ctx *ctx, const sb_domain *d, const void *d_coeff, void *d_ext, cudaStream_t st);
 int32_t dom_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st);
 int32_t dom_div_vanishing(sb_ctx *ctx, const sb_domain *d, void *d_ext, cudaStream_t st);
+int32_t dom_div_e2c(sb_ctx *ctx, const sb_domain *d, void *d_ext, void *d_coeff, cudaStream_t st);  // divide_by_vanishing_poly + extended_to_coeff in one transform
 
 struct CtxGuard {
     std::lock_guard<std::mutex> lk;

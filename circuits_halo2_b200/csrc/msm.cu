@@ -788,11 +788,14 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     // ---- 5: window sums -> host fold ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[4], st));
     SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_win, (size_t)sh.Wb * 128, cudaMemcpyDeviceToHost, st));
+    // the number of non-zero signed digits that were sorted and accumulated (the scan's grand total): the level-1 additions actually performed
+    uint32_t *h_total = (uint32_t *)((uint8_t *)ctx->pinned + ctx->pinned_bytes - 64);
+    SB_CUDA_TRY(cudaMemcpyAsync(h_total, d_counts + nb, 4, cudaMemcpyDeviceToHost, st));
     SB_CUDA_TRY(cudaStreamSynchronize(st));
     for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
     cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
     for (int e = 0; e < 5; e++) ctx->acc_msm_ms[e] += ctx->msm_phase_ms[e];   // running totals since sb_perf_reset (one proof = several launch sets)
-    ctx->acc_msm_digits += (uint64_t)sh.W * n * batch;
+    ctx->acc_msm_digits += *h_total;
     ctx->acc_msm_sets++;
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
     if (w_hi >= 0) memcpy(out_affine, ctx->pinned, (size_t)sh.Wb * 128);

@@ -1,179 +1,183 @@
-// Batched-tile multi-pass NTT over BN254 Fr for sm_100a.
+// Multi-pass NTT over BN254 Fr for sm_100a: register radix-8 tiles, cp.async staging, fused domain scalings.
 //
-// Replaces halo2_proofs::arithmetic::best_fft (reference call sites reach it through
-// EvaluationDomain from zk_prover/src/circuits/utils.rs:75-76,94-102).  Natural order in, natural
-// order out, any power-of-two size up to 2^28.
+// Replaces halo2_proofs::arithmetic::best_fft (reference call sites reach it through EvaluationDomain from
+// zk_prover/src/circuits/utils.rs:75-76,94-102) and carries the scalings EvaluationDomain wraps around it: n^-1 of the
+// inverse transforms, the zeta-coset patterns, t(X)^-1, zero padding and truncation are folded into the first pass' loads, the inter-pass
+// twiddle table or the last pass' stores.  Natural order in, natural order out, any power-of-two size up to 2^28.
 //
 // Decomposition (mixed-radix Cooley-Tukey, "four-step" generalised to P passes):
-//   N = R_1 R_2 ... R_P, every R_t <= 256.  Before pass t the array is indexed [a][j][c] with
-//   a = (k_1 .. k_{t-1}) the digits already transformed, j < R_t the digit transformed now and
-//   c < C_t the still-contiguous remainder.  A CTA owns a tile of R_t x G elements (G consecutive
-//   c's, 2048 elements = 64 KB of shared memory), runs log2(R_t) decimation-in-frequency levels in
-//   shared memory, multiplies by the inter-pass twiddle omega^(A_t c k) and writes row k back.
-//   The last pass reads G rows whose leading digit k_1 is consecutive and scatters them to
-//   out[k_1 + R_1 (k_2 + R_2 (...)) + A k], i.e. every global access of every pass moves G x 32 B
-//   contiguous bytes and each pass is exactly one HBM round trip.
-// Twiddles: per-pass omega_R^e table (<= 128 entries, staged in shared memory) for the butterflies;
-//   inter-pass factors from a two-level table omega^lo * omega^(hi << h) (2 x 2^(n/2) entries,
-//   L2-resident) -- one extra product per element per pass boundary.
-// The index algebra is pinned on the CPU by tests/models/ntt_model.py (same plan, same formulas).
+//   N = R_1 R_2 ... R_P.  Before pass t the array is indexed [a][j][c] with a = (k_1 .. k_{t-1}) the digits already transformed, j < R_t the
+//   digit transformed now and c < C_t the still-contiguous remainder.  A CTA owns a tile of R_t x G elements (2^11 elements = 64 KB of shared
+//   memory with two CTAs per SM, or 2^12 = 128 KB with one), transforms digit j in registers (ntt_core.cuh), multiplies by the inter-pass
+//   twiddle omega^(A_t c k) and writes row k back in place.  The last pass reads G rows whose leading digit k_1 is consecutive (contiguous rows,
+//   staged by cp.async) and scatters them to out[k_1 + R_1 (k_2 + R_2 (...)) + A k]: one HBM round trip per pass, TWO passes up to 2^22 (2^24
+//   with the 128 KB tile), three beyond.
+// Twiddles: per-pass omega_R^e table (R/2 entries, cp.async'ed into shared memory, swizzled); inter-pass factors from ONE table per pass boundary
+//   laid out exactly like the pass' output (coalesced 32-byte reads, one product per element, the plan's scale n^-1 folded in); plans whose
+//   tables would exceed SB_NTT_TW_MB (default 1024 MiB) fall back to a two-level omega^lo * omega^(hi << h) pair (one more product).
+// HBM is not the binding roof for a 254-bit field (~11 products = 1500 wide multiply-adds per 64 B moved per pass); what the layout buys
+// is fewer products (11 per element at 2^22 instead of 13.5), fewer barriers and 3x less shared-memory traffic.
+// The index algebra is pinned on the CPU: tests/host/host_ntt_harness.cpp runs ntt_core.cuh for every thread of every tile.
 #include "common.cuh"
+#include "ntt_core.cuh"
 
 namespace sb {
 
-static const uint32_t TILE_LOG = 11;  // elements per tile (2^11 x 32 B = 64 KB)
-static const uint32_t RMAX_LOG = 8;   // largest per-pass radix (multi-pass plans)
-static const int NTT_THREADS = 256;
-static const int MAX_PASS = 8;
-
-struct NttPassArgs {
-    const uint4 *src;
-    uint4 *dst;
-    const uint4 *w_block;  // omega_R^e, e < R/2 (32 B each)
-    const uint4 *t_lo;     // omega^i, i < 2^log_tlo
-    const uint4 *t_hi;     // omega^(i << log_tlo)
-    uint32_t log_n, log_r, log_g, log_a, log_c, log_r1, log_tlo;
-    uint32_t last, npass, n_mid;
-    uint32_t mid_bits[MAX_PASS];  // radices of passes 2 .. P-1 (for the last pass' digit reversal)
-};
+static const uint32_t SMALL_MAX_LOG = 10;  // single-pass sizes up to here use the simple shared-memory kernel
 
 struct NttPlan {
-    uint32_t log_n = 0;
+    uint32_t log_n = 0, tile_log = 11;
     int npass = 0;
-    uint32_t radix[MAX_PASS];
-    uint4 *w_block[MAX_PASS];
+    uint32_t radix[NTT_MAX_PASS];
+    uint4 *w_block[NTT_MAX_PASS];
+    uint4 *tw_full[NTT_MAX_PASS];  // per strided pass, or null
     uint4 *t_lo = nullptr, *t_hi = nullptr;
     uint32_t log_tlo = 0;
-    void *tables = nullptr;  // one allocation backing all of the above
+    fr_t scale;                   // folded into the first inter-pass boundary (multi-pass plans)
+    void *tables = nullptr;       // w_block + t_lo + t_hi
+    void *full_tables = nullptr;  // the tw_full tables
 };
 
-__device__ __forceinline__ fr_t lds_fr(const uint4 *lo, const uint4 *hi, uint32_t i) {
-    uint4 a = lo[i], b = hi[i];
-    fr_t r;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+struct SmemTwiddle {
+    const uint4 *lo, *hi;
+    __device__ __forceinline__ nfr_t operator()(uint32_t e) const {
+        const uint32_t s = ntt_swz(e);
+        const uint4 a = lo[s], b = hi[s];
+        nfr_t r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+};
+
+__device__ __forceinline__ nfr_t lds_fr(const uint4 *lo, const uint4 *hi, uint32_t i) {
+    const uint4 a = lo[i], b = hi[i];
+    nfr_t r;
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
     r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
     return r;
 }
-__device__ __forceinline__ void sts_fr(uint4 *lo, uint4 *hi, uint32_t i, const fr_t &x) {
+__device__ __forceinline__ void sts_fr(uint4 *lo, uint4 *hi, uint32_t i, const nfr_t &x) {
     lo[i] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     hi[i] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const NttPassArgs p) {
+// One tile of one pass.  blockDim.x = 2^(r + g - 3): eight elements per thread.
+template <int T_LOG>
+__global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pass_kernel(const NttPassArgs p) {
     extern __shared__ uint4 smem[];
-    const uint32_t r = p.log_r, g = p.log_g;
-    const uint32_t R = 1u << r, G = 1u << g, tile = R << g, gmask = G - 1;
+    const NttGeom G(p);
+    const uint32_t tile = 1u << G.t, T = tile >> 3, tid = threadIdx.x, half_r = 1u << (G.r - 1);
     uint4 *s_lo = smem, *s_hi = smem + tile;
-    uint4 *w_lo = s_hi + tile, *w_hi = w_lo + (R > 1 ? R / 2 : 1);
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    uint4 *w_lo = s_hi + tile, *w_hi = w_lo + half_r;
+    const NttTileCoord tc(p, blockIdx.x);
 
-    for (uint32_t e = tid; e < R / 2; e += nt) {
-        w_lo[e] = __ldg(p.w_block + 2 * e);
-        w_hi[e] = __ldg(p.w_block + 2 * e + 1);
+    // butterfly twiddles of this pass: global -> shared through cp.async (no register staging), under the data loads below
+    for (uint32_t e = tid; e < half_r; e += T) {
+        const uint32_t s = ntt_swz(e);
+        cp_async16(w_lo + s, p.w + 2 * e);
+        cp_async16(w_hi + s, p.w + 2 * e + 1);
     }
 
-    // ---- tile coordinates ------------------------------------------------------------
-    const uint64_t tile_id = blockIdx.x;
-    uint64_t base = 0;       // strided / single pass: element (j, gg) at base + (j << log_c) + gg
-    uint32_t c0 = 0;         // first column of the tile (strided pass)
-    uint64_t k1_0 = 0, rest = 0, rev = 0;
-    uint32_t log_rest = 0;
-    if (!p.last) {
-        const uint32_t log_cg = p.log_c - g;
-        const uint64_t a_idx = tile_id >> log_cg;
-        c0 = (uint32_t)(tile_id & ((1ull << log_cg) - 1)) << g;
-        base = (a_idx << (r + p.log_c)) + c0;
-    } else if (p.npass > 1) {
-        log_rest = p.log_a - p.log_r1;
-        rest = tile_id & ((1ull << log_rest) - 1);
-        k1_0 = (tile_id >> log_rest) << g;
-        // digit-reverse rest = (k_2 .. k_{P-1}), most significant first -> k_2 + R_2 k_3 + ...
-        uint64_t tmp = rest;
-        for (int m = (int)p.n_mid - 1; m >= 0; m--) {
-            const uint32_t bits = p.mid_bits[m];
-            const uint64_t d = tmp & ((1ull << bits) - 1);
-            tmp >>= bits;
-            uint32_t shift = 0;  // digit m lands above digits 0 .. m-1
-            for (int q = 0; q < m; q++) shift += p.mid_bits[q];
-            rev |= d << shift;
+    nfr_t x[8];
+    uint32_t pw = G.window(0);
+    if (p.kind == NTT_LAST) {
+        // the tile's G rows are contiguous in HBM: stage them with cp.async, coalesced, straight to their swizzled slots
+        for (uint32_t i = tid; i < tile; i += T) {
+            const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
+            const uint32_t s = ntt_swz(i);
+            cp_async16(s_lo + s, p.src + 2 * gi);
+            cp_async16(s_hi + s, p.src + 2 * gi + 1);
         }
-    }
-
-    // ---- load tile into shared memory (swizzled so both access orders are conflict-free) ---
-    if (!p.last || p.npass == 1) {
-        for (uint32_t idx = tid; idx < tile; idx += nt) {
-            const uint32_t gg = idx & gmask, j = idx >> g;
-            const uint4 *q = p.src + 2 * (base + ((uint64_t)j << p.log_c) + gg);
-            const uint32_t s = (j << g) | (gg ^ (j & gmask));
-            s_lo[s] = q[0];
-            s_hi[s] = q[1];
-        }
+        cp_async_wait_all();
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < 8; b++) x[b] = lds_fr(s_lo, s_hi, ntt_swz(G.idx(tid, pw, (uint32_t)b)));
     } else {
-        for (uint32_t idx = tid; idx < tile; idx += nt) {
-            const uint32_t j = idx & (R - 1), gg = idx >> r;
-            const uint4 *q = p.src + 2 * (((((k1_0 + gg) << log_rest) + rest) << r) + j);
-            const uint32_t s = (j << g) | (gg ^ (j & gmask));
-            s_lo[s] = q[0];
-            s_hi[s] = q[1];
+        const bool first = (p.log_a == 0);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t i = G.idx(tid, pw, (uint32_t)b);
+            const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
+            x[b] = first ? ntt_fetch_input(p, gi) : ntt_load_fr(p.src + 2 * gi);
         }
-    }
-    __syncthreads();
-
-    // ---- log2(R) decimation-in-frequency levels ---------------------------------------------
-    const uint32_t nbf = tile >> 1;
-    for (uint32_t l = 0; l < r; l++) {
-        const uint32_t sh = r - 1 - l, h = 1u << sh;
-        const bool trivial = (l == r - 1);
-        for (uint32_t b = tid; b < nbf; b += nt) {
-            const uint32_t gg = b & gmask, q = b >> g;
-            const uint32_t i = ((q >> sh) << (sh + 1)) | (q & (h - 1));
-            const uint32_t e = (q & (h - 1)) << l;
-            const uint32_t s0 = (i << g) | (gg ^ (i & gmask));
-            const uint32_t i1 = i + h;
-            const uint32_t s1 = (i1 << g) | (gg ^ (i1 & gmask));
-            fr_t u = lds_fr(s_lo, s_hi, s0), v = lds_fr(s_lo, s_hi, s1);
-            sts_fr(s_lo, s_hi, s0, add(u, v));
-            fr_t d = sub(u, v);
-            if (!trivial) d = mul(d, lds_fr(w_lo, w_hi, e));
-            sts_fr(s_lo, s_hi, s1, d);
-        }
+        cp_async_wait_all();
         __syncthreads();
     }
 
-    // ---- write back: row i of the tile holds output digit k = bitrev(i) -----------------------
-    if (!p.last) {
-        const uint32_t lo_mask = (1u << p.log_tlo) - 1;
-        for (uint32_t idx = tid; idx < tile; idx += nt) {
-            const uint32_t gg = idx & gmask, i = idx >> g;
-            const uint32_t k = r ? (__brev(i) >> (32 - r)) : 0;
-            fr_t x = lds_fr(s_lo, s_hi, (i << g) | (gg ^ (i & gmask)));
-            const uint64_t E = ((uint64_t)(c0 + gg) * k) << p.log_a;  // < N
-            if (E != 0) {
-                fr_t tw = ldg_fp<FrParams>(p.t_lo + 2 * (E & lo_mask));
-                const uint64_t eh = E >> p.log_tlo;
-                if (eh) tw = mul(tw, ldg_fp<FrParams>(p.t_hi + 2 * eh));
-                x = mul(x, tw);
-            }
-            store_fp(p.dst + 2 * (base + ((uint64_t)k << p.log_c) + gg), x);
+    const SmemTwiddle tw{w_lo, w_hi};
+    uint32_t low = G.r, prev = pw;
+    for (uint32_t s = 0; s < G.n_stages; s++) {
+        pw = G.window(s);
+        if (s > 0) {
+            __syncthreads();  // every thread is done reading the previous contents of the exchange buffer
+#pragma unroll
+            for (int b = 0; b < 8; b++) sts_fr(s_lo, s_hi, ntt_swz(G.idx(tid, prev, (uint32_t)b)), x[b]);
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 8; b++) x[b] = lds_fr(s_lo, s_hi, ntt_swz(G.idx(tid, pw, (uint32_t)b)));
         }
-    } else if (p.npass == 1) {
-        for (uint32_t idx = tid; idx < tile; idx += nt) {
-            const uint32_t k = r ? (__brev(idx) >> (32 - r)) : 0;
-            store_fp(p.dst + 2 * (uint64_t)k, lds_fr(s_lo, s_hi, idx));
+        ntt_stage_butterflies(x, G, tid, pw, low, tw);
+        low = pw - G.jshift;
+        prev = pw;
+    }
+
+    // ---- write back: register b holds output digit k = bitrev(j) of column gg ----
+    if (p.kind == NTT_LAST && p.g > 0) {
+        // contiguous runs on the output side need gg fastest across lanes: one more exchange
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < 8; b++) sts_fr(s_lo, s_hi, ntt_swz(G.idx(tid, prev, (uint32_t)b)), x[b]);
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t m = tid + T * (uint32_t)b;
+            const uint32_t gg = m & ((1u << p.g) - 1u), jj = m >> p.g;
+            ntt_emit(p, tc, ntt_brev(jj, G.r), gg, lds_fr(s_lo, s_hi, ntt_swz((gg << G.r) | jj)));
         }
     } else {
-        const uint32_t sh_k = p.log_a - p.log_r1;
-        for (uint32_t idx = tid; idx < tile; idx += nt) {
-            const uint32_t gg = idx & gmask, i = idx >> g;
-            const uint32_t k = r ? (__brev(i) >> (32 - r)) : 0;
-            fr_t x = lds_fr(s_lo, s_hi, (i << g) | (gg ^ (i & gmask)));
-            const uint64_t o = (k1_0 + gg) + ((rev + ((uint64_t)k << sh_k)) << p.log_r1);
-            store_fp(p.dst + 2 * o, x);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t i = G.idx(tid, prev, (uint32_t)b);
+            ntt_emit(p, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), x[b]);
         }
     }
 }
 
-// out[i] = base^(i * stride)  (i < count), per-thread square-and-multiply; table setup only
+// sizes below 2^11: the whole transform in one CTA, one level per barrier (launch-bound territory)
+__global__ void __launch_bounds__(256) ntt_small_kernel(const NttPassArgs p) {
+    extern __shared__ uint4 smem[];
+    const uint32_t r = p.r, R = 1u << r;
+    uint4 *s_lo = smem, *s_hi = smem + R;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t j = tid; j < R; j += nt) sts_fr(s_lo, s_hi, j, ntt_fetch_input(p, j));
+    __syncthreads();
+    for (uint32_t l = 0; l < r; l++) {
+        const uint32_t sh = r - 1 - l, h = 1u << sh;
+        for (uint32_t q = tid; q < R / 2; q += nt) {
+            const uint32_t i = ((q >> sh) << (sh + 1)) | (q & (h - 1));
+            const uint32_t e = (q & (h - 1)) << l;
+            const nfr_t u = lds_fr(s_lo, s_hi, i), v = lds_fr(s_lo, s_hi, i + h);
+            sts_fr(s_lo, s_hi, i, add(u, v));
+            nfr_t d = sub(u, v);
+            if (l != r - 1) d = mul(d, ntt_load_fr(p.w + 2 * e));
+            sts_fr(s_lo, s_hi, i + h, d);
+        }
+        __syncthreads();
+    }
+    const NttTileCoord tc(p, 0);
+    for (uint32_t j = tid; j < R; j += nt) ntt_emit(p, tc, r ? (__brev(j) >> (32 - r)) : 0, 0, lds_fr(s_lo, s_hi, j));
+}
+
+// out[i] = base^i  (i < count), per-thread square-and-multiply; table setup only
 __global__ void gen_powers_kernel(uint4 *out, fr_t base, uint64_t count) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -185,6 +189,22 @@ __global__ void gen_powers_kernel(uint4 *out, fr_t base, uint64_t count) {
         e >>= 1;
     }
     store_fp(out + 2 * i, acc);
+}
+// a[i] *= s
+__global__ void scale_table_kernel(uint4 *a, fr_t s, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < count) store_fp(a + 2 * i, mul(load_fp<FrParams>(a + 2 * i), s));
+}
+// out[(k << log_c) + c] = t_lo[E & mask] * t_hi[E >> log_tlo],  E = (c k) << log_a   (t_lo carries the plan's scale)
+__global__ void gen_tw_full_kernel(uint4 *out, const uint4 *t_lo, const uint4 *t_hi, uint32_t log_tlo, uint32_t log_a, uint32_t log_c, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t c = i & ((1ull << log_c) - 1), k = i >> log_c;
+    const uint64_t E = (c * k) << log_a;
+    fr_t tw = load_fp<FrParams>(t_lo + 2 * (E & ((1ull << log_tlo) - 1)));
+    const uint64_t eh = E >> log_tlo;
+    if (eh) tw = mul(tw, load_fp<FrParams>(t_hi + 2 * eh));
+    store_fp(out + 2 * i, tw);
 }
 
 int32_t fr_gen_powers(sb_ctx *ctx, void *d_out, const fr_t &base, size_t count, cudaStream_t st) {
@@ -210,20 +230,29 @@ fr_t fr_from_u64_host(uint64_t x) {
     return to_mont(a);
 }
 
-static void make_radices(uint32_t log_n, int *npass, uint32_t *radix) {
-    if (log_n <= TILE_LOG) {
+// pass radices, most significant digit first; mirrored by tests/host/host_ntt_harness.cpp through sb_test_ntt_plan
+void ntt_make_plan(uint32_t log_n, uint32_t tile_log, uint32_t max_passes_hint, int *npass, uint32_t *radix) {
+    if (log_n <= SMALL_MAX_LOG || log_n <= tile_log) {
         *npass = 1;
         radix[0] = log_n;
         return;
     }
-    uint32_t p = (log_n + RMAX_LOG - 1) / RMAX_LOG;
-    uint32_t base = log_n / p, extra = log_n % p;
+    uint32_t p = (log_n + tile_log - 1) / tile_log;
+    if (max_passes_hint > p) p = max_passes_hint;
+    const uint32_t base = log_n / p, extra = log_n % p;
     *npass = (int)p;
     for (uint32_t t = 0; t < p; t++) radix[t] = base + (t < extra ? 1 : 0);
 }
 
-static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, cudaStream_t st, NttPlan **out) {
+static uint32_t pick_tile_log(const sb_ctx *ctx, uint32_t log_n) {
+    if (ctx->tune.ntt_tile == 11 || ctx->tune.ntt_tile == 12) return (uint32_t)ctx->tune.ntt_tile;
+    if (log_n == 12) return 12;              // one 4096-element tile instead of two passes
+    return (log_n == 23 || log_n == 24) ? 12 : 11;  // two passes up to 2^24
+}
+
+static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, const fr_t &scale, cudaStream_t st, NttPlan **out) {
     std::string key((const char *)omega, 32);
+    key.append((const char *)scale.v, 32);
     key.push_back((char)log_n);
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) {
@@ -232,11 +261,13 @@ static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, cu
     }
     NttPlan *pl = new NttPlan();
     pl->log_n = log_n;
-    make_radices(log_n, &pl->npass, pl->radix);
+    pl->scale = scale;
+    pl->tile_log = pick_tile_log(ctx, log_n);
+    ntt_make_plan(log_n, pl->tile_log, (uint32_t)(ctx->tune.ntt_passes > 0 ? ctx->tune.ntt_passes : 0), &pl->npass, pl->radix);
     pl->log_tlo = (log_n + 1) / 2;
     const uint64_t n_lo = 1ull << pl->log_tlo, n_hi = 1ull << (log_n - pl->log_tlo);
     uint64_t total = n_lo + n_hi;
-    uint64_t off_w[MAX_PASS];
+    uint64_t off_w[NTT_MAX_PASS];
     for (int t = 0; t < pl->npass; t++) {
         off_w[t] = total;
         uint64_t cnt = (1ull << pl->radix[t]) / 2;
@@ -248,6 +279,13 @@ static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, cu
         set_last_error("ntt plan: cudaMalloc(%llu) failed: %s", (unsigned long long)(total * 32), cudaGetErrorString(e));
         return SB_ERR_ALLOC;
     }
+    auto fail = [&](int32_t rc) {
+        cudaStreamSynchronize(st);
+        cudaFree(pl->tables);
+        if (pl->full_tables) cudaFree(pl->full_tables);
+        delete pl;
+        return rc;
+    };
     uint4 *tb = (uint4 *)pl->tables;
     pl->t_lo = tb;
     pl->t_hi = tb + 2 * n_lo;
@@ -258,18 +296,48 @@ static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, cu
         SB_LAUNCH(ctx, gen_powers_kernel, blocks, 128, 0, st, dst, b, cnt);
         return SB_OK;
     };
-    SB_TRY(gen(pl->t_lo, w, n_lo));
-    SB_TRY(gen(pl->t_hi, fr_pow_host(w, n_lo), n_hi));
-    for (int t = 0; t < pl->npass; t++) {
+    int32_t rc = gen(pl->t_lo, w, n_lo);
+    if (rc == SB_OK) rc = gen(pl->t_hi, fr_pow_host(w, n_lo), n_hi);
+    for (int t = 0; t < pl->npass && rc == SB_OK; t++) {
         pl->w_block[t] = tb + 2 * off_w[t];
+        pl->tw_full[t] = nullptr;
         uint64_t cnt = (1ull << pl->radix[t]) / 2;
         if (cnt == 0) cnt = 1;
-        // omega_R = omega^(N / R)
-        SB_TRY(gen(pl->w_block[t], fr_pow_host(w, 1ull << (log_n - pl->radix[t])), cnt));
+        rc = gen(pl->w_block[t], fr_pow_host(w, 1ull << (log_n - pl->radix[t])), cnt);  // omega_R = omega^(N / R)
     }
-    // the tables are generated on `st` but a plan is used from any stream of the context afterwards (create_proof runs its coset NTTs
-    // on a side stream): make them visible once, here
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc != SB_OK) return fail(rc);
+    // one inter-pass twiddle table per strided pass, in the pass' output layout, when they fit the budget
+    if (pl->npass > 1) {
+        uint64_t full = 0, log_a = 0;
+        for (int t = 0; t + 1 < pl->npass; t++) { full += 1ull << (log_n - log_a); log_a += pl->radix[t]; }
+        if (full * 32 <= (uint64_t)ctx->tune.ntt_tw_mb << 20) {
+            e = cudaMalloc(&pl->full_tables, full * 32);
+            if (e == cudaSuccess) {
+                uint64_t off = 0;
+                log_a = 0;
+                for (int t = 0; t + 1 < pl->npass; t++) {
+                    const uint64_t cnt = 1ull << (log_n - log_a);
+                    const uint32_t log_c = log_n - (uint32_t)log_a - pl->radix[t];
+                    pl->tw_full[t] = (uint4 *)pl->full_tables + 2 * off;
+                    gen_tw_full_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(pl->tw_full[t], pl->t_lo, pl->t_hi, pl->log_tlo, (uint32_t)log_a, log_c, cnt);
+                    ctx->launches++;
+                    if (t == 0 && !(scale == fr_t::one())) {
+                        // the plan's scale (n^-1 of an inverse transform) rides in the FIRST boundary's twiddles: no pass of its own
+                        scale_table_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(pl->tw_full[t], scale, cnt);
+                        ctx->launches++;
+                    }
+                    off += cnt;
+                    log_a += pl->radix[t];
+                }
+            } else {
+                cudaGetLastError();  // no room: the two-level tables do the job
+                pl->full_tables = nullptr;
+            }
+        }
+    }
+    if (cudaGetLastError() != cudaSuccess) return fail(SB_ERR_CUDA);
+    // the tables are generated on `st` but a plan is used from any stream of the context afterwards: make them visible once, here
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(SB_ERR_CUDA);
     ctx->ntt_plans[key] = pl;
     *out = pl;
     return SB_OK;
@@ -278,32 +346,53 @@ static int32_t plan_get(sb_ctx *ctx, const uint8_t omega[32], uint32_t log_n, cu
 void ntt_plans_free(sb_ctx *ctx) {
     for (auto &kv : ctx->ntt_plans) {
         if (kv.second->tables) cudaFree(kv.second->tables);
+        if (kv.second->full_tables) cudaFree(kv.second->full_tables);
         delete kv.second;
     }
     ctx->ntt_plans.clear();
 }
 
-static size_t pass_smem(uint32_t log_r, uint32_t log_g) {
-    size_t tile = (size_t)1 << (log_r + log_g);
-    size_t w = ((size_t)1 << log_r) / 2;
-    if (w == 0) w = 1;
-    return (tile + w) * 32;
-}
+static size_t pass_smem(uint32_t r, uint32_t g) { return ((size_t)32 << (r + g)) + ((size_t)16 << r); }
 
-int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n, cudaStream_t st) {
+int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t omega[32], uint32_t log_n, const NttFuse *fuse, cudaStream_t st) {
     SB_REQUIRE(log_n <= 28, "best_fft: log_n > 28 (Fr two-adicity is 28)");
-    if (log_n == 0) return SB_OK;
+    const uint64_t n = 1ull << log_n;
+    NttFuse f0;
+    if (!fuse) fuse = &f0;
+    SB_REQUIRE(fuse->pre_m <= 8 && fuse->post_m <= 8, "ntt: pattern lengths must be <= 8");
+    const uint64_t n_in = fuse->n_in ? fuse->n_in : n, n_out = fuse->n_out ? fuse->n_out : n;
+    SB_REQUIRE(n_in <= n && n_out <= n, "ntt: n_in / n_out exceed the transform size");
+    const bool has_scale = fuse->has_scale;
+    if (log_n == 0) {
+        // the identity transform: only the fused scalings remain
+        if (d_out != d_in) SB_CUDA_TRY(cudaMemcpyAsync(d_out, d_in, 32, cudaMemcpyDeviceToDevice, st));
+        fr_t s = has_scale ? fuse->scale : fr_t::one();
+        if (fuse->pre_m) s = mul(s, fuse->pre_pat[0]);
+        if (fuse->post_m) s = mul(s, fuse->post_pat[0]);
+        SB_REQUIRE(!fuse->pre_vec && !fuse->post_vec, "ntt: vector scalings on a size-1 transform are not supported");
+        return (s == fr_t::one()) ? SB_OK : fr_scale(ctx, d_out, 1, s, st);
+    }
     NttPlan *pl = nullptr;
-    SB_TRY(plan_get(ctx, omega, log_n, st, &pl));
+    // multi-pass plans carry the scale in their inter-pass twiddles; single-pass plans apply it with the post pattern
+    const fr_t one = fr_t::one();
+    SB_TRY(plan_get(ctx, omega, log_n, (has_scale && log_n > SMALL_MAX_LOG) ? fuse->scale : one, st, &pl));
+    const bool scale_in_post = has_scale && pl->npass == 1;
     static bool attr_set[64] = {false};  // per device
     if (ctx->device >= 64 || !attr_set[ctx->device]) {
-        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(TILE_LOG, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)32 << SMALL_MAX_LOG)));
         if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     const size_t bytes = (size_t)32 << log_n;
-    void *d_tmp = nullptr;
-    // the ping-pong buffer is per stream: create_proof runs coset NTTs on the side stream while the main stream transforms other columns
-    if (pl->npass > 1) SB_TRY(scratch_get(ctx, st == ctx->side_stream ? "ntt_tmp_side" : "ntt_tmp", bytes, &d_tmp));
+    // strided passes run in place on a work buffer, the last pass goes work -> d_out.  The input itself is never written unless d_out == d_in.
+    void *d_work = nullptr;
+    if (pl->npass > 1) {
+        // one ping-pong buffer per stream: calls on different streams of a context may be in flight together
+        char slot[48];
+        snprintf(slot, sizeof slot, "ntt_tmp_%llx", (unsigned long long)(uintptr_t)st);
+        SB_TRY(scratch_get(ctx, slot, bytes, &d_work));
+    }
 
     uint32_t log_a = 0;
     for (int t = 0; t < pl->npass; t++) {
@@ -311,32 +400,62 @@ int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n,
         memset(&a, 0, sizeof a);
         const bool last = (t == pl->npass - 1);
         a.log_n = log_n;
-        a.log_r = pl->radix[t];
-        a.log_g = pl->npass == 1 ? 0 : TILE_LOG - a.log_r;
+        a.r = pl->radix[t];
         a.log_a = log_a;
-        a.log_c = log_n - log_a - a.log_r;
+        a.log_c = log_n - log_a - a.r;
         a.log_r1 = pl->radix[0];
         a.log_tlo = pl->log_tlo;
-        a.last = last ? 1 : 0;
         a.npass = (uint32_t)pl->npass;
+        a.kind = pl->npass == 1 ? NTT_SINGLE : (last ? NTT_LAST : NTT_STRIDED);
+        a.g = pl->npass == 1 ? 0 : pl->tile_log - a.r;
+        if (a.kind == NTT_STRIDED && a.g > a.log_c) a.g = a.log_c;
+        if (a.kind == NTT_LAST && a.g > a.log_r1) a.g = a.log_r1;
         a.n_mid = 0;
         for (int m = 1; m < pl->npass - 1; m++) a.mid_bits[a.n_mid++] = pl->radix[m];
-        a.w_block = pl->w_block[t];
+        a.w = pl->w_block[t];
+        a.tw_full = last ? nullptr : pl->tw_full[t];
         a.t_lo = pl->t_lo;
         a.t_hi = pl->t_hi;
-        // ping-pong: first pass d_a -> tmp, middle passes tmp -> tmp (in place), last pass tmp -> d_a
-        if (pl->npass == 1) {
-            a.src = (const uint4 *)d_a;
-            a.dst = (uint4 *)d_a;
-        } else {
-            a.src = (const uint4 *)(t == 0 ? d_a : d_tmp);
-            a.dst = (uint4 *)(last ? d_a : d_tmp);
+        if (t == 0 && !last && !a.tw_full && !(pl->scale == one)) { a.has_tw_scale = 1; a.tw_scale = pl->scale; }
+        a.n_in = n;
+        a.n_out = n;
+        if (t == 0) {
+            a.pre_vec = (const uint4 *)fuse->pre_vec;
+            a.pre_m = fuse->pre_m;
+            for (uint32_t i = 0; i < fuse->pre_m; i++) a.pre_pat[i] = fuse->pre_pat[i];
+            a.n_in = n_in;
         }
-        const uint64_t tiles = 1ull << (log_n - a.log_r - a.log_g);
-        SB_LAUNCH(ctx, ntt_pass_kernel, (unsigned)tiles, NTT_THREADS, pass_smem(a.log_r, a.log_g), st, a);
-        log_a += a.log_r;
+        if (last) {
+            a.n_out = n_out;
+            a.post_vec = (const uint4 *)fuse->post_vec;
+            a.post_m = fuse->post_m;
+            for (uint32_t i = 0; i < fuse->post_m; i++) a.post_pat[i] = scale_in_post ? mul(fuse->post_pat[i], fuse->scale) : fuse->post_pat[i];
+            if (scale_in_post && fuse->post_m == 0) { a.post_m = 1; a.post_pat[0] = fuse->scale; }
+        }
+        if (pl->npass == 1) {
+            a.src = (const uint4 *)d_in;
+            a.dst = (uint4 *)d_out;
+        } else {
+            // first pass reads the caller's input and writes the work buffer at the same indices; middle passes stay in place
+            a.src = (const uint4 *)(t == 0 ? d_in : d_work);
+            a.dst = (uint4 *)(last ? d_out : d_work);
+        }
+        if (a.r <= SMALL_MAX_LOG && pl->npass == 1) {
+            const unsigned nt = a.r >= 9 ? 256u : (a.r >= 6 ? 64u : 32u);
+            SB_LAUNCH(ctx, ntt_small_kernel, 1, nt, (size_t)32 << a.r, st, a);
+        } else {
+            const uint64_t tiles = 1ull << (log_n - a.r - a.g);
+            const unsigned threads = 1u << (a.r + a.g - 3);
+            if (a.r + a.g == 12) SB_LAUNCH(ctx, ntt_pass_kernel<12>, (unsigned)tiles, threads, pass_smem(a.r, a.g), st, a);
+            else SB_LAUNCH(ctx, ntt_pass_kernel<11>, (unsigned)tiles, threads, pass_smem(a.r, a.g), st, a);
+        }
+        log_a += a.r;
     }
     return SB_OK;
+}
+
+int32_t ntt_run(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log_n, cudaStream_t st) {
+    return ntt_run_fused(ctx, d_a, d_a, omega, log_n, nullptr, st);
 }
 
 }  // namespace sb

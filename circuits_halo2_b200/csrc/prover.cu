@@ -422,16 +422,19 @@ int32_t poly_div_by_roots_k(sb_ctx *ctx, uint32_t k, const fr_t &omega_d, const 
     const size_t n = (size_t)1 << k;
     void *d_den;
     SB_TRY(scratch_get(ctx, "div_den", n * 32, &d_den));
-    SB_TRY(fp_vec_op(ctx, 0, 0, d_p, g_pows, d_p, n, st));
-    SB_TRY(ntt_run(ctx, d_p, (const uint8_t *)omega_d.v, k, st));
+    {
+        NttFuse f;
+        f.pre_vec = g_pows;
+        SB_TRY(ntt_run_fused(ctx, d_p, d_p, (const uint8_t *)omega_d.v, k, &f, st));
+    }
     std::vector<fr_t> rd;
     for (const Fr &r : roots) rd.push_back(to_dev(r));
     SB_TRY(fr_vanish(ctx, div_x, rd, d_den, n, st));
     SB_TRY(fr_batch_invert(ctx, d_den, n, st));
     SB_TRY(fp_vec_op(ctx, 0, 0, d_p, d_den, d_p, n, st));
-    SB_TRY(ntt_run(ctx, d_p, (const uint8_t *)omega_inv_d.v, k, st));
-    SB_TRY(fp_vec_op(ctx, 0, 0, d_p, ginv_scaled, d_p, n, st));
-    return SB_OK;
+    NttFuse fi;
+    fi.post_vec = ginv_scaled;
+    return ntt_run_fused(ctx, d_p, d_p, (const uint8_t *)omega_inv_d.v, k, &fi, st);
 }
 int32_t poly_div_by_roots(sb_ctx *ctx, const sb_pk *pk, void *d_p, const std::vector<Fr> &roots, cudaStream_t st) {
     return poly_div_by_roots_k(ctx, pk->k, pk->dom->omega, pk->dom->omega_inv, pk->div_g_pows, pk->div_x, pk->div_ginv_scaled, d_p, roots, st);
@@ -523,8 +526,11 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         SB_REQUIRE(head_d.size() <= 4, "shplonk: rotation sets of more than 4 points are not supported");
         SB_TRY(fr_lincomb(ctx, d_nx, lc_polys, lc_coeffs, head_d, n, false, st));
         // N_i on the coset
-        SB_TRY(fp_vec_op(ctx, 0, 0, d_nx, pk->div_g_pows, d_nx, n, st));
-        SB_TRY(ntt_run(ctx, d_nx, (const uint8_t *)pk->dom->omega.v, pk->k, st));
+        {
+            NttFuse f;
+            f.pre_vec = pk->div_g_pows;
+            SB_TRY(ntt_run_fused(ctx, d_nx, d_nx, (const uint8_t *)pk->dom->omega.v, pk->k, &f, st));
+        }
         std::vector<fr_t> comp;
         for (const Fr &p : super) {
             bool in = false;
@@ -534,8 +540,11 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         SB_TRY(fr_div_combine(ctx, d_hx, d_nx, d_invd, pk->div_x, comp, to_dev(v_pow), n, si == 0, st));
         v_pow = hfr::mul(v_pow, v);
     }
-    SB_TRY(ntt_run(ctx, d_hx, (const uint8_t *)pk->dom->omega_inv.v, pk->k, st));
-    SB_TRY(fp_vec_op(ctx, 0, 0, d_hx, pk->div_ginv_scaled, d_hx, n, st));
+    {
+        NttFuse f;
+        f.post_vec = pk->div_ginv_scaled;  // g^-i / n
+        SB_TRY(ntt_run_fused(ctx, d_hx, d_hx, (const uint8_t *)pk->dom->omega_inv.v, pk->k, &f, st));
+    }
     uint8_t pt[64];
     SB_TRY(msm_commit(ctx, comm, pk->srs, 0, d_hx, n, pt, st));
     if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
@@ -804,8 +813,9 @@ int32_t pk_coset_pows(sb_ctx *ctx, const sb_pk *pk, uint32_t j, void **out, cuda
 int32_t coset_values(sb_ctx *ctx, const sb_pk *pk, const void *d_coeff, uint32_t j, void *d_out, cudaStream_t st) {
     void *pw;
     SB_TRY(pk_coset_pows(ctx, pk, j, &pw, st));
-    SB_TRY(fp_vec_op(ctx, 0, 0, d_coeff, pw, d_out, pk->n, st));
-    return ntt_run(ctx, d_out, (const uint8_t *)pk->dom->omega.v, pk->k, st);
+    NttFuse f;
+    f.pre_vec = pw;
+    return ntt_run_fused(ctx, d_coeff, d_out, (const uint8_t *)pk->dom->omega.v, pk->k, &f, st);
 }
 
 // where the assigned advice cells come from: dense host columns (A x n x 32 B), dense device columns (left untouched), or the non-zero cells only
@@ -1234,8 +1244,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     }
     mark();  // [6] evaluate_h (fused program)
     // ---- quotient: / t(X), back to coefficients, pieces
-    if (!comm) SB_TRY(dom_div_vanishing(ctx, d, d_h, st));
-    SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
+    if (!comm) SB_TRY(dom_div_e2c(ctx, d, d_h, d_h, st));  // the sharded path divided while interleaving the cosets
+    else SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
     const int n_pieces = cs.degree - 1;
     for (int i = 0; i < n_pieces; i++) (void)rng.next_fr();
     {

@@ -1,7 +1,8 @@
 """CPU-side checks of the product's own host-testable pieces:
   * the device field / curve headers (fp.cuh, ec.cuh) compiled for the host with the bit-exact
     emulation of the PTX carry chain, compared with the oracle;
-  * the index / control-logic models of the NTT and MSM kernels (tests/models);
+  * the NTT kernel's tile code (csrc/ntt_core.cuh) run for every thread of every tile on the host, and the control-logic model of the
+    MSM kernels (tests/models);
   * the C ABI: the library loads, exports every symbol include/summa_b200.h declares, and refuses
     to create a context without a GPU (no CPU fallback)."""
 import ctypes
@@ -13,7 +14,7 @@ import numpy as np
 import pytest
 
 from oracle import bn254 as B
-from tests.models import msm_model, ntt_model
+from tests.models import msm_model
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -83,20 +84,6 @@ def test_device_curve_code_on_host(harness):
     assert B.g1_from_mont_bytes(out.tobytes()) == B.g1_mul(pts[1], 32)
     harness.ht_add_xyzz(_p(out), _p(_arr(B.g1_to_mont_bytes(pts[1]))), _p(_arr(B.g1_to_mont_bytes(B.g1_mul(pts[1], 2)))))
     assert B.g1_from_mont_bytes(out.tobytes()) == B.g1_mul(pts[1], 8)  # 4p + 2(2p): general-add doubling path
-
-
-@pytest.mark.parametrize("tile_log,rmax_log,ks", [(4, 3, range(1, 12)), (11, 8, (11, 12, 13))])
-def test_ntt_plan_model_matches_best_fft(tile_log, rmax_log, ks):
-    rnd = random.Random(3)
-    old = ntt_model.TILE_LOG, ntt_model.RMAX_LOG
-    ntt_model.TILE_LOG, ntt_model.RMAX_LOG = tile_log, rmax_log
-    try:
-        for k in ks:
-            w = B.omega_for(k)
-            a = [rnd.randrange(B.R) for _ in range(1 << k)]
-            assert ntt_model.ntt(a, w, k) == B.best_fft(a, w, k), (k, ntt_model.plan(k))
-    finally:
-        ntt_model.TILE_LOG, ntt_model.RMAX_LOG = old
 
 
 def _scalars(rnd, n, mode):
@@ -195,3 +182,73 @@ def test_evaluate_h_compiler_matches_direct_evaluation(seed):
     assert a.any() and (a == b).all()
     instr, n_mul, n_add, slots = list(shape)
     assert n_mul <= 125 and slots <= 8 and n_mul + n_add <= instr <= n_mul + n_add + 1, list(shape)
+
+
+# ------------------------------------------------------------------ the NTT tile code (csrc/ntt_core.cuh) on the host
+@pytest.fixture(scope="module")
+def ntt_harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("htntt") / "htntt.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", so,
+                           os.path.join(ROOT, "tests", "host", "host_ntt_harness.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.ht_ntt.restype = ctypes.c_uint32
+    return lib
+
+
+def _run_device_ntt_on_host(lib, log_n, tile, min_passes, full_tw, seed=0, scale=None, pre_vec=None, pre_pat=None, post_pat=None, post_vec=None, n_in=0, n_out=0):
+    """Every thread of every tile of every pass of ntt_pass_kernel, emulated phase by phase on the CPU, vs the oracle's best_fft
+    with the same fused scalings applied as separate passes.  Returns (equal, worst shared-memory bank-conflict degree)."""
+    from oracle import cpu
+    n = 1 << log_n
+    a = cpu.random_fr(n, seed + log_n)
+    w = np.frombuffer(B.fr_to_mont_bytes(B.omega_for(log_n)), dtype=np.uint64).copy()
+    got = a.copy()
+    pp = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None
+    worst = lib.ht_ntt(pp(got), pp(w), log_n, tile, min_passes, int(full_tw), pp(scale), pp(pre_vec), pp(pre_pat), 0 if pre_pat is None else pre_pat.shape[0],
+                       pp(post_pat), 0 if post_pat is None else post_pat.shape[0], ctypes.c_uint64(n_in), ctypes.c_uint64(n_out), pp(post_vec))
+    x = a.copy()
+    if n_in:
+        x[n_in:] = 0
+    if pre_vec is not None:
+        x = cpu.fr_mul(x.reshape(-1), pre_vec.reshape(-1)).reshape(-1, 4)
+    if pre_pat is not None:
+        x = cpu.fr_scale_pattern(x.reshape(-1), pre_pat.reshape(-1)).reshape(-1, 4)
+    ref = cpu.best_fft(x.reshape(-1), w, log_n, threads=4).reshape(-1, 4)
+    if scale is not None:
+        ref = cpu.fr_scale(ref.reshape(-1), scale).reshape(-1, 4)
+    if post_pat is not None:
+        ref = cpu.fr_scale_pattern(ref.reshape(-1), post_pat.reshape(-1)).reshape(-1, 4)
+    if post_vec is not None:
+        ref = cpu.fr_mul(ref.reshape(-1), post_vec.reshape(-1)).reshape(-1, 4)
+    no = n_out or n
+    return bool((got[:no] == ref[:no]).all() and (got[no:].view(np.uint8) == 0xAB).all()), worst
+
+
+@pytest.mark.parametrize("tile", [11, 12])
+def test_device_ntt_tile_code_on_host_all_plans(ntt_harness, tile):
+    """single pass (2^tile), two passes and three passes, full inter-pass twiddle tables and the two-level fallback; every shared-memory
+    access pattern (exchanges, twiddle reads, the last pass' transposition) at most 2-way bank conflicted."""
+    for log_n in range(tile, 17):
+        for min_passes in (0, 3):
+            for full_tw in (0, 1):
+                if log_n <= tile and (min_passes or full_tw):
+                    continue
+                ok, worst = _run_device_ntt_on_host(ntt_harness, log_n, tile, min_passes, full_tw)
+                assert ok, (tile, log_n, min_passes, full_tw)
+                assert worst <= 2, (tile, log_n, min_passes, full_tw, worst)
+
+
+@pytest.mark.parametrize("log_n,tile,min_passes,full_tw", [(11, 11, 0, 0), (12, 12, 0, 0), (13, 11, 0, 1), (15, 11, 3, 0), (15, 12, 0, 1)])
+def test_device_ntt_fused_scalings_on_host(ntt_harness, log_n, tile, min_passes, full_tw):
+    """what EvaluationDomain folds into the transform: n^-1 (scale), zeta^(i mod 3) on the way in, t(X)^-1 (8-pattern) on the way in, zeta^-(i mod 3) on
+    the way out, vector scalings (coset powers, g^-i / n), zero padding (n_in) and truncation (n_out) -- one at a time and all together"""
+    from oracle import cpu
+    n = 1 << log_n
+    m = lambda x: np.frombuffer(B.fr_to_mont_bytes(x % B.R), dtype=np.uint64).copy()
+    scale, pre_vec, post_vec = m(pow(n, -1, B.R)), cpu.random_fr(n, 77), cpu.random_fr(n, 80)
+    pat8, pat3 = cpu.random_fr(8, 78), cpu.random_fr(3, 79)
+    cases = [dict(scale=scale), dict(pre_vec=pre_vec), dict(pre_pat=pat8), dict(pre_pat=pat3), dict(post_pat=pat3), dict(post_vec=post_vec), dict(n_in=n // 8),
+             dict(n_out=5 * n // 8), dict(scale=scale, pre_vec=pre_vec, pre_pat=pat3, post_pat=pat3, post_vec=post_vec, n_in=n // 2, n_out=n // 2 + 3)]
+    for kw in cases:
+        ok, _ = _run_device_ntt_on_host(ntt_harness, log_n, tile, min_passes, full_tw, **kw)
+        assert ok, (log_n, tile, sorted(kw))

@@ -405,8 +405,9 @@ def main():
         ms_sparse, _ = timed(ctx, e2e_sparse, K)
         assert p_dense == proof and p_sparse == proof, "host-witness / sparse-witness proofs differ from the device-witness proof"
         fcom, scom = pkey.commitments()
-        ext_pts = nrow * 8 // world
-        h_rate = ext_pts * int(hprog[1]) / (hms.value * 1e-3) / 1e9 if hms.value else None
+        hrows = ctypes.c_uint64()
+        L.sb_last_h_rows(ctx.handle, ctypes.byref(hrows))   # rows of the quotient's cosets this rank evaluated: (j - 1) = 5 cosets x n on one GPU
+        h_rate = hrows.value * int(hprog[1]) / (hms.value * 1e-3) / 1e9 if hms.value else None
         l1_rate = dig.value * 10 * 136 / (mm[1] * 1e-3) / 1e12 if mm[1] else None
         rec = {"k": pk_k, "circuit": circuit_name(pk_k), "n_gpus": world, "ms_per_proof": ms_res, "e2e_ms_per_proof": ms_dense, "e2e_sparse_witness_ms_per_proof": ms_sparse,
                "h2d_bytes_per_proof": 3 * nrow * 32 + len(insts) * 32, "h2d_bytes_per_proof_sparse": int(cells.nbytes + vals.nbytes) + len(insts) * 32,
@@ -417,7 +418,7 @@ def main():
                        "phases_ms": {"recode_sort": mm[0], "reduce_level1": mm[1], "reduce_levels_ge2": mm[2], "bucket_reduce": mm[3], "device_total": mm[4]},
                        "roofline": {"kernel": "msm_reduce_first_kernel (level-1 bucket accumulation, all commitments of one proof)", "bound": "imad", "achieved": l1_rate,
                                     "peak": imadw_peak, "unit": "T wide-IMAD/s", "frac": l1_rate / imadw_peak if l1_rate else None, "share_of_proof": mm[1] / ms_res}},
-               "evaluate_h": {"ms": hms.value, "instructions": int(hprog[0]), "field_mul": int(hprog[1]), "field_addsub": int(hprog[2]), "live_slots": int(hprog[3]),
+               "evaluate_h": {"ms": hms.value, "rows": int(hrows.value), "instructions": int(hprog[0]), "field_mul": int(hprog[1]), "field_addsub": int(hprog[2]), "live_slots": int(hprog[3]),
                               "roofline": {"kernel": "expr_eval_kernel (fused quotient numerator)", "bound": "imad (field products)", "achieved": h_rate, "peak": fmul_peak,
                                            "unit": "G field-mul/s", "frac": h_rate / fmul_peak if h_rate else None, "share_of_proof": hms.value / ms_res}},
                "_proof": proof, "_fixed_comms": fcom, "_sigma_comms": scom}
@@ -570,9 +571,9 @@ def main():
             "metric": METRIC, "value": head["ms_per_proof"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": head["ms_per_proof"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": DTYPE, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "k": HEADLINE_K, "rows": 1 << HEADLINE_K, "extended_rows": 1 << (HEADLINE_K + 3), "advice": 3, "fixed": 11, "permutation_columns": 6,
+            "config": {"workload": WORKLOAD, "k": HEADLINE_K, "rows": 1 << HEADLINE_K, "quotient_rows": 5 << HEADLINE_K, "advice": 3, "fixed": 11, "permutation_columns": 6,
                        "lookups": 1, "constraint_degree": 6, "srs": "unsafe synthetic SRS, tau = 0x5A110000 + k (no k=20 ptau in the reference tree)", "rng": "ChaCha20 seed_from_u64(42)",
-                       "parallelism": "single GPU" if world == 1 else f"one proof sharded over {world} GPUs: commitments by window, coset NTTs / evaluate_h by coset",
+                       "parallelism": "single GPU" if world == 1 else f"one proof sharded over {world} GPUs: commitments by window, coset NTTs / evaluate_h / quotient iNTTs by coset (5 cosets)",
                        "l2": "working set of a proof (key 5.4 GiB + per-proof columns) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": head["e2e_ms_per_proof"], "unit": UNIT, "ms_per_step": head["e2e_ms_per_proof"], "h2d_bytes_per_step": head["h2d_bytes_per_proof"],
                     "d2h_bytes_per_step": head["d2h_bytes_per_proof"],

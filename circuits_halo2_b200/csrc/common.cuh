@@ -112,6 +112,7 @@ struct sb_ctx {
     // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
     cudaEvent_t h_ev[2] = {nullptr, nullptr};
     float last_h_ms = 0;
+    uint64_t last_h_rows = 0;  // rows the fused program was evaluated on (owned cosets x n)
     uint32_t last_h_program[4] = {0, 0, 0, 0};
     float last_proof_stage_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // prover.cu `mark()` stages
 };
@@ -148,6 +149,10 @@ struct NttFuse {
     bool has_scale = false;
     fr_t scale;
     uint64_t n_in = 0, n_out = 0;  // 0 = the full size
+    // `batch` transforms in ONE launch set (grid.y): transform b reads d_in + b * src_stride (0 = all read the same input), writes
+    // d_out + b * dst_stride (0 = densely packed), uses pre_vec + b * pre_stride and post_vec + b * post_stride (strides in elements)
+    uint32_t batch = 0;
+    uint64_t src_stride = 0, dst_stride = 0, pre_stride = 0, post_stride = 0;
 };
 int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t omega[32], uint32_t log_n, const NttFuse *fuse, cudaStream_t st);
 void ntt_make_plan(uint32_t log_n, uint32_t tile_log, uint32_t max_passes_hint, int *npass, uint32_t *radix);

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
     uint4 *s_lo = smem, *s_hi = smem + tile;
     uint4 *w_lo = s_hi + tile, *w_hi = w_lo + half_r;
     const NttTileCoord tc(p, blockIdx.x);
+    const NttBatch bo(p, blockIdx.y);
 
     // butterfly twiddles of this pass: global -> shared through cp.async (no register staging), under the data loads below
     for (uint32_t e = tid; e < half_r; e += T) {
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         for (uint32_t i = tid; i < tile; i += T) {
             const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
             const uint32_t s = ntt_swz(i);
-            cp_async16(s_lo + s, p.src + 2 * gi);
-            cp_async16(s_hi + s, p.src + 2 * gi + 1);
+            cp_async16(s_lo + s, p.src + 2 * (bo.src + gi));
+            cp_async16(s_hi + s, p.src + 2 * (bo.src + gi) + 1);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         for (int b = 0; b < 8; b++) {
             const uint32_t i = G.idx(tid, pw, (uint32_t)b);
             const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
-            x[b] = first ? ntt_fetch_input(p, gi) : ntt_load_fr(p.src + 2 * gi);
+            x[b] = first ? ntt_fetch_input(p, bo, gi) : ntt_load_fr(p.src + 2 * (bo.src + gi));
         }
         cp_async_wait_all();
         __syncthreads();
@@ -141,13 +142,13 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         for (int b = 0; b < 8; b++) {
             const uint32_t m = tid + T * (uint32_t)b;
             const uint32_t gg = m & ((1u << p.g) - 1u), jj = m >> p.g;
-            ntt_emit(p, tc, ntt_brev(jj, G.r), gg, lds_fr(s_lo, s_hi, ntt_swz((gg << G.r) | jj)));
+            ntt_emit(p, bo, tc, ntt_brev(jj, G.r), gg, lds_fr(s_lo, s_hi, ntt_swz((gg << G.r) | jj)));
         }
     } else {
 #pragma unroll
         for (int b = 0; b < 8; b++) {
             const uint32_t i = G.idx(tid, prev, (uint32_t)b);
-            ntt_emit(p, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), x[b]);
+            ntt_emit(p, bo, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), x[b]);
         }
     }
 }
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(256) ntt_small_kernel(const NttPassArgs p) {
     const uint32_t r = p.r, R = 1u << r;
     uint4 *s_lo = smem, *s_hi = smem + R;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    for (uint32_t j = tid; j < R; j += nt) sts_fr(s_lo, s_hi, j, ntt_fetch_input(p, j));
+    const NttBatch bo(p, blockIdx.y);
+    for (uint32_t j = tid; j < R; j += nt) sts_fr(s_lo, s_hi, j, ntt_fetch_input(p, bo, j));
     __syncthreads();
     for (uint32_t l = 0; l < r; l++) {
         const uint32_t sh = r - 1 - l, h = 1u << sh;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256) ntt_small_kernel(const NttPassArgs p) {
         __syncthreads();
     }
     const NttTileCoord tc(p, 0);
-    for (uint32_t j = tid; j < R; j += nt) ntt_emit(p, tc, r ? (__brev(j) >> (32 - r)) : 0, 0, lds_fr(s_lo, s_hi, j));
+    for (uint32_t j = tid; j < R; j += nt) ntt_emit(p, bo, tc, r ? (__brev(j) >> (32 - r)) : 0, 0, lds_fr(s_lo, s_hi, j));
 }
 
 // out[i] = base^i  (i < count), per-thread square-and-multiply; table setup only
@@ -363,7 +365,10 @@ int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t 
     const uint64_t n_in = fuse->n_in ? fuse->n_in : n, n_out = fuse->n_out ? fuse->n_out : n;
     SB_REQUIRE(n_in <= n && n_out <= n, "ntt: n_in / n_out exceed the transform size");
     const bool has_scale = fuse->has_scale;
+    const uint32_t batch = fuse->batch ? fuse->batch : 1;
+    SB_REQUIRE(batch <= 65535, "ntt: batch too large");
     if (log_n == 0) {
+        SB_REQUIRE(batch == 1, "ntt: batched size-1 transforms are not supported");
         // the identity transform: only the fused scalings remain
         if (d_out != d_in) SB_CUDA_TRY(cudaMemcpyAsync(d_out, d_in, 32, cudaMemcpyDeviceToDevice, st));
         fr_t s = has_scale ? fuse->scale : fr_t::one();
@@ -391,7 +396,7 @@ int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t 
         // one ping-pong buffer per stream: calls on different streams of a context may be in flight together
         char slot[48];
         snprintf(slot, sizeof slot, "ntt_tmp_%llx", (unsigned long long)(uintptr_t)st);
-        SB_TRY(scratch_get(ctx, slot, bytes, &d_work));
+        SB_TRY(scratch_get(ctx, slot, bytes * batch, &d_work));
     }
 
     uint32_t log_a = 0;
@@ -432,22 +437,28 @@ int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t 
             for (uint32_t i = 0; i < fuse->post_m; i++) a.post_pat[i] = scale_in_post ? mul(fuse->post_pat[i], fuse->scale) : fuse->post_pat[i];
             if (scale_in_post && fuse->post_m == 0) { a.post_m = 1; a.post_pat[0] = fuse->scale; }
         }
+        a.pre_bstride = fuse->pre_stride;
+        a.post_bstride = fuse->post_stride;
         if (pl->npass == 1) {
             a.src = (const uint4 *)d_in;
             a.dst = (uint4 *)d_out;
+            a.src_bstride = fuse->src_stride;
+            a.dst_bstride = fuse->dst_stride ? fuse->dst_stride : n;
         } else {
             // first pass reads the caller's input and writes the work buffer at the same indices; middle passes stay in place
             a.src = (const uint4 *)(t == 0 ? d_in : d_work);
             a.dst = (uint4 *)(last ? d_out : d_work);
+            a.src_bstride = t == 0 ? fuse->src_stride : n;
+            a.dst_bstride = last ? (fuse->dst_stride ? fuse->dst_stride : n) : n;
         }
         if (a.r <= SMALL_MAX_LOG && pl->npass == 1) {
             const unsigned nt = a.r >= 9 ? 256u : (a.r >= 6 ? 64u : 32u);
-            SB_LAUNCH(ctx, ntt_small_kernel, 1, nt, (size_t)32 << a.r, st, a);
+            SB_LAUNCH(ctx, ntt_small_kernel, dim3(1, batch), nt, (size_t)32 << a.r, st, a);
         } else {
             const uint64_t tiles = 1ull << (log_n - a.r - a.g);
             const unsigned threads = 1u << (a.r + a.g - 3);
-            if (a.r + a.g == 12) SB_LAUNCH(ctx, ntt_pass_kernel<12>, (unsigned)tiles, threads, pass_smem(a.r, a.g), st, a);
-            else SB_LAUNCH(ctx, ntt_pass_kernel<11>, (unsigned)tiles, threads, pass_smem(a.r, a.g), st, a);
+            if (a.r + a.g == 12) SB_LAUNCH(ctx, ntt_pass_kernel<12>, dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
+            else SB_LAUNCH(ctx, ntt_pass_kernel<11>, dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
         }
         log_a += a.r;
     }

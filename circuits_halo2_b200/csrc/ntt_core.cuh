@@ -38,6 +38,8 @@ struct NttPassArgs {
     uint32_t post_m;   // optional, last pass: output element i is multiplied by post_pat[i % post_m] (post_m <= 8; 0 = off)
     uint64_t n_in;     // first pass: input elements at index >= n_in read as zero (zero-padded polynomial)
     uint64_t n_out;    // last pass: output elements at index >= n_out are not stored (truncation)
+    // batched launch (gridDim.y transforms at once): element strides between consecutive transforms of src / dst / pre_vec / post_vec
+    uint64_t src_bstride, dst_bstride, pre_bstride, post_bstride;
     uint32_t has_tw_scale;  // two-level fallback, first pass: the plan's scale (n^-1 of an inverse transform) multiplies the twiddle
     Fp<FrParams> tw_scale;
     Fp<FrParams> pre_pat[8], post_pat[8];
@@ -173,17 +175,23 @@ SB_HD void ntt_store_fr(uint4 *p, const nfr_t &x) {
 }
 SB_HD nfr_t ntt_zero() { return nfr_t::zero(); }
 
+// element offsets of transform `bi` of a batched launch
+struct NttBatch {
+    uint64_t src, dst, pre, post;
+    SB_HD NttBatch(const NttPassArgs &p, uint32_t bi) : src(bi * p.src_bstride), dst(bi * p.dst_bstride), pre(bi * p.pre_bstride), post(bi * p.post_bstride) {}
+};
+
 // input element `gi` of the first pass with the optional fused pre-operations (zero padding, vector / pattern scaling)
-SB_HD nfr_t ntt_fetch_input(const NttPassArgs &p, uint64_t gi) {
+SB_HD nfr_t ntt_fetch_input(const NttPassArgs &p, const NttBatch &bo, uint64_t gi) {
     if (gi >= p.n_in) return ntt_zero();
-    nfr_t x = ntt_load_fr(p.src + 2 * gi);
-    if (p.pre_vec) x = ntt_mul(x, ntt_load_fr(p.pre_vec + 2 * gi));
+    nfr_t x = ntt_load_fr(p.src + 2 * (bo.src + gi));
+    if (p.pre_vec) x = ntt_mul(x, ntt_load_fr(p.pre_vec + 2 * (bo.pre + gi)));
     if (p.pre_m) x = ntt_mul(x, p.pre_pat[(uint32_t)gi % p.pre_m]);
     return x;
 }
 
 // finishing touch and store of output digit k (already bit-reversed) of column gg
-SB_HD void ntt_emit(const NttPassArgs &p, const NttTileCoord &tc, uint32_t k, uint32_t gg, nfr_t x) {
+SB_HD void ntt_emit(const NttPassArgs &p, const NttBatch &bo, const NttTileCoord &tc, uint32_t k, uint32_t gg, nfr_t x) {
     const uint64_t o = tc.out_index(p, k, gg);
     if (p.kind == NTT_STRIDED) {
         const uint32_t c = tc.c0 + gg;
@@ -200,9 +208,9 @@ SB_HD void ntt_emit(const NttPassArgs &p, const NttTileCoord &tc, uint32_t k, ui
     } else {
         if (o >= p.n_out) return;
         if (p.post_m) x = ntt_mul(x, p.post_pat[(uint32_t)o % p.post_m]);
-        if (p.post_vec) x = ntt_mul(x, ntt_load_fr(p.post_vec + 2 * o));
+        if (p.post_vec) x = ntt_mul(x, ntt_load_fr(p.post_vec + 2 * (bo.post + o)));
     }
-    ntt_store_fr(p.dst + 2 * o, x);
+    ntt_store_fr(p.dst + 2 * (bo.dst + o), x);
 }
 
 }  // namespace sb

@@ -264,10 +264,16 @@ struct sb_pk {
     Fr transcript_repr;
     int P = 0;
     // device-resident (all Montgomery Fr arrays)
+    // The quotient h(X) has degree < (j - 1) n, so its numerator is evaluated on n_cos = j - 1 cosets g_s H of the size-n subgroup (g_s = zeta *
+    // ext_omega^s, s < n_cos: the first n_cos of the 2^(ext_k - k) cosets that make up halo2's extended domain) instead of on all of them: every
+    // "coset" array below is COSET-MAJOR, [n_cos][n], slot s holding the values on g_s H.  h's coefficients come back by one size-n inverse NTT per
+    // coset and a constant n_cos x n_cos matrix (the inverse Vandermonde of g_s^n, with 1 / t(g_s) folded in): the same polynomial, 5/8 of the work.
+    int n_cos = 0;
+    fr_t combine[64];                                            // row-major [q][s]: h_{q n + i} = sum_s combine[q][s] * d_s[i]
     std::vector<void *> fixed_values, fixed_polys, fixed_cosets;
     std::vector<void *> sigma_values, sigma_polys, sigma_cosets;
-    void *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;  // extended
-    void *x_coset = nullptr;                                     // zeta * ext_omega^i (extended)
+    void *l0 = nullptr, *l_last = nullptr, *l_active = nullptr;  // coset-major
+    void *x_coset = nullptr;                                     // X on the cosets: g_s * omega^i (coset-major)
     void *omega_pows = nullptr;                                  // omega^i (n)
     void *div_g_pows = nullptr, *div_x = nullptr, *div_ginv_scaled = nullptr;  // SHPLONK coset division: g^i, g*omega^i, g^-i / n
     std::vector<uint8_t> fixed_comms, sigma_comms;               // affine, 64 B each
@@ -280,8 +286,8 @@ struct sb_pk {
         std::vector<std::pair<uint32_t, int>> delta_beta, ypow;  // (slot, j): delta^j * beta ; (slot, e): y^e
     };
     mutable HProgramCache hcache;
-    // sharded proving: zeta^(m mod 3) * ext_omega^(j m), m < n, for coset j of the extended domain (built on first use)
-    mutable std::vector<void *> coset_pows;
+    // g_s^m and g_s^-m (m < n) for coset slot s, coset-major slabs [n_cos][n]: coefficient scaling before the forward / after the inverse size-n NTT
+    void *coset_pows = nullptr, *coset_pows_inv = nullptr;
     mutable std::vector<void *> owned;
 };
 
@@ -308,9 +314,58 @@ struct SparseAssignment {  // keygen output in sparse form (cells that differ fr
 };
 
 int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint8_t *sigma_values, const SparseAssignment *sparse, cudaStream_t st) {
-    const size_t n = pk->n, en = pk->ext_n;
+    const size_t n = pk->n;
     const sb_domain *d = pk->dom;
     const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+    // ---- the cosets of the quotient argument and the matrix that turns per-coset data back into h's coefficients
+    const int m = pk->n_cos = (int)d->quotient_degree;
+    const size_t cn = (size_t)m * n;  // elements of a coset-major array
+    SB_REQUIRE(m >= 1 && m <= 8 && (uint32_t)m <= d->n_t, "quotient degree must be within the cosets of the extended domain");
+    {
+        const Fr zeta = to_host(d->coset[1]), ext_omega = to_host(d->ext_omega);
+        std::vector<Fr> g(m), v(m);
+        for (int s2 = 0; s2 < m; s2++) {
+            g[s2] = hfr::mul(zeta, hfr::pow_u64(ext_omega, (uint64_t)s2));
+            v[s2] = hfr::pow_u64(g[s2], (uint64_t)n);  // g_s^n: the node of the Vandermonde system sum_q h_q(i) v_s^q = d_s(i)
+        }
+        // invert V[s][q] = v_s^q by Gauss-Jordan (m <= 8)
+        std::vector<std::vector<Fr>> a(m, std::vector<Fr>(2 * m, hfr::ZERO));
+        for (int s2 = 0; s2 < m; s2++) {
+            Fr pw = hfr::ONE;
+            for (int q = 0; q < m; q++) { a[s2][q] = pw; pw = hfr::mul(pw, v[s2]); }
+            a[s2][m + s2] = hfr::ONE;
+        }
+        for (int c = 0; c < m; c++) {
+            int piv = c;
+            while (piv < m && a[piv][c] == hfr::ZERO) piv++;
+            SB_REQUIRE(piv < m, "quotient cosets: singular Vandermonde system");
+            std::swap(a[c], a[piv]);
+            const Fr iv = hfr::inv(a[c][c]);
+            for (int x = 0; x < 2 * m; x++) a[c][x] = hfr::mul(a[c][x], iv);
+            for (int r2 = 0; r2 < m; r2++) {
+                if (r2 == c || a[r2][c] == hfr::ZERO) continue;
+                const Fr f = a[r2][c];
+                for (int x = 0; x < 2 * m; x++) a[r2][x] = hfr::sub(a[r2][x], hfr::mul(f, a[c][x]));
+            }
+        }
+        // combine[q][s] = Vinv[q][s] / t(g_s): the division by the vanishing polynomial (constant on a coset) rides along
+        for (int q = 0; q < m; q++)
+            for (int s2 = 0; s2 < m; s2++) pk->combine[q * 8 + s2] = to_dev(hfr::mul(a[q][m + s2], to_host(d->t_inv[s2])));
+        SB_TRY(dalloc(pk, cn * 32, &pk->coset_pows));
+        SB_TRY(dalloc(pk, cn * 32, &pk->coset_pows_inv));
+        for (int s2 = 0; s2 < m; s2++) {
+            SB_TRY(fr_gen_powers(ctx, (uint8_t *)pk->coset_pows + (size_t)s2 * n * 32, to_dev(g[s2]), n, st));
+            SB_TRY(fr_gen_powers(ctx, (uint8_t *)pk->coset_pows_inv + (size_t)s2 * n * 32, to_dev(hfr::inv(g[s2])), n, st));
+        }
+    }
+    // values of a coefficient-form polynomial on every coset, coset-major: ONE batched launch set (the same input, n_cos scalings, n_cos outputs)
+    auto to_cosets = [&](const void *d_coeff, void *d_cm) -> int32_t {
+        NttFuse f;
+        f.pre_vec = pk->coset_pows;
+        f.batch = (uint32_t)m;
+        f.src_stride = 0; f.pre_stride = n; f.dst_stride = n;
+        return ntt_run_fused(ctx, d_coeff, d_cm, (const uint8_t *)d->omega.v, pk->k, &f, st);
+    };
     // omega^i first: the sparse permutation columns are built from it
     SB_TRY(dalloc(pk, n * 32, &pk->omega_pows));
     SB_TRY(fr_gen_powers(ctx, pk->omega_pows, d->omega, n, st));
@@ -319,7 +374,7 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
             void *v, *p, *e;
             SB_TRY(dalloc(pk, n * 32, &v));
             SB_TRY(dalloc(pk, n * 32, &p));
-            SB_TRY(dalloc(pk, en * 32, &e));
+            SB_TRY(dalloc(pk, cn * 32, &e));
             vals.push_back(v); polys.push_back(p); cosets.push_back(e);
         }
         return SB_OK;
@@ -366,44 +421,50 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
         for (int c = 0; c < count; c++) {
             SB_CUDA_TRY(cudaMemcpyAsync(polys[c], vals[c], n * 32, cudaMemcpyDeviceToDevice, st));
             SB_TRY(dom_l2c(ctx, d, polys[c], st));
-            SB_TRY(dom_c2e(ctx, d, polys[c], cosets[c], st));
+            SB_TRY(to_cosets(polys[c], cosets[c]));
             SB_TRY(srs_msm(ctx, pk->srs, 1, vals[c], n, comms.data() + (size_t)c * 64, st));
         }
         return SB_OK;
     };
     SB_TRY(derive_forms(pk->cs.F, pk->fixed_values, pk->fixed_polys, pk->fixed_cosets, pk->fixed_comms));
     SB_TRY(derive_forms(pk->P, pk->sigma_values, pk->sigma_polys, pk->sigma_cosets, pk->sigma_comms));
-    // l_0, l_last, l_blind (Lagrange unit vectors) -> extended; l_active = 1 - (l_last + l_blind)
+    // l_0, l_last, l_blind (Lagrange unit vectors) -> cosets; l_active = 1 - (l_last + l_blind)
     const int bf = pk->cs.blinding;
     std::vector<fr_t> tmp(n, fr_t::zero());
     void *d_tmp, *d_lblind;
     SB_TRY(scratch_get(ctx, "pk_tmp", n * 32, &d_tmp));
-    SB_TRY(scratch_get(ctx, "pk_lblind", en * 32, &d_lblind));
-    auto unit_ext = [&](const std::vector<size_t> &rows, void *d_ext) -> int32_t {
+    SB_TRY(scratch_get(ctx, "pk_lblind", cn * 32, &d_lblind));
+    auto unit_cosets = [&](const std::vector<size_t> &rows, void *d_cm) -> int32_t {
         std::fill(tmp.begin(), tmp.end(), fr_t::zero());
         for (size_t r : rows) tmp[r] = fr_t::one();
         SB_CUDA_TRY(cudaMemcpyAsync(d_tmp, tmp.data(), n * 32, cudaMemcpyHostToDevice, st));
         SB_CUDA_TRY(cudaStreamSynchronize(st));
         SB_TRY(dom_l2c(ctx, d, d_tmp, st));
-        return dom_c2e(ctx, d, d_tmp, d_ext, st);
+        return to_cosets(d_tmp, d_cm);
     };
-    SB_TRY(dalloc(pk, en * 32, &pk->l0));
-    SB_TRY(dalloc(pk, en * 32, &pk->l_last));
-    SB_TRY(dalloc(pk, en * 32, &pk->l_active));
-    SB_TRY(unit_ext({0}, pk->l0));
-    SB_TRY(unit_ext({n - (size_t)bf - 1}, pk->l_last));
+    SB_TRY(dalloc(pk, cn * 32, &pk->l0));
+    SB_TRY(dalloc(pk, cn * 32, &pk->l_last));
+    SB_TRY(dalloc(pk, cn * 32, &pk->l_active));
+    SB_TRY(unit_cosets({0}, pk->l0));
+    SB_TRY(unit_cosets({n - (size_t)bf - 1}, pk->l_last));
     std::vector<size_t> blind_rows;
     for (size_t r = n - (size_t)bf; r < n; r++) blind_rows.push_back(r);
-    SB_TRY(unit_ext(blind_rows, d_lblind));
+    SB_TRY(unit_cosets(blind_rows, d_lblind));
     {
-        std::vector<const void *> cols = {pk->l_last, d_lblind};
         Program p = compile_terms({e_sub(e_const(fr_t::one()), e_add(e_col(0, 0), e_col(1, 0)))}, nullptr);
-        SB_TRY(expr_eval(ctx, p, cols, pk->ext_k, 0, pk->l_active, st));
+        for (int s2 = 0; s2 < m; s2++) {
+            const size_t off = (size_t)s2 * n * 32;
+            std::vector<const void *> cols = {(const uint8_t *)pk->l_last + off, (const uint8_t *)d_lblind + off};
+            SB_TRY(expr_eval(ctx, p, cols, pk->k, 0, (uint8_t *)pk->l_active + off, st));
+        }
     }
-    // coset X column: zeta * ext_omega^i ; omega^i ; SHPLONK division helpers
-    SB_TRY(dalloc(pk, en * 32, &pk->x_coset));
-    SB_TRY(fr_gen_powers(ctx, pk->x_coset, d->ext_omega, en, st));
-    SB_TRY(fr_scale(ctx, pk->x_coset, en, d->coset[1], st));
+    // X on coset s: g_s * omega^i ; SHPLONK division helpers
+    SB_TRY(dalloc(pk, cn * 32, &pk->x_coset));
+    for (int s2 = 0; s2 < m; s2++) {
+        void *xs = (uint8_t *)pk->x_coset + (size_t)s2 * n * 32;
+        SB_CUDA_TRY(cudaMemcpyAsync(xs, pk->omega_pows, n * 32, cudaMemcpyDeviceToDevice, st));
+        SB_TRY(fr_scale(ctx, xs, n, to_dev(hfr::mul(to_host(d->coset[1]), hfr::pow_u64(to_host(d->ext_omega), (uint64_t)s2))), st));
+    }
     SB_TRY(dalloc(pk, n * 32, &pk->div_g_pows));
     SB_TRY(dalloc(pk, n * 32, &pk->div_x));
     SB_TRY(dalloc(pk, n * 32, &pk->div_ginv_scaled));
@@ -795,26 +856,14 @@ int32_t msm_commit_batch_mixed(sb_ctx *ctx, const sb_comm *comm, const sb_srs *s
     return SB_OK;
 }
 
-int32_t pk_coset_pows(sb_ctx *ctx, const sb_pk *pk, uint32_t j, void **out, cudaStream_t st) {
-    const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
-    if (pk->coset_pows.size() != n_cosets) pk->coset_pows.assign(n_cosets, nullptr);
-    if (!pk->coset_pows[j]) {
-        void *p;
-        SB_TRY(dalloc(pk, pk->n * 32, &p));
-        SB_TRY(fr_gen_powers(ctx, p, to_dev(hfr::pow_u64(to_host(pk->dom->ext_omega), j)), pk->n, st));
-        SB_TRY(fr_scale_pattern(ctx, p, pk->n, pk->dom->coset, 3, st));
-        pk->coset_pows[j] = p;
-    }
-    *out = pk->coset_pows[j];
-    return SB_OK;
-}
-
-// values of the polynomial `d_coeff` (n coefficients) on coset j: NTT_n(coeff[m] * zeta^(m mod 3) * ext_omega^(j m))
-int32_t coset_values(sb_ctx *ctx, const sb_pk *pk, const void *d_coeff, uint32_t j, void *d_out, cudaStream_t st) {
-    void *pw;
-    SB_TRY(pk_coset_pows(ctx, pk, j, &pw, st));
+// values of the polynomial `d_coeff` (n coefficients) on the coset slots s0, s0 + step, ... (count of them): NTT_n(coeff[m] * g_s^m), the scaling
+// applied as the coefficients are loaded; one batched launch set, output b at d_out + b * out_stride elements
+int32_t coset_values(sb_ctx *ctx, const sb_pk *pk, const void *d_coeff, uint32_t s0, uint32_t step, uint32_t count, void *d_out, size_t out_stride, cudaStream_t st) {
+    if (count == 0) return SB_OK;
     NttFuse f;
-    f.pre_vec = pw;
+    f.pre_vec = (const uint8_t *)pk->coset_pows + (size_t)s0 * pk->n * 32;
+    f.batch = count;
+    f.src_stride = 0; f.pre_stride = (uint64_t)step * pk->n; f.dst_stride = out_stride;
     return ntt_run_fused(ctx, d_coeff, d_out, (const uint8_t *)pk->dom->omega.v, pk->k, &f, st);
 }
 
@@ -832,10 +881,9 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
                           Transcript &tr, cudaStream_t st) {
     const ConstraintSystem &cs = pk->cs;
     const sb_domain *d = pk->dom;
-    const size_t n = pk->n, en = pk->ext_n;
+    const size_t n = pk->n;
     const int A = cs.A, F = cs.F, bf = cs.blinding, P = pk->P;
     const size_t usable = n - (size_t)(bf + 1);
-    const uint32_t rs_log = pk->ext_k - pk->k;
     SB_REQUIRE(n_inst <= usable, "create_proof: too many instance values");
     const Fr omega = to_host(d->omega), omega_inv = to_host(d->omega_inv);
     uint8_t pt[64];
@@ -872,18 +920,21 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         cudaStream_t s; bool on;
         ~SideJoin() { if (on) cudaStreamSynchronize(s); }
     } side_join{st2, use_side};
-    // Sharded proving: this rank's cosets of the extended domain and the slab that receives the per-proof polynomials' values on them
-    // (index [local coset][polynomial][row]); polynomial order: advice | instance | permutation Z | per lookup (Z, A', S')
+    // The quotient's cosets (sb_pk: n_cos = j - 1 cosets of the size-n subgroup), dealt round-robin to the ranks of a sharded proof (slot s belongs
+    // to rank s mod world; a single GPU owns them all), and the slab that receives the per-proof polynomials' values on the owned cosets
+    // (index [owned coset][polynomial][row]); polynomial order: advice | instance | permutation Z | per lookup (Z, A', S')
     const int n_sets_all = (P + (cs.degree - 2) - 1) / (cs.degree - 2);
-    const uint32_t n_cosets = 1u << rs_log;
-    const uint32_t co_per = comm ? n_cosets / (uint32_t)comm->world : 0, co_lo = comm ? (uint32_t)comm->rank * co_per : 0;
+    const uint32_t n_cos = (uint32_t)pk->n_cos;
+    const uint32_t world = comm ? (uint32_t)comm->world : 1u, rank = comm ? (uint32_t)comm->rank : 0u;
+    std::vector<uint32_t> own;  // coset slots of this rank
+    for (uint32_t s2 = rank; s2 < n_cos; s2 += world) own.push_back(s2);
+    const uint32_t co_per = (uint32_t)own.size();
     const size_t n_dyn = (size_t)A + 1 + (size_t)n_sets_all + 3 * cs.lookups.size();
     uint8_t *d_dyn = nullptr;
-    if (comm) SB_TRY(scratch_get(ctx, "pf_coset_dyn", (size_t)co_per * n_dyn * n * 32, (void **)&d_dyn));
+    SB_TRY(scratch_get(ctx, "pf_coset_dyn", (size_t)(co_per ? co_per : 1) * n_dyn * n * 32, (void **)&d_dyn));
     auto dyn_slot = [&](uint32_t jl, size_t q) -> void * { return d_dyn + ((size_t)jl * n_dyn + q) * n * 32; };
     auto side_cosets = [&](size_t q, const void *d_coeff) -> int32_t {  // values of one polynomial on every owned coset, on the side stream
-        for (uint32_t jl = 0; jl < co_per; jl++) SB_TRY(coset_values(ctx, pk, d_coeff, co_lo + jl, dyn_slot(jl, q), st2));
-        return SB_OK;
+        return coset_values(ctx, pk, d_coeff, rank, world, co_per, dyn_slot(0, q), n_dyn * n, st2);
     };
 
     // ---- transcript preamble
@@ -893,25 +944,22 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     for (const Fr &v : inst) tr.common_scalar(v);
 
     // ---- device buffers of this proof
-    void *d_inst, *d_inst_poly, *d_inst_coset;
+    void *d_inst, *d_inst_poly;
     SB_TRY(scratch_get(ctx, "pf_inst", n * 32, &d_inst));
     SB_TRY(scratch_get(ctx, "pf_inst_poly", n * 32, &d_inst_poly));
-    SB_TRY(scratch_get(ctx, "pf_inst_coset", en * 32, &d_inst_coset));
     SB_CUDA_TRY(cudaMemsetAsync(d_inst, 0, n * 32, st));
     SB_CUDA_TRY(cudaMemcpyAsync(d_inst, inst.data(), n_inst * 32, cudaMemcpyHostToDevice, st));
     SB_CUDA_TRY(cudaMemcpyAsync(d_inst_poly, d_inst, n * 32, cudaMemcpyDeviceToDevice, st));
     SB_TRY(dom_l2c(ctx, d, d_inst_poly, st));
-    std::vector<void *> adv(A), adv_poly(A), adv_coset(A);
+    std::vector<void *> adv(A), adv_poly(A);
     void *d_random_early = nullptr;
     {
-        uint8_t *base_v, *base_p, *base_c;
+        uint8_t *base_v, *base_p;
         SB_TRY(scratch_get(ctx, "pf_adv", (size_t)(A + 1) * n * 32, (void **)&base_v));  // + 1: the vanishing argument's random polynomial (early commitment)
         SB_TRY(scratch_get(ctx, "pf_adv_poly", (size_t)A * n * 32, (void **)&base_p));
-        SB_TRY(scratch_get(ctx, "pf_adv_coset", (size_t)A * en * 32, (void **)&base_c));
         for (int c = 0; c < A; c++) {
             adv[c] = base_v + (size_t)c * n * 32;
             adv_poly[c] = base_p + (size_t)c * n * 32;
-            adv_coset[c] = base_c + (size_t)c * en * 32;
         }
         d_random_early = base_v + (size_t)A * n * 32;
         const size_t adv_bytes = (size_t)A * n * 32;
@@ -948,18 +996,17 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(upload_frs(ctx, (uint8_t *)adv[c] + usable * 32, blind, st));
     }
     for (int c = 0; c < A; c++) (void)rng.next_fr();
-    for (int c = 0; c < A; c++) {
-        SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
-        SB_TRY(dom_l2c(ctx, d, adv_poly[c], st));
+    {   // lagrange_to_coeff of the A advice columns: one batched out-of-place inverse transform (n^-1 folded in)
+        NttFuse f;
+        f.has_scale = true;
+        f.scale = d->ifft_divisor;
+        f.batch = (uint32_t)A;
+        f.src_stride = n; f.dst_stride = n;
+        SB_TRY(ntt_run_fused(ctx, adv[0], adv_poly[0], (const uint8_t *)d->omega_inv.v, pk->k, &f, st));
     }
     SB_TRY(side_after_main());  // advice / instance cosets on the side stream, under the commitment below
-    if (!comm) {
-        for (int c = 0; c < A; c++) SB_TRY(dom_c2e(ctx, d, adv_poly[c], adv_coset[c], st2));
-        SB_TRY(dom_c2e(ctx, d, d_inst_poly, d_inst_coset, st2));
-    } else {
-        for (int c = 0; c < A; c++) SB_TRY(side_cosets((size_t)c, adv_poly[c]));
-        SB_TRY(side_cosets((size_t)A, d_inst_poly));
-    }
+    for (int c = 0; c < A; c++) SB_TRY(side_cosets((size_t)c, adv_poly[c]));
+    SB_TRY(side_cosets((size_t)A, d_inst_poly));
     // The vanishing argument's random polynomial depends on no challenge, only on the RNG stream: a CLONE of the RNG is advanced past every
     // draw that precedes its seed (all data-independent counts), so the polynomial can be generated now and committed in the SAME launch set
     // as the advice columns (mixed-basis batch: advice over the Lagrange tables, the random polynomial over the monomial tables).  The main
@@ -1007,15 +1054,14 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     lcols[L_OMEGA] = pk->omega_pows;
 
     // ---- lookups: compress, permute, commit
-    struct LookupState { void *c_in, *c_tab, *p_in, *p_tab, *in_poly, *tab_poly, *z_poly, *z_coset, *in_coset, *tab_coset; };
+    struct LookupState { void *c_in, *c_tab, *p_in, *p_tab, *in_poly, *tab_poly, *z_poly; };
     std::vector<LookupState> lks(cs.lookups.size());
     for (size_t li = 0; li < cs.lookups.size(); li++) {
         LookupState &L = lks[li];
         uint8_t *b;
-        SB_TRY(scratch_get(ctx, ("pf_lk" + std::to_string(li)).c_str(), 7 * n * 32 + 3 * en * 32, (void **)&b));
+        SB_TRY(scratch_get(ctx, ("pf_lk" + std::to_string(li)).c_str(), 7 * n * 32, (void **)&b));
         L.c_in = b; L.c_tab = b + n * 32; L.p_in = b + 2 * n * 32; L.p_tab = b + 3 * n * 32;
         L.in_poly = b + 4 * n * 32; L.tab_poly = b + 5 * n * 32; L.z_poly = b + 6 * n * 32;
-        L.z_coset = b + 7 * n * 32; L.in_coset = (uint8_t *)L.z_coset + en * 32; L.tab_coset = (uint8_t *)L.in_coset + en * 32;
         std::vector<ExprP> in_terms, tab_terms;
         for (auto &e : cs.lookups[li].input) in_terms.push_back(bind_expr(*e, lm));
         for (auto &e : cs.lookups[li].table) tab_terms.push_back(bind_expr(*e, lm));
@@ -1036,13 +1082,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
         (void)rng.next_fr();
         SB_TRY(side_after_main());
-        if (!comm) {
-            SB_TRY(dom_c2e(ctx, d, L.in_poly, L.in_coset, st2));
-            SB_TRY(dom_c2e(ctx, d, L.tab_poly, L.tab_coset, st2));
-        } else {
-            SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 1, L.in_poly));
-            SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 2, L.tab_poly));
-        }
+        SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 1, L.in_poly));
+        SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 2, L.tab_poly));
         uint8_t pin_tab[128];
         SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, L.p_in, n, 2, pin_tab, st));  // p_in and p_tab are adjacent in the lookup scratch block
         if (!tr.write_point(pin_tab) || !tr.write_point(pin_tab + 64)) { set_last_error("lookup commitment is the identity"); return SB_ERR_ARG; }
@@ -1056,7 +1097,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     //      scanned from 1 and scaled afterwards by the running boundary value (read back once), which is the same field element.
     const int chunk = cs.degree - 2;
     const int n_sets = (P + chunk - 1) / chunk;
-    struct PermSet { void *z_poly, *z_coset; int first, count; };
+    struct PermSet { void *z_poly; int first, count; };
     std::vector<PermSet> psets(n_sets);
     if (n_sets + (int)lks.size() > 0) {  // a circuit with neither copy constraints nor lookups has no grand product to commit
         const int n_z = n_sets + (int)lks.size();
@@ -1065,7 +1106,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(scratch_get(ctx, "pf_perm_num", (size_t)n_z * n * 32, (void **)&d_num));
         SB_TRY(scratch_get(ctx, "pf_z_all", (size_t)n_z * n * 32, (void **)&d_zall));
         uint8_t *zb;
-        SB_TRY(scratch_get(ctx, "pf_perm_polys", (size_t)n_sets * (n + en) * 32, (void **)&zb));
+        SB_TRY(scratch_get(ctx, "pf_perm_polys", (size_t)n_sets * n * 32, (void **)&zb));
         Fr delta_pow = hfr::ONE;
         const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
         // numerators and denominators of every grand product side by side, then ONE batch inversion and ONE product pass for all of them
@@ -1077,8 +1118,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             PermSet &S = psets[s];
             S.first = s * chunk;
             S.count = std::min(chunk, P - S.first);
-            S.z_poly = zb + (size_t)s * (n + en) * 32;
-            S.z_coset = (uint8_t *)S.z_poly + n * 32;
+            S.z_poly = zb + (size_t)s * n * 32;
             ExprP den = nullptr, num = nullptr;
             for (int j = 0; j < S.count; j++) {
                 const auto &pc = cs.perm_cols[S.first + j];
@@ -1124,15 +1164,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             PermSet &S = psets[s];
             SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
             SB_TRY(dom_l2c(ctx, d, S.z_poly, st2));
-            if (!comm) SB_TRY(dom_c2e(ctx, d, S.z_poly, S.z_coset, st2));
-            else SB_TRY(side_cosets((size_t)A + 1 + s, S.z_poly));
+            SB_TRY(side_cosets((size_t)A + 1 + s, S.z_poly));
         }
         for (size_t li = 0; li < lks.size(); li++) {
             LookupState &L = lks[li];
             SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
             SB_TRY(dom_l2c(ctx, d, L.z_poly, st2));
-            if (!comm) SB_TRY(dom_c2e(ctx, d, L.z_poly, L.z_coset, st2));
-            else SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li, L.z_poly));
+            SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li, L.z_poly));
         }
         std::vector<uint8_t> pts((size_t)n_z * 64);
         SB_TRY(msm_commit_batch(ctx, comm, pk->srs, 1, d_zall, n, (uint32_t)n_z, pts.data(), st));
@@ -1169,22 +1207,16 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     SB_TRY(main_after_side());
     mark();  // [5] coeff_to_extended of advice / instance / lookup polynomials (sharded: done per owned coset in stage 6)
     const int E_SIGMA = A + F + 1, E_PZ = E_SIGMA + P, E_L0 = E_PZ + n_sets, E_LLAST = E_L0 + 1, E_LACT = E_L0 + 2, E_X = E_L0 + 3, E_LK = E_L0 + 4;
-    std::vector<const void *> ecols(E_LK + 3 * lks.size(), nullptr);
-    for (int c = 0; c < A; c++) ecols[c] = adv_coset[c];
-    for (int c = 0; c < F; c++) ecols[A + c] = pk->fixed_cosets[c];
-    ecols[A + F] = d_inst_coset;
-    for (int j = 0; j < P; j++) ecols[E_SIGMA + j] = pk->sigma_cosets[j];
-    for (int s = 0; s < n_sets; s++) ecols[E_PZ + s] = psets[s].z_coset;
-    ecols[E_L0] = pk->l0; ecols[E_LLAST] = pk->l_last; ecols[E_LACT] = pk->l_active; ecols[E_X] = pk->x_coset;
-    for (size_t li = 0; li < lks.size(); li++) {
-        ecols[E_LK + 3 * li] = lks[li].z_coset;
-        ecols[E_LK + 3 * li + 1] = lks[li].in_coset;
-        ecols[E_LK + 3 * li + 2] = lks[li].tab_coset;
-    }
+    const size_t n_ecols = (size_t)E_LK + 3 * lks.size();
     std::vector<std::pair<int, int>> set_ranges;
     for (int s2 = 0; s2 < n_sets; s2++) set_ranges.push_back({psets[s2].first, psets[s2].count});
+    // per-coset data of the quotient: slot (r, jl) of the exchange buffer holds coset slot jl * world + r; `per` slots per rank
+    const uint32_t per = (n_cos + world - 1) / world;
+    uint8_t *d_hcm;
     void *d_h;
-    SB_TRY(scratch_get(ctx, "pf_h", en * 32, &d_h));
+    SB_TRY(scratch_get(ctx, "pf_h_cm", (size_t)per * world * n * 32, (void **)&d_hcm));
+    SB_TRY(scratch_get(ctx, "pf_h", (size_t)n_cos * n * 32, &d_h));
+    auto hcm_slot = [&](uint32_t s2) -> uint8_t * { return d_hcm + ((size_t)(s2 % world) * per + s2 / world) * n * 32; };
     {
         Program hp;
         if (ctx->tune.no_hprog_cache) {
@@ -1197,55 +1229,59 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         ctx->last_h_program[1] = hp.n_mul;
         ctx->last_h_program[2] = hp.n_addsub;
         ctx->last_h_program[3] = hp.n_slots;
+        ctx->last_h_rows = (uint64_t)co_per * n;
         if (!ctx->h_ev[0]) {  // created once per context: an early SB_TRY return below leaks nothing
             SB_CUDA_TRY(cudaEventCreate(&ctx->h_ev[0]));
             SB_CUDA_TRY(cudaEventCreate(&ctx->h_ev[1]));
         }
         cudaEvent_t e0 = ctx->h_ev[0], e1 = ctx->h_ev[1];
         SB_CUDA_TRY(cudaEventRecord(e0, st));
-        if (!comm) {
-            SB_TRY(expr_eval(ctx, hp, ecols, pk->ext_k, rs_log, d_h, st));
-        } else {
-            // coset-sharded: this rank owns cosets [rank * per, (rank + 1) * per) of the 2^rs_log cosets; the per-proof polynomials' values on
-            // them were computed on the side stream as the polynomials appeared (slab d_dyn), the key's columns are read in place at stride 8
-            const uint32_t W = (uint32_t)comm->world, per = co_per;
-            std::vector<int> dyn_col;  // ecols index of polynomial q
-            for (int c = 0; c < A; c++) dyn_col.push_back(c);
-            dyn_col.push_back(A + F);
-            for (int s2 = 0; s2 < n_sets; s2++) dyn_col.push_back(E_PZ + s2);
-            for (size_t li = 0; li < lks.size(); li++) {
-                dyn_col.push_back(E_LK + 3 * (int)li);
-                dyn_col.push_back(E_LK + 3 * (int)li + 1);
-                dyn_col.push_back(E_LK + 3 * (int)li + 2);
-            }
-            uint8_t *d_hcm;
-            SB_TRY(scratch_get(ctx, "pf_h_cm", en * 32, (void **)&d_hcm));
-            std::vector<const void *> ccols(ecols.size(), nullptr);
-            std::vector<uint8_t> shifts(ecols.size(), (uint8_t)rs_log);
-            for (uint32_t jl = 0; jl < per; jl++) {
-                const uint32_t j = co_lo + jl;
-                for (size_t c = 0; c < ecols.size(); c++) ccols[c] = ecols[c] ? (const uint8_t *)ecols[c] + (size_t)j * 32 : nullptr;
-                for (size_t q = 0; q < dyn_col.size(); q++) {
-                    ccols[dyn_col[q]] = dyn_slot(jl, q);
-                    shifts[dyn_col[q]] = 0;
-                }
-                SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, d_hcm + (size_t)j * n * 32, st, &shifts));
-            }
-            if (W > 1) {
-                SB_CUDA_TRY(cudaStreamSynchronize(st));
-                if (comm->allgather_dev(comm->user, d_hcm, (size_t)per * n * 32, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
-            }
-            // coset-major -> extended order, fused with the division by t(X) (constant t_inv[j] on coset j)
-            SB_TRY(fr_coset_interleave_scale(ctx, d_hcm, d_h, pk->k, rs_log, d->t_inv, st));
+        // one launch of the fused program per owned coset: the key's columns are coset-major slabs, the per-proof polynomials' values were
+        // computed on the side stream as the polynomials appeared (slab d_dyn); rotations move inside a coset
+        std::vector<int> dyn_col;  // column-table index of per-proof polynomial q
+        for (int c = 0; c < A; c++) dyn_col.push_back(c);
+        dyn_col.push_back(A + F);
+        for (int s2 = 0; s2 < n_sets; s2++) dyn_col.push_back(E_PZ + s2);
+        for (size_t li = 0; li < lks.size(); li++) {
+            dyn_col.push_back(E_LK + 3 * (int)li);
+            dyn_col.push_back(E_LK + 3 * (int)li + 1);
+            dyn_col.push_back(E_LK + 3 * (int)li + 2);
+        }
+        std::vector<const void *> ccols(n_ecols, nullptr);
+        for (uint32_t jl = 0; jl < co_per; jl++) {
+            const size_t off = (size_t)own[jl] * n * 32;
+            for (int c = 0; c < F; c++) ccols[A + c] = (const uint8_t *)pk->fixed_cosets[c] + off;
+            for (int j = 0; j < P; j++) ccols[E_SIGMA + j] = (const uint8_t *)pk->sigma_cosets[j] + off;
+            ccols[E_L0] = (const uint8_t *)pk->l0 + off; ccols[E_LLAST] = (const uint8_t *)pk->l_last + off;
+            ccols[E_LACT] = (const uint8_t *)pk->l_active + off; ccols[E_X] = (const uint8_t *)pk->x_coset + off;
+            for (size_t q = 0; q < dyn_col.size(); q++) ccols[dyn_col[q]] = dyn_slot(jl, q);
+            SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, hcm_slot(own[jl]), st));
         }
         SB_CUDA_TRY(cudaEventRecord(e1, st));
         SB_CUDA_TRY(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ctx->last_h_ms, e0, e1);
     }
-    mark();  // [6] evaluate_h (fused program)
-    // ---- quotient: / t(X), back to coefficients, pieces
-    if (!comm) SB_TRY(dom_div_e2c(ctx, d, d_h, d_h, st));  // the sharded path divided while interleaving the cosets
-    else SB_TRY(dom_e2c(ctx, d, d_h, d_h, st));
+    mark();  // [6] evaluate_h (fused program, one launch per owned coset)
+    // ---- quotient: per coset, back to the coefficients d_s(X) = sum_q h_q(X) g_s^(qn) of the numerator restricted to g_s H (size-n inverse NTT, n^-1
+    //      and the un-scaling g_s^-i fused); the cosets meet (sharded: one all-gather); a constant matrix gives h's pieces (and divides by t(X))
+    if (co_per) {  // the owned slots are adjacent in the exchange buffer: one batched launch set
+        NttFuse f;
+        f.has_scale = true;
+        f.scale = d->ifft_divisor;
+        f.post_vec = (const uint8_t *)pk->coset_pows_inv + (size_t)rank * n * 32;
+        f.batch = co_per;
+        f.src_stride = n; f.dst_stride = n; f.post_stride = (uint64_t)world * n;
+        SB_TRY(ntt_run_fused(ctx, hcm_slot(rank), hcm_slot(rank), (const uint8_t *)d->omega_inv.v, pk->k, &f, st));
+    }
+    if (world > 1) {
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (comm->allgather_dev(comm->user, d_hcm, (size_t)per * n * 32, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
+    }
+    {
+        std::vector<const void *> slots(n_cos);
+        for (uint32_t s2 = 0; s2 < n_cos; s2++) slots[s2] = hcm_slot(s2);
+        SB_TRY(fr_coset_combine(ctx, slots, pk->combine, d_h, n, st));
+    }
     const int n_pieces = cs.degree - 1;
     for (int i = 0; i < n_pieces; i++) (void)rng.next_fr();
     {
@@ -1255,7 +1291,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             if (!tr.write_point(pts.data() + (size_t)i * 64)) { set_last_error("quotient piece commitment is the identity"); return SB_ERR_ARG; }
     }
     const Fr x = tr.squeeze();
-    mark();  // [7] divide by t(X), extended iNTT, quotient piece commitments
+    mark();  // [7] per-coset inverse NTTs, coset combine (includes the division by t(X)), quotient piece commitments
     const Fr xn = fpow(x, (uint64_t)n);
     // h(X) folded at x^n
     void *d_hfold;
@@ -1463,7 +1499,7 @@ static int32_t create_proof_entry(sb_ctx *ctx, const sb_pk *pk, const sb_comm *c
     if (comm) {
         const uint32_t n_cosets = 1u << (pk->ext_k - pk->k);
         SB_REQUIRE(comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world, "sb_comm: rank / world out of range");
-        SB_REQUIRE((uint32_t)comm->world <= n_cosets && n_cosets % (uint32_t)comm->world == 0, "sb_comm: world must divide the 2^(extended_k - k) cosets of the extended domain");
+        SB_REQUIRE((uint32_t)comm->world <= n_cosets, "sb_comm: world must not exceed the 2^(extended_k - k) cosets of the extended domain");
         SB_REQUIRE(comm->world == 1 || (comm->allgather_host && comm->allgather_dev), "sb_comm: callbacks missing");
     }
     CtxGuard g(ctx);
@@ -1812,6 +1848,11 @@ int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digi
 int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]) {
     if (!ctx || !out_ms) return SB_ERR_ARG;
     for (int i = 0; i < 12; i++) out_ms[i] = ctx->last_proof_stage_ms[i];
+    return SB_OK;
+}
+int32_t sb_last_h_rows(const sb_ctx *ctx, uint64_t *out_rows) {
+    if (!ctx || !out_rows) return SB_ERR_ARG;
+    *out_rows = ctx->last_h_rows;
     return SB_OK;
 }
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]) {

@@ -32,6 +32,9 @@ int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_
 int32_t scatter_cells(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, const void *d_values, size_t n_cells, cudaStream_t st);
 int32_t sigma_patch(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, size_t n_cells, const void *d_omega_pows, const fr_t *delta_pows, cudaStream_t st);
 
+// out[q * n + i] = sum_s m[q * 8 + s] * slots[s][i]: the per-coset data of the quotient -> h's coefficient pieces
+int32_t fr_coset_combine(sb_ctx *ctx, const std::vector<const void *> &slots, const fr_t *m, void *d_out, size_t n, cudaStream_t st);
+
 // ---- expr.cu: expression DAGs compiled to a register program, evaluated over whole columns ---
 struct Expr;
 typedef std::shared_ptr<Expr> ExprP;

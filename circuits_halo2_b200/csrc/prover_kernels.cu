@@ -710,4 +710,32 @@ int32_t sigma_patch(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const v
     return SB_OK;
 }
 
+// ---- quotient: per-coset data -> coefficients of h.  out[q * n + i] = sum_s m[q][s] * d_s[i]  (q, s < n_cos <= 8; m = inverse Vandermonde of the
+// cosets' g_s^n with 1 / t(g_s) folded in, sb_pk::combine) ----
+struct CombineArgs {
+    const uint4 *d[8];
+    fr_t m[64];
+    uint32_t n_cos;
+};
+__global__ void __launch_bounds__(128) fr_coset_combine_kernel(const CombineArgs a, uint4 *out, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t d[8];
+    for (uint32_t s = 0; s < a.n_cos; s++) d[s] = load_fp<FrParams>(a.d[s] + 2 * i);
+    for (uint32_t q = 0; q < a.n_cos; q++) {
+        fr_t acc = mul(a.m[q * 8], d[0]);
+        for (uint32_t s = 1; s < a.n_cos; s++) acc = add(acc, mul(a.m[q * 8 + s], d[s]));
+        store_fp(out + 2 * ((uint64_t)q * n + i), acc);
+    }
+}
+int32_t fr_coset_combine(sb_ctx *ctx, const std::vector<const void *> &slots, const fr_t *m, void *d_out, size_t n, cudaStream_t st) {
+    SB_REQUIRE(slots.size() >= 1 && slots.size() <= 8, "fr_coset_combine: 1..8 cosets");
+    CombineArgs a;
+    a.n_cos = (uint32_t)slots.size();
+    for (uint32_t s = 0; s < 8; s++) a.d[s] = s < a.n_cos ? (const uint4 *)slots[s] : nullptr;
+    for (int i = 0; i < 64; i++) a.m[i] = m[i];
+    SB_LAUNCH(ctx, fr_coset_combine_kernel, (unsigned)((n + 127) / 128), 128, 0, st, a, (uint4 *)d_out, (uint64_t)n);
+    return SB_OK;
+}
+
 }  // namespace sb

@@ -112,7 +112,7 @@ def shard_range(n: int, rank: int, world: int):
 
 class ShardComm:
     """`sb_comm` over a torch.distributed process group: one process per GPU, NCCL (device all-gather of the quotient's coset
-    values over NVLink) and NCCL or gloo for the 64-byte partial commitments.  `world` must divide 2^(extended_k - k) = 8."""
+    values over NVLink) and NCCL or gloo for the 64-byte partial commitments.  the quotient's j - 1 = 5 cosets are dealt round-robin to the ranks (`world` <= 8; ranks beyond the fifth idle in that stage)."""
 
     def __init__(self, group=None, device: Optional[int] = None):
         import torch

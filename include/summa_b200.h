@@ -178,6 +178,8 @@ int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_co
 /* device time (ms) of the fused evaluate_h kernel of the last create_proof on this context and its program shape:
  * instructions, field products, additions/subtractions, live value slots */
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);
+/* rows the fused program ran on in that proof on this rank: (owned cosets of the quotient argument) x 2^k */
+int32_t sb_last_h_rows(const sb_ctx *ctx, uint64_t *out_rows);
 /* host wall-clock (ms) of the stages of the last create_proof: [0] advice upload + commitments, [1] lookup permute + commitments,
  * [2] permutation products, [3] lookup product, [4] random polynomial, [5] coset NTTs, [6] evaluate_h, [7] quotient + commitments,
  * [8] evaluations, [9] SHPLONK */

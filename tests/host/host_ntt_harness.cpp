@@ -139,6 +139,7 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
         p.dst = npass == 1 ? out.data() : (last ? out.data() : work.data());
 
         const NttGeom G(p);
+        const NttBatch bo(p, 0);
         const uint32_t tile = 1u << G.t, T = tile >> 3;
         const uint64_t tiles = 1ull << (log_n - p.r - p.g);
         std::vector<nfr_t> smem(tile);
@@ -157,7 +158,7 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
                     for (uint32_t b = 0; b < 8; b++) {
                         const uint32_t i = G.idx(tid, pw, b);
                         const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
-                        regs[tid * 8 + b] = p.log_a == 0 ? ntt_fetch_input(p, gi) : ntt_load_fr(p.src + 2 * gi);
+                        regs[tid * 8 + b] = p.log_a == 0 ? ntt_fetch_input(p, bo, gi) : ntt_load_fr(p.src + 2 * gi);
                     }
             }
             uint32_t low = G.r, prev = pw;
@@ -193,7 +194,7 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
                         const uint32_t gg = m & ((1u << p.g) - 1u), jj = m >> p.g;
                         const uint32_t a = ntt_swz((gg << G.r) | jj);
                         rd[tid].push_back(a);
-                        ntt_emit(p, tc, ntt_brev(jj, G.r), gg, smem[a]);
+                        ntt_emit(p, bo, tc, ntt_brev(jj, G.r), gg, smem[a]);
                     }
                 if (audit)
                     for (size_t slot = 0; slot < 8; slot++) { const uint32_t c1 = conflict_degree(rd, slot); worst = c1 > worst ? c1 : worst; }
@@ -201,7 +202,7 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
                 for (uint32_t tid = 0; tid < T; tid++)
                     for (uint32_t b = 0; b < 8; b++) {
                         const uint32_t i = G.idx(tid, prev, b);
-                        ntt_emit(p, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), regs[tid * 8 + b]);
+                        ntt_emit(p, bo, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), regs[tid * 8 + b]);
                     }
             }
         }

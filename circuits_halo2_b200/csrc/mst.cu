@@ -189,20 +189,25 @@ __device__ __forceinline__ void leaf_from_preimage(const TreeView &t, uint64_t i
 #define SB_MAX_CUR 32
 
 // entries given as (username bytes, u64 balances); rows >= n_entries are zero entries (entry.rs:30-38)
-__global__ void mst_leaf_entries_kernel(TreeView t, const uint8_t *names, const uint32_t *offs, const uint64_t *bal64, uint64_t n_entries) {
+// a balance as `limbs` little-endian u64 words (1: N_BYTES <= 8, the common case; 4: a 256-bit BigUint, entry.rs / csv/entry_16_bigints.csv), to Fr:
+// `big_uint_to_fp` (operation_helpers.rs:10-12) reduces mod r, which to_mont does for any 256-bit input
+__device__ __forceinline__ fr_t balance_to_fr(const uint64_t *w, uint32_t limbs) {
+    fr_t x = fr_t::zero();
+    for (uint32_t l = 0; l < limbs; l++) {
+        x.v[2 * l] = (uint32_t)w[l];
+        x.v[2 * l + 1] = (uint32_t)(w[l] >> 32);
+    }
+    return to_mont(x);
+}
+
+__global__ void mst_leaf_entries_kernel(TreeView t, const uint8_t *names, const uint32_t *offs, const uint64_t *bal64, uint32_t limbs, uint64_t n_entries) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= (1ull << t.depth)) return;
     fr_t uname = fr_t::zero();
     fr_t bals[SB_MAX_CUR];
     if (i < n_entries) {
         uname = keccak_username_fr(names + offs[i], offs[i + 1] - offs[i]);
-        for (uint32_t c = 0; c < t.n_cur; c++) {
-            uint64_t b = bal64[i * t.n_cur + c];
-            fr_t x = fr_t::zero();
-            x.v[0] = (uint32_t)b;
-            x.v[1] = (uint32_t)(b >> 32);
-            bals[c] = to_mont(x);
-        }
+        for (uint32_t c = 0; c < t.n_cur; c++) bals[c] = balance_to_fr(bal64 + (i * t.n_cur + c) * limbs, limbs);
     } else {
         for (uint32_t c = 0; c < t.n_cur; c++) bals[c] = fr_t::zero();
     }
@@ -291,15 +296,10 @@ __global__ void mst_proof_kernel(TreeView t, const uint64_t *idx, uint4 *out, ui
 
 
 // MerkleSumTree::update_leaf (mst.rs:158-197): new balances for one entry, then the path to the root; one thread (depth + 1 dependent hashes)
-__global__ void mst_update_kernel(TreeView t, uint64_t index, const uint64_t *bal64) {
+__global__ void mst_update_kernel(TreeView t, uint64_t index, const uint64_t *bal64, uint32_t limbs) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     fr_t bals[SB_MAX_CUR];
-    for (uint32_t c = 0; c < t.n_cur; c++) {
-        fr_t x = fr_t::zero();
-        x.v[0] = (uint32_t)bal64[c];
-        x.v[1] = (uint32_t)(bal64[c] >> 32);
-        bals[c] = to_mont(x);
-    }
+    for (uint32_t c = 0; c < t.n_cur; c++) bals[c] = balance_to_fr(bal64 + c * limbs, limbs);
     leaf_from_preimage(t, index, load_fp<FrParams>(t.uname + 2 * index), bals);
     for (uint32_t level = 1; level <= t.depth; level++) {
         __threadfence();
@@ -409,8 +409,8 @@ static uint32_t depth_for(size_t n_entries) {  // mst.rs:106: ceil(log2(len))
 
 extern "C" {
 
-int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint64_t *balances, size_t n_entries, uint32_t n_currencies,
-                     sb_mst **out_mst) {
+static int32_t mst_build_impl(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint64_t *balances, uint32_t limbs, size_t n_entries,
+                              uint32_t n_currencies, sb_mst **out_mst) {
     if (!ctx || !out_mst) return SB_ERR_ARG;
     SB_REQUIRE(n_entries >= 1 && usernames && offsets && balances, "sb_mst_build: empty input");
     SB_REQUIRE(n_currencies >= 1 && n_currencies <= SB_MAX_CUR, "sb_mst_build: n_currencies must be 1..32");
@@ -428,7 +428,7 @@ int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offs
     void *d_names = nullptr, *d_offs = nullptr, *d_b64 = nullptr;
     int32_t rc = scratch_get(ctx, "mst_names", name_bytes + 16, &d_names);
     if (rc == SB_OK) rc = scratch_get(ctx, "mst_offs", (n_entries + 1) * 4, &d_offs);
-    if (rc == SB_OK) rc = scratch_get(ctx, "mst_b64", n_entries * n_currencies * 8, &d_b64);
+    if (rc == SB_OK) rc = scratch_get(ctx, "mst_b64", n_entries * n_currencies * 8 * limbs, &d_b64);
     if (rc != SB_OK) { sb_mst_destroy(m); return rc; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -437,10 +437,10 @@ int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offs
         SB_CUDA_TRY(cudaEventRecord(e0, st));
         SB_CUDA_TRY(cudaMemcpyAsync(d_names, usernames, name_bytes, cudaMemcpyHostToDevice, st));
         SB_CUDA_TRY(cudaMemcpyAsync(d_offs, offsets, (n_entries + 1) * 4, cudaMemcpyHostToDevice, st));
-        SB_CUDA_TRY(cudaMemcpyAsync(d_b64, balances, n_entries * n_currencies * 8, cudaMemcpyHostToDevice, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(d_b64, balances, n_entries * n_currencies * 8 * limbs, cudaMemcpyHostToDevice, st));
         const uint64_t leaves = 1ull << depth;
         SB_LAUNCH(ctx, mst_leaf_entries_kernel, (unsigned)((leaves + 127) / 128), 128, 0, st, m->view(), (const uint8_t *)d_names, (const uint32_t *)d_offs,
-                  (const uint64_t *)d_b64, (uint64_t)n_entries);
+                  (const uint64_t *)d_b64, limbs, (uint64_t)n_entries);
         SB_TRY(mst_build_levels(ctx, m, st));
         SB_CUDA_TRY(cudaEventRecord(e1, st));
         SB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -453,6 +453,15 @@ int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offs
     if (rc != SB_OK) { sb_mst_destroy(m); return rc; }
     *out_mst = m;
     return SB_OK;
+}
+
+int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint64_t *balances, size_t n_entries, uint32_t n_currencies,
+                     sb_mst **out_mst) {
+    return mst_build_impl(ctx, usernames, offsets, balances, 1, n_entries, n_currencies, out_mst);
+}
+int32_t sb_mst_build_wide(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint8_t *balances_le32, size_t n_entries, uint32_t n_currencies,
+                          sb_mst **out_mst) {
+    return mst_build_impl(ctx, usernames, offsets, (const uint64_t *)balances_le32, 4, n_entries, n_currencies, out_mst);
 }
 
 int32_t sb_mst_build_from_preimages(sb_ctx *ctx, const uint8_t *leaf_preimages, size_t n_leaves, uint32_t n_currencies, sb_mst **out_mst) {
@@ -568,20 +577,26 @@ int32_t sb_mst_proofs(const sb_mst *mst, const uint64_t *indices, size_t n_proof
     return SB_OK;
 }
 
-int32_t sb_mst_update_leaf(sb_mst *mst, size_t index, const uint64_t *new_balances, uint8_t out_root_hash[32], uint8_t *out_root_balances) {
+static int32_t mst_update_impl(sb_mst *mst, size_t index, const uint64_t *new_balances, uint32_t limbs, uint8_t out_root_hash[32], uint8_t *out_root_balances) {
     if (!mst || !new_balances) return SB_ERR_ARG;
     SB_REQUIRE(index < (1ull << mst->depth), "sb_mst_update_leaf: index out of bounds");
     sb_ctx *ctx = mst->ctx;
     {
         CtxGuard g(ctx);
         void *d_b;
-        SB_TRY(scratch_get(ctx, "mst_upd", mst->n_cur * 8, &d_b));
-        SB_TRY(h2d_staged(ctx, d_b, new_balances, mst->n_cur * 8, ctx->stream));
-        SB_LAUNCH(ctx, mst_update_kernel, 1, 32, 0, ctx->stream, mst->view(), (uint64_t)index, (const uint64_t *)d_b);
+        SB_TRY(scratch_get(ctx, "mst_upd", (size_t)mst->n_cur * 8 * limbs, &d_b));
+        SB_TRY(h2d_staged(ctx, d_b, new_balances, (size_t)mst->n_cur * 8 * limbs, ctx->stream));
+        SB_LAUNCH(ctx, mst_update_kernel, 1, 32, 0, ctx->stream, mst->view(), (uint64_t)index, (const uint64_t *)d_b, limbs);
         SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     if (out_root_hash && out_root_balances) return sb_mst_root(mst, out_root_hash, out_root_balances);
     return SB_OK;
+}
+int32_t sb_mst_update_leaf(sb_mst *mst, size_t index, const uint64_t *new_balances, uint8_t out_root_hash[32], uint8_t *out_root_balances) {
+    return mst_update_impl(mst, index, new_balances, 1, out_root_hash, out_root_balances);
+}
+int32_t sb_mst_update_leaf_wide(sb_mst *mst, size_t index, const uint8_t *new_balances_le32, uint8_t out_root_hash[32], uint8_t *out_root_balances) {
+    return mst_update_impl(mst, index, (const uint64_t *)new_balances_le32, 4, out_root_hash, out_root_balances);
 }
 
 int32_t sb_mst_verify_proofs(sb_ctx *ctx, uint32_t n_currencies, uint32_t depth, const uint8_t *preimages, const uint8_t *path_indices, const uint8_t root_hash[32],

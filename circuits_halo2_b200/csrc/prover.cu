@@ -1675,6 +1675,120 @@ int32_t sb_kate_division(sb_ctx *ctx, const uint8_t *a, uint32_t log_n, const ui
     return SB_OK;
 }
 
+// ---- halo2 `Evaluator::evaluate_h` as a standalone entry: the quotient numerator of a constraint system over caller-supplied columns ----
+// Column order (HLayout): advice (A) | fixed (F) | instance (1) | sigma (P) | permutation Z (ceil(P / (degree - 2))) | l_0, l_last, l_active, X |
+// per lookup: Z, A', S'.  Every column holds 2^log_rows values of its polynomial on ONE common domain; a row rotation r moves by r << rot_scale_log
+// entries cyclically (halo2's extended domain in natural order: rot_scale_log = extended_k - k; one coset of the size-n subgroup: 0).
+static int32_t evaluate_h_common(sb_ctx *ctx, const char *cs_json, const std::vector<const void *> &cols, uint32_t log_rows, uint32_t rot_scale_log, const uint8_t theta[32],
+                                 const uint8_t beta[32], const uint8_t gamma[32], const uint8_t y[32], void *d_out, cudaStream_t st) {
+    ConstraintSystem cs;
+    try {
+        cs = parse_cs(cs_json);
+        validate_cs(cs, (size_t)1 << 28);
+    } catch (const std::exception &e) {
+        set_last_error("sb_evaluate_h: %s", e.what());
+        return SB_ERR_ARG;
+    }
+    const int P = (int)cs.perm_cols.size(), chunk = cs.degree - 2;
+    std::vector<std::pair<int, int>> sets;
+    for (int f = 0; f < P; f += chunk) sets.push_back({f, std::min(chunk, P - f)});
+    const HLayout lay(cs, P, (int)sets.size(), cs.lookups.size());
+    SB_REQUIRE((int)cols.size() == lay.n_cols, "sb_evaluate_h: column count does not match the constraint system (advice | fixed | instance | sigma | Z | l0 l_last l_active X | lookups)");
+    Fr th, be, ga, yy;
+    memcpy(th.v, theta, 32); memcpy(be.v, beta, 32); memcpy(ga.v, gamma, 32); memcpy(yy.v, y, 32);
+    try {
+        fr_t yd = to_dev(yy);
+        const Program hp = compile_terms(h_terms(cs, P, sets, cs.lookups.size(), th, be, ga), &yd);
+        ctx->last_h_program[0] = (uint32_t)(hp.code.size() / 3); ctx->last_h_program[1] = hp.n_mul; ctx->last_h_program[2] = hp.n_addsub; ctx->last_h_program[3] = hp.n_slots;
+        return expr_eval(ctx, hp, cols, log_rows, rot_scale_log, d_out, st);
+    } catch (const std::exception &e) {
+        set_last_error("sb_evaluate_h: %s", e.what());
+        return SB_ERR_ARG;
+    }
+}
+int32_t sb_evaluate_h_dev(sb_ctx *ctx, const char *cs_json, const void *const *d_columns, size_t n_columns, uint32_t log_rows, uint32_t rot_scale_log, const uint8_t theta[32],
+                          const uint8_t beta[32], const uint8_t gamma[32], const uint8_t y[32], void *d_out, void *stream) {
+    if (!ctx || !cs_json || !d_columns || !theta || !beta || !gamma || !y || !d_out) return SB_ERR_ARG;
+    SB_REQUIRE(log_rows >= 1 && log_rows <= 28 && rot_scale_log < log_rows, "sb_evaluate_h: log_rows must be in [1, 28] and rot_scale_log below it");
+    for (size_t i = 0; i < n_columns; i++) SB_REQUIRE(d_columns[i] != nullptr, "sb_evaluate_h: null column");
+    CtxGuard g(ctx);
+    return evaluate_h_common(ctx, cs_json, std::vector<const void *>(d_columns, d_columns + n_columns), log_rows, rot_scale_log, theta, beta, gamma, y, d_out, pick_stream(ctx, stream));
+}
+int32_t sb_evaluate_h(sb_ctx *ctx, const char *cs_json, const uint8_t *const *columns, size_t n_columns, uint32_t log_rows, uint32_t rot_scale_log, const uint8_t theta[32],
+                      const uint8_t beta[32], const uint8_t gamma[32], const uint8_t y[32], uint8_t *out) {
+    if (!ctx || !cs_json || !columns || !theta || !beta || !gamma || !y || !out) return SB_ERR_ARG;
+    SB_REQUIRE(log_rows >= 1 && log_rows <= 28 && rot_scale_log < log_rows, "sb_evaluate_h: log_rows must be in [1, 28] and rot_scale_log below it");
+    CtxGuard g(ctx);
+    const size_t bytes = (size_t)32 << log_rows;
+    uint8_t *slab;
+    void *d_out;
+    SB_TRY(scratch_get(ctx, "eh_cols", bytes * n_columns, (void **)&slab));
+    SB_TRY(scratch_get(ctx, "eh_out", bytes, &d_out));
+    std::vector<const void *> cols(n_columns);
+    for (size_t i = 0; i < n_columns; i++) {
+        SB_REQUIRE(columns[i] != nullptr, "sb_evaluate_h: null column");
+        cols[i] = slab + i * bytes;
+        SB_CUDA_TRY(cudaMemcpyAsync(slab + i * bytes, columns[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SB_TRY(evaluate_h_common(ctx, cs_json, cols, log_rows, rot_scale_log, theta, beta, gamma, y, d_out, ctx->stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// ---- ParamsKZG::commit / commit_lagrange for m polynomials at once (one launch set over the fixed-base tables) ----
+int32_t sb_msm_g1_batch(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const uint8_t *scalars, size_t n, size_t m, uint8_t *out_affine) {
+    if (!ctx || !srs || !out_affine || (n && m && !scalars)) return SB_ERR_ARG;
+    SB_REQUIRE(basis == SB_BASIS_MONOMIAL || basis == SB_BASIS_LAGRANGE, "basis must be 0 or 1");
+    SB_REQUIRE(n <= ((size_t)1 << srs->k), "msm: more scalars than SRS bases");
+    SB_REQUIRE(m >= 1 && m <= 64, "sb_msm_g1_batch: 1..64 vectors");
+    CtxGuard g(ctx);
+    void *ds;
+    SB_TRY(scratch_get(ctx, "mx_scalars", n * m * 32 + 32, &ds));
+    SB_CUDA_TRY(cudaMemcpyAsync(ds, scalars, n * m * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // launch sets of at most 8 vectors (the bucket arena of a set grows with its width)
+    for (size_t j0 = 0; j0 < m; j0 += 8) {
+        const uint32_t cnt = (uint32_t)std::min<size_t>(8, m - j0);
+        SB_TRY(srs_msm_batch(ctx, srs, basis, (const uint8_t *)ds + j0 * n * 32, n, cnt, out_affine + j0 * 64, ctx->stream));
+    }
+    return SB_OK;
+}
+int32_t sb_msm_g1_batch_dev(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const void *d_scalars, size_t n, size_t m, uint8_t *out_affine, void *stream) {
+    if (!ctx || !srs || !out_affine || (n && m && !d_scalars)) return SB_ERR_ARG;
+    SB_REQUIRE(basis == SB_BASIS_MONOMIAL || basis == SB_BASIS_LAGRANGE, "basis must be 0 or 1");
+    SB_REQUIRE(n <= ((size_t)1 << srs->k), "msm: more scalars than SRS bases");
+    SB_REQUIRE(m >= 1 && m <= 64, "sb_msm_g1_batch: 1..64 vectors");
+    CtxGuard g(ctx);
+    for (size_t j0 = 0; j0 < m; j0 += 8) {
+        const uint32_t cnt = (uint32_t)std::min<size_t>(8, m - j0);
+        SB_TRY(srs_msm_batch(ctx, srs, basis, (const uint8_t *)d_scalars + j0 * n * 32, n, cnt, out_affine + j0 * 64, pick_stream(ctx, stream)));
+    }
+    return SB_OK;
+}
+
+// ---- the grand-product column of the permutation / lookup arguments (halo2 permutation::Argument::commit inner loop):
+//      z[0] = init, z[i + 1] = z[i] * num[i] / den[i]; n_z values are written (n_z <= n + 1).  One batch inversion, one product pass, one scan. ----
+int32_t sb_grand_product(sb_ctx *ctx, const uint8_t *numerators, const uint8_t *denominators, size_t n, const uint8_t init[32], uint8_t *z, size_t n_z) {
+    if (!ctx || !init || (n && (!numerators || !denominators)) || (n_z && !z)) return SB_ERR_ARG;
+    SB_REQUIRE(n_z <= n + 1, "sb_grand_product: n_z must be <= n + 1");
+    CtxGuard g(ctx);
+    cudaStream_t st = ctx->stream;
+    void *dn, *dd, *dz;
+    SB_TRY(scratch_get(ctx, "bb_a", (n + 1) * 32, &dn));
+    SB_TRY(scratch_get(ctx, "bb_b", (n + 1) * 32, &dd));
+    SB_TRY(scratch_get(ctx, "bb_c", (n_z + 1) * 32, &dz));
+    SB_CUDA_TRY(cudaMemcpyAsync(dn, numerators, n * 32, cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(dd, denominators, n * 32, cudaMemcpyHostToDevice, st));
+    SB_TRY(fr_batch_invert(ctx, dd, n, st));
+    SB_TRY(fp_vec_op(ctx, 0, 0, dd, dn, dd, n, st));
+    fr_t i0;
+    memcpy(i0.v, init, 32);
+    SB_TRY(fr_running_product(ctx, dd, n, i0, dz, n_z, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(z, dz, n_z * 32, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
 // `ParamsKZG::setup(k, rng)` (utils.rs:70) with an explicit secret: g[i] = [tau^i] G, g_lagrange[i] = [L_i(tau)] G, all on the device.
 // UNSAFE by construction (the caller knows tau): test / benchmark SRS only.
 int32_t sb_srs_setup_unsafe(sb_ctx *ctx, uint32_t k, const uint8_t tau_mont[32], sb_srs **out_srs) {

@@ -62,27 +62,33 @@ class MerkleSumTree:
             raise AssertionError("MerkleSumTree: no entries")
         n_cur = len(entries[0].balances)
         names = [e.username.encode() for e in entries]
-        bal = np.zeros((len(entries), n_cur), dtype=np.uint64)
-        for i, e in enumerate(entries):
+        for e in entries:
             if len(e.balances) != n_cur:
                 raise AssertionError("MerkleSumTree: every entry needs N_CURRENCIES balances")
-            for j, b in enumerate(e.balances):
-                if not 0 <= b < (1 << 64):
-                    raise AssertionError("balance outside the N_BYTES <= 8 range")
-                bal[i, j] = b
+            if any(not 0 <= b < (1 << 256) for b in e.balances):
+                raise AssertionError("balance outside the 256-bit range")
+        if all(b < (1 << 64) for e in entries for b in e.balances):
+            bal = np.array([[b for b in e.balances] for e in entries], dtype=np.uint64).reshape(len(entries), n_cur)
+        else:
+            # BigUint balances (entry.rs:10; csv/entry_16_bigints.csv): 32-byte little-endian integers, the wide entry point
+            bal = np.frombuffer(b"".join(int(b).to_bytes(32, "little") for e in entries for b in e.balances), dtype=np.uint64).reshape(len(entries), n_cur, 4).copy()
         return cls.from_arrays(names, bal, cryptocurrencies, is_sorted, ctx, entries=list(entries))
 
     @classmethod
     def from_arrays(cls, names: Sequence[bytes], balances: np.ndarray, cryptocurrencies=None, is_sorted=False, ctx: Optional[Context] = None, entries=None):
-        """names: one bytes object per user; balances: (n, N_CURRENCIES) uint64."""
+        """names: one bytes object per user; balances: (n, N_CURRENCIES) uint64, or (n, N_CURRENCIES, 4) uint64 = 256-bit little-endian
+        BigUint balances (reduced mod r like the reference's `big_uint_to_fp`)."""
         ctx = ctx or default_context()
         n = len(names)
-        bal = np.ascontiguousarray(balances, dtype=np.uint64).reshape(n, -1)
+        bal = np.ascontiguousarray(balances, dtype=np.uint64)
+        wide = bal.ndim == 3
+        bal = bal.reshape(n, -1, 4) if wide else bal.reshape(n, -1)
         offs = np.zeros(n + 1, dtype=np.uint32)
         np.cumsum([len(x) for x in names], out=offs[1:])
         blob = np.frombuffer(b"".join(names) + b"\0", dtype=np.uint8).copy()
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().sb_mst_build(ctx.handle, ptr(blob), ptr(offs), ptr(bal), ctypes.c_size_t(n), ctypes.c_uint32(bal.shape[1]), ctypes.byref(h)), "sb_mst_build")
+        fn = _lib.lib().sb_mst_build_wide if wide else _lib.lib().sb_mst_build
+        _lib.check(fn(ctx.handle, ptr(blob), ptr(offs), ptr(bal), ctypes.c_size_t(n), ctypes.c_uint32(bal.shape[1]), ctypes.byref(h)), "sb_mst_build")
         return cls(h, ctx, entries, cryptocurrencies, is_sorted)
 
     @classmethod
@@ -96,7 +102,7 @@ class MerkleSumTree:
             if len(parts) != 3 or parts[0] != "balance":
                 raise ValueError(f"Invalid header: {h}")
             cur.append({"name": parts[1], "chain": parts[2]})
-        entries = [Entry(r[0], [int(x) for x in r[1:]]) for r in rows[1:]]
+        entries = [Entry(r[0], [int(x) for x in r[1:]]) for r in rows[1:] if r]  # empty lines are skipped like the csv crate does
         if sort:
             entries.sort(key=lambda e: e.username)
         return cls.from_entries(entries, cur, sort, ctx)
@@ -171,10 +177,14 @@ class MerkleSumTree:
         index = self.index_of_username(username)
         if len(new_balances) != self.n_currencies:
             raise AssertionError("update_leaf: N_CURRENCIES balances expected")
-        bal = np.ascontiguousarray(new_balances, dtype=np.uint64)
         hs = np.zeros(4, dtype=np.uint64)
         bl = np.zeros((self.n_currencies, 4), dtype=np.uint64)
-        _lib.check(_lib.lib().sb_mst_update_leaf(self._h, ctypes.c_size_t(index), ptr(bal), ptr(hs), ptr(bl)), "sb_mst_update_leaf")
+        if all(0 <= int(b) < (1 << 64) for b in new_balances):
+            bal = np.array([int(b) for b in new_balances], dtype=np.uint64)
+            _lib.check(_lib.lib().sb_mst_update_leaf(self._h, ctypes.c_size_t(index), ptr(bal), ptr(hs), ptr(bl)), "sb_mst_update_leaf")
+        else:
+            bal = np.frombuffer(b"".join(int(b).to_bytes(32, "little") for b in new_balances), dtype=np.uint64).copy()
+            _lib.check(_lib.lib().sb_mst_update_leaf_wide(self._h, ctypes.c_size_t(index), ptr(bal), ptr(hs), ptr(bl)), "sb_mst_update_leaf_wide")
         self._entries[index] = Entry(username, [int(x) for x in new_balances])
         return Node(fields.fr_from_mont(hs), _fr_list(bl))
 

@@ -187,6 +187,23 @@ int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]);
 /* the commitments (MSM launch sets) of the last create_proof on this context: summed device times of the phases listed at sb_msm_phase_times,
  * the number of signed digits accumulated (= level-1 mixed additions: sum over launch sets of windows x points x vectors) and of launch sets */
 int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digits, uint32_t *out_launch_sets);
+/* ---- halo2_proofs::plonk::evaluation::Evaluator::evaluate_h as a standalone entry (the finer-grained Cargo patch: the body of evaluate_h) ----
+ * The quotient NUMERATOR sum_i y^(T-1-i) term_i of the constraint system `cs_json` (gate polynomials, then the permutation argument's terms, then
+ * every lookup's terms: SURVEY A.8) over caller-supplied columns, 2^log_rows values each on one common domain, in this order:
+ *   advice (A) | fixed (F) | instance (1) | sigma (P) | permutation Z (ceil(P / (degree - 2))) | l_0, l_last, l_active, X | per lookup: Z, A', S'
+ * A row rotation r reads (row + (r << rot_scale_log)) mod 2^log_rows: halo2's extended domain in natural order has rot_scale_log = extended_k - k;
+ * one coset of the size-n subgroup has 0.  X is the column of evaluation points.  Division by t(X) is NOT included (sb_divide_by_vanishing_poly). */
+int32_t sb_evaluate_h(sb_ctx *ctx, const char *cs_json, const uint8_t *const *columns, size_t n_columns, uint32_t log_rows, uint32_t rot_scale_log, const uint8_t theta[32],
+                      const uint8_t beta[32], const uint8_t gamma[32], const uint8_t y[32], uint8_t *out);
+int32_t sb_evaluate_h_dev(sb_ctx *ctx, const char *cs_json, const void *const *d_columns, size_t n_columns, uint32_t log_rows, uint32_t rot_scale_log, const uint8_t theta[32],
+                          const uint8_t beta[32], const uint8_t gamma[32], const uint8_t y[32], void *d_out, void *stream);
+/* ParamsKZG::commit / commit_lagrange for m polynomials of n coefficients at once (scalars: m x n x 32 B, contiguous; out: m x 64 B): one launch set
+ * per 8 vectors over the fixed-base tables (create_proof commits its advice / lookup / product / quotient columns this way) */
+int32_t sb_msm_g1_batch(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const uint8_t *scalars, size_t n, size_t m, uint8_t *out_affine);
+int32_t sb_msm_g1_batch_dev(sb_ctx *ctx, const sb_srs *srs, int32_t basis, const void *d_scalars, size_t n, size_t m, uint8_t *out_affine, void *stream);
+/* the grand-product column of the permutation / lookup arguments (halo2 permutation::Argument::commit, lookup commit_product: SURVEY A.6 / A.7):
+ * z[0] = init, z[i + 1] = z[i] * numerators[i] / denominators[i]; n_z <= n + 1 values written */
+int32_t sb_grand_product(sb_ctx *ctx, const uint8_t *numerators, const uint8_t *denominators, size_t n, const uint8_t init[32], uint8_t *z, size_t n_z);
 /* building blocks of create_proof with host buffers (halo2 arithmetic::{eval_polynomial, kate_division},
  * poly::batch_invert, the grand-product scan of permutation / lookup Z, lookup `permute_expression_pair`) */
 int32_t sb_fr_batch_invert(sb_ctx *ctx, uint8_t *a, size_t n);                                   /* zeros stay zero */
@@ -213,6 +230,10 @@ typedef struct sb_mst sb_mst;
 /* usernames: concatenated UTF-8 bytes, entry i = usernames[offsets[i] .. offsets[i+1]); balances: n_entries x n_currencies u64 (N_BYTES <= 8) */
 int32_t sb_mst_build(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint64_t *balances, size_t n_entries, uint32_t n_currencies,
                      sb_mst **out_mst);
+/* the same with BigUint balances (entry.rs:10: `balances: [BigUint; N_CURRENCIES]`; merkle_sum_tree/tests.rs:130, csv/entry_16_bigints.csv hold values
+ * >= 2^64): n_entries x n_currencies x 32 B little-endian integers, reduced mod r like `big_uint_to_fp` (operation_helpers.rs:10-12) */
+int32_t sb_mst_build_wide(sb_ctx *ctx, const uint8_t *usernames, const uint32_t *offsets, const uint8_t *balances_le32, size_t n_entries, uint32_t n_currencies,
+                          sb_mst **out_mst);
 /* build_merkle_tree_from_leaves over Node::leaf_node_from_preimage: n_leaves (a power of two) x (n_currencies + 1) x 32 B: [username, balances...] */
 int32_t sb_mst_build_from_preimages(sb_ctx *ctx, const uint8_t *leaf_preimages, size_t n_leaves, uint32_t n_currencies, sb_mst **out_mst);
 int32_t sb_mst_destroy(sb_mst *mst);
@@ -228,6 +249,7 @@ int32_t sb_mst_proofs(const sb_mst *mst, const uint64_t *indices, size_t n_proof
 /* MerkleSumTree::update_leaf (mst.rs:158-197): new balances (n_currencies u64) for the entry at `index`, the path to the root is rehashed;
  * optionally returns the new root */
 int32_t sb_mst_update_leaf(sb_mst *mst, size_t index, const uint64_t *new_balances, uint8_t out_root_hash[32], uint8_t *out_root_balances);
+int32_t sb_mst_update_leaf_wide(sb_mst *mst, size_t index, const uint8_t *new_balances_le32 /* n_currencies x 32 B LE */, uint8_t out_root_hash[32], uint8_t *out_root_balances);
 /* Tree::verify_proof (tree.rs:139-186) for n_proofs proofs in the layout sb_mst_proofs writes, against one root; out_ok[j] = 1 iff proof j
  * hashes up to root_hash with balances equal to root_balances */
 int32_t sb_mst_verify_proofs(sb_ctx *ctx, uint32_t n_currencies, uint32_t depth, const uint8_t *preimages, const uint8_t *path_indices, const uint8_t root_hash[32],

@@ -79,7 +79,7 @@ class MerkleSumTree:
     def from_csv(cls, path: str) -> "MerkleSumTree":
         with open(path) as f:
             rows = list(csv.reader(f))
-        return cls([Entry(r[0], [int(x) for x in r[1:]]) for r in rows[1:]])
+        return cls([Entry(r[0], [int(x) for x in r[1:]]) for r in rows[1:] if r])  # the csv crate skips empty lines (csv/entry_17.csv ends with one)
 
     def generate_proof(self, index: int) -> dict:
         sib = index + 1 if index % 2 == 0 else index - 1

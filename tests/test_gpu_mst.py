@@ -157,3 +157,49 @@ def test_verify_update_and_sorted_like_the_reference_tests(ctx, golden_dir):
 def fr_int(limbs):
     from circuits_halo2_b200 import fields
     return fields.fr_from_mont(limbs)
+
+
+def test_entry_13_and_17_csv_goldens_with_zero_padding(ctx, golden_dir):
+    """merkle_sum_tree/tests.rs:205-264 (`test_tree_with_zero_element_1/2`): 13 entries pad to 16 (depth 4), 17 pad to 32 (depth 5) with zero entries;
+    root balances are the reference's goldens; every index proves and verifies, the first out-of-range index errors."""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200._lib import SummaB200Error
+    for name, n_real, depth, balances in (("entry_13.csv", 13, 4, [385969, 459661]), ("entry_17.csv", 17, 5, [556863, 556863])):
+        t = sb.MerkleSumTree.from_csv(os.path.join(golden_dir, name), ctx)
+        o = M.MerkleSumTree.from_csv(os.path.join(golden_dir, name))
+        root = t.root()
+        assert t.depth() == depth and root.balances == balances and root.hash != 0
+        assert (root.hash, root.balances) == (o.root[0], o.root[1])
+        zero_leaf = M.poseidon_hash([0, 0, 0])
+        for i in range(n_real, 1 << depth):
+            assert t.node(0, i).hash == zero_leaf and t.node(0, i).balances == [0, 0]     # Entry::zero_entry
+        proofs = [t.generate_proof(i) for i in range(1 << depth)]
+        assert all(t.verify_proofs(proofs))
+        with pytest.raises((SummaB200Error, IndexError, AssertionError)):
+            t.generate_proof(1 << depth)
+        t.close()
+
+
+def test_biguint_balances_entry_16_bigints(ctx, golden_dir):
+    """entry.rs:10 balances are BigUint; csv/entry_16_bigints.csv:2 holds 18446744073709551616 = 2^64 (merkle_sum_tree/tests.rs:130 `test_big_uint_conversion`).
+    The wide entry point builds the same tree as the oracle; update_leaf accepts a wide balance too and restores the original root afterwards."""
+    import circuits_halo2_b200 as sb
+    path = os.path.join(golden_dir, "entry_16_bigints.csv")
+    t = sb.MerkleSumTree.from_csv(path, ctx)
+    o = M.MerkleSumTree.from_csv(path)
+    assert sum(b >= (1 << 64) for e in o.entries for b in e.balances) >= 1
+    root = t.root()
+    assert (root.hash, root.balances) == (o.root[0], o.root[1])
+    assert root.balances == [sum(e.balances[c] for e in o.entries) for c in range(2)] and max(root.balances) > (1 << 64)
+    for lvl in range(o.depth + 1):
+        assert [t.node(lvl, i).hash for i in range(len(o.nodes[lvl]))] == [h for h, _ in o.nodes[lvl]]
+    assert all(t.verify_proofs([t.generate_proof(i) for i in range(16)]))
+    big = (1 << 200) + 12345
+    new_root = t.update_leaf(o.entries[3].username, [big, 7])
+    ents = [M.Entry(e.username, list(e.balances)) for e in o.entries]
+    ents[3] = M.Entry(ents[3].username, [big, 7])
+    o2 = M.MerkleSumTree(ents)
+    assert (new_root.hash, new_root.balances) == (o2.root[0], o2.root[1])
+    back = t.update_leaf(o.entries[3].username, o.entries[3].balances)
+    assert (back.hash, back.balances) == (o.root[0], o.root[1])
+    t.close()

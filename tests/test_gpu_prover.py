@@ -342,3 +342,66 @@ def test_levels_20_circuit_fixture_proof_equals_oracle(ctx, golden_dir):
     tr = KeccakTranscript()
     HP.create_proof(oparams, opk, instances, advice, ChaCha20Rng.seed_from_u64(20), tr)
     assert got == tr.finalize()
+
+
+# ------------------------------------------------------------------ standalone boundary entries
+@pytest.mark.parametrize("rot_scale_log,log_rows", [(3, 9), (0, 7)])
+def test_evaluate_h_standalone_matches_oracle_numerator(ctx, golden_dir, rot_scale_log, log_rows):
+    """sb_evaluate_h over RANDOM columns of the reference circuit's constraint system == the oracle's quotient numerator (oracle/halo2_prover.py
+    `_h_numerator_program` / column-wise form), bit for bit: kernel-level parity of `Evaluator::evaluate_h`, both for halo2's extended-domain layout
+    (rotation = 8 entries) and for a single coset (rotation = 1 entry)."""
+    import types
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    rows = 1 << log_rows
+    A, F, Pn = cs["num_advice_columns"], cs["num_fixed_columns"], len(cs["permutation_columns"])
+    chunk = cs["degree"] - 2
+    n_sets = -(-Pn // chunk)
+    n_cols = A + F + 1 + Pn + n_sets + 4 + 3 * len(cs["lookups"])
+    cols = [cpu.random_fr(rows, 900 + i) for i in range(n_cols)]
+    theta, beta, gamma, y = [B.fr_from_mont_bytes(cpu.random_fr(1, 950 + i).tobytes()) for i in range(4)]
+    E_SIGMA = A + F + 1
+    E_PZ = E_SIGMA + Pn
+    E_L0 = E_PZ + n_sets
+    E_LK = E_L0 + 4
+    pk = types.SimpleNamespace(fixed_cosets=cols[A:A + F], sigma_cosets=cols[E_SIGMA:E_SIGMA + Pn], l0=cols[E_L0], l_last=cols[E_L0 + 1], l_active_row=cols[E_L0 + 2],
+                               x_coset=cols[E_L0 + 3])
+    pcols = [tuple(c) for c in cs["permutation_columns"]]
+    perm_sets = [dict(coset=cols[E_PZ + s], cols=pcols[s * chunk:(s + 1) * chunk], first=s * chunk) for s in range(n_sets)]
+    lk_cosets = [[cols[E_LK + 3 * li + j] for j in range(3)] for li in range(len(cs["lookups"]))]
+    want = HP._h_numerator_program(cs, pk, cols[:A], cols[A + F], perm_sets, lk_cosets, theta, beta, gamma, y, rows, 1 << rot_scale_log, cs["blinding_factors"])
+    out = np.zeros((rows, 4), dtype=np.uint64)
+    ptrs = (ctypes.c_void_p * n_cols)(*[c.ctypes.data for c in cols])
+    text = json.dumps(cs).encode()
+    L().check(L().lib().sb_evaluate_h(ctx.handle, ctypes.c_char_p(text), ptrs, ctypes.c_size_t(n_cols), ctypes.c_uint32(log_rows), ctypes.c_uint32(rot_scale_log),
+                                      P(fr(theta)), P(fr(beta)), P(fr(gamma)), P(fr(y)), P(out)), "sb_evaluate_h")
+    assert (out == want).all()
+    # a wrong column count is an argument error, not a crash
+    from circuits_halo2_b200._lib import SummaB200Error
+    with pytest.raises(SummaB200Error):
+        L().check(L().lib().sb_evaluate_h(ctx.handle, ctypes.c_char_p(text), ptrs, ctypes.c_size_t(n_cols - 1), ctypes.c_uint32(log_rows), ctypes.c_uint32(rot_scale_log),
+                                          P(fr(theta)), P(fr(beta)), P(fr(gamma)), P(fr(y)), P(out)), "sb_evaluate_h")
+
+
+def test_msm_batch_and_grand_product_entries(ctx, golden_dir):
+    import circuits_halo2_b200 as sb
+    params = sb.ParamsKZG.read(os.path.join(golden_dir, "hermez-raw-11"), ctx)
+    n, m = 1 << 11, 11
+    sc = cpu.random_fr(n * m, 321).reshape(m, n, 4)
+    sc[3, 100:] = 0          # a sparse column
+    sc[5] = sc[5, 0]         # a constant column (one hot bucket per window)
+    for precompute in (False, True):
+        if precompute:
+            params.precompute()
+        for basis in (0, 1):
+            out = np.zeros((m, 8), dtype=np.uint64)
+            L().check(L().lib().sb_msm_g1_batch(ctx.handle, params.handle, ctypes.c_int32(basis), P(sc), ctypes.c_size_t(n), ctypes.c_size_t(m), P(out)), "sb_msm_g1_batch")
+            bases = params.g if basis == 0 else params.g_lagrange
+            for j in range(m):
+                assert (out[j] == cpu.best_multiexp(sc[j], bases, threads=8)).all(), (precompute, basis, j)
+    # grand product: z[i + 1] = z[i] * num[i] / den[i]
+    for nn in (1, 77, 5000):
+        num, den, init = cpu.random_fr(nn, 11), cpu.random_fr(nn, 12), fr(777)
+        z = np.zeros((nn + 1, 4), dtype=np.uint64)
+        L().check(L().lib().sb_grand_product(ctx.handle, P(num), P(den), ctypes.c_size_t(nn), P(init), P(z), ctypes.c_size_t(nn + 1)), "sb_grand_product")
+        ratio = cpu.fr_mul(num.reshape(-1), cpu.fr_batch_invert(den.reshape(-1)))
+        assert (z.reshape(-1) == cpu.fr_running_product(ratio, init, nn + 1)).all()

@@ -126,3 +126,17 @@ def test_golden_proofs_are_accepted_by_the_reference_verifier(golden_dir, k):
     inst = gold["instances"].copy()
     inst[2, 0] ^= np.uint64(1)
     assert not RV.verify_mont(*args, proof, inst)
+
+
+def test_oracle_reproduces_entry_13_17_and_bigints_goldens(golden_dir):
+    """merkle_sum_tree/tests.rs:219,251: root balances of csv/entry_13.csv (385969, 459661; depth 4) and csv/entry_17.csv (556863 twice; depth 5, the
+    file ends with an empty line the csv crate skips); csv/entry_16_bigints.csv carries 2^64 (tests.rs:130)."""
+    o13 = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_13.csv"))
+    o17 = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_17.csv"))
+    ob = M.MerkleSumTree.from_csv(os.path.join(golden_dir, "entry_16_bigints.csv"))
+    assert (o13.depth, o13.root[1]) == (4, [385969, 459661])
+    assert (o17.depth, o17.root[1]) == (5, [556863, 556863])
+    assert ob.depth == 4 and max(b for e in ob.entries for b in e.balances) == 1 << 64
+    if os.path.exists("/root/reference/csv/entry_17.csv"):
+        for f in ("entry_13.csv", "entry_17.csv", "entry_16_bigints.csv"):
+            assert open(os.path.join(golden_dir, f), "rb").read() == open("/root/reference/csv/" + f, "rb").read()

@@ -13,7 +13,7 @@ Arrays are numpy views of halo2curves' memory layout (Montgomery, little-endian 
 Fr vectors have shape (n, 4) uint64, G1Affine vectors (n, 8) uint64.
 """
 from .context import Context, default_context  # noqa: F401
-from .arithmetic import best_fft, best_multiexp  # noqa: F401
+from .arithmetic import best_fft, best_fft_dist, best_multiexp  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .params import ParamsKZG  # noqa: F401
 from .merkle_sum_tree import Entry, MerkleProof, MerkleSumTree, Node  # noqa: F401

@@ -39,3 +39,25 @@ def best_fft(a, omega, log_n: int, ctx: Optional[Context] = None) -> np.ndarray:
     w = as_u64(omega, 4)
     _lib.check(_lib.lib().sb_best_fft(ctx.handle, ptr(arr), ptr(w), ctypes.c_uint32(log_n)), "sb_best_fft")
     return arr
+
+
+def best_fft_dist(a, omega, log_n: int, comm, ctx: Optional[Context] = None, scale=None) -> np.ndarray:
+    """`best_fft` as a distributed four-step NTT over the ranks of `comm` (ShardComm / LocalComm): every rank passes the SAME vector, does
+    1 / world of both passes, and gets the whole transform back (all-to-all between the passes, all-gather at the end, over NVLink)."""
+    ctx = ctx or default_context()
+    arr = as_u64(a, 4)
+    if arr.shape[0] != (1 << log_n):
+        raise AssertionError("best_fft_dist: a.len() != 1 << log_n")
+    w = as_u64(omega, 4)
+    d = ctx.alloc(arr.nbytes)
+    try:
+        ctx.upload(d, arr)
+        sc = ptr(as_u64(scale, 4)) if scale is not None else None
+        st = _lib.lib().sb_ntt_dist(ctx.handle, ctypes.byref(comm.struct), ctypes.c_void_p(d), ptr(w), ctypes.c_uint32(log_n), sc, None)
+        if st != 0 and getattr(comm, "error", None) is not None:
+            raise comm.error
+        _lib.check(st, "sb_ntt_dist")
+        ctx.synchronize()
+        return ctx.download(d, arr.nbytes).reshape(-1, 4)
+    finally:
+        ctx.free(d)

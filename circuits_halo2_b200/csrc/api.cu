@@ -72,6 +72,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.ntt_tile = geti("SB_NTT_TILE", 0);
     t.ntt_passes = geti("SB_NTT_PASSES", 0);
     t.ntt_tw_mb = geti("SB_NTT_TW_MB", 1024);
+    t.dist_ntt_min_k = geti("SB_DIST_NTT_MIN_K", 22);
     t.msm_no_cta_scan = getb("SB_MSM_NO_CTA_SCAN");
     t.shard_msm_by_range = getb("SB_SHARD_MSM_BY_RANGE");
     t.no_side_stream = getb("SB_NO_SIDE_STREAM");
@@ -446,6 +447,14 @@ int32_t sb_ntt_dev(sb_ctx *ctx, void *d_a, const uint8_t omega[32], uint32_t log
     if (!ctx || !d_a || !omega) return SB_ERR_ARG;
     Guard g(ctx);
     return ntt_run(ctx, d_a, omega, log_n, pick_stream(ctx, stream));
+}
+int32_t sb_ntt_dist(sb_ctx *ctx, const sb_comm *comm, void *d_a, const uint8_t omega[32], uint32_t log_n, const uint8_t *scale, void *stream) {
+    if (!ctx || !comm || !d_a || !omega) return SB_ERR_ARG;
+    SB_REQUIRE(comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world, "sb_comm: rank / world out of range");
+    Guard g(ctx);
+    fr_t s;
+    if (scale) memcpy(s.v, scale, 32);
+    return ntt_run_dist(ctx, comm, d_a, omega, log_n, scale ? &s : nullptr, pick_stream(ctx, stream));
 }
 int32_t sb_best_fft(sb_ctx *ctx, uint8_t *a, const uint8_t omega[32], uint32_t log_n) {
     if (!ctx || !a || !omega) return SB_ERR_ARG;

@@ -61,6 +61,7 @@ struct Tuning {
     int msm_finish_at = 16384;  // SB_MSM_FINISH_AT: bucket count below which the hierarchy finishes in one step
     int ntt_tile = 0;         // SB_NTT_TILE: 11 | 12 = log2 elements per NTT tile (0 = choose from the size)
     int ntt_passes = 0;       // SB_NTT_PASSES: minimum number of NTT passes (0 = as few as the tile allows)
+    int dist_ntt_min_k = 22;  // SB_DIST_NTT_MIN_K: sharded proofs run their replicated size-n transforms as distributed four-step NTTs from this k on
     int ntt_tw_mb = 1024;     // SB_NTT_TW_MB: budget (MiB) of a plan's full inter-pass twiddle tables; above it the two-level tables are used
     bool msm_no_cta_scan = false;    // SB_MSM_NO_CTA_SCAN
     bool shard_msm_by_range = false; // SB_SHARD_MSM_BY_RANGE
@@ -155,6 +156,7 @@ struct NttFuse {
     uint64_t src_stride = 0, dst_stride = 0, pre_stride = 0, post_stride = 0;
 };
 int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t omega[32], uint32_t log_n, const NttFuse *fuse, cudaStream_t st);
+int32_t ntt_run_dist(sb_ctx *ctx, const sb_comm *comm, void *d_a, const uint8_t omega[32], uint32_t log_n, const fr_t *scale, cudaStream_t st);
 void ntt_make_plan(uint32_t log_n, uint32_t tile_log, uint32_t max_passes_hint, int *npass, uint32_t *radix);
 void ntt_plans_free(sb_ctx *ctx);
 

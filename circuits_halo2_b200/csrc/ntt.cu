@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
     const uint32_t tile = 1u << G.t, T = tile >> 3, tid = threadIdx.x, half_r = 1u << (G.r - 1);
     uint4 *s_lo = smem, *s_hi = smem + tile;
     uint4 *w_lo = s_hi + tile, *w_hi = w_lo + half_r;
-    const NttTileCoord tc(p, blockIdx.x);
+    const NttTileCoord tc(p, blockIdx.x + p.tile0);
     const NttBatch bo(p, blockIdx.y);
 
     // butterfly twiddles of this pass: global -> shared through cp.async (no register staging), under the data loads below
@@ -461,6 +461,98 @@ int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t 
             else SB_LAUNCH(ctx, ntt_pass_kernel<11>, dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
         }
         log_a += a.r;
+    }
+    return SB_OK;
+}
+
+// ---- distributed four-step NTT (the one place an all-to-all belongs) ------------------------------------------------------------
+// One transform of a vector that every rank holds in full (the sharded prover's polynomials are replicated), each rank doing 1 / world of both
+// passes of the two-pass plan:
+//   pass 1  the rank's share of the column tiles (columns c in [rank C / world, (rank + 1) C / world)), twiddles applied, in place in a work buffer;
+//   A       all-to-all: the rank receives rows k1 in [rank R1 / world, ...) of everybody's columns (blocks packed / unpacked by 2D device copies);
+//   pass 2  the rank's share of the row tiles -> its stripe out[k1 + R1 k2] of the natural-order result;
+//   B       all-gather of the stripes: every rank ends with the whole transform, like the local ntt_run.
+// The exchanges go through the caller's collective library (sb_comm: NCCL all_to_all / all_gather over NVLink); world = 1 skips them.
+int32_t ntt_run_dist(sb_ctx *ctx, const sb_comm *comm, void *d_a, const uint8_t omega[32], uint32_t log_n, const fr_t *scale, cudaStream_t st) {
+    const uint32_t W = comm ? (uint32_t)comm->world : 1u, rk = comm ? (uint32_t)comm->rank : 0u;
+    const fr_t one = fr_t::one();
+    NttFuse f;
+    if (scale) { f.has_scale = true; f.scale = *scale; }
+    SB_REQUIRE(log_n <= 28, "ntt_dist: log_n > 28");
+    if (log_n < 16) return ntt_run_fused(ctx, d_a, d_a, omega, log_n, &f, st);  // too small to be worth two exchanges: every rank transforms it locally
+    SB_REQUIRE((W & (W - 1)) == 0 && W <= 8, "ntt_dist: world must be 1, 2, 4 or 8");
+    SB_REQUIRE(W == 1 || (comm->alltoall_dev && comm->allgather_dev), "ntt_dist: sb_comm needs alltoall_dev and allgather_dev");
+    NttPlan *pl = nullptr;
+    SB_TRY(plan_get(ctx, omega, log_n, scale ? *scale : one, st, &pl));
+    SB_REQUIRE(pl->npass == 2, "ntt_dist: the size needs a two-pass plan (2^16 .. 2^24)");
+    static bool attr_set[64] = {false};
+    if (ctx->device >= 64 || !attr_set[ctx->device]) {
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
+        if (ctx->device < 64) attr_set[ctx->device] = true;
+    }
+    const uint64_t n = 1ull << log_n;
+    const uint32_t r1 = pl->radix[0], r2 = pl->radix[1];
+    const uint64_t R1 = 1ull << r1, Cc = 1ull << r2;
+    uint8_t *d_work, *d_send, *d_recv;
+    char slot[3][48];   // per stream, like the local transform's ping-pong buffer
+    snprintf(slot[0], 48, "nttd_work_%llx", (unsigned long long)(uintptr_t)st);
+    snprintf(slot[1], 48, "nttd_send_%llx", (unsigned long long)(uintptr_t)st);
+    snprintf(slot[2], 48, "nttd_recv_%llx", (unsigned long long)(uintptr_t)st);
+    SB_TRY(scratch_get(ctx, slot[0], n * 32, (void **)&d_work));
+    SB_TRY(scratch_get(ctx, slot[1], n * 32, (void **)&d_send));   // exchange A: n / W; exchange B: the stripes of all ranks (n)
+    SB_TRY(scratch_get(ctx, slot[2], (n / W) * 32, (void **)&d_recv));
+    NttPassArgs a;
+    auto base_args = [&](int t) {
+        memset(&a, 0, sizeof a);
+        a.log_n = log_n; a.r = pl->radix[t]; a.log_a = t == 0 ? 0 : r1; a.log_c = log_n - a.log_a - a.r; a.log_r1 = r1; a.log_tlo = pl->log_tlo;
+        a.npass = 2; a.kind = t == 0 ? NTT_STRIDED : NTT_LAST;
+        a.g = pl->tile_log - a.r;
+        if (a.kind == NTT_STRIDED && a.g > a.log_c) a.g = a.log_c;
+        if (a.kind == NTT_LAST && a.g > a.log_r1) a.g = a.log_r1;
+        a.w = pl->w_block[t]; a.tw_full = t == 0 ? pl->tw_full[0] : nullptr; a.t_lo = pl->t_lo; a.t_hi = pl->t_hi;
+        if (t == 0 && !a.tw_full && !(pl->scale == one)) { a.has_tw_scale = 1; a.tw_scale = pl->scale; }
+        a.n_in = n; a.n_out = n;
+    };
+    auto launch = [&](uint64_t tiles_all) -> int32_t {
+        SB_REQUIRE(tiles_all % W == 0 && tiles_all / W >= 1, "ntt_dist: world does not divide the tiles of a pass");
+        const uint64_t mine = tiles_all / W;
+        a.tile0 = (uint32_t)(rk * mine);
+        const unsigned threads = 1u << (a.r + a.g - 3);
+        if (a.r + a.g == 12) SB_LAUNCH(ctx, ntt_pass_kernel<12>, dim3((unsigned)mine, 1), threads, pass_smem(a.r, a.g), st, a);
+        else SB_LAUNCH(ctx, ntt_pass_kernel<11>, dim3((unsigned)mine, 1), threads, pass_smem(a.r, a.g), st, a);
+        return SB_OK;
+    };
+    // ---- pass 1 on my columns
+    base_args(0);
+    a.src = (const uint4 *)d_a; a.dst = (uint4 *)d_work;
+    SB_TRY(launch(1ull << (log_n - a.r - a.g)));
+    // ---- exchange A
+    const uint64_t rows_w = R1 / W, cols_w = Cc / W, blk = rows_w * cols_w * 32;
+    if (W > 1) {
+        for (uint32_t q = 0; q < W; q++)   // block for rank q: its rows of my columns
+            SB_CUDA_TRY(cudaMemcpy2DAsync(d_send + q * blk, cols_w * 32, d_work + ((uint64_t)q * rows_w * Cc + (uint64_t)rk * cols_w) * 32, Cc * 32, cols_w * 32, rows_w,
+                                          cudaMemcpyDeviceToDevice, st));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (comm->alltoall_dev(comm->user, d_send, d_recv, blk, (void *)st) != 0) { set_last_error("sb_comm.alltoall_dev failed"); return SB_ERR_ARG; }
+        for (uint32_t q = 0; q < W; q++)   // from rank q: my rows of its columns
+            SB_CUDA_TRY(cudaMemcpy2DAsync(d_work + ((uint64_t)rk * rows_w * Cc + (uint64_t)q * cols_w) * 32, Cc * 32, d_recv + q * blk, cols_w * 32, cols_w * 32, rows_w,
+                                          cudaMemcpyDeviceToDevice, st));
+    }
+    // ---- pass 2 on my rows
+    base_args(1);
+    a.src = (const uint4 *)d_work; a.dst = (uint4 *)d_a;
+    SB_TRY(launch(1ull << (log_n - a.r - a.g)));
+    // ---- exchange B: my stripe out[k1 + R1 k2], k1 in my range, to everybody
+    if (W > 1) {
+        const uint64_t stripe = (n / W) * 32;
+        SB_CUDA_TRY(cudaMemcpy2DAsync(d_send + rk * stripe, rows_w * 32, (uint8_t *)d_a + (uint64_t)rk * rows_w * 32, R1 * 32, rows_w * 32, Cc, cudaMemcpyDeviceToDevice, st));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (comm->allgather_dev(comm->user, d_send, stripe, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
+        for (uint32_t q = 0; q < W; q++) {
+            if (q == rk) continue;
+            SB_CUDA_TRY(cudaMemcpy2DAsync((uint8_t *)d_a + (uint64_t)q * rows_w * 32, R1 * 32, d_send + q * stripe, rows_w * 32, rows_w * 32, Cc, cudaMemcpyDeviceToDevice, st));
+        }
     }
     return SB_OK;
 }

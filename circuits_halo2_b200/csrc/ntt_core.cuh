@@ -33,6 +33,7 @@ struct NttPassArgs {
     const uint4 *post_vec; // optional, last pass: output element i is multiplied by post_vec[i]
     uint32_t log_n, r, g, log_a, log_c, log_r1, log_tlo;
     uint32_t kind, npass, n_mid;
+    uint32_t tile0;        // first tile of this launch (a rank of a distributed transform runs a sub-range of a pass' tiles)
     uint32_t mid_bits[NTT_MAX_PASS];  // radices of passes 2 .. P-1 (for the last pass' digit reversal)
     uint32_t pre_m;    // optional, first pass: input element i is multiplied by pre_pat[i % pre_m] (pre_m <= 8; 0 = off)
     uint32_t post_m;   // optional, last pass: output element i is multiplied by post_pat[i % post_m] (post_m <= 8; 0 = off)

@@ -937,6 +937,14 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         return coset_values(ctx, pk, d_coeff, rank, world, co_per, dyn_slot(0, q), n_dyn * n, st2);
     };
 
+    // lagrange_to_coeff of a column every rank holds in full: a distributed four-step NTT at the largest k (each rank 1 / world of both passes, an
+    // all-to-all between them, an all-gather after), the local fused transform otherwise.  The choice depends on (k, world) only: lock step.
+    const bool dist_ntt = comm && world > 1 && comm->alltoall_dev && (world & (world - 1)) == 0 && pk->k >= (uint32_t)ctx->tune.dist_ntt_min_k && pk->k >= 16 && pk->k <= 24;
+    auto l2c_repl = [&](void *d_poly, cudaStream_t s) -> int32_t {
+        if (dist_ntt) return ntt_run_dist(ctx, comm, d_poly, (const uint8_t *)d->omega_inv.v, pk->k, &d->ifft_divisor, s);
+        return dom_l2c(ctx, d, d_poly, s);
+    };
+
     // ---- transcript preamble
     tr.common_scalar(pk->transcript_repr);
     std::vector<Fr> inst(n_inst);
@@ -996,7 +1004,12 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(upload_frs(ctx, (uint8_t *)adv[c] + usable * 32, blind, st));
     }
     for (int c = 0; c < A; c++) (void)rng.next_fr();
-    {   // lagrange_to_coeff of the A advice columns: one batched out-of-place inverse transform (n^-1 folded in)
+    if (dist_ntt) {
+        for (int c = 0; c < A; c++) {
+            SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
+            SB_TRY(l2c_repl(adv_poly[c], st));
+        }
+    } else {   // lagrange_to_coeff of the A advice columns: one batched out-of-place inverse transform (n^-1 folded in)
         NttFuse f;
         f.has_scale = true;
         f.scale = d->ifft_divisor;
@@ -1076,10 +1089,10 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         for (Fr &x : blind) x = rng.next_fr();
         SB_TRY(upload_frs(ctx, (uint8_t *)L.p_tab + usable * 32, blind, st));
         SB_CUDA_TRY(cudaMemcpyAsync(L.in_poly, L.p_in, n * 32, cudaMemcpyDeviceToDevice, st));
-        SB_TRY(dom_l2c(ctx, d, L.in_poly, st));
+        SB_TRY(l2c_repl(L.in_poly, st));
         (void)rng.next_fr();
         SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
-        SB_TRY(dom_l2c(ctx, d, L.tab_poly, st));
+        SB_TRY(l2c_repl(L.tab_poly, st));
         (void)rng.next_fr();
         SB_TRY(side_after_main());
         SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 1, L.in_poly));
@@ -1163,13 +1176,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         for (int s = 0; s < n_sets; s++) {
             PermSet &S = psets[s];
             SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
-            SB_TRY(dom_l2c(ctx, d, S.z_poly, st2));
+            SB_TRY(l2c_repl(S.z_poly, st2));
             SB_TRY(side_cosets((size_t)A + 1 + s, S.z_poly));
         }
         for (size_t li = 0; li < lks.size(); li++) {
             LookupState &L = lks[li];
             SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
-            SB_TRY(dom_l2c(ctx, d, L.z_poly, st2));
+            SB_TRY(l2c_repl(L.z_poly, st2));
             SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li, L.z_poly));
         }
         std::vector<uint8_t> pts((size_t)n_z * 64);

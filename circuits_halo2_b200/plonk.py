@@ -94,7 +94,9 @@ class ProvingKey:
 class _SbComm(ctypes.Structure):
     _AG_HOST = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
     _AG_DEV = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
-    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("user", ctypes.c_void_p), ("allgather_host", _AG_HOST), ("allgather_dev", _AG_DEV)]
+    _A2A_DEV = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("user", ctypes.c_void_p), ("allgather_host", _AG_HOST), ("allgather_dev", _AG_DEV),
+                ("alltoall_dev", _A2A_DEV)]
 
 
 class _DevMem:
@@ -123,7 +125,8 @@ class ShardComm:
         self.host_on_cpu = "gloo" in backend
         self.device = device if device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else None)
         self.error = None
-        self._c = _SbComm(self.rank, self.world, None, _SbComm._AG_HOST(self._allgather_host), _SbComm._AG_DEV(self._allgather_dev))
+        self._c = _SbComm(self.rank, self.world, None, _SbComm._AG_HOST(self._allgather_host), _SbComm._AG_DEV(self._allgather_dev),
+                          _SbComm._A2A_DEV(self._alltoall_dev))
 
     def _allgather_host(self, _user, send, recv, nbytes):
         try:
@@ -156,6 +159,22 @@ class ShardComm:
             self.error = e
             return 1
 
+    def _alltoall_dev(self, _user, d_send, d_recv, bytes_per_pair, stream):
+        """NCCL all-to-all over NVLink (the transpose step of the distributed four-step NTT): block q of d_send -> rank q"""
+        try:
+            torch, dist = self.torch, self.dist
+            dev = torch.device("cuda", self.device)
+            send = torch.as_tensor(_DevMem(d_send, bytes_per_pair * self.world), device=dev)
+            recv = torch.as_tensor(_DevMem(d_recv, bytes_per_pair * self.world), device=dev)
+            ext = torch.cuda.ExternalStream(stream, device=dev) if stream else torch.cuda.current_stream()
+            with torch.cuda.stream(ext):
+                dist.all_to_all_single(recv, send, group=self.group)
+            ext.synchronize()
+            return 0
+        except Exception as e:
+            self.error = e
+            return 1
+
     @property
     def struct(self):
         return self._c
@@ -166,7 +185,7 @@ class LocalComm:
 
     def __init__(self):
         self.rank, self.world, self.error = 0, 1, None
-        self._c = _SbComm(0, 1, None, _SbComm._AG_HOST(0), _SbComm._AG_DEV(0))
+        self._c = _SbComm(0, 1, None, _SbComm._AG_HOST(0), _SbComm._AG_DEV(0), _SbComm._A2A_DEV(0))
 
     @property
     def struct(self):

@@ -167,7 +167,15 @@ typedef struct sb_comm {
     void *user;
     int32_t (*allgather_host)(void *user, const void *send, void *recv, size_t bytes_per_rank);
     int32_t (*allgather_dev)(void *user, void *d_buf, size_t bytes_per_rank, void *stream);
+    /* all-to-all of device memory: block q of d_send (bytes_per_pair each) goes to rank q, block q of d_recv comes from rank q; complete (or
+     * stream-ordered on `stream`) on return.  Needed by sb_ntt_dist (and by sharded proofs at k >= SB_DIST_NTT_MIN_K); may be NULL otherwise. */
+    int32_t (*alltoall_dev)(void *user, const void *d_send, void *d_recv, size_t bytes_per_pair, void *stream);
 } sb_comm;
+/* Distributed four-step NTT (north_star: "an NCCL all-to-all over NVLink ... for a distributed four-step NTT at the largest K"): best_fft of a
+ * vector that every rank holds in full at d_a, in place; each rank computes 1 / world of both passes, an all-to-all transposes between them and an
+ * all-gather replicates the result.  Sizes 2^16 .. 2^24 (two-pass plans); smaller sizes are transformed locally by every rank.  `scale` (or NULL)
+ * multiplies the result (n^-1 of an inverse transform).  Every rank must call it with the same arguments. */
+int32_t sb_ntt_dist(sb_ctx *ctx, const sb_comm *comm, void *d_a, const uint8_t omega[32], uint32_t log_n, const uint8_t *scale /* 32 B or NULL */, void *stream);
 int32_t sb_create_proof_sharded(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint8_t *advice,
                                 const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
 int32_t sb_create_proof_sharded_dev(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const void *d_advice,

@@ -39,6 +39,16 @@ def main():
         plain = sb.create_proof(pk, instances, advice, seed, transcript)
         sharded = sb.create_proof(pk, instances, advice, seed, transcript, comm=comm)
         assert sharded == plain, f"rank {rank}: sharded proof differs from the single-GPU proof (transcript {transcript})"
+    # the distributed four-step NTT (all-to-all between the passes, all-gather after): every rank ends with the local transform's result, bit for bit
+    for ln in (16, 19, 20, 22):
+        a = np.random.default_rng(ln).integers(0, 1 << 62, size=(1 << ln, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 61) - 1)   # < 2^253 < r: canonical residues
+        w = fields.fr_to_mont(fields.omega(ln))
+        want = sb.best_fft(a.copy(), w, ln, ctx)
+        got = sb.best_fft_dist(a.copy(), w, ln, comm, ctx)
+        assert (got == want).all(), f"rank {rank}: distributed NTT 2^{ln} differs from the local transform"
+        winv, ninv = fields.fr_to_mont(pow(fields.omega(ln), -1, fields.FR_MODULUS)), fields.fr_to_mont(pow(1 << ln, -1, fields.FR_MODULUS))
+        assert (sb.best_fft_dist(want.copy(), winv, ln, comm, ctx, scale=ninv) == a).all(), f"rank {rank}: distributed inverse NTT 2^{ln} (n^-1 folded in) is not the inverse"
     # timing (wall clock around the lock-step call, max over ranks)
     def timed(fn):
         dist.barrier()

@@ -53,7 +53,24 @@ def test_coset_path_world1_equals_plain_path(ctx, golden_dir, k):
         assert sb.create_proof(pk, instances, advice, sb.seed_from_u64(k), tk, comm=sb.LocalComm()) == sb.create_proof(pk, instances, advice, sb.seed_from_u64(k), tk)
 
 
-def test_sharded_rejects_world_that_does_not_divide_the_cosets(ctx, golden_dir):
+@pytest.mark.parametrize("log_n", [16, 17, 20, 22])
+def test_distributed_ntt_world1_equals_local(ctx, log_n):
+    """sb_ntt_dist with a single rank (no exchange): the tile-range launches of both passes reproduce best_fft, with and without the folded scale"""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import fields
+    a = np.random.default_rng(log_n).integers(0, 1 << 62, size=(1 << log_n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)   # < 2^253 < r: canonical residues
+    w = fields.fr_to_mont(fields.omega(log_n))
+    want = sb.best_fft(a.copy(), w, log_n, ctx)
+    assert (sb.best_fft_dist(a.copy(), w, log_n, sb.LocalComm(), ctx) == want).all()
+    d = sb.EvaluationDomain(3, log_n, ctx)
+    winv = fields.fr_to_mont(pow(fields.omega(log_n), -1, fields.FR_MODULUS))
+    ninv = fields.fr_to_mont(pow(1 << log_n, -1, fields.FR_MODULUS))
+    assert (sb.best_fft_dist(want.copy(), winv, log_n, sb.LocalComm(), ctx, scale=ninv) == a).all()          # inverse with n^-1 folded in: round trip
+    assert (d.lagrange_to_coeff(want.copy()) == a).all()
+
+
+def test_sharded_rejects_comm_without_callbacks(ctx, golden_dir):
     import circuits_halo2_b200 as sb
     from circuits_halo2_b200 import fields
     from circuits_halo2_b200._lib import SummaB200Error
@@ -76,6 +93,12 @@ def test_two_gpu_sharded_proof_equals_single_gpu_proof():
            os.path.join(ROOT, "tests", "multi", "sharded_proof_worker.py"), "14"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    # the same with every replicated size-n transform run as a distributed four-step NTT (the k >= 22 path, forced at k = 16)
+    env = dict(os.environ, SB_DIST_NTT_MIN_K="10")
+    cmd[cmd.index("29533")] = "29535"
+    out = subprocess.run(cmd[:-1] + ["16"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    cmd[cmd.index("29535")] = "29533"
     # the north_star's other split of a commitment: by base range, 64-byte partial points added on the host
     env = dict(os.environ, SB_SHARD_MSM_BY_RANGE="1")
     cmd[cmd.index("29533")] = "29534"

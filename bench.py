@@ -50,12 +50,21 @@ def env_int(name, default):
 
 
 def witness_file(k):
-    """k >= 20: the LEVELS = 20 circuit over the real 2^20-user tree; smaller k: the reference's own LEVELS = 4 example (csv/entry_16.csv, user 0)"""
-    return "mst_inclusion_assignment_l20_tree.npz" if k >= 20 else "mst_inclusion_assignment.npz"
+    """k >= 23: BASELINE configs[3]'s MstInclusionCircuit<23,8,8> (2^23 users, 8 currencies); k >= 20: configs[2]'s <20,2,8> over the 2^20-user tree;
+    smaller k: the reference's own LEVELS = 4 example (csv/entry_16.csv, user 0)"""
+    return "mst_inclusion_assignment_l23_n8_tree.npz" if k >= 23 else "mst_inclusion_assignment_l20_tree.npz" if k >= 20 else "mst_inclusion_assignment.npz"
+
+
+def cs_file(k):
+    """the 8-currency constraint system is generated from the chip definitions (oracle/mst_circuit.py constraint_system(8)); the 2-currency one is
+    the reference verifier contract's"""
+    return "mst_inclusion_cs_n8.json" if k >= 23 else "mst_inclusion_cs.json"
 
 
 def circuit_name(k):
-    return "MstInclusionCircuit<20,2,8>, user 123456 of a 2^20-user tree" if k >= 20 else "MstInclusionCircuit<4,2,8>, csv/entry_16.csv user 0"
+    if k >= 23:
+        return "MstInclusionCircuit<23,8,8>, user 7654321 of a 2^23-user 8-currency tree (BASELINE configs[3])"
+    return "MstInclusionCircuit<20,2,8>, user 123456 of a 2^20-user tree (BASELINE configs[2])" if k >= 20 else "MstInclusionCircuit<4,2,8>, csv/entry_16.csv user 0"
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -125,7 +134,7 @@ def _oracle_prove(k, threads, with_commitments=False):
     from oracle.transcript import KeccakTranscript
     cpu.set_threads(threads)
     fx = np.load(os.path.join(GOLDEN, witness_file(k)))
-    cs = json.load(open(os.path.join(GOLDEN, "mst_inclusion_cs.json")))
+    cs = json.load(open(os.path.join(GOLDEN, cs_file(k))))
     t0 = time.perf_counter()
     params = HP.Params.setup(k, 0x5A110000 + k, threads)
     pk = HP.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], 0x1234)
@@ -174,12 +183,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def check_batch_samples(bc):
+    """Rank 0, checker leg: three of the batched inclusion proofs judged by the reference's verifier contract with each user's own public inputs."""
+    from oracle import bn254 as B
+    from oracle import reference_verifier as RV
+    k = bc["k"]
+    v = RV.verifier_for_key(k, 0x5A110000 + k, [B.g1_from_mont_bytes(c.tobytes()) for c in bc["fixed_comms"]], [B.g1_from_mont_bytes(c.tobytes()) for c in bc["sigma_comms"]], 0x1234)
+    ok = all(v.verify(p, inst) for _, p, inst in bc["samples"])
+    assert ok, "a batched inclusion proof was rejected by the reference verifier"
+    return ok
+
+
 def checker_and_cpu_baseline(records, args, time_cpu):
     """Rank 0.  oracle/ as the CHECKER of what was just timed, and (N = 1) as the bounded CPU baseline.
     For every proved k: the key's 17 commitments equal the closed-form keygen (known tau), the proof equals the committed CPU-oracle golden proof
     where one exists (k = 17, 20), and the reference's verifier contract accepts the proof and rejects a tampered copy."""
     import numpy as np
     from oracle import bn254 as B
+    from oracle import halo2_verifier as HV
     from oracle import reference_verifier as RV
     out = {}
     for rec in records:
@@ -192,13 +213,17 @@ def checker_and_cpu_baseline(records, args, time_cpu):
         key_ok = fgot == fexp and sgot == sexp
         gold_path = os.path.join(GOLDEN, f"golden_proof_k{k}.npz")
         golden = bool(np.load(gold_path)["proof"].tobytes() == rec["_proof"]) if os.path.exists(gold_path) else None
-        v = RV.verifier_for_key(k, tau, fgot, sgot, 0x1234)
         inst = [B.fr_from_mont_bytes(x.tobytes()) for x in fx["instances"]]
-        ok = bool(v.verify(rec["_proof"], inst))
         bad = bytearray(rec["_proof"])
         bad[0x400] ^= 1
-        rejected = not v.verify(bytes(bad), inst)
-        out[k] = {"verified": ok and rejected, "reference_verifier_accepts": ok, "tampered_rejected": rejected, "key_commitments_equal_closed_form_keygen": key_ok,
+        cs = json.load(open(os.path.join(GOLDEN, cs_file(k))))
+        generic = lambda p: bool(HV.verify_proof(cs, k, fgot, sgot, 0x1234, inst, p, keccak=True, tau=tau))
+        if cs_file(k) == "mst_inclusion_cs.json":
+            v = RV.verifier_for_key(k, tau, fgot, sgot, 0x1234)      # the reference's own verifier contract (2-currency circuit)
+            ok, rejected, judge = bool(v.verify(rec["_proof"], inst)) and generic(rec["_proof"]), not v.verify(bytes(bad), inst), "reference verifier contract + oracle/halo2_verifier.py"
+        else:
+            ok, rejected, judge = generic(rec["_proof"]), not generic(bytes(bad)), "oracle/halo2_verifier.py (the reference has no contract for 8 currencies)"
+        out[k] = {"verified": ok and rejected, "verifier": judge, "verifier_accepts": ok, "tampered_rejected": rejected, "key_commitments_equal_closed_form_keygen": key_ok,
                   "proof_equals_cpu_oracle_golden": golden}
         assert ok and rejected and key_ok and golden is not False, f"k={k}: checker failed: {out[k]}"
     cpu_baseline = None
@@ -229,7 +254,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=22, help="size of the MSM side record (2^log_n points per GPU; 0 = skip)")
     ap.add_argument("--ntt-log-n", type=int, default=22, help="size of the NTT side record (0 = skip)")
     ap.add_argument("--batch-k", type=int, default=13, help="k of the batched inclusion-proof side record (0 = skip)")
-    ap.add_argument("--batch-proofs", type=int, default=64, help="proofs per GPU in the batch")
+    ap.add_argument("--batch-proofs", type=int, default=2048, help="distinct users proved per GPU in the batch (2048 x 8 GPUs = configs[4]'s 2^14)")
     ap.add_argument("--batch-workers", type=str, default="8", help="worker threads (contexts) per GPU to sweep")
     ap.add_argument("--mst-log-n", type=int, default=20, help="users (2^x) of the Merkle-sum-tree build (0 = skip; 20 also feeds the headline's public inputs)")
     ap.add_argument("--cpu-sample-k", type=int, default=17, help="k of the bounded CPU-baseline sample")
@@ -349,13 +374,14 @@ def main():
     # ---- create_proof at every requested k ----------------------------------------------------------------------------------------
     ks = sorted(set([int(x) for x in args.proof_k.split(",") if x] + [HEADLINE_K]))
     comm = sb.ShardComm(device=local) if world > 1 else None
-    cs_text = open(os.path.join(GOLDEN, "mst_inclusion_cs.json")).read()
+    mst23 = None
     records = []
     clocks = None
     for pk_k in ks:
         ctx = sb.Context(local)   # a context per k: its scratch arena is released before the next (larger) k
         nrow = 1 << pk_k
         fx = np.load(os.path.join(GOLDEN, witness_file(pk_k)))
+        cs_text = open(os.path.join(GOLDEN, cs_file(pk_k))).read()
         t0 = time.perf_counter()
         kzg = sb.ParamsKZG.setup(pk_k, 0x5A110000 + pk_k, ctx, download=False)
         t_srs = time.perf_counter() - t0
@@ -365,6 +391,23 @@ def main():
         insts = [fields_mod.fr_from_mont(v) for v in fx["instances"]]
         if pk_k == HEADLINE_K and tree_instances is not None:
             assert insts == tree_instances, "the GPU-built 2^20-user tree does not give the fixture's public inputs (leaf hash, root hash, root balances)"
+        if pk_k >= 23 and rank == 0 and world == 1 and args.mst_log_n:
+            # configs[3]: the 2^23-user, 8-currency tree on the GPU gives this circuit's public inputs; the product's witness generator gives its witness
+            n23 = int(fx["n_users"][0])
+            bal23 = np.random.default_rng(int(fx["balance_seed"][0])).integers(0, 1 << 40, size=(n23, 8), dtype=np.uint64)
+            t0 = time.perf_counter()
+            tree23 = sb.MerkleSumTree.from_arrays([b"user_%d" % i for i in range(n23)], bal23, ctx=ctx)
+            t_tree23 = time.perf_counter() - t0
+            idx23 = int(fx["user_index"][0])
+            pre23, path23 = tree23.raw_proofs([idx23])
+            inst23, cells23, vals23 = sb.mst_inclusion_witness(23, 8, pk_k, pre23[0], path23[0])
+            assert inst23 == insts, "the GPU-built 2^23-user 8-currency tree does not give the fixture's public inputs"
+            got_w = {(int(c), int(r)): v.tobytes() for (c, r), v in zip(cells23, vals23)}
+            assert got_w == {(int(c), int(r)): v.tobytes() for (c, r), v in zip(fx["advice_cells"], fx["advice_values"])}, "product witness != fixture witness"
+            mst23 = {"users": n23, "currencies": 8, "device_ms": tree23.build_ms, "wall_s_incl_host_packing": t_tree23,
+                     "witness_equals_fixture": True, "public_inputs_equal_fixture": True}
+            tree23.close()
+            del bal23
         cells, vals = np.ascontiguousarray(fx["advice_cells"]), np.ascontiguousarray(fx["advice_values"])
         adv_host = torch.zeros((3, nrow, 4), dtype=torch.int64).pin_memory()
         adv_np = adv_host.numpy().view(np.uint64)
@@ -527,37 +570,52 @@ def main():
     # ---- side record: batched inclusion proofs (BASELINE configs[4]): many create_proof calls against one resident key, replicas only --------
     batched = None
     if args.batch_k:
+        # distinct users of ONE 2^20-user tree (rebuilt on this rank's GPU), one resident key at the circuit's minimum k = 13: Merkle proofs gathered
+        # on the GPU in one launch, then per user on the worker threads: witness generation (csrc/witness.cpp) + create_proof (sparse witness entry).
+        # --batch-proofs users per rank; at 8 GPUs the default 2048 per rank is configs[4]'s 2^14 distinct users.
         bk, nb_proofs = args.batch_k, args.batch_proofs
         ctx = sb.Context(local)
-        fxb = np.load(os.path.join(GOLDEN, "mst_inclusion_assignment_l20_tree.npz" if bk >= 13 else "mst_inclusion_assignment.npz"))
+        fxb = np.load(os.path.join(GOLDEN, "mst_inclusion_assignment_l20_tree.npz"))
+        cs20 = open(os.path.join(GOLDEN, "mst_inclusion_cs.json")).read()
         kzg = sb.ParamsKZG.setup(bk, 0x5A110000 + bk, ctx, download=False)
-        pkey = sb.ProvingKey.from_sparse(kzg, cs_text, fxb["fixed_cells"], fxb["fixed_values"], fxb["perm_cells"], 0x1234, ctx)
-        insts = [fields_mod.fr_from_mont(v) for v in fxb["instances"]]
-        cells, vals = np.ascontiguousarray(fxb["advice_cells"]), np.ascontiguousarray(fxb["advice_values"])
-        jobs = [(insts, cells, vals, sb.seed_from_u64(1000 * rank + j), sb.TRANSCRIPT_KECCAK) for j in range(nb_proofs)]
-        first = sb.create_proof_sparse(pkey, *jobs[0])
+        pkey = sb.ProvingKey.from_sparse(kzg, cs20, fxb["fixed_cells"], fxb["fixed_values"], fxb["perm_cells"], 0x1234, ctx)
+        nmb = 1 << 20
+        balb = np.random.default_rng(20).integers(0, 1 << 40, size=(nmb, 2), dtype=np.uint64)
+        treeb = sb.MerkleSumTree.from_arrays([b"user_%d" % i for i in range(nmb)], balb, ctx=ctx)
+        users = [int(x) for x in (np.arange(nb_proofs, dtype=np.int64) * 509 + rank * nb_proofs * 509 + 1) % nmb]   # distinct across ranks
+        seeds = [sb.seed_from_u64(7000000 + u) for u in users]
         sweep = {}
+        sample = None
         for workers in [int(x) for x in args.batch_workers.split(",") if x]:
             bp = sb.BatchProver(pkey, workers)
-            bp.prove_many_sparse(jobs[: 2 * workers])  # warm-up: scratch arenas and NTT plans of every context
+            bp.prove_users(treeb, users[: 2 * workers], seeds[: 2 * workers])  # warm-up: scratch arenas and NTT plans of every context
             barrier()
             t0 = time.perf_counter()
-            outp = bp.prove_many_sparse(jobs)
+            outp = bp.prove_users(treeb, users, seeds)
             torch.cuda.synchronize()
             dt = max_over_ranks(time.perf_counter() - t0)
-            assert outp[0] == first and len(set(outp)) == len(outp), "batched proofs must equal the sequential ones and differ per seed"
+            assert len(set(outp)) == len(outp), "proofs of distinct users must differ"
             sweep[str(workers)] = world * nb_proofs / dt
+            sample = [(users[j], outp[j]) for j in (0, nb_proofs // 2, nb_proofs - 1)]
             bp.close()
-        batched = {"k": bk, "proofs_per_rank": nb_proofs, "n_gpus": world, "proofs_per_s_by_workers_per_gpu": sweep, "best_proofs_per_s": max(sweep.values()),
-                   "host_cores": os.cpu_count(), "circuit": "MstInclusionCircuit<20,2,8> (LEVELS = 20), sparse witness entry, one ChaCha20 seed per proof",
-                   "timing": "wall clock over the whole batch, barrier + synchronize on both sides, max over ranks"}
-        del pkey, kzg
+        rootb = treeb.root()
+        fcb, scb = pkey.commitments()
+        batch_check = {"k": bk, "fixed_comms": fcb, "sigma_comms": scb,
+                       "samples": [(u, p, [treeb.node(0, u).hash, rootb.hash] + list(rootb.balances)) for u, p in sample]}
+        batched = {"k": bk, "distinct_users_per_rank": nb_proofs, "distinct_users_total": world * nb_proofs, "n_gpus": world, "proofs_per_s_by_workers_per_gpu": sweep,
+                   "best_proofs_per_s": max(sweep.values()), "host_cores": os.cpu_count(),
+                   "circuit": "MstInclusionCircuit<20,2,8> (LEVELS = 20) over one 2^20-user GPU-built tree; per user: GPU Merkle proof -> host witness generation -> create_proof",
+                   "timing": "wall clock over the whole batch incl. Merkle-proof gathering and witness generation, barrier + synchronize on both sides, max over ranks"}
+        treeb.close()
+        del pkey, kzg, balb
         ctx.close()
 
     # ---- rank 0: the checker (oracle as judge of the timed proofs) and, at N = 1, the bounded CPU baseline -----------------------------------
     checks, cpu_baseline = {}, None
     if rank == 0 and not args.no_checker:
         checks, cpu_baseline = checker_and_cpu_baseline(records, args, time_cpu=(world == 1 and not args.no_cpu_baseline))
+        if batched:
+            batched["sample_proofs_verified"] = check_batch_samples(batch_check)
     if world > 1:
         dist.barrier()
 
@@ -591,7 +649,7 @@ def main():
                          "traffic": traffic_db.get("msm_reduce_level1_dram_bytes_per_launch_proof_k20"), "traffic_source": traffic_db.get("source"),
                          "other_kernels": {"evaluate_h": head["evaluate_h"]["roofline"], "ntt": ntt["roofline"] if ntt else None}},
             "cpu_baseline": cpu_baseline,
-            "create_proof": records, "msm": msm, "ntt": ntt, "merkle_sum_tree": mst, "batched_inclusion_proofs": batched,
+            "create_proof": records, "msm": msm, "ntt": ntt, "merkle_sum_tree": mst, "merkle_sum_tree_2p23_x8": mst23, "batched_inclusion_proofs": batched,
         }
         print(json.dumps(line), flush=True)
     ctx0.close()

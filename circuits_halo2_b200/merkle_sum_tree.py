@@ -156,6 +156,17 @@ class MerkleSumTree:
             out.append(MerkleProof(vals[: c + 1], root, vals[c + 1: 2 * (c + 1)], mids, [int(x) for x in path[j, :d]]))
         return out
 
+    def raw_proofs(self, indices: Sequence[int]):
+        """`generate_proofs` without the python objects: (preimages (m, per, 4) uint64 Montgomery, path_indices (m, depth) uint8), the layout
+        sb_mst_proofs writes and sb_mst_inclusion_witness reads"""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        m, d, c = idx.shape[0], self._depth, self.n_currencies
+        per = 2 * (c + 1) + max(d - 1, 0) * (c + 2)
+        pre = np.zeros((m, per, 4), dtype=np.uint64)
+        path = np.zeros((m, max(d, 1)), dtype=np.uint8)
+        _lib.check(_lib.lib().sb_mst_proofs(self._h, ptr(idx), ctypes.c_size_t(m), ptr(pre), ptr(path)), "sb_mst_proofs")
+        return pre, path
+
     def index_of_username(self, username: str) -> int:
         """mst.rs:200-216: linear search, or binary search when the tree was built sorted"""
         if self._entries is None:

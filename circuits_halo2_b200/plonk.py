@@ -273,6 +273,24 @@ def create_proof_dev(pk: ProvingKey, instances: Sequence[int], d_advice: int, rn
     return _finish(st, "sb_create_proof_dev", None, out, plen)
 
 
+def mst_inclusion_witness(levels: int, n_currencies: int, k: int, preimages: np.ndarray, path_indices: np.ndarray, n_bytes: int = 8):
+    """`MstInclusionCircuit::<LEVELS, N_CURRENCIES, N_BYTES>::init(merkle_proof)` + the witness side of `synthesize`
+    (circuits/merkle_sum_tree.rs:86-103,228-520) for ONE Merkle proof in sb_mst_proofs' layout (MerkleSumTree.raw_proofs).
+    Returns (instances as python ints, advice_cells (m, 2) uint32, advice_values (m, 4) uint64): the sparse witness create_proof_sparse takes."""
+    pre = np.ascontiguousarray(preimages, dtype=np.uint64)
+    path = np.ascontiguousarray(path_indices, dtype=np.uint8)
+    n = ctypes.c_size_t()
+    inst = np.zeros((2 + n_currencies, 4), dtype=np.uint64)
+    L = _lib.lib()
+    _lib.check(L.sb_mst_inclusion_witness(ctypes.c_uint32(levels), ctypes.c_uint32(n_currencies), ctypes.c_uint32(n_bytes), ctypes.c_uint32(k), ptr(pre), ptr(path),
+                                          None, None, ctypes.c_size_t(0), ctypes.byref(n), ptr(inst)), "sb_mst_inclusion_witness")
+    cells = np.zeros((n.value, 2), dtype=np.uint32)
+    vals = np.zeros((n.value, 4), dtype=np.uint64)
+    _lib.check(L.sb_mst_inclusion_witness(ctypes.c_uint32(levels), ctypes.c_uint32(n_currencies), ctypes.c_uint32(n_bytes), ctypes.c_uint32(k), ptr(pre), ptr(path),
+                                          ptr(cells), ptr(vals), ctypes.c_size_t(n.value), ctypes.byref(n), ptr(inst)), "sb_mst_inclusion_witness")
+    return [fields.fr_from_mont(inst[i]) for i in range(inst.shape[0])], cells, vals
+
+
 class BatchProver:
     """Many independent proofs against ONE proving key (BASELINE configs[4]; the reference proves one user per
     `create_proof` call, backend/src/apis/round.rs:153-174, so a batch is many calls with a shared key).  Each worker thread
@@ -308,6 +326,24 @@ class BatchProver:
             return create_proof_sparse(self.pk, instances, cells, values, seed, transcript, ctx=c)
         finally:
             self._free.put(c)
+
+    def _one_user(self, job):
+        levels, n_cur, k, pre, path, seed, transcript = job
+        c = self._free.get()
+        try:
+            inst, cells, vals = mst_inclusion_witness(levels, n_cur, k, pre, path)
+            return create_proof_sparse(self.pk, inst, cells, vals, seed, transcript, ctx=c)
+        finally:
+            self._free.put(c)
+
+    def prove_users(self, tree, indices, seeds, transcript: int = TRANSCRIPT_KECCAK):
+        """BASELINE configs[4] / backend/src/apis/round.rs:153-174 for many users of one tree: Merkle proofs gathered on the GPU in one launch
+        (`Tree::generate_proof`), then per user, on the worker threads: witness generation (`MstInclusionCircuit::init` + synthesize) and
+        create_proof against the shared resident key.  Returns the proofs in `indices` order."""
+        pre, path = tree.raw_proofs(indices)
+        k = self.pk.params.k()
+        jobs = [(tree.depth(), tree.n_currencies, k, pre[j], path[j], seeds[j], transcript) for j in range(len(indices))]
+        return list(self._pool.map(self._one_user, jobs))
 
     def prove_many_sparse(self, jobs):
         """jobs: iterable of (instances, advice_cells, advice_values, rng_seed, transcript): the sparse-witness entry, one user per job."""

@@ -263,6 +263,14 @@ int32_t sb_mst_update_leaf_wide(sb_mst *mst, size_t index, const uint8_t *new_ba
 int32_t sb_mst_verify_proofs(sb_ctx *ctx, uint32_t n_currencies, uint32_t depth, const uint8_t *preimages, const uint8_t *path_indices, const uint8_t root_hash[32],
                              const uint8_t *root_balances, size_t n_proofs, uint8_t *out_ok);
 
+/* ---- zk_prover::circuits::merkle_sum_tree::MstInclusionCircuit: witness generation (host) ------------------------------------------------------
+ * The advice cells `Circuit::synthesize` assigns (circuits/merkle_sum_tree.rs:228-520) for one Merkle proof in the layout sb_mst_proofs writes, placed
+ * like halo2's SimpleFloorPlanner places the circuit's regions; plus the circuit's instances [leaf hash, root hash, root balances...]
+ * (merkle_sum_tree.rs:54-58).  Output is sparse: (column, row) u32 pairs + 32 B values of the NON-ZERO cells, ready for sb_create_proof_sparse.
+ * cap_cells = 0 only reports the number of cells.  Errors: the circuit does not fit 2^k rows; a balance exceeds N_BYTES bytes. */
+int32_t sb_mst_inclusion_witness(uint32_t levels, uint32_t n_currencies, uint32_t n_bytes, uint32_t k, const uint8_t *preimages, const uint8_t *path_indices,
+                                 uint32_t *out_cells, uint8_t *out_values, size_t cap_cells, size_t *out_n_cells, uint8_t *out_instances);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int32_t sb_launch_count(const sb_ctx *ctx, uint64_t *out);

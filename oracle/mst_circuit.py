@@ -338,3 +338,61 @@ def advice_columns(lay: Layouter) -> List[List[int]]:
             v[row] = val
         dense.append(v)
     return dense
+
+
+# ------------------------------------------------------------------ the constraint system itself, from the chip definitions
+def constraint_system(n_currencies: int) -> dict:
+    """`ConstraintSystem` of `MstInclusionCircuit<_, N_CURRENCIES, _>` after selector compression, in the JSON schema of
+    tests/golden/mst_inclusion_cs.json, GENERATED from the chip definitions (not parsed from the 2-currency verifier contract):
+    Pow5Chip gates of halo2_gadgets (`full round`, `partial rounds`, `pad-and-add`) for the two Poseidon configurations
+    (circuits/merkle_sum_tree.rs:163-186, chips/poseidon/hash.rs:62-72), the `bool constraint`, `swap constraint` and `sum constraint` gates of
+    chips/merkle_sum_tree.rs:38-95 -- ONE sum polynomial per currency (:78-88) --, the range check's `lookup_any` (chips/range/range_check.rs:71-84).
+    Selector compression assigns (SURVEY A.8): complex lookup selector -> fixed 5; {bool_and_swap, sum, pad_and_add(entry), pad_and_add(middle)}
+    -> one column fixed 6 with values 1..4; s_full / s_partial of the two Pow5 configs -> fixed 7..10.
+    For N_CURRENCIES = 2 it equals the system parsed from contracts/src/InclusionVerifier.sol gate by gate as polynomials (tests/test_oracle_scale.py)."""
+    hx = lambda v: hex(v % R)
+    c = lambda v: ["const", hx(v)]
+    adv = lambda col, rot=0: ["advice", col, rot]
+    fix = lambda col, rot=0: ["fixed", col, rot]
+    add = lambda a, b: ["add", a, b]
+    mul = lambda a, b: ["mul", a, b]
+    neg = lambda a: ["neg", a]
+    sub = lambda a, b: add(a, neg(b))
+
+    def pow5(x):
+        x2 = mul(x, x)
+        return mul(mul(x2, x2), x)
+    m, mi = M.MDS, M.MDS_INV
+
+    def pow5_gates(s_full, s_partial, q_pad):
+        cur = [add(adv(0), fix(0)), add(adv(1), fix(1))]          # state + round constant (rc_a)
+        full = [mul(fix(s_full), sub(add(mul(pow5(cur[0]), c(m[i][0])), mul(pow5(cur[1]), c(m[i][1]))), adv(i, 1))) for i in range(2)]
+        mid0 = adv(2)                                               # partial_sbox
+        lin = lambda i, rc: add(add(mul(mid0, c(m[i][0])), mul(cur[1], c(m[i][1]))), fix(rc))
+        nxt = lambda i: add(mul(adv(0, 1), c(mi[i][0])), mul(adv(1, 1), c(mi[i][1])))
+        partial = [mul(fix(s_partial), sub(pow5(cur[0]), mid0)),
+                   mul(fix(s_partial), sub(pow5(lin(0, 2)), nxt(0))),
+                   mul(fix(s_partial), sub(lin(1, 3), nxt(1)))]
+        pad = [mul(q_pad, sub(add(adv(0, -1), adv(0, 0)), adv(0, 1))), mul(q_pad, sub(adv(1, -1), adv(1, 1)))]
+        return full + partial + pad
+
+    def combined(v):   # q * prod_{j in 1..4, j != v} (j - q): the gate factor of the selector that got value v in the shared column
+        q = fix(6)
+        e = q
+        for j in range(1, 5):
+            if j != v:
+                e = mul(e, add(c(j), neg(q)))
+        return e
+    gates = pow5_gates(7, 8, combined(3)) + pow5_gates(9, 10, combined(4))
+    gates.append(mul(mul(combined(1), adv(2)), add(c(1), neg(adv(2)))))                                           # bool
+    gates.append(mul(combined(1), sub(add(mul(sub(adv(1), adv(0)), adv(2)), adv(0)), adv(0, 1))))                  # swap (left)
+    gates.append(mul(combined(1), sub(add(mul(sub(adv(0), adv(1)), adv(2)), adv(1)), adv(1, 1))))                  # swap (right)
+    gates += [mul(combined(2), sub(add(adv(0), adv(1)), adv(2))) for _ in range(n_currencies)]                     # one sum polynomial per currency
+    lookup = {"input": [mul(fix(5), add(adv(0), neg(mul(adv(0, 1), c(256)))))], "table": [fix(4)]}
+    return {"_source": f"generated by oracle/mst_circuit.py constraint_system({n_currencies}) from the chip definitions",
+            "num_advice_columns": 3, "num_fixed_columns": 11, "num_instance_columns": 1, "num_instances": 2 + n_currencies,
+            "advice_queries": [[0, 0], [1, 0], [0, 1], [1, 1], [2, 0], [1, -1], [0, -1]],
+            "fixed_queries": [[2, 0], [3, 0], [0, 0], [1, 0], [4, 0], [5, 0], [6, 0], [7, 0], [8, 0], [9, 0], [10, 0]],
+            "instance_queries": [[0, 0]], "gates": gates, "lookups": [lookup],
+            "permutation_columns": [["fixed", 2], ["advice", 0], ["advice", 1], ["fixed", 3], ["advice", 2], ["instance", 0]],
+            "degree": 6, "blinding_factors": 5}

@@ -252,3 +252,64 @@ def test_device_ntt_fused_scalings_on_host(ntt_harness, log_n, tile, min_passes,
     for kw in cases:
         ok, _ = _run_device_ntt_on_host(ntt_harness, log_n, tile, min_passes, full_tw, **kw)
         assert ok, (log_n, tile, sorted(kw))
+
+
+# ------------------------------------------------------------------ witness generation (csrc/witness.cpp, host C++ of the product)
+def _product_witness(proof, levels, nc, k, n_bytes=8):
+    import circuits_halo2_b200 as sb
+    pre = [proof["entry"].preimage(), proof["sibling_leaf_node_hash_preimage"]] + list(proof["sibling_middle_node_hash_preimages"])
+    flat = np.concatenate([np.frombuffer(B.fr_to_mont_bytes(v % B.R), dtype=np.uint64) for p in pre for v in p])
+    inst, cells, vals = sb.mst_inclusion_witness(levels, nc, k, flat, np.array(proof["path_indices"], dtype=np.uint8), n_bytes)
+    return inst, {(int(c), int(r)): B.fr_from_mont_bytes(v.tobytes()) for (c, r), v in zip(cells, vals)}
+
+
+def test_product_witness_equals_oracle_synthesis():
+    """sb_mst_inclusion_witness (the product's restatement of `MstInclusionCircuit::synthesize`'s witness side + SimpleFloorPlanner placement) vs
+    the oracle's synthesis (oracle/mst_circuit.py, pinned on the reference vk and MockProver region indices): every advice cell and every instance,
+    for LEVELS = 4 (csv/entry_16.csv, several users), 3 currencies with ragged padding, and the LEVELS = 20 / LEVELS = 23 x 8-currency fixtures."""
+    from oracle import mst as M
+    from oracle import mst_circuit as C
+    golden = os.path.join(ROOT, "tests", "golden")
+    tree = M.MerkleSumTree.from_csv(os.path.join(golden, "entry_16.csv"))
+    for user in (0, 5, 15):
+        pr = tree.generate_proof(user)
+        lay = C.synthesize(11, pr, 4, 2, 8)
+        want = {(col, row): v for col, dense in enumerate(C.advice_columns(lay)) for row, v in enumerate(dense) if v}
+        inst, got = _product_witness(pr, 4, 2, 11)
+        assert got == want and inst == [tree.nodes[0][user][0], tree.root[0]] + tree.root[1]
+    t3 = M.MerkleSumTree([M.Entry(f"u{i}", [i * 1000 + 7, 5 * i, (1 << 60) + i]) for i in range(5)])
+    pr = t3.generate_proof(3)
+    lay = C.synthesize(12, pr, 3, 3, 8)
+    inst, got = _product_witness(pr, 3, 3, 12)
+    assert got == {(col, row): v for col, dense in enumerate(C.advice_columns(lay)) for row, v in enumerate(dense) if v}
+    assert inst == [t3.nodes[0][3][0], t3.root[0]] + t3.root[1]
+    um = lambda x: B.fr_from_mont_bytes(np.ascontiguousarray(x).tobytes())
+
+    class _E:
+        def __init__(self, p):
+            self.p = p
+
+        def preimage(self):
+            return self.p
+    for name, levels, nc, k in (("mst_inclusion_assignment_l20_tree.npz", 20, 2, 13), ("mst_inclusion_assignment_l23_n8_tree.npz", 23, 8, 15)):
+        fx = np.load(os.path.join(golden, name))
+        idx, seed = int(fx["user_index"][0]), int(fx["balance_seed"][0])
+        bal = np.random.default_rng(seed).integers(0, 1 << 40, size=(1 << levels, nc), dtype=np.uint64)[idx]
+        entry = M.Entry("user_%d" % idx, [int(x) for x in bal])
+        pr = {"entry": _E(entry.preimage()), "sibling_leaf_node_hash_preimage": [um(v) for v in fx["sibling_leaf_preimage"]],
+              "sibling_middle_node_hash_preimages": [[um(v) for v in pre] for pre in fx["sibling_middle_preimages"]], "path_indices": [int(b) for b in fx["path_indices"]]}
+        inst, got = _product_witness(pr, levels, nc, k)
+        assert got == {(int(c), int(r)): um(v) for (c, r), v in zip(fx["advice_cells"], fx["advice_values"])}
+        assert inst == [um(v) for v in fx["instances"]]
+
+
+def test_product_witness_rejects_what_the_circuit_cannot_satisfy():
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200._lib import SummaB200Error
+    from oracle import mst as M
+    t = M.MerkleSumTree([M.Entry(f"u{i}", [(1 << 63) + i, 1]) for i in range(4)])   # sums leave the 8-byte range at level 1
+    with pytest.raises(SummaB200Error):
+        _product_witness(t.generate_proof(0), 2, 2, 11)
+    ok = M.MerkleSumTree.from_csv(os.path.join(ROOT, "tests", "golden", "entry_16.csv"))
+    with pytest.raises(SummaB200Error):
+        _product_witness(ok.generate_proof(0), 4, 2, 10)   # LEVELS = 4 needs k = 11 (circuits/tests.rs:23): NotEnoughRowsAvailable

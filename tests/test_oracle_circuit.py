@@ -126,3 +126,43 @@ def test_blake2b_transcript_proof_shape(setup):
     tr = Blake2bTranscript()
     HP.create_proof(setup["params"], setup["pk"], setup["instances"], setup["advice"], ChaCha20Rng.seed_from_u64(1), tr)
     assert len(tr.finalize()) == 16 * 32 + 35 * 32
+
+
+@needs_reference
+def test_generic_verifier_agrees_with_the_reference_contract(setup, golden_dir):
+    """oracle/halo2_verifier.py (any constraint system) vs the reference's verifier contract (2-currency circuit) on the REAL SRS / vk at k = 11,
+    pairing path with [s]_2 from the contract's constants: the checked-in golden calldata proof, a fresh oracle proof, tampered proofs, wrong
+    instances -- same verdict every time.  And a Blake2b-transcript proof (`full_prover`, utils.rs:93), which no contract can judge, verifies too."""
+    from oracle import halo2_verifier as V
+    from oracle.yul import SolidityVerifier
+    v = SolidityVerifier.from_file(SOL)
+    vc = json.load(open(os.path.join(golden_dir, "verifier_constants.json")))
+    g = lambda name: int(vc[name], 16)
+    s_g2 = ((g("neg_s_g2_x_2"), g("neg_s_g2_x_1")), ((-g("neg_s_g2_y_2")) % B.Q, (-g("neg_s_g2_y_1")) % B.Q))   # the contract stores -[s]_2, imaginary part first
+    fixed = [(g(f"fixed_comms[{i}].x"), g(f"fixed_comms[{i}].y")) for i in range(11)]
+    sigma = [(g(f"permutation_comms[{i}].x"), g(f"permutation_comms[{i}].y")) for i in range(6)]
+    cs = setup["cs"]
+    check = lambda proof, inst: V.verify_proof(cs, 11, fixed, sigma, g("vk_digest"), inst, proof, keccak=True, s_g2=s_g2)
+    cd = json.load(open(os.path.join(golden_dir, "inclusion_proof_solidity_calldata.json")))
+    gproof, ginst = bytes.fromhex(cd["proof"][2:]), [int(x, 16) for x in cd["public_inputs"]]
+    tr = KeccakTranscript()
+    HP.create_proof(setup["params"], setup["pk"], setup["instances"], setup["advice"], ChaCha20Rng.seed_from_u64(7), tr)
+    fresh = tr.finalize()
+    cases = [(gproof, ginst), (fresh, setup["instances"]), (fresh, ginst)]
+    for off in (0x10, 0x150, 0x250, 0x390, 0x700, 0x7f0, 0x830):
+        bad = bytearray(fresh)
+        bad[off] ^= 1
+        cases.append((bytes(bad), setup["instances"]))
+    cases.append((fresh[:-1], setup["instances"]))
+    verdicts = [(check(p, i), v.verify(p, i) if len(p) == 2144 else False) for p, i in cases]
+    assert all(a == b for a, b in verdicts), verdicts
+    assert verdicts[0] == (True, True) and verdicts[1] == (True, True) and not any(a for a, _ in verdicts[2:])
+    # the Blake2b transcript (compressed points, little-endian scalars)
+    trb = Blake2bTranscript()
+    HP.create_proof(setup["params"], setup["pk"], setup["instances"], setup["advice"], ChaCha20Rng.seed_from_u64(3), trb)
+    bproof = trb.finalize()
+    okb = lambda p, inst: V.verify_proof(cs, 11, fixed, sigma, setup["pk"].transcript_repr, inst, p, keccak=False, s_g2=s_g2)
+    assert okb(bproof, setup["instances"])
+    bad = bytearray(bproof)
+    bad[600] ^= 1
+    assert not okb(bytes(bad), setup["instances"])

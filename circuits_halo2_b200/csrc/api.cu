@@ -399,7 +399,9 @@ int32_t srs_precompute_impl(sb_ctx *ctx, sb_srs *srs, int32_t basis_mask, uint32
     if (srs->k < 11) return SB_OK;  // tiny SRS: plain Pippenger is launch-bound either way
     uint32_t c = window_bits;
     if (c == 0) {
-        c = srs->k <= 20 ? srs->k : (srs->k >= 23 ? 22 : 20);
+        // window bits: fewer windows (level-1 additions) against more buckets (2 general additions each in the bucket reduction); measured on the k = 20
+        // proof (profiles/r02e_window_sweep.txt): c = 17 -> 70.0 ms, 18 -> 71.4, 19 -> 71.2, 20 -> 72.1
+        c = srs->k <= 19 ? srs->k : (srs->k == 20 ? 17 : (srs->k >= 23 ? 22 : 20));
         if (ctx->tune.tab_c > 0) c = (uint32_t)ctx->tune.tab_c;
     }
     std::lock_guard<std::mutex> tab_lock(srs->tab_mu);

@@ -198,7 +198,8 @@ def test_configs4_flow_tree_to_witness_to_proof_for_distinct_users(ctx, golden_d
     for u, p in zip(users, proofs):
         inst = [tree.node(0, u).hash, root.hash] + list(root.balances)
         assert v.verify(p, inst), f"user {u}: the reference verifier rejects the proof"
-        assert not v.verify(p, [tree.node(0, (u + 1) % 256).hash, root.hash] + list(root.balances)), "a proof must not verify for another user's leaf"
+        other = 3 if u != 3 else 4   # a real user with a different leaf (the zero-padding entries all share one leaf hash)
+        assert not v.verify(p, [tree.node(0, other).hash, root.hash] + list(root.balances)), "a proof must not verify for another user's leaf"
     # byte equality with the oracle prover for one user (oracle synthesis of that user's circuit)
     u = 77
     layu = C.synthesize(k, otree.generate_proof(u), levels, 2, 8)

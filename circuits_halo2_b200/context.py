@@ -41,6 +41,10 @@ class Context:
     def synchronize(self) -> None:
         _lib.check(_lib.lib().sb_ctx_synchronize(self.handle), "sb_ctx_synchronize")
 
+    def set_blocking_sync(self, on: bool = True) -> None:
+        """throughput mode: host waits sleep instead of spinning (use when many worker contexts share the host's cores)"""
+        _lib.check(_lib.lib().sb_ctx_set_blocking_sync(self.handle, ctypes.c_int32(1 if on else 0)), "sb_ctx_set_blocking_sync")
+
     def stream(self) -> int:
         """the context's cudaStream_t (for CUDA-event timing by the caller)"""
         out = ctypes.c_void_p()

@@ -69,6 +69,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.msm_seg = geti("SB_MSM_SEG", -1);
     t.msm_seg1 = geti("SB_MSM_SEG1", 2);
     t.msm_finish_at = geti("SB_MSM_FINISH_AT", 16384);
+    ctx->blocking_sync = getb("SB_BLOCKING_SYNC");
     t.ntt_tile = geti("SB_NTT_TILE", 0);
     t.ntt_passes = geti("SB_NTT_PASSES", 0);
     t.ntt_tw_mb = geti("SB_NTT_TW_MB", 1024);
@@ -80,6 +81,16 @@ void ctx_read_env(sb_ctx *ctx) {
     t.no_hprog_cache = getb("SB_NO_HPROG_CACHE");
     t.no_tables = getb("SB_NO_TABLES");
     t.no_smallkey_sort = getb("SB_NO_SMALLKEY_SORT");
+}
+cudaError_t sync_stream(sb_ctx *ctx, cudaStream_t st) {
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(st);
+    if (!ctx->block_ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->block_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->block_ev, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->block_ev);
 }
 void ctx_retain(sb_ctx *ctx) { ctx->refs.fetch_add(1, std::memory_order_relaxed); }
 void ctx_release(sb_ctx *ctx) {
@@ -98,6 +109,7 @@ void ctx_release(sb_ctx *ctx) {
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     for (int e = 0; e < 5; e++)
         if (ctx->msm_ev[e]) cudaEventDestroy(ctx->msm_ev[e]);
+    if (ctx->block_ev) cudaEventDestroy(ctx->block_ev);
     for (int i = 0; i < 2; i++) {
         if (ctx->side_ev[i]) cudaEventDestroy(ctx->side_ev[i]);
         if (ctx->h_ev[i]) cudaEventDestroy(ctx->h_ev[i]);
@@ -244,6 +256,12 @@ int32_t sb_ctx_synchronize(sb_ctx *ctx) {
     return SB_OK;
 }
 
+int32_t sb_ctx_set_blocking_sync(sb_ctx *ctx, int32_t on) {
+    if (!ctx) return SB_ERR_ARG;
+    Guard g(ctx);
+    ctx->blocking_sync = on != 0;
+    return SB_OK;
+}
 int32_t sb_ctx_stream(const sb_ctx *ctx, void **out_stream) {
     if (!ctx || !out_stream) return SB_ERR_ARG;
     *out_stream = (void *)ctx->stream;

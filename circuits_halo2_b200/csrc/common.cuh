@@ -85,6 +85,10 @@ struct sb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t side_stream = nullptr;  // create_proof: coset NTTs that no challenge is waiting for run here, under the MSM tails
     cudaEvent_t side_ev[2] = {nullptr, nullptr};
+    // throughput mode (sb_ctx_set_blocking_sync): host waits sleep on a blocking event instead of spinning in cudaStreamSynchronize, so that many
+    // worker contexts (BatchProver: several per GPU, one process per GPU) do not burn the host cores their own transcript / witness work needs
+    bool blocking_sync = false;
+    cudaEvent_t block_ev = nullptr;
     std::mutex mu;
     uint64_t launches = 0;
     std::map<std::string, sb::Scratch> scratch;
@@ -122,6 +126,7 @@ namespace sb {
 
 int32_t scratch_get(sb_ctx *ctx, const char *slot, size_t bytes, void **out);
 void ctx_read_env(sb_ctx *ctx);
+cudaError_t sync_stream(sb_ctx *ctx, cudaStream_t st);  // cudaStreamSynchronize, or a sleeping wait in throughput mode
 void ctx_retain(sb_ctx *ctx);
 void ctx_release(sb_ctx *ctx);  // frees the context when the last reference goes
 

@@ -640,7 +640,7 @@ int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c,
         if (e != cudaSuccess) { set_last_error("msm tables: cudaMalloc(%zu): %s", (size_t)W * n * 64, cudaGetErrorString(e)); return SB_ERR_ALLOC; }
     }
     SB_LAUNCH(ctx, msm_table_build_kernel, (unsigned)((n + 127) / 128), 128, 0, st, (const uint4 *)d_bases, (uint64_t)n, (uint64_t)n, c, W, (uint4 *)d_tab);
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     out->d_tables = d_tab;
     out->c = c;
     out->W = W;
@@ -791,7 +791,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     // the number of non-zero signed digits that were sorted and accumulated (the scan's grand total): the level-1 additions actually performed
     uint32_t *h_total = (uint32_t *)((uint8_t *)ctx->pinned + ctx->pinned_bytes - 64);
     SB_CUDA_TRY(cudaMemcpyAsync(h_total, d_counts + nb, 4, cudaMemcpyDeviceToHost, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     for (int e = 0; e < 4; e++) cudaEventElapsedTime(&ctx->msm_phase_ms[e], ctx->msm_ev[e], ctx->msm_ev[e + 1]);
     cudaEventElapsedTime(&ctx->msm_phase_ms[4], ctx->msm_ev[0], ctx->msm_ev[4]);
     for (int e = 0; e < 5; e++) ctx->acc_msm_ms[e] += ctx->msm_phase_ms[e];   // running totals since sb_perf_reset (one proof = several launch sets)

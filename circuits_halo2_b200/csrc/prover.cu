@@ -414,7 +414,7 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
             SB_CUDA_TRY(cudaMemcpyAsync(d_cells, sparse->perm_cells, sparse->n_perm * 16, cudaMemcpyHostToDevice, st));
             SB_TRY(sigma_patch(ctx, pk->sigma_values.data(), (uint32_t)pk->P, d_cells, sparse->n_perm, pk->omega_pows, delta_pows.data(), st));
         }
-        SB_CUDA_TRY(cudaStreamSynchronize(st));  // the caller's (pageable) cell arrays are free again
+        SB_CUDA_TRY(sync_stream(ctx, st));  // the caller's (pageable) cell arrays are free again
     }
     auto derive_forms = [&](int count, std::vector<void *> &vals, std::vector<void *> &polys, std::vector<void *> &cosets, std::vector<uint8_t> &comms) -> int32_t {
         comms.resize((size_t)count * 64);
@@ -438,7 +438,7 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
         std::fill(tmp.begin(), tmp.end(), fr_t::zero());
         for (size_t r : rows) tmp[r] = fr_t::one();
         SB_CUDA_TRY(cudaMemcpyAsync(d_tmp, tmp.data(), n * 32, cudaMemcpyHostToDevice, st));
-        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        SB_CUDA_TRY(sync_stream(ctx, st));
         SB_TRY(dom_l2c(ctx, d, d_tmp, st));
         return to_cosets(d_tmp, d_cm);
     };
@@ -473,7 +473,7 @@ int32_t pk_build(sb_ctx *ctx, sb_pk *pk, const uint8_t *fixed_values, const uint
     SB_TRY(fr_scale(ctx, pk->div_x, n, to_dev(DIV_G), st));
     SB_TRY(fr_gen_powers(ctx, pk->div_ginv_scaled, to_dev(hfr::inv(DIV_G)), n, st));
     SB_TRY(fr_scale(ctx, pk->div_ginv_scaled, n, d->ifft_divisor, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     return SB_OK;
 }
 
@@ -891,7 +891,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     int stage = 0;
     auto t_prev = std::chrono::steady_clock::now();
     auto mark = [&]() {
-        cudaStreamSynchronize(st);
+        sync_stream(ctx, st);
         auto now = std::chrono::steady_clock::now();
         if (stage < 12) ctx->last_proof_stage_ms[stage++] = std::chrono::duration<float, std::milli>(now - t_prev).count();
         t_prev = now;
@@ -991,7 +991,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             // every rank holds the same host witness: upload 1 / world of it over PCIe and gather the rest over NVLink
             const size_t per = adv_bytes / (size_t)comm->world, off = per * (size_t)comm->rank;
             SB_CUDA_TRY(cudaMemcpyAsync(base_v + off, wit.host + off, per, cudaMemcpyHostToDevice, st));
-            SB_CUDA_TRY(cudaStreamSynchronize(st));
+            SB_CUDA_TRY(sync_stream(ctx, st));
             if (comm->allgather_dev(comm->user, base_v, per, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
         } else {
             SB_CUDA_TRY(cudaMemcpyAsync(base_v, wit.host, adv_bytes, cudaMemcpyHostToDevice, st));
@@ -1158,7 +1158,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         std::vector<Fr> local_last(n_sets);
         for (int s = 0; s + 1 < n_sets; s++)
             SB_CUDA_TRY(cudaMemcpyAsync(&local_last[s], d_zall + ((size_t)s * n + (n - (size_t)bf - 1)) * 32, 32, cudaMemcpyDeviceToHost, st));
-        if (n_sets > 1) SB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (n_sets > 1) SB_CUDA_TRY(sync_stream(ctx, st));
         Fr carry = hfr::ONE;
         for (int s = 1; s < n_sets; s++) {
             carry = hfr::mul(carry, local_last[s - 1]);
@@ -1271,7 +1271,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, hcm_slot(own[jl]), st));
         }
         SB_CUDA_TRY(cudaEventRecord(e1, st));
-        SB_CUDA_TRY(cudaEventSynchronize(e1));
+        SB_CUDA_TRY(sync_stream(ctx, st));
         cudaEventElapsedTime(&ctx->last_h_ms, e0, e1);
     }
     mark();  // [6] evaluate_h (fused program, one launch per owned coset)
@@ -1287,7 +1287,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(ntt_run_fused(ctx, hcm_slot(rank), hcm_slot(rank), (const uint8_t *)d->omega_inv.v, pk->k, &f, st));
     }
     if (world > 1) {
-        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        SB_CUDA_TRY(sync_stream(ctx, st));
         if (comm->allgather_dev(comm->user, d_hcm, (size_t)per * n * 32, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
     }
     {
@@ -1684,7 +1684,7 @@ int32_t sb_kate_division(sb_ctx *ctx, const uint8_t *a, uint32_t log_n, const ui
     sb_domain_destroy(dom);
     if (rc != SB_OK) return rc;
     SB_CUDA_TRY(cudaMemcpyAsync(q, dp, n * 32, cudaMemcpyDeviceToHost, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     return SB_OK;
 }
 
@@ -1798,7 +1798,7 @@ int32_t sb_grand_product(sb_ctx *ctx, const uint8_t *numerators, const uint8_t *
     memcpy(i0.v, init, 32);
     SB_TRY(fr_running_product(ctx, dd, n, i0, dz, n_z, st));
     SB_CUDA_TRY(cudaMemcpyAsync(z, dz, n_z * 32, cudaMemcpyDeviceToHost, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     return SB_OK;
 }
 

@@ -265,7 +265,7 @@ int32_t fr_eval_polys(sb_ctx *ctx, const std::vector<const void *> &polys, const
     SB_LAUNCH(ctx, eval_poly_partial, dim3(bpj, (unsigned)m), EV_THREADS, 0, st, (const EvalJob *)d_jobs, (uint64_t)n, (uint4 *)d_part, bpj);
     SB_LAUNCH(ctx, eval_poly_finish, (unsigned)m, 1, 0, st, (const uint4 *)d_part, bpj, (uint4 *)d_out);
     SB_CUDA_TRY(cudaMemcpyAsync(out.data(), d_out, m * 32, cudaMemcpyDeviceToHost, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     return SB_OK;
 }
 
@@ -396,7 +396,7 @@ int32_t sort_u256(sb_ctx *ctx, void *d_a, size_t count, size_t capacity_pow2, cu
         SB_LAUNCH(ctx, smallkey_hist_kernel, (unsigned)((count + 255) / 256), 256, 0, st, (const uint4 *)d_a, (uint64_t)count, d_hist, d_hist + SMALLKEY_BINS + 1);
         uint32_t too_big = 1;
         SB_CUDA_TRY(cudaMemcpyAsync(&too_big, d_hist + SMALLKEY_BINS + 1, 4, cudaMemcpyDeviceToHost, st));
-        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        SB_CUDA_TRY(sync_stream(ctx, st));
         if (!too_big) {
             SB_LAUNCH(ctx, smallkey_scan_kernel, 1, 1024, 0, st, d_hist);
             SB_LAUNCH(ctx, smallkey_expand_kernel, (unsigned)((count + 255) / 256), 256, 0, st, (const uint32_t *)d_hist, (uint4 *)d_a, (uint64_t)count);
@@ -490,7 +490,7 @@ int32_t lookup_permute(sb_ctx *ctx, const void *d_in, const void *d_tab, size_t 
     SB_TRY(scan_u32(ctx, left, left_pos, u, totals + 1, st));
     uint32_t h_tot[2];
     SB_CUDA_TRY(cudaMemcpyAsync(h_tot, totals, 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    SB_CUDA_TRY(sync_stream(ctx, st));
     if (h_tot[0] != h_tot[1]) {
         set_last_error("lookup: an input value is not contained in the table (repeated rows %u, leftover table values %u)", h_tot[0], h_tot[1]);
         return SB_ERR_ARG;

@@ -297,11 +297,13 @@ class BatchProver:
     owns a context (stream + scratch) on the key's GPU; the key and the SRS stay resident and are shared read-only, so the
     small kernels of different proofs overlap on the device and the host-side transcript work runs on several cores."""
 
-    def __init__(self, pk: ProvingKey, workers: int = 4):
+    def __init__(self, pk: ProvingKey, workers: int = 4, blocking_sync: bool = True):
         from concurrent.futures import ThreadPoolExecutor
         import queue
         self.pk = pk
         self.contexts = [Context(pk.ctx.device) for _ in range(workers)]
+        for c in self.contexts:
+            c.set_blocking_sync(blocking_sync)   # workers sleep while their GPU work runs: the host cores go to transcripts and witness generation
         self._free = queue.SimpleQueue()
         for c in self.contexts:
             self._free.put(c)

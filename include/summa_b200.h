@@ -48,6 +48,8 @@ int32_t sb_device_count(int32_t *out_count);
 int32_t sb_ctx_create(int32_t device, sb_ctx **out_ctx);
 int32_t sb_ctx_destroy(sb_ctx *ctx);
 int32_t sb_ctx_synchronize(sb_ctx *ctx);
+/* throughput mode: host waits of this context sleep on a blocking event instead of spinning (many worker contexts per host: BatchProver) */
+int32_t sb_ctx_set_blocking_sync(sb_ctx *ctx, int32_t on);
 /* the context's own CUDA stream (a cudaStream_t): callers that time with CUDA events record them here */
 int32_t sb_ctx_stream(const sb_ctx *ctx, void **out_stream);
 /* device memory helpers for callers without a CUDA runtime of their own (Rust FFI crate) */

@@ -587,7 +587,8 @@ def main():
         sweep = {}
         sample = None
         for workers in [int(x) for x in args.batch_workers.split(",") if x]:
-            bp = sb.BatchProver(pkey, workers)
+            # worker threads sleep in their waits when the ranks' workers would otherwise spin on more than half of the host's cores
+            bp = sb.BatchProver(pkey, workers, blocking_sync=(world * workers > (os.cpu_count() or 1) // 2))
             bp.prove_users(treeb, users[: 2 * workers], seeds[: 2 * workers])  # warm-up: scratch arenas and NTT plans of every context
             barrier()
             t0 = time.perf_counter()

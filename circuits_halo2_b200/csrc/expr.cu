@@ -396,21 +396,11 @@ struct ExprArgs {
     uint32_t log_n, rot_scale_log;
     uint4 *out;
     uint32_t out_slot;  // (n_slots << 16) | output slot
-    uint32_t n_cols, n_inputs;
-};
-
-static const uint32_t EXPR_MAX_INPUTS = 192;
-// operand tables of the launch staged in shared memory: an input operand is then ONE shared-memory read (pointer, stride, rotation packed per
-// input) ahead of its column load instead of four dependent global loads
-struct ExprInputRef {
-    const uint4 *base;
-    int32_t rot;
-    uint32_t shift;
 };
 
 static const int EXPR_THREADS = 128;
 
-__device__ __forceinline__ fr_t expr_fetch(uint32_t opnd, const ExprArgs &A, const uint4 *s_lo, const uint4 *s_hi, const ExprInputRef *s_in, uint32_t tid, uint64_t row) {
+__device__ __forceinline__ fr_t expr_fetch(uint32_t opnd, const ExprArgs &A, const uint4 *s_lo, const uint4 *s_hi, uint32_t tid, uint64_t row) {
     const uint32_t kind = opnd >> 30, idx = opnd & 0x3fffffffu;
     fr_t r;
     if (kind == K_REG) {
@@ -419,17 +409,11 @@ __device__ __forceinline__ fr_t expr_fetch(uint32_t opnd, const ExprArgs &A, con
     } else if (kind == K_CONST) {
         r = ldg_fp<FrParams>(A.consts + 2 * idx);
     } else {
+        const int32_t col = __ldg(A.inputs + 2 * idx), rot = __ldg(A.inputs + 2 * idx + 1);
         const uint64_t mask = (1ull << A.log_n) - 1;
-        if (s_in) {
-            const ExprInputRef in = s_in[idx];
-            const uint64_t j = (row + (uint64_t)((int64_t)in.rot * (int64_t)(1ll << A.rot_scale_log))) & mask;
-            r = ldg_fp<FrParams>(in.base + 2 * (j << in.shift));
-        } else {
-            const int32_t col = __ldg(A.inputs + 2 * idx), rot = __ldg(A.inputs + 2 * idx + 1);
-            const uint64_t j = (row + (uint64_t)((int64_t)rot * (int64_t)(1ll << A.rot_scale_log))) & mask;
-            const uint4 *base = A.cols[col];
-            r = ldg_fp<FrParams>(base + 2 * (j << __ldg(A.col_shift + col)));
-        }
+        const uint64_t j = (row + (uint64_t)((int64_t)rot * (int64_t)(1ll << A.rot_scale_log))) & mask;
+        const uint4 *base = A.cols[col];
+        r = ldg_fp<FrParams>(base + 2 * (j << __ldg(A.col_shift + col)));
     }
     return r;
 }
@@ -442,30 +426,17 @@ __global__ void __launch_bounds__(EXPR_THREADS) expr_eval_kernel(const ExprArgs 
     const uint32_t n_slots = A.out_slot >> 16;
     uint4 *lo = smem, *hi = smem + (size_t)n_slots * EXPR_THREADS;
     const uint32_t out_slot = A.out_slot & 0xffffu;
-    // resolved input references (column pointer, stride, rotation) in shared memory, behind the value slots
-    const ExprInputRef *s_in = nullptr;
-    if (A.n_inputs <= EXPR_MAX_INPUTS) {
-        ExprInputRef *w = reinterpret_cast<ExprInputRef *>(smem + 2 * (size_t)n_slots * EXPR_THREADS);
-        for (uint32_t i = tid; i < A.n_inputs; i += EXPR_THREADS) {
-            const int32_t col = __ldg(A.inputs + 2 * i);
-            w[i].base = A.cols[col];
-            w[i].rot = __ldg(A.inputs + 2 * i + 1);
-            w[i].shift = __ldg(A.col_shift + col);
-        }
-        __syncthreads();
-        s_in = w;
-    }
     for (uint32_t pc = 0; pc < A.n_instr; pc++) {
         const uint32_t w0 = __ldg(A.code + 3 * pc), wa = __ldg(A.code + 3 * pc + 1), wb = __ldg(A.code + 3 * pc + 2);
         const uint32_t op = w0 >> 16, dst = w0 & 0xffffu;
-        fr_t a = expr_fetch(wa, A, lo, hi, s_in, tid, row);
+        fr_t a = expr_fetch(wa, A, lo, hi, tid, row);
         fr_t r;
         if (op == OP_MUL) {
-            r = mul(a, expr_fetch(wb, A, lo, hi, s_in, tid, row));
+            r = mul(a, expr_fetch(wb, A, lo, hi, tid, row));
         } else if (op == OP_ADD) {
-            r = add(a, expr_fetch(wb, A, lo, hi, s_in, tid, row));
+            r = add(a, expr_fetch(wb, A, lo, hi, tid, row));
         } else if (op == OP_SUB) {
-            r = sub(a, expr_fetch(wb, A, lo, hi, s_in, tid, row));
+            r = sub(a, expr_fetch(wb, A, lo, hi, tid, row));
         } else if (op == OP_NEG) {
             r = neg(a);
         } else {
@@ -514,11 +485,9 @@ int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void
     A.rot_scale_log = rot_scale_log;
     A.out = (uint4 *)d_out;
     A.out_slot = (prog.n_slots << 16) | prog.out_slot;
-    A.n_cols = (uint32_t)cols.size();
-    A.n_inputs = (uint32_t)(prog.inputs.size() / 2);
-    const size_t smem = (size_t)prog.n_slots * EXPR_THREADS * 32 + (A.n_inputs <= EXPR_MAX_INPUTS ? (size_t)A.n_inputs * sizeof(ExprInputRef) : 0);
+    const size_t smem = (size_t)prog.n_slots * EXPR_THREADS * 32;
     // per device and idempotent: safe to repeat from concurrent contexts
-    SB_CUDA_TRY(cudaFuncSetAttribute(expr_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EXPR_THREADS * 32 + (int)(EXPR_MAX_INPUTS * sizeof(ExprInputRef))));
+    SB_CUDA_TRY(cudaFuncSetAttribute(expr_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EXPR_THREADS * 32));
     SB_LAUNCH(ctx, expr_eval_kernel, (unsigned)(n / EXPR_THREADS), EXPR_THREADS, smem, st, A);
     return SB_OK;
 }

@@ -297,7 +297,7 @@ class BatchProver:
     owns a context (stream + scratch) on the key's GPU; the key and the SRS stay resident and are shared read-only, so the
     small kernels of different proofs overlap on the device and the host-side transcript work runs on several cores."""
 
-    def __init__(self, pk: ProvingKey, workers: int = 4, blocking_sync: bool = True):
+    def __init__(self, pk: ProvingKey, workers: int = 4, blocking_sync: bool = False):
         from concurrent.futures import ThreadPoolExecutor
         import queue
         self.pk = pk

@@ -79,6 +79,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.no_side_stream = getb("SB_NO_SIDE_STREAM");
     t.no_early_random = getb("SB_NO_EARLY_RANDOM");
     t.no_hprog_cache = getb("SB_NO_HPROG_CACHE");
+    t.no_jit = getb("SB_NO_JIT");
     t.no_tables = getb("SB_NO_TABLES");
     t.no_smallkey_sort = getb("SB_NO_SMALLKEY_SORT");
 }

@@ -68,6 +68,7 @@ struct Tuning {
     bool no_side_stream = false;     // SB_NO_SIDE_STREAM
     bool no_early_random = false;    // SB_NO_EARLY_RANDOM
     bool no_hprog_cache = false;     // SB_NO_HPROG_CACHE
+    bool no_jit = false;             // SB_NO_JIT: evaluate_h through the interpreter instead of the NVRTC-specialised kernel
     bool no_tables = false;          // SB_NO_TABLES
     bool no_smallkey_sort = false;   // SB_NO_SMALLKEY_SORT
 };
@@ -117,6 +118,7 @@ struct sb_ctx {
     // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
     cudaEvent_t h_ev[2] = {nullptr, nullptr};
     float last_h_ms = 0;
+    bool last_h_jit = false;   // the last evaluate_h ran the NVRTC-specialised kernel (false: the interpreter)
     uint64_t last_h_rows = 0;  // rows the fused program was evaluated on (owned cosets x n)
     uint32_t last_h_program[4] = {0, 0, 0, 0};
     float last_proof_stage_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // prover.cu `mark()` stages

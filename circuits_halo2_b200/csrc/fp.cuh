@@ -10,7 +10,9 @@
 // between products.  The carry primitives below have a bit-exact host emulation so the very same
 // source is unit-tested on the CPU (tests/test_host_field.py) before it ever reaches a GPU.
 #pragma once
+#ifndef __CUDACC_RTC__  // the NVRTC-compiled evaluate_h kernels (expr_jit.cu) embed this header and bring their own typedefs
 #include <stdint.h>
+#endif
 
 #ifdef __CUDACC__
 #define SB_HD __host__ __device__ __forceinline__

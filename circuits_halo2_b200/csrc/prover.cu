@@ -284,6 +284,10 @@ struct sb_pk {
         Program prog;
         std::vector<uint32_t> theta, beta, gamma;               // constant slots holding theta / beta / gamma
         std::vector<std::pair<uint32_t, int>> delta_beta, ypow;  // (slot, j): delta^j * beta ; (slot, e): y^e
+        // the program as straight-line sm_100a code (NVRTC, compiled on first use); nullptr + jit_tried: not available, the interpreter runs
+        ExprJit *jit = nullptr;
+        bool jit_tried = false;
+        std::string jit_why;
     };
     mutable HProgramCache hcache;
     // g_s^m and g_s^-m (m < n) for coset slot s, coset-major slabs [n_cos][n]: coefficient scaling before the forward / after the inverse size-n NTT
@@ -1260,6 +1264,28 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             dyn_col.push_back(E_LK + 3 * (int)li + 1);
             dyn_col.push_back(E_LK + 3 * (int)li + 2);
         }
+        // the key's program as compiled straight-line code when NVRTC is there (same DAG, same schedule: same values); only its constants are per proof
+        const ExprJit *jit = nullptr;
+        void *d_jit_consts = nullptr;
+        if (!ctx->tune.no_jit && !ctx->tune.no_hprog_cache) {
+            sb_pk::HProgramCache &hc = pk->hcache;
+            std::lock_guard<std::mutex> lk(hc.mu);
+            if (!hc.jit_tried) {
+                hc.jit_tried = true;
+                hc.jit = expr_jit_compile(hc.prog, &hc.jit_why);
+            }
+            jit = hc.jit;
+        }
+        ctx->last_h_jit = jit != nullptr;
+        if (jit) {
+            static thread_local uint32_t ring = 0;
+            uint8_t *slab;
+            const size_t slice = 16 << 10;
+            SB_REQUIRE(hp.consts.size() * 32 <= slice, "evaluate_h: constant table too large");
+            SB_TRY(scratch_get(ctx, "hjit_consts", 4 * slice, (void **)&slab));
+            d_jit_consts = slab + (size_t)(ring++ % 4) * slice;
+            SB_TRY(h2d_staged(ctx, d_jit_consts, hp.consts.data(), hp.consts.size() * 32, st));
+        }
         std::vector<const void *> ccols(n_ecols, nullptr);
         for (uint32_t jl = 0; jl < co_per; jl++) {
             const size_t off = (size_t)own[jl] * n * 32;
@@ -1268,7 +1294,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             ccols[E_L0] = (const uint8_t *)pk->l0 + off; ccols[E_LLAST] = (const uint8_t *)pk->l_last + off;
             ccols[E_LACT] = (const uint8_t *)pk->l_active + off; ccols[E_X] = (const uint8_t *)pk->x_coset + off;
             for (size_t q = 0; q < dyn_col.size(); q++) ccols[dyn_col[q]] = dyn_slot(jl, q);
-            SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, hcm_slot(own[jl]), st));
+            if (jit) SB_TRY(expr_jit_run(ctx, jit, d_jit_consts, ccols, pk->k, 0, hcm_slot(own[jl]), st));
+            else SB_TRY(expr_eval(ctx, hp, ccols, pk->k, 0, hcm_slot(own[jl]), st));
         }
         SB_CUDA_TRY(cudaEventRecord(e1, st));
         SB_CUDA_TRY(sync_stream(ctx, st));
@@ -1391,6 +1418,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
 extern "C" {
 
 static void pk_free(sb_pk *pk) {
+    expr_jit_free(pk->hcache.jit);
     for (void *p : pk->owned) cudaFree(p);
     if (pk->dom) sb_domain_destroy(pk->dom);
     if (pk->srs) sb_srs_destroy(const_cast<sb_srs *>(pk->srs));  // drops the key's reference
@@ -1965,6 +1993,27 @@ int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_progra
     return SB_OK;
 }
 
+// CPU-side check of the evaluate_h code generator: the CUDA source the JIT would compile for this constraint system
+int32_t sb_test_h_jit_source(const char *cs_json, char *out, size_t cap, size_t *out_len) {
+    if (!cs_json || !out_len) return SB_ERR_ARG;
+    try {
+        ConstraintSystem cs = parse_cs(cs_json);
+        const int P = (int)cs.perm_cols.size(), chunk = cs.degree - 2;
+        std::vector<std::pair<int, int>> sets;
+        for (int f = 0; f < P; f += chunk) sets.push_back({f, std::min(chunk, P - f)});
+        sb_pk fake;
+        fake.cs = cs;
+        fake.P = P;
+        const Program prog = h_program_for(&fake, sets, cs.lookups.size(), hfr::ONE, hfr::ONE, hfr::ONE, hfr::ONE);
+        const std::string src = expr_jit_source(prog);
+        *out_len = src.size();
+        if (out && cap >= src.size()) memcpy(out, src.data(), src.size());
+    } catch (const std::exception &e) {
+        set_last_error("sb_test_h_jit_source: %s", e.what());
+        return SB_ERR_ARG;
+    }
+    return SB_OK;
+}
 int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digits, uint32_t *out_launch_sets) {
     if (!ctx || !out_ms) return SB_ERR_ARG;
     for (int i = 0; i < 5; i++) out_ms[i] = ctx->acc_msm_ms[i];
@@ -1980,6 +2029,11 @@ int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]) {
 int32_t sb_last_h_rows(const sb_ctx *ctx, uint64_t *out_rows) {
     if (!ctx || !out_rows) return SB_ERR_ARG;
     *out_rows = ctx->last_h_rows;
+    return SB_OK;
+}
+int32_t sb_last_h_jit(const sb_ctx *ctx, int32_t *out_used) {
+    if (!ctx || !out_used) return SB_ERR_ARG;
+    *out_used = ctx->last_h_jit ? 1 : 0;
     return SB_OK;
 }
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]) {

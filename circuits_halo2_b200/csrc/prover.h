@@ -69,6 +69,14 @@ fr_t program_eval_host(const Program &prog, const std::vector<fr_t> &inputs);
 int32_t expr_eval(sb_ctx *ctx, const Program &prog, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out, cudaStream_t st,
                   const std::vector<uint8_t> *col_shift = nullptr);
 
+// ---- expr_jit.cu: the same program as straight-line code compiled by NVRTC (nullptr when NVRTC is unavailable: the interpreter runs instead) ----
+struct ExprJit;
+ExprJit *expr_jit_compile(const Program &prog, std::string *why);
+void expr_jit_free(ExprJit *j);
+std::string expr_jit_source(const Program &prog);  // the generated CUDA source (CPU test: it must compile offline with nvcc)
+int32_t expr_jit_run(sb_ctx *ctx, const ExprJit *j, const void *d_consts, const std::vector<const void *> &cols, uint32_t log_n, uint32_t rot_scale_log, void *d_out,
+                     cudaStream_t st, const std::vector<uint8_t> *col_shift = nullptr);
+
 inline fr_t to_dev(const hfr::Fr &x) { fr_t r; memcpy(r.v, x.v, 32); return r; }
 inline hfr::Fr to_host(const fr_t &x) { hfr::Fr r; memcpy(r.v, x.v, 32); return r; }
 

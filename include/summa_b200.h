@@ -190,6 +190,8 @@ int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_co
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);
 /* rows the fused program ran on in that proof on this rank: (owned cosets of the quotient argument) x 2^k */
 int32_t sb_last_h_rows(const sb_ctx *ctx, uint64_t *out_rows);
+/* 1 when that evaluate_h ran the key's program as NVRTC-compiled straight-line code, 0 when the interpreter ran it (NVRTC absent, or SB_NO_JIT) */
+int32_t sb_last_h_jit(const sb_ctx *ctx, int32_t *out_used);
 /* host wall-clock (ms) of the stages of the last create_proof: [0] advice upload + commitments, [1] lookup permute + commitments,
  * [2] permutation products, [3] lookup product, [4] random polynomial, [5] coset NTTs, [6] evaluate_h, [7] quotient + commitments,
  * [8] evaluations, [9] SHPLONK */
@@ -229,6 +231,8 @@ int32_t sb_test_chacha_fr(uint64_t seed_u64, uint32_t skip_bytes, uint32_t count
 /* evaluate_h compiler on the CPU: quotient-numerator program of `cs_json` (challenges from `seed`) run by the host interpreter on one
  * pseudo-random row vs a direct walk of the expression trees; out_shape = instructions, field products, add/sub, live value slots */
 int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_program_value[32], uint8_t out_direct_value[32], uint32_t out_shape[4]);
+/* the CUDA source the NVRTC path compiles for `cs_json`'s quotient-numerator program (cap 0: size query) */
+int32_t sb_test_h_jit_source(const char *cs_json, char *out, size_t cap, size_t *out_len);
 int32_t sb_test_host_fr(int32_t op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 
 /* ---- zk_prover::merkle_sum_tree: MerkleSumTree::from_entries / Tree::generate_proof ------------------

@@ -208,3 +208,34 @@ def test_configs4_flow_tree_to_witness_to_proof_for_distinct_users(ctx, golden_d
                     ChaCha20Rng.seed_from_u64(1000 + u), tr)
     assert proofs[users.index(u)] == tr.finalize()
     tree.close()
+
+
+def test_evaluate_h_nvrtc_kernel_is_used_and_equals_the_interpreter(golden_dir):
+    """The key's quotient-numerator program runs as NVRTC-compiled straight-line sm_100a code (csrc/expr_jit.cu); a context created with SB_NO_JIT runs
+    the interpreter (csrc/expr.cu) instead.  Same program, same values: the two proofs are byte-identical (and equal the k = 17 golden)."""
+    import circuits_halo2_b200 as sb
+    from circuits_halo2_b200 import _lib, fields
+    k = 17
+    gold = np.load(os.path.join(golden_dir, "golden_proof_k17.npz"))
+    fx = np.load(os.path.join(golden_dir, "mst_inclusion_assignment.npz"))
+    cs = json.load(open(os.path.join(golden_dir, "mst_inclusion_cs.json")))
+    instances = [fields.fr_from_mont(v) for v in fx["instances"]]
+    seed = sb.seed_from_u64(int(gold["seed_u64"][0]))
+    proofs, used = [], []
+    for no_jit in (False, True):
+        if no_jit:
+            os.environ["SB_NO_JIT"] = "1"
+        try:
+            c = sb.Context(0)
+        finally:
+            os.environ.pop("SB_NO_JIT", None)
+        params = sb.ParamsKZG.setup(k, int(gold["tau"][0]), c, download=False)
+        pk = sb.ProvingKey.from_sparse(params, cs, fx["fixed_cells"], fx["fixed_values"], fx["perm_cells"], int(gold["transcript_repr"][0]), c)
+        proofs.append(sb.create_proof_sparse(pk, instances, fx["advice_cells"], fx["advice_values"], seed, sb.TRANSCRIPT_KECCAK))
+        u = ctypes.c_int32(-1)
+        _lib.check(_lib.lib().sb_last_h_jit(c.handle, ctypes.byref(u)), "sb_last_h_jit")
+        used.append(u.value)
+        del pk, params
+        c.close()
+    assert used == [1, 0], f"NVRTC kernel used: {used} (expected the JIT on the default context and the interpreter under SB_NO_JIT)"
+    assert proofs[0] == proofs[1] == gold["proof"].tobytes()

@@ -313,3 +313,24 @@ def test_product_witness_rejects_what_the_circuit_cannot_satisfy():
     ok = M.MerkleSumTree.from_csv(os.path.join(ROOT, "tests", "golden", "entry_16.csv"))
     with pytest.raises(SummaB200Error):
         _product_witness(ok.generate_proof(0), 4, 2, 10)   # LEVELS = 4 needs k = 11 (circuits/tests.rs:23): NotEnoughRowsAvailable
+
+
+def test_evaluate_h_generated_source_compiles_offline(tmp_path):
+    """the CUDA source csrc/expr_jit.cu generates for the reference circuit's quotient program (what NVRTC compiles on the GPU box) compiles for
+    sm_100a with nvcc here, without spills; one non-inlined Montgomery product, straight-line body"""
+    from circuits_halo2_b200 import _lib
+    L = _lib.lib()
+    for name in ("mst_inclusion_cs.json", "mst_inclusion_cs_n8.json"):
+        cs = open(os.path.join(ROOT, "tests", "golden", name)).read().encode()
+        n = ctypes.c_size_t()
+        assert L.sb_test_h_jit_source(cs, None, ctypes.c_size_t(0), ctypes.byref(n)) == 0
+        buf = ctypes.create_string_buffer(n.value + 1)
+        assert L.sb_test_h_jit_source(cs, buf, ctypes.c_size_t(n.value), ctypes.byref(n)) == 0
+        src = tmp_path / (name + ".cu")
+        src.write_bytes(buf.raw[: n.value])
+        out = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-cubin", "-Xptxas", "-v", "-o", str(tmp_path / "h.cubin"), str(src)],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "0 bytes spill stores" in out.stderr and "sb_h_jit" in out.stderr
+        body = buf.raw[: n.value].decode()
+        assert body.count("jmul(") >= 100 and "for (" not in body.split("sb_h_jit")[-1]

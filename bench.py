@@ -373,7 +373,11 @@ def main():
 
     # ---- create_proof at every requested k ----------------------------------------------------------------------------------------
     ks = sorted(set([int(x) for x in args.proof_k.split(",") if x] + [HEADLINE_K]))
-    comm = sb.ShardComm(device=local) if world > 1 else None
+    # the ranks' exchanges: the library's own shared-memory mailbox + CUDA IPC peer copies (no Python / NCCL on the data path); SB_BENCH_COMM=nccl
+    # selects the torch.distributed callbacks instead
+    comm = None
+    if world > 1:
+        comm = sb.ShardComm(device=local) if os.environ.get("SB_BENCH_COMM") == "nccl" else sb.ShmComm.from_process_group()
     mst23 = None
     records = []
     clocks = None
@@ -632,6 +636,7 @@ def main():
             "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": WORKLOAD, "k": HEADLINE_K, "rows": 1 << HEADLINE_K, "quotient_rows": 5 << HEADLINE_K, "advice": 3, "fixed": 11, "permutation_columns": 6,
                        "lookups": 1, "constraint_degree": 6, "srs": "unsafe synthetic SRS, tau = 0x5A110000 + k (no k=20 ptau in the reference tree)", "rng": "ChaCha20 seed_from_u64(42)",
+                       "exchange": None if world == 1 else ("torch.distributed / NCCL callbacks" if os.environ.get("SB_BENCH_COMM") == "nccl" else "sb_comm_shm: shared-memory mailbox + CUDA IPC peer copies over NVLink"),
                        "parallelism": "single GPU" if world == 1 else f"one proof sharded over {world} GPUs: commitments by window, coset NTTs / evaluate_h / quotient iNTTs by coset (5 cosets)",
                        "l2": "working set of a proof (key 5.4 GiB + per-proof columns) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": head["e2e_ms_per_proof"], "unit": UNIT, "ms_per_step": head["e2e_ms_per_proof"], "h2d_bytes_per_step": head["h2d_bytes_per_proof"],

@@ -17,6 +17,6 @@ from .arithmetic import best_fft, best_fft_dist, best_multiexp  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .params import ParamsKZG  # noqa: F401
 from .merkle_sum_tree import Entry, MerkleProof, MerkleSumTree, Node  # noqa: F401
-from .plonk import mst_inclusion_witness, BatchProver, LocalComm, ShardComm, shard_range, ProvingKey, create_proof, create_proof_dev, create_proof_sparse, seed_from_u64, TRANSCRIPT_BLAKE2B, TRANSCRIPT_KECCAK  # noqa: F401
+from .plonk import mst_inclusion_witness, BatchProver, LocalComm, ShardComm, ShmComm, shard_range, ProvingKey, create_proof, create_proof_dev, create_proof_sparse, seed_from_u64, TRANSCRIPT_BLAKE2B, TRANSCRIPT_KECCAK  # noqa: F401
 
 __all__ = ["Context", "default_context", "best_fft", "best_multiexp", "EvaluationDomain", "ParamsKZG", "ProvingKey", "create_proof", "create_proof_sparse", "create_proof_dev", "seed_from_u64", "MerkleSumTree", "Entry", "Node", "MerkleProof"]

@@ -180,6 +180,51 @@ class ShardComm:
         return self._c
 
 
+class ShmComm:
+    """`sb_comm` implemented INSIDE the library for the ranks of one box (sb_comm_shm_create): shared-memory mailbox for the small host records, CUDA IPC
+    peer copies over NVLink for device buffers.  No torch / NCCL / Python on the data path.  `name`: same on every rank, unique per job."""
+
+    def __init__(self, name: str, rank: int, world: int, ctx: Optional[Context] = None):
+        self.rank, self.world, self.error = rank, world, None
+        self._c = _SbComm()
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sb_comm_shm_create(ctx.handle if ctx is not None else None, ctypes.c_char_p(name.encode()), ctypes.c_int32(rank), ctypes.c_int32(world),
+                                                 ctypes.byref(self._c), ctypes.byref(self._h)), "sb_comm_shm_create")
+
+    @classmethod
+    def from_process_group(cls, ctx: Optional[Context] = None, group=None) -> "ShmComm":
+        """one communicator per torch.distributed process group: rank 0 picks a fresh name and broadcasts it"""
+        import os
+        import uuid
+        import torch.distributed as dist
+        box = [uuid.uuid4().hex[:16] if dist.get_rank(group) == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(f"{os.environ.get('MASTER_PORT', '0')}_{box[0]}", dist.get_rank(group), dist.get_world_size(group), ctx)
+
+    def allgather_host(self, data: bytes) -> bytes:
+        """the mailbox exchange on its own (tests)"""
+        out = ctypes.create_string_buffer(len(data) * self.world)
+        rc = self._c.allgather_host(self._c.user, data, out, len(data))
+        if rc != 0:
+            raise RuntimeError(_lib.lib().sb_last_error().decode(errors="replace"))
+        return out.raw
+
+    @property
+    def struct(self):
+        return self._c
+
+    def close(self):
+        if self._h:
+            _lib.lib().sb_comm_shm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LocalComm:
     """world = 1: the coset-sharded code path on a single GPU (all cosets owned, no exchange)"""
 

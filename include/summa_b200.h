@@ -185,6 +185,13 @@ int32_t sb_create_proof_sharded_dev(sb_ctx *ctx, const sb_pk *pk, const sb_comm 
 int32_t sb_create_proof_sharded_sparse(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, const uint8_t *instances, size_t n_instances, const uint32_t *advice_cells,
                                        const uint8_t *advice_cell_values, size_t n_cells, const uint8_t rng_seed[32], int32_t transcript_kind, uint8_t *proof_out,
                                        size_t proof_cap, size_t *proof_len);
+/* A ready-made sb_comm for the ranks of ONE box (one process per GPU) that needs no collective library: small host records meet in a POSIX
+ * shared-memory mailbox (microseconds per exchange), device buffers move by direct peer copies over NVLink through CUDA IPC mappings.  `name` must be
+ * the same on every rank and unique per job (a stale segment of the same name must not exist); `ctx` may be NULL for host-only use.  The call
+ * returns when all `world` ranks have attached.  The filled sb_comm stays valid until sb_comm_shm_destroy. */
+typedef struct sb_shm_comm sb_shm_comm;
+int32_t sb_comm_shm_create(sb_ctx *ctx, const char *name, int32_t rank, int32_t world, sb_comm *out_comm, sb_shm_comm **out_handle);
+int32_t sb_comm_shm_destroy(sb_shm_comm *handle);
 /* device time (ms) of the fused evaluate_h kernel of the last create_proof on this context and its program shape:
  * instructions, field products, additions/subtractions, live value slots */
 int32_t sb_last_h_profile(const sb_ctx *ctx, float *out_ms, uint32_t out_program[4]);

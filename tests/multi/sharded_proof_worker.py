@@ -34,7 +34,8 @@ def main():
     advice[fx["advice_cells"][:, 0], fx["advice_cells"][:, 1]] = fx["advice_values"]
     instances = [fields.fr_from_mont(v) for v in fx["instances"]]
     seed = sb.seed_from_u64(99)
-    comm = sb.ShardComm()
+    # argv[3] = "shm": the library's own communicator (shared-memory mailbox + CUDA IPC peer copies) instead of the torch.distributed callbacks
+    comm = sb.ShmComm.from_process_group() if (len(sys.argv) > 3 and sys.argv[3] == "shm") else sb.ShardComm()
     for transcript in (sb.TRANSCRIPT_KECCAK, sb.TRANSCRIPT_BLAKE2B):
         plain = sb.create_proof(pk, instances, advice, seed, transcript)
         sharded = sb.create_proof(pk, instances, advice, seed, transcript, comm=comm)

@@ -93,6 +93,12 @@ def test_two_gpu_sharded_proof_equals_single_gpu_proof():
            os.path.join(ROOT, "tests", "multi", "sharded_proof_worker.py"), "14"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    # the library's own communicator (shared-memory mailbox for host records, CUDA IPC peer copies for device buffers) instead of torch / NCCL,
+    # including the distributed NTT's all-to-all
+    cmd[cmd.index("29533")] = "29536"
+    out = subprocess.run(cmd[:-1] + ["15", "1", "shm"], capture_output=True, text=True, timeout=600, env=dict(os.environ, SB_DIST_NTT_MIN_K="10"))
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    cmd[cmd.index("29536")] = "29533"
     # the same with every replicated size-n transform run as a distributed four-step NTT (the k >= 22 path, forced at k = 16)
     env = dict(os.environ, SB_DIST_NTT_MIN_K="10")
     cmd[cmd.index("29533")] = "29535"

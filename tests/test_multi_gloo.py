@@ -73,3 +73,45 @@ def test_sharded_msm_host_fold_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _shm_worker(rank, world, name, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import circuits_halo2_b200 as sb
+        comm = sb.ShmComm(name, rank, world)          # host-only: no context, no GPU
+        for it in range(3000):
+            size = (16, 128, 1024, 8 * 128)[it % 4]
+            mine = bytes([(rank * 37 + it + j) & 0xFF for j in range(size)])
+            got = comm.allgather_host(mine)
+            want = b"".join(bytes([(r * 37 + it + j) & 0xFF for j in range(size)]) for r in range(world))
+            assert got == want, (rank, it)
+        # a record larger than a mailbox slot is an error on every rank, not a hang
+        try:
+            comm.allgather_host(b"x" * (17 << 10))
+            raise AssertionError("oversized record accepted")
+        except RuntimeError:
+            pass
+        comm.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc() + repr(e)))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_shared_memory_mailbox_allgather(world):
+    """sb_comm_shm (csrc/comm_shm.cu), host half: the ranks' small records (partial commitments, IPC handles) meet in a POSIX shared-memory mailbox.
+    3000 back-to-back exchanges of changing sizes between `world` processes: every rank always reads every rank's record of the SAME generation."""
+    import uuid
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    name = "t" + uuid.uuid4().hex[:12]
+    procs = [ctxm.Process(target=_shm_worker, args=(r, world, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res

@@ -73,6 +73,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.ntt_tile = geti("SB_NTT_TILE", 0);
     t.ntt_passes = geti("SB_NTT_PASSES", 0);
     t.ntt_tw_mb = geti("SB_NTT_TW_MB", 1024);
+    t.ntt_eb = geti("SB_NTT_EB", 3);
     t.dist_ntt_min_k = geti("SB_DIST_NTT_MIN_K", 22);
     t.msm_no_cta_scan = getb("SB_MSM_NO_CTA_SCAN");
     t.shard_msm_by_range = getb("SB_SHARD_MSM_BY_RANGE");

@@ -62,6 +62,7 @@ struct Tuning {
     int ntt_tile = 0;         // SB_NTT_TILE: 11 | 12 = log2 elements per NTT tile (0 = choose from the size)
     int ntt_passes = 0;       // SB_NTT_PASSES: minimum number of NTT passes (0 = as few as the tile allows)
     int dist_ntt_min_k = 22;  // SB_DIST_NTT_MIN_K: sharded proofs run their replicated size-n transforms as distributed four-step NTTs from this k on
+    int ntt_eb = 3;           // SB_NTT_EB: 3 = eight elements per thread (radix-8 stages), 2 = four (radix-4 stages, twice the warps)
     int ntt_tw_mb = 1024;     // SB_NTT_TW_MB: budget (MiB) of a plan's full inter-pass twiddle tables; above it the two-level tables are used
     bool msm_no_cta_scan = false;    // SB_MSM_NO_CTA_SCAN
     bool shard_msm_by_range = false; // SB_SHARD_MSM_BY_RANGE

@@ -70,12 +70,14 @@ __device__ __forceinline__ void sts_fr(uint4 *lo, uint4 *hi, uint32_t i, const n
     hi[i] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
 
-// One tile of one pass.  blockDim.x = 2^(r + g - 3): eight elements per thread.
-template <int T_LOG>
-__global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pass_kernel(const NttPassArgs p) {
+// One tile of one pass.  blockDim.x = 2^(r + g - EB): 2^EB elements per thread (EB = 3: radix-8 stages, 128 registers, 16 warps / SM;
+// EB = 2: radix-4 stages, one more exchange per pass, 64 registers, 32 warps / SM).
+template <int T_LOG, int EB>
+__global__ void __launch_bounds__(1 << (T_LOG - EB), T_LOG == 11 ? 2 : 1) ntt_pass_kernel(const NttPassArgs p) {
     extern __shared__ uint4 smem[];
     const NttGeom G(p);
-    const uint32_t tile = 1u << G.t, T = tile >> 3, tid = threadIdx.x, half_r = 1u << (G.r - 1);
+    constexpr int E = 1 << EB;
+    const uint32_t tile = 1u << G.t, T = tile >> EB, tid = threadIdx.x, half_r = 1u << (G.r - 1);
     uint4 *s_lo = smem, *s_hi = smem + tile;
     uint4 *w_lo = s_hi + tile, *w_hi = w_lo + half_r;
     const NttTileCoord tc(p, blockIdx.x + p.tile0);
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         cp_async16(w_hi + s, p.w + 2 * e + 1);
     }
 
-    nfr_t x[8];
+    nfr_t x[E];
     uint32_t pw = G.window(0);
     if (p.kind == NTT_LAST) {
         // the tile's G rows are contiguous in HBM: stage them with cp.async, coalesced, straight to their swizzled slots
@@ -101,11 +103,11 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         cp_async_wait_all();
         __syncthreads();
 #pragma unroll
-        for (int b = 0; b < 8; b++) x[b] = lds_fr(s_lo, s_hi, ntt_swz(G.idx(tid, pw, (uint32_t)b)));
+        for (int b = 0; b < E; b++) x[b] = lds_fr(s_lo, s_hi, ntt_swz(G.idx(tid, pw, (uint32_t)b)));
     } else {
         const bool first = (p.log_a == 0);
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
+        for (int b = 0; b < E; b++) {
             const uint32_t i = G.idx(tid, pw, (uint32_t)b);
             const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
             x[b] = first ? ntt_fetch_input(p, bo, gi) : ntt_load_fr(p.src + 2 * (bo.src + gi));
@@ -121,12 +123,12 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         if (s > 0) {
             __syncthreads();  // every thread is done reading the previous contents of the exchange buffer
 #pragma unroll
-            for (int b = 0; b < 8; b++) sts_fr(s_lo, s_hi, ntt_swz(G.idx(tid, prev, (uint32_t)b)), x[b]);
+            for (int b = 0; b < E; b++) sts_fr(s_lo, s_hi, ntt_swz(G.idx(tid, prev, (uint32_t)b)), x[b]);
             __syncthreads();
 #pragma unroll
-            for (int b = 0; b < 8; b++) x[b] = lds_fr(s_lo, s_hi, ntt_swz(G.idx(tid, pw, (uint32_t)b)));
+            for (int b = 0; b < E; b++) x[b] = lds_fr(s_lo, s_hi, ntt_swz(G.idx(tid, pw, (uint32_t)b)));
         }
-        ntt_stage_butterflies(x, G, tid, pw, low, tw);
+        ntt_stage_butterflies<EB>(x, G, tid, pw, low, tw);
         low = pw - G.jshift;
         prev = pw;
     }
@@ -136,17 +138,17 @@ __global__ void __launch_bounds__(1 << (T_LOG - 3), T_LOG == 11 ? 2 : 1) ntt_pas
         // contiguous runs on the output side need gg fastest across lanes: one more exchange
         __syncthreads();
 #pragma unroll
-        for (int b = 0; b < 8; b++) sts_fr(s_lo, s_hi, ntt_swz(G.idx(tid, prev, (uint32_t)b)), x[b]);
+        for (int b = 0; b < E; b++) sts_fr(s_lo, s_hi, ntt_swz(G.idx(tid, prev, (uint32_t)b)), x[b]);
         __syncthreads();
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
+        for (int b = 0; b < E; b++) {
             const uint32_t m = tid + T * (uint32_t)b;
             const uint32_t gg = m & ((1u << p.g) - 1u), jj = m >> p.g;
             ntt_emit(p, bo, tc, ntt_brev(jj, G.r), gg, lds_fr(s_lo, s_hi, ntt_swz((gg << G.r) | jj)));
         }
     } else {
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
+        for (int b = 0; b < E; b++) {
             const uint32_t i = G.idx(tid, prev, (uint32_t)b);
             ntt_emit(p, bo, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), x[b]);
         }
@@ -384,8 +386,10 @@ int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t 
     const bool scale_in_post = has_scale && pl->npass == 1;
     static bool attr_set[64] = {false};  // per device
     if (ctx->device >= 64 || !attr_set[ctx->device]) {
-        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
-        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
         SB_CUDA_TRY(cudaFuncSetAttribute(ntt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)32 << SMALL_MAX_LOG)));
         if (ctx->device < 64) attr_set[ctx->device] = true;
     }
@@ -456,9 +460,13 @@ int32_t ntt_run_fused(sb_ctx *ctx, const void *d_in, void *d_out, const uint8_t 
             SB_LAUNCH(ctx, ntt_small_kernel, dim3(1, batch), nt, (size_t)32 << a.r, st, a);
         } else {
             const uint64_t tiles = 1ull << (log_n - a.r - a.g);
-            const unsigned threads = 1u << (a.r + a.g - 3);
-            if (a.r + a.g == 12) SB_LAUNCH(ctx, ntt_pass_kernel<12>, dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
-            else SB_LAUNCH(ctx, ntt_pass_kernel<11>, dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
+            a.eb = (ctx->tune.ntt_eb == 2 && a.r + a.g >= 4) ? 2 : 3;
+            const unsigned threads = 1u << (a.r + a.g - a.eb);
+            if (a.eb == 2) {
+                if (a.r + a.g == 12) SB_LAUNCH(ctx, (ntt_pass_kernel<12, 2>), dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
+                else SB_LAUNCH(ctx, (ntt_pass_kernel<11, 2>), dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
+            } else if (a.r + a.g == 12) SB_LAUNCH(ctx, (ntt_pass_kernel<12, 3>), dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
+            else SB_LAUNCH(ctx, (ntt_pass_kernel<11, 3>), dim3((unsigned)tiles, batch), threads, pass_smem(a.r, a.g), st, a);
         }
         log_a += a.r;
     }
@@ -487,8 +495,10 @@ int32_t ntt_run_dist(sb_ctx *ctx, const sb_comm *comm, void *d_a, const uint8_t 
     SB_REQUIRE(pl->npass == 2, "ntt_dist: the size needs a two-pass plan (2^16 .. 2^24)");
     static bool attr_set[64] = {false};
     if (ctx->device >= 64 || !attr_set[ctx->device]) {
-        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
-        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(11, 0)));
+        SB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem(12, 0)));
         if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     const uint64_t n = 1ull << log_n;
@@ -518,9 +528,10 @@ int32_t ntt_run_dist(sb_ctx *ctx, const sb_comm *comm, void *d_a, const uint8_t 
         SB_REQUIRE(tiles_all % W == 0 && tiles_all / W >= 1, "ntt_dist: world does not divide the tiles of a pass");
         const uint64_t mine = tiles_all / W;
         a.tile0 = (uint32_t)(rk * mine);
+        a.eb = 3;
         const unsigned threads = 1u << (a.r + a.g - 3);
-        if (a.r + a.g == 12) SB_LAUNCH(ctx, ntt_pass_kernel<12>, dim3((unsigned)mine, 1), threads, pass_smem(a.r, a.g), st, a);
-        else SB_LAUNCH(ctx, ntt_pass_kernel<11>, dim3((unsigned)mine, 1), threads, pass_smem(a.r, a.g), st, a);
+        if (a.r + a.g == 12) SB_LAUNCH(ctx, (ntt_pass_kernel<12, 3>), dim3((unsigned)mine, 1), threads, pass_smem(a.r, a.g), st, a);
+        else SB_LAUNCH(ctx, (ntt_pass_kernel<11, 3>), dim3((unsigned)mine, 1), threads, pass_smem(a.r, a.g), st, a);
         return SB_OK;
     };
     // ---- pass 1 on my columns

@@ -33,6 +33,7 @@ struct NttPassArgs {
     const uint4 *post_vec; // optional, last pass: output element i is multiplied by post_vec[i]
     uint32_t log_n, r, g, log_a, log_c, log_r1, log_tlo;
     uint32_t kind, npass, n_mid;
+    uint32_t eb;           // log2 of the elements a thread keeps in registers: 3 (radix-8 stages) or 2 (radix-4 stages, twice the threads per tile)
     uint32_t tile0;        // first tile of this launch (a rank of a distributed transform runs a sub-range of a pass' tiles)
     uint32_t mid_bits[NTT_MAX_PASS];  // radices of passes 2 .. P-1 (for the last pass' digit reversal)
     uint32_t pre_m;    // optional, first pass: input element i is multiplied by pre_pat[i % pre_m] (pre_m <= 8; 0 = off)
@@ -61,19 +62,20 @@ SB_HD uint32_t ntt_brev(uint32_t x, uint32_t bits) {
 // geometry of one pass, derived once per thread
 struct NttGeom {
     uint32_t r, g, t, jshift;  // j sits at idx bits [jshift, jshift + r); gg at [0, g) (strided) or [r, r + g) (last)
-    uint32_t n_stages;
+    uint32_t n_stages, eb;
     SB_HD NttGeom(const NttPassArgs &p) {
         r = p.r; g = p.g; t = r + g;
+        eb = p.eb ? p.eb : 3;
         jshift = (p.kind == NTT_STRIDED) ? g : 0;
-        n_stages = (r + 2) / 3;
+        n_stages = (r + eb - 1) / eb;
     }
     // lowest idx bit of the register window of stage s
     SB_HD uint32_t window(uint32_t s) const {
-        const int w = (int)jshift + (int)r - 3 * ((int)s + 1);
+        const int w = (int)jshift + (int)r - (int)eb * ((int)s + 1);
         return (uint32_t)(w < (int)jshift ? (int)jshift : w);
     }
     // tile index of register b of thread tid in a stage whose window starts at p
-    SB_HD uint32_t idx(uint32_t tid, uint32_t p, uint32_t b) const { return ((tid >> p) << (p + 3)) | (b << p) | (tid & ((1u << p) - 1u)); }
+    SB_HD uint32_t idx(uint32_t tid, uint32_t p, uint32_t b) const { return ((tid >> p) << (p + eb)) | (b << p) | (tid & ((1u << p) - 1u)); }
     SB_HD uint32_t j_of(uint32_t idx_) const { return (idx_ >> jshift) & ((1u << r) - 1u); }
     SB_HD uint32_t gg_of(uint32_t idx_) const { return jshift ? (idx_ & ((1u << g) - 1u)) : (idx_ >> r); }
 };
@@ -137,17 +139,17 @@ SB_HD nfr_t ntt_mul(const nfr_t &a, const nfr_t &b) {
 
 // ---- the DIF levels of one stage on the eight registers -------------------------------------------------------------------------------
 // TW: functor e -> omega_R^e (e < R / 2).  `low` = first j-bit NOT yet processed by earlier stages (levels at j-bits >= low are skipped).
-template <class TW>
-SB_HD void ntt_stage_butterflies(nfr_t x[8], const NttGeom &G, uint32_t tid, uint32_t p, uint32_t low, const TW &tw) {
+template <int EB, class TW>
+SB_HD void ntt_stage_butterflies(nfr_t x[1 << EB], const NttGeom &G, uint32_t tid, uint32_t p, uint32_t low, const TW &tw) {
     const uint32_t jb0 = p - G.jshift;                          // j-bit of window bit 0
     const uint32_t tl = (tid & ((1u << p) - 1u)) >> G.jshift;   // the thread's j bits below the window
 #pragma unroll
-    for (int wb = 2; wb >= 0; wb--) {
+    for (int wb = EB - 1; wb >= 0; wb--) {
         const uint32_t q = jb0 + (uint32_t)wb;                  // j-bit of this level: pairs differ in it, h = 2^q
         if (q >= low || q >= G.r) continue;
         const uint32_t sh = G.r - 1 - q;
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
+        for (int b = 0; b < (1 << EB); b++) {
             if (b & (1 << wb)) continue;
             const int b1 = b | (1 << wb);
             const uint32_t jlow = (((uint32_t)b & ((1u << wb) - 1u)) << jb0) | tl;   // j mod 2^q

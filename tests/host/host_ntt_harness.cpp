@@ -63,7 +63,7 @@ extern "C" {
 // a: n = 2^log_n elements (8 x u32 each, Montgomery) transformed in place like sb_best_fft; fused operations as in NttFuse (null = off).
 // Returns the worst shared-memory bank-conflict degree seen (1 = conflict-free), or 0 on a usage error.
 uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, uint32_t tile_log, uint32_t min_passes, int use_full_tw, const uint32_t *scale_words,
-                const uint32_t *pre_vec_words, const uint32_t *pre_pat_words, uint32_t pre_m, const uint32_t *post_pat_words, uint32_t post_m, uint64_t n_in, uint64_t n_out, const uint32_t *post_vec_words) {
+                const uint32_t *pre_vec_words, const uint32_t *pre_pat_words, uint32_t pre_m, const uint32_t *post_pat_words, uint32_t post_m, uint64_t n_in, uint64_t n_out, const uint32_t *post_vec_words, uint32_t eb) {
     const uint64_t n = 1ull << log_n;
     if (log_n < 3) return 0;
     nfr_t omega, scale = nfr_t::one();
@@ -138,12 +138,14 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
         p.src = npass == 1 ? in.data() : (t == 0 ? in.data() : work.data());
         p.dst = npass == 1 ? out.data() : (last ? out.data() : work.data());
 
+        p.eb = eb;
         const NttGeom G(p);
         const NttBatch bo(p, 0);
-        const uint32_t tile = 1u << G.t, T = tile >> 3;
+        const uint32_t E = 1u << G.eb;
+        const uint32_t tile = 1u << G.t, T = tile >> G.eb;
         const uint64_t tiles = 1ull << (log_n - p.r - p.g);
         std::vector<nfr_t> smem(tile);
-        std::vector<nfr_t> regs((size_t)T * 8);
+        std::vector<nfr_t> regs((size_t)T * E);
         for (uint64_t tile_id = 0; tile_id < tiles; tile_id++) {
             const NttTileCoord tc(p, tile_id);
             const bool audit = tile_id == 0;  // the access pattern is the same for every tile
@@ -152,13 +154,13 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
             if (p.kind == NTT_LAST) {
                 for (uint32_t i = 0; i < tile; i++) smem[ntt_swz(i)] = ntt_load_fr(p.src + 2 * tc.in_index(p, G.j_of(i), G.gg_of(i)));
                 for (uint32_t tid = 0; tid < T; tid++)
-                    for (uint32_t b = 0; b < 8; b++) regs[tid * 8 + b] = smem[ntt_swz(G.idx(tid, pw, b))];
+                    for (uint32_t b = 0; b < E; b++) regs[tid * E + b] = smem[ntt_swz(G.idx(tid, pw, b))];
             } else {
                 for (uint32_t tid = 0; tid < T; tid++)
-                    for (uint32_t b = 0; b < 8; b++) {
+                    for (uint32_t b = 0; b < E; b++) {
                         const uint32_t i = G.idx(tid, pw, b);
                         const uint64_t gi = tc.in_index(p, G.j_of(i), G.gg_of(i));
-                        regs[tid * 8 + b] = p.log_a == 0 ? ntt_fetch_input(p, bo, gi) : ntt_load_fr(p.src + 2 * gi);
+                        regs[tid * E + b] = p.log_a == 0 ? ntt_fetch_input(p, bo, gi) : ntt_load_fr(p.src + 2 * gi);
                     }
             }
             uint32_t low = G.r, prev = pw;
@@ -167,16 +169,17 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
                 if (s > 0) {
                     std::vector<std::vector<uint32_t>> wr(T), rd(T);
                     for (uint32_t tid = 0; tid < T; tid++)
-                        for (uint32_t b = 0; b < 8; b++) { const uint32_t a = ntt_swz(G.idx(tid, prev, b)); smem[a] = regs[tid * 8 + b]; wr[tid].push_back(a); }
+                        for (uint32_t b = 0; b < E; b++) { const uint32_t a = ntt_swz(G.idx(tid, prev, b)); smem[a] = regs[tid * E + b]; wr[tid].push_back(a); }
                     for (uint32_t tid = 0; tid < T; tid++)
-                        for (uint32_t b = 0; b < 8; b++) { const uint32_t a = ntt_swz(G.idx(tid, pw, b)); regs[tid * 8 + b] = smem[a]; rd[tid].push_back(a); }
+                        for (uint32_t b = 0; b < E; b++) { const uint32_t a = ntt_swz(G.idx(tid, pw, b)); regs[tid * E + b] = smem[a]; rd[tid].push_back(a); }
                     if (audit)
-                        for (size_t slot = 0; slot < 8; slot++) { const uint32_t c1 = conflict_degree(wr, slot), c2 = conflict_degree(rd, slot); worst = c1 > worst ? c1 : worst; worst = c2 > worst ? c2 : worst; }
+                        for (size_t slot = 0; slot < E; slot++) { const uint32_t c1 = conflict_degree(wr, slot), c2 = conflict_degree(rd, slot); worst = c1 > worst ? c1 : worst; worst = c2 > worst ? c2 : worst; }
                 }
                 std::vector<std::vector<uint32_t>> twlog(T);
                 for (uint32_t tid = 0; tid < T; tid++) {
                     HostTwiddle tw{&w, audit ? &twlog[tid] : nullptr};
-                    ntt_stage_butterflies(&regs[tid * 8], G, tid, pw, low, tw);
+                    if (G.eb == 2) ntt_stage_butterflies<2>(&regs[tid * E], G, tid, pw, low, tw);
+                    else ntt_stage_butterflies<3>(&regs[tid * E], G, tid, pw, low, tw);
                 }
                 if (audit)
                     for (size_t slot = 0; slot < 12; slot++) { const uint32_t c1 = conflict_degree(twlog, slot); worst = c1 > worst ? c1 : worst; }
@@ -187,9 +190,9 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
             if (p.kind == NTT_LAST && p.g > 0) {
                 std::vector<std::vector<uint32_t>> rd(T);
                 for (uint32_t tid = 0; tid < T; tid++)
-                    for (uint32_t b = 0; b < 8; b++) smem[ntt_swz(G.idx(tid, prev, b))] = regs[tid * 8 + b];
+                    for (uint32_t b = 0; b < E; b++) smem[ntt_swz(G.idx(tid, prev, b))] = regs[tid * E + b];
                 for (uint32_t tid = 0; tid < T; tid++)
-                    for (uint32_t b = 0; b < 8; b++) {
+                    for (uint32_t b = 0; b < E; b++) {
                         const uint32_t m = tid + T * b;
                         const uint32_t gg = m & ((1u << p.g) - 1u), jj = m >> p.g;
                         const uint32_t a = ntt_swz((gg << G.r) | jj);
@@ -197,12 +200,12 @@ uint32_t ht_ntt(uint32_t *a_words, const uint32_t *omega_words, uint32_t log_n, 
                         ntt_emit(p, bo, tc, ntt_brev(jj, G.r), gg, smem[a]);
                     }
                 if (audit)
-                    for (size_t slot = 0; slot < 8; slot++) { const uint32_t c1 = conflict_degree(rd, slot); worst = c1 > worst ? c1 : worst; }
+                    for (size_t slot = 0; slot < E; slot++) { const uint32_t c1 = conflict_degree(rd, slot); worst = c1 > worst ? c1 : worst; }
             } else {
                 for (uint32_t tid = 0; tid < T; tid++)
-                    for (uint32_t b = 0; b < 8; b++) {
+                    for (uint32_t b = 0; b < E; b++) {
                         const uint32_t i = G.idx(tid, prev, b);
-                        ntt_emit(p, bo, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), regs[tid * 8 + b]);
+                        ntt_emit(p, bo, tc, ntt_brev(G.j_of(i), G.r), G.gg_of(i), regs[tid * E + b]);
                     }
             }
         }

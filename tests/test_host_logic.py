@@ -195,7 +195,7 @@ def ntt_harness(tmp_path_factory):
     return lib
 
 
-def _run_device_ntt_on_host(lib, log_n, tile, min_passes, full_tw, seed=0, scale=None, pre_vec=None, pre_pat=None, post_pat=None, post_vec=None, n_in=0, n_out=0):
+def _run_device_ntt_on_host(lib, log_n, tile, min_passes, full_tw, seed=0, scale=None, pre_vec=None, pre_pat=None, post_pat=None, post_vec=None, n_in=0, n_out=0, eb=3):
     """Every thread of every tile of every pass of ntt_pass_kernel, emulated phase by phase on the CPU, vs the oracle's best_fft
     with the same fused scalings applied as separate passes.  Returns (equal, worst shared-memory bank-conflict degree)."""
     from oracle import cpu
@@ -205,7 +205,7 @@ def _run_device_ntt_on_host(lib, log_n, tile, min_passes, full_tw, seed=0, scale
     got = a.copy()
     pp = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None
     worst = lib.ht_ntt(pp(got), pp(w), log_n, tile, min_passes, int(full_tw), pp(scale), pp(pre_vec), pp(pre_pat), 0 if pre_pat is None else pre_pat.shape[0],
-                       pp(post_pat), 0 if post_pat is None else post_pat.shape[0], ctypes.c_uint64(n_in), ctypes.c_uint64(n_out), pp(post_vec))
+                       pp(post_pat), 0 if post_pat is None else post_pat.shape[0], ctypes.c_uint64(n_in), ctypes.c_uint64(n_out), pp(post_vec), eb)
     x = a.copy()
     if n_in:
         x[n_in:] = 0
@@ -233,9 +233,10 @@ def test_device_ntt_tile_code_on_host_all_plans(ntt_harness, tile):
             for full_tw in (0, 1):
                 if log_n <= tile and (min_passes or full_tw):
                     continue
-                ok, worst = _run_device_ntt_on_host(ntt_harness, log_n, tile, min_passes, full_tw)
-                assert ok, (tile, log_n, min_passes, full_tw)
-                assert worst <= 2, (tile, log_n, min_passes, full_tw, worst)
+                for eb in (3, 2):   # eight (radix-8 stages) or four (radix-4 stages) elements per thread
+                    ok, worst = _run_device_ntt_on_host(ntt_harness, log_n, tile, min_passes, full_tw, eb=eb)
+                    assert ok, (tile, log_n, min_passes, full_tw, eb)
+                    assert worst <= 2, (tile, log_n, min_passes, full_tw, eb, worst)
 
 
 @pytest.mark.parametrize("log_n,tile,min_passes,full_tw", [(11, 11, 0, 0), (12, 12, 0, 0), (13, 11, 0, 1), (15, 11, 3, 0), (15, 12, 0, 1)])

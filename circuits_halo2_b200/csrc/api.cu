@@ -69,6 +69,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.msm_seg = geti("SB_MSM_SEG", -1);
     t.msm_seg1 = geti("SB_MSM_SEG1", 2);
     t.msm_finish_at = geti("SB_MSM_FINISH_AT", 16384);
+    t.msm_cta_scan_max = geti("SB_MSM_CTA_SCAN_MAX", 65536);
     ctx->blocking_sync = getb("SB_BLOCKING_SYNC");
     t.ntt_tile = geti("SB_NTT_TILE", 0);
     t.ntt_passes = geti("SB_NTT_PASSES", 0);
@@ -81,6 +82,10 @@ void ctx_read_env(sb_ctx *ctx) {
     t.no_early_random = getb("SB_NO_EARLY_RANDOM");
     t.no_hprog_cache = getb("SB_NO_HPROG_CACHE");
     t.no_jit = getb("SB_NO_JIT");
+    t.no_binv2 = getb("SB_NO_BINV2");
+    t.no_shplonk_lagrange = getb("SB_NO_SHPLONK_LAGRANGE");
+    t.msm_no_bucket_tree = getb("SB_MSM_NO_BUCKET_TREE");
+    t.no_inst_direct = getb("SB_NO_INST_DIRECT");
     t.no_tables = getb("SB_NO_TABLES");
     t.no_smallkey_sort = getb("SB_NO_SMALLKEY_SORT");
 }
@@ -216,7 +221,7 @@ static int32_t ctx_init(sb_ctx *c, int32_t device) {
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) SB_CUDA_TRY(cudaEventCreateWithFlags(&c->side_ev[i], cudaEventDisableTiming));
-    c->pinned_bytes = 1 << 16;
+    c->pinned_bytes = 1 << 20;
     SB_CUDA_TRY(cudaHostAlloc(&c->pinned, c->pinned_bytes, cudaHostAllocDefault));
     SB_CUDA_TRY(cudaHostAlloc((void **)&c->stage, sb_ctx::STAGE_SLOTS * sb_ctx::STAGE_SLOT_BYTES, cudaHostAllocDefault));
     for (int i = 0; i < sb_ctx::STAGE_SLOTS; i++) SB_CUDA_TRY(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));

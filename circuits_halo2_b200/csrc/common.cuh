@@ -58,6 +58,7 @@ struct Tuning {
     int msm_l1 = 0;           // SB_MSM_L1: chunk length of reduce level 1 (0 = choose)
     int msm_seg = -1;         // SB_MSM_SEG: log2 segment of the first bucket level (-1 = choose)
     int msm_seg1 = 2;         // SB_MSM_SEG1: log2 segment of later bucket levels
+    int msm_cta_scan_max = 65536;  // SB_MSM_CTA_SCAN_MAX: reduce levels with at most this many slots use one CTA-wide segmented scan per 256 slots
     int msm_finish_at = 16384;  // SB_MSM_FINISH_AT: bucket count below which the hierarchy finishes in one step
     int ntt_tile = 0;         // SB_NTT_TILE: 11 | 12 = log2 elements per NTT tile (0 = choose from the size)
     int ntt_passes = 0;       // SB_NTT_PASSES: minimum number of NTT passes (0 = as few as the tile allows)
@@ -69,6 +70,10 @@ struct Tuning {
     bool no_side_stream = false;     // SB_NO_SIDE_STREAM
     bool no_early_random = false;    // SB_NO_EARLY_RANDOM
     bool no_hprog_cache = false;     // SB_NO_HPROG_CACHE
+    bool msm_no_bucket_tree = false; // SB_MSM_NO_BUCKET_TREE: bucket reduction by the running-sum hierarchy instead of the tree kernels
+    bool no_shplonk_lagrange = false; // SB_NO_SHPLONK_LAGRANGE: SHPLONK through the division coset (8 transforms) instead of the evaluation domain (1)
+    bool no_inst_direct = false;     // SB_NO_INST_DIRECT: instance column to the cosets through transforms even when it holds few values
+    bool no_binv2 = false;           // SB_NO_BINV2: batch inversion of long vectors through the single-level kernel
     bool no_jit = false;             // SB_NO_JIT: evaluate_h through the interpreter instead of the NVRTC-specialised kernel
     bool no_tables = false;          // SB_NO_TABLES
     bool no_smallkey_sort = false;   // SB_NO_SMALLKEY_SORT

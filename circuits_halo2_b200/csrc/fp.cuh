@@ -90,6 +90,10 @@ struct FrParams {  // scalar field r (InclusionVerifier.sol:210)
         return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u
              : i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
     }
+    SB_HD static constexpr uint32_t r3(int i) {  // R^3 mod r
+        return i == 0 ? 0xb4bf0040u : i == 1 ? 0x5e94d8e1u : i == 2 ? 0x1cfbb6b8u : i == 3 ? 0x2a489cbeu
+             : i == 4 ? 0xa19fcfedu : i == 5 ? 0x893cc664u : i == 6 ? 0x7fcc657cu : 0x0cf8594bu;
+    }
 };
 struct FqParams {  // base field q (InclusionVerifier.sol:209)
     static constexpr uint32_t INV = 0xe4866389u;
@@ -104,6 +108,10 @@ struct FqParams {  // base field q (InclusionVerifier.sol:209)
     SB_HD static constexpr uint32_t r2(int i) {
         return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u
              : i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+    }
+    SB_HD static constexpr uint32_t r3(int i) {
+        return i == 0 ? 0xda1530dfu : i == 1 ? 0xb1cd6dafu : i == 2 ? 0xa7283db6u : i == 3 ? 0x62f210e6u
+             : i == 4 ? 0x0ada0afbu : i == 5 ? 0xef7f0b0cu : i == 6 ? 0x2d592544u : 0x20fd6e90u;
     }
 };
 
@@ -265,9 +273,9 @@ SB_HD Fp<P> from_mont(const Fp<P> &a) {
     return mul(a, o);
 }
 
-// a^(p-2) (Fermat).  Used only off the hot path (normalisation, constants).
+// a^(p-2) (Fermat): 254 dependent squarings, ~0.26 ms of latency for one thread on a B200 (profiles/r02n).  Kept as the cross-check of inv().
 template <class P>
-SB_HD Fp<P> inv(const Fp<P> &a) {
+SB_HD Fp<P> inv_fermat(const Fp<P> &a) {
     Fp<P> acc = Fp<P>::one();
     for (int i = 255; i >= 0; i--) {
         acc = sqr(acc);
@@ -277,6 +285,67 @@ SB_HD Fp<P> inv(const Fp<P> &a) {
         if ((w >> (i & 31)) & 1) acc = mul(acc, a);
     }
     return acc;
+}
+
+// a^-1 (0 for a = 0) by the binary extended Euclid: at most ~2 * 254 rounds of a 256-bit compare / subtract / shift and no product, against the
+// 380 dependent products of Fermat's exponentiation -- the batch inversions and normalisations that call this are single latency chains.
+// Invariants for the integer A = a.v (the Montgomery representation): x1 * A = u and x2 * A = v (mod p), v odd; the loop ends with u = 0,
+// v = gcd = 1 and x2 = A^-1 = a^-1 R^-1, which one product with R^3 turns into the Montgomery form a^-1 R.
+template <class P>
+SB_HD Fp<P> inv(const Fp<P> &a) {
+    using namespace ptx;
+    uint32_t u[8], v[8];
+    Fp<P> x1 = Fp<P>::zero(), x2 = Fp<P>::zero();
+    x1.v[0] = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        u[i] = a.v[i];
+        v[i] = P::mod(i);
+    }
+    while ((u[0] | u[1] | u[2] | u[3] | u[4] | u[5] | u[6] | u[7]) != 0) {
+        if (u[0] & 1) {
+            uint32_t d[8];
+            d[0] = sub_cc(u[0], v[0]);
+#pragma unroll
+            for (int i = 1; i < 8; i++) d[i] = subc_cc(u[i], v[i]);
+            const uint32_t lt = subc(0, 0);  // all-ones iff u < v
+            if (lt) {                        // (u, v, x1, x2) <- (v - u, u, x2 - x1, x1)
+                const Fp<P> t = sub(x2, x1);
+                x2 = x1;
+                x1 = t;
+                uint32_t e[8];
+                e[0] = sub_cc(v[0], u[0]);
+#pragma unroll
+                for (int i = 1; i < 8; i++) e[i] = subc_cc(v[i], u[i]);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    v[i] = u[i];
+                    u[i] = e[i];
+                }
+            } else {
+                x1 = sub(x1, x2);
+#pragma unroll
+                for (int i = 0; i < 8; i++) u[i] = d[i];
+            }
+        }
+        // u is even: halve it, and x1 with it (x1 / 2 mod p = (x1 + p) / 2 for odd x1; x1 + p < 2^255)
+#pragma unroll
+        for (int i = 0; i < 7; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
+        u[7] >>= 1;
+        const uint32_t odd = 0u - (x1.v[0] & 1u);
+        uint32_t h[8];
+        h[0] = add_cc(x1.v[0], P::mod(0) & odd);
+#pragma unroll
+        for (int i = 1; i < 7; i++) h[i] = addc_cc(x1.v[i], P::mod(i) & odd);
+        h[7] = addc(x1.v[7], P::mod(7) & odd);
+#pragma unroll
+        for (int i = 0; i < 7; i++) x1.v[i] = (h[i] >> 1) | (h[i + 1] << 31);
+        x1.v[7] = h[7] >> 1;
+    }
+    Fp<P> r3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r3.v[i] = P::r3(i);
+    return mul(x2, r3);
 }
 
 typedef Fp<FrParams> fr_t;

@@ -32,6 +32,7 @@
 namespace sb {
 
 void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_affine[64]);
+void host_bucket_combine(const uint8_t *fin, int n_bits, int shift, int x_slot, uint8_t out_xyzz[128]);
 
 static const uint32_t INVALID_KEY = 0xffffffffu;
 // chunk length of reduce levels >= 2: these levels are chains of dependent EC additions on few threads, so short chunks (more, smaller
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                                                        uint32_t *svals) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    // warp-uniform trip count so that every lane reaches the match_any below
+    // warp-uniform trip count so that every lane reaches the shuffles / ballots below
     const uint64_t n_all = n * sh.batch;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_all; base += stride) {
         const uint64_t gi = base + lane;
@@ -102,15 +103,20 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
             }
             if (w < sh.w_lo) continue;  // warp-uniform: earlier windows only feed the carry
             const uint32_t key = (live && d) ? (sh.tab_stride ? piece * sh.B : (w - sh.w_lo) * sh.B) + d - 1 : INVALID_KEY;
-            // warp aggregation: one atomic per distinct key per warp (hot buckets stay cheap)
-            const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            const uint32_t leader = __ffs(peers) - 1;
+            // warp aggregation by RUNS of equal keys in neighbouring lanes: one atomic per run.  Equal scalars sit in neighbouring rows (constant and
+            // selector-like columns, the sorted permuted lookup columns), so runs catch the hot buckets; match.any would also catch scattered
+            // duplicates but costs ~70 cycles of a shared unit per digit (ncu: 89 % busy, profiles/r02l), twice the whole histogram otherwise.
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+            const uint32_t leader = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));       // head of my run
+            const uint32_t after = heads & ~(0xffffffffu >> (31u - lane));                    // heads above my lane
+            const uint32_t run_end = after ? (uint32_t)__ffs(after) - 1u : 32u;               // first lane of the next run
             uint32_t pos = 0;
-            if (lane == leader && key != INVALID_KEY) pos = atomicAdd(counts + key, __popc(peers));
+            if (lane == leader && key != INVALID_KEY) pos = atomicAdd(counts + key, run_end - leader);
             if (SCATTER) {
                 pos = __shfl_sync(0xffffffffu, pos, leader);
                 if (key != INVALID_KEY) {
-                    pos += __popc(peers & ((1u << lane) - 1));
+                    pos += lane - leader;
                     svals[pos] = (uint32_t)(sh.tab_stride ? sh.piece_off[piece & 7] + w * sh.tab_stride + i : i) | (neg << 31);
                 }
             }
@@ -520,6 +526,61 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const uint4 *seg_su
     if (tid == 0) store_xyzz(win_sums + 8 * (uint64_t)w, acc);
 }
 
+// ------------------------------------------------------------------ 4': bucket reduction as a tree (default)
+// The running sums above are chains of dependent additions on few threads (16 + ~30 + 7 per launch set, ~4 us each: 0.5 ms per set whatever the
+// load).  Here R = sum_i (i + 1) B_i = T + sum_b 2^b S_b with T = sum_i B_i and S_b = sum_{i : bit b of i set} B_i, and (T, S_0 .. S_{l-1}) of a
+// block of 2^l consecutive buckets follow from its two halves by l + 1 independent additions (T = T_L + T_R, S_b = S_b^L + S_b^R, S_{l-1} = T_R):
+// a CTA folds 256 buckets in 8 steps of at most one addition per thread (2 additions per bucket in total, like the running sums), a second launch
+// folds the <= 256 node records of a set (CTA 0: the same tree over the nodes' T for the upper bits; CTAs 1..8: plain sums of the nodes' S_b), and
+// the host finishes with the Horner fold over <= 16 bits that it does for windows anyway (host_g1.cpp).  Depth: 16 additions.
+static const int BT_LOG = 8, BT = 1 << BT_LOG;         // buckets per CTA
+static const int BT_SLOTS = BT_LOG + 1;                // node record: T, S_0 .. S_7
+static const int BT_FIN = 2 * BT_LOG + 2;              // per set: T, S_0 .. S_15, and the plain sum of the Q vector when a running-sum level ran first
+static const int BT_THREADS = BT / 2;                  // every step has at most BT / 2 additions
+static const size_t BT_SMEM = (size_t)(BT + 3 * BT / 4) * 128;   // records of 2 buckets (BT points) | records of 4 buckets (3 BT / 4 points), ping-pong
+extern __shared__ uint4 bt_smem[];
+__global__ void __launch_bounds__(BT_THREADS, 3) msm_bucket_tree_kernel(const uint4 *in, uint64_t job_stride, uint32_t elem_stride, uint32_t m, uint32_t with_bits,
+                                                                        uint32_t colsum, uint4 *out, uint32_t out_job_stride, uint32_t out_node_stride, uint32_t dst_slot0,
+                                                                        uint32_t dst_bits0) {
+    uint4 *buf[2] = {bt_smem + BT * 8, bt_smem};   // buf[1] (BT points) takes the records of 2 buckets, buf[0] those of 4, ...
+    const uint32_t tid = threadIdx.x, job = blockIdx.y;
+    // colsum: every CTA of the row reads the same m records, CTA x their slot x; only CTA 0 keeps the bit sums
+    const uint32_t node = colsum ? 0u : blockIdx.x, src_off = colsum ? blockIdx.x : 0u;
+    const bool bits = with_bits && (!colsum || blockIdx.x == 0);
+    {   // records of 2 buckets straight from global memory: T = V_2t + V_2t+1, S_0 = V_2t+1
+        const uint64_t e = (uint64_t)node * BT + 2 * tid;
+        const uint4 *src = in + 8 * ((uint64_t)job * job_stride + src_off);
+        xyzz_t a = xyzz_t::identity(), b = xyzz_t::identity();
+        if (e < m) a = load_xyzz(src + 8 * (e * elem_stride));
+        if (e + 1 < m) b = load_xyzz(src + 8 * ((e + 1) * elem_stride));
+        if (bits) store_xyzz(buf[1] + 8 * (2 * tid + 1), b);
+        add(a, b);
+        store_xyzz(buf[1] + 8 * (bits ? 2 * tid : tid), a);
+    }
+    __syncthreads();
+    int cur = 1;
+    for (uint32_t l = 1; l < (uint32_t)BT_LOG; l++) {   // records of 2^l buckets -> records of 2^(l+1)
+        const uint32_t per_in = bits ? l + 1 : 1, per_out = bits ? l + 2 : 1, n_out = (uint32_t)BT >> (l + 1);
+        if (tid < n_out * per_in) {
+            const uint32_t j = tid / per_in, q = tid - j * per_in;
+            xyzz_t a = load_xyzz(buf[cur] + 8 * ((2 * j) * per_in + q));
+            const xyzz_t b = load_xyzz(buf[cur] + 8 * ((2 * j + 1) * per_in + q));
+            if (bits && q == 0) store_xyzz(buf[cur ^ 1] + 8 * (j * per_out + l + 1), b);  // S_l = T of the upper half
+            add(a, b);
+            store_xyzz(buf[cur ^ 1] + 8 * (j * per_out + q), a);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    uint4 *dst = out + 8 * ((uint64_t)job * out_job_stride + (uint64_t)node * out_node_stride);
+    const uint32_t n_rec = bits ? (uint32_t)BT_SLOTS : 1u;
+    for (uint32_t i = tid; i < n_rec * 8; i += BT_THREADS) {
+        const uint32_t slot = i >> 3;
+        const uint32_t d = slot == 0 ? dst_slot0 + (colsum ? blockIdx.x : 0u) : dst_bits0 + slot - 1;
+        dst[8 * d + (i & 7)] = buf[cur][i];
+    }
+}
+
 // ------------------------------------------------------------------ fixed-base window tables
 // tables[w * stride + i] = 2^(c w) * P_i (affine) for w < W: with them every window of the scalar addresses the SAME bucket
 // set, so the window size can grow (c = 20: 13 windows instead of 16) at no bucket-reduction cost.  One thread per base: the
@@ -741,7 +802,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     uint64_t slots = slots_a;
     uint32_t *kin = d_keys_a, *kout = d_keys_b;
     uint4 *pin = d_pts_a, *pout = d_pts_b;
-    static const uint64_t CTA_SCAN_MAX = 16384;  // below this many slots the levels are latency-bound: one CTA-wide scan per 256 slots
+    const uint64_t CTA_SCAN_MAX = (uint64_t)ctx->tune.msm_cta_scan_max;  // below this many slots the levels are latency-bound: one CTA-wide scan per 256 slots
     while (slots > FINAL_MAX) {
         uint64_t nch;
         if (slots <= CTA_SCAN_MAX && !ctx->tune.msm_no_cta_scan) {
@@ -759,7 +820,46 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
 
     // ---- 4: bucket reduction ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[3], st));
-    {
+    const bool tree = !ctx->tune.msm_no_bucket_tree && (size_t)sh.Wb * BT_FIN * 128 + 64 <= ctx->pinned_bytes;
+    uint32_t tree_bits = 0, tree_shift = 0;   // R = X + 2^shift * sum_{b < bits} 2^b S_b
+    uint4 *d_fin = nullptr;
+    if (tree) {
+        const uint64_t cap = (uint64_t)sh.Wb * (sh.B >> 1) + 128;
+        const uint4 *bP = d_buckets, *bQ = nullptr;
+        uint32_t m = sh.B;
+        if (m > (uint32_t)BT * BT) {   // more than 2^16 buckets per set: one running-sum level first (segments of m / 2^16 buckets per thread)
+            tree_shift = ilog2_floor(m) - 2 * BT_LOG;
+            const uint32_t threads = sh.Wb * (m >> tree_shift);
+            SB_LAUNCH(ctx, msm_bucket_level_kernel<false>, (threads + 127) / 128, 128, 0, st, bP, bQ, sh.Wb, m, tree_shift, 0u, d_seg, d_seg + 8 * cap);
+            bP = d_seg;
+            bQ = d_seg + 8 * cap;
+            m >>= tree_shift;
+        }
+        tree_bits = ilog2_floor(m);
+        const uint32_t n_nodes = (m + BT - 1) / BT;
+        uint4 *d_nodes;
+        SB_TRY(scratch_get(ctx, "msm_fin", ((uint64_t)sh.Wb * BT_FIN + 8) * 128, (void **)&d_fin));
+        SB_TRY(scratch_get(ctx, "msm_nodes", (2 * (uint64_t)sh.Wb * n_nodes * BT_SLOTS + 8) * 128, (void **)&d_nodes));
+        static bool attr_set = false;
+        if (!attr_set) {
+            SB_CUDA_TRY(cudaFuncSetAttribute(msm_bucket_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+            attr_set = true;
+        }
+        const size_t smem = BT_SMEM;
+        if (n_nodes == 1) {
+            SB_LAUNCH(ctx, msm_bucket_tree_kernel, dim3(1, sh.Wb), BT_THREADS, smem, st, bP, (uint64_t)m, 1u, m, 1u, 0u, d_fin, (uint32_t)BT_FIN, 0u, 0u, 1u);
+        } else {
+            SB_LAUNCH(ctx, msm_bucket_tree_kernel, dim3(n_nodes, sh.Wb), BT_THREADS, smem, st, bP, (uint64_t)m, 1u, m, 1u, 0u, d_nodes, n_nodes * BT_SLOTS, (uint32_t)BT_SLOTS, 0u, 1u);
+            SB_LAUNCH(ctx, msm_bucket_tree_kernel, dim3(BT_SLOTS, sh.Wb), BT_THREADS, smem, st, (const uint4 *)d_nodes, (uint64_t)n_nodes * BT_SLOTS, (uint32_t)BT_SLOTS, n_nodes, 1u, 1u,
+                      d_fin, (uint32_t)BT_FIN, 0u, 0u, (uint32_t)BT_SLOTS);
+        }
+        if (bQ) {   // plain sum of the Q vector (m = 2^16 elements per set) into slot BT_FIN - 1
+            uint4 *d_nodes_q = d_nodes + 8 * ((uint64_t)sh.Wb * n_nodes * BT_SLOTS);
+            SB_LAUNCH(ctx, msm_bucket_tree_kernel, dim3(n_nodes, sh.Wb), BT_THREADS, smem, st, bQ, (uint64_t)m, 1u, m, 0u, 0u, d_nodes_q, n_nodes * BT_SLOTS, (uint32_t)BT_SLOTS, 0u, 1u);
+            SB_LAUNCH(ctx, msm_bucket_tree_kernel, dim3(1, sh.Wb), BT_THREADS, smem, st, (const uint4 *)d_nodes_q, (uint64_t)n_nodes * BT_SLOTS, (uint32_t)BT_SLOTS, n_nodes, 0u, 1u,
+                      d_fin, (uint32_t)BT_FIN, 0u, (uint32_t)BT_FIN - 1, 0u);
+        }
+    } else {
         // scratch layout (XYZZ slots): P/Q ping-pong of the level kernels, CTA partials, window sums
         const uint64_t cap = (uint64_t)sh.Wb * (sh.B >> 1) + 128;
         uint4 *bufP[2] = {d_seg, d_seg + 8 * cap}, *bufQ[2] = {d_seg + 16 * cap, d_seg + 24 * cap};
@@ -787,7 +887,8 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
 
     // ---- 5: window sums -> host fold ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[4], st));
-    SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_win, (size_t)sh.Wb * 128, cudaMemcpyDeviceToHost, st));
+    if (tree) SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_fin, (size_t)sh.Wb * BT_FIN * 128, cudaMemcpyDeviceToHost, st));
+    else SB_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, d_win, (size_t)sh.Wb * 128, cudaMemcpyDeviceToHost, st));
     // the number of non-zero signed digits that were sorted and accumulated (the scan's grand total): the level-1 additions actually performed
     uint32_t *h_total = (uint32_t *)((uint8_t *)ctx->pinned + ctx->pinned_bytes - 64);
     SB_CUDA_TRY(cudaMemcpyAsync(h_total, d_counts + nb, 4, cudaMemcpyDeviceToHost, st));
@@ -798,6 +899,15 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     ctx->acc_msm_digits += *h_total;
     ctx->acc_msm_sets++;
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
+    if (tree) {   // per set: X + 2^shift * sum_b 2^b S_b, written back over the head of the pinned buffer as one XYZZ point per set (set j's record starts
+                  // at j * BT_FIN * 128 >= j * 128, so the compaction never overtakes its input)
+        uint8_t *hp = (uint8_t *)ctx->pinned;
+        for (uint32_t j = 0; j < sh.Wb; j++) {
+            uint8_t pt[128];
+            host_bucket_combine(hp + (size_t)j * BT_FIN * 128, (int)tree_bits, (int)tree_shift, tree_shift ? BT_FIN - 1 : 0, pt);
+            memcpy(hp + (size_t)j * 128, pt, 128);
+        }
+    }
     if (w_hi >= 0) memcpy(out_affine, ctx->pinned, (size_t)sh.Wb * 128);
     else if (tabs)
         for (uint32_t j = 0; j < batch; j++) host_fold_windows((const uint8_t *)ctx->pinned + (size_t)j * 128, 1, (int)sh.c, out_affine + (size_t)j * 64);

@@ -517,6 +517,7 @@ struct Query {
     Fr point;
     const void *d_poly;
     Fr eval;
+    const void *d_lagr = nullptr;  // the same polynomial's values on the size-n subgroup, when the prover still holds them
 };
 
 int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &tr, const std::vector<Query> &queries, cudaStream_t st) {
@@ -556,6 +557,114 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
     SB_TRY(scratch_get(ctx, "sh_nx", n * 32, &d_nx));
     SB_TRY(scratch_get(ctx, "sh_lx", n * 32, &d_lx));
     SB_TRY(scratch_get(ctx, "sh_invd", n * 32, &d_invd));
+    // The whole argument in the evaluation domain H itself (default).  Almost every opened polynomial still exists as its values on H (advice,
+    // fixed and sigma columns, the grand products, the permuted lookup columns), so N_i on H is a linear combination of those vectors -- no
+    // transform -- plus ONE transform for the members held as coefficients only (the folded quotient and the random polynomial, both in the set
+    // {x}); h and the opening quotient stay in the evaluation domain and are committed over the Lagrange basis (deg < n: the same points).
+    // 1 transform instead of 8.  Needs every opening point outside H (a point of H would be a root of Z_T on H): else the coset path below.
+    bool on_h = !ctx->tune.no_shplonk_lagrange && pk->srs->d_g_lagrange != nullptr;
+    for (const Fr &p : super_points) {
+        Fr t = p;
+        for (uint32_t i = 0; i < pk->k; i++) t = hfr::mul(t, t);
+        if (t == hfr::ONE) on_h = false;
+    }
+    if (on_h) {
+        std::map<int, const void *> lagr;
+        for (const Query &q : queries)
+            if (q.d_lagr) lagr[q.poly_id] = q.d_lagr;
+        const std::vector<Fr> super(super_points.begin(), super_points.end());
+        uint8_t *d_m;
+        SB_TRY(scratch_get(ctx, "sh_m", sets.size() * n * 32, (void **)&d_m));
+        {
+            std::vector<fr_t> sd;
+            for (const Fr &p : super) sd.push_back(to_dev(p));
+            SB_TRY(fr_vanish(ctx, pk->omega_pows, sd, d_invd, n, st));
+            SB_TRY(fr_batch_invert(ctx, d_invd, n, st));
+        }
+        std::vector<std::vector<std::vector<Fr>>> low(sets.size());
+        auto complement = [&](const RSet &s) {
+            std::vector<Fr> c;
+            for (const Fr &p : super) {
+                bool in = false;
+                for (const Fr &q : s.pts) in = in || (q == p);
+                if (!in) c.push_back(p);
+            }
+            return c;
+        };
+        Fr v_pow = hfr::ONE;
+        for (size_t si = 0; si < sets.size(); si++) {
+            RSet &s = sets[si];
+            Fr y_pow = hfr::ONE;
+            std::vector<Fr> head(s.pts.size(), hfr::ZERO);
+            std::vector<const void *> lag_polys, coef_polys;
+            std::vector<fr_t> lag_coeffs, coef_coeffs;
+            const std::vector<std::vector<Fr>> basis = lagrange_basis(s.pts);
+            for (size_t mi = 0; mi < s.members.size(); mi++) {
+                const int pid = s.members[mi];
+                std::vector<Fr> evs;
+                for (const Fr &p : s.pts) evs.push_back(find_eval(pid, p));
+                std::vector<Fr> r = lagrange_interpolate(basis, evs);
+                low[si].push_back(r);
+                for (size_t i = 0; i < r.size(); i++) head[i] = hfr::add(head[i], hfr::mul(r[i], y_pow));
+                if (lagr.count(pid)) { lag_polys.push_back(lagr[pid]); lag_coeffs.push_back(to_dev(y_pow)); }
+                else { coef_polys.push_back(polys[pid]); coef_coeffs.push_back(to_dev(y_pow)); }
+                y_pow = hfr::mul(y_pow, y);
+            }
+            std::vector<fr_t> head_d;
+            for (const Fr &h : head) head_d.push_back(to_dev(h));
+            SB_REQUIRE(head_d.size() <= 8, "shplonk: rotation sets of more than 8 points are not supported");
+            void *d_mi = d_m + si * n * 32;   // M_i = sum_m y^m p_m on H (kept for the opening quotient)
+            if (!coef_polys.empty()) {
+                SB_TRY(fr_lincomb(ctx, d_nx, coef_polys, coef_coeffs, {}, n, false, st));
+                SB_TRY(ntt_run(ctx, d_nx, (const uint8_t *)pk->dom->omega.v, pk->k, st));
+                lag_polys.push_back(d_nx);
+                lag_coeffs.push_back(to_dev(hfr::ONE));
+            }
+            SB_TRY(fr_lincomb(ctx, d_mi, lag_polys, lag_coeffs, {}, n, false, st));
+            std::vector<fr_t> comp;
+            for (const Fr &p : complement(s)) comp.push_back(to_dev(p));
+            SB_TRY(fr_div_combine(ctx, d_hx, d_mi, d_invd, pk->omega_pows, comp, to_dev(v_pow), n, si == 0, st, &head_d));
+            v_pow = hfr::mul(v_pow, v);
+        }
+        uint8_t pt[64];
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_hx, n, pt, st));
+        if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
+        const Fr u = tr.squeeze();
+        {   // u in H would make X - u vanish on the evaluation domain: negligible, but not silently wrong
+            Fr t = u;
+            for (uint32_t i = 0; i < pk->k; i++) t = hfr::mul(t, t);
+            SB_REQUIRE(!(t == hfr::ONE), "shplonk: the opening challenge lies in the evaluation domain");
+        }
+        std::vector<const void *> lc_polys;
+        std::vector<fr_t> lc_coeffs;
+        Fr const_term = hfr::ZERO, z0 = hfr::ONE;
+        v_pow = hfr::ONE;
+        for (size_t si = 0; si < sets.size(); si++) {
+            Fr z_i = hfr::ONE;
+            for (const Fr &p : complement(sets[si])) z_i = hfr::mul(z_i, hfr::sub(u, p));
+            if (si == 0) z0 = z_i;
+            const Fr scale = hfr::mul(z_i, v_pow);
+            Fr y_pow = hfr::ONE;
+            for (size_t mi = 0; mi < sets[si].members.size(); mi++) {
+                const_term = hfr::add(const_term, hfr::mul(hfr::mul(scale, y_pow), eval_small(low[si][mi], u)));
+                y_pow = hfr::mul(y_pow, y);
+            }
+            lc_polys.push_back(d_m + si * n * 32);
+            lc_coeffs.push_back(to_dev(scale));
+            v_pow = hfr::mul(v_pow, v);
+        }
+        Fr zt = hfr::ONE;
+        for (const Fr &p : super) zt = hfr::mul(zt, hfr::sub(u, p));
+        lc_polys.push_back(d_hx);
+        lc_coeffs.push_back(to_dev(hfr::neg(zt)));
+        SB_TRY(fr_lincomb(ctx, d_lx, lc_polys, lc_coeffs, {}, n, false, st));
+        SB_TRY(fr_vanish(ctx, pk->omega_pows, {to_dev(u)}, d_nx, n, st));
+        SB_TRY(fr_batch_invert(ctx, d_nx, n, st));
+        SB_TRY(fr_open_quotient(ctx, d_lx, d_lx, d_nx, to_dev(const_term), to_dev(hfr::inv(z0)), n, st));
+        SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_lx, n, pt, st));
+        if (!tr.write_point(pt)) { set_last_error("shplonk: opening commitment is the identity"); return SB_ERR_ARG; }
+        return SB_OK;
+    }
     // h(X) = sum_i v^i N_i(X) / Z_{S_i}(X), all divisions exact.  Work on the coset g*H: E = sum_i v^i NTT(g^j N_i) * (1 / Z_{S_i}) is
     // accumulated in the evaluation domain, so the whole sum needs ONE inverse NTT, and 1 / Z_{S_i} = (1 / Z_T) * prod_{p in T \ S_i}(x - p)
     // with T the super set of opening points, so ONE batch inversion serves every rotation set.
@@ -961,8 +1070,12 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     SB_TRY(scratch_get(ctx, "pf_inst_poly", n * 32, &d_inst_poly));
     SB_CUDA_TRY(cudaMemsetAsync(d_inst, 0, n * 32, st));
     SB_CUDA_TRY(cudaMemcpyAsync(d_inst, inst.data(), n_inst * 32, cudaMemcpyHostToDevice, st));
-    SB_CUDA_TRY(cudaMemcpyAsync(d_inst_poly, d_inst, n * 32, cudaMemcpyDeviceToDevice, st));
-    SB_TRY(dom_l2c(ctx, d, d_inst_poly, st));
+    // few instance values: their coset values come from rotations of the key's l_0 coset (prover_kernels.cu::instance_coset), no transform
+    const bool inst_direct = n_inst <= 12 && !ctx->tune.no_inst_direct;
+    if (!inst_direct) {
+        SB_CUDA_TRY(cudaMemcpyAsync(d_inst_poly, d_inst, n * 32, cudaMemcpyDeviceToDevice, st));
+        SB_TRY(dom_l2c(ctx, d, d_inst_poly, st));
+    }
     std::vector<void *> adv(A), adv_poly(A);
     void *d_random_early = nullptr;
     {
@@ -1023,7 +1136,12 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     }
     SB_TRY(side_after_main());  // advice / instance cosets on the side stream, under the commitment below
     for (int c = 0; c < A; c++) SB_TRY(side_cosets((size_t)c, adv_poly[c]));
-    SB_TRY(side_cosets((size_t)A, d_inst_poly));
+    if (inst_direct) {
+        for (uint32_t jl = 0; jl < co_per; jl++)
+            SB_TRY(instance_coset(ctx, (const uint8_t *)pk->l0 + (size_t)own[jl] * n * 32, d_inst, (uint32_t)n_inst, n, dyn_slot(jl, (size_t)A), st2));
+    } else {
+        SB_TRY(side_cosets((size_t)A, d_inst_poly));
+    }
     // The vanishing argument's random polynomial depends on no challenge, only on the RNG stream: a CLONE of the RNG is advanced past every
     // draw that precedes its seed (all data-independent counts), so the polynomial can be generated now and committed in the SAME launch set
     // as the advice columns (mixed-basis batch: advice over the Lagrange tables, the random polynomial over the monomial tables).  The main
@@ -1071,7 +1189,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     lcols[L_OMEGA] = pk->omega_pows;
 
     // ---- lookups: compress, permute, commit
-    struct LookupState { void *c_in, *c_tab, *p_in, *p_tab, *in_poly, *tab_poly, *z_poly; };
+    struct LookupState { void *c_in, *c_tab, *p_in, *p_tab, *in_poly, *tab_poly, *z_poly, *z_vals = nullptr; };
     std::vector<LookupState> lks(cs.lookups.size());
     for (size_t li = 0; li < cs.lookups.size(); li++) {
         LookupState &L = lks[li];
@@ -1114,7 +1232,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     //      scanned from 1 and scaled afterwards by the running boundary value (read back once), which is the same field element.
     const int chunk = cs.degree - 2;
     const int n_sets = (P + chunk - 1) / chunk;
-    struct PermSet { void *z_poly; int first, count; };
+    struct PermSet { void *z_poly; int first, count; void *z_vals = nullptr; };
     std::vector<PermSet> psets(n_sets);
     if (n_sets + (int)lks.size() > 0) {  // a circuit with neither copy constraints nor lookups has no grand product to commit
         const int n_z = n_sets + (int)lks.size();
@@ -1179,12 +1297,14 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(side_after_main());
         for (int s = 0; s < n_sets; s++) {
             PermSet &S = psets[s];
+            S.z_vals = d_zall + (size_t)s * n * 32;   // the values on the subgroup stay valid to the end of the proof (SHPLONK reads them)
             SB_CUDA_TRY(cudaMemcpyAsync(S.z_poly, d_zall + (size_t)s * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
             SB_TRY(l2c_repl(S.z_poly, st2));
             SB_TRY(side_cosets((size_t)A + 1 + s, S.z_poly));
         }
         for (size_t li = 0; li < lks.size(); li++) {
             LookupState &L = lks[li];
+            L.z_vals = d_zall + (size_t)(n_sets + (int)li) * n * 32;
             SB_CUDA_TRY(cudaMemcpyAsync(L.z_poly, d_zall + (size_t)(n_sets + (int)li) * n * 32, n * 32, cudaMemcpyDeviceToDevice, st2));
             SB_TRY(l2c_repl(L.z_poly, st2));
             SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li, L.z_poly));
@@ -1386,28 +1506,28 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     auto pid = [&](const void *p) { auto it = ids.find(p); if (it != ids.end()) return it->second; return ids[p] = next_id++; };
     for (size_t i = 0; i < cs.advice_q.size(); i++) {
         const void *p = adv_poly[cs.advice_q[i].first];
-        q.push_back({pid(p), rotate(x, omega, omega_inv, cs.advice_q[i].second), p, ev[i_adv[i]]});
+        q.push_back({pid(p), rotate(x, omega, omega_inv, cs.advice_q[i].second), p, ev[i_adv[i]], adv[cs.advice_q[i].first]});
     }
     for (int s = 0; s < n_sets; s++) {
-        q.push_back({pid(psets[s].z_poly), x, psets[s].z_poly, ev[i_perm[s][0]]});
-        q.push_back({pid(psets[s].z_poly), x_next, psets[s].z_poly, ev[i_perm[s][1]]});
+        q.push_back({pid(psets[s].z_poly), x, psets[s].z_poly, ev[i_perm[s][0]], psets[s].z_vals});
+        q.push_back({pid(psets[s].z_poly), x_next, psets[s].z_poly, ev[i_perm[s][1]], psets[s].z_vals});
     }
-    for (int s = n_sets - 2; s >= 0; s--) q.push_back({pid(psets[s].z_poly), x_last, psets[s].z_poly, ev[i_perm[s][2]]});
+    for (int s = n_sets - 2; s >= 0; s--) q.push_back({pid(psets[s].z_poly), x_last, psets[s].z_poly, ev[i_perm[s][2]], psets[s].z_vals});
     for (size_t li = 0; li < lks.size(); li++) {
         const LookupState &L = lks[li];
-        q.push_back({pid(L.z_poly), x, L.z_poly, ev[i_lk[li][0]]});
-        q.push_back({pid(L.in_poly), x, L.in_poly, ev[i_lk[li][2]]});
-        q.push_back({pid(L.tab_poly), x, L.tab_poly, ev[i_lk[li][4]]});
-        q.push_back({pid(L.in_poly), x_prev, L.in_poly, ev[i_lk[li][3]]});
-        q.push_back({pid(L.z_poly), x_next, L.z_poly, ev[i_lk[li][1]]});
+        q.push_back({pid(L.z_poly), x, L.z_poly, ev[i_lk[li][0]], L.z_vals});
+        q.push_back({pid(L.in_poly), x, L.in_poly, ev[i_lk[li][2]], L.p_in});
+        q.push_back({pid(L.tab_poly), x, L.tab_poly, ev[i_lk[li][4]], L.p_tab});
+        q.push_back({pid(L.in_poly), x_prev, L.in_poly, ev[i_lk[li][3]], L.p_in});
+        q.push_back({pid(L.z_poly), x_next, L.z_poly, ev[i_lk[li][1]], L.z_vals});
     }
     for (size_t i = 0; i < cs.fixed_q.size(); i++) {
         const void *p = pk->fixed_polys[cs.fixed_q[i].first];
-        q.push_back({pid(p), rotate(x, omega, omega_inv, cs.fixed_q[i].second), p, ev[i_fix[i]]});
+        q.push_back({pid(p), rotate(x, omega, omega_inv, cs.fixed_q[i].second), p, ev[i_fix[i]], pk->fixed_values[cs.fixed_q[i].first]});
     }
-    for (int j = 0; j < P; j++) q.push_back({pid(pk->sigma_polys[j]), x, pk->sigma_polys[j], ev[i_sig[j]]});
-    q.push_back({pid(d_hfold), x, d_hfold, ev[i_h]});
-    q.push_back({pid(d_random), x, d_random, ev[i_rand]});
+    for (int j = 0; j < P; j++) q.push_back({pid(pk->sigma_polys[j]), x, pk->sigma_polys[j], ev[i_sig[j]], pk->sigma_values[j]});
+    q.push_back({pid(d_hfold), x, d_hfold, ev[i_h], nullptr});
+    q.push_back({pid(d_random), x, d_random, ev[i_rand], nullptr});
     int32_t rc_sh = shplonk(ctx, pk, comm, tr, q, st);
     mark();  // [9] SHPLONK
     return rc_sh;

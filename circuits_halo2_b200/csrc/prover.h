@@ -26,13 +26,15 @@ int32_t fr_lincomb(sb_ctx *ctx, void *d_out, const std::vector<const void *> &po
 int32_t fr_vanish(sb_ctx *ctx, const void *d_x, const std::vector<fr_t> &roots, void *d_out, size_t n, cudaStream_t st);
 // acc[j] (+)= scale * f[j] * inv_d[j] * prod_{r in comp} (x[j] - r)
 int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_inv_d, const void *d_x, const std::vector<fr_t> &comp, const fr_t &scale, size_t n, bool first,
-                       cudaStream_t st);
+                       cudaStream_t st, const std::vector<fr_t> *head = nullptr);
+int32_t fr_open_quotient(sb_ctx *ctx, void *d_out, const void *d_f, const void *d_inv_d, const fr_t &cst, const fr_t &scale, size_t n, cudaStream_t st);
 
 // sparse cells -> dense columns (device copies of the cell / value arrays; indices validated by the caller)
 int32_t scatter_cells(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, const void *d_values, size_t n_cells, cudaStream_t st);
 int32_t sigma_patch(sb_ctx *ctx, void *const *col_ptrs, uint32_t n_cols, const void *d_cells, size_t n_cells, const void *d_omega_pows, const fr_t *delta_pows, cudaStream_t st);
 
 // out[q * n + i] = sum_s m[q * 8 + s] * slots[s][i]: the per-coset data of the quotient -> h's coefficient pieces
+int32_t instance_coset(sb_ctx *ctx, const void *d_l0_coset, const void *d_vals, uint32_t n_vals, size_t n, void *d_out, cudaStream_t st);
 int32_t fr_coset_combine(sb_ctx *ctx, const std::vector<const void *> &slots, const fr_t *m, void *d_out, size_t n, cudaStream_t st);
 
 // ---- expr.cu: expression DAGs compiled to a register program, evaluated over whole columns ---

@@ -115,8 +115,66 @@ __global__ void __launch_bounds__(128) fr_batch_invert_kernel(uint4 *a, uint4 *t
         iv = mul(iv, x);
     }
 }
+// Two-level form for long vectors.  The single kernel above spends 310 products of a Fermat inversion per 32 elements (3 n + 10 n products); here a
+// thread owns only 8 elements, strided by 32 so that a warp reads 1 KB rows, multiplies them up (n products), the 8x shorter vector of thread totals
+// is inverted by the kernel above, and a second pass rebuilds the prefixes in registers and back-substitutes (3 n products): 4 n + 1.6 n products.
+static const int BINV_C1 = 8;
+__global__ void __launch_bounds__(128) fr_binv_totals_kernel(const uint4 *a, uint4 *tot, uint64_t n) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t base = (t >> 5) * (32 * BINV_C1) + (t & 31);
+    if (base >= n) return;
+    fr_t acc = fr_t::one();
+#pragma unroll
+    for (int q = 0; q < BINV_C1; q++) {
+        const uint64_t i = base + 32 * q;
+        if (i < n) {
+            const fr_t x = load_fp<FrParams>(a + 2 * i);
+            if (!x.is_zero()) acc = mul(acc, x);
+        }
+    }
+    store_fp(tot + 2 * t, acc);
+}
+__global__ void __launch_bounds__(128) fr_binv_apply_kernel(uint4 *a, const uint4 *tot_inv, uint64_t n) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t base = (t >> 5) * (32 * BINV_C1) + (t & 31);
+    if (base >= n) return;
+    fr_t pre[BINV_C1];
+    fr_t acc = fr_t::one();
+#pragma unroll
+    for (int q = 0; q < BINV_C1; q++) {
+        const uint64_t i = base + 32 * q;
+        pre[q] = acc;
+        if (i < n) {
+            const fr_t x = load_fp<FrParams>(a + 2 * i);
+            if (!x.is_zero()) acc = mul(acc, x);
+        }
+    }
+    fr_t iv = load_fp<FrParams>(tot_inv + 2 * t);
+#pragma unroll
+    for (int q = BINV_C1 - 1; q >= 0; q--) {
+        const uint64_t i = base + 32 * q;
+        if (i < n) {
+            const fr_t x = load_fp<FrParams>(a + 2 * i);
+            if (!x.is_zero()) {
+                store_fp(a + 2 * i, mul(iv, pre[q]));
+                iv = mul(iv, x);
+            }
+        }
+    }
+}
 int32_t fr_batch_invert(sb_ctx *ctx, void *d_a, size_t n, cudaStream_t st) {
     if (n == 0) return SB_OK;
+    if (n >= (1u << 16) && !ctx->tune.no_binv2) {
+        const uint64_t warps = (n + 32 * BINV_C1 - 1) / (32 * BINV_C1), t1 = warps * 32;
+        void *d_tot, *d_tmp2;
+        SB_TRY(scratch_get(ctx, "binv_tot", t1 * 32, &d_tot));
+        SB_TRY(scratch_get(ctx, "binv_tmp", t1 * 32, &d_tmp2));
+        SB_LAUNCH(ctx, fr_binv_totals_kernel, (unsigned)((t1 + 127) / 128), 128, 0, st, (const uint4 *)d_a, (uint4 *)d_tot, (uint64_t)n);
+        const uint64_t t2 = (t1 + BINV_CHUNK - 1) / BINV_CHUNK;
+        SB_LAUNCH(ctx, fr_batch_invert_kernel, (unsigned)((t2 + 127) / 128), 128, 0, st, (uint4 *)d_tot, (uint4 *)d_tmp2, t1);
+        SB_LAUNCH(ctx, fr_binv_apply_kernel, (unsigned)((t1 + 127) / 128), 128, 0, st, (uint4 *)d_a, (const uint4 *)d_tot, (uint64_t)n);
+        return SB_OK;
+    }
     void *d_tmp;
     SB_TRY(scratch_get(ctx, "binv_tmp", n * 32, &d_tmp));
     const uint64_t threads = (n + BINV_CHUNK - 1) / BINV_CHUNK;
@@ -650,25 +708,46 @@ int32_t fr_vanish(sb_ctx *ctx, const void *d_x, const std::vector<fr_t> &roots, 
 
 // acc[j] (+)= scale * f[j] * inv_d[j] * prod_{r in comp} (x[j] - r):  f / Z_S on the coset, with 1 / Z_S = (1 / Z_T) * prod over the
 // points of the super set T that are NOT in S (one batch inversion of Z_T serves every rotation set)
-__global__ void fr_div_combine_kernel(uint4 *acc, const uint4 *f, const uint4 *inv_d, const uint4 *x, RootArgs comp, fr_t scale, uint64_t n, int first) {
+// `head` (evaluation-domain form of the sum): f is first reduced by the low-degree interpolant r(x[j]) = sum_q head.r[q] x[j]^q, which the
+// coefficient-domain form subtracts from the leading coefficients instead
+__global__ void fr_div_combine_kernel(uint4 *acc, const uint4 *f, const uint4 *inv_d, const uint4 *x, RootArgs comp, RootArgs head, fr_t scale, uint64_t n, int first) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fr_t v = mul(mul(load_fp<FrParams>(f + 2 * i), load_fp<FrParams>(inv_d + 2 * i)), scale);
-    if (comp.k) {
-        const fr_t xv = load_fp<FrParams>(x + 2 * i);
-        for (uint32_t q = 0; q < comp.k; q++) v = mul(v, sub(xv, comp.r[q]));
+    fr_t fv = load_fp<FrParams>(f + 2 * i);
+    fr_t xv = fr_t::zero();
+    if (comp.k || head.k) xv = load_fp<FrParams>(x + 2 * i);
+    if (head.k) {
+        fr_t r = head.r[head.k - 1];
+        for (uint32_t q = head.k - 1; q-- > 0;) r = add(mul(r, xv), head.r[q]);
+        fv = sub(fv, r);
     }
+    fr_t v = mul(mul(fv, load_fp<FrParams>(inv_d + 2 * i)), scale);
+    for (uint32_t q = 0; q < comp.k; q++) v = mul(v, sub(xv, comp.r[q]));
     if (!first) v = add(v, load_fp<FrParams>(acc + 2 * i));
     store_fp(acc + 2 * i, v);
 }
 int32_t fr_div_combine(sb_ctx *ctx, void *d_acc, const void *d_f, const void *d_inv_d, const void *d_x, const std::vector<fr_t> &comp, const fr_t &scale, size_t n, bool first,
-                       cudaStream_t st) {
-    SB_REQUIRE(comp.size() <= 8, "fr_div_combine: at most 8 complement roots");
-    RootArgs ra;
+                       cudaStream_t st, const std::vector<fr_t> *head) {
+    SB_REQUIRE(comp.size() <= 8 && (!head || head->size() <= 8), "fr_div_combine: at most 8 complement roots / interpolant coefficients");
+    RootArgs ra, ha;
     for (size_t q = 0; q < 8; q++) ra.r[q] = q < comp.size() ? comp[q] : fr_t::zero();
     ra.k = (uint32_t)comp.size();
-    SB_LAUNCH(ctx, fr_div_combine_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_acc, (const uint4 *)d_f, (const uint4 *)d_inv_d, (const uint4 *)d_x, ra, scale,
+    for (size_t q = 0; q < 8; q++) ha.r[q] = head && q < head->size() ? (*head)[q] : fr_t::zero();
+    ha.k = head ? (uint32_t)head->size() : 0u;
+    SB_LAUNCH(ctx, fr_div_combine_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_acc, (const uint4 *)d_f, (const uint4 *)d_inv_d, (const uint4 *)d_x, ra, ha, scale,
               (uint64_t)n, first ? 1 : 0);
+    return SB_OK;
+}
+
+// out[j] = (f[j] - cst) * inv_d[j] * scale: the opening quotient (L(X) - L(u)) / (X - u) in the evaluation domain (inv_d[j] = 1 / (x[j] - u))
+__global__ void fr_open_quotient_kernel(uint4 *out, const uint4 *f, const uint4 *inv_d, fr_t cst, fr_t scale, uint64_t n) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr_t v = mul(sub(load_fp<FrParams>(f + 2 * i), cst), mul(load_fp<FrParams>(inv_d + 2 * i), scale));
+    store_fp(out + 2 * i, v);
+}
+int32_t fr_open_quotient(sb_ctx *ctx, void *d_out, const void *d_f, const void *d_inv_d, const fr_t &cst, const fr_t &scale, size_t n, cudaStream_t st) {
+    SB_LAUNCH(ctx, fr_open_quotient_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (uint4 *)d_out, (const uint4 *)d_f, (const uint4 *)d_inv_d, cst, scale, (uint64_t)n);
     return SB_OK;
 }
 
@@ -735,6 +814,25 @@ int32_t fr_coset_combine(sb_ctx *ctx, const std::vector<const void *> &slots, co
     for (uint32_t s = 0; s < 8; s++) a.d[s] = s < a.n_cos ? (const uint4 *)slots[s] : nullptr;
     for (int i = 0; i < 64; i++) a.m[i] = m[i];
     SB_LAUNCH(ctx, fr_coset_combine_kernel, (unsigned)((n + 127) / 128), 128, 0, st, a, (uint4 *)d_out, (uint64_t)n);
+    return SB_OK;
+}
+
+// ---- instance column on a coset without a transform.  The column is sum_i v_i L_i(X) with a handful of values, and L_i(X) = L_0(omega^-i X): on
+// the coset g H its value at g omega^j is sum_i v_i * l0_coset[(j - i) mod n], a few products per row against the key's l_0 coset (the transform
+// pair it replaces -- lagrange_to_coeff + one size-n NTT per coset -- costs 1.4 ms at k = 20) ----
+__global__ void __launch_bounds__(128) instance_coset_kernel(const uint4 *l0_coset, const uint4 *vals, uint32_t n_vals, uint64_t n, uint4 *out) {
+    const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    fr_t acc = fr_t::zero();
+    for (uint32_t i = 0; i < n_vals; i++) {
+        const fr_t v = ldg_fp<FrParams>(vals + 2 * i);
+        const fr_t l = load_fp<FrParams>(l0_coset + 2 * ((j - i) & (n - 1)));
+        acc = add(acc, mul(v, l));
+    }
+    store_fp(out + 2 * j, acc);
+}
+int32_t instance_coset(sb_ctx *ctx, const void *d_l0_coset, const void *d_vals, uint32_t n_vals, size_t n, void *d_out, cudaStream_t st) {
+    SB_LAUNCH(ctx, instance_coset_kernel, (unsigned)((n + 127) / 128), 128, 0, st, (const uint4 *)d_l0_coset, (const uint4 *)d_vals, n_vals, (uint64_t)n, (uint4 *)d_out);
     return SB_OK;
 }
 

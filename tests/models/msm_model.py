@@ -205,7 +205,85 @@ def bucket_hierarchy(grp, buckets, n_sets, B, seg_log0, finish_at=8):
     return out
 
 
-def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None, cta_scan_max=0):
+def _tree_cta(grp, load, m, node, bt_log, bits):
+    """msm_bucket_tree_kernel, one CTA: fold elements [node * BT, (node + 1) * BT) (identity beyond m) into one record
+    (T, S_0 .. S_{bt_log - 1}) -- or just T when `bits` is false -- with the kernel's slot layout and ping-pong steps."""
+    BT = 1 << bt_log
+    recs = []                                   # records of 2 buckets, straight from "global memory"
+    for t in range(BT // 2):
+        e = node * BT + 2 * t
+        a = load(e) if e < m else grp.zero()
+        b = load(e + 1) if e + 1 < m else grp.zero()
+        recs.append([grp.add(a, b), b] if bits else [grp.add(a, b)])
+    for l in range(1, bt_log):
+        per_in = l + 1 if bits else 1
+        n_out = BT >> (l + 1)
+        nxt = []
+        for j in range(n_out):
+            L, R = recs[2 * j], recs[2 * j + 1]
+            assert len(L) == per_in and len(R) == per_in
+            rec = [grp.add(L[q], R[q]) for q in range(per_in)]
+            if bits:
+                rec.append(R[0])                # S_l = T of the upper half
+            nxt.append(rec)
+        recs = nxt
+    assert len(recs) == 1
+    return recs[0]
+
+
+def bucket_tree(grp, buckets, n_sets, B, bt_log=8):
+    """sum_i (i + 1) * B_i per set through msm_bucket_tree_kernel + host_bucket_combine: R = X + 2^shift * sum_b 2^b S_b."""
+    BT = 1 << bt_log
+    FIN = 2 * bt_log + 2
+    out = []
+    for w in range(n_sets):
+        P = list(buckets[w * B:(w + 1) * B])
+        Q = None
+        m, shift = B, 0
+        if m > BT * BT:                         # one running-sum level first (msm_bucket_level_kernel<false>, lambda = 1)
+            shift = (m.bit_length() - 1) - 2 * bt_log
+            S = 1 << shift
+            nP, nQ = [], []
+            for sg in range(m >> shift):
+                run, acc = grp.zero(), grp.zero()
+                for j in range(S - 1, 0, -1):
+                    run = grp.add(run, P[sg * S + j])
+                    acc = grp.add(acc, run)
+                run = grp.add(run, P[sg * S])
+                nP.append(run)
+                nQ.append(grp.add(acc, run))
+            P, Q = nP, nQ
+            m >>= shift
+        n_bits = m.bit_length() - 1
+        n_nodes = (m + BT - 1) // BT
+        fin = [None] * FIN
+        if n_nodes == 1:
+            rec = _tree_cta(grp, lambda e: P[e], m, 0, bt_log, True)
+            fin[0] = rec[0]
+            for b in range(bt_log):
+                fin[1 + b] = rec[1 + b]
+        else:
+            nodes = [_tree_cta(grp, lambda e: P[e], m, nd, bt_log, True) for nd in range(n_nodes)]
+            for x in range(bt_log + 1):         # the colsum launch: CTA x folds slot x of every node record
+                rec = _tree_cta(grp, lambda e: nodes[e][x], n_nodes, 0, bt_log, x == 0)
+                fin[x] = rec[0]
+                if x == 0:
+                    for b in range(bt_log):
+                        fin[bt_log + 1 + b] = rec[1 + b]
+        if Q is not None:
+            nodes_q = [_tree_cta(grp, lambda e: Q[e], m, nd, bt_log, False) for nd in range(n_nodes)]
+            fin[FIN - 1] = _tree_cta(grp, lambda e: nodes_q[e][0], n_nodes, 0, bt_log, False)[0]
+        # host_bucket_combine
+        acc = grp.zero()
+        for b in reversed(range(n_bits)):
+            acc = grp.add(grp.dbl(acc), fin[1 + b])
+        for _ in range(shift):
+            acc = grp.dbl(acc)
+        out.append(grp.add(acc, fin[FIN - 1] if shift else fin[0]))
+    return out
+
+
+def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None, cta_scan_max=0, tree_log=None):
     """scalars: batch * n values (vector j = scalars[j n:(j+1) n], tables only).  Returns the list of `batch` results (tables), or the
     single result; with a window range [w_lo, w_hi) the partial sum over those windows (tables: already carrying 2^(c w))."""
     n = len(bases)
@@ -262,7 +340,7 @@ def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=Fals
         else:
             keys, pts = reduce_level(grp, keys, pts, LK, buckets)
     final_level(grp, keys, pts, buckets)
-    wins = bucket_hierarchy(grp, buckets, n_sets, B, seg_log)
+    wins = bucket_tree(grp, buckets, n_sets, B, tree_log) if tree_log else bucket_hierarchy(grp, buckets, n_sets, B, seg_log)
     if tables:
         return wins                           # one (partial) commitment per scalar vector
     if w_hi - w_lo != W_all:

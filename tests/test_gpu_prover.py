@@ -36,7 +36,7 @@ def P(a):
     return ptr(a)
 
 
-@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 1 << 16])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 1 << 16, (1 << 16) + 77, 300001])  # >= 2^16: the two-level kernels
 def test_batch_invert(ctx, n):
     a = cpu.random_fr(n, 11 + n)
     a[::7] = 0  # zeros stay zero (halo2 batch_invert)

@@ -55,8 +55,11 @@ def test_device_field_code_on_host(harness, name, mod):
     fn(_p(out), _p(a), _p(b), ctypes.c_size_t(n), 2)
     assert dec(n) == [(x - y) % mod for x, y in zip(xs, ys)]
     m = 20
-    fn(_p(out), _p(a[8 * 8:]), _p(b), ctypes.c_size_t(m), 3)
+    fn(_p(out), _p(a[8 * 8:]), _p(b), ctypes.c_size_t(m), 6)   # Fermat
     assert dec(m) == [pow(x, -1, mod) * (1 << 512) % mod for x in xs[8:8 + m]]
+    m = 1000                                                    # binary extended Euclid (the one in use), edge values included; inv(0) = 0
+    fn(_p(out), _p(a), _p(b), ctypes.c_size_t(m), 3)
+    assert dec(m) == [pow(x, -1, mod) * (1 << 512) % mod if x else 0 for x in xs[:m]]
 
 
 def test_device_curve_code_on_host(harness):
@@ -110,7 +113,9 @@ def test_msm_pipeline_model():
             sc[0] = B.R - 1
         bs = [rnd.randrange(B.R) for _ in range(n)]
         exp = sum(s * b for s, b in zip(sc, bs)) % B.R
-        got = msm_model.msm(g, sc, bs, c, L1=rnd.choice([4, 8]), LK=rnd.choice([3, 4]), final_max=rnd.choice([4, 16]), seg_log=rnd.choice([0, 1, 2, 3]))
+        # tree_log: buckets per CTA of the tree bucket reduction (2^8 in CUDA); 1 and 2 reach the two-stage and the running-sum-first paths at these sizes
+        got = msm_model.msm(g, sc, bs, c, L1=rnd.choice([4, 8]), LK=rnd.choice([3, 4]), final_max=rnd.choice([4, 16]), seg_log=rnd.choice([0, 1, 2, 3]),
+                            tree_log=rnd.choice([None, 1, 2, 3, 8]))
         assert got == exp, (trial, n, c, mode)
 
 
@@ -128,7 +133,8 @@ def test_msm_model_tables_batches_and_window_shards():
         for _ in range(batch):
             sc += _scalars(rnd, n, rnd.choice("UZCS"))
         exp = [sum(s * b for s, b in zip(sc[j * n:(j + 1) * n], bs)) % B.R for j in range(batch)]
-        kw = dict(L1=rnd.choice([4, 8]), LK=4, final_max=rnd.choice([4, 16]), seg_log=rnd.choice([1, 2, 3]), cta_scan_max=rnd.choice([0, 64, 1 << 20]))
+        kw = dict(L1=rnd.choice([4, 8]), LK=4, final_max=rnd.choice([4, 16]), seg_log=rnd.choice([1, 2, 3]), cta_scan_max=rnd.choice([0, 64, 1 << 20]),
+                  tree_log=rnd.choice([None, 1, 2, 3, 8]))
         assert msm_model.msm(g, sc, bs, c, tables=True, batch=batch, **kw) == exp, (trial, "batch")
         W = msm_model.window_count(c)
         world = rnd.choice([2, 4, 8])

@@ -53,6 +53,26 @@ def launches(src, dst, cmd):
             f.write(f"{k},{a[0]},{a[1]:.1f},{a[1] / total:.3f}\n")
 
 
+def sequence(src, dst, cmd, last):
+    """the last `last` launches in order (one proof): kernel, grid, duration"""
+    rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if r]
+    hdr = rows[0]
+    ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    gi = hdr.index("Grid Size") if "Grid Size" in hdr else None
+    seq = []
+    for r in rows[1:]:
+        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
+            continue
+        v = float(r[vi].replace(",", ""))
+        us = {"ns": v / 1e3, "us": v, "usecond": v, "nsecond": v / 1e3, "ms": v * 1e3, "msecond": v * 1e3}.get(r[ui], v / 1e3)
+        seq.append((short(r[ki]), r[gi] if gi is not None else "", us))
+    seq = seq[-int(last):]
+    with open(dst, "w") as f:
+        f.write(f"# the last {last} launches of: {cmd}\n# (ncu --metrics gpu__time_duration.sum --clock-control none: cold-cache, serialised)\n# total {sum(x[2] for x in seq) / 1e3:.3f} ms\nindex,kernel,grid,us\n")
+        for i, (k, g, us) in enumerate(seq):
+            f.write(f"{i},{k},{g.replace(', ', 'x')},{us:.1f}\n")
+
+
 def full(src, dst, cmd, traffic_json=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -83,5 +103,7 @@ def full(src, dst, cmd, traffic_json=None):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(*sys.argv[2:5])
+    elif sys.argv[1] == "sequence":
+        sequence(*sys.argv[2:6])
     else:
         full(*sys.argv[2:6])

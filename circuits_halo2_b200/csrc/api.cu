@@ -83,6 +83,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.no_hprog_cache = getb("SB_NO_HPROG_CACHE");
     t.no_jit = getb("SB_NO_JIT");
     t.no_binv2 = getb("SB_NO_BINV2");
+    t.no_shplonk_shard = getb("SB_NO_SHPLONK_SHARD");
     t.no_shplonk_lagrange = getb("SB_NO_SHPLONK_LAGRANGE");
     t.msm_no_bucket_tree = getb("SB_MSM_NO_BUCKET_TREE");
     t.no_inst_direct = getb("SB_NO_INST_DIRECT");
@@ -176,6 +177,22 @@ __global__ void bench_imad_wide_kernel(uint64_t *out, uint32_t iters) {
 #pragma unroll
     for (int q = 0; q < 8; q++) r ^= x[q];
     if (r == 0x12345678ull) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+__global__ void bench_imad_hi_kernel(uint32_t *out, uint32_t iters) {
+    // 8 independent IMAD.HI chains (upper half of 32x32, + 32-bit addend): is the high half as cheap as the low half, or as dear as IMAD.WIDE?
+    uint32_t x[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = threadIdx.x * 2654435761u + q;
+    const uint32_t m = 0xfffffff1u - blockIdx.x, c = threadIdx.x | 0x80000000u;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) x[q] = __umulhi(x[q], m) + c;
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) r ^= x[q];
+    if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 }  // namespace sb
@@ -711,7 +728,8 @@ static int32_t timed(sb_ctx *ctx, float *out_ms, int which, uint32_t blocks, uin
         if (which == 0) SB_LAUNCH(ctx, bench_field_mul_kernel<FrParams>, blocks, threads, 0, ctx->stream, (uint4 *)d, iters);
         else if (which == 1) SB_LAUNCH(ctx, bench_field_mul_kernel<FqParams>, blocks, threads, 0, ctx->stream, (uint4 *)d, iters);
         else if (which == 2) SB_LAUNCH(ctx, bench_imad_kernel, blocks, threads, 0, ctx->stream, (uint32_t *)d, iters);
-        else SB_LAUNCH(ctx, bench_imad_wide_kernel, blocks, threads, 0, ctx->stream, (uint64_t *)d, iters);
+        else if (which == 3) SB_LAUNCH(ctx, bench_imad_wide_kernel, blocks, threads, 0, ctx->stream, (uint64_t *)d, iters);
+        else SB_LAUNCH(ctx, bench_imad_hi_kernel, blocks, threads, 0, ctx->stream, (uint32_t *)d, iters);
         SB_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
         SB_CUDA_TRY(cudaEventSynchronize(e1));
     }
@@ -734,6 +752,11 @@ int32_t sb_bench_imad_wide(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint3
     if (!ctx || !out_ms) return SB_ERR_ARG;
     Guard g(ctx);
     return timed(ctx, out_ms, 3, blocks, threads, iters);
+}
+int32_t sb_bench_imad_hi(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, float *out_ms) {
+    if (!ctx || !out_ms) return SB_ERR_ARG;
+    Guard g(ctx);
+    return timed(ctx, out_ms, 4, blocks, threads, iters);
 }
 int32_t sb_g1_sum_affine(const uint8_t *pts, size_t n, uint8_t out_affine[64]) {
     if (!pts || !out_affine) return SB_ERR_ARG;

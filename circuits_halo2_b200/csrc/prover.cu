@@ -573,13 +573,25 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
         for (const Query &q : queries)
             if (q.d_lagr) lagr[q.poly_id] = q.d_lagr;
         const std::vector<Fr> super(super_points.begin(), super_points.end());
+        // Sharded proof: everything below except the one transform is elementwise over H, so rank r computes rows [r n / world, (r + 1) n / world)
+        // of h and of the opening quotient; the slices meet in one all-gather each, right before their (window-sharded) commitments.
+        const bool by_rows = comm && comm->world > 1 && comm->allgather_dev && n % ((size_t)comm->world * 32) == 0 && !ctx->tune.no_shplonk_shard;
+        const size_t cnt = by_rows ? n / (size_t)comm->world : n, off = by_rows ? cnt * (size_t)comm->rank : 0;
+        auto sl = [&](const void *p) -> const void * { return (const uint8_t *)p + off * 32; };
+        auto slw = [&](void *p) -> void * { return (uint8_t *)p + off * 32; };
+        auto gather = [&](void *d_buf) -> int32_t {
+            if (!by_rows) return SB_OK;
+            SB_CUDA_TRY(sync_stream(ctx, st));
+            if (comm->allgather_dev(comm->user, d_buf, cnt * 32, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
+            return SB_OK;
+        };
         uint8_t *d_m;
         SB_TRY(scratch_get(ctx, "sh_m", sets.size() * n * 32, (void **)&d_m));
         {
             std::vector<fr_t> sd;
             for (const Fr &p : super) sd.push_back(to_dev(p));
-            SB_TRY(fr_vanish(ctx, pk->omega_pows, sd, d_invd, n, st));
-            SB_TRY(fr_batch_invert(ctx, d_invd, n, st));
+            SB_TRY(fr_vanish(ctx, sl(pk->omega_pows), sd, slw(d_invd), cnt, st));
+            SB_TRY(fr_batch_invert(ctx, slw(d_invd), cnt, st));
         }
         std::vector<std::vector<std::vector<Fr>>> low(sets.size());
         auto complement = [&](const RSet &s) {
@@ -606,7 +618,7 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
                 std::vector<Fr> r = lagrange_interpolate(basis, evs);
                 low[si].push_back(r);
                 for (size_t i = 0; i < r.size(); i++) head[i] = hfr::add(head[i], hfr::mul(r[i], y_pow));
-                if (lagr.count(pid)) { lag_polys.push_back(lagr[pid]); lag_coeffs.push_back(to_dev(y_pow)); }
+                if (lagr.count(pid)) { lag_polys.push_back(sl(lagr[pid])); lag_coeffs.push_back(to_dev(y_pow)); }
                 else { coef_polys.push_back(polys[pid]); coef_coeffs.push_back(to_dev(y_pow)); }
                 y_pow = hfr::mul(y_pow, y);
             }
@@ -617,16 +629,17 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
             if (!coef_polys.empty()) {
                 SB_TRY(fr_lincomb(ctx, d_nx, coef_polys, coef_coeffs, {}, n, false, st));
                 SB_TRY(ntt_run(ctx, d_nx, (const uint8_t *)pk->dom->omega.v, pk->k, st));
-                lag_polys.push_back(d_nx);
+                lag_polys.push_back(sl(d_nx));
                 lag_coeffs.push_back(to_dev(hfr::ONE));
             }
-            SB_TRY(fr_lincomb(ctx, d_mi, lag_polys, lag_coeffs, {}, n, false, st));
+            SB_TRY(fr_lincomb(ctx, slw(d_mi), lag_polys, lag_coeffs, {}, cnt, false, st));
             std::vector<fr_t> comp;
             for (const Fr &p : complement(s)) comp.push_back(to_dev(p));
-            SB_TRY(fr_div_combine(ctx, d_hx, d_mi, d_invd, pk->omega_pows, comp, to_dev(v_pow), n, si == 0, st, &head_d));
+            SB_TRY(fr_div_combine(ctx, slw(d_hx), sl(d_mi), sl(d_invd), sl(pk->omega_pows), comp, to_dev(v_pow), cnt, si == 0, st, &head_d));
             v_pow = hfr::mul(v_pow, v);
         }
         uint8_t pt[64];
+        SB_TRY(gather(d_hx));
         SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_hx, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("shplonk: quotient commitment is the identity"); return SB_ERR_ARG; }
         const Fr u = tr.squeeze();
@@ -649,18 +662,19 @@ int32_t shplonk(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, Transcript &t
                 const_term = hfr::add(const_term, hfr::mul(hfr::mul(scale, y_pow), eval_small(low[si][mi], u)));
                 y_pow = hfr::mul(y_pow, y);
             }
-            lc_polys.push_back(d_m + si * n * 32);
+            lc_polys.push_back(sl(d_m + si * n * 32));
             lc_coeffs.push_back(to_dev(scale));
             v_pow = hfr::mul(v_pow, v);
         }
         Fr zt = hfr::ONE;
         for (const Fr &p : super) zt = hfr::mul(zt, hfr::sub(u, p));
-        lc_polys.push_back(d_hx);
+        lc_polys.push_back(sl(d_hx));
         lc_coeffs.push_back(to_dev(hfr::neg(zt)));
-        SB_TRY(fr_lincomb(ctx, d_lx, lc_polys, lc_coeffs, {}, n, false, st));
-        SB_TRY(fr_vanish(ctx, pk->omega_pows, {to_dev(u)}, d_nx, n, st));
-        SB_TRY(fr_batch_invert(ctx, d_nx, n, st));
-        SB_TRY(fr_open_quotient(ctx, d_lx, d_lx, d_nx, to_dev(const_term), to_dev(hfr::inv(z0)), n, st));
+        SB_TRY(fr_lincomb(ctx, slw(d_lx), lc_polys, lc_coeffs, {}, cnt, false, st));
+        SB_TRY(fr_vanish(ctx, sl(pk->omega_pows), {to_dev(u)}, slw(d_nx), cnt, st));
+        SB_TRY(fr_batch_invert(ctx, slw(d_nx), cnt, st));
+        SB_TRY(fr_open_quotient(ctx, slw(d_lx), sl(d_lx), sl(d_nx), to_dev(const_term), to_dev(hfr::inv(z0)), cnt, st));
+        SB_TRY(gather(d_lx));
         SB_TRY(msm_commit(ctx, comm, pk->srs, 1, d_lx, n, pt, st));
         if (!tr.write_point(pt)) { set_last_error("shplonk: opening commitment is the identity"); return SB_ERR_ARG; }
         return SB_OK;
@@ -1486,7 +1500,24 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     }
     const int i_h = want(d_hfold, x);
     std::vector<fr_t> evd;
-    SB_TRY(fr_eval_polys(ctx, ev_polys, ev_pts, n, evd, st));
+    if (world > 1 && !ctx->tune.no_shplonk_shard) {
+        // sharded proof: the (polynomial, point) pairs are dealt to the ranks in contiguous runs; the 32-byte values meet on the host
+        const size_t m_ev = ev_polys.size(), per_ev = (m_ev + world - 1) / world;
+        const size_t lo = std::min(m_ev, per_ev * rank), hi = std::min(m_ev, lo + per_ev);
+        std::vector<fr_t> mine_v;
+        if (hi > lo) {
+            std::vector<const void *> sub_p(ev_polys.begin() + lo, ev_polys.begin() + hi);
+            std::vector<fr_t> sub_x(ev_pts.begin() + lo, ev_pts.begin() + hi);
+            SB_TRY(fr_eval_polys(ctx, sub_p, sub_x, n, mine_v, st));
+        }
+        std::vector<fr_t> mine(per_ev, fr_t::zero()), all(per_ev * world);
+        for (size_t i = 0; i < mine_v.size(); i++) mine[i] = mine_v[i];
+        if (comm->allgather_host(comm->user, mine.data(), all.data(), per_ev * 32) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+        evd.resize(m_ev);
+        for (size_t i = 0; i < m_ev; i++) evd[i] = all[(i / per_ev) * per_ev + (i % per_ev)];
+    } else {
+        SB_TRY(fr_eval_polys(ctx, ev_polys, ev_pts, n, evd, st));
+    }
     std::vector<Fr> ev(evd.size());
     for (size_t i = 0; i < evd.size(); i++) ev[i] = to_host(evd[i]);
     for (int i : i_adv) tr.write_scalar(ev[i]);

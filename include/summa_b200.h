@@ -296,6 +296,7 @@ int32_t sb_msm_phase_times(const sb_ctx *ctx, float out_ms[5], uint32_t out_shap
 int32_t sb_bench_field_mul(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, int32_t field /*0 Fr,1 Fq*/, float *out_ms);
 int32_t sb_bench_imad(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, float *out_ms);      /* 8 IMAD chains / thread */
 int32_t sb_bench_imad_wide(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, float *out_ms); /* 8 IMAD.WIDE chains / thread */
+int32_t sb_bench_imad_hi(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, float *out_ms);   /* 8 IMAD.HI chains / thread */
 
 /* ---- host helper: sum of n affine points (folding the per-GPU partial MSM results; the
  * north_star's "partial G1 sums are reduced on the host") ---------------------------------- */

@@ -19,7 +19,16 @@ static __device__ __noinline__ fq_t ec_mul(fq_t a, fq_t b) { return mul(a, b); }
 #else
 SB_HD fq_t ec_mul(const fq_t &a, const fq_t &b) { return mul(a, b); }
 #endif
+// Squares: the dedicated squaring (fp.cuh sqr, 91 + 9 wide multiply-adds against 120 + 8) is 14 % cheaper on the multiplier pipe in isolation, but as a
+// second shared subroutine of the MSM kernels it bought nothing measurable (level 1 of a k = 20 proof: 30.7 ms with it, 30.6 without; 2^22 MSM
+// 361.8 vs 361.7 Mpts/s, profiles/r02q) -- its extra carry bookkeeping lands on the same pipe.  Opt in with -DSB_EC_SQR.
+#if defined(SB_EC_SQR) && defined(SB_EC_NOINLINE_MUL) && defined(__CUDA_ARCH__)
+static __device__ __noinline__ fq_t ec_sqr(fq_t a) { return sqr(a); }
+#elif defined(SB_EC_SQR)
+SB_HD fq_t ec_sqr(const fq_t &a) { return sqr(a); }
+#else
 SB_HD fq_t ec_sqr(const fq_t &a) { return ec_mul(a, a); }
+#endif
 
 struct affine_t {  // halo2curves G1Affine: 64 B, identity = (0, 0)
     fq_t x, y;

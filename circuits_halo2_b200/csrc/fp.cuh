@@ -261,8 +261,102 @@ SB_HD Fp<P> mul(const Fp<P> &a, const Fp<P> &b) {
     return r;
 }
 
+// Montgomery square a * a * 2^-256 mod p, fully reduced: 100 wide multiply-adds instead of the product's 128 (IMAD.WIDE is 4.6 issue cycles per warp
+// on sm_100a, everything else here is 2: profiles/r02q_imad_pipes.json).  Separated operand scanning: (A) the 28 products a_i a_j, i < j, row by
+// row into an even-aligned and an odd-aligned 512-bit accumulator -- a row is one carry chain per alignment and its carry-out lands in a limb the
+// accumulator has not reached yet; (B) S = even + odd, doubled, plus the 8 squares a_i^2 as one more chain; (C) eight reduction rounds m = T_i *
+// (-p^-1), T += m p 2^(32 i), again one chain per alignment, whose carry-outs all land in limbs >= 8 -- never read by a later m -- and are
+// therefore only counted and added once at the end.
 template <class P>
-SB_HD Fp<P> sqr(const Fp<P> &a) { return mul(a, a); }
+SB_HD Fp<P> sqr(const Fp<P> &x) {
+    using namespace ptx;
+    const uint32_t *a = x.v;
+    uint32_t te[16], to[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) te[k] = to[k] = 0;
+    // (A) upper triangle
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        // odd distance j - i: limb i + j is odd-aligned to the row start
+        {
+            bool first = true;
+            int top = 0;
+#pragma unroll
+            for (int j = i + 1; j < 8; j += 2) {
+                const int q = i + j;
+                to[q] = first ? mad_lo_cc(a[i], a[j], to[q]) : madc_lo_cc(a[i], a[j], to[q]);
+                to[q + 1] = madc_hi_cc(a[i], a[j], to[q + 1]);
+                first = false;
+                top = q + 2;
+            }
+            if (top < 16) to[top] = addc(to[top], 0);
+        }
+        if (i + 2 < 8) {
+            bool first = true;
+            int top = 0;
+#pragma unroll
+            for (int j = i + 2; j < 8; j += 2) {
+                const int q = i + j;
+                te[q] = first ? mad_lo_cc(a[i], a[j], te[q]) : madc_lo_cc(a[i], a[j], te[q]);
+                te[q + 1] = madc_hi_cc(a[i], a[j], te[q + 1]);
+                first = false;
+                top = q + 2;
+            }
+            if (top < 16) te[top] = addc(te[top], 0);
+        }
+    }
+    // (B) T = 2 (te + to) + sum_i a_i^2 2^(64 i)
+    uint32_t t[16];
+    t[0] = 0;
+    t[1] = to[1];
+    t[2] = add_cc(te[2], to[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k++) t[k] = addc_cc(te[k], to[k]);
+    t[15] = addc(te[15], to[15]);
+#pragma unroll
+    for (int k = 15; k >= 1; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    t[0] = mad_lo_cc(a[0], a[0], 0);
+    t[1] = madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) {
+        t[2 * i] = madc_lo_cc(a[i], a[i], t[2 * i]);
+        t[2 * i + 1] = madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+    }
+    t[14] = madc_lo_cc(a[7], a[7], t[14]);
+    t[15] = madc_hi(a[7], a[7], t[15]);
+    // (C) Montgomery reduction
+    uint32_t cl[16];
+#pragma unroll
+    for (int k = 8; k < 16; k++) cl[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t m = mul_lo(t[i], P::INV);
+        t[i] = mad_lo_cc(m, P::mod(0), t[i]);
+        t[i + 1] = madc_hi_cc(m, P::mod(0), t[i + 1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            t[i + j] = madc_lo_cc(m, P::mod(j), t[i + j]);
+            t[i + j + 1] = madc_hi_cc(m, P::mod(j), t[i + j + 1]);
+        }
+        cl[i + 8] = addc(cl[i + 8], 0);
+        t[i + 1] = mad_lo_cc(m, P::mod(1), t[i + 1]);
+        t[i + 2] = madc_hi_cc(m, P::mod(1), t[i + 2]);
+#pragma unroll
+        for (int j = 3; j < 8; j += 2) {
+            t[i + j] = madc_lo_cc(m, P::mod(j), t[i + j]);
+            t[i + j + 1] = madc_hi_cc(m, P::mod(j), t[i + j + 1]);
+        }
+        if (i + 9 < 16) cl[i + 9] = addc(cl[i + 9], 0);  // i = 7: a carry out of limb 15 cannot happen (a^2 + m p < 2^512)
+    }
+    uint32_t r[8];
+    r[0] = add_cc(t[8], cl[8]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) r[k] = addc_cc(t[8 + k], cl[8 + k]);
+    r[7] = addc(t[15], cl[15]);
+    Fp<P> out;
+    final_sub<P>(out.v, r);
+    return out;
+}
 
 template <class P>
 SB_HD Fp<P> to_mont(const Fp<P> &a) { return mul(a, Fp<P>::r2()); }

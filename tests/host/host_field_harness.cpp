@@ -9,7 +9,7 @@ template <class F> static void binop(uint32_t *r, const uint32_t *a, const uint3
     for (size_t i = 0; i < n; i++) {
         F x, y, z;
         memcpy(x.v, a + 8 * i, 32); memcpy(y.v, b + 8 * i, 32);
-        z = op == 0 ? mul(x, y) : op == 1 ? add(x, y) : op == 2 ? sub(x, y) : op == 3 ? inv(x) : op == 4 ? to_mont(x) : op == 6 ? inv_fermat(x) : from_mont(x);
+        z = op == 0 ? mul(x, y) : op == 1 ? add(x, y) : op == 2 ? sub(x, y) : op == 3 ? inv(x) : op == 4 ? to_mont(x) : op == 6 ? inv_fermat(x) : op == 7 ? sqr(x) : from_mont(x);
         memcpy(r + 8 * i, z.v, 32);
     }
 }

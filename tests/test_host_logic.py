@@ -54,6 +54,19 @@ def test_device_field_code_on_host(harness, name, mod):
     assert dec(n) == [(x + y) % mod for x, y in zip(xs, ys)]
     fn(_p(out), _p(a), _p(b), ctypes.c_size_t(n), 2)
     assert dec(n) == [(x - y) % mod for x, y in zip(xs, ys)]
+    # the dedicated squaring, with limb patterns that saturate its carry chains
+    pat = [0xFFFFFFFF, 0, 1, 0x80000000, 0xFFFFFFFE, 0x7FFFFFFF]
+    sq = list(xs)
+    for t in range(3000):
+        v = 0
+        for limb in range(8):
+            v |= (rnd.choice(pat) if rnd.random() < 0.7 else rnd.getrandbits(32)) << (32 * limb)
+        sq.append(v % mod)
+    a2 = _arr(b"".join(x.to_bytes(32, "little") for x in sq))
+    out2 = np.empty_like(a2)
+    fn(_p(out2), _p(a2), _p(a2), ctypes.c_size_t(len(sq)), 7)
+    got = [int.from_bytes(out2[8 * i:8 * i + 8].tobytes(), "little") for i in range(len(sq))]
+    assert got == [x * x * rinv % mod for x in sq]
     m = 20
     fn(_p(out), _p(a[8 * 8:]), _p(b), ctypes.c_size_t(m), 6)   # Fermat
     assert dec(m) == [pow(x, -1, mod) * (1 << 512) % mod for x in xs[8:8 + m]]

@@ -73,6 +73,7 @@ struct Tuning {
     bool msm_no_bucket_tree = false; // SB_MSM_NO_BUCKET_TREE: bucket reduction by the running-sum hierarchy instead of the tree kernels
     bool no_shplonk_lagrange = false; // SB_NO_SHPLONK_LAGRANGE: SHPLONK through the division coset (8 transforms) instead of the evaluation domain (1)
     bool no_shplonk_shard = false;   // SB_NO_SHPLONK_SHARD: sharded proofs compute SHPLONK's evaluation-domain vectors in full on every rank
+    bool shard_msm_by_window = false; // SB_SHARD_MSM_BY_WINDOW: sharded commitments split by signed-digit window instead of by bucket residue
     bool no_inst_direct = false;     // SB_NO_INST_DIRECT: instance column to the cosets through transforms even when it holds few values
     bool no_binv2 = false;           // SB_NO_BINV2: batch inversion of long vectors through the single-level kernel
     bool no_jit = false;             // SB_NO_JIT: evaluate_h through the interpreter instead of the NVRTC-specialised kernel
@@ -189,7 +190,7 @@ int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars
 int32_t msm_run_tables_batch(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, uint8_t *out_affine, cudaStream_t st);
 // piece_off (optional, <= 8 vectors): table-entry offset per vector inside one slab (mixed-basis batch)
 int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, int32_t w_lo, int32_t w_hi, uint8_t *out,
-                                     cudaStream_t st, const uint32_t *piece_off = nullptr);
+                                     cudaStream_t st, const uint32_t *piece_off = nullptr, uint32_t res = 0, uint32_t log_mod = 0);
 // window-sharded MSM (multi-GPU): window bits / count for n points, the XYZZ sums of windows [w_lo, w_hi), and the host Horner fold
 void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W);
 int32_t msm_run_windows(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint32_t w_lo, uint32_t w_hi, uint8_t *win_out, cudaStream_t st);

@@ -228,6 +228,29 @@ void host_bucket_combine(const uint8_t *fin, int n_bits, int shift, int x_slot, 
     memcpy(out_xyzz, &acc, 128);
 }
 
+// Residue shard of a table MSM (msm.cu): the rank kept the digits with (|d| - 1) mod 2^log_mod == res in bucket b' = (|d| - 1) >> log_mod, whose true
+// weight is 2^log_mod b' + res + 1.  r = sum (b' + 1) V_b' comes in, total = sum V_b';  r <- 2^log_mod r - (2^log_mod - res - 1) total.
+void host_residue_fixup(uint8_t r_xyzz[128], const uint8_t total_xyzz[128], int log_mod, int res) {
+    pt r, t;
+    memcpy(&r, r_xyzz, 128);
+    memcpy(&t, total_xyzz, 128);
+    for (int i = 0; i < log_mod; i++) r = pdbl(r);
+    const unsigned k = (1u << log_mod) - (unsigned)res - 1u;
+    pt m;
+    memset(&m, 0, sizeof m);
+    for (int b = 31; b >= 0; b--) {   // m = k * total
+        m = pdbl(m);
+        if ((k >> b) & 1) m = padd(m, t);
+    }
+    if (!is_zero(m.zz)) {
+        fe zero;
+        memset(&zero, 0, sizeof zero);
+        m.y = sub(zero, m.y);
+        r = padd(r, m);
+    }
+    memcpy(r_xyzz, &r, 128);
+}
+
 // Fq Montgomery (32 B) -> canonical little-endian bytes (transcript encodings of commitments)
 void host_fq_to_canonical(const uint8_t mont[32], uint8_t canon_le[32]) {
     fe a, one_c;

@@ -33,6 +33,7 @@ namespace sb {
 
 void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_affine[64]);
 void host_bucket_combine(const uint8_t *fin, int n_bits, int shift, int x_slot, uint8_t out_xyzz[128]);
+void host_residue_fixup(uint8_t r_xyzz[128], const uint8_t total_xyzz[128], int log_mod, int res);
 
 static const uint32_t INVALID_KEY = 0xffffffffu;
 // chunk length of reduce levels >= 2: these levels are chains of dependent EC additions on few threads, so short chunks (more, smaller
@@ -50,6 +51,7 @@ struct MsmShape {
     uint32_t batch;        // scalar vectors sharing the bases (tables only): vector j = scalars[j n .. (j+1) n), bucket set j
     uint32_t piece_off[8]; // table-entry offset of vector j (0, or the distance to the other basis' tables inside one slab)
     uint32_t tab_stride;   // 0, or the table stride: the point for (window w, base i) is tables[w * tab_stride + i] = 2^(c w) * P_i
+    uint32_t res, log_mod; // residue shard (multi-GPU, tables): only digits with (|d| - 1) mod 2^log_mod == res are kept, in bucket (|d| - 1) >> log_mod; B is the reduced count
 };
 
 // ------------------------------------------------------------------ 1+2: recode, histogram, scatter
@@ -102,7 +104,11 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint4 *scalars, uin
                 carry = 0;
             }
             if (w < sh.w_lo) continue;  // warp-uniform: earlier windows only feed the carry
-            const uint32_t key = (live && d) ? (sh.tab_stride ? piece * sh.B : (w - sh.w_lo) * sh.B) + d - 1 : INVALID_KEY;
+            uint32_t key = INVALID_KEY;
+            if (live && d) {
+                const uint32_t dm = d - 1;
+                if ((dm & ((1u << sh.log_mod) - 1u)) == sh.res) key = (sh.tab_stride ? piece * sh.B : (w - sh.w_lo) * sh.B) + (dm >> sh.log_mod);
+            }
             // warp aggregation by RUNS of equal keys in neighbouring lanes: one atomic per run.  Equal scalars sit in neighbouring rows (constant and
             // selector-like columns, the sorted permuted lookup columns), so runs catch the hot buckets; match.any would also catch scattered
             // duplicates but costs ~70 cycles of a shared unit per digit (ncu: 89 % busy, profiles/r02l), twice the whole histogram otherwise.
@@ -631,7 +637,8 @@ static uint32_t ilog2_floor(uint64_t x) {
     return r;
 }
 
-static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1, const MsmTables *tabs = nullptr, uint32_t batch = 1) {
+static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_hi = -1, const MsmTables *tabs = nullptr, uint32_t batch = 1, uint32_t res = 0,
+                          uint32_t log_mod = 0) {
     MsmShape sh;
     memset(&sh, 0, sizeof sh);
     int c = (int)ilog2_floor(n) - 3;
@@ -644,7 +651,9 @@ static MsmShape msm_shape(sb_ctx *ctx, uint64_t n, int32_t w_lo = 0, int32_t w_h
     sh.tab_stride = tabs ? (uint32_t)tabs->stride : 0;
     sh.w_lo = (uint32_t)w_lo;
     sh.W = (w_hi < 0 ? sh.W_all : (uint32_t)w_hi) - sh.w_lo;
-    sh.B = 1u << (sh.c - 1);
+    sh.res = res;
+    sh.log_mod = log_mod;
+    sh.B = (1u << (sh.c - 1)) >> log_mod;
     sh.batch = batch;
     sh.Wb = tabs ? batch : sh.W;
     sh.n = n;
@@ -666,7 +675,7 @@ void msm_window_shape(sb_ctx *ctx, size_t n, uint32_t *c, uint32_t *W) {
 }
 
 static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out, cudaStream_t st,
-                            uint32_t batch = 1, const uint32_t *piece_off = nullptr);
+                            uint32_t batch = 1, const uint32_t *piece_off = nullptr, uint32_t res = 0, uint32_t log_mod = 0);
 
 int32_t msm_run(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, uint8_t out_affine[64], cudaStream_t st) {
     return msm_run_impl(ctx, d_bases, d_scalars, n, 0, -1, nullptr, out_affine, st);
@@ -685,10 +694,10 @@ int32_t msm_run_tables(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars
 }
 // windows [w_lo, w_hi) of `batch` scalar vectors in one launch set: out = batch XYZZ partials (128 B each) that carry their 2^(c w) factors
 int32_t msm_run_tables_batch_windows(sb_ctx *ctx, const MsmTables *tabs, const void *d_scalars, size_t n, uint32_t batch, int32_t w_lo, int32_t w_hi, uint8_t *out,
-                                     cudaStream_t st, const uint32_t *piece_off) {
+                                     cudaStream_t st, const uint32_t *piece_off, uint32_t res, uint32_t log_mod) {
     SB_REQUIRE(tabs && tabs->d_tables && n <= tabs->stride && batch >= 1 && w_lo < w_hi, "msm_run_tables_batch_windows: bad arguments");
     SB_REQUIRE((uint64_t)(w_hi - w_lo) * n * batch < (1ull << 32) - 8, "msm_run_tables_batch_windows: batch too large");
-    return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st, batch, piece_off);
+    return msm_run_impl(ctx, tabs->d_tables, d_scalars, n, w_lo, w_hi, tabs, out, st, batch, piece_off, res, log_mod);
 }
 
 int32_t msm_tables_build(sb_ctx *ctx, const void *d_bases, size_t n, uint32_t c, MsmTables *out, cudaStream_t st, void *d_dst) {
@@ -739,14 +748,15 @@ int32_t msm_run_tables_batch_mixed(sb_ctx *ctx, const MsmTables *t0, const MsmTa
 }
 
 static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scalars, size_t n, int32_t w_lo, int32_t w_hi, const MsmTables *tabs, uint8_t *out_affine,
-                            cudaStream_t st, uint32_t batch, const uint32_t *piece_off) {
+                            cudaStream_t st, uint32_t batch, const uint32_t *piece_off, uint32_t res, uint32_t log_mod) {
     if (n == 0) {
         memset(out_affine, 0, w_hi < 0 ? (size_t)64 * batch : (size_t)(tabs ? batch : (uint32_t)(w_hi - w_lo)) * 128);
         return SB_OK;
     }
     SB_REQUIRE(n < (1ull << 31), "msm: n must be < 2^31");
     SB_REQUIRE(batch == 1 || tabs, "msm: batches need table bases");
-    MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs, batch);
+    SB_REQUIRE(log_mod == 0 || (tabs && w_hi >= 0 && res < (1u << log_mod) && tabs->c >= log_mod + 2), "msm: residue shards need table bases and a window range");
+    MsmShape sh = msm_shape(ctx, n, w_lo, w_hi, tabs, batch, res, log_mod);
     SB_REQUIRE(!piece_off || batch <= 8, "msm: at most 8 vectors in a mixed-basis batch");
     for (uint32_t j = 0; j < 8; j++) sh.piece_off[j] = (piece_off && j < batch) ? piece_off[j] : 0;
     SB_REQUIRE(w_hi < 0 || (uint32_t)w_hi <= sh.W_all, "msm: window range exceeds the scalar");
@@ -821,6 +831,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     // ---- 4: bucket reduction ----
     SB_CUDA_TRY(cudaEventRecord(ctx->msm_ev[3], st));
     const bool tree = !ctx->tune.msm_no_bucket_tree && (size_t)sh.Wb * BT_FIN * 128 + 64 <= ctx->pinned_bytes;
+    SB_REQUIRE(tree || log_mod == 0, "msm: residue shards need the tree bucket reduction");
     uint32_t tree_bits = 0, tree_shift = 0;   // R = X + 2^shift * sum_{b < bits} 2^b S_b
     uint4 *d_fin = nullptr;
     if (tree) {
@@ -905,6 +916,8 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
         for (uint32_t j = 0; j < sh.Wb; j++) {
             uint8_t pt[128];
             host_bucket_combine(hp + (size_t)j * BT_FIN * 128, (int)tree_bits, (int)tree_shift, tree_shift ? BT_FIN - 1 : 0, pt);
+            // residue shard: bucket b' stands for the digit 2^log_mod * b' + res + 1, so the sum is 2^log_mod * sum (b' + 1) V_b' - (2^log_mod - res - 1) * sum V_b'
+            if (log_mod) host_residue_fixup(pt, hp + (size_t)j * BT_FIN * 128 /* slot 0: sum of all buckets */, (int)log_mod, (int)res);
             memcpy(hp + (size_t)j * 128, pt, 128);
         }
     }

@@ -283,14 +283,16 @@ def bucket_tree(grp, buckets, n_sets, B, bt_log=8):
     return out
 
 
-def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None, cta_scan_max=0, tree_log=None):
+def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=False, batch=1, w_lo=0, w_hi=None, cta_scan_max=0, tree_log=None, residue=None):
     """scalars: batch * n values (vector j = scalars[j n:(j+1) n], tables only).  Returns the list of `batch` results (tables), or the
     single result; with a window range [w_lo, w_hi) the partial sum over those windows (tables: already carrying 2^(c w))."""
     n = len(bases)
     assert len(scalars) == n * batch and (batch == 1 or tables)
     W_all = window_count(c)
     w_hi = W_all if w_hi is None else w_hi
-    B = 1 << (c - 1)
+    res, log_mod = residue if residue else (0, 0)   # residue shard (tables + tree only): digits with (|d| - 1) mod 2^log_mod == res, bucket (|d| - 1) >> log_mod
+    assert not residue or (tables and tree_log and c >= log_mod + 2)
+    B = (1 << (c - 1)) >> log_mod
     n_sets = batch if tables else (w_hi - w_lo)
     nb = n_sets * B
     if tables:   # tables[w * n + i] = 2^(c w) * P_i
@@ -307,7 +309,10 @@ def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=Fals
 
     def key_val(gi, w, d):
         piece, i = divmod(gi, n)
-        key = (piece * B if tables else (w - w_lo) * B) + abs(d) - 1
+        dm = abs(d) - 1
+        if (dm & ((1 << log_mod) - 1)) != res:
+            return None, None
+        key = (piece * B if tables else (w - w_lo) * B) + (dm >> log_mod)
         val = (w * n + i if tables else i) | ((1 << 31) if d < 0 else 0)
         return key, val
 
@@ -315,7 +320,7 @@ def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=Fals
     for gi in range(n * batch):
         for w in range(w_lo, w_hi):
             d = digs[gi][w]
-            if d:
+            if d and key_val(gi, w, d)[0] is not None:
                 counts[key_val(gi, w, d)[0]] += 1
     offsets, run = [], 0
     for x in counts:
@@ -330,6 +335,8 @@ def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=Fals
             d = digs[gi][w]
             if d:
                 k, v = key_val(gi, w, d)
+                if k is None:
+                    continue
                 svals[cursor[k]] = v
                 cursor[k] += 1
     buckets = [grp.zero()] * nb
@@ -341,6 +348,21 @@ def msm(grp, scalars, bases, c, L1=8, LK=4, final_max=16, seg_log=2, tables=Fals
             keys, pts = reduce_level(grp, keys, pts, LK, buckets)
     final_level(grp, keys, pts, buckets)
     wins = bucket_tree(grp, buckets, n_sets, B, tree_log) if tree_log else bucket_hierarchy(grp, buckets, n_sets, B, seg_log)
+    if log_mod:   # host_residue_fixup: true weight of bucket b' is 2^log_mod b' + res + 1
+        fixed = []
+        for j in range(n_sets):
+            total = grp.zero()
+            for b in range(B):
+                total = grp.add(total, buckets[j * B + b])
+            r = wins[j]
+            for _ in range(log_mod):
+                r = grp.dbl(r)
+            k = (1 << log_mod) - res - 1
+            m = grp.zero()
+            for _ in range(k):
+                m = grp.add(m, total)
+            fixed.append(grp.add(r, grp.neg(m)))
+        wins = fixed
     if tables:
         return wins                           # one (partial) commitment per scalar vector
     if w_hi - w_lo != W_all:

@@ -151,6 +151,11 @@ def test_msm_model_tables_batches_and_window_shards():
         assert msm_model.msm(g, sc, bs, c, tables=True, batch=batch, **kw) == exp, (trial, "batch")
         W = msm_model.window_count(c)
         world = rnd.choice([2, 4, 8])
+        lg = world.bit_length() - 1
+        if c >= lg + 2:   # bucket-residue shards (the multi-GPU split of table MSMs): partial sums over the residues add up
+            kw_t = dict(kw, tree_log=kw["tree_log"] or 2)
+            parts = [msm_model.msm(g, sc, bs, c, tables=True, batch=batch, residue=(r, lg), **kw_t) for r in range(world)]
+            assert [sum(p[j] for p in parts) % B.R for j in range(batch)] == exp, (trial, "residue shards")
         if W >= world:
             parts = [msm_model.msm(g, sc, bs, c, tables=True, batch=batch, w_lo=r * W // world, w_hi=(r + 1) * W // world, **kw) for r in range(world)]
             assert [sum(p[j] for p in parts) % B.R for j in range(batch)] == exp, (trial, "window shards, tables")

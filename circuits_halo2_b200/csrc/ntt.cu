@@ -249,8 +249,12 @@ void ntt_make_plan(uint32_t log_n, uint32_t tile_log, uint32_t max_passes_hint, 
 }
 
 static uint32_t pick_tile_log(const sb_ctx *ctx, uint32_t log_n) {
-    if (ctx->tune.ntt_tile == 11 || ctx->tune.ntt_tile == 12) return (uint32_t)ctx->tune.ntt_tile;
+    if (ctx->tune.ntt_tile >= 9 && ctx->tune.ntt_tile <= 12) return (uint32_t)ctx->tune.ntt_tile;
     if (log_n == 12) return 12;              // one 4096-element tile instead of two passes
+    if (log_n == 11) return 11;
+    // up to 2^20 two passes fit 2^10-element tiles: 128-thread CTAs, four per SM instead of two -- barriers and load phases of one tile hide under
+    // three others (2^20: 0.265 vs 0.279 ms, 2^16: 0.054 vs 0.071 ms; profiles/r02v_ntt_tile_sweep.txt)
+    if (log_n <= 20) return 10;
     return (log_n == 23 || log_n == 24) ? 12 : 11;  // two passes up to 2^24
 }
 

@@ -248,7 +248,7 @@ def _run_device_ntt_on_host(lib, log_n, tile, min_passes, full_tw, seed=0, scale
     return bool((got[:no] == ref[:no]).all() and (got[no:].view(np.uint8) == 0xAB).all()), worst
 
 
-@pytest.mark.parametrize("tile", [11, 12])
+@pytest.mark.parametrize("tile", [10, 11, 12])
 def test_device_ntt_tile_code_on_host_all_plans(ntt_harness, tile):
     """single pass (2^tile), two passes and three passes, full inter-pass twiddle tables and the two-level fallback; every shared-memory
     access pattern (exchanges, twiddle reads, the last pass' transposition) at most 2-way bank conflicted."""

@@ -27,7 +27,7 @@ for ln in sizes:
     a0[:, 3] &= (1 << 61) - 1
     w = fields.fr_to_mont(fields.omega(ln))
     ref = None
-    for tile in (11, 12):
+    for tile in [int(t) for t in os.environ.get("SWEEP_TILES", "11,12").split(",")]:
         for passes in (0, 3):
             for tw_mb in (1024, 0):
                 os.environ["SB_NTT_TILE"], os.environ["SB_NTT_PASSES"], os.environ["SB_NTT_TW_MB"] = str(tile), str(passes), str(tw_mb)

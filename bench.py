@@ -455,10 +455,14 @@ def main():
         hrows = ctypes.c_uint64()
         L.sb_last_h_rows(ctx.handle, ctypes.byref(hrows))   # rows of the quotient's cosets this rank evaluated: (j - 1) = 5 cosets x n on one GPU
         h_rate = hrows.value * int(hprog[1]) / (hms.value * 1e-3) / 1e9 if hms.value else None
+        d2h = ctypes.c_uint64()
+        L.sb_last_proof_d2h(ctx.handle, ctypes.byref(d2h))  # commitments: 18 XYZZ records per scalar vector, folded on the host; + 36 evaluations + the proof's tail
+        hjit = ctypes.c_int32()
+        L.sb_last_h_jit(ctx.handle, ctypes.byref(hjit))     # 1: the NVRTC-specialised kernel ran, 0: the interpreter
         l1_rate = dig.value * 10 * 136 / (mm[1] * 1e-3) / 1e12 if mm[1] else None
         rec = {"k": pk_k, "circuit": circuit_name(pk_k), "n_gpus": world, "ms_per_proof": ms_res, "e2e_ms_per_proof": ms_dense, "e2e_sparse_witness_ms_per_proof": ms_sparse,
                "h2d_bytes_per_proof": 3 * nrow * 32 + len(insts) * 32, "h2d_bytes_per_proof_sparse": int(cells.nbytes + vals.nbytes) + len(insts) * 32,
-               "d2h_bytes_per_proof": int(sets.value) * 128 + 36 * 32, "proof_bytes": len(proof), "launches_per_proof": int(launches),
+               "d2h_bytes_per_proof": int(d2h.value) + 36 * 32 + 64, "proof_bytes": len(proof), "launches_per_proof": int(launches),
                "setup_srs_s": t_srs, "keygen_pk_s": t_pk, "stages_ms": {nm_: round(float(stg[i]), 3) for i, nm_ in enumerate(STAGES)},
                "sharded_equals_single_gpu": (single == proof) if single is not None else None,
                "msm": {"launch_sets": int(sets.value), "level1_additions": int(dig.value),
@@ -466,7 +470,9 @@ def main():
                        "roofline": {"kernel": "msm_reduce_first_kernel (level-1 bucket accumulation, all commitments of one proof)", "bound": "imad", "achieved": l1_rate,
                                     "peak": imadw_peak, "unit": "T wide-IMAD/s", "frac": l1_rate / imadw_peak if l1_rate else None, "share_of_proof": mm[1] / ms_res}},
                "evaluate_h": {"ms": hms.value, "rows": int(hrows.value), "instructions": int(hprog[0]), "field_mul": int(hprog[1]), "field_addsub": int(hprog[2]), "live_slots": int(hprog[3]),
-                              "roofline": {"kernel": "expr_eval_kernel (fused quotient numerator)", "bound": "imad (field products)", "achieved": h_rate, "peak": fmul_peak,
+                              "jit": bool(hjit.value),
+                              "roofline": {"kernel": "sb_h_jit (NVRTC-generated straight-line quotient numerator)" if hjit.value else "expr_eval_kernel (interpreted quotient numerator)",
+                                           "bound": "imad (field products)", "achieved": h_rate, "peak": fmul_peak,
                                            "unit": "G field-mul/s", "frac": h_rate / fmul_peak if h_rate else None, "share_of_proof": hms.value / ms_res}},
                "_proof": proof, "_fixed_comms": fcom, "_sigma_comms": scom}
         records.append(rec)
@@ -637,7 +643,7 @@ def main():
             "config": {"workload": WORKLOAD, "k": HEADLINE_K, "rows": 1 << HEADLINE_K, "quotient_rows": 5 << HEADLINE_K, "advice": 3, "fixed": 11, "permutation_columns": 6,
                        "lookups": 1, "constraint_degree": 6, "srs": "unsafe synthetic SRS, tau = 0x5A110000 + k (no k=20 ptau in the reference tree)", "rng": "ChaCha20 seed_from_u64(42)",
                        "exchange": None if world == 1 else ("torch.distributed / NCCL callbacks" if os.environ.get("SB_BENCH_COMM") == "nccl" else "sb_comm_shm: shared-memory mailbox + CUDA IPC peer copies over NVLink"),
-                       "parallelism": "single GPU" if world == 1 else f"one proof sharded over {world} GPUs: commitments by window, coset NTTs / evaluate_h / quotient iNTTs by coset (5 cosets)",
+                       "parallelism": "single GPU" if world == 1 else f"one proof sharded over {world} GPUs: commitments by bucket residue (by window when the rank count is not a power of two), coset NTTs / evaluate_h / quotient iNTTs by coset (5 cosets), SHPLONK's evaluation-domain vectors by row range, evaluations by polynomial",
                        "l2": "working set of a proof (key 5.4 GiB + per-proof columns) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": head["e2e_ms_per_proof"], "unit": UNIT, "ms_per_step": head["e2e_ms_per_proof"], "h2d_bytes_per_step": head["h2d_bytes_per_proof"],
                     "d2h_bytes_per_step": head["d2h_bytes_per_proof"],

@@ -122,6 +122,7 @@ struct sb_ctx {
     float acc_msm_ms[5] = {0, 0, 0, 0, 0};
     uint64_t acc_msm_digits = 0;
     uint32_t acc_msm_sets = 0;
+    uint64_t acc_msm_d2h = 0;                      // bytes the commitments of the last proof copied back (bucket-tree records, digit counters)
     // device time of every NTT pass kernel since the last reset is NOT kept (it would need an event pair per pass); bench.py's ncu launch list has it
     // evaluate_h of the last create_proof: device time and program shape (instructions, products, add/sub, live slots)
     cudaEvent_t h_ev[2] = {nullptr, nullptr};

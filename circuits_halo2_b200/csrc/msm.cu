@@ -909,6 +909,7 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
     for (int e = 0; e < 5; e++) ctx->acc_msm_ms[e] += ctx->msm_phase_ms[e];   // running totals since sb_perf_reset (one proof = several launch sets)
     ctx->acc_msm_digits += *h_total;
     ctx->acc_msm_sets++;
+    ctx->acc_msm_d2h += (tree ? (uint64_t)sh.Wb * BT_FIN * 128 : (uint64_t)sh.Wb * 128) + 4;
     ctx->msm_last_shape[0] = sh.c; ctx->msm_last_shape[1] = sh.W; ctx->msm_last_shape[2] = sh.L1; ctx->msm_last_shape[3] = sh.seg_log;
     if (tree) {   // per set: X + 2^shift * sum_b 2^b S_b, written back over the head of the pinned buffer as one XYZZ point per set (set j's record starts
                   // at j * BT_FIN * 128 >= j * 128, so the compaction never overtakes its input)

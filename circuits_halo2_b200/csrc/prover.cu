@@ -1045,6 +1045,7 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
     for (int i = 0; i < 5; i++) ctx->acc_msm_ms[i] = 0;
     ctx->acc_msm_digits = 0;
     ctx->acc_msm_sets = 0;
+    ctx->acc_msm_d2h = 0;
     // Side stream: coeff_to_extended of the per-proof polynomials depends on no later challenge, so it is enqueued as soon as a
     // polynomial exists and runs under the latency-bound tails of the commitments on the main stream; joined before evaluate_h.
     const bool use_side = ctx->side_stream && st == ctx->stream && !ctx->tune.no_side_stream;
@@ -2188,6 +2189,11 @@ int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digi
     for (int i = 0; i < 5; i++) out_ms[i] = ctx->acc_msm_ms[i];
     if (out_digits) *out_digits = ctx->acc_msm_digits;
     if (out_launch_sets) *out_launch_sets = ctx->acc_msm_sets;
+    return SB_OK;
+}
+int32_t sb_last_proof_d2h(const sb_ctx *ctx, uint64_t *out_bytes) {
+    if (!ctx || !out_bytes) return SB_ERR_ARG;
+    *out_bytes = ctx->acc_msm_d2h;
     return SB_OK;
 }
 int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]) {

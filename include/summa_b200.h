@@ -206,6 +206,8 @@ int32_t sb_last_proof_stages(const sb_ctx *ctx, float out_ms[12]);
 /* the commitments (MSM launch sets) of the last create_proof on this context: summed device times of the phases listed at sb_msm_phase_times,
  * the number of signed digits accumulated (= level-1 mixed additions: sum over launch sets of windows x points x vectors) and of launch sets */
 int32_t sb_last_proof_msm(const sb_ctx *ctx, float out_ms[5], uint64_t *out_digits, uint32_t *out_launch_sets);
+/* device -> host bytes of the last proof's commitments (per commitment: the bucket reduction's 18 XYZZ records of 128 B, folded on the host) */
+int32_t sb_last_proof_d2h(const sb_ctx *ctx, uint64_t *out_bytes);
 /* ---- halo2_proofs::plonk::evaluation::Evaluator::evaluate_h as a standalone entry (the finer-grained Cargo patch: the body of evaluate_h) ----
  * The quotient NUMERATOR sum_i y^(T-1-i) term_i of the constraint system `cs_json` (gate polynomials, then the permutation argument's terms, then
  * every lookup's terms: SURVEY A.8) over caller-supplied columns, 2^log_rows values each on one common domain, in this order:

@@ -84,6 +84,7 @@ void ctx_read_env(sb_ctx *ctx) {
     t.no_jit = getb("SB_NO_JIT");
     t.no_binv2 = getb("SB_NO_BINV2");
     t.shard_msm_by_window = getb("SB_SHARD_MSM_BY_WINDOW");
+    t.shard_msm_by_residue = getb("SB_SHARD_MSM_BY_RESIDUE");
     t.no_shplonk_shard = getb("SB_NO_SHPLONK_SHARD");
     t.no_shplonk_lagrange = getb("SB_NO_SHPLONK_LAGRANGE");
     t.msm_no_bucket_tree = getb("SB_MSM_NO_BUCKET_TREE");

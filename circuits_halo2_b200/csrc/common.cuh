@@ -73,7 +73,8 @@ struct Tuning {
     bool msm_no_bucket_tree = false; // SB_MSM_NO_BUCKET_TREE: bucket reduction by the running-sum hierarchy instead of the tree kernels
     bool no_shplonk_lagrange = false; // SB_NO_SHPLONK_LAGRANGE: SHPLONK through the division coset (8 transforms) instead of the evaluation domain (1)
     bool no_shplonk_shard = false;   // SB_NO_SHPLONK_SHARD: sharded proofs compute SHPLONK's evaluation-domain vectors in full on every rank
-    bool shard_msm_by_window = false; // SB_SHARD_MSM_BY_WINDOW: sharded commitments split by signed-digit window instead of by bucket residue
+    bool shard_msm_by_window = false; // SB_SHARD_MSM_BY_WINDOW / SB_SHARD_MSM_BY_RESIDUE: force the split of sharded table commitments (default: by measured rule)
+    bool shard_msm_by_residue = false;
     bool no_inst_direct = false;     // SB_NO_INST_DIRECT: instance column to the cosets through transforms even when it holds few values
     bool no_binv2 = false;           // SB_NO_BINV2: batch inversion of long vectors through the single-level kernel
     bool no_jit = false;             // SB_NO_JIT: evaluate_h through the interpreter instead of the NVRTC-specialised kernel

@@ -901,16 +901,21 @@ Program h_program_for(const sb_pk *pk, const std::vector<std::pair<int, int>> &s
 //   * 2^(ext_k-k) / world cosets of the extended domain: extended index i = (i >> rs_log) * 2^rs_log + j lies on the coset
 //     zeta * ext_omega^j * H, rotations move inside a coset, so coset NTTs, evaluate_h and the division by t(X) need no exchange;
 //     the quotient's coset-major values are all-gathered once (device buffer) before the extended inverse NTT.
-// Table bases on a power-of-two number of ranks: shard by BUCKET RESIDUE instead (rank r keeps the digits whose bucket index is r mod world): every
-// rank still walks all scalars, but accumulation, sort AND the bucket reduction divide by world exactly (15 windows do not divide by 8; the bucket
-// reduction of a window shard is as large as the single-GPU one).  log2(world), or 0 for the window split.
-static uint32_t msm_residue_log(sb_ctx *ctx, const sb_comm *comm, const MsmTables *tabs) {
+// Table bases on a power-of-two number of ranks can also be sharded by BUCKET RESIDUE (rank r keeps the digits whose bucket index is r mod world):
+// accumulation, sort atomics AND the bucket reduction divide by world exactly (15 windows do not divide by 8, and the bucket reduction of a window
+// shard is as large as the single-GPU one), but every rank recodes every window of every scalar.  Measured (profiles/r02u, r02s, r02y): the residue
+// split wins where the bucket sets are large (c >= 20, i.e. k >= 23: 8 GPUs 134.5 -> 117.6 ms, 2 GPUs 297 -> 284 ms) and on 2 GPUs at k = 20
+// (38.8 -> 38.1 ms); at k = 20 on 8 GPUs the window split is faster (18.6 vs 19.5 ms) -- the replicated recoding outweighs a 0.2 ms bucket tree.
+// Returns log2(world) for the residue split, 0 for the window split.  SB_SHARD_MSM_BY_WINDOW / SB_SHARD_MSM_BY_RESIDUE force one.
+static uint32_t msm_residue_log(sb_ctx *ctx, const sb_comm *comm, const MsmTables *tabs, size_t n) {
     if (!comm || comm->world <= 1 || !tabs || ctx->tune.shard_msm_by_window || ctx->tune.msm_no_bucket_tree) return 0;
     const uint32_t w = (uint32_t)comm->world;
     if (w & (w - 1)) return 0;
     uint32_t lg = 0;
     while ((1u << lg) < w) lg++;
-    return tabs->c >= lg + 9 ? lg : 0;   // at least 256 buckets per rank
+    if (tabs->c < lg + 9) return 0;   // at least 256 buckets per rank
+    if (ctx->tune.shard_msm_by_residue) return lg;
+    return (tabs->c >= 20 || (w == 2 && n >= ((size_t)1 << 19))) ? lg : 0;
 }
 
 int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basis, const void *d_scalars, size_t n, uint8_t out[64], cudaStream_t st) {
@@ -929,7 +934,7 @@ int32_t msm_commit(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, int basi
         if (tabs) {
             uint8_t mine[128];
             std::vector<uint8_t> all((size_t)Wd * 128);
-            const uint32_t rl = msm_residue_log(ctx, comm, tabs);
+            const uint32_t rl = msm_residue_log(ctx, comm, tabs, n);
             if (rl) SB_TRY(msm_run_tables_batch_windows(ctx, tabs, d_scalars, n, 1, 0, (int32_t)W, mine, st, nullptr, r, rl));
             else SB_TRY(msm_run_tables(ctx, tabs, d_scalars, n, (int32_t)lo, (int32_t)hi, mine, st));
             if (comm->allgather_host(comm->user, mine, all.data(), 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
@@ -965,7 +970,7 @@ int32_t msm_commit_batch(sb_ctx *ctx, const sb_comm *comm, const sb_srs *srs, in
         // all m commitments, this rank's windows, ONE launch set and ONE exchange of m XYZZ partials per rank
         const uint32_t lo = r * tabs->W / Wd, hi = (r + 1) * tabs->W / Wd;
         std::vector<uint8_t> mine((size_t)m * 128), all((size_t)Wd * m * 128), col((size_t)Wd * 128);
-        const uint32_t rl = msm_residue_log(ctx, comm, tabs);
+        const uint32_t rl = msm_residue_log(ctx, comm, tabs, n);
         if (rl) SB_TRY(msm_run_tables_batch_windows(ctx, tabs, d_scalars, n, m, 0, (int32_t)tabs->W, mine.data(), st, nullptr, r, rl));
         else SB_TRY(msm_run_tables_batch_windows(ctx, tabs, d_scalars, n, m, (int32_t)lo, (int32_t)hi, mine.data(), st));
         if (comm->allgather_host(comm->user, mine.data(), all.data(), (size_t)m * 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
@@ -990,7 +995,7 @@ int32_t msm_commit_batch_mixed(sb_ctx *ctx, const sb_comm *comm, const sb_srs *s
     for (uint32_t j = 0; j < m; j++) off[j] = basis_of[j] ? (uint32_t)((uint64_t)t0->W * t0->stride) : 0u;
     const uint32_t lo = r * t0->W / Wd, hi = (r + 1) * t0->W / Wd;
     std::vector<uint8_t> mine((size_t)m * 128), all((size_t)Wd * m * 128), col((size_t)Wd * 128);
-    const uint32_t rl = msm_residue_log(ctx, comm, t0);
+    const uint32_t rl = msm_residue_log(ctx, comm, t0, n);
     if (rl) SB_TRY(msm_run_tables_batch_windows(ctx, t0, d_scalars, n, m, 0, (int32_t)t0->W, mine.data(), st, off, r, rl));
     else SB_TRY(msm_run_tables_batch_windows(ctx, t0, d_scalars, n, m, (int32_t)lo, (int32_t)hi, mine.data(), st, off));
     if (comm->allgather_host(comm->user, mine.data(), all.data(), (size_t)m * 128) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }

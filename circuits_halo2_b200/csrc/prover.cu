@@ -1159,10 +1159,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(upload_frs(ctx, (uint8_t *)adv[c] + usable * 32, blind, st));
     }
     for (int c = 0; c < A; c++) (void)rng.next_fr();
+    // The commitment below is over the Lagrange basis, so the coefficient forms (needed by the coset transforms and the evaluations only) are
+    // made on the side stream too: in a sharded proof the commitment is latency-bound and these replicated transforms hide under it.
+    SB_TRY(side_after_main());  // advice coefficient forms, advice / instance cosets on the side stream, under the commitment below
     if (dist_ntt) {
         for (int c = 0; c < A; c++) {
-            SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st));
-            SB_TRY(l2c_repl(adv_poly[c], st));
+            SB_CUDA_TRY(cudaMemcpyAsync(adv_poly[c], adv[c], n * 32, cudaMemcpyDeviceToDevice, st2));
+            SB_TRY(l2c_repl(adv_poly[c], st2));
         }
     } else {   // lagrange_to_coeff of the A advice columns: one batched out-of-place inverse transform (n^-1 folded in)
         NttFuse f;
@@ -1170,9 +1173,8 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         f.scale = d->ifft_divisor;
         f.batch = (uint32_t)A;
         f.src_stride = n; f.dst_stride = n;
-        SB_TRY(ntt_run_fused(ctx, adv[0], adv_poly[0], (const uint8_t *)d->omega_inv.v, pk->k, &f, st));
+        SB_TRY(ntt_run_fused(ctx, adv[0], adv_poly[0], (const uint8_t *)d->omega_inv.v, pk->k, &f, st2));
     }
-    SB_TRY(side_after_main());  // advice / instance cosets on the side stream, under the commitment below
     for (int c = 0; c < A; c++) SB_TRY(side_cosets((size_t)c, adv_poly[c]));
     if (inst_direct) {
         for (uint32_t jl = 0; jl < co_per; jl++)
@@ -1248,13 +1250,13 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         SB_TRY(upload_frs(ctx, (uint8_t *)L.p_in + usable * 32, blind, st));
         for (Fr &x : blind) x = rng.next_fr();
         SB_TRY(upload_frs(ctx, (uint8_t *)L.p_tab + usable * 32, blind, st));
-        SB_CUDA_TRY(cudaMemcpyAsync(L.in_poly, L.p_in, n * 32, cudaMemcpyDeviceToDevice, st));
-        SB_TRY(l2c_repl(L.in_poly, st));
+        SB_TRY(side_after_main());   // coefficient and coset forms on the side stream, under the (Lagrange-basis) commitment below
+        SB_CUDA_TRY(cudaMemcpyAsync(L.in_poly, L.p_in, n * 32, cudaMemcpyDeviceToDevice, st2));
+        SB_TRY(l2c_repl(L.in_poly, st2));
         (void)rng.next_fr();
-        SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st));
-        SB_TRY(l2c_repl(L.tab_poly, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(L.tab_poly, L.p_tab, n * 32, cudaMemcpyDeviceToDevice, st2));
+        SB_TRY(l2c_repl(L.tab_poly, st2));
         (void)rng.next_fr();
-        SB_TRY(side_after_main());
         SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 1, L.in_poly));
         SB_TRY(side_cosets((size_t)A + 1 + n_sets_all + 3 * li + 2, L.tab_poly));
         uint8_t pin_tab[128];

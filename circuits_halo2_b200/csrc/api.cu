@@ -83,6 +83,8 @@ void ctx_read_env(sb_ctx *ctx) {
     t.no_hprog_cache = getb("SB_NO_HPROG_CACHE");
     t.no_jit = getb("SB_NO_JIT");
     t.no_binv2 = getb("SB_NO_BINV2");
+    t.no_grand_shard = getb("SB_NO_GRAND_SHARD");
+    t.grand_shard = getb("SB_GRAND_SHARD");
     t.shard_msm_by_window = getb("SB_SHARD_MSM_BY_WINDOW");
     t.shard_msm_by_residue = getb("SB_SHARD_MSM_BY_RESIDUE");
     t.no_shplonk_shard = getb("SB_NO_SHPLONK_SHARD");

@@ -72,6 +72,8 @@ struct Tuning {
     bool no_hprog_cache = false;     // SB_NO_HPROG_CACHE
     bool msm_no_bucket_tree = false; // SB_MSM_NO_BUCKET_TREE: bucket reduction by the running-sum hierarchy instead of the tree kernels
     bool no_shplonk_lagrange = false; // SB_NO_SHPLONK_LAGRANGE: SHPLONK through the division coset (8 transforms) instead of the evaluation domain (1)
+    bool no_grand_shard = false;     // SB_NO_GRAND_SHARD / SB_GRAND_SHARD: never / always shard the grand products of a sharded proof by rows (default: by measured rule)
+    bool grand_shard = false;
     bool no_shplonk_shard = false;   // SB_NO_SHPLONK_SHARD: sharded proofs compute SHPLONK's evaluation-domain vectors in full on every rank
     bool shard_msm_by_window = false; // SB_SHARD_MSM_BY_WINDOW / SB_SHARD_MSM_BY_RESIDUE: force the split of sharded table commitments (default: by measured rule)
     bool shard_msm_by_residue = false;

@@ -1285,7 +1285,24 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
         Fr delta_pow = hfr::ONE;
         const Fr DELTA = fr_from_hex("0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
         // numerators and denominators of every grand product side by side, then ONE batch inversion and ONE product pass for all of them
+        // Sharded proof: the ratios, their inversion and the running products are computed for rows [r n / world, (r + 1) n / world) only (the
+        // expressions read every column at rotation 0); the slices' total products meet on the host, every rank scales its slice by the product
+        // of the slices before it, and one in-place all-gather per Z column replicates the result for the (window / residue sharded) commitment.
+        uint32_t gp_log = 0;
+        while (world > 1 && (1u << gp_log) < world) gp_log++;
+        // (one more host exchange and an all-gather per column.  Measured: 2 GPUs k = 23 284.8 -> 281.5 ms but k = 20 37.6 -> 37.8; 8 GPUs k = 23 117.6 ->
+        // 111.6, k = 20 18.18 -> 18.03, k = 17 6.9 -> 7.3: on from k = 22, and from k = 20 on four or more ranks)
+        const bool gp_rows = world > 1 && (1u << gp_log) == world && comm->allgather_dev && pk->k >= gp_log + 12 && !ctx->tune.no_grand_shard &&
+                             (pk->k >= 22 || (world >= 4 && pk->k >= 20) || ctx->tune.grand_shard);
+        const size_t gp_cnt = gp_rows ? n >> gp_log : n, gp_off = gp_rows ? gp_cnt * rank : 0;
+        std::vector<const void *> lcols_sl;
         auto ratio_terms = [&](ExprP den, ExprP num, int z) -> int32_t {
+            if (gp_rows) {
+                lcols_sl.resize(lcols.size());
+                for (size_t c = 0; c < lcols.size(); c++) lcols_sl[c] = lcols[c] ? (const uint8_t *)lcols[c] + gp_off * 32 : nullptr;
+                SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols_sl, pk->k - gp_log, 0, d_den + ((size_t)z * n + gp_off) * 32, st));
+                return expr_eval(ctx, compile_terms({num}, nullptr), lcols_sl, pk->k - gp_log, 0, d_num + ((size_t)z * n + gp_off) * 32, st);
+            }
             SB_TRY(expr_eval(ctx, compile_terms({den}, nullptr), lcols, pk->k, 0, d_den + (size_t)z * n * 32, st));
             return expr_eval(ctx, compile_terms({num}, nullptr), lcols, pk->k, 0, d_num + (size_t)z * n * 32, st);
         };
@@ -1313,11 +1330,44 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             ExprP num = e_mul(e_add(e_col(L_LK + 0, 0), ec(beta)), e_add(e_col(L_LK + 1, 0), ec(gamma)));
             SB_TRY(ratio_terms(den, num, n_sets + (int)li));
         }
+        std::vector<Fr> local_last(n_sets);
+        if (gp_rows) {
+            // per column: this rank's rows.  Host record per rank: n_z slice totals, then (last rank) the un-chained boundary values z_s[n - bf - 1]
+            std::vector<Fr> rec(2 * (size_t)n_z, hfr::ZERO), last_z(n_z), last_r(n_z);
+            const size_t b_row = n - (size_t)bf - 1;   // boundary row: lies in the last rank's slice (bf + 1 < n / world)
+            for (int z = 0; z < n_z; z++) {
+                uint8_t *den_sl = d_den + ((size_t)z * n + gp_off) * 32, *z_sl = d_zall + ((size_t)z * n + gp_off) * 32;
+                SB_TRY(fr_batch_invert(ctx, den_sl, gp_cnt, st));
+                SB_TRY(fp_vec_op(ctx, 0, 0, den_sl, d_num + ((size_t)z * n + gp_off) * 32, den_sl, gp_cnt, st));
+                SB_TRY(fr_running_product(ctx, den_sl, gp_cnt, fr_t::one(), z_sl, gp_cnt, st));
+                SB_CUDA_TRY(cudaMemcpyAsync(&last_z[z], z_sl + (gp_cnt - 1) * 32, 32, cudaMemcpyDeviceToHost, st));
+                SB_CUDA_TRY(cudaMemcpyAsync(&last_r[z], den_sl + (gp_cnt - 1) * 32, 32, cudaMemcpyDeviceToHost, st));
+                if (rank + 1 == world) SB_CUDA_TRY(cudaMemcpyAsync(&rec[(size_t)n_z + z], d_zall + ((size_t)z * n + b_row) * 32, 32, cudaMemcpyDeviceToHost, st));
+            }
+            SB_CUDA_TRY(sync_stream(ctx, st));
+            for (int z = 0; z < n_z; z++) rec[z] = hfr::mul(last_z[z], last_r[z]);
+            std::vector<Fr> all(2 * (size_t)n_z * world);
+            if (comm->allgather_host(comm->user, rec.data(), all.data(), rec.size() * 32) != 0) { set_last_error("sb_comm.allgather_host failed"); return SB_ERR_ARG; }
+            Fr carry = hfr::ONE;   // chains the permutation sets: set s starts from the (chained) boundary value of set s - 1
+            for (int z = 0; z < n_z; z++) {
+                Fr before = hfr::ONE, before_last = hfr::ONE;   // product of the slices before this rank / before the last rank
+                for (uint32_t q = 0; q + 1 < world; q++) {
+                    if (q < rank) before = hfr::mul(before, all[(size_t)q * 2 * n_z + z]);
+                    before_last = hfr::mul(before_last, all[(size_t)q * 2 * n_z + z]);
+                }
+                const bool perm = z < n_sets;
+                const Fr scale = perm ? hfr::mul(before, carry) : before;
+                if (!(scale == hfr::ONE)) SB_TRY(fr_scale(ctx, d_zall + ((size_t)z * n + gp_off) * 32, gp_cnt, to_dev(scale), st));
+                if (perm) {
+                    local_last[z] = hfr::mul(before_last, all[(size_t)(world - 1) * 2 * n_z + n_z + z]);   // un-chained z_s[n - bf - 1]
+                    carry = hfr::mul(carry, local_last[z]);
+                }
+            }
+        } else {
         SB_TRY(fr_batch_invert(ctx, d_den, (size_t)n_z * n, st));
         SB_TRY(fp_vec_op(ctx, 0, 0, d_den, d_num, d_den, (size_t)n_z * n, st));
         for (int z = 0; z < n_z; z++) SB_TRY(fr_running_product(ctx, d_den + (size_t)z * n * 32, n, fr_t::one(), d_zall + (size_t)z * n * 32, n, st));
         // boundary values of the un-chained permutation products, one read-back
-        std::vector<Fr> local_last(n_sets);
         for (int s = 0; s + 1 < n_sets; s++)
             SB_CUDA_TRY(cudaMemcpyAsync(&local_last[s], d_zall + ((size_t)s * n + (n - (size_t)bf - 1)) * 32, 32, cudaMemcpyDeviceToHost, st));
         if (n_sets > 1) SB_CUDA_TRY(sync_stream(ctx, st));
@@ -1326,12 +1376,18 @@ int32_t create_proof_impl(sb_ctx *ctx, const sb_pk *pk, const sb_comm *comm, con
             carry = hfr::mul(carry, local_last[s - 1]);
             SB_TRY(fr_scale(ctx, d_zall + (size_t)s * n * 32, n, to_dev(carry), st));
         }
+        }
         // blinding rows and blinds in halo2's draw order: every permutation set, then every lookup product
         for (int z = 0; z < n_z; z++) {
             std::vector<Fr> blind(bf);
             for (Fr &x : blind) x = rng.next_fr();
             SB_TRY(upload_frs(ctx, d_zall + ((size_t)z * n + (n - bf)) * 32, blind, st));
             (void)rng.next_fr();
+        }
+        if (gp_rows) {   // the blinding rows above landed in every rank's copy of the last slice; the gather brings the last rank's (identical) ones
+            SB_CUDA_TRY(sync_stream(ctx, st));
+            for (int z = 0; z < n_z; z++)
+                if (comm->allgather_dev(comm->user, d_zall + (size_t)z * n * 32, gp_cnt * 32, (void *)st) != 0) { set_last_error("sb_comm.allgather_dev failed"); return SB_ERR_ARG; }
         }
         // coefficient and coset forms of every Z on the side stream (sharded proving: coefficient form only), under the batched commitment
         SB_TRY(side_after_main());

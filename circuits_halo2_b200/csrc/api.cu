@@ -7,6 +7,9 @@
 namespace sb {
 
 void host_sum_affine(const uint8_t *pts, int n, uint8_t out_affine[64]);
+void host_fold_windows(const uint8_t *win, int n_windows, int c, uint8_t out_affine[64]);
+void host_bucket_combine(const uint8_t *fin, int n_bits, int shift, int x_slot, uint8_t out_xyzz[128]);
+void host_residue_fixup(uint8_t r_xyzz[128], const uint8_t total_xyzz[128], int log_mod, int res);
 
 static thread_local char g_err[512] = "";
 void set_last_error(const char *fmt, ...) {
@@ -761,6 +764,14 @@ int32_t sb_bench_imad_hi(sb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_
     if (!ctx || !out_ms) return SB_ERR_ARG;
     Guard g(ctx);
     return timed(ctx, out_ms, 4, blocks, threads, iters);
+}
+int32_t sb_test_msm_host_tail(const uint8_t *fin, int32_t n_bits, int32_t shift, int32_t x_slot, int32_t log_mod, int32_t res, uint8_t out_affine[64]) {
+    if (!fin || !out_affine || n_bits < 0 || n_bits > 16 || shift < 0 || x_slot < 0 || x_slot > 17 || log_mod < 0 || log_mod > 8 || res < 0 || res >= (1 << log_mod)) return SB_ERR_ARG;
+    uint8_t pt[128];
+    sb::host_bucket_combine(fin, n_bits, shift, x_slot, pt);
+    if (log_mod) sb::host_residue_fixup(pt, fin, log_mod, res);
+    sb::host_fold_windows(pt, 1, 0, out_affine);
+    return SB_OK;
 }
 int32_t sb_g1_sum_affine(const uint8_t *pts, size_t n, uint8_t out_affine[64]) {
     if (!pts || !out_affine) return SB_ERR_ARG;

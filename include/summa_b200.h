@@ -242,6 +242,10 @@ int32_t sb_test_chacha_fr(uint64_t seed_u64, uint32_t skip_bytes, uint32_t count
 int32_t sb_test_h_program(const char *cs_json, uint64_t seed, uint8_t out_program_value[32], uint8_t out_direct_value[32], uint32_t out_shape[4]);
 /* the CUDA source the NVRTC path compiles for `cs_json`'s quotient-numerator program (cap 0: size query) */
 int32_t sb_test_h_jit_source(const char *cs_json, char *out, size_t cap, size_t *out_len);
+/* Host tail of a table MSM, callable without a GPU (test hook; csrc/host_g1.cpp).  `fin`: 18 XYZZ records of 128 B as the bucket-tree kernels leave them
+ * ([0] = sum of all buckets T, [1 + b] = S_b, [17] = the plain sum of the Q vector when a running-sum level ran first); out = fin[x_slot] + 2^shift *
+ * sum_{b < n_bits} 2^b S_b, then -- for a bucket-residue shard (log_mod > 0) -- 2^log_mod * out - (2^log_mod - res - 1) * T; normalised to 64 B affine. */
+int32_t sb_test_msm_host_tail(const uint8_t *fin, int32_t n_bits, int32_t shift, int32_t x_slot, int32_t log_mod, int32_t res, uint8_t out_affine[64]);
 int32_t sb_test_host_fr(int32_t op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 
 /* ---- zk_prover::merkle_sum_tree: MerkleSumTree::from_entries / Tree::generate_proof ------------------

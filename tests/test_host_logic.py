@@ -359,3 +359,39 @@ def test_evaluate_h_generated_source_compiles_offline(tmp_path):
         assert "0 bytes spill stores" in out.stderr and "sb_h_jit" in out.stderr
         body = buf.raw[: n.value].decode()
         assert body.count("jmul(") >= 100 and "for (" not in body.split("sb_h_jit")[-1]
+
+
+def test_msm_host_tail_bucket_tree_records_and_residue_shards():
+    """host side of a table MSM (csrc/host_g1.cpp: Horner fold over the bucket tree's bit sums, the running-sum pre-level's shift, the
+    bucket-residue rescaling, normalisation by the binary-Euclid inversion), on the CPU against the oracle's group law"""
+    from circuits_halo2_b200 import _lib
+    L = _lib.lib()
+    rnd = random.Random(23)
+
+    def xyzz(p):   # affine point (or None) as a 128-byte XYZZ record, zz = zzz = 1 (identity: zeros)
+        if p is None:
+            return bytes(128)
+        one = B.fq_to_mont_bytes(1) if hasattr(B, "fq_to_mont_bytes") else ((1 << 256) % B.Q).to_bytes(32, "little")
+        return B.g1_to_mont_bytes(p) + one + one
+
+    for trial in range(12):
+        n_bits = rnd.choice([0, 3, 8, 16])
+        shift = rnd.choice([0, 0, 5])
+        log_mod = rnd.choice([0, 1, 3])
+        res = rnd.randrange(1 << log_mod)
+        x_slot = 17 if shift else 0
+        pts = [B.g1_mul(B.G1_GEN, rnd.randrange(1, B.R)) if rnd.random() < 0.85 else None for _ in range(18)]
+        fin = np.frombuffer(b"".join(xyzz(p) for p in pts), dtype=np.uint8).copy()
+        exp = None
+        for b in range(n_bits):
+            if pts[1 + b] is not None:
+                exp = B.g1_add(exp, B.g1_mul(pts[1 + b], 1 << (b + shift)))
+        exp = B.g1_add(exp, pts[x_slot])
+        if log_mod:
+            exp = B.g1_mul(exp, 1 << log_mod) if exp is not None else None
+            k = (1 << log_mod) - res - 1
+            if k and pts[0] is not None:
+                exp = B.g1_add(exp, B.g1_neg(B.g1_mul(pts[0], k)))
+        out = np.zeros(64, dtype=np.uint8)
+        assert L.sb_test_msm_host_tail(_p(fin), n_bits, shift, x_slot, log_mod, res, _p(out)) == 0
+        assert B.g1_from_mont_bytes(out.tobytes()) == exp, (trial, n_bits, shift, log_mod, res)

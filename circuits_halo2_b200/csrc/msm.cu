@@ -851,10 +851,10 @@ static int32_t msm_run_impl(sb_ctx *ctx, const void *d_bases, const void *d_scal
         uint4 *d_nodes;
         SB_TRY(scratch_get(ctx, "msm_fin", ((uint64_t)sh.Wb * BT_FIN + 8) * 128, (void **)&d_fin));
         SB_TRY(scratch_get(ctx, "msm_nodes", (2 * (uint64_t)sh.Wb * n_nodes * BT_SLOTS + 8) * 128, (void **)&d_nodes));
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {false};  // the attribute is per device: a process may drive several GPUs through several contexts
+        if (ctx->device >= 64 || !attr_set[ctx->device]) {
             SB_CUDA_TRY(cudaFuncSetAttribute(msm_bucket_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
-            attr_set = true;
+            if (ctx->device < 64) attr_set[ctx->device] = true;
         }
         const size_t smem = BT_SMEM;
         if (n_nodes == 1) {

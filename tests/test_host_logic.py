@@ -395,3 +395,53 @@ def test_msm_host_tail_bucket_tree_records_and_residue_shards():
         out = np.zeros(64, dtype=np.uint8)
         assert L.sb_test_msm_host_tail(_p(fin), n_bits, shift, x_slot, log_mod, res, _p(out)) == 0
         assert B.g1_from_mont_bytes(out.tobytes()) == exp, (trial, n_bits, shift, log_mod, res)
+
+
+def test_row_sharded_grand_products_model():
+    """control logic of the row-sharded grand products of a sharded proof (csrc/prover.cu, gp_rows), over integers mod r: every rank scans its row
+    range from 1, the slice totals and the last rank's un-chained boundary values meet in one host exchange, every rank scales its slice by the
+    product of the slices before it (and, for permutation sets, by the chained boundary values of the sets before) -- equal to the single-GPU
+    columns: running products chained from set to set at row n - bf - 1."""
+    rnd = random.Random(31)
+    R = B.R
+    for world, n, n_sets, n_lk, bf in [(2, 64, 2, 1, 5), (4, 64, 3, 0, 5), (8, 256, 1, 2, 7), (4, 128, 2, 2, 3)]:
+        n_z = n_sets + n_lk
+        ratio = [[rnd.randrange(1, R) for _ in range(n)] for _ in range(n_z)]
+        b_row = n - bf - 1
+
+        def scan(a, init=1):   # fr_running_product: z[i] = init * prod_{j < i} a[j]
+            z, cur = [], init
+            for x in a:
+                z.append(cur)
+                cur = cur * x % R
+            return z
+
+        # single GPU
+        ref = [scan(ratio[z]) for z in range(n_z)]
+        ref_unchained = [list(c) for c in ref]         # the library reads every boundary value first and scales afterwards
+        carry = 1
+        for s in range(1, n_sets):
+            carry = carry * ref_unchained[s - 1][b_row] % R
+            ref[s] = [v * carry % R for v in ref_unchained[s]]
+        # sharded
+        cnt = n // world
+        assert bf + 1 < cnt
+        local = [[scan(ratio[z][r * cnt:(r + 1) * cnt]) for z in range(n_z)] for r in range(world)]
+        rec = [[local[r][z][cnt - 1] * ratio[z][(r + 1) * cnt - 1] % R for z in range(n_z)] +
+               [local[r][z][b_row - r * cnt] if r == world - 1 else 0 for z in range(n_z)] for r in range(world)]   # the allgather_host records
+        out = [[None] * n for _ in range(n_z)]
+        for r in range(world):
+            carry = 1
+            for z in range(n_z):
+                before = before_last = 1
+                for q in range(world - 1):
+                    if q < r:
+                        before = before * rec[q][z] % R
+                    before_last = before_last * rec[q][z] % R
+                perm = z < n_sets
+                scale = before * carry % R if perm else before
+                for i in range(cnt):
+                    out[z][r * cnt + i] = local[r][z][i] * scale % R
+                if perm:
+                    carry = carry * (before_last * rec[world - 1][n_z + z] % R) % R
+        assert out == ref, (world, n, n_sets, n_lk)
